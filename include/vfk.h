@@ -1,0 +1,164 @@
+/* vfk.h -- C ABI of the B200 pileup-annotation library (libvfk.so).
+ *
+ * The reference (TRON-Bioinformatics/vafator v3.0.0) is pure Python and has no FFI; the seam
+ * this library fills is three Python call sites inside vafator/annotator.py:
+ *
+ *   collect_metrics_for_chrom(...)      vafator/pileups.py:106-159   (called at annotator.py:225-232, :56-63)
+ *     -> vfk_pileup()                   per-(variant, BAM) allele counts, depth, medians and
+ *                                       rank-sum sufficient statistics, all integers
+ *   get_rank_sum_tests(...)             vafator/rank_sum_test.py:15-26 (called at annotator.py:350, :417)
+ *   PowerCalculator.calculate_power / calculate_absolute_power
+ *                                       vafator/power.py:39-50, :116-131 (annotator.py:325-333, :394-400)
+ *     -> vfk_epilogue()                 FP64 z / p / pu / pw / k from those integers
+ *   vfk_annotate_host() runs both with HOST buffers (pinned or pageable), copies included.
+ *
+ * Conventions: every function returns 0 (VFK_OK) or a negative VFK_E* code and never throws or
+ * aborts; vfk_last_error() gives the thread-local message.  All buffers are caller owned; the
+ * library keeps no reference to them after the stream work it enqueued has completed.  Calls
+ * are asynchronous with respect to the host until vfk_sync() (except vfk_annotate_host, which
+ * returns after its results are in host memory).  `stream` is a cudaStream_t passed as void*
+ * (NULL = the handle's own stream).  One handle per device; different handles may be driven
+ * from different host threads.
+ */
+#ifndef VFK_H
+#define VFK_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VFK_VERSION 100 /* 0.1.0 */
+
+enum {
+    VFK_OK = 0,
+    VFK_EINVAL = -1,       /* bad argument */
+    VFK_ECUDA = -2,        /* CUDA runtime error (message in vfk_last_error) */
+    VFK_ENOMEM = -3,
+    VFK_EUNSUPPORTED = -4, /* e.g. reads longer than VFK_MAX_READ_LEN */
+    VFK_ENODEVICE = -5
+};
+
+#define VFK_MAX_READ_LEN 4095 /* longest l_qseq the read-position histograms cover */
+#define VFK_NO_MATE 0xFFFFFFFFu
+#define VFK_CODE_NONE 0xFFu
+
+/* ---- read batch, HBM layout (DESIGN.md "Data layout") -------------------------------------
+ * Reads are coordinate sorted (BAM order); unplaced reads are not part of the batch.          */
+typedef struct {
+    int32_t pos;   /* 0-based leftmost reference position                                      */
+    uint32_t span; /* reference bases consumed by the CIGAR (M,D,N,=,X); end = pos + span       */
+    uint32_t fmk;  /* flag (bits 0-15) | mapq << 16 | shape << 24;
+                      shape 0: the CIGAR is one M/=/X op (qpos = column - pos, l_qseq = span),
+                      shape 1: general, see the cold record                                    */
+    uint32_t pay;  /* payload offset, in 32-byte sectors                                       */
+} vfk_read_hot;
+
+typedef struct {
+    uint32_t cigar_off; /* index into cigar[] (BAM encoding len<<4|op)                         */
+    uint32_t n_cigar;
+    uint32_t l_qseq;
+    uint32_t reserved;
+} vfk_read_cold;
+
+/* payload: read i owns ceil(l_qseq/21) sectors from hot.pay; sector s holds query positions
+ * 21s .. 21s+20: bytes 0-20 base qualities, bytes 21-31 the 4-bit base codes (position 21s+r in
+ * byte 21 + r/2, high nibble when r is even).  One (read, column) lookup = one 32-byte sector. */
+typedef struct {
+    int64_t n_reads;
+    int32_t n_contigs;
+    int32_t max_l_qseq;
+    const int64_t *contig_off;    /* [n_contigs+1] reads of contig t are [off[t], off[t+1])      */
+    const vfk_read_hot *hot;      /* [n_reads]                                                  */
+    const vfk_read_cold *cold;    /* [n_reads]                                                  */
+    const uint32_t *mate;         /* [n_reads] overlap partner | tie_break << 31, VFK_NO_MATE   */
+    const int32_t *starts;        /* [n_reads] == hot[i].pos, dense for the position search     */
+    const int32_t *pmax_end;      /* [n_reads] running max of pos+span within the contig        */
+    const uint32_t *cigar;        /* [n_cigar_words]                                            */
+    const uint8_t *payload;       /* [n_sectors * 32], 32-byte aligned                          */
+    int64_t n_cigar_words;
+    int64_t n_sectors;
+} vfk_read_batch;
+
+/* ---- variant units: one per (VCF record, ALT allele) that needs a column evaluation --------- */
+#define VFK_KIND_SNV 0u
+#define VFK_KIND_INS 1u
+#define VFK_KIND_DEL 2u
+typedef struct {
+    int64_t n_units;
+    const int32_t *tid;      /* contig index in the read batch                                  */
+    const int32_t *pos;      /* 0-based column (POS - 1)                                        */
+    const uint32_t *meta;    /* kind | ref_code << 8 | alt_code << 16 (BAM 4-bit code or VFK_CODE_NONE) */
+    const int32_t *length;   /* inserted / deleted length (len(ALT0)-len(REF) / len(REF)-len(ALT0)) */
+    const uint32_t *seq_off; /* insertions: offset of ALT0[1:] in ins_seq                       */
+    const uint8_t *ins_seq;  /* one 4-bit code per byte, VFK_CODE_NONE = can never match        */
+    const int32_t *stop;     /* pysam fetch stop of the unit's chromosome group = its last POS
+                                (vafator/pileups.py:137-138); may be NULL (= no bound)          */
+    int64_t n_ins_seq;
+} vfk_variant_batch;
+
+/* ---- parameters (vafator/pileups.py:71-80 keyword arguments + pysam 0.21.0 defaults) -------- */
+typedef struct {
+    int32_t min_mapq;          /* --mapping-quality   (CLI default 1, Annotator default 0)       */
+    int32_t min_baseq;         /* --base-call-quality (CLI default 30, Annotator default 29)     */
+    uint32_t flag_filter;      /* 0x704: UNMAP|SECONDARY|QCFAIL|DUP                              */
+    int32_t ignore_orphans;    /* 1 */
+    int32_t ignore_overlaps;   /* 1 */
+    int32_t include_ambiguous; /* 1 unless --exclude-ambiguous-bases                             */
+} vfk_params;
+
+/* ---- pileup output: integers only ---------------------------------------------------------- */
+#define VFK_ST_KIND_MASK 0x3u
+#define VFK_ST_DEFERRED 0x10u  /* column deeper than the warp path handles; done by the block path */
+#define VFK_ST_READLEN 0x20u   /* a read position fell outside the histogram: result invalid      */
+typedef struct {
+    int32_t dp;         /* depth as vafator reports it (pileups.py:224-227, :264, :330)          */
+    int32_t n_amb;      /* SNV: IUPAC-ambiguous bases in the column (annotator.py:386)           */
+    int32_t ac_ref;     /* SNV: reads showing REF; indel: reads with no indel here (REF support)  */
+    int32_t ac_alt;     /* reads supporting this unit's ALT                                       */
+    int32_t med2[3][2]; /* [mq,bq,pos][ref,alt]: twice the median, -1 when the list is empty      */
+    uint32_t status;
+    uint32_t n_cand;    /* candidate reads inspected                                              */
+    uint64_t s2[3];     /* [mq,bq,pos]: twice the sum of the ALT mid-ranks in the pooled ranking   */
+    uint64_t reserved;
+} vfk_counts; /* 80 bytes */
+
+/* ---- epilogue output: FP64, unrounded ------------------------------------------------------ */
+typedef struct {
+    double z[3];  /* [mq,bq,pos] rank-sum statistic as scipy.stats.ranksums(alt, ref); NaN if a side is empty */
+    double p[3];  /* two-sided p-value */
+    double pu;    /* binom.cdf(ac_alt, dp, eaf)          vafator/power.py:39-50   */
+    double pw;    /* Carter-2012 power                   vafator/power.py:116-131 */
+    int32_t k;    /* minimum supporting reads            vafator/power.py:106-114 */
+    int32_t pad;
+} vfk_stats; /* 72 bytes */
+
+typedef struct vfk_handle vfk_handle;
+
+int vfk_version(void);
+const char *vfk_last_error(void);
+int vfk_create(int device, vfk_handle **out);
+int vfk_destroy(vfk_handle *h);
+int vfk_sync(vfk_handle *h);
+
+/* all pointers inside the batches and `out` are DEVICE pointers */
+int vfk_pileup(vfk_handle *h, const vfk_read_batch *reads, const vfk_variant_batch *units,
+               const vfk_params *params, vfk_counts *out, void *stream);
+
+/* counts / eaf / out are DEVICE pointers; eaf[u] = expected VAF of unit u (vafator/power.py:52-82) */
+int vfk_epilogue(vfk_handle *h, int64_t n_units, const vfk_counts *counts, const double *eaf,
+                 double fpr, double error_rate, vfk_stats *out, void *stream);
+
+/* Same path with HOST buffers: copies the batches to the device (staging memory owned by the
+ * handle, grown on demand), runs both kernels and copies counts/stats back before returning.   */
+int vfk_annotate_host(vfk_handle *h, const vfk_read_batch *reads, const vfk_variant_batch *units,
+                      const vfk_params *params, const double *eaf, double fpr, double error_rate,
+                      vfk_counts *counts_out, vfk_stats *stats_out);
+
+/* Number of kernel launches issued through this handle since it was created. */
+int64_t vfk_launch_count(vfk_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,106 @@
+"""CPU-side checks of the product's host code: HBM packing, mate linking, C-ABI surface."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import c_oracle
+from vafator_b200 import build, device
+from vafator_b200.batch import ReadBatch, build_units, SEQ_CHARS, CODE_NONE
+
+SCENARIOS = H.golden_scenarios()
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_quality_scaling_is_integer_exact():
+    """htslib stores (uint8_t)(0.8 * q); the kernel uses (4*q)/5 -- identical for every byte value."""
+    for q in range(256):
+        assert int(0.8 * q) == (4 * q) // 5
+
+
+@pytest.mark.parametrize("path", SCENARIOS, ids=[os.path.basename(p) for p in SCENARIOS])
+def test_pack_layout_round_trips(path):
+    sc = H.load_scenario(path)
+    for recs, batch in zip(sc["bams"], H.scenario_batches(sc)):
+        pk = device.pack_reads(batch, device.make_params())
+        assert pk.n_reads == len(recs)
+        assert pk.contig_off[0] == 0 and pk.contig_off[-1] == len(recs)
+        assert np.all(np.diff(pk.starts.astype(np.int64))[batch.tid[1:] == batch.tid[:-1]] >= 0)
+        for i, r in enumerate(recs):
+            assert pk.hot["pos"][i] == r["pos"]
+            assert (pk.hot["fmk"][i] & 0xFFFF) == r["flag"] and ((pk.hot["fmk"][i] >> 16) & 0xFF) == r["mapq"]
+            lq = len(r["seq"])
+            base = int(pk.hot["pay"][i]) * 32
+            for q in range(lq):
+                s, rr = divmod(q, 21)
+                assert pk.payload[base + 32 * s + rr] == ord(r["qual"][q]) - 33
+                b = pk.payload[base + 32 * s + 21 + rr // 2]
+                code = (b & 15) if rr & 1 else (b >> 4)
+                assert SEQ_CHARS[code] == r["seq"][q]
+            ops = re.findall(r"(\d+)([MIDNSHP=X])", r["cigar"])
+            span = sum(int(n) for n, o in ops if o in "MDN=X")
+            assert pk.hot["span"][i] == span
+            simple = len(ops) == 1 and ops[0][1] in "M=X"
+            assert (pk.hot["fmk"][i] >> 24) == (0 if simple else 1)
+            if not simple:
+                co, nc = int(pk.cold["cigar_off"][i]), int(pk.cold["n_cigar"][i])
+                assert [(int(w) >> 4, "MIDNSHP=X"[int(w) & 15]) for w in pk.cigar[co:co + nc]] == [(int(n), o) for n, o in ops]
+            assert pk.cold["l_qseq"][i] == lq
+        # running max of the end, per contig
+        for t in range(len(sc["contigs"])):
+            a, b = pk.contig_off[t], pk.contig_off[t + 1]
+            ends = pk.hot["pos"][a:b].astype(np.int64) + pk.hot["span"][a:b]
+            assert np.array_equal(pk.pmax_end[a:b], np.maximum.accumulate(ends)) if b > a else True
+
+
+@pytest.mark.parametrize("path", SCENARIOS, ids=[os.path.basename(p) for p in SCENARIOS])
+def test_link_mates_matches_oracle(path):
+    sc = H.load_scenario(path)
+    for batch in H.scenario_batches(sc):
+        for mq, orphans, overlaps in ((0, True, True), (1, True, True), (30, False, True), (0, True, False)):
+            prm = device.make_params(min_mapq=mq, ignore_orphans=orphans, ignore_overlaps=overlaps)
+            got = device.link_mates(batch, prm)
+            want = c_oracle.link_mates(batch.as_dict(), c_oracle.params(min_mapq=mq, ignore_orphans=orphans,
+                                                                        ignore_overlaps=overlaps))
+            partner = np.where(got == device.NO_MATE, -1, (got & 0x7FFFFFFF).astype(np.int64))
+            assert np.array_equal(partner, want)
+            linked = np.nonzero(partner >= 0)[0]
+            assert np.array_equal(partner[partner[linked]], linked)  # symmetric
+            if overlaps:
+                assert len(linked) > 0 or sc["name"] == "none"
+
+
+def test_units_encoding():
+    u = build_units([("c", 10, "A", ["T", "G"]), ("c", 11, "A", ["AT"]), ("c", 12, "ATT", ["A"]),
+                     ("c", 13, "AT", ["GC"]), ("c", 14, "a", ["t"]), ("c", 15, "A", ["AnT", "ATT"])], ["c"])
+    assert u.n_units == 2 + 1 + 1 + 0 + 1 + 1
+    assert u.unit_of[(0, 0)] == 0 and u.unit_of[(0, 1)] == 1 and (3, 0) not in u.unit_of
+    assert list(u.pos[:2]) == [9, 9]
+    assert (u.meta[0] & 3) == 0 and ((u.meta[0] >> 8) & 0xFF) == SEQ_CHARS.index("A") and ((u.meta[1] >> 16) & 0xFF) == SEQ_CHARS.index("G")
+    assert (u.meta[2] & 3) == 1 and u.length[2] == 1 and u.ins_seq[u.seq_off[2]] == SEQ_CHARS.index("T")
+    assert (u.meta[3] & 3) == 2 and u.length[3] == 2
+    assert ((u.meta[4] >> 8) & 0xFF) == CODE_NONE and ((u.meta[4] >> 16) & 0xFF) == CODE_NONE  # lowercase never matches
+    assert u.ins_seq[u.seq_off[5]] == CODE_NONE and u.ins_seq[u.seq_off[5] + 1] == SEQ_CHARS.index("T")
+    with pytest.raises(ValueError):
+        build_units([("zz", 1, "A", ["T"])], ["c"])
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    """The shared libraries build (nvcc cross-compiles without a GPU), load, and export exactly what
+    include/*.h declares.  No compute call is made here."""
+    libvfk, libio = build.build_all()
+    for header, path in (("vfk.h", libvfk), ("vfk_io.h", libio)):
+        text = open(os.path.join(ROOT, "include", header)).read()
+        declared = set(re.findall(r"\b(vfk(?:io)?_[a-z_]+)\s*\(", text))
+        lib = C.CDLL(path)
+        for name in sorted(declared):
+            assert hasattr(lib, name), (header, name)
+    lib = C.CDLL(libvfk)
+    assert lib.vfk_version() == 100
+    assert np.dtype(device.COUNTS_DTYPE).itemsize == 80
+    sass = subprocess.run(["cuobjdump", "-lelf", libvfk], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass

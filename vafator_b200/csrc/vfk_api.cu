@@ -1,0 +1,251 @@
+// vfk_api.cu -- the C ABI declared in include/vfk.h.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+#include "vfk.h"
+#include "vfk_device.cuh"
+
+namespace vfk {
+cudaError_t launch_pileup(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, int max_l_qseq, vfk_counts *out,
+                          unsigned long long *work_counter, uint32_t *deferred, uint32_t *n_deferred, int sm_count,
+                          cudaStream_t stream, int *launches);
+cudaError_t launch_epilogue(int64_t n_units, const vfk_counts *counts, const double *eaf, double fpr, double error_rate,
+                            vfk_stats *out, cudaStream_t stream, int *launches);
+}  // namespace vfk
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, const char *detail = "") {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+#define CU(call)                                                                  \
+    do {                                                                          \
+        cudaError_t e_ = (call);                                                  \
+        if (e_ != cudaSuccess) return fail(VFK_ECUDA, #call ": %s", cudaGetErrorString(e_)); \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return VFK_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) return fail(VFK_ENOMEM, "cudaMalloc: %s", cudaGetErrorString(e));
+        cap = want;
+        return VFK_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct vfk_handle {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    unsigned long long *work_counter = nullptr;  // 8 B + n_deferred 4 B
+    uint32_t *n_deferred = nullptr;
+    DevBuf deferred;
+    int64_t launches = 0;
+    // staging for vfk_annotate_host
+    DevBuf s_contig, s_hot, s_cold, s_mate, s_starts, s_pmax, s_cigar, s_payload;
+    DevBuf s_tid, s_pos, s_meta, s_len, s_soff, s_ins, s_stop, s_eaf, s_counts, s_stats;
+};
+
+extern "C" int vfk_version(void) { return VFK_VERSION; }
+extern "C" const char *vfk_last_error(void) { return g_err; }
+
+extern "C" int vfk_create(int device, vfk_handle **out) {
+    if (!out) return fail(VFK_EINVAL, "vfk_create: out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(VFK_ENODEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(VFK_EINVAL, "vfk_create: device index out of range");
+    CU(cudaSetDevice(device));
+    vfk_handle *h = new (std::nothrow) vfk_handle();
+    if (!h) return fail(VFK_ENOMEM, "vfk_create: out of host memory");
+    h->device = device;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->done, cudaEventDisableTiming));
+    void *p = nullptr;
+    CU(cudaMalloc(&p, 16));
+    h->work_counter = (unsigned long long *)p;
+    h->n_deferred = (uint32_t *)((char *)p + 8);
+    *out = h;
+    return VFK_OK;
+}
+
+extern "C" int vfk_destroy(vfk_handle *h) {
+    if (!h) return VFK_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    DevBuf *bufs[] = {&h->deferred, &h->s_contig, &h->s_hot, &h->s_cold, &h->s_mate, &h->s_starts, &h->s_pmax, &h->s_cigar,
+                      &h->s_payload, &h->s_tid, &h->s_pos, &h->s_meta, &h->s_len, &h->s_soff, &h->s_ins, &h->s_stop,
+                      &h->s_eaf, &h->s_counts, &h->s_stats};
+    for (DevBuf *b : bufs) b->release();
+    if (h->work_counter) cudaFree(h->work_counter);
+    if (h->done) cudaEventDestroy(h->done);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return VFK_OK;
+}
+
+extern "C" int vfk_sync(vfk_handle *h) {
+    if (!h) return fail(VFK_EINVAL, "vfk_sync: NULL handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaDeviceSynchronize());
+    return VFK_OK;
+}
+
+extern "C" int64_t vfk_launch_count(vfk_handle *h) { return h ? h->launches : 0; }
+
+static int check_batches(const vfk_read_batch *r, const vfk_variant_batch *v, const vfk_params *p) {
+    if (!r || !v || !p) return fail(VFK_EINVAL, "NULL batch or params");
+    if (r->n_reads < 0 || v->n_units < 0 || r->n_contigs < 0) return fail(VFK_EINVAL, "negative size");
+    if (r->n_reads > 0x7FFFFFFF) return fail(VFK_EUNSUPPORTED, "more than 2^31-1 reads in one batch: split it");
+    if (r->max_l_qseq > VFK_MAX_READ_LEN) return fail(VFK_EUNSUPPORTED, "read longer than VFK_MAX_READ_LEN");
+    if (!r->contig_off) return fail(VFK_EINVAL, "contig_off is NULL");
+    if (r->n_reads > 0 && (!r->hot || !r->cold || !r->mate || !r->starts || !r->pmax_end || !r->payload))
+        return fail(VFK_EINVAL, "read batch has a NULL array");
+    if (v->n_units > 0 && (!v->tid || !v->pos || !v->meta || !v->length || !v->seq_off || !v->ins_seq))
+        return fail(VFK_EINVAL, "variant batch has a NULL array");
+    return VFK_OK;
+}
+
+static void to_dev(const vfk_read_batch *r, const vfk_variant_batch *v, vfk::ReadsDev &R, vfk::UnitsDev &V) {
+    R.hot = (const uint4 *)r->hot;
+    R.cold = (const uint4 *)r->cold;
+    R.mate = r->mate;
+    R.starts = r->starts;
+    R.pmax_end = r->pmax_end;
+    R.cigar = r->cigar;
+    R.payload = r->payload;
+    R.contig_off = r->contig_off;
+    R.n_reads = r->n_reads;
+    R.n_contigs = r->n_contigs;
+    V.n = v->n_units;
+    V.tid = v->tid;
+    V.pos = v->pos;
+    V.meta = v->meta;
+    V.length = v->length;
+    V.seq_off = v->seq_off;
+    V.ins_seq = v->ins_seq;
+    V.stop = v->stop;
+}
+
+extern "C" int vfk_pileup(vfk_handle *h, const vfk_read_batch *reads, const vfk_variant_batch *units,
+                          const vfk_params *params, vfk_counts *out, void *stream) {
+    if (!h) return fail(VFK_EINVAL, "vfk_pileup: NULL handle");
+    int rc = check_batches(reads, units, params);
+    if (rc) return rc;
+    if (units->n_units == 0) return VFK_OK;
+    if (!out) return fail(VFK_EINVAL, "vfk_pileup: out is NULL");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    rc = h->deferred.reserve((size_t)units->n_units * sizeof(uint32_t));
+    if (rc) return rc;
+    vfk::ReadsDev R;
+    vfk::UnitsDev V;
+    to_dev(reads, units, R, V);
+    int launches = 0;
+    cudaError_t e = vfk::launch_pileup(R, V, *params, reads->max_l_qseq, out, h->work_counter, (uint32_t *)h->deferred.p,
+                                       h->n_deferred, h->sm_count, st, &launches);
+    h->launches += launches;
+    if (e != cudaSuccess) return fail(VFK_ECUDA, "pileup launch: %s", cudaGetErrorString(e));
+    return VFK_OK;
+}
+
+extern "C" int vfk_epilogue(vfk_handle *h, int64_t n_units, const vfk_counts *counts, const double *eaf, double fpr,
+                            double error_rate, vfk_stats *out, void *stream) {
+    if (!h) return fail(VFK_EINVAL, "vfk_epilogue: NULL handle");
+    if (n_units < 0) return fail(VFK_EINVAL, "vfk_epilogue: negative size");
+    if (n_units == 0) return VFK_OK;
+    if (!counts || !eaf || !out) return fail(VFK_EINVAL, "vfk_epilogue: NULL array");
+    if (!(fpr >= 0.0) || !(error_rate >= 0.0)) return fail(VFK_EINVAL, "vfk_epilogue: fpr / error_rate must be >= 0");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    int launches = 0;
+    cudaError_t e = vfk::launch_epilogue(n_units, counts, eaf, fpr, error_rate, out, st, &launches);
+    h->launches += launches;
+    if (e != cudaSuccess) return fail(VFK_ECUDA, "epilogue launch: %s", cudaGetErrorString(e));
+    return VFK_OK;
+}
+
+#define STAGE(buf, src, bytes)                                                                   \
+    do {                                                                                         \
+        size_t b_ = (size_t)(bytes);                                                             \
+        int rc_ = (buf).reserve(b_ ? b_ : 16);                                                   \
+        if (rc_) return rc_;                                                                     \
+        if (b_) CU(cudaMemcpyAsync((buf).p, (src), b_, cudaMemcpyHostToDevice, st));             \
+    } while (0)
+
+extern "C" int vfk_annotate_host(vfk_handle *h, const vfk_read_batch *reads, const vfk_variant_batch *units,
+                                 const vfk_params *params, const double *eaf, double fpr, double error_rate,
+                                 vfk_counts *counts_out, vfk_stats *stats_out) {
+    if (!h) return fail(VFK_EINVAL, "vfk_annotate_host: NULL handle");
+    int rc = check_batches(reads, units, params);
+    if (rc) return rc;
+    const int64_t nu = units->n_units, nr = reads->n_reads;
+    if (nu == 0) return VFK_OK;
+    if (!eaf || !counts_out || !stats_out) return fail(VFK_EINVAL, "vfk_annotate_host: NULL array");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    STAGE(h->s_contig, reads->contig_off, (size_t)(reads->n_contigs + 1) * sizeof(int64_t));
+    STAGE(h->s_hot, reads->hot, (size_t)nr * sizeof(vfk_read_hot));
+    STAGE(h->s_cold, reads->cold, (size_t)nr * sizeof(vfk_read_cold));
+    STAGE(h->s_mate, reads->mate, (size_t)nr * 4);
+    STAGE(h->s_starts, reads->starts, (size_t)nr * 4);
+    STAGE(h->s_pmax, reads->pmax_end, (size_t)nr * 4);
+    STAGE(h->s_cigar, reads->cigar, (size_t)reads->n_cigar_words * 4);
+    STAGE(h->s_payload, reads->payload, (size_t)reads->n_sectors * 32);
+    STAGE(h->s_tid, units->tid, (size_t)nu * 4);
+    STAGE(h->s_pos, units->pos, (size_t)nu * 4);
+    STAGE(h->s_meta, units->meta, (size_t)nu * 4);
+    STAGE(h->s_len, units->length, (size_t)nu * 4);
+    STAGE(h->s_soff, units->seq_off, (size_t)nu * 4);
+    STAGE(h->s_ins, units->ins_seq, (size_t)(units->n_ins_seq > 0 ? units->n_ins_seq : 1));
+    if (units->stop) STAGE(h->s_stop, units->stop, (size_t)nu * 4);
+    STAGE(h->s_eaf, eaf, (size_t)nu * sizeof(double));
+    rc = h->s_counts.reserve((size_t)nu * sizeof(vfk_counts));
+    if (rc) return rc;
+    rc = h->s_stats.reserve((size_t)nu * sizeof(vfk_stats));
+    if (rc) return rc;
+    vfk_read_batch dr = *reads;
+    dr.contig_off = (const int64_t *)h->s_contig.p;
+    dr.hot = (const vfk_read_hot *)h->s_hot.p;
+    dr.cold = (const vfk_read_cold *)h->s_cold.p;
+    dr.mate = (const uint32_t *)h->s_mate.p;
+    dr.starts = (const int32_t *)h->s_starts.p;
+    dr.pmax_end = (const int32_t *)h->s_pmax.p;
+    dr.cigar = (const uint32_t *)h->s_cigar.p;
+    dr.payload = (const uint8_t *)h->s_payload.p;
+    vfk_variant_batch dv = *units;
+    dv.tid = (const int32_t *)h->s_tid.p;
+    dv.pos = (const int32_t *)h->s_pos.p;
+    dv.meta = (const uint32_t *)h->s_meta.p;
+    dv.length = (const int32_t *)h->s_len.p;
+    dv.seq_off = (const uint32_t *)h->s_soff.p;
+    dv.ins_seq = (const uint8_t *)h->s_ins.p;
+    dv.stop = units->stop ? (const int32_t *)h->s_stop.p : nullptr;
+    rc = vfk_pileup(h, &dr, &dv, params, (vfk_counts *)h->s_counts.p, st);
+    if (rc) return rc;
+    rc = vfk_epilogue(h, nu, (const vfk_counts *)h->s_counts.p, (const double *)h->s_eaf.p, fpr, error_rate,
+                      (vfk_stats *)h->s_stats.p, st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(counts_out, h->s_counts.p, (size_t)nu * sizeof(vfk_counts), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(stats_out, h->s_stats.p, (size_t)nu * sizeof(vfk_stats), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return VFK_OK;
+}

@@ -1,0 +1,429 @@
+// vfk_device.cuh -- device-side building blocks shared by the pileup kernels (sm_100a).
+//
+// What is evaluated per (variant column, read) pair follows pysam 0.21.0 / htslib 1.17 as
+// vafator drives them (vafator/pileups.py:71-80, :184-362):
+//   read filter          pysam __advance_samtools (flag filter, MAPQ, orphans) + bam_plp_push
+//   column resolution    htslib resolve_cigar2 (qpos, is_del, is_refskip, indel)
+//   mate overlap         htslib overlap_push / tweak_overlap_quality, applied on the fly
+//   base-quality filter  pysam pileup_base_qual_skip
+//   allele support       vafator/pileups.py:199-212 (SNV), :263-294 (insertion), :329-351 (deletion)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "vfk.h"
+
+namespace vfk {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+enum : int { OP_M = 0, OP_I = 1, OP_D = 2, OP_N = 3, OP_S = 4, OP_H = 5, OP_P = 6, OP_EQ = 7, OP_X = 8 };
+enum : unsigned { F_PAIRED = 1, F_PROPER = 2, F_UNMAP = 4, F_MUNMAP = 8 };
+
+struct ReadsDev {
+    const uint4 *__restrict__ hot;
+    const uint4 *__restrict__ cold;
+    const uint32_t *__restrict__ mate;
+    const int32_t *__restrict__ starts;
+    const int32_t *__restrict__ pmax_end;
+    const uint32_t *__restrict__ cigar;
+    const uint8_t *__restrict__ payload;
+    const int64_t *__restrict__ contig_off;
+    int64_t n_reads;
+    int32_t n_contigs;
+};
+
+struct UnitsDev {
+    int64_t n;
+    const int32_t *__restrict__ tid;
+    const int32_t *__restrict__ pos;
+    const uint32_t *__restrict__ meta;
+    const int32_t *__restrict__ length;
+    const uint32_t *__restrict__ seq_off;
+    const uint8_t *__restrict__ ins_seq;
+    const int32_t *__restrict__ stop;  // may be nullptr
+};
+
+struct Unit {
+    int32_t col;    // 0-based column
+    int32_t stop;   // reads starting at or beyond it were never fetched by the reference
+    uint32_t kind;
+    uint32_t ref_code, alt_code;
+    int32_t len;
+    const uint8_t *ins;
+    int64_t c0, c1;  // read range of the contig
+    int64_t lo, hi;  // candidate range: pmax_end > col ... starts <= col
+};
+
+// one read's contribution to a column
+struct Contribution {
+    bool in_dp;
+    bool ambiguous;
+    bool ref;      // value goes to the REF list
+    uint32_t alt;  // how many times the value goes to the ALT list
+    int mq, bq, qpos;
+    bool pos_overflow;
+};
+
+__device__ __forceinline__ bool is_ref_op(int op) { return op == OP_M || op == OP_D || op == OP_N || op == OP_EQ || op == OP_X; }
+__device__ __forceinline__ bool is_aln_op(int op) { return op == OP_M || op == OP_EQ || op == OP_X; }
+
+// ---- payload sector addressing: 21 (quality, base) pairs per 32-byte sector ----
+__device__ __forceinline__ void sector_of(uint32_t q, uint32_t &s, uint32_t &r) {
+    s = q / 21u;
+    r = q - s * 21u;
+}
+__device__ __forceinline__ int pay_qual(const uint8_t *__restrict__ payload, uint32_t pay, uint32_t q) {
+    uint32_t s, r;
+    sector_of(q, s, r);
+    return __ldg(payload + ((size_t)(pay + s) << 5) + r);
+}
+__device__ __forceinline__ int pay_base(const uint8_t *__restrict__ payload, uint32_t pay, uint32_t q) {
+    uint32_t s, r;
+    sector_of(q, s, r);
+    int b = __ldg(payload + ((size_t)(pay + s) << 5) + 21u + (r >> 1));
+    return (r & 1u) ? (b & 15) : (b >> 4);
+}
+
+__device__ __forceinline__ uint32_t wang_hash(uint32_t k) {
+    k += ~(k << 15); k ^= (k >> 10); k += (k << 3); k ^= (k >> 6); k += ~(k << 11); k ^= (k >> 16);
+    return k;
+}
+
+// BAM 4-bit codes "=ACMGRSVTWYHKDBN": everything but = A C G T is IUPAC-ambiguous (vafator/constants.py:5)
+__device__ __forceinline__ bool code_is_ambiguous(int c) { return ((0x0117u >> c) & 1u) == 0u; }
+
+__device__ __forceinline__ bool read_passes(uint32_t fmk, const vfk_params &P) {
+    uint32_t flag = fmk & 0xFFFFu;
+    int mapq = (fmk >> 16) & 0xFF;
+    if (flag & (P.flag_filter | F_UNMAP)) return false;
+    if (mapq < P.min_mapq) return false;
+    if (P.ignore_orphans && (flag & F_PAIRED) && !(flag & F_PROPER)) return false;
+    return true;
+}
+
+// ---- column resolution ----
+struct Resolved {
+    bool covered;
+    bool is_del, is_refskip;
+    int qpos;
+    int indel;
+    int l_qseq;
+};
+
+// general CIGAR walk for a shape-1 read (cold record needed)
+__device__ __forceinline__ Resolved resolve_general(const ReadsDev &R, int32_t rpos, const uint4 &cold, int32_t col) {
+    Resolved o;
+    o.covered = false; o.is_del = false; o.is_refskip = false; o.qpos = 0; o.indel = 0; o.l_qseq = (int)cold.z;
+    const uint32_t *__restrict__ c = R.cigar + cold.x;
+    const int n = (int)cold.y;
+    int32_t x = rpos, y = 0;
+    for (int k = 0; k < n; ++k) {
+        uint32_t w = __ldg(c + k);
+        int op = w & 15;
+        int32_t l = (int32_t)(w >> 4);
+        if (is_ref_op(op)) {
+            if (col < x + l) {
+                o.covered = true;
+                if (x + l - 1 == col && k + 1 < n) {  // peek: does an indel start right after this column?
+                    uint32_t w2 = __ldg(c + k + 1);
+                    int op2 = w2 & 15;
+                    int32_t l2 = (int32_t)(w2 >> 4);
+                    if (op2 == OP_D && op != OP_D) {
+                        o.indel = -l2;
+                        for (int j = k + 2; j < n; ++j) {
+                            uint32_t wj = __ldg(c + j);
+                            if ((wj & 15) != OP_D) break;
+                            o.indel -= (int32_t)(wj >> 4);
+                        }
+                    } else if (op2 == OP_I) {
+                        o.indel = l2;
+                        for (int j = k + 2; j < n; ++j) {
+                            uint32_t wj = __ldg(c + j);
+                            int oj = wj & 15;
+                            if (oj == OP_I) o.indel += (int32_t)(wj >> 4);
+                            else if (oj != OP_P) break;
+                        }
+                    } else if (op2 == OP_P && k + 2 < n) {
+                        int32_t l3 = 0;
+                        for (int j = k + 2; j < n; ++j) {
+                            uint32_t wj = __ldg(c + j);
+                            int oj = wj & 15;
+                            if (oj == OP_I) l3 += (int32_t)(wj >> 4);
+                            else if (is_ref_op(oj)) break;
+                        }
+                        if (l3 > 0) o.indel = l3;
+                    }
+                }
+                if (is_aln_op(op)) {
+                    o.qpos = y + (col - x);
+                } else {
+                    o.qpos = y;
+                    o.is_del = true;
+                    o.is_refskip = (op == OP_N);
+                }
+                return o;
+            }
+            x += l;
+            if (is_aln_op(op)) y += l;
+        } else if (op == OP_I || op == OP_S) {
+            y += l;
+        }
+    }
+    return o;
+}
+
+// reference position aligned to query index q of a shape-1 read, -1 if q is not in an M/=/X op
+__device__ __forceinline__ int32_t refpos_of_query(const ReadsDev &R, int32_t rpos, const uint4 &cold, int q) {
+    const uint32_t *__restrict__ c = R.cigar + cold.x;
+    int32_t x = rpos, y = 0;
+    for (int k = 0; k < (int)cold.y; ++k) {
+        uint32_t w = __ldg(c + k);
+        int op = w & 15;
+        int32_t l = (int32_t)(w >> 4);
+        if (is_aln_op(op)) {
+            if (q < y + l) return x + (q - y);
+            x += l; y += l;
+        } else if (op == OP_D || op == OP_N) {
+            x += l;
+        } else if (op == OP_I || op == OP_S) {
+            if (q < y + l) return -1;
+            y += l;
+        }
+    }
+    return -1;
+}
+
+// first read at or after `from` (same contig, start < stop) that the reference would have pushed
+__device__ __forceinline__ int64_t next_pushed(const ReadsDev &R, const vfk_params &P, int64_t from, int64_t c1, int32_t stop) {
+    for (int64_t j = from; j < c1; ++j) {
+        uint4 h = __ldg(R.hot + j);
+        if ((int32_t)h.x >= stop) break;
+        if (read_passes(h.z, P)) return j;
+    }
+    return -1;
+}
+
+// Quality of query base q of read i as the reference sees it when column `col` is emitted:
+// htslib tweak_overlap_quality has run for the pair iff the second mate has been pushed, i.e. it
+// starts at or before `col` or is the first pushed record after it (bam_plp_auto reads one ahead).
+__device__ __forceinline__ int tweaked_quality(const ReadsDev &R, const vfk_params &P, const Unit &U, int64_t i,
+                                               const uint4 &hot, const uint4 &cold_if_general, bool general, int q,
+                                               int l_qseq, bool q_is_column_base) {
+    if (q >= l_qseq) return 0;
+    int qi = pay_qual(R.payload, hot.w, (uint32_t)q);
+    uint32_t flag = hot.z & 0xFFFFu;
+    if (!P.ignore_overlaps || !(flag & F_PROPER) || (flag & F_MUNMAP)) return qi;
+    uint32_t mw = __ldg(R.mate + i);
+    if (mw == VFK_NO_MATE) return qi;
+    int64_t m = (int64_t)(mw & 0x7FFFFFFFu);
+    uint32_t sel = mw >> 31;
+    uint4 mh = __ldg(R.hot + m);
+    if (m > i && (int32_t)mh.x > U.col) {
+        if (q_is_column_base) return qi;  // the mate cannot cover this column
+        if (next_pushed(R, P, U.hi, U.c1, U.stop) != m) return qi;
+    }
+    int32_t rp = q_is_column_base ? U.col : (general ? refpos_of_query(R, (int32_t)hot.x, cold_if_general, q)
+                                                     : (int32_t)hot.x + q);
+    if (rp < 0) return qi;
+    if (rp < (int32_t)mh.x || rp >= (int32_t)mh.x + (int32_t)mh.y) return qi;
+    int mq_index, ml;
+    if ((mh.z >> 24) == 0u) {
+        mq_index = rp - (int32_t)mh.x;
+        ml = (int)mh.y;
+    } else {
+        uint4 mc = __ldg(R.cold + m);
+        Resolved mr = resolve_general(R, (int32_t)mh.x, mc, rp);
+        if (!mr.covered || mr.is_del) return qi;
+        mq_index = mr.qpos;
+        ml = mr.l_qseq;
+    }
+    if (mq_index >= ml) return qi;
+    int qm = pay_qual(R.payload, mh.w, (uint32_t)mq_index);
+    int bm = pay_base(R.payload, mh.w, (uint32_t)mq_index);
+    int bi = pay_base(R.payload, hot.w, (uint32_t)q);
+    bool i_first = i < m;  // the earlier record holds the hash slot ("a" in htslib)
+    uint32_t mymul = i_first ? sel : (1u - sel);
+    if (bi == bm) {
+        int s = qi + qm;
+        if (s > 200) s = 200;
+        return mymul ? s : 0;
+    }
+    // (uint8_t)(0.8 * q) in IEEE double == floor(4q/5) for every q in 0..255 (tests/test_host.py)
+    if (qi > qm) return (qi * 4) / 5;
+    if (qi < qm) return 0;
+    return mymul ? (qi * 4) / 5 : 0;
+}
+
+// vafator/pileups.py:267-290 -- how many times the read supports the insertion
+__device__ __forceinline__ uint32_t insertion_hits(const ReadsDev &R, const uint4 &hot, const uint4 &cold, const Unit &U) {
+    const uint32_t *__restrict__ c = R.cigar + cold.x;
+    const int n = (int)cold.y;
+    const int32_t pos1 = U.col + 1;
+    int32_t qs = 0, qe = (int32_t)cold.z;  // pysam `query`: soft clips trimmed at both ends
+    for (int k = 0; k < n; ++k) {
+        uint32_t w = __ldg(c + k);
+        int op = w & 15;
+        if (op == OP_H) continue;
+        if (op == OP_S) qs += (int32_t)(w >> 4); else break;
+    }
+    for (int k = n - 1; k >= 1; --k) {
+        uint32_t w = __ldg(c + k);
+        int op = w & 15;
+        if (op == OP_H) continue;
+        if (op == OP_S) qe -= (int32_t)(w >> 4); else break;
+    }
+    const int32_t qlen = qe - qs;
+    int32_t index = (int32_t)hot.x, rel = 0;
+    uint32_t hits = 0;
+    for (int k = 0; k < n; ++k) {
+        uint32_t w = __ldg(c + k);
+        int op = w & 15;
+        int32_t l = (int32_t)(w >> 4);
+        if (is_ref_op(op)) {
+            index += l;
+            if (index > pos1) break;
+        }
+        if (op == OP_M || op == OP_I || op == OP_S || op == OP_EQ || op == OP_X) rel += l;
+        if (op == OP_I && index == pos1 && l == U.len) {
+            // the reference compares the L bases FOLLOWING the insertion (rel already includes it,
+            // and any leading soft clip) against ALT[0][1:]  -- SURVEY.md A.5
+            bool ok = rel + U.len <= qlen;
+            for (int t = 0; ok && t < U.len; ++t)
+                ok = pay_base(R.payload, hot.w, (uint32_t)(qs + rel + t)) == (int)U.ins[t];
+            hits += ok ? 1u : 0u;
+        }
+    }
+    return hits;
+}
+
+// vafator/pileups.py:333-347
+__device__ __forceinline__ uint32_t deletion_hits(const ReadsDev &R, const uint4 &hot, const uint4 &cold, const Unit &U) {
+    const uint32_t *__restrict__ c = R.cigar + cold.x;
+    const int32_t pos1 = U.col + 1;
+    int32_t start = (int32_t)hot.x;
+    for (int k = 0; k < (int)cold.y; ++k) {
+        uint32_t w = __ldg(c + k);
+        int op = w & 15;
+        int32_t l = (int32_t)(w >> 4);
+        if (op == OP_M || op == OP_N || op == OP_EQ || op == OP_X) {
+            start += l;
+        } else if (op == OP_D) {
+            if (start == pos1 && l == U.len) return 1u;
+            start += l;
+        }
+        if (start > pos1) break;
+    }
+    return 0u;
+}
+
+// Everything one read contributes to one unit.
+__device__ __forceinline__ Contribution evaluate(const ReadsDev &R, const vfk_params &P, const Unit &U, int64_t i) {
+    Contribution o;
+    o.in_dp = false; o.ambiguous = false; o.ref = false; o.alt = 0; o.mq = 0; o.bq = 0; o.qpos = 0; o.pos_overflow = false;
+    const uint4 hot = __ldg(R.hot + i);
+    const int32_t rpos = (int32_t)hot.x;
+    if (U.col < rpos || U.col >= rpos + (int32_t)hot.y) return o;
+    if (!read_passes(hot.z, P)) return o;
+    const bool general = (hot.z >> 24) != 0u;
+    uint4 cold = make_uint4(0, 0, 0, 0);
+    Resolved r;
+    if (!general) {
+        r.covered = true; r.is_del = false; r.is_refskip = false; r.indel = 0;
+        r.qpos = U.col - rpos;
+        r.l_qseq = (int)hot.y;
+    } else {
+        cold = __ldg(R.cold + i);
+        r = resolve_general(R, rpos, cold, U.col);
+        if (!r.covered) return o;
+    }
+    const int q = tweaked_quality(R, P, U, i, hot, cold, general, r.qpos, r.l_qseq, !r.is_del);
+    if (q < P.min_baseq) return o;  // pysam pileup_base_qual_skip
+    o.mq = (int)((hot.z >> 16) & 0xFF);
+    o.bq = q;
+    o.qpos = r.qpos;
+    if (U.kind == VFK_KIND_SNV) {
+        if (r.is_refskip) return o;
+        o.in_dp = true;
+        if (r.is_del) return o;  // counted in DP as the "" allele, belongs to no reported list
+        int code = pay_base(R.payload, hot.w, (uint32_t)r.qpos);
+        o.ambiguous = code_is_ambiguous(code);
+        o.ref = (uint32_t)code == U.ref_code;
+        o.alt = ((uint32_t)code == U.alt_code) ? 1u : 0u;
+    } else {
+        o.in_dp = true;
+        o.bq = 0;
+        if (r.indel == 0) {
+            o.ref = true;  // "considers all reads without indels to be the reference" (pileups.py:291-294)
+        } else if (general) {
+            if (U.kind == VFK_KIND_INS && r.indel > 0) o.alt = insertion_hits(R, hot, cold, U);
+            else if (U.kind == VFK_KIND_DEL && r.indel < 0) o.alt = deletion_hits(R, hot, cold, U);
+        }
+    }
+    return o;
+}
+
+// ---- warp-cooperative lower bound: first index in [lo, hi) with a[idx] > key, else hi ----
+__device__ __forceinline__ int64_t warp_first_greater(const int32_t *__restrict__ a, int64_t lo, int64_t hi, int32_t key, int lane) {
+    while (hi - lo > 32) {
+        const int64_t n = hi - lo;
+        const int64_t idx = lo + (((int64_t)(lane + 1) * n) >> 5) - 1;
+        const bool t = __ldg(a + idx) > key;
+        const unsigned b = __ballot_sync(FULL, t);
+        if (b == 0u) return hi;
+        const int j = __ffs(b) - 1;
+        const int64_t nlo = lo + (((int64_t)j * n) >> 5);
+        hi = lo + (((int64_t)(j + 1) * n) >> 5) - 1;  // known to satisfy the predicate
+        lo = nlo;
+    }
+    const int64_t idx = lo + lane;
+    const bool t = (idx < hi) ? (__ldg(a + idx) > key) : true;
+    const unsigned b = __ballot_sync(FULL, t);
+    return lo + (__ffs(b) - 1);
+}
+
+// both bounds of a column at once (independent probe chains -> two loads in flight per step)
+__device__ __forceinline__ void warp_locate(const ReadsDev &R, Unit &U, int lane) {
+    int64_t lo0 = U.c0, hi0 = U.c1, lo1 = U.c0, hi1 = U.c1;
+    while (hi0 - lo0 > 32 || hi1 - lo1 > 32) {
+        const bool a0 = hi0 - lo0 > 32, a1 = hi1 - lo1 > 32;
+        const int64_t n0 = hi0 - lo0, n1 = hi1 - lo1;
+        const int64_t i0 = lo0 + (((int64_t)(lane + 1) * n0) >> 5) - 1;
+        const int64_t i1 = lo1 + (((int64_t)(lane + 1) * n1) >> 5) - 1;
+        int32_t v0 = 0, v1 = 0;
+        if (a0) v0 = __ldg(R.pmax_end + i0);
+        if (a1) v1 = __ldg(R.starts + i1);
+        if (a0) {
+            const unsigned b = __ballot_sync(FULL, v0 > U.col);
+            if (b == 0u) { lo0 = hi0; }
+            else { const int j = __ffs(b) - 1; const int64_t nlo = lo0 + (((int64_t)j * n0) >> 5); hi0 = lo0 + (((int64_t)(j + 1) * n0) >> 5) - 1; lo0 = nlo; }
+        }
+        if (a1) {
+            const unsigned b = __ballot_sync(FULL, v1 > U.col);
+            if (b == 0u) { lo1 = hi1; }
+            else { const int j = __ffs(b) - 1; const int64_t nlo = lo1 + (((int64_t)j * n1) >> 5); hi1 = lo1 + (((int64_t)(j + 1) * n1) >> 5) - 1; lo1 = nlo; }
+        }
+    }
+    {
+        const int64_t i0 = lo0 + lane, i1 = lo1 + lane;
+        const bool t0 = (i0 < hi0) ? (__ldg(R.pmax_end + i0) > U.col) : true;
+        const bool t1 = (i1 < hi1) ? (__ldg(R.starts + i1) > U.col) : true;
+        U.lo = lo0 + (__ffs(__ballot_sync(FULL, t0)) - 1);
+        U.hi = lo1 + (__ffs(__ballot_sync(FULL, t1)) - 1);
+    }
+    if (U.hi < U.lo) U.hi = U.lo;
+}
+
+__device__ __forceinline__ void load_unit(const ReadsDev &R, const UnitsDev &V, int64_t u, Unit &U) {
+    const int32_t tid = __ldg(V.tid + u);
+    const uint32_t meta = __ldg(V.meta + u);
+    U.col = __ldg(V.pos + u);
+    U.stop = V.stop ? __ldg(V.stop + u) : 0x7FFFFFFF;
+    U.kind = meta & 3u;
+    U.ref_code = (meta >> 8) & 0xFFu;
+    U.alt_code = (meta >> 16) & 0xFFu;
+    U.len = __ldg(V.length + u);
+    U.ins = V.ins_seq + __ldg(V.seq_off + u);
+    U.c0 = __ldg(R.contig_off + tid);
+    U.c1 = __ldg(R.contig_off + tid + 1);
+}
+
+}  // namespace vfk

@@ -1,0 +1,118 @@
+// vfk_epilogue.cu -- FP64 statistics epilogue (sm_100a), one thread per unit.
+//
+// Replaces, from the integer record the pileup kernel wrote:
+//   vafator/rank_sum_test.py:6-12   scipy.stats.ranksums(x=alt, y=ref): mid-ranks, NO tie or
+//                                   continuity correction, p = 2*ndtr(-|z|)        
+//   vafator/power.py:39-50          pu = binom.cdf(ac, dp, eaf)
+//   vafator/power.py:84-131         Carter-2012 k, d and power pw
+// Rounding to 3/5 decimals is presentation and stays on the host.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include "vfk.h"
+
+namespace vfk {
+
+__device__ __forceinline__ double log_binom_pmf(int64_t k, int64_t n, double logp, double log1mp) {
+    return lgamma((double)n + 1.0) - lgamma((double)k + 1.0) - lgamma((double)(n - k) + 1.0) + (double)k * logp +
+           (double)(n - k) * log1mp;
+}
+
+__device__ double binom_pmf(int64_t k, int64_t n, double p) {
+    if (k < 0 || k > n) return 0.0;
+    if (p <= 0.0) return k == 0 ? 1.0 : 0.0;
+    if (p >= 1.0) return k == n ? 1.0 : 0.0;
+    return exp(log_binom_pmf(k, n, log(p), log1p(-p)));
+}
+
+// lower tail P[X <= k] by direct summation of the probability mass, starting from the largest
+// term of the tail that is summed so that every further term is smaller (no cancellation).
+__device__ double binom_cdf(int64_t k, int64_t n, double p) {
+    if (k < 0) return 0.0;
+    if (k >= n) return 1.0;
+    if (p <= 0.0) return 1.0;
+    if (p >= 1.0) return 0.0;
+    const double logp = log(p), log1mp = log1p(-p);
+    const double odds = p / (1.0 - p);
+    if ((double)k < (double)(n + 1) * p) {
+        // k below the mode: sum k, k-1, ... downwards
+        double term = exp(log_binom_pmf(k, n, logp, log1mp));
+        double sum = term;
+        for (int64_t i = k; i > 0; --i) {
+            term *= ((double)i / (double)(n - i + 1)) / odds;
+            sum += term;
+            if (term < sum * 1e-18) break;
+        }
+        return sum;
+    }
+    // upper tail k+1, k+2, ... then complement
+    double term = exp(log_binom_pmf(k + 1, n, logp, log1mp));
+    double sum = term;
+    for (int64_t i = k + 1; i < n; ++i) {
+        term *= ((double)(n - i) / (double)(i + 1)) * odds;
+        sum += term;
+        if (term < sum * 1e-18) break;
+    }
+    return 1.0 - sum;
+}
+
+// vafator/power.py:84-93 -- P(m, n) = 1 - binom.cdf(m-1, n, err/3), 1 when m < 1
+__device__ __forceinline__ double carter_p(int64_t m, int64_t n, double e3) {
+    return m >= 1 ? 1.0 - binom_cdf(m - 1, n, e3) : 1.0;
+}
+
+__global__ void __launch_bounds__(128)
+epilogue_kernel(int64_t n_units, const vfk_counts *__restrict__ counts, const double *__restrict__ eaf, double fpr,
+                double error_rate, vfk_stats *__restrict__ out) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_units) return;
+    const vfk_counts c = counts[u];
+    vfk_stats s;
+    const bool has_bq = (c.status & VFK_ST_KIND_MASK) == VFK_KIND_SNV;
+    const double n1 = (double)c.ac_alt, n2 = (double)c.ac_ref;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+        const bool present = c.ac_alt > 0 && c.ac_ref > 0 && (m != 1 || has_bq);
+        if (!present) {
+            s.z[m] = nan("");
+            s.p[m] = nan("");
+            continue;
+        }
+        // scipy: s = sum(ranks of x); expected = n1*(n1+n2+1)/2.0; z = (s-expected)/sqrt(n1*n2*(n1+n2+1)/12.0)
+        const double ranks = (double)c.s2[m] * 0.5;  // exact: multiples of 0.5 well below 2^53
+        const double expected = n1 * (n1 + n2 + 1.0) / 2.0;
+        const uint64_t prod = (uint64_t)c.ac_alt * (uint64_t)c.ac_ref * (uint64_t)(c.ac_alt + c.ac_ref + 1);
+        const double z = (ranks - expected) / sqrt((double)prod / 12.0);
+        s.z[m] = z;
+        s.p[m] = erfc(fabs(z) * 0.70710678118654752440);  // 2*ndtr(-|z|)
+    }
+    const int64_t dp = c.dp;
+    const double f = eaf[u];
+    s.pu = binom_cdf(c.ac_alt, dp, f);
+    // k = min{k >= 1 : P(k, dp) <= fpr}   (vafator/power.py:106-114)
+    const double e3 = error_rate / 3.0;
+    int64_t k = 1;
+    double pk = carter_p(1, dp, e3), pk_1 = 1.0;
+    while (pk > fpr) {
+        ++k;
+        pk_1 = pk;
+        pk = carter_p(k, dp, e3);
+    }
+    const double d = (fpr - pk) / (pk_1 - pk);
+    s.pw = 1.0 - binom_cdf(k - 1, dp, f) + d * binom_pmf(k, dp, f);
+    s.k = (int32_t)k;
+    s.pad = 0;
+    out[u] = s;
+}
+
+cudaError_t launch_epilogue(int64_t n_units, const vfk_counts *counts, const double *eaf, double fpr, double error_rate,
+                            vfk_stats *out, cudaStream_t stream, int *launches) {
+    if (n_units <= 0) return cudaSuccess;
+    const int block = 128;
+    const int64_t grid = (n_units + block - 1) / block;
+    epilogue_kernel<<<(unsigned)grid, block, 0, stream>>>(n_units, counts, eaf, fpr, error_rate, out);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+}  // namespace vfk

@@ -1,0 +1,336 @@
+// vfk_pileup.cu -- the pileup kernels (sm_100a).
+//
+// Replaces vafator/pileups.py:106-362 + vafator/pileup_utils.py:64-92: for every unit (variant
+// column x ALT allele) find the overlapping reads, classify them, and reduce the per-allele
+// MQ / BQ / read-position distributions to integers: counts, twice-the-median, and twice the
+// ALT mid-rank sum that scipy.stats.ranksums would compute (vafator/rank_sum_test.py:11).
+//
+// pileup_warp_kernel : one warp per unit, lanes = candidate reads, histograms in shared memory
+//                      (u16 counters, two per word).  Persistent grid, units handed out in small
+//                      contiguous grabs from a global counter.
+// pileup_block_kernel: one CTA per unit for the (rare) columns too deep for u16 counters.
+#include "vfk_device.cuh"
+
+namespace vfk {
+
+constexpr int WARPS_PER_CTA = 8;
+constexpr int GRAB = 4;
+constexpr int WARP_PATH_MAX_CAND = 32767;  // u16 bins, weight <= 2 per read
+
+template <int POSB>
+struct Layout {
+    static constexpr int MQ_OFF = 0;
+    static constexpr int BQ_OFF = 256;
+    static constexpr int POS_OFF = 512;
+    static constexpr int BINS = 512 + POSB;  // per slot
+};
+
+// ------------------------------------------------------------------------------------------
+// histogram access.  CT = uint16_t: two bins per 32-bit word; CT = uint32_t: one bin per word.
+// ------------------------------------------------------------------------------------------
+template <typename CT>
+__device__ __forceinline__ void hist_add(uint32_t *slot, int bin, uint32_t w) {
+    if (sizeof(CT) == 2) atomicAdd(slot + (bin >> 1), w << ((bin & 1) * 16));
+    else atomicAdd(slot + bin, w);
+}
+template <typename CT>
+__device__ __forceinline__ uint32_t hist_get(const uint32_t *slot, int bin) {
+    if (sizeof(CT) == 2) return (slot[bin >> 1] >> ((bin & 1) * 16)) & 0xFFFFu;
+    return slot[bin];
+}
+
+__device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(FULL, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// One metric (B bins starting at bin `off` of each slot): medians of both lists and the ALT
+// mid-rank sum over the pooled ranking.  Executed by one full warp.
+//   2*rank_sum(ALT) = sum_v alt[v] * (2*below(v) + ties(v) + 1)
+template <typename CT, int B>
+__device__ __forceinline__ void reduce_metric(const uint32_t *ref_slot, const uint32_t *alt_slot, int off, int lane,
+                                              int &med2_ref, int &med2_alt, uint64_t &s2) {
+    constexpr int BPL = B / 32;  // consecutive bins per lane
+    const int b0 = off + lane * BPL;
+    uint32_t tr = 0, ta = 0;
+#pragma unroll 4
+    for (int j = 0; j < BPL; ++j) {
+        tr += hist_get<CT>(ref_slot, b0 + j);
+        ta += hist_get<CT>(alt_slot, b0 + j);
+    }
+    const uint32_t ir = warp_incl_scan(tr, lane), ia = warp_incl_scan(ta, lane);
+    const uint32_t nr = __shfl_sync(FULL, ir, 31), na = __shfl_sync(FULL, ia, 31);
+    uint32_t cr = ir - tr, ca = ia - ta;  // exclusive prefixes
+    // 0-based order statistics that make the median
+    const uint32_t r1 = nr ? (nr - 1) >> 1 : 0, r2 = nr >> 1, a1 = na ? (na - 1) >> 1 : 0, a2 = na >> 1;
+    int vr1 = -1, vr2 = -1, va1 = -1, va2 = -1;
+    uint64_t acc = 0;
+    if (tr | ta) {
+        for (int j = 0; j < BPL; ++j) {
+            const uint32_t hr = hist_get<CT>(ref_slot, b0 + j), ha = hist_get<CT>(alt_slot, b0 + j);
+            const int v = lane * BPL + j;
+            if (ha) acc += (uint64_t)ha * (uint64_t)(2u * (cr + ca) + hr + ha + 1u);
+            if (hr) {
+                if (r1 >= cr && r1 < cr + hr) vr1 = v;
+                if (r2 >= cr && r2 < cr + hr) vr2 = v;
+            }
+            if (ha) {
+                if (a1 >= ca && a1 < ca + ha) va1 = v;
+                if (a2 >= ca && a2 < ca + ha) va2 = v;
+            }
+            cr += hr;
+            ca += ha;
+        }
+    }
+    s2 = na ? warp_sum_u64(acc) : 0;
+    if (nr) {
+        vr1 = __reduce_max_sync(FULL, vr1);
+        vr2 = __reduce_max_sync(FULL, vr2);
+        med2_ref = vr1 + vr2;
+    } else {
+        med2_ref = -1;
+    }
+    if (na) {
+        va1 = __reduce_max_sync(FULL, va1);
+        va2 = __reduce_max_sync(FULL, va2);
+        med2_alt = va1 + va2;
+    } else {
+        med2_alt = -1;
+    }
+}
+
+__device__ __forceinline__ void store_counts(vfk_counts *out, int dp, int n_amb, int ac_ref, int ac_alt,
+                                             const int med2[3][2], const uint64_t s2[3], uint32_t status, uint32_t n_cand) {
+    uint4 *o = reinterpret_cast<uint4 *>(out);
+    o[0] = make_uint4((uint32_t)dp, (uint32_t)n_amb, (uint32_t)ac_ref, (uint32_t)ac_alt);
+    o[1] = make_uint4((uint32_t)med2[0][0], (uint32_t)med2[0][1], (uint32_t)med2[1][0], (uint32_t)med2[1][1]);
+    o[2] = make_uint4((uint32_t)med2[2][0], (uint32_t)med2[2][1], status, n_cand);
+    o[3] = make_uint4((uint32_t)s2[0], (uint32_t)(s2[0] >> 32), (uint32_t)s2[1], (uint32_t)(s2[1] >> 32));
+    o[4] = make_uint4((uint32_t)s2[2], (uint32_t)(s2[2] >> 32), 0u, 0u);
+}
+
+template <typename CT, int POSB>
+__device__ __forceinline__ void accumulate(uint32_t *ref_slot, uint32_t *alt_slot, const Contribution &c, bool with_bq,
+                                           uint32_t &status) {
+    using L = Layout<POSB>;
+    if (!(c.ref || c.alt)) return;
+    const bool pos_ok = c.qpos < POSB;
+    if (!pos_ok) status |= VFK_ST_READLEN;
+    if (c.ref) {
+        hist_add<CT>(ref_slot, L::MQ_OFF + c.mq, 1u);
+        if (with_bq) hist_add<CT>(ref_slot, L::BQ_OFF + c.bq, 1u);
+        if (pos_ok) hist_add<CT>(ref_slot, L::POS_OFF + c.qpos, 1u);
+    }
+    if (c.alt) {
+        hist_add<CT>(alt_slot, L::MQ_OFF + c.mq, c.alt);
+        if (with_bq) hist_add<CT>(alt_slot, L::BQ_OFF + c.bq, c.alt);
+        if (pos_ok) hist_add<CT>(alt_slot, L::POS_OFF + c.qpos, c.alt);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// warp per unit
+// ------------------------------------------------------------------------------------------
+template <int POSB>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+pileup_warp_kernel(ReadsDev R, UnitsDev V, vfk_params P, vfk_counts *__restrict__ out,
+                   unsigned long long *__restrict__ work_counter, uint32_t *__restrict__ deferred,
+                   uint32_t *__restrict__ n_deferred) {
+    using L = Layout<POSB>;
+    constexpr int WORDS = L::BINS / 2;  // u16 bins
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *ref_slot = smem + (size_t)warp * 2 * WORDS;
+    uint32_t *alt_slot = ref_slot + WORDS;
+
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(work_counter, (unsigned long long)GRAB);
+        base = __shfl_sync(FULL, base, 0);
+        if ((int64_t)base >= V.n) break;
+        const int64_t end = min((int64_t)base + GRAB, V.n);
+        for (int64_t u = (int64_t)base; u < end; ++u) {
+            Unit U;
+            load_unit(R, V, u, U);
+            warp_locate(R, U, lane);
+            const int64_t n_cand = U.hi - U.lo;
+            int med2[3][2] = {{-1, -1}, {-1, -1}, {-1, -1}};
+            uint64_t s2[3] = {0, 0, 0};
+            if (n_cand == 0) {
+                if (lane == 0) store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind, 0u);
+                continue;
+            }
+            if (n_cand > WARP_PATH_MAX_CAND) {
+                if (lane == 0) {
+                    deferred[atomicAdd(n_deferred, 1u)] = (uint32_t)u;
+                    store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind | VFK_ST_DEFERRED, (uint32_t)n_cand);
+                }
+                continue;
+            }
+            // clear this warp's histograms
+            {
+                uint4 *z = reinterpret_cast<uint4 *>(ref_slot);
+                for (int w = lane; w < (2 * WORDS) / 4; w += 32) z[w] = make_uint4(0, 0, 0, 0);
+            }
+            __syncwarp();
+            int dp = 0, n_amb = 0, ac_ref = 0, ac_alt = 0;
+            uint32_t status = U.kind;
+            const bool with_bq = U.kind == VFK_KIND_SNV;
+            for (int64_t b = U.lo; b < U.hi; b += 32) {
+                const int64_t i = b + lane;
+                if (i < U.hi) {
+                    const Contribution c = evaluate(R, P, U, i);
+                    dp += c.in_dp ? 1 : 0;
+                    n_amb += c.ambiguous ? 1 : 0;
+                    ac_ref += c.ref ? 1 : 0;
+                    ac_alt += (int)c.alt;
+                    accumulate<uint16_t, POSB>(ref_slot, alt_slot, c, with_bq, status);
+                }
+            }
+            __syncwarp();
+            dp = __reduce_add_sync(FULL, dp);
+            n_amb = __reduce_add_sync(FULL, n_amb);
+            ac_ref = __reduce_add_sync(FULL, ac_ref);
+            ac_alt = __reduce_add_sync(FULL, ac_alt);
+            status = __reduce_or_sync(FULL, status);
+            if (ac_ref | ac_alt) {
+                reduce_metric<uint16_t, 256>(ref_slot, alt_slot, L::MQ_OFF, lane, med2[0][0], med2[0][1], s2[0]);
+                if (with_bq) reduce_metric<uint16_t, 256>(ref_slot, alt_slot, L::BQ_OFF, lane, med2[1][0], med2[1][1], s2[1]);
+                reduce_metric<uint16_t, POSB>(ref_slot, alt_slot, L::POS_OFF, lane, med2[2][0], med2[2][1], s2[2]);
+            }
+            if (U.kind == VFK_KIND_SNV && !P.include_ambiguous) dp -= n_amb;  // pileups.py:224-227
+            if (lane == 0) store_counts(out + u, dp, n_amb, ac_ref, ac_alt, med2, s2, status, (uint32_t)n_cand);
+            __syncwarp();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// CTA per unit, u32 counters: columns deeper than the warp path's u16 bins allow
+// ------------------------------------------------------------------------------------------
+template <int POSB>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+pileup_block_kernel(ReadsDev R, UnitsDev V, vfk_params P, vfk_counts *__restrict__ out,
+                    const uint32_t *__restrict__ deferred, const uint32_t *__restrict__ n_deferred) {
+    using L = Layout<POSB>;
+    constexpr int WORDS = L::BINS;  // u32 bins
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ int red[4];
+    __shared__ uint32_t red_status;
+    __shared__ int s_med2[3][2];
+    __shared__ unsigned long long s_s2[3];
+    uint32_t *ref_slot = smem, *alt_slot = smem + WORDS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nd = *n_deferred;
+    for (uint32_t d = blockIdx.x; d < nd; d += gridDim.x) {
+        const int64_t u = deferred[d];
+        Unit U;
+        load_unit(R, V, u, U);
+        warp_locate(R, U, lane);  // every warp locates for itself (same result)
+        for (int w = threadIdx.x; w < 2 * WORDS; w += blockDim.x) smem[w] = 0u;
+        if (threadIdx.x < 4) red[threadIdx.x] = 0;
+        if (threadIdx.x == 0) red_status = U.kind;
+        if (threadIdx.x < 6) s_med2[threadIdx.x >> 1][threadIdx.x & 1] = -1;
+        if (threadIdx.x < 3) s_s2[threadIdx.x] = 0ull;
+        __syncthreads();
+        int dp = 0, n_amb = 0, ac_ref = 0, ac_alt = 0;
+        uint32_t status = U.kind;
+        const bool with_bq = U.kind == VFK_KIND_SNV;
+        for (int64_t i = U.lo + threadIdx.x; i < U.hi; i += blockDim.x) {
+            const Contribution c = evaluate(R, P, U, i);
+            dp += c.in_dp ? 1 : 0;
+            n_amb += c.ambiguous ? 1 : 0;
+            ac_ref += c.ref ? 1 : 0;
+            ac_alt += (int)c.alt;
+            accumulate<uint32_t, POSB>(ref_slot, alt_slot, c, with_bq, status);
+        }
+        dp = __reduce_add_sync(FULL, dp);
+        n_amb = __reduce_add_sync(FULL, n_amb);
+        ac_ref = __reduce_add_sync(FULL, ac_ref);
+        ac_alt = __reduce_add_sync(FULL, ac_alt);
+        status = __reduce_or_sync(FULL, status);
+        if (lane == 0) {
+            atomicAdd(&red[0], dp); atomicAdd(&red[1], n_amb); atomicAdd(&red[2], ac_ref); atomicAdd(&red[3], ac_alt);
+            atomicOr(&red_status, status);
+        }
+        __syncthreads();
+        if (red[2] | red[3]) {  // warps 0..2 reduce one metric each
+            int m0 = -1, m1 = -1;
+            uint64_t s = 0;
+            if (warp == 0) reduce_metric<uint32_t, 256>(ref_slot, alt_slot, L::MQ_OFF, lane, m0, m1, s);
+            else if (warp == 1 && with_bq) reduce_metric<uint32_t, 256>(ref_slot, alt_slot, L::BQ_OFF, lane, m0, m1, s);
+            else if (warp == 2) reduce_metric<uint32_t, POSB>(ref_slot, alt_slot, L::POS_OFF, lane, m0, m1, s);
+            if (warp < 3 && lane == 0) { s_med2[warp][0] = m0; s_med2[warp][1] = m1; s_s2[warp] = s; }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int med2[3][2];
+            uint64_t s2[3];
+            for (int m = 0; m < 3; ++m) { med2[m][0] = s_med2[m][0]; med2[m][1] = s_med2[m][1]; s2[m] = s_s2[m]; }
+            int d_p = red[0];
+            if (U.kind == VFK_KIND_SNV && !P.include_ambiguous) d_p -= red[1];
+            store_counts(out + u, d_p, red[1], red[2], red[3], med2, s2, red_status, (uint32_t)(U.hi - U.lo));
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side launchers (called from vfk_api.cu)
+// ------------------------------------------------------------------------------------------
+template <int POSB>
+static cudaError_t launch_posb(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, vfk_counts *out,
+                               unsigned long long *work_counter, uint32_t *deferred, uint32_t *n_deferred, int sm_count,
+                               cudaStream_t stream, int *launches) {
+    using L = Layout<POSB>;
+    const size_t smem_warp = (size_t)WARPS_PER_CTA * 2 * (L::BINS / 2) * sizeof(uint32_t);
+    const size_t smem_block = (size_t)2 * L::BINS * sizeof(uint32_t);
+    cudaError_t e;
+    if (smem_warp > 48 * 1024) {  // opt in to large dynamic shared memory (long-read instantiation only)
+        e = cudaFuncSetAttribute(pileup_warp_kernel<POSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_warp);
+        if (e != cudaSuccess) return e;
+    }
+    int ctas_per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pileup_warp_kernel<POSB>, WARPS_PER_CTA * 32, smem_warp);
+    if (e != cudaSuccess) return e;
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    // persistent grid: a whole number of waves, never more CTAs than there is work
+    int64_t want = (V.n + (int64_t)GRAB * WARPS_PER_CTA - 1) / ((int64_t)GRAB * WARPS_PER_CTA);
+    int64_t grid = (int64_t)sm_count * ctas_per_sm;
+    if (want < grid) grid = want < 1 ? 1 : want;
+    e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(n_deferred, 0, sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
+    pileup_warp_kernel<POSB><<<(unsigned)grid, WARPS_PER_CTA * 32, smem_warp, stream>>>(R, V, P, out, work_counter, deferred, n_deferred);
+    ++*launches;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (R.n_reads > WARP_PATH_MAX_CAND) {  // only then can a column be too deep for the warp path
+        pileup_block_kernel<POSB><<<(unsigned)sm_count, WARPS_PER_CTA * 32, smem_block, stream>>>(R, V, P, out, deferred, n_deferred);
+        ++*launches;
+        e = cudaGetLastError();
+    }
+    return e;
+}
+
+cudaError_t launch_pileup(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, int max_l_qseq, vfk_counts *out,
+                          unsigned long long *work_counter, uint32_t *deferred, uint32_t *n_deferred, int sm_count,
+                          cudaStream_t stream, int *launches) {
+    // read positions run 0 .. l_qseq (a read hanging in a trailing deletion reports l_qseq)
+    if (max_l_qseq < 256) return launch_posb<256>(R, V, P, out, work_counter, deferred, n_deferred, sm_count, stream, launches);
+    if (max_l_qseq < 512) return launch_posb<512>(R, V, P, out, work_counter, deferred, n_deferred, sm_count, stream, launches);
+    if (max_l_qseq < 1024) return launch_posb<1024>(R, V, P, out, work_counter, deferred, n_deferred, sm_count, stream, launches);
+    return launch_posb<4096>(R, V, P, out, work_counter, deferred, n_deferred, sm_count, stream, launches);
+}
+
+}  // namespace vfk

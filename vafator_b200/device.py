@@ -1,0 +1,339 @@
+"""ctypes binding of the C ABI (include/vfk.h, include/vfk_io.h).
+
+torch is used for what it is good at here -- device memory, pinned host memory and streams --
+and nothing else: every computation happens inside libvfk.so.  There is NO CPU fallback: if the
+CUDA library is missing or no device is present the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import build as _build
+from .batch import ReadBatch, VariantUnits
+
+NO_MATE = 0xFFFFFFFF
+
+COUNTS_DTYPE = np.dtype([("dp", "<i4"), ("n_amb", "<i4"), ("ac_ref", "<i4"), ("ac_alt", "<i4"),
+                         ("med2", "<i4", (3, 2)), ("status", "<u4"), ("n_cand", "<u4"), ("s2", "<u8", (3,)),
+                         ("reserved", "<u8")])
+STATS_DTYPE = np.dtype([("z", "<f8", (3,)), ("p", "<f8", (3,)), ("pu", "<f8"), ("pw", "<f8"), ("k", "<i4"),
+                        ("pad", "<i4")])
+HOT_DTYPE = np.dtype([("pos", "<i4"), ("span", "<u4"), ("fmk", "<u4"), ("pay", "<u4")])
+COLD_DTYPE = np.dtype([("cigar_off", "<u4"), ("n_cigar", "<u4"), ("l_qseq", "<u4"), ("reserved", "<u4")])
+assert COUNTS_DTYPE.itemsize == 80 and STATS_DTYPE.itemsize == 72
+
+ST_KIND_MASK, ST_DEFERRED, ST_READLEN = 0x3, 0x10, 0x20
+
+
+class VfkError(RuntimeError):
+    pass
+
+
+class _ReadBatchC(C.Structure):
+    _fields_ = [("n_reads", C.c_int64), ("n_contigs", C.c_int32), ("max_l_qseq", C.c_int32),
+                ("contig_off", C.c_void_p), ("hot", C.c_void_p), ("cold", C.c_void_p), ("mate", C.c_void_p),
+                ("starts", C.c_void_p), ("pmax_end", C.c_void_p), ("cigar", C.c_void_p), ("payload", C.c_void_p),
+                ("n_cigar_words", C.c_int64), ("n_sectors", C.c_int64)]
+
+
+class _VariantBatchC(C.Structure):
+    _fields_ = [("n_units", C.c_int64), ("tid", C.c_void_p), ("pos", C.c_void_p), ("meta", C.c_void_p),
+                ("length", C.c_void_p), ("seq_off", C.c_void_p), ("ins_seq", C.c_void_p), ("stop", C.c_void_p),
+                ("n_ins_seq", C.c_int64)]
+
+
+class ParamsC(C.Structure):
+    _fields_ = [("min_mapq", C.c_int32), ("min_baseq", C.c_int32), ("flag_filter", C.c_uint32),
+                ("ignore_orphans", C.c_int32), ("ignore_overlaps", C.c_int32), ("include_ambiguous", C.c_int32)]
+
+
+def make_params(min_mapq=0, min_baseq=29, include_ambiguous=True, flag_filter=0x704, ignore_orphans=True,
+                ignore_overlaps=True) -> ParamsC:
+    """Defaults: Annotator class defaults (vafator/annotator.py:76-77) + pysam 0.21.0 pileup defaults."""
+    return ParamsC(int(min_mapq), int(min_baseq), int(flag_filter), int(bool(ignore_orphans)),
+                   int(bool(ignore_overlaps)), int(bool(include_ambiguous)))
+
+
+class _IoReadsC(C.Structure):
+    _fields_ = [("n", C.c_int64), ("n_contigs", C.c_int32), ("pad", C.c_int32)] + [(k, C.c_void_p) for k in (
+        "tid", "pos", "flag", "mapq", "l_qseq", "n_cigar", "cigar_off", "seq_off", "qual_off", "cigar", "seq", "qual",
+        "mtid", "mpos", "isize", "qname_id", "qname_hash")]
+
+
+class _PlanC(C.Structure):
+    _fields_ = [("n_placed", C.c_int64), ("n_cigar_words", C.c_int64), ("n_sectors", C.c_int64),
+                ("max_l_qseq", C.c_int32), ("pad", C.c_int32)]
+
+
+_IO_DT = dict(tid=np.int32, pos=np.int32, flag=np.uint16, mapq=np.uint8, l_qseq=np.int32, n_cigar=np.int32,
+              cigar_off=np.int64, seq_off=np.int64, qual_off=np.int64, cigar=np.uint32, seq=np.uint8, qual=np.uint8,
+              mtid=np.int32, mpos=np.int32, isize=np.int32, qname_id=np.uint64, qname_hash=np.uint32)
+
+_libio = None
+_libvfk = None
+
+
+def libio():
+    """libvfkio.so (host companion).  Built in-tree on first use."""
+    global _libio
+    if _libio is None:
+        path = _build.LIBVFKIO if os.path.exists(_build.LIBVFKIO) and not os.environ.get("VFK_REBUILD") else _build.build_host()
+        lib = C.CDLL(path)
+        lib.vfkio_last_error.restype = C.c_char_p
+        _libio = lib
+    return _libio
+
+
+def libvfk():
+    """libvfk.so (CUDA).  Raises if it cannot be loaded -- there is no fallback path."""
+    global _libvfk
+    if _libvfk is None:
+        path = _build.LIBVFK
+        if not os.path.exists(path):
+            path = _build.build_cuda()
+        try:
+            lib = C.CDLL(path)
+        except OSError as e:  # pragma: no cover
+            raise VfkError("cannot load the CUDA library %s: %s" % (path, e))
+        lib.vfk_last_error.restype = C.c_char_p
+        lib.vfk_launch_count.restype = C.c_int64
+        lib.vfk_launch_count.argtypes = [C.c_void_p]
+        lib.vfk_epilogue.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
+                                     C.c_void_p, C.c_void_p]
+        lib.vfk_pileup.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.vfk_annotate_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+                                          C.c_double, C.c_void_p, C.c_void_p]
+        _libvfk = lib
+    return _libvfk
+
+
+def _io_check(rc: int):
+    if rc != 0:
+        raise ValueError("vfkio: %s" % libio().vfkio_last_error().decode())
+
+
+def _check(rc: int):
+    if rc != 0:
+        msg = libvfk().vfk_last_error().decode()
+        if rc == -1:
+            raise ValueError("vfk: %s" % msg)
+        raise VfkError("vfk error %d: %s" % (rc, msg))
+
+
+def _io_reads(batch: ReadBatch):
+    keep = {k: np.ascontiguousarray(getattr(batch, k), dtype=dt) for k, dt in _IO_DT.items()}
+    s = _IoReadsC()
+    s.n = batch.n_reads
+    s.n_contigs = len(batch.contigs)
+    for k, a in keep.items():
+        setattr(s, k, a.ctypes.data)
+    return s, keep
+
+
+def _empty(n, dtype, pinned: bool):
+    """Host array; pinned (page-locked) through torch when asked and a device is present."""
+    if pinned:
+        import torch
+        if torch.cuda.is_available():
+            t = torch.empty(max(int(n), 1) * np.dtype(dtype).itemsize, dtype=torch.uint8, pin_memory=True)
+            a = t.numpy().view(dtype)[:n]
+            return a
+    return np.empty(n, dtype)
+
+
+@dataclass
+class PackedReads:
+    """Host copy of the HBM layout (include/vfk.h vfk_read_batch)."""
+    contigs: list
+    contig_off: np.ndarray
+    hot: np.ndarray
+    cold: np.ndarray
+    mate: np.ndarray
+    starts: np.ndarray
+    pmax_end: np.ndarray
+    cigar: np.ndarray
+    payload: np.ndarray
+    max_l_qseq: int
+
+    @property
+    def n_reads(self):
+        return int(self.hot.shape[0])
+
+    def nbytes(self) -> int:
+        return int(sum(a.nbytes for a in (self.contig_off, self.hot, self.cold, self.mate, self.starts,
+                                          self.pmax_end, self.cigar, self.payload)))
+
+    def c_struct(self, arrays: Optional[Dict[str, int]] = None) -> _ReadBatchC:
+        p = arrays or {k: getattr(self, k).ctypes.data for k in
+                       ("contig_off", "hot", "cold", "mate", "starts", "pmax_end", "cigar", "payload")}
+        s = _ReadBatchC()
+        s.n_reads, s.n_contigs, s.max_l_qseq = self.n_reads, len(self.contigs), self.max_l_qseq
+        s.n_cigar_words, s.n_sectors = int(self.cigar.shape[0]), int(self.payload.shape[0] // 32)
+        for k, v in p.items():
+            setattr(s, k, v)
+        return s
+
+
+def link_mates(batch: ReadBatch, params: ParamsC) -> np.ndarray:
+    s, keep = _io_reads(batch)
+    n_placed = int(np.count_nonzero(batch.tid >= 0))
+    mate = np.empty(n_placed, np.uint32)
+    _io_check(libio().vfkio_link_mates(C.byref(s), C.byref(params), C.c_void_p(mate.ctypes.data)))
+    return mate
+
+
+def pack_reads(batch: ReadBatch, params: ParamsC, pinned: bool = False) -> PackedReads:
+    """Canonical batch -> HBM layout (+ mate links under `params`)."""
+    s, keep = _io_reads(batch)
+    plan = _PlanC()
+    _io_check(libio().vfkio_pack_plan(C.byref(s), C.byref(plan)))
+    n = plan.n_placed
+    contig_off = np.empty(len(batch.contigs) + 1, np.int64)
+    hot = _empty(n, HOT_DTYPE, pinned)
+    cold = _empty(n, COLD_DTYPE, pinned)
+    starts = _empty(n, np.int32, pinned)
+    pmax = _empty(n, np.int32, pinned)
+    cigar = _empty(max(plan.n_cigar_words, 1), np.uint32, pinned)[:plan.n_cigar_words]
+    payload = _empty(plan.n_sectors * 32, np.uint8, pinned)
+    _io_check(libio().vfkio_pack(C.byref(s), C.byref(plan), C.c_void_p(contig_off.ctypes.data),
+                                 C.c_void_p(hot.ctypes.data), C.c_void_p(cold.ctypes.data),
+                                 C.c_void_p(starts.ctypes.data), C.c_void_p(pmax.ctypes.data),
+                                 C.c_void_p(cigar.ctypes.data), C.c_void_p(payload.ctypes.data)))
+    mate = _empty(n, np.uint32, pinned)
+    _io_check(libio().vfkio_link_mates(C.byref(s), C.byref(params), C.c_void_p(mate.ctypes.data)))
+    return PackedReads(list(batch.contigs), contig_off, hot, cold, mate, starts, pmax, cigar, payload,
+                       int(plan.max_l_qseq))
+
+
+def units_c_struct(u: VariantUnits, stop: Optional[np.ndarray], ptrs: Optional[Dict[str, int]] = None) -> _VariantBatchC:
+    s = _VariantBatchC()
+    s.n_units = u.n_units
+    s.n_ins_seq = int(u.ins_seq.shape[0])
+    if ptrs is None:
+        ptrs = dict(tid=u.tid.ctypes.data, pos=u.pos.ctypes.data, meta=u.meta.ctypes.data,
+                    length=u.length.ctypes.data, seq_off=u.seq_off.ctypes.data, ins_seq=u.ins_seq.ctypes.data,
+                    stop=stop.ctypes.data if stop is not None else None)
+    for k, v in ptrs.items():
+        setattr(s, k, v)
+    return s
+
+
+class DeviceReads:
+    """A read batch resident in HBM (torch tensors own the memory)."""
+
+    def __init__(self, packed: PackedReads, device, non_blocking: bool = True):
+        import torch
+        self.packed = packed
+        self.t = {}
+        for k in ("contig_off", "hot", "cold", "mate", "starts", "pmax_end", "cigar", "payload"):
+            a = getattr(packed, k)
+            h = torch.from_numpy(a.view(np.uint8).reshape(-1)) if a.size else torch.zeros(16, dtype=torch.uint8)
+            self.t[k] = h.to(device, non_blocking=non_blocking) if a.size else h.to(device)
+        self.c = packed.c_struct({k: v.data_ptr() for k, v in self.t.items()})
+
+    def nbytes(self):
+        return self.packed.nbytes()
+
+
+class DeviceUnits:
+    def __init__(self, units: VariantUnits, stop: Optional[np.ndarray], device):
+        import torch
+        self.units = units
+        self.t = {}
+        src = dict(tid=units.tid, pos=units.pos, meta=units.meta, length=units.length, seq_off=units.seq_off,
+                   ins_seq=units.ins_seq)
+        if stop is not None:
+            src["stop"] = np.ascontiguousarray(stop, np.int32)
+        for k, a in src.items():
+            h = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)) if a.size else torch.zeros(16, dtype=torch.uint8)
+            self.t[k] = h.to(device)
+        ptrs = {k: v.data_ptr() for k, v in self.t.items()}
+        ptrs.setdefault("stop", None)
+        self.c = units_c_struct(units, stop, ptrs)
+        self.n_units = units.n_units
+
+
+class Device:
+    """One vfk_handle on one GPU."""
+
+    def __init__(self, index: int = 0):
+        import torch
+        if not torch.cuda.is_available():
+            raise VfkError("no CUDA device: vafator_b200 has no CPU path")
+        self.torch = torch
+        self.index = index
+        self.device = torch.device("cuda", index)
+        self.lib = libvfk()
+        h = C.c_void_p()
+        _check(self.lib.vfk_create(C.c_int(index), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.lib.vfk_destroy(self.h)
+            self.h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def launch_count(self) -> int:
+        return int(self.lib.vfk_launch_count(self.h))
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def upload_reads(self, packed: PackedReads) -> DeviceReads:
+        return DeviceReads(packed, self.device)
+
+    def upload_units(self, units: VariantUnits, stop: Optional[np.ndarray] = None) -> DeviceUnits:
+        return DeviceUnits(units, stop, self.device)
+
+    def alloc_counts(self, n):
+        return self.torch.empty(max(n, 1) * COUNTS_DTYPE.itemsize, dtype=self.torch.uint8, device=self.device)
+
+    def alloc_stats(self, n):
+        return self.torch.empty(max(n, 1) * STATS_DTYPE.itemsize, dtype=self.torch.uint8, device=self.device)
+
+    def pileup(self, reads: DeviceReads, units: DeviceUnits, params: ParamsC, out=None):
+        """Enqueue the pileup kernel on torch's current stream; returns the device counts buffer."""
+        if out is None:
+            out = self.alloc_counts(units.n_units)
+        _check(self.lib.vfk_pileup(self.h, C.byref(reads.c), C.byref(units.c), C.byref(params),
+                                   C.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    def epilogue(self, n_units: int, counts, eaf, fpr: float, error_rate: float, out=None):
+        if out is None:
+            out = self.alloc_stats(n_units)
+        _check(self.lib.vfk_epilogue(self.h, n_units, C.c_void_p(counts.data_ptr()), C.c_void_p(eaf.data_ptr()),
+                                     float(fpr), float(error_rate), C.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    def annotate_host(self, packed: PackedReads, units: VariantUnits, stop, params: ParamsC, eaf: np.ndarray,
+                      fpr: float, error_rate: float, counts_out=None, stats_out=None):
+        """HOST buffers in, HOST results out (copies inside): the end-to-end entry point."""
+        n = units.n_units
+        counts = counts_out if counts_out is not None else np.empty(n, COUNTS_DTYPE)
+        stats = stats_out if stats_out is not None else np.empty(n, STATS_DTYPE)
+        eaf = np.ascontiguousarray(eaf, np.float64)
+        rc = packed.c_struct()
+        stop = None if stop is None else np.ascontiguousarray(stop, np.int32)
+        uc = units_c_struct(units, stop)
+        _check(self.lib.vfk_annotate_host(self.h, C.byref(rc), C.byref(uc), C.byref(params),
+                                          C.c_void_p(eaf.ctypes.data), float(fpr), float(error_rate),
+                                          C.c_void_p(counts.ctypes.data), C.c_void_p(stats.ctypes.data)))
+        return counts, stats
+
+    def to_host(self, buf, dtype, n):
+        return buf.cpu().numpy().view(dtype)[:n].copy()
+
+    def sync(self):
+        _check(self.lib.vfk_sync(self.h))
