@@ -120,7 +120,8 @@ typedef struct {
     uint32_t status;
     uint32_t n_cand;    /* candidate reads inspected                                              */
     uint64_t s2[3];     /* [mq,bq,pos]: twice the sum of the ALT mid-ranks in the pooled ranking   */
-    uint64_t reserved;
+    uint32_t n_cover;   /* reads overlapping the column before any filter (D_raw of SURVEY.md 8d)   */
+    uint32_t reserved;
 } vfk_counts; /* 80 bytes */
 
 /* ---- epilogue output: FP64, unrounded ------------------------------------------------------ */

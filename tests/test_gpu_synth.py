@@ -1,0 +1,136 @@
+"""GPU vs the C oracle on seeded synthetic batches (sizes the oracle finishes in seconds), plus
+size-independent properties of the path: idempotence, unit-order invariance, shard invariance."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle
+from vafator_b200 import device, synth
+from vafator_b200.batch import build_units
+
+pytestmark = pytest.mark.gpu
+
+INT_FIELDS = ("dp", "n_amb", "ac_ref", "ac_alt")
+
+
+@pytest.fixture(scope="module")
+def dev():
+    d = device.Device(0)
+    yield d
+    d.close()
+
+
+def _setup(cfg):
+    batch = synth.reads(cfg)
+    recs = synth.variant_records(cfg)
+    units = build_units(recs, cfg.contigs)
+    last = {}
+    for c, p, r, a in recs:
+        last[c] = p
+    stop = np.asarray([last[recs[i][0]] for i in units.rec], np.int32)
+    tid_of = {c: i for i, c in enumerate(cfg.contigs)}
+    ounits = [(tid_of[recs[i][0]], recs[i][1], recs[i][2], recs[i][3][j], recs[i][3][0], last[recs[i][0]])
+              for i, j in zip(units.rec, units.alt_index)]
+    return batch, recs, units, stop, ounits
+
+
+def _gpu(dev, batch, units, stop, mq, bq, amb=True):
+    params = device.make_params(min_mapq=mq, min_baseq=bq, include_ambiguous=amb)
+    dreads = dev.upload_reads(device.pack_reads(batch, params))
+    buf = dev.pileup(dreads, dev.upload_units(units, stop), params)
+    dev.sync()
+    return dev.to_host(buf, device.COUNTS_DTYPE, units.n_units)
+
+
+def _compare(got, want, amb=True):
+    assert np.all(want["supported"] == 1)
+    assert int((got["status"] & (device.ST_DEFERRED | device.ST_READLEN)).max()) == 0
+    dp = want["dp"] if amb else want["dp"] - np.where((got["status"] & 3) == 0, want["n_amb"], 0)
+    assert np.array_equal(got["dp"], dp)
+    for f in ("n_amb", "ac_ref", "ac_alt"):
+        assert np.array_equal(got[f], want[f]), f
+    assert np.array_equal(got["med2"], want["med2"])
+    both = (want["ac_ref"] > 0) & (want["ac_alt"] > 0)
+    snv = (got["status"] & 3) == 0
+    assert np.array_equal(got["s2"][both][:, [0, 2]], want["s2"][both][:, [0, 2]])
+    assert np.array_equal(got["s2"][both & snv][:, 1], want["s2"][both & snv][:, 1])
+
+
+CASES = {
+    "wes": (lambda: synth.wes(n_tiles=3000), [(1, 30), (0, 0), (20, 13)]),
+    "wgs_indels": (lambda: synth.wgs(contig_len=1_500_000, n_contigs=2, multiallelic_pct=5), [(1, 30), (0, 0)]),
+    "amplicon_1000x": (lambda: synth.amplicon(n_tiles=24, depth_pairs=900), [(1, 30), (0, 20)]),
+    "noisy_cigars": (lambda: synth.wes(n_tiles=1500, indel_period=40, snv_period=30, multiallelic_pct=20, p_softclip=0.2,
+                                       p_del=0.15, p_ins=0.15, p_skip=0.05, p_supp=0.05, p_orphan=0.05, p_n=0.02,
+                                       frag_mean=200.0, frag_sd=40.0), [(1, 30), (0, 0), (0, 41)]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_gpu_matches_c_oracle(dev, name):
+    make, thresholds = CASES[name]
+    batch, recs, units, stop, ounits = _setup(make())
+    assert units.n_units > 100
+    for mq, bq in thresholds:
+        want = c_oracle.pileup(batch.as_dict(), ounits, c_oracle.params(min_mapq=mq, min_baseq=bq))
+        _compare(_gpu(dev, batch, units, stop, mq, bq), want)
+    want = c_oracle.pileup(batch.as_dict(), ounits, c_oracle.params(min_mapq=1, min_baseq=30))
+    _compare(_gpu(dev, batch, units, stop, 1, 30, amb=False), want, amb=False)
+    assert want["ac_alt"].sum() > 0 and want["n_amb"].sum() >= 0
+
+
+def test_deep_column_block_path(dev):
+    """Columns deeper than the warp path's u16 bins (> 32767 candidate reads) take the CTA-per-unit kernel."""
+    cfg = synth.amplicon(n_tiles=2, depth_pairs=30000, snv_period=60, indel_period=120)
+    batch, recs, units, stop, ounits = _setup(cfg)
+    got = _gpu(dev, batch, units, stop, 1, 30)
+    assert int(got["n_cand"].max()) > 32767
+    want = c_oracle.pileup(batch.as_dict(), ounits, c_oracle.params(min_mapq=1, min_baseq=30))
+    _compare(got, want)
+
+
+def test_properties_at_scale(dev):
+    """A full-size-like batch (1.4 M reads): the result does not depend on the order or grouping of units,
+    and a second launch reproduces it bit for bit."""
+    cfg = synth.wes(n_tiles=20_000, indel_period=3000)
+    batch = synth.reads(cfg)
+    recs = synth.variant_records(cfg)
+    units = build_units(recs, cfg.contigs)
+    params = device.make_params(min_mapq=1, min_baseq=30)
+    dreads = dev.upload_reads(device.pack_reads(batch, params))
+    def run(u):
+        buf = dev.pileup(dreads, dev.upload_units(u, None), params)
+        dev.sync()
+        return dev.to_host(buf, device.COUNTS_DTYPE, u.n_units)
+    a, b = run(units), run(units)
+    assert a.tobytes() == b.tobytes()
+    rng = np.random.default_rng(7)
+    perm = rng.permutation(units.n_units)
+    from dataclasses import replace
+    pu = replace(units, tid=units.tid[perm], pos=units.pos[perm], meta=units.meta[perm], length=units.length[perm],
+                 seq_off=units.seq_off[perm], rec=units.rec[perm], alt_index=units.alt_index[perm])
+    c = run(pu)
+    assert c.tobytes() == a[perm].tobytes()
+    half = units.n_units // 2
+    first = replace(units, tid=units.tid[:half], pos=units.pos[:half], meta=units.meta[:half], length=units.length[:half],
+                    seq_off=units.seq_off[:half], rec=units.rec[:half], alt_index=units.alt_index[:half])
+    assert run(first).tobytes() == a[:half].tobytes()
+    # depth sanity: dp <= reads covering the column <= candidates inspected
+    assert np.all(a["dp"] <= a["n_cover"]) and np.all(a["n_cover"] <= a["n_cand"])
+    assert np.all(a["ac_ref"] + a["ac_alt"] <= a["dp"] + (a["status"] & 3 != 0) * a["dp"])
+
+
+def test_error_paths(dev):
+    cfg = synth.wes(n_tiles=1100)
+    batch = synth.reads(cfg)
+    with pytest.raises(ValueError):
+        build_units([("nope", 5, "A", ["T"])], cfg.contigs)
+    bad = synth.reads(cfg)
+    bad.pos = bad.pos[::-1].copy()
+    with pytest.raises(ValueError):
+        device.pack_reads(bad, device.make_params())
+    # empty unit list and empty read batch are fine
+    units = build_units([], cfg.contigs)
+    params = device.make_params()
+    dreads = dev.upload_reads(device.pack_reads(batch, params))
+    dev.pileup(dreads, dev.upload_units(units, None), params)
+    dev.sync()

@@ -55,6 +55,7 @@ struct Unit {
 
 // one read's contribution to a column
 struct Contribution {
+    bool covers;   // the read spans the column (before any filter)
     bool in_dp;
     bool ambiguous;
     bool ref;      // value goes to the REF list
@@ -318,10 +319,11 @@ __device__ __forceinline__ uint32_t deletion_hits(const ReadsDev &R, const uint4
 // Everything one read contributes to one unit.
 __device__ __forceinline__ Contribution evaluate(const ReadsDev &R, const vfk_params &P, const Unit &U, int64_t i) {
     Contribution o;
-    o.in_dp = false; o.ambiguous = false; o.ref = false; o.alt = 0; o.mq = 0; o.bq = 0; o.qpos = 0; o.pos_overflow = false;
+    o.covers = false; o.in_dp = false; o.ambiguous = false; o.ref = false; o.alt = 0; o.mq = 0; o.bq = 0; o.qpos = 0; o.pos_overflow = false;
     const uint4 hot = __ldg(R.hot + i);
     const int32_t rpos = (int32_t)hot.x;
     if (U.col < rpos || U.col >= rpos + (int32_t)hot.y) return o;
+    o.covers = true;
     if (!read_passes(hot.z, P)) return o;
     const bool general = (hot.z >> 24) != 0u;
     uint4 cold = make_uint4(0, 0, 0, 0);

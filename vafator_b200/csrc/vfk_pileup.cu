@@ -109,13 +109,14 @@ __device__ __forceinline__ void reduce_metric(const uint32_t *ref_slot, const ui
 }
 
 __device__ __forceinline__ void store_counts(vfk_counts *out, int dp, int n_amb, int ac_ref, int ac_alt,
-                                             const int med2[3][2], const uint64_t s2[3], uint32_t status, uint32_t n_cand) {
+                                             const int med2[3][2], const uint64_t s2[3], uint32_t status, uint32_t n_cand,
+                                             uint32_t n_cover) {
     uint4 *o = reinterpret_cast<uint4 *>(out);
     o[0] = make_uint4((uint32_t)dp, (uint32_t)n_amb, (uint32_t)ac_ref, (uint32_t)ac_alt);
     o[1] = make_uint4((uint32_t)med2[0][0], (uint32_t)med2[0][1], (uint32_t)med2[1][0], (uint32_t)med2[1][1]);
     o[2] = make_uint4((uint32_t)med2[2][0], (uint32_t)med2[2][1], status, n_cand);
     o[3] = make_uint4((uint32_t)s2[0], (uint32_t)(s2[0] >> 32), (uint32_t)s2[1], (uint32_t)(s2[1] >> 32));
-    o[4] = make_uint4((uint32_t)s2[2], (uint32_t)(s2[2] >> 32), 0u, 0u);
+    o[4] = make_uint4((uint32_t)s2[2], (uint32_t)(s2[2] >> 32), n_cover, 0u);
 }
 
 template <typename CT, int POSB>
@@ -166,13 +167,13 @@ pileup_warp_kernel(ReadsDev R, UnitsDev V, vfk_params P, vfk_counts *__restrict_
             int med2[3][2] = {{-1, -1}, {-1, -1}, {-1, -1}};
             uint64_t s2[3] = {0, 0, 0};
             if (n_cand == 0) {
-                if (lane == 0) store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind, 0u);
+                if (lane == 0) store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind, 0u, 0u);
                 continue;
             }
             if (n_cand > WARP_PATH_MAX_CAND) {
                 if (lane == 0) {
                     deferred[atomicAdd(n_deferred, 1u)] = (uint32_t)u;
-                    store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind | VFK_ST_DEFERRED, (uint32_t)n_cand);
+                    store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind | VFK_ST_DEFERRED, (uint32_t)n_cand, 0u);
                 }
                 continue;
             }
@@ -182,13 +183,14 @@ pileup_warp_kernel(ReadsDev R, UnitsDev V, vfk_params P, vfk_counts *__restrict_
                 for (int w = lane; w < (2 * WORDS) / 4; w += 32) z[w] = make_uint4(0, 0, 0, 0);
             }
             __syncwarp();
-            int dp = 0, n_amb = 0, ac_ref = 0, ac_alt = 0;
+            int dp = 0, n_amb = 0, ac_ref = 0, ac_alt = 0, n_cover = 0;
             uint32_t status = U.kind;
             const bool with_bq = U.kind == VFK_KIND_SNV;
             for (int64_t b = U.lo; b < U.hi; b += 32) {
                 const int64_t i = b + lane;
                 if (i < U.hi) {
                     const Contribution c = evaluate(R, P, U, i);
+                    n_cover += c.covers ? 1 : 0;
                     dp += c.in_dp ? 1 : 0;
                     n_amb += c.ambiguous ? 1 : 0;
                     ac_ref += c.ref ? 1 : 0;
@@ -201,6 +203,7 @@ pileup_warp_kernel(ReadsDev R, UnitsDev V, vfk_params P, vfk_counts *__restrict_
             n_amb = __reduce_add_sync(FULL, n_amb);
             ac_ref = __reduce_add_sync(FULL, ac_ref);
             ac_alt = __reduce_add_sync(FULL, ac_alt);
+            n_cover = __reduce_add_sync(FULL, n_cover);
             status = __reduce_or_sync(FULL, status);
             if (ac_ref | ac_alt) {
                 reduce_metric<uint16_t, 256>(ref_slot, alt_slot, L::MQ_OFF, lane, med2[0][0], med2[0][1], s2[0]);
@@ -208,7 +211,7 @@ pileup_warp_kernel(ReadsDev R, UnitsDev V, vfk_params P, vfk_counts *__restrict_
                 reduce_metric<uint16_t, POSB>(ref_slot, alt_slot, L::POS_OFF, lane, med2[2][0], med2[2][1], s2[2]);
             }
             if (U.kind == VFK_KIND_SNV && !P.include_ambiguous) dp -= n_amb;  // pileups.py:224-227
-            if (lane == 0) store_counts(out + u, dp, n_amb, ac_ref, ac_alt, med2, s2, status, (uint32_t)n_cand);
+            if (lane == 0) store_counts(out + u, dp, n_amb, ac_ref, ac_alt, med2, s2, status, (uint32_t)n_cand, (uint32_t)n_cover);
             __syncwarp();
         }
     }
@@ -224,7 +227,7 @@ pileup_block_kernel(ReadsDev R, UnitsDev V, vfk_params P, vfk_counts *__restrict
     using L = Layout<POSB>;
     constexpr int WORDS = L::BINS;  // u32 bins
     extern __shared__ __align__(16) uint32_t smem[];
-    __shared__ int red[4];
+    __shared__ int red[5];
     __shared__ uint32_t red_status;
     __shared__ int s_med2[3][2];
     __shared__ unsigned long long s_s2[3];
@@ -237,16 +240,17 @@ pileup_block_kernel(ReadsDev R, UnitsDev V, vfk_params P, vfk_counts *__restrict
         load_unit(R, V, u, U);
         warp_locate(R, U, lane);  // every warp locates for itself (same result)
         for (int w = threadIdx.x; w < 2 * WORDS; w += blockDim.x) smem[w] = 0u;
-        if (threadIdx.x < 4) red[threadIdx.x] = 0;
+        if (threadIdx.x < 5) red[threadIdx.x] = 0;
         if (threadIdx.x == 0) red_status = U.kind;
         if (threadIdx.x < 6) s_med2[threadIdx.x >> 1][threadIdx.x & 1] = -1;
         if (threadIdx.x < 3) s_s2[threadIdx.x] = 0ull;
         __syncthreads();
-        int dp = 0, n_amb = 0, ac_ref = 0, ac_alt = 0;
+        int dp = 0, n_amb = 0, ac_ref = 0, ac_alt = 0, n_cover = 0;
         uint32_t status = U.kind;
         const bool with_bq = U.kind == VFK_KIND_SNV;
         for (int64_t i = U.lo + threadIdx.x; i < U.hi; i += blockDim.x) {
             const Contribution c = evaluate(R, P, U, i);
+            n_cover += c.covers ? 1 : 0;
             dp += c.in_dp ? 1 : 0;
             n_amb += c.ambiguous ? 1 : 0;
             ac_ref += c.ref ? 1 : 0;
@@ -257,8 +261,10 @@ pileup_block_kernel(ReadsDev R, UnitsDev V, vfk_params P, vfk_counts *__restrict
         n_amb = __reduce_add_sync(FULL, n_amb);
         ac_ref = __reduce_add_sync(FULL, ac_ref);
         ac_alt = __reduce_add_sync(FULL, ac_alt);
+        n_cover = __reduce_add_sync(FULL, n_cover);
         status = __reduce_or_sync(FULL, status);
         if (lane == 0) {
+            atomicAdd(&red[4], n_cover);
             atomicAdd(&red[0], dp); atomicAdd(&red[1], n_amb); atomicAdd(&red[2], ac_ref); atomicAdd(&red[3], ac_alt);
             atomicOr(&red_status, status);
         }
@@ -278,7 +284,8 @@ pileup_block_kernel(ReadsDev R, UnitsDev V, vfk_params P, vfk_counts *__restrict
             for (int m = 0; m < 3; ++m) { med2[m][0] = s_med2[m][0]; med2[m][1] = s_med2[m][1]; s2[m] = s_s2[m]; }
             int d_p = red[0];
             if (U.kind == VFK_KIND_SNV && !P.include_ambiguous) d_p -= red[1];
-            store_counts(out + u, d_p, red[1], red[2], red[3], med2, s2, red_status, (uint32_t)(U.hi - U.lo));
+            store_counts(out + u, d_p, red[1], red[2], red[3], med2, s2, red_status & ~VFK_ST_DEFERRED, (uint32_t)(U.hi - U.lo),
+                         (uint32_t)red[4]);
         }
         __syncthreads();
     }

@@ -20,7 +20,7 @@ NO_MATE = 0xFFFFFFFF
 
 COUNTS_DTYPE = np.dtype([("dp", "<i4"), ("n_amb", "<i4"), ("ac_ref", "<i4"), ("ac_alt", "<i4"),
                          ("med2", "<i4", (3, 2)), ("status", "<u4"), ("n_cand", "<u4"), ("s2", "<u8", (3,)),
-                         ("reserved", "<u8")])
+                         ("n_cover", "<u4"), ("reserved", "<u4")])
 STATS_DTYPE = np.dtype([("z", "<f8", (3,)), ("p", "<f8", (3,)), ("pu", "<f8"), ("pw", "<f8"), ("k", "<i4"),
                         ("pad", "<i4")])
 HOT_DTYPE = np.dtype([("pos", "<i4"), ("span", "<u4"), ("fmk", "<u4"), ("pay", "<u4")])
