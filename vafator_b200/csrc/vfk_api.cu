@@ -1,6 +1,7 @@
 // vfk_api.cu -- the C ABI declared in include/vfk.h.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 #include "vfk.h"
@@ -57,7 +58,7 @@ struct vfk_handle {
     DevBuf deferred;
     int64_t launches = 0;
     // staging for vfk_annotate_host
-    DevBuf s_contig, s_hot, s_cold, s_mate, s_starts, s_pmax, s_cigar, s_payload;
+    DevBuf s_contig, s_hot, s_cold, s_mate, s_sb, s_tree, s_cigar, s_payload;
     DevBuf s_tid, s_pos, s_meta, s_len, s_soff, s_ins, s_stop, s_eaf, s_counts, s_stats;
 };
 
@@ -77,6 +78,14 @@ extern "C" int vfk_create(int device, vfk_handle **out) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     h->sm_count = prop.multiProcessorCount;
+    {
+        // The path gathers single 32-byte sectors (one payload sector per (read, column) pair):
+        // ask L2 not to promote misses to 64/128-byte DRAM fetches.  A hint; failure is harmless.
+        size_t gran = 32;
+        if (const char *env = getenv("VFK_L2_FETCH_GRANULARITY")) gran = (size_t)atoi(env);
+        if (gran == 32 || gran == 64 || gran == 128) (void)cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+        (void)cudaGetLastError();
+    }
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&h->done, cudaEventDisableTiming));
     void *p = nullptr;
@@ -91,7 +100,7 @@ extern "C" int vfk_destroy(vfk_handle *h) {
     if (!h) return VFK_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf *bufs[] = {&h->deferred, &h->s_contig, &h->s_hot, &h->s_cold, &h->s_mate, &h->s_starts, &h->s_pmax, &h->s_cigar,
+    DevBuf *bufs[] = {&h->deferred, &h->s_contig, &h->s_hot, &h->s_cold, &h->s_mate, &h->s_sb, &h->s_tree, &h->s_cigar,
                       &h->s_payload, &h->s_tid, &h->s_pos, &h->s_meta, &h->s_len, &h->s_soff, &h->s_ins, &h->s_stop,
                       &h->s_eaf, &h->s_counts, &h->s_stats};
     for (DevBuf *b : bufs) b->release();
@@ -114,10 +123,11 @@ extern "C" int64_t vfk_launch_count(vfk_handle *h) { return h ? h->launches : 0;
 static int check_batches(const vfk_read_batch *r, const vfk_variant_batch *v, const vfk_params *p) {
     if (!r || !v || !p) return fail(VFK_EINVAL, "NULL batch or params");
     if (r->n_reads < 0 || v->n_units < 0 || r->n_contigs < 0) return fail(VFK_EINVAL, "negative size");
+    if (r->n_levels < 1 || r->n_levels > 7) return fail(VFK_EINVAL, "position index: n_levels out of range");
     if (r->n_reads > 0x7FFFFFFF) return fail(VFK_EUNSUPPORTED, "more than 2^31-1 reads in one batch: split it");
     if (r->max_l_qseq > VFK_MAX_READ_LEN) return fail(VFK_EUNSUPPORTED, "read longer than VFK_MAX_READ_LEN");
     if (!r->contig_off) return fail(VFK_EINVAL, "contig_off is NULL");
-    if (r->n_reads > 0 && (!r->hot || !r->cold || !r->mate || !r->starts || !r->pmax_end || !r->payload))
+    if (r->n_reads > 0 && (!r->hot || !r->cold || !r->mate || !r->sb || !r->tree || !r->payload))
         return fail(VFK_EINVAL, "read batch has a NULL array");
     if (v->n_units > 0 && (!v->tid || !v->pos || !v->meta || !v->length || !v->seq_off || !v->ins_seq))
         return fail(VFK_EINVAL, "variant batch has a NULL array");
@@ -128,8 +138,10 @@ static void to_dev(const vfk_read_batch *r, const vfk_variant_batch *v, vfk::Rea
     R.hot = (const uint4 *)r->hot;
     R.cold = (const uint4 *)r->cold;
     R.mate = r->mate;
-    R.starts = r->starts;
-    R.pmax_end = r->pmax_end;
+    R.sb = (const int2 *)r->sb;
+    R.tree = r->tree;
+    for (int k = 0; k < 8; ++k) { R.tree_off[k] = r->tree_off[k]; R.tree_cnt[k] = r->tree_cnt[k]; }
+    R.n_levels = r->n_levels;
     R.cigar = r->cigar;
     R.payload = r->payload;
     R.contig_off = r->contig_off;
@@ -153,7 +165,7 @@ extern "C" int vfk_pileup(vfk_handle *h, const vfk_read_batch *reads, const vfk_
     if (units->n_units == 0) return VFK_OK;
     if (!out) return fail(VFK_EINVAL, "vfk_pileup: out is NULL");
     CU(cudaSetDevice(h->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    cudaStream_t st = (cudaStream_t)stream;  // NULL = the CUDA default stream
     rc = h->deferred.reserve((size_t)units->n_units * sizeof(uint32_t));
     if (rc) return rc;
     vfk::ReadsDev R;
@@ -175,7 +187,7 @@ extern "C" int vfk_epilogue(vfk_handle *h, int64_t n_units, const vfk_counts *co
     if (!counts || !eaf || !out) return fail(VFK_EINVAL, "vfk_epilogue: NULL array");
     if (!(fpr >= 0.0) || !(error_rate >= 0.0)) return fail(VFK_EINVAL, "vfk_epilogue: fpr / error_rate must be >= 0");
     CU(cudaSetDevice(h->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    cudaStream_t st = (cudaStream_t)stream;  // NULL = the CUDA default stream
     int launches = 0;
     cudaError_t e = vfk::launch_epilogue(n_units, counts, eaf, fpr, error_rate, out, st, &launches);
     h->launches += launches;
@@ -206,8 +218,8 @@ extern "C" int vfk_annotate_host(vfk_handle *h, const vfk_read_batch *reads, con
     STAGE(h->s_hot, reads->hot, (size_t)nr * sizeof(vfk_read_hot));
     STAGE(h->s_cold, reads->cold, (size_t)nr * sizeof(vfk_read_cold));
     STAGE(h->s_mate, reads->mate, (size_t)nr * 4);
-    STAGE(h->s_starts, reads->starts, (size_t)nr * 4);
-    STAGE(h->s_pmax, reads->pmax_end, (size_t)nr * 4);
+    STAGE(h->s_sb, reads->sb, (size_t)nr * 8);
+    STAGE(h->s_tree, reads->tree, (size_t)(reads->tree_off[reads->n_levels] + reads->tree_cnt[reads->n_levels]) * 8);
     STAGE(h->s_cigar, reads->cigar, (size_t)reads->n_cigar_words * 4);
     STAGE(h->s_payload, reads->payload, (size_t)reads->n_sectors * 32);
     STAGE(h->s_tid, units->tid, (size_t)nu * 4);
@@ -227,8 +239,8 @@ extern "C" int vfk_annotate_host(vfk_handle *h, const vfk_read_batch *reads, con
     dr.hot = (const vfk_read_hot *)h->s_hot.p;
     dr.cold = (const vfk_read_cold *)h->s_cold.p;
     dr.mate = (const uint32_t *)h->s_mate.p;
-    dr.starts = (const int32_t *)h->s_starts.p;
-    dr.pmax_end = (const int32_t *)h->s_pmax.p;
+    dr.sb = (const int32_t *)h->s_sb.p;
+    dr.tree = (const uint64_t *)h->s_tree.p;
     dr.cigar = (const uint32_t *)h->s_cigar.p;
     dr.payload = (const uint8_t *)h->s_payload.p;
     vfk_variant_batch dv = *units;

@@ -22,8 +22,10 @@ struct ReadsDev {
     const uint4 *__restrict__ hot;
     const uint4 *__restrict__ cold;
     const uint32_t *__restrict__ mate;
-    const int32_t *__restrict__ starts;
-    const int32_t *__restrict__ pmax_end;
+    const int2 *__restrict__ sb;        // {start, back}
+    const uint64_t *__restrict__ tree;  // upper levels of the position index
+    int64_t tree_off[8], tree_cnt[8];
+    int32_t n_levels;
     const uint32_t *__restrict__ cigar;
     const uint8_t *__restrict__ payload;
     const int64_t *__restrict__ contig_off;
@@ -43,6 +45,7 @@ struct UnitsDev {
 };
 
 struct Unit {
+    int32_t tid;
     int32_t col;    // 0-based column
     int32_t stop;   // reads starting at or beyond it were never fetched by the reference
     uint32_t kind;
@@ -363,60 +366,58 @@ __device__ __forceinline__ Contribution evaluate(const ReadsDev &R, const vfk_pa
     return o;
 }
 
-// ---- warp-cooperative lower bound: first index in [lo, hi) with a[idx] > key, else hi ----
-__device__ __forceinline__ int64_t warp_first_greater(const int32_t *__restrict__ a, int64_t lo, int64_t hi, int32_t key, int lane) {
-    while (hi - lo > 32) {
-        const int64_t n = hi - lo;
-        const int64_t idx = lo + (((int64_t)(lane + 1) * n) >> 5) - 1;
-        const bool t = __ldg(a + idx) > key;
-        const unsigned b = __ballot_sync(FULL, t);
-        if (b == 0u) return hi;
-        const int j = __ffs(b) - 1;
-        const int64_t nlo = lo + (((int64_t)j * n) >> 5);
-        hi = lo + (((int64_t)(j + 1) * n) >> 5) - 1;  // known to satisfy the predicate
-        lo = nlo;
-    }
-    const int64_t idx = lo + lane;
-    const bool t = (idx < hi) ? (__ldg(a + idx) > key) : true;
-    const unsigned b = __ballot_sync(FULL, t);
-    return lo + (__ffs(b) - 1);
-}
-
-// both bounds of a column at once (independent probe chains -> two loads in flight per step)
+// ---- locating the candidate reads of a column ----
+// Position index = a 32-ary search tree stored level by level (host built, vfkio_pack):
+//   level 0   sb[i] = {start_i, back_i}                                   (one int2 per read)
+//   level k   tree[off[k] + j] = (tid << 32 | start) of the LAST read of node j,
+//             node j of level k covering reads [j*32^k, (j+1)*32^k)
+// A lookup reads 32 consecutive entries per level (one 256-byte line group, L2 resident for
+// every level but the last) instead of 32 strided probes of a flat array.
+//   hi = first read of the contig with start > col
+//   lo = back[hi-1] = first read whose running-maximum end exceeds start[hi-1] (<= col), so
+//        every read overlapping col lies in [lo, hi).
 __device__ __forceinline__ void warp_locate(const ReadsDev &R, Unit &U, int lane) {
-    int64_t lo0 = U.c0, hi0 = U.c1, lo1 = U.c0, hi1 = U.c1;
-    while (hi0 - lo0 > 32 || hi1 - lo1 > 32) {
-        const bool a0 = hi0 - lo0 > 32, a1 = hi1 - lo1 > 32;
-        const int64_t n0 = hi0 - lo0, n1 = hi1 - lo1;
-        const int64_t i0 = lo0 + (((int64_t)(lane + 1) * n0) >> 5) - 1;
-        const int64_t i1 = lo1 + (((int64_t)(lane + 1) * n1) >> 5) - 1;
-        int32_t v0 = 0, v1 = 0;
-        if (a0) v0 = __ldg(R.pmax_end + i0);
-        if (a1) v1 = __ldg(R.starts + i1);
-        if (a0) {
-            const unsigned b = __ballot_sync(FULL, v0 > U.col);
-            if (b == 0u) { lo0 = hi0; }
-            else { const int j = __ffs(b) - 1; const int64_t nlo = lo0 + (((int64_t)j * n0) >> 5); hi0 = lo0 + (((int64_t)(j + 1) * n0) >> 5) - 1; lo0 = nlo; }
-        }
-        if (a1) {
-            const unsigned b = __ballot_sync(FULL, v1 > U.col);
-            if (b == 0u) { lo1 = hi1; }
-            else { const int j = __ffs(b) - 1; const int64_t nlo = lo1 + (((int64_t)j * n1) >> 5); hi1 = lo1 + (((int64_t)(j + 1) * n1) >> 5) - 1; lo1 = nlo; }
-        }
+    const uint64_t key = ((uint64_t)(uint32_t)U.tid << 32) | (uint32_t)U.col;
+    int64_t node = 0;
+    bool past_end = false;
+    for (int k = R.n_levels; k >= 1; --k) {
+        const uint64_t *__restrict__ lvl = R.tree + R.tree_off[k];
+        const int64_t idx = node * 32 + lane;
+        const bool t = (idx < R.tree_cnt[k]) ? (__ldg(lvl + idx) > key) : true;
+        const unsigned b = __ballot_sync(FULL, t);
+        if (k == R.n_levels && (b == 0u || node * 32 + (__ffs(b) - 1) >= R.tree_cnt[k])) { past_end = true; break; }
+        node = node * 32 + (__ffs(b) - 1);
     }
-    {
-        const int64_t i0 = lo0 + lane, i1 = lo1 + lane;
-        const bool t0 = (i0 < hi0) ? (__ldg(R.pmax_end + i0) > U.col) : true;
-        const bool t1 = (i1 < hi1) ? (__ldg(R.starts + i1) > U.col) : true;
-        U.lo = lo0 + (__ffs(__ballot_sync(FULL, t0)) - 1);
-        U.hi = lo1 + (__ffs(__ballot_sync(FULL, t1)) - 1);
+    int64_t hi;
+    int2 mine = make_int2(0, 0);
+    if (past_end) {
+        hi = U.c1;
+    } else {
+        const int64_t idx = node * 32 + lane;
+        bool t = true;
+        if (idx < U.c1) {
+            mine = __ldg(R.sb + idx);
+            t = (idx >= U.c0) ? (mine.x > U.col) : false;
+        }
+        const unsigned b = __ballot_sync(FULL, t);
+        hi = node * 32 + (__ffs(b) - 1);
+        if (hi > U.c1) hi = U.c1;
+        if (hi < U.c0) hi = U.c0;
     }
-    if (U.hi < U.lo) U.hi = U.lo;
+    U.hi = hi;
+    if (hi <= U.c0) { U.lo = hi; return; }
+    // back pointer of read hi-1: it sits in this leaf unless hi is the leaf's first entry
+    const int64_t want = hi - 1;
+    int32_t back;
+    if (!past_end && want >= node * 32) back = __shfl_sync(FULL, mine.y, (int)(want - node * 32));
+    else back = __ldg(&R.sb[want].y);
+    U.lo = (int64_t)back;
 }
 
 __device__ __forceinline__ void load_unit(const ReadsDev &R, const UnitsDev &V, int64_t u, Unit &U) {
     const int32_t tid = __ldg(V.tid + u);
     const uint32_t meta = __ldg(V.meta + u);
+    U.tid = tid;
     U.col = __ldg(V.pos + u);
     U.stop = V.stop ? __ldg(V.stop + u) : 0x7FFFFFFF;
     U.kind = meta & 3u;

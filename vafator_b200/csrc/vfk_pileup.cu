@@ -5,9 +5,13 @@
 // MQ / BQ / read-position distributions to integers: counts, twice-the-median, and twice the
 // ALT mid-rank sum that scipy.stats.ranksums would compute (vafator/rank_sum_test.py:11).
 //
-// pileup_warp_kernel : one warp per unit, lanes = candidate reads, histograms in shared memory
-//                      (u16 counters, two per word).  Persistent grid, units handed out in small
-//                      contiguous grabs from a global counter.
+// pileup_warp_kernel : one warp per unit, lanes = candidate reads.  Persistent grid, units handed
+//                      out in small contiguous grabs from a global counter.  Two ways to reduce
+//                      the distributions:
+//     shallow  (<= 64 candidates, <= 32 of them contributing): values stay in registers, ranks
+//              come from a bit-sliced (radix) comparison built on warp ballots -- no shared
+//              memory traffic, no atomics;
+//     deep     histograms in shared memory (u16 counters, two per word) + warp scans.
 // pileup_block_kernel: one CTA per unit for the (rare) columns too deep for u16 counters.
 #include "vfk_device.cuh"
 
@@ -23,6 +27,7 @@ struct Layout {
     static constexpr int BQ_OFF = 256;
     static constexpr int POS_OFF = 512;
     static constexpr int BINS = 512 + POSB;  // per slot
+    static constexpr int POS_BITS = POSB == 256 ? 8 : POSB == 512 ? 9 : POSB == 1024 ? 10 : 12;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -57,8 +62,8 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 // mid-rank sum over the pooled ranking.  Executed by one full warp.
 //   2*rank_sum(ALT) = sum_v alt[v] * (2*below(v) + ties(v) + 1)
 template <typename CT, int B>
-__device__ __forceinline__ void reduce_metric(const uint32_t *ref_slot, const uint32_t *alt_slot, int off, int lane,
-                                              int &med2_ref, int &med2_alt, uint64_t &s2) {
+__device__ __noinline__ void reduce_metric(const uint32_t *ref_slot, const uint32_t *alt_slot, int off, int lane,
+                                           int &med2_ref, int &med2_alt, uint64_t &s2) {
     constexpr int BPL = B / 32;  // consecutive bins per lane
     const int b0 = off + lane * BPL;
     uint32_t tr = 0, ta = 0;
@@ -139,10 +144,109 @@ __device__ __forceinline__ void accumulate(uint32_t *ref_slot, uint32_t *alt_slo
 }
 
 // ------------------------------------------------------------------------------------------
+// shallow path: one value per lane, ranks from bit-sliced comparisons
+// ------------------------------------------------------------------------------------------
+// packed contribution: mq | bq << 8 | qpos << 16 | ref << 28 | alt << 29
+constexpr uint32_t PK_REF = 1u << 28, PK_ALT = 1u << 29;
+__device__ __forceinline__ uint32_t pack(const Contribution &c) {
+    return (uint32_t)c.mq | ((uint32_t)c.bq << 8) | ((uint32_t)c.qpos << 16) | (c.ref ? PK_REF : 0u) | (c.alt ? PK_ALT : 0u);
+}
+
+// For this lane's value v (NBITS wide): which contributing lanes hold a smaller value (lt) and
+// which an equal one (eq, itself included).  Walks the bits from the top; a bit on which all
+// contributing lanes agree cannot separate anything and is skipped (warp-uniform branch).
+template <int NBITS>
+__device__ __forceinline__ void radix_compare(uint32_t v, uint32_t contributing, uint32_t &lt, uint32_t &eq) {
+    lt = 0u;
+    eq = contributing;
+#pragma unroll
+    for (int bit = NBITS - 1; bit >= 0; --bit) {
+        const bool mine = (v >> bit) & 1u;
+        const uint32_t b = __ballot_sync(FULL, mine) & contributing;
+        if (b == 0u || b == contributing) continue;
+        const uint32_t zeros = eq & ~b;
+        lt |= mine ? zeros : 0u;
+        eq = mine ? (eq & b) : zeros;
+    }
+}
+
+// medians of the REF / ALT lists and the ALT mid-rank sum, from the lt / eq masks
+__device__ __forceinline__ void radix_finish(uint32_t v, uint32_t R, uint32_t A, bool is_ref, bool is_alt, uint32_t lt,
+                                             uint32_t eq, int &med2_ref, int &med2_alt, uint64_t &s2) {
+    const int nr = __popc(R), na = __popc(A);
+    // the pooled sample is the concatenation of both lists: a lane in both counts twice
+    const int below = __popc(lt & R) + __popc(lt & A), ties = __popc(eq & R) + __popc(eq & A);
+    s2 = (nr && na) ? (uint64_t)__reduce_add_sync(FULL, is_alt ? (unsigned)(2 * below + ties + 1) : 0u) : 0ull;
+    if (nr) {
+        const int br = __popc(lt & R), tr = __popc(eq & R), k1 = (nr - 1) >> 1, k2 = nr >> 1;
+        const int v1 = __reduce_max_sync(FULL, (is_ref && br <= k1 && k1 < br + tr) ? (int)v : -1);
+        const int v2 = __reduce_max_sync(FULL, (is_ref && br <= k2 && k2 < br + tr) ? (int)v : -1);
+        med2_ref = v1 + v2;
+    } else {
+        med2_ref = -1;
+    }
+    if (na) {
+        const int ba = __popc(lt & A), ta = __popc(eq & A), k1 = (na - 1) >> 1, k2 = na >> 1;
+        const int v1 = __reduce_max_sync(FULL, (is_alt && ba <= k1 && k1 < ba + ta) ? (int)v : -1);
+        const int v2 = __reduce_max_sync(FULL, (is_alt && ba <= k2 && k2 < ba + ta) ? (int)v : -1);
+        med2_alt = v1 + v2;
+    } else {
+        med2_alt = -1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// deep path of the warp kernel: shared-memory histograms
+// ------------------------------------------------------------------------------------------
+template <int POSB>
+__device__ __noinline__ void unit_by_histogram(const ReadsDev &R, const vfk_params &P, const Unit &U, uint32_t *ref_slot,
+                                               uint32_t *alt_slot, int lane, vfk_counts *out) {
+    using L = Layout<POSB>;
+    constexpr int WORDS = L::BINS / 2;
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(ref_slot);
+        for (int w = lane; w < (2 * WORDS) / 4; w += 32) z[w] = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+    int dp = 0, n_amb = 0, ac_ref = 0, ac_alt = 0, n_cover = 0;
+    uint32_t status = U.kind;
+    const bool with_bq = U.kind == VFK_KIND_SNV;
+    for (int64_t b = U.lo; b < U.hi; b += 32) {
+        const int64_t i = b + lane;
+        if (i < U.hi) {
+            const Contribution c = evaluate(R, P, U, i);
+            n_cover += c.covers ? 1 : 0;
+            dp += c.in_dp ? 1 : 0;
+            n_amb += c.ambiguous ? 1 : 0;
+            ac_ref += c.ref ? 1 : 0;
+            ac_alt += (int)c.alt;
+            accumulate<uint16_t, POSB>(ref_slot, alt_slot, c, with_bq, status);
+        }
+    }
+    __syncwarp();
+    dp = __reduce_add_sync(FULL, dp);
+    n_amb = __reduce_add_sync(FULL, n_amb);
+    ac_ref = __reduce_add_sync(FULL, ac_ref);
+    ac_alt = __reduce_add_sync(FULL, ac_alt);
+    n_cover = __reduce_add_sync(FULL, n_cover);
+    status = __reduce_or_sync(FULL, status);
+    int med2[3][2] = {{-1, -1}, {-1, -1}, {-1, -1}};
+    uint64_t s2[3] = {0, 0, 0};
+    if (ac_ref | ac_alt) {
+        reduce_metric<uint16_t, 256>(ref_slot, alt_slot, L::MQ_OFF, lane, med2[0][0], med2[0][1], s2[0]);
+        if (with_bq) reduce_metric<uint16_t, 256>(ref_slot, alt_slot, L::BQ_OFF, lane, med2[1][0], med2[1][1], s2[1]);
+        reduce_metric<uint16_t, POSB>(ref_slot, alt_slot, L::POS_OFF, lane, med2[2][0], med2[2][1], s2[2]);
+    }
+    if (U.kind == VFK_KIND_SNV && !P.include_ambiguous) dp -= n_amb;  // pileups.py:224-227
+    if (lane == 0) store_counts(out, dp, n_amb, ac_ref, ac_alt, med2, s2, status, (uint32_t)(U.hi - U.lo), (uint32_t)n_cover);
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
 // warp per unit
 // ------------------------------------------------------------------------------------------
 template <int POSB>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
 pileup_warp_kernel(ReadsDev R, UnitsDev V, vfk_params P, vfk_counts *__restrict__ out,
                    unsigned long long *__restrict__ work_counter, uint32_t *__restrict__ deferred,
                    uint32_t *__restrict__ n_deferred) {
@@ -150,6 +254,7 @@ pileup_warp_kernel(ReadsDev R, UnitsDev V, vfk_params P, vfk_counts *__restrict_
     constexpr int WORDS = L::BINS / 2;  // u16 bins
     extern __shared__ __align__(16) uint32_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t *ref_slot = smem + (size_t)warp * 2 * WORDS;
     uint32_t *alt_slot = ref_slot + WORDS;
 
@@ -177,42 +282,54 @@ pileup_warp_kernel(ReadsDev R, UnitsDev V, vfk_params P, vfk_counts *__restrict_
                 }
                 continue;
             }
-            // clear this warp's histograms
-            {
-                uint4 *z = reinterpret_cast<uint4 *>(ref_slot);
-                for (int w = lane; w < (2 * WORDS) / 4; w += 32) z[w] = make_uint4(0, 0, 0, 0);
+            if (n_cand > 64) {
+                unit_by_histogram<POSB>(R, P, U, ref_slot, alt_slot, lane, out + u);
+                continue;
             }
-            __syncwarp();
-            int dp = 0, n_amb = 0, ac_ref = 0, ac_alt = 0, n_cover = 0;
-            uint32_t status = U.kind;
-            const bool with_bq = U.kind == VFK_KIND_SNV;
-            for (int64_t b = U.lo; b < U.hi; b += 32) {
-                const int64_t i = b + lane;
-                if (i < U.hi) {
-                    const Contribution c = evaluate(R, P, U, i);
-                    n_cover += c.covers ? 1 : 0;
-                    dp += c.in_dp ? 1 : 0;
-                    n_amb += c.ambiguous ? 1 : 0;
-                    ac_ref += c.ref ? 1 : 0;
-                    ac_alt += (int)c.alt;
-                    accumulate<uint16_t, POSB>(ref_slot, alt_slot, c, with_bq, status);
+            // ---- shallow: at most two reads per lane ----
+            Contribution c0, c1;
+            c0.covers = c0.in_dp = c0.ambiguous = c0.ref = false; c0.alt = 0; c0.mq = c0.bq = c0.qpos = 0;
+            c1 = c0;
+            if (lane < n_cand) c0 = evaluate(R, P, U, U.lo + lane);
+            if (n_cand > 32 && lane + 32 < n_cand) c1 = evaluate(R, P, U, U.lo + 32 + lane);
+            const bool k0 = c0.ref || c0.alt, k1 = c1.ref || c1.alt;
+            const uint32_t m0 = __ballot_sync(FULL, k0), m1 = __ballot_sync(FULL, k1);
+            const bool heavy = __any_sync(FULL, c0.alt > 1u || c1.alt > 1u || c0.qpos >= POSB || c1.qpos >= POSB);
+            if (heavy || __popc(m0) + __popc(m1) > 32) {  // rare: re-done through the histograms
+                unit_by_histogram<POSB>(R, P, U, ref_slot, alt_slot, lane, out + u);
+                continue;
+            }
+            int dp = __popc(__ballot_sync(FULL, c0.in_dp)) + __popc(__ballot_sync(FULL, c1.in_dp));
+            const int n_amb = __popc(__ballot_sync(FULL, c0.ambiguous)) + __popc(__ballot_sync(FULL, c1.ambiguous));
+            const int n_cover = __popc(__ballot_sync(FULL, c0.covers)) + __popc(__ballot_sync(FULL, c1.covers));
+            uint32_t pk = k0 ? pack(c0) : 0u;
+            if (m1) {  // move the second chunk's contributions into lanes the first one left free
+                const int n1 = __popc(m1);
+                if (k1) ref_slot[__popc(m1 & lt_mask)] = pack(c1);
+                __syncwarp();
+                if (!k0) {
+                    const int f = __popc(~m0 & lt_mask);
+                    if (f < n1) pk = ref_slot[f];
                 }
+                __syncwarp();
             }
-            __syncwarp();
-            dp = __reduce_add_sync(FULL, dp);
-            n_amb = __reduce_add_sync(FULL, n_amb);
-            ac_ref = __reduce_add_sync(FULL, ac_ref);
-            ac_alt = __reduce_add_sync(FULL, ac_alt);
-            n_cover = __reduce_add_sync(FULL, n_cover);
-            status = __reduce_or_sync(FULL, status);
-            if (ac_ref | ac_alt) {
-                reduce_metric<uint16_t, 256>(ref_slot, alt_slot, L::MQ_OFF, lane, med2[0][0], med2[0][1], s2[0]);
-                if (with_bq) reduce_metric<uint16_t, 256>(ref_slot, alt_slot, L::BQ_OFF, lane, med2[1][0], med2[1][1], s2[1]);
-                reduce_metric<uint16_t, POSB>(ref_slot, alt_slot, L::POS_OFF, lane, med2[2][0], med2[2][1], s2[2]);
+            const bool is_ref = pk & PK_REF, is_alt = pk & PK_ALT;
+            const uint32_t Rm = __ballot_sync(FULL, is_ref), Am = __ballot_sync(FULL, is_alt);
+            const int ac_ref = __popc(Rm), ac_alt = __popc(Am);
+            if (Rm | Am) {
+                uint32_t lt, eq;
+                const uint32_t mq = pk & 0xFFu, bq = (pk >> 8) & 0xFFu, qp = (pk >> 16) & 0xFFFu;
+                radix_compare<8>(mq, Rm | Am, lt, eq);
+                radix_finish(mq, Rm, Am, is_ref, is_alt, lt, eq, med2[0][0], med2[0][1], s2[0]);
+                if (U.kind == VFK_KIND_SNV) {
+                    radix_compare<8>(bq, Rm | Am, lt, eq);
+                    radix_finish(bq, Rm, Am, is_ref, is_alt, lt, eq, med2[1][0], med2[1][1], s2[1]);
+                }
+                radix_compare<L::POS_BITS>(qp, Rm | Am, lt, eq);
+                radix_finish(qp, Rm, Am, is_ref, is_alt, lt, eq, med2[2][0], med2[2][1], s2[2]);
             }
             if (U.kind == VFK_KIND_SNV && !P.include_ambiguous) dp -= n_amb;  // pileups.py:224-227
-            if (lane == 0) store_counts(out + u, dp, n_amb, ac_ref, ac_alt, med2, s2, status, (uint32_t)n_cand, (uint32_t)n_cover);
-            __syncwarp();
+            if (lane == 0) store_counts(out + u, dp, n_amb, ac_ref, ac_alt, med2, s2, U.kind, (uint32_t)n_cand, (uint32_t)n_cover);
         }
     }
 }
@@ -314,9 +431,7 @@ static cudaError_t launch_posb(const ReadsDev &R, const UnitsDev &V, const vfk_p
     int64_t want = (V.n + (int64_t)GRAB * WARPS_PER_CTA - 1) / ((int64_t)GRAB * WARPS_PER_CTA);
     int64_t grid = (int64_t)sm_count * ctas_per_sm;
     if (want < grid) grid = want < 1 ? 1 : want;
-    e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
-    if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(n_deferred, 0, sizeof(uint32_t), stream);
+    e = cudaMemsetAsync(work_counter, 0, 16, stream);  // work counter and deferred-unit count share one allocation
     if (e != cudaSuccess) return e;
     pileup_warp_kernel<POSB><<<(unsigned)grid, WARPS_PER_CTA * 32, smem_warp, stream>>>(R, V, P, out, work_counter, deferred, n_deferred);
     ++*launches;

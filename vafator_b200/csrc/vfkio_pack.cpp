@@ -56,12 +56,25 @@ extern "C" int vfkio_pack_plan(const vfkio_reads *r, vfkio_plan *plan) {
     plan->n_cigar_words = words;
     plan->n_sectors = sectors;
     plan->max_l_qseq = maxl;
-    plan->pad = 0;
+    // upper levels of the 32-ary position index: level k has ceil(n / 32^k) entries, up to a root of <= 32
+    plan->n_levels = 0;
+    plan->n_tree = 0;
+    for (int k = 0; k < 8; ++k) plan->tree_off[k] = plan->tree_cnt[k] = 0;
+    int64_t cnt = placed;
+    while (cnt > 32 || plan->n_levels == 0) {
+        cnt = (cnt + 31) / 32;
+        if (cnt < 1) cnt = 1;
+        const int k = ++plan->n_levels;
+        plan->tree_off[k] = plan->n_tree;
+        plan->tree_cnt[k] = cnt;
+        plan->n_tree += cnt;
+        if (k == 7) break;
+    }
     return VFK_OK;
 }
 
 extern "C" int vfkio_pack(const vfkio_reads *r, const vfkio_plan *plan, int64_t *contig_off, vfk_read_hot *hot,
-                          vfk_read_cold *cold, int32_t *starts, int32_t *pmax_end, uint32_t *cigar, uint8_t *payload) {
+                          vfk_read_cold *cold, int32_t *sb, uint64_t *tree, uint32_t *cigar, uint8_t *payload) {
     if (!r || !plan || !contig_off) return vfkio_fail(VFK_EINVAL, "vfkio_pack: NULL argument");
     const int64_t n = plan->n_placed;
     // per-read offsets (serial prefix sums), then a parallel fill
@@ -94,7 +107,7 @@ extern "C" int vfkio_pack(const vfkio_reads *r, const vfkio_plan *plan, int64_t 
         cold[i].n_cigar = (uint32_t)r->n_cigar[i];
         cold[i].l_qseq = (uint32_t)r->l_qseq[i];
         cold[i].reserved = 0;
-        starts[i] = r->pos[i];
+        sb[2 * i] = r->pos[i];
         if (!sh.simple) memcpy(cigar + cig[i], r->cigar + r->cigar_off[i], (size_t)r->n_cigar[i] * 4);
         // payload sectors: 21 qualities + 21 nibbles each
         const int32_t l = r->l_qseq[i];
@@ -112,13 +125,30 @@ extern "C" int vfkio_pack(const vfkio_reads *r, const vfkio_plan *plan, int64_t 
             }
         }
     }
-    // running maximum of the reference end, restarted at every contig
+    // back pointers: with pmax[j] the running maximum of the reference end inside the contig,
+    // back[i] = first j with pmax[j] > start[i] (two monotone cursors)
     for (int32_t t = 0; t < r->n_contigs; ++t) {
-        int32_t mx = INT32_MIN;
-        for (int64_t i = contig_off[t]; i < contig_off[t + 1]; ++i) {
-            const int64_t e = (int64_t)hot[i].pos + hot[i].span;
-            mx = std::max<int64_t>(mx, std::min<int64_t>(e, INT32_MAX));
-            pmax_end[i] = mx;
+        const int64_t a = contig_off[t], b = contig_off[t + 1];
+        int64_t j = a, mx = INT64_MIN;
+        std::vector<int64_t> pmax;
+        pmax.reserve((size_t)(b - a));
+        for (int64_t i = a; i < b; ++i) {
+            mx = std::max<int64_t>(mx, (int64_t)hot[i].pos + hot[i].span);
+            pmax.push_back(mx);
+        }
+        for (int64_t i = a; i < b; ++i) {
+            while (j < i && pmax[(size_t)(j - a)] <= (int64_t)hot[i].pos) ++j;
+            sb[2 * i + 1] = (int32_t)j;
+        }
+    }
+    // upper levels: key of the last read of every node
+    for (int k = 1; k <= plan->n_levels; ++k) {
+        uint64_t *lvl = tree + plan->tree_off[k];
+        int64_t width = 1;
+        for (int q = 0; q < k; ++q) width *= 32;
+        for (int64_t j = 0; j < plan->tree_cnt[k]; ++j) {
+            const int64_t last = std::min<int64_t>((j + 1) * width, n) - 1;
+            lvl[j] = last >= 0 ? (((uint64_t)(uint32_t)r->tid[last] << 32) | (uint32_t)r->pos[last]) : ~0ull;
         }
     }
     return VFK_OK;
