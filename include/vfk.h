@@ -72,16 +72,9 @@ typedef struct {
     const vfk_read_hot *hot;      /* [n_reads]                                                  */
     const vfk_read_cold *cold;    /* [n_reads]                                                  */
     const uint32_t *mate;         /* [n_reads] overlap partner | tie_break << 31, VFK_NO_MATE   */
-    const int32_t *sb;            /* [n_reads][2] {start, back}: level 0 of the position index;
+    const int32_t *sb;            /* [n_reads][2] {start, back}: the position index;
                                      back[i] = first read of the contig whose running-maximum end
                                      exceeds start[i], i.e. no earlier read can overlap it        */
-    const uint64_t *tree;         /* upper levels of the 32-ary position index, concatenated:
-                                     level k (1..n_levels) entry j = (tid << 32 | start) of the
-                                     last read of [j*32^k, (j+1)*32^k)                            */
-    int64_t tree_off[8];          /* offset of level k in tree[] (index 0 unused)                 */
-    int64_t tree_cnt[8];          /* entries of level k                                           */
-    int32_t n_levels;
-    int32_t pad;
     const uint32_t *cigar;        /* [n_cigar_words]                                            */
     const uint8_t *payload;       /* [n_sectors * 32], 32-byte aligned                          */
     int64_t n_cigar_words;

@@ -37,9 +37,7 @@ typedef struct {
     int64_t n_cigar_words; /* CIGAR words of the shape-1 reads */
     int64_t n_sectors;     /* 32-byte payload sectors */
     int32_t max_l_qseq;
-    int32_t n_levels;      /* upper levels of the position index */
-    int64_t tree_off[8], tree_cnt[8];
-    int64_t n_tree;        /* total entries of the upper levels */
+    int32_t pad;
 } vfkio_plan;
 
 const char *vfkio_last_error(void);
@@ -49,8 +47,8 @@ int vfkio_pack_plan(const vfkio_reads *r, vfkio_plan *plan);
 
 /* fill caller-allocated arrays sized by the plan (host memory, pinned or not) */
 int vfkio_pack(const vfkio_reads *r, const vfkio_plan *plan, int64_t *contig_off /*[n_contigs+1]*/,
-               vfk_read_hot *hot, vfk_read_cold *cold, int32_t *sb /*[n][2]*/, uint64_t *tree /*[n_tree]*/,
-               uint32_t *cigar, uint8_t *payload);
+               vfk_read_hot *hot, vfk_read_cold *cold, int32_t *sb /*[n][2]*/, uint32_t *cigar,
+               uint8_t *payload);
 
 /* htslib overlap_push / overlap_remove emulation (sam.c): mate[i] = partner |
  * tie_break << 31 or VFK_NO_MATE, for the reads the reference would push under `params`. */

@@ -9,7 +9,7 @@
 
 namespace vfk {
 cudaError_t launch_pileup(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, int max_l_qseq, vfk_counts *out,
-                          unsigned long long *work_counter, uint32_t *deferred, uint32_t *n_deferred, int sm_count,
+                          void *resolved_scratch, unsigned long long *work_counter, uint32_t *deferred, uint32_t *n_deferred, int sm_count,
                           cudaStream_t stream, int *launches);
 cudaError_t launch_epilogue(int64_t n_units, const vfk_counts *counts, const double *eaf, double fpr, double error_rate,
                             vfk_stats *out, cudaStream_t stream, int *launches);
@@ -55,10 +55,10 @@ struct vfk_handle {
     cudaEvent_t done = nullptr;
     unsigned long long *work_counter = nullptr;  // 8 B + n_deferred 4 B
     uint32_t *n_deferred = nullptr;
-    DevBuf deferred;
+    DevBuf deferred, resolved;  // per-launch scratch: deep-unit list, located units (32 B each)
     int64_t launches = 0;
     // staging for vfk_annotate_host
-    DevBuf s_contig, s_hot, s_cold, s_mate, s_sb, s_tree, s_cigar, s_payload;
+    DevBuf s_contig, s_hot, s_cold, s_mate, s_sb, s_cigar, s_payload;
     DevBuf s_tid, s_pos, s_meta, s_len, s_soff, s_ins, s_stop, s_eaf, s_counts, s_stats;
 };
 
@@ -100,7 +100,7 @@ extern "C" int vfk_destroy(vfk_handle *h) {
     if (!h) return VFK_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf *bufs[] = {&h->deferred, &h->s_contig, &h->s_hot, &h->s_cold, &h->s_mate, &h->s_sb, &h->s_tree, &h->s_cigar,
+    DevBuf *bufs[] = {&h->deferred, &h->resolved, &h->s_contig, &h->s_hot, &h->s_cold, &h->s_mate, &h->s_sb, &h->s_cigar,
                       &h->s_payload, &h->s_tid, &h->s_pos, &h->s_meta, &h->s_len, &h->s_soff, &h->s_ins, &h->s_stop,
                       &h->s_eaf, &h->s_counts, &h->s_stats};
     for (DevBuf *b : bufs) b->release();
@@ -123,11 +123,10 @@ extern "C" int64_t vfk_launch_count(vfk_handle *h) { return h ? h->launches : 0;
 static int check_batches(const vfk_read_batch *r, const vfk_variant_batch *v, const vfk_params *p) {
     if (!r || !v || !p) return fail(VFK_EINVAL, "NULL batch or params");
     if (r->n_reads < 0 || v->n_units < 0 || r->n_contigs < 0) return fail(VFK_EINVAL, "negative size");
-    if (r->n_levels < 1 || r->n_levels > 7) return fail(VFK_EINVAL, "position index: n_levels out of range");
     if (r->n_reads > 0x7FFFFFFF) return fail(VFK_EUNSUPPORTED, "more than 2^31-1 reads in one batch: split it");
     if (r->max_l_qseq > VFK_MAX_READ_LEN) return fail(VFK_EUNSUPPORTED, "read longer than VFK_MAX_READ_LEN");
     if (!r->contig_off) return fail(VFK_EINVAL, "contig_off is NULL");
-    if (r->n_reads > 0 && (!r->hot || !r->cold || !r->mate || !r->sb || !r->tree || !r->payload))
+    if (r->n_reads > 0 && (!r->hot || !r->cold || !r->mate || !r->sb || !r->payload))
         return fail(VFK_EINVAL, "read batch has a NULL array");
     if (v->n_units > 0 && (!v->tid || !v->pos || !v->meta || !v->length || !v->seq_off || !v->ins_seq))
         return fail(VFK_EINVAL, "variant batch has a NULL array");
@@ -139,9 +138,6 @@ static void to_dev(const vfk_read_batch *r, const vfk_variant_batch *v, vfk::Rea
     R.cold = (const uint4 *)r->cold;
     R.mate = r->mate;
     R.sb = (const int2 *)r->sb;
-    R.tree = r->tree;
-    for (int k = 0; k < 8; ++k) { R.tree_off[k] = r->tree_off[k]; R.tree_cnt[k] = r->tree_cnt[k]; }
-    R.n_levels = r->n_levels;
     R.cigar = r->cigar;
     R.payload = r->payload;
     R.contig_off = r->contig_off;
@@ -168,11 +164,13 @@ extern "C" int vfk_pileup(vfk_handle *h, const vfk_read_batch *reads, const vfk_
     cudaStream_t st = (cudaStream_t)stream;  // NULL = the CUDA default stream
     rc = h->deferred.reserve((size_t)units->n_units * sizeof(uint32_t));
     if (rc) return rc;
+    rc = h->resolved.reserve((size_t)units->n_units * 32);
+    if (rc) return rc;
     vfk::ReadsDev R;
     vfk::UnitsDev V;
     to_dev(reads, units, R, V);
     int launches = 0;
-    cudaError_t e = vfk::launch_pileup(R, V, *params, reads->max_l_qseq, out, h->work_counter, (uint32_t *)h->deferred.p,
+    cudaError_t e = vfk::launch_pileup(R, V, *params, reads->max_l_qseq, out, h->resolved.p, h->work_counter, (uint32_t *)h->deferred.p,
                                        h->n_deferred, h->sm_count, st, &launches);
     h->launches += launches;
     if (e != cudaSuccess) return fail(VFK_ECUDA, "pileup launch: %s", cudaGetErrorString(e));
@@ -219,7 +217,6 @@ extern "C" int vfk_annotate_host(vfk_handle *h, const vfk_read_batch *reads, con
     STAGE(h->s_cold, reads->cold, (size_t)nr * sizeof(vfk_read_cold));
     STAGE(h->s_mate, reads->mate, (size_t)nr * 4);
     STAGE(h->s_sb, reads->sb, (size_t)nr * 8);
-    STAGE(h->s_tree, reads->tree, (size_t)(reads->tree_off[reads->n_levels] + reads->tree_cnt[reads->n_levels]) * 8);
     STAGE(h->s_cigar, reads->cigar, (size_t)reads->n_cigar_words * 4);
     STAGE(h->s_payload, reads->payload, (size_t)reads->n_sectors * 32);
     STAGE(h->s_tid, units->tid, (size_t)nu * 4);
@@ -240,7 +237,6 @@ extern "C" int vfk_annotate_host(vfk_handle *h, const vfk_read_batch *reads, con
     dr.cold = (const vfk_read_cold *)h->s_cold.p;
     dr.mate = (const uint32_t *)h->s_mate.p;
     dr.sb = (const int32_t *)h->s_sb.p;
-    dr.tree = (const uint64_t *)h->s_tree.p;
     dr.cigar = (const uint32_t *)h->s_cigar.p;
     dr.payload = (const uint8_t *)h->s_payload.p;
     vfk_variant_batch dv = *units;

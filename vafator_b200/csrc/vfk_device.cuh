@@ -22,10 +22,7 @@ struct ReadsDev {
     const uint4 *__restrict__ hot;
     const uint4 *__restrict__ cold;
     const uint32_t *__restrict__ mate;
-    const int2 *__restrict__ sb;        // {start, back}
-    const uint64_t *__restrict__ tree;  // upper levels of the position index
-    int64_t tree_off[8], tree_cnt[8];
-    int32_t n_levels;
+    const int2 *__restrict__ sb;  // {start, back}
     const uint32_t *__restrict__ cigar;
     const uint8_t *__restrict__ payload;
     const int64_t *__restrict__ contig_off;
@@ -44,16 +41,26 @@ struct UnitsDev {
     const int32_t *__restrict__ stop;  // may be nullptr
 };
 
+// A unit after the locate pass: everything the pileup kernels need, one 32-byte record.
+struct __align__(16) ResolvedUnit {
+    int32_t col;       // 0-based column
+    uint32_t meta;     // kind | ref_code << 8 | alt_code << 16
+    int32_t len;       // inserted / deleted length
+    uint32_t ins_off;  // offset of ALT0[1:] in ins_seq
+    uint32_t lo, hi;   // candidate reads [lo, hi): hi = first read starting beyond col, lo = back[hi-1]
+    int32_t stop;      // reads starting at or beyond it were never fetched by the reference
+    uint32_t c1;       // end of the contig's read range
+};
+
 struct Unit {
-    int32_t tid;
-    int32_t col;    // 0-based column
-    int32_t stop;   // reads starting at or beyond it were never fetched by the reference
+    int32_t col;
+    int32_t stop;
     uint32_t kind;
     uint32_t ref_code, alt_code;
     int32_t len;
     const uint8_t *ins;
-    int64_t c0, c1;  // read range of the contig
-    int64_t lo, hi;  // candidate range: pmax_end > col ... starts <= col
+    int64_t c1;
+    int64_t lo, hi;
 };
 
 // one read's contribution to a column
@@ -210,13 +217,12 @@ __device__ __forceinline__ int64_t next_pushed(const ReadsDev &R, const vfk_para
 // htslib tweak_overlap_quality has run for the pair iff the second mate has been pushed, i.e. it
 // starts at or before `col` or is the first pushed record after it (bam_plp_auto reads one ahead).
 __device__ __forceinline__ int tweaked_quality(const ReadsDev &R, const vfk_params &P, const Unit &U, int64_t i,
-                                               const uint4 &hot, const uint4 &cold_if_general, bool general, int q,
-                                               int l_qseq, bool q_is_column_base) {
+                                               const uint4 &hot, uint32_t mw, const uint4 &cold_if_general, bool general,
+                                               int q, int l_qseq, bool q_is_column_base) {
     if (q >= l_qseq) return 0;
     int qi = pay_qual(R.payload, hot.w, (uint32_t)q);
     uint32_t flag = hot.z & 0xFFFFu;
     if (!P.ignore_overlaps || !(flag & F_PROPER) || (flag & F_MUNMAP)) return qi;
-    uint32_t mw = __ldg(R.mate + i);
     if (mw == VFK_NO_MATE) return qi;
     int64_t m = (int64_t)(mw & 0x7FFFFFFFu);
     uint32_t sel = mw >> 31;
@@ -319,11 +325,12 @@ __device__ __forceinline__ uint32_t deletion_hits(const ReadsDev &R, const uint4
     return 0u;
 }
 
-// Everything one read contributes to one unit.
-__device__ __forceinline__ Contribution evaluate(const ReadsDev &R, const vfk_params &P, const Unit &U, int64_t i) {
+// Everything one read contributes to one unit.  `hot` / `mw` are the read's header and mate word
+// (the caller loads them, possibly one unit ahead of use).
+__device__ __forceinline__ Contribution evaluate(const ReadsDev &R, const vfk_params &P, const Unit &U, int64_t i,
+                                                 const uint4 &hot, uint32_t mw) {
     Contribution o;
     o.covers = false; o.in_dp = false; o.ambiguous = false; o.ref = false; o.alt = 0; o.mq = 0; o.bq = 0; o.qpos = 0; o.pos_overflow = false;
-    const uint4 hot = __ldg(R.hot + i);
     const int32_t rpos = (int32_t)hot.x;
     if (U.col < rpos || U.col >= rpos + (int32_t)hot.y) return o;
     o.covers = true;
@@ -340,7 +347,7 @@ __device__ __forceinline__ Contribution evaluate(const ReadsDev &R, const vfk_pa
         r = resolve_general(R, rpos, cold, U.col);
         if (!r.covered) return o;
     }
-    const int q = tweaked_quality(R, P, U, i, hot, cold, general, r.qpos, r.l_qseq, !r.is_del);
+    const int q = tweaked_quality(R, P, U, i, hot, mw, cold, general, r.qpos, r.l_qseq, !r.is_del);
     if (q < P.min_baseq) return o;  // pysam pileup_base_qual_skip
     o.mq = (int)((hot.z >> 16) & 0xFF);
     o.bq = q;
@@ -366,67 +373,21 @@ __device__ __forceinline__ Contribution evaluate(const ReadsDev &R, const vfk_pa
     return o;
 }
 
-// ---- locating the candidate reads of a column ----
-// Position index = a 32-ary search tree stored level by level (host built, vfkio_pack):
-//   level 0   sb[i] = {start_i, back_i}                                   (one int2 per read)
-//   level k   tree[off[k] + j] = (tid << 32 | start) of the LAST read of node j,
-//             node j of level k covering reads [j*32^k, (j+1)*32^k)
-// A lookup reads 32 consecutive entries per level (one 256-byte line group, L2 resident for
-// every level but the last) instead of 32 strided probes of a flat array.
-//   hi = first read of the contig with start > col
-//   lo = back[hi-1] = first read whose running-maximum end exceeds start[hi-1] (<= col), so
-//        every read overlapping col lies in [lo, hi).
-__device__ __forceinline__ void warp_locate(const ReadsDev &R, Unit &U, int lane) {
-    const uint64_t key = ((uint64_t)(uint32_t)U.tid << 32) | (uint32_t)U.col;
-    int64_t node = 0;
-    bool past_end = false;
-    for (int k = R.n_levels; k >= 1; --k) {
-        const uint64_t *__restrict__ lvl = R.tree + R.tree_off[k];
-        const int64_t idx = node * 32 + lane;
-        const bool t = (idx < R.tree_cnt[k]) ? (__ldg(lvl + idx) > key) : true;
-        const unsigned b = __ballot_sync(FULL, t);
-        if (k == R.n_levels && (b == 0u || node * 32 + (__ffs(b) - 1) >= R.tree_cnt[k])) { past_end = true; break; }
-        node = node * 32 + (__ffs(b) - 1);
-    }
-    int64_t hi;
-    int2 mine = make_int2(0, 0);
-    if (past_end) {
-        hi = U.c1;
-    } else {
-        const int64_t idx = node * 32 + lane;
-        bool t = true;
-        if (idx < U.c1) {
-            mine = __ldg(R.sb + idx);
-            t = (idx >= U.c0) ? (mine.x > U.col) : false;
-        }
-        const unsigned b = __ballot_sync(FULL, t);
-        hi = node * 32 + (__ffs(b) - 1);
-        if (hi > U.c1) hi = U.c1;
-        if (hi < U.c0) hi = U.c0;
-    }
-    U.hi = hi;
-    if (hi <= U.c0) { U.lo = hi; return; }
-    // back pointer of read hi-1: it sits in this leaf unless hi is the leaf's first entry
-    const int64_t want = hi - 1;
-    int32_t back;
-    if (!past_end && want >= node * 32) back = __shfl_sync(FULL, mine.y, (int)(want - node * 32));
-    else back = __ldg(&R.sb[want].y);
-    U.lo = (int64_t)back;
+__device__ __forceinline__ Contribution evaluate(const ReadsDev &R, const vfk_params &P, const Unit &U, int64_t i) {
+    return evaluate(R, P, U, i, __ldg(R.hot + i), __ldg(R.mate + i));
 }
 
-__device__ __forceinline__ void load_unit(const ReadsDev &R, const UnitsDev &V, int64_t u, Unit &U) {
-    const int32_t tid = __ldg(V.tid + u);
-    const uint32_t meta = __ldg(V.meta + u);
-    U.tid = tid;
-    U.col = __ldg(V.pos + u);
-    U.stop = V.stop ? __ldg(V.stop + u) : 0x7FFFFFFF;
-    U.kind = meta & 3u;
-    U.ref_code = (meta >> 8) & 0xFFu;
-    U.alt_code = (meta >> 16) & 0xFFu;
-    U.len = __ldg(V.length + u);
-    U.ins = V.ins_seq + __ldg(V.seq_off + u);
-    U.c0 = __ldg(R.contig_off + tid);
-    U.c1 = __ldg(R.contig_off + tid + 1);
+__device__ __forceinline__ void unit_from(const ResolvedUnit &r, const uint8_t *__restrict__ ins_seq, Unit &U) {
+    U.col = r.col;
+    U.stop = r.stop;
+    U.kind = r.meta & 3u;
+    U.ref_code = (r.meta >> 8) & 0xFFu;
+    U.alt_code = (r.meta >> 16) & 0xFFu;
+    U.len = r.len;
+    U.ins = ins_seq + r.ins_off;
+    U.c1 = (int64_t)r.c1;
+    U.lo = (int64_t)r.lo;
+    U.hi = (int64_t)r.hi;
 }
 
 }  // namespace vfk

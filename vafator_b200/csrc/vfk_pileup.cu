@@ -18,7 +18,7 @@
 namespace vfk {
 
 constexpr int WARPS_PER_CTA = 8;
-constexpr int GRAB = 4;
+constexpr int GRAB = 8;  // units a warp takes per visit to the global counter (<= 32)
 constexpr int WARP_PATH_MAX_CAND = 32767;  // u16 bins, weight <= 2 per read
 
 template <int POSB>
@@ -29,6 +29,41 @@ struct Layout {
     static constexpr int BINS = 512 + POSB;  // per slot
     static constexpr int POS_BITS = POSB == 256 ? 8 : POSB == 512 ? 9 : POSB == 1024 ? 10 : 12;
 };
+
+// ------------------------------------------------------------------------------------------
+// locate pass: one THREAD per unit.  A binary search is a chain of dependent loads; with one
+// thread per unit every unit's chain is in flight at once, which a warp-cooperative search
+// cannot offer.  Emits the 32-byte ResolvedUnit records the pileup kernels consume.
+//   hi = first read of the contig starting beyond the column
+//   lo = back[hi-1] = first read whose running-maximum end exceeds start[hi-1] (<= col):
+//        no earlier read can overlap the column
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+locate_kernel(ReadsDev R, UnitsDev V, ResolvedUnit *__restrict__ res) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= V.n) return;
+    const int32_t tid = __ldg(V.tid + u);
+    const int32_t col = __ldg(V.pos + u);
+    const int64_t c0 = __ldg(R.contig_off + tid), c1 = __ldg(R.contig_off + tid + 1);
+    int64_t a = c0, b = c1;
+    while (a < b) {
+        const int64_t m = (a + b) >> 1;
+        if (__ldg(&R.sb[m].x) > col) b = m; else a = m + 1;
+    }
+    ResolvedUnit r;
+    r.col = col;
+    r.meta = __ldg(V.meta + u);
+    r.len = __ldg(V.length + u);
+    r.ins_off = __ldg(V.seq_off + u);
+    r.hi = (uint32_t)a;
+    r.lo = a > c0 ? (uint32_t)__ldg(&R.sb[a - 1].y) : (uint32_t)a;
+    r.stop = V.stop ? __ldg(V.stop + u) : 0x7FFFFFFF;
+    r.c1 = (uint32_t)c1;
+    uint4 *o = reinterpret_cast<uint4 *>(res + u);
+    const uint4 *q = reinterpret_cast<const uint4 *>(&r);
+    o[0] = q[0];
+    o[1] = q[1];
+}
 
 // ------------------------------------------------------------------------------------------
 // histogram access.  CT = uint16_t: two bins per 32-bit word; CT = uint32_t: one bin per word.
@@ -247,9 +282,9 @@ __device__ __noinline__ void unit_by_histogram(const ReadsDev &R, const vfk_para
 // ------------------------------------------------------------------------------------------
 template <int POSB>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
-pileup_warp_kernel(ReadsDev R, UnitsDev V, vfk_params P, vfk_counts *__restrict__ out,
-                   unsigned long long *__restrict__ work_counter, uint32_t *__restrict__ deferred,
-                   uint32_t *__restrict__ n_deferred) {
+pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_units, const uint8_t *__restrict__ ins_seq,
+                   vfk_params P, vfk_counts *__restrict__ out, unsigned long long *__restrict__ work_counter,
+                   uint32_t *__restrict__ deferred, uint32_t *__restrict__ n_deferred) {
     using L = Layout<POSB>;
     constexpr int WORDS = L::BINS / 2;  // u16 bins
     extern __shared__ __align__(16) uint32_t smem[];
@@ -262,12 +297,38 @@ pileup_warp_kernel(ReadsDev R, UnitsDev V, vfk_params P, vfk_counts *__restrict_
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(work_counter, (unsigned long long)GRAB);
         base = __shfl_sync(FULL, base, 0);
-        if ((int64_t)base >= V.n) break;
-        const int64_t end = min((int64_t)base + GRAB, V.n);
-        for (int64_t u = (int64_t)base; u < end; ++u) {
+        if ((int64_t)base >= n_units) break;
+        const int n_here = (int)min((int64_t)GRAB, n_units - (int64_t)base);
+        // lane j keeps the record of unit base+j; one coalesced read for the whole grab
+        uint4 ra = make_uint4(0, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
+        if (lane < n_here) {
+            const uint4 *q = reinterpret_cast<const uint4 *>(res + base + lane);
+            ra = __ldg(q);
+            rb = __ldg(q + 1);
+        }
+        // software pipeline: the header + mate word of the NEXT unit's first 32 candidates are
+        // requested before the current unit is processed
+        uint4 hot_n = make_uint4(0, 0, 0, 0);
+        uint32_t mw_n = VFK_NO_MATE;
+        {
+            const uint32_t lo0 = __shfl_sync(FULL, rb.x, 0), hi0 = __shfl_sync(FULL, rb.y, 0);
+            if (lo0 + lane < hi0) { hot_n = __ldg(R.hot + lo0 + lane); mw_n = __ldg(R.mate + lo0 + lane); }
+        }
+        for (int j = 0; j < n_here; ++j) {
+            const int64_t u = (int64_t)base + j;
+            ResolvedUnit ru;
+            ru.col = (int32_t)__shfl_sync(FULL, ra.x, j); ru.meta = __shfl_sync(FULL, ra.y, j);
+            ru.len = (int32_t)__shfl_sync(FULL, ra.z, j); ru.ins_off = __shfl_sync(FULL, ra.w, j);
+            ru.lo = __shfl_sync(FULL, rb.x, j); ru.hi = __shfl_sync(FULL, rb.y, j);
+            ru.stop = (int32_t)__shfl_sync(FULL, rb.z, j); ru.c1 = __shfl_sync(FULL, rb.w, j);
             Unit U;
-            load_unit(R, V, u, U);
-            warp_locate(R, U, lane);
+            unit_from(ru, ins_seq, U);
+            const uint4 hot_c = hot_n;
+            const uint32_t mw_c = mw_n;
+            if (j + 1 < n_here) {
+                const uint32_t lo1 = __shfl_sync(FULL, rb.x, j + 1), hi1 = __shfl_sync(FULL, rb.y, j + 1);
+                if (lo1 + lane < hi1) { hot_n = __ldg(R.hot + lo1 + lane); mw_n = __ldg(R.mate + lo1 + lane); }
+            }
             const int64_t n_cand = U.hi - U.lo;
             int med2[3][2] = {{-1, -1}, {-1, -1}, {-1, -1}};
             uint64_t s2[3] = {0, 0, 0};
@@ -290,7 +351,7 @@ pileup_warp_kernel(ReadsDev R, UnitsDev V, vfk_params P, vfk_counts *__restrict_
             Contribution c0, c1;
             c0.covers = c0.in_dp = c0.ambiguous = c0.ref = false; c0.alt = 0; c0.mq = c0.bq = c0.qpos = 0;
             c1 = c0;
-            if (lane < n_cand) c0 = evaluate(R, P, U, U.lo + lane);
+            if (lane < n_cand) c0 = evaluate(R, P, U, U.lo + lane, hot_c, mw_c);
             if (n_cand > 32 && lane + 32 < n_cand) c1 = evaluate(R, P, U, U.lo + 32 + lane);
             const bool k0 = c0.ref || c0.alt, k1 = c1.ref || c1.alt;
             const uint32_t m0 = __ballot_sync(FULL, k0), m1 = __ballot_sync(FULL, k1);
@@ -339,8 +400,9 @@ pileup_warp_kernel(ReadsDev R, UnitsDev V, vfk_params P, vfk_counts *__restrict_
 // ------------------------------------------------------------------------------------------
 template <int POSB>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-pileup_block_kernel(ReadsDev R, UnitsDev V, vfk_params P, vfk_counts *__restrict__ out,
-                    const uint32_t *__restrict__ deferred, const uint32_t *__restrict__ n_deferred) {
+pileup_block_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, const uint8_t *__restrict__ ins_seq, vfk_params P,
+                    vfk_counts *__restrict__ out, const uint32_t *__restrict__ deferred,
+                    const uint32_t *__restrict__ n_deferred) {
     using L = Layout<POSB>;
     constexpr int WORDS = L::BINS;  // u32 bins
     extern __shared__ __align__(16) uint32_t smem[];
@@ -354,8 +416,7 @@ pileup_block_kernel(ReadsDev R, UnitsDev V, vfk_params P, vfk_counts *__restrict
     for (uint32_t d = blockIdx.x; d < nd; d += gridDim.x) {
         const int64_t u = deferred[d];
         Unit U;
-        load_unit(R, V, u, U);
-        warp_locate(R, U, lane);  // every warp locates for itself (same result)
+        unit_from(res[u], ins_seq, U);
         for (int w = threadIdx.x; w < 2 * WORDS; w += blockDim.x) smem[w] = 0u;
         if (threadIdx.x < 5) red[threadIdx.x] = 0;
         if (threadIdx.x == 0) red_status = U.kind;
@@ -412,7 +473,7 @@ pileup_block_kernel(ReadsDev R, UnitsDev V, vfk_params P, vfk_counts *__restrict
 // host-side launchers (called from vfk_api.cu)
 // ------------------------------------------------------------------------------------------
 template <int POSB>
-static cudaError_t launch_posb(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, vfk_counts *out,
+static cudaError_t launch_posb(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, vfk_counts *out, ResolvedUnit *res,
                                unsigned long long *work_counter, uint32_t *deferred, uint32_t *n_deferred, int sm_count,
                                cudaStream_t stream, int *launches) {
     using L = Layout<POSB>;
@@ -433,12 +494,18 @@ static cudaError_t launch_posb(const ReadsDev &R, const UnitsDev &V, const vfk_p
     if (want < grid) grid = want < 1 ? 1 : want;
     e = cudaMemsetAsync(work_counter, 0, 16, stream);  // work counter and deferred-unit count share one allocation
     if (e != cudaSuccess) return e;
-    pileup_warp_kernel<POSB><<<(unsigned)grid, WARPS_PER_CTA * 32, smem_warp, stream>>>(R, V, P, out, work_counter, deferred, n_deferred);
+    locate_kernel<<<(unsigned)((V.n + 255) / 256), 256, 0, stream>>>(R, V, res);
+    ++*launches;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    pileup_warp_kernel<POSB><<<(unsigned)grid, WARPS_PER_CTA * 32, smem_warp, stream>>>(R, res, V.n, V.ins_seq, P, out, work_counter,
+                                                                                        deferred, n_deferred);
     ++*launches;
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (R.n_reads > WARP_PATH_MAX_CAND) {  // only then can a column be too deep for the warp path
-        pileup_block_kernel<POSB><<<(unsigned)sm_count, WARPS_PER_CTA * 32, smem_block, stream>>>(R, V, P, out, deferred, n_deferred);
+        pileup_block_kernel<POSB><<<(unsigned)sm_count, WARPS_PER_CTA * 32, smem_block, stream>>>(R, res, V.ins_seq, P, out, deferred,
+                                                                                                  n_deferred);
         ++*launches;
         e = cudaGetLastError();
     }
@@ -446,13 +513,13 @@ static cudaError_t launch_posb(const ReadsDev &R, const UnitsDev &V, const vfk_p
 }
 
 cudaError_t launch_pileup(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, int max_l_qseq, vfk_counts *out,
-                          unsigned long long *work_counter, uint32_t *deferred, uint32_t *n_deferred, int sm_count,
+                          void *resolved_scratch, unsigned long long *work_counter, uint32_t *deferred, uint32_t *n_deferred, int sm_count,
                           cudaStream_t stream, int *launches) {
     // read positions run 0 .. l_qseq (a read hanging in a trailing deletion reports l_qseq)
-    if (max_l_qseq < 256) return launch_posb<256>(R, V, P, out, work_counter, deferred, n_deferred, sm_count, stream, launches);
-    if (max_l_qseq < 512) return launch_posb<512>(R, V, P, out, work_counter, deferred, n_deferred, sm_count, stream, launches);
-    if (max_l_qseq < 1024) return launch_posb<1024>(R, V, P, out, work_counter, deferred, n_deferred, sm_count, stream, launches);
-    return launch_posb<4096>(R, V, P, out, work_counter, deferred, n_deferred, sm_count, stream, launches);
+    if (max_l_qseq < 256) return launch_posb<256>(R, V, P, out, (ResolvedUnit *)resolved_scratch, work_counter, deferred, n_deferred, sm_count, stream, launches);
+    if (max_l_qseq < 512) return launch_posb<512>(R, V, P, out, (ResolvedUnit *)resolved_scratch, work_counter, deferred, n_deferred, sm_count, stream, launches);
+    if (max_l_qseq < 1024) return launch_posb<1024>(R, V, P, out, (ResolvedUnit *)resolved_scratch, work_counter, deferred, n_deferred, sm_count, stream, launches);
+    return launch_posb<4096>(R, V, P, out, (ResolvedUnit *)resolved_scratch, work_counter, deferred, n_deferred, sm_count, stream, launches);
 }
 
 }  // namespace vfk

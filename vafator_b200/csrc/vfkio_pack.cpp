@@ -56,25 +56,12 @@ extern "C" int vfkio_pack_plan(const vfkio_reads *r, vfkio_plan *plan) {
     plan->n_cigar_words = words;
     plan->n_sectors = sectors;
     plan->max_l_qseq = maxl;
-    // upper levels of the 32-ary position index: level k has ceil(n / 32^k) entries, up to a root of <= 32
-    plan->n_levels = 0;
-    plan->n_tree = 0;
-    for (int k = 0; k < 8; ++k) plan->tree_off[k] = plan->tree_cnt[k] = 0;
-    int64_t cnt = placed;
-    while (cnt > 32 || plan->n_levels == 0) {
-        cnt = (cnt + 31) / 32;
-        if (cnt < 1) cnt = 1;
-        const int k = ++plan->n_levels;
-        plan->tree_off[k] = plan->n_tree;
-        plan->tree_cnt[k] = cnt;
-        plan->n_tree += cnt;
-        if (k == 7) break;
-    }
+    plan->pad = 0;
     return VFK_OK;
 }
 
 extern "C" int vfkio_pack(const vfkio_reads *r, const vfkio_plan *plan, int64_t *contig_off, vfk_read_hot *hot,
-                          vfk_read_cold *cold, int32_t *sb, uint64_t *tree, uint32_t *cigar, uint8_t *payload) {
+                          vfk_read_cold *cold, int32_t *sb, uint32_t *cigar, uint8_t *payload) {
     if (!r || !plan || !contig_off) return vfkio_fail(VFK_EINVAL, "vfkio_pack: NULL argument");
     const int64_t n = plan->n_placed;
     // per-read offsets (serial prefix sums), then a parallel fill
@@ -139,16 +126,6 @@ extern "C" int vfkio_pack(const vfkio_reads *r, const vfkio_plan *plan, int64_t 
         for (int64_t i = a; i < b; ++i) {
             while (j < i && pmax[(size_t)(j - a)] <= (int64_t)hot[i].pos) ++j;
             sb[2 * i + 1] = (int32_t)j;
-        }
-    }
-    // upper levels: key of the last read of every node
-    for (int k = 1; k <= plan->n_levels; ++k) {
-        uint64_t *lvl = tree + plan->tree_off[k];
-        int64_t width = 1;
-        for (int q = 0; q < k; ++q) width *= 32;
-        for (int64_t j = 0; j < plan->tree_cnt[k]; ++j) {
-            const int64_t last = std::min<int64_t>((j + 1) * width, n) - 1;
-            lvl[j] = last >= 0 ? (((uint64_t)(uint32_t)r->tid[last] << 32) | (uint32_t)r->pos[last]) : ~0ull;
         }
     }
     return VFK_OK;

@@ -37,8 +37,7 @@ class VfkError(RuntimeError):
 class _ReadBatchC(C.Structure):
     _fields_ = [("n_reads", C.c_int64), ("n_contigs", C.c_int32), ("max_l_qseq", C.c_int32),
                 ("contig_off", C.c_void_p), ("hot", C.c_void_p), ("cold", C.c_void_p), ("mate", C.c_void_p),
-                ("sb", C.c_void_p), ("tree", C.c_void_p), ("tree_off", C.c_int64 * 8), ("tree_cnt", C.c_int64 * 8),
-                ("n_levels", C.c_int32), ("pad", C.c_int32), ("cigar", C.c_void_p), ("payload", C.c_void_p),
+                ("sb", C.c_void_p), ("cigar", C.c_void_p), ("payload", C.c_void_p),
                 ("n_cigar_words", C.c_int64), ("n_sectors", C.c_int64)]
 
 
@@ -68,8 +67,7 @@ class _IoReadsC(C.Structure):
 
 class _PlanC(C.Structure):
     _fields_ = [("n_placed", C.c_int64), ("n_cigar_words", C.c_int64), ("n_sectors", C.c_int64),
-                ("max_l_qseq", C.c_int32), ("n_levels", C.c_int32), ("tree_off", C.c_int64 * 8),
-                ("tree_cnt", C.c_int64 * 8), ("n_tree", C.c_int64)]
+                ("max_l_qseq", C.c_int32), ("pad", C.c_int32)]
 
 
 _IO_DT = dict(tid=np.int32, pos=np.int32, flag=np.uint16, mapq=np.uint8, l_qseq=np.int32, n_cigar=np.int32,
@@ -157,10 +155,6 @@ class PackedReads:
     cold: np.ndarray
     mate: np.ndarray
     sb: np.ndarray        # [n, 2] int32 {start, back}
-    tree: np.ndarray      # uint64, upper levels of the position index
-    tree_off: list
-    tree_cnt: list
-    n_levels: int
     cigar: np.ndarray
     payload: np.ndarray
     max_l_qseq: int
@@ -174,16 +168,13 @@ class PackedReads:
         return int(self.hot.shape[0])
 
     def nbytes(self) -> int:
-        return int(sum(a.nbytes for a in (self.contig_off, self.hot, self.cold, self.mate, self.sb, self.tree,
-                                          self.cigar, self.payload)))
+        return int(sum(a.nbytes for a in (self.contig_off, self.hot, self.cold, self.mate, self.sb, self.cigar,
+                                          self.payload)))
 
     def c_struct(self, arrays: Optional[Dict[str, int]] = None) -> _ReadBatchC:
         p = arrays or {k: getattr(self, k).ctypes.data for k in
-                       ("contig_off", "hot", "cold", "mate", "sb", "tree", "cigar", "payload")}
+                       ("contig_off", "hot", "cold", "mate", "sb", "cigar", "payload")}
         s = _ReadBatchC()
-        s.n_levels = self.n_levels
-        for k in range(8):
-            s.tree_off[k], s.tree_cnt[k] = self.tree_off[k], self.tree_cnt[k]
         s.n_reads, s.n_contigs, s.max_l_qseq = self.n_reads, len(self.contigs), self.max_l_qseq
         s.n_cigar_words, s.n_sectors = int(self.cigar.shape[0]), int(self.payload.shape[0] // 32)
         for k, v in p.items():
@@ -209,17 +200,16 @@ def pack_reads(batch: ReadBatch, params: ParamsC, pinned: bool = False) -> Packe
     hot = _empty(n, HOT_DTYPE, pinned)
     cold = _empty(n, COLD_DTYPE, pinned)
     sb = _empty(2 * n, np.int32, pinned)
-    tree = _empty(max(plan.n_tree, 1), np.uint64, pinned)[:plan.n_tree]
     cigar = _empty(max(plan.n_cigar_words, 1), np.uint32, pinned)[:plan.n_cigar_words]
     payload = _empty(plan.n_sectors * 32, np.uint8, pinned)
     _io_check(libio().vfkio_pack(C.byref(s), C.byref(plan), C.c_void_p(contig_off.ctypes.data),
                                  C.c_void_p(hot.ctypes.data), C.c_void_p(cold.ctypes.data),
-                                 C.c_void_p(sb.ctypes.data), C.c_void_p(tree.ctypes.data),
+                                 C.c_void_p(sb.ctypes.data),
                                  C.c_void_p(cigar.ctypes.data), C.c_void_p(payload.ctypes.data)))
     mate = _empty(n, np.uint32, pinned)
     _io_check(libio().vfkio_link_mates(C.byref(s), C.byref(params), C.c_void_p(mate.ctypes.data)))
-    return PackedReads(list(batch.contigs), contig_off, hot, cold, mate, sb.reshape(-1, 2), tree, list(plan.tree_off),
-                       list(plan.tree_cnt), int(plan.n_levels), cigar, payload, int(plan.max_l_qseq))
+    return PackedReads(list(batch.contigs), contig_off, hot, cold, mate, sb.reshape(-1, 2), cigar, payload,
+                       int(plan.max_l_qseq))
 
 
 def units_c_struct(u: VariantUnits, stop: Optional[np.ndarray], ptrs: Optional[Dict[str, int]] = None) -> _VariantBatchC:
@@ -242,7 +232,7 @@ class DeviceReads:
         import torch
         self.packed = packed
         self.t = {}
-        for k in ("contig_off", "hot", "cold", "mate", "sb", "tree", "cigar", "payload"):
+        for k in ("contig_off", "hot", "cold", "mate", "sb", "cigar", "payload"):
             a = getattr(packed, k)
             h = torch.from_numpy(a.view(np.uint8).reshape(-1)) if a.size else torch.zeros(16, dtype=torch.uint8)
             self.t[k] = h.to(device, non_blocking=non_blocking) if a.size else h.to(device)
