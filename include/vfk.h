@@ -122,7 +122,8 @@ typedef struct {
     uint32_t n_cand;    /* candidate reads inspected                                              */
     uint64_t s2[3];     /* [mq,bq,pos]: twice the sum of the ALT mid-ranks in the pooled ranking   */
     uint32_t n_cover;   /* reads overlapping the column before any filter (D_raw of SURVEY.md 8d)   */
-    uint32_t reserved;
+    uint32_t n_col;     /* reads in the htslib column (read filter passed) BEFORE the base-quality filter:
+                           0 means the reference sees no column at all (-> EMPTY_METRICS)             */
 } vfk_counts; /* 80 bytes */
 
 /* ---- epilogue output: FP64, unrounded ------------------------------------------------------ */
@@ -156,6 +157,20 @@ int vfk_epilogue(vfk_handle *h, int64_t n_units, const vfk_counts *counts, const
 int vfk_annotate_host(vfk_handle *h, const vfk_read_batch *reads, const vfk_variant_batch *units,
                       const vfk_params *params, const double *eaf, double fpr, double error_rate,
                       vfk_counts *counts_out, vfk_stats *stats_out);
+
+/* ---- list-shaped auxiliaries (DEVICE pointers) ------------------------------------------------
+ * vfk_pileup_values: per unit, the per-read values the reference keeps in all_mqs / all_bqs /
+ * all_positions (vafator/pileups.py:214-216), one packed word each:
+ *     mq | bq << 8 | read_position << 16 | in_REF_list << 28 | in_ALT_list << 29
+ * values[u * max_per_unit + k], n_values[u] = number of values (may exceed max_per_unit: call
+ * again with a larger buffer).  Used for the replicate merge of vafator/annotator.py:285-287.
+ * vfk_ranksum_values: s2[p][mq,bq,pos] = twice the ALT mid-rank sum of the pooled lists of pair p
+ * (alt[alt_off[p]:alt_off[p+1]] vs ref[ref_off[p]:ref_off[p+1]]), packed words as above -- the
+ * integer core of scipy.stats.ranksums(x=alt, y=ref) behind vafator/rank_sum_test.py:6-26.     */
+int vfk_pileup_values(vfk_handle *h, const vfk_read_batch *reads, const vfk_variant_batch *units,
+                      const vfk_params *params, int32_t max_per_unit, uint32_t *values, int32_t *n_values, void *stream);
+int vfk_ranksum_values(vfk_handle *h, int64_t n_pairs, const uint32_t *alt, const int64_t *alt_off, const uint32_t *ref,
+                       const int64_t *ref_off, uint64_t *s2, void *stream);
 
 /* Number of kernel launches issued through this handle since it was created. */
 int64_t vfk_launch_count(vfk_handle *h);

@@ -54,6 +54,24 @@ int vfkio_pack(const vfkio_reads *r, const vfkio_plan *plan, int64_t *contig_off
  * tie_break << 31 or VFK_NO_MATE, for the reads the reference would push under `params`. */
 int vfkio_link_mates(const vfkio_reads *r, const vfk_params *params, uint32_t *mate /*[n_placed]*/);
 
+/* ---- BGZF / BAM decoding (coordinate-sorted BAM; CRAM is reported as unsupported) -----------
+ * vfkio_bam_open inflates the file (blocks in parallel) and indexes its placed records;
+ * vfkio_bam_fill writes them, in file order, into caller-allocated canonical arrays sized by
+ * vfkio_bam_plan.  Unplaced reads (tid < 0) are skipped: they can never reach a pileup column. */
+typedef struct vfkio_bam vfkio_bam;
+typedef struct {
+    int64_t n_reads, n_cigar, n_seq_bytes, n_qual_bytes;
+} vfkio_synth_plan; /* also the size plan of the synthetic generator below */
+int vfkio_bam_open(const char *path, vfkio_bam **out);
+void vfkio_bam_close(vfkio_bam *b);
+int32_t vfkio_bam_n_contigs(const vfkio_bam *b);
+const char *vfkio_bam_contig_name(const vfkio_bam *b, int32_t i);
+int64_t vfkio_bam_contig_length(const vfkio_bam *b, int32_t i);
+const char *vfkio_bam_header_text(const vfkio_bam *b);
+int32_t vfkio_bam_is_sorted(const vfkio_bam *b);
+int vfkio_bam_plan(const vfkio_bam *b, vfkio_synth_plan *plan);
+int vfkio_bam_fill(const vfkio_bam *b, vfkio_reads *out);
+
 /* ---- synthetic read batches: seeded, reproducible, generated tile by tile ----
  * A contig is covered by `tiles_per_contig` tiles starting every `tile_stride` bases from
  * `tile_offset`; the first mate of each of the `pairs_per_tile` pairs of a tile starts inside
@@ -75,10 +93,6 @@ typedef struct {
     float p_dup, p_supp, p_secondary, p_qcfail, p_orphan;
     float p_mapq60, base_error, p_n;
 } vfkio_synth_cfg;
-
-typedef struct {
-    int64_t n_reads, n_cigar, n_seq_bytes, n_qual_bytes;
-} vfkio_synth_plan;
 
 /* tile_sizes: [4 * n_contigs * tiles_per_contig] scratch filled by the plan pass and handed to the fill pass */
 int vfkio_synth_plan_reads(const vfkio_synth_cfg *cfg, vfkio_synth_plan *plan, int64_t *tile_sizes);

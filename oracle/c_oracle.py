@@ -42,7 +42,7 @@ class _Variants(C.Structure):
 
 
 COUNTS_DTYPE = np.dtype([("supported", "<i4"), ("dp", "<i4"), ("n_amb", "<i4"), ("ac_ref", "<i4"), ("ac_alt", "<i4"),
-                         ("n_val", "<i4", (3, 2)), ("med2", "<i4", (3, 2)), ("_pad", "<i4"), ("s2", "<u8", (3,))])
+                         ("n_val", "<i4", (3, 2)), ("med2", "<i4", (3, 2)), ("_pad", "<i4"), ("s2", "<u8", (3,)), ("n_col", "<i4"), ("_pad2", "<i4")])
 
 _DT = dict(tid=np.int32, pos=np.int32, flag=np.uint16, mapq=np.uint8, l_qseq=np.int32, n_cigar=np.int32,
            cigar_off=np.int64, seq_off=np.int64, qual_off=np.int64, cigar=np.uint32, seq=np.uint8, qual=np.uint8,

@@ -60,6 +60,8 @@ typedef struct {
     int32_t n_val[3][2]; /* [mq,bq,pos][ref,alt] number of values in the distribution */
     int32_t med2[3][2];  /* twice the median, -1 when empty */
     uint64_t s2[3];      /* twice the sum of the ALT mid-ranks in the pooled ranking */
+    int32_t n_col;       /* reads in the htslib column before the base-quality filter (0: no column) */
+    int32_t pad;
 } orc_counts;
 
 static inline int is_ref_op(int op) { return op == OP_M || op == OP_D || op == OP_N || op == OP_EQ || op == OP_X; }
@@ -376,6 +378,7 @@ int orc_pileup(const orc_reads *r, const orc_variants *v, const orc_params *p, c
             if (!read_passes(r, i, p)) continue;
             plp_t pl = resolve_at(r, i, p0);
             if (!pl.covered) continue;
+            o->n_col++;
             int q = tweaked_qual(r, mate, i, pl.qpos, p0, nxt);
             if (q < p->min_baseq) continue; /* pysam pileup_base_qual_skip */
             int mq = r->mapq[i];

@@ -1,0 +1,117 @@
+"""CPU tests of the formats and CLI surface around the hot path."""
+import gzip
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import helpers as H
+from vafator_b200 import bamio, vcf
+from vafator_b200.batch import ReadBatch
+from vafator_b200.command_line import _validate_alignment_file_extension, annotator as cli, build_parser
+from vafator_b200.ploidies import PloidyManager
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_RES = "/root/reference/vafator/tests/resources"
+
+
+def test_help_exits_zero():
+    """BASELINE config 1, literally tests/integration_test_00.sh:4 -- `vafator --help`."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "vafator"), "--help"], capture_output=True, text=True)
+    assert r.returncode == 0 and "--input-vcf" in r.stdout and "--bam" in r.stdout
+
+
+def test_cli_defaults_and_validation():
+    a = build_parser().parse_args(["--input-vcf", "x", "--output-vcf", "y"])
+    assert (a.mapping_quality, a.base_call_quality, a.normal_ploidy, a.fpr, a.error_rate) == (1, 30, 2, 5e-7, 1e-3)
+    assert a.exclude_ambiguous_bases is False and a.num_processes == 1
+    with pytest.raises(ValueError, match="SAM input is not supported"):
+        _validate_alignment_file_extension("reads.sam")
+    with pytest.raises(ValueError, match="at least one bam"):
+        cli(["--input-vcf", "x", "--output-vcf", "y"])
+    with pytest.raises(ValueError, match="purity value for a sample for which no BAM"):
+        cli(["--input-vcf", "x", "--output-vcf", "y", "--bam", "t", "a.bam", "--purity", "n", "0.5"])
+    with pytest.raises(ValueError, match="Multiple purity"):
+        cli(["--input-vcf", "x", "--output-vcf", "y", "--bam", "t", "a.bam", "--purity", "t", "0.5", "--purity", "t", "0.6"])
+    with pytest.raises(ValueError, match="neither a copy number value or a BED"):
+        cli(["--input-vcf", "x", "--output-vcf", "y", "--bam", "t", "a.bam", "--tumor-ploidy", "t", "/no/such.bed"])
+
+
+def test_ploidy_manager_reference_cases(tmp_path):
+    """vafator/tests/test_ploidy_manager.py:10-114 boundary cases (BED reproduced here)."""
+    assert PloidyManager().ploidy == 2.0
+    assert PloidyManager(genome_wide_ploidy=3.5).get_ploidies(["chr1"], [5])[0] == 3.5
+    bed = tmp_path / "cn.bed"
+    bed.write_text("chr1\t10000\t20000\t1.2\nchr1\t20000\t30000\t2.1\nchr2\t10000\t20000\t3.2\n")
+    pm = PloidyManager(local_copy_numbers=str(bed))
+    assert pm.get_ploidies(["chr1"] * 4 + ["chr2", "chr3"], [10000, 10001, 20000, 20001, 15000, 15000]).tolist() == \
+        [2.0, 1.2, 1.2, 2.1, 3.2, 2.0]
+    assert pm.report_value == str(bed)
+    with pytest.raises(ValueError):
+        PloidyManager(local_copy_numbers="/no/such/file.bed")
+    # overlapping rows: the first one in file order wins; numeric-only chromosome names never match (pandas dtype)
+    bed.write_text("chr1\t0\t100\t4\nchr1\t50\t200\t6\n")
+    assert PloidyManager(local_copy_numbers=str(bed)).get_ploidies(["chr1"] * 2, [60, 150]).tolist() == [4.0, 6.0]
+    bed.write_text("1\t0\t100\t4\n")
+    assert PloidyManager(local_copy_numbers=str(bed)).get_ploidies(["1"], [60]).tolist() == [2.0]
+
+
+def test_vcf_round_trip(tmp_path):
+    src = tmp_path / "a.vcf"
+    src.write_text("##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS1\n"
+                   "chr1\t10\t.\tA\tT,G\t.\tPASS\tDP=3;X\tGT\t0/1\nchr1\t12\trs1\tAT\tA\t50\t.\t.\tGT\t1/1\n")
+    for out_name in ("o.vcf", "o.vcf.gz"):
+        r = vcf.VcfReader(str(src))
+        r.add_to_header("##note=1")
+        r.add_info_to_header({"ID": "t_af", "Number": "A", "Type": "Float", "Description": "d"})
+        w = vcf.VcfWriter(str(tmp_path / out_name), r)
+        recs = list(r)
+        assert (recs[0].CHROM, recs[0].POS, recs[0].REF, recs[0].ALT) == ("chr1", 10, "A", ["T", "G"])
+        recs[0].INFO["t_af"] = "0.5,0.1"
+        recs[0].INFO["DP"] = 9
+        recs[1].INFO["t_dp"] = 4
+        for x in recs:
+            w.write_record(x)
+        w.close()
+        opener = gzip.open if out_name.endswith(".gz") else open
+        lines = opener(tmp_path / out_name, "rt").read().splitlines()
+        assert lines[:4] == ["##fileformat=VCFv4.2", "##note=1", '##INFO=<ID=t_af,Number=A,Type=Float,Description="d">',
+                             "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS1"]
+        assert lines[4].split("\t")[7] == "DP=9;X;t_af=0.5,0.1" and lines[4].endswith("GT\t0/1")
+        assert lines[5].split("\t")[7] == "t_dp=4"
+        assert [x.POS for x in vcf.VcfReader(str(tmp_path / out_name))] == [10, 12]
+
+
+def test_bam_round_trip(tmp_path):
+    sc = H.load_scenario(H.golden_scenarios()[0])
+    p = tmp_path / "t.bam"
+    bamio.write_bam(str(p), sc["bams"][0], sc["contigs"])
+    b = bamio.BamFile(str(p))
+    got, want = b.read_batch(), ReadBatch.from_records(sc["bams"][0], sc["contigs"])
+    assert b.contigs == sc["contigs"]
+    for k in ("tid", "pos", "flag", "mapq", "l_qseq", "n_cigar", "cigar", "seq", "qual", "mtid", "mpos", "isize",
+              "qname_id", "qname_hash"):
+        assert np.array_equal(getattr(got, k), getattr(want, k)), k
+    (tmp_path / "bad.bam").write_bytes(b"not a bam")
+    with pytest.raises(ValueError):
+        bamio.BamFile(str(tmp_path / "bad.bam"))
+    with pytest.raises(FileNotFoundError):
+        bamio.BamFile(str(tmp_path / "missing.bam"))
+    unsorted = list(reversed(sc["bams"][0]))
+    bamio.write_bam(str(tmp_path / "u.bam"), unsorted, sc["contigs"])
+    with pytest.raises(ValueError, match="not coordinate sorted"):
+        bamio.BamFile(str(tmp_path / "u.bam")).read_batch()
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_RES, "TESTX_S1_L001.bam")), reason="reference checkout not present")
+def test_decoder_on_the_references_real_bams():
+    """The two real BAMs the reference ships (bwa, 101 bp, 4 contigs): record census from SURVEY.md 8(c)."""
+    b = bamio.BamFile(os.path.join(REF_RES, "TESTX_S1_L001.bam"))
+    r = b.read_batch()
+    assert b.contigs == ["chr1", "chr2", "chr3", "chr4"] and list(b.lengths) == [1000000] * 4
+    ops = np.bincount(r.cigar & 15, minlength=9)
+    assert (ops[2], ops[1], ops[4]) == (34, 18, 124)  # D / I / S operations
+    assert int(np.count_nonzero((r.flag & 4) == 0)) == 638 and set(np.unique(r.l_qseq)) == {101}
+    r.check_sorted()

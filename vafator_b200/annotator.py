@@ -1,0 +1,119 @@
+"""Annotator -- same constructor, same `run()`, same output contract as vafator/annotator.py:68-500;
+the three arithmetic call sites (collect_metrics_for_chrom, get_rank_sum_tests, PowerCalculator.*)
+are served by the CUDA library through vafator_b200.engine.Engine."""
+from __future__ import annotations
+
+import datetime
+import json
+import os
+from collections import OrderedDict
+
+import numpy as np
+
+import vafator_b200
+from .bamio import BamFile
+from .constants import BATCH_SIZE, _HEADER_TEMPLATES, _REPLICATE_HEADER_TEMPLATES
+from .engine import Engine
+from .ploidies import DEFAULT_PLOIDY
+from .power import DEFAULT_ERROR_RATE, DEFAULT_FPR, PowerCalculator
+from .vcf import VcfReader, VcfWriter
+
+
+class Annotator(object):
+
+    def __init__(self, input_vcf: str, output_vcf: str, input_bams: dict, purities: dict = None,
+                 mapping_qual_thr: int = 0, base_call_qual_thr: int = 29, tumor_ploidies: dict = None,
+                 normal_ploidy: int = 2, fpr: float = DEFAULT_FPR, error_rate: float = DEFAULT_ERROR_RATE,
+                 include_ambiguous_bases: bool = True, num_processes: int = 1, device: int = 0):
+        """Arguments as vafator/annotator.py:70-98.  `num_processes` is accepted for compatibility (the
+        reference forks one CPU worker per chromosome); here all chromosomes go to the GPU in one batch.
+        `device`: CUDA device index."""
+        purities = {} if purities is None else purities
+        tumor_ploidies = {} if tumor_ploidies is None else tumor_ploidies
+        self.mapping_quality_threshold = mapping_qual_thr
+        self.base_call_quality_threshold = base_call_qual_thr
+        self.purities = purities
+        self.tumor_ploidies = tumor_ploidies
+        self.normal_ploidy = normal_ploidy
+        self.include_ambiguous_bases = include_ambiguous_bases
+        self.num_processes = num_processes
+        self.power = PowerCalculator(normal_ploidy=normal_ploidy, tumor_ploidies=tumor_ploidies, purities=purities,
+                                     error_rate=error_rate, fpr=fpr, device_index=device)
+        self.vcf = VcfReader(input_vcf)
+        # provenance header, key for key as vafator/annotator.py:123-154
+        self.header = {
+            "name": "vafator",
+            "version": vafator_b200.VERSION,
+            "date": datetime.datetime.now().ctime(),
+            "timestamp": datetime.datetime.now().timestamp(),
+            "input_vcf": os.path.abspath(input_vcf),
+            "output_vcf": os.path.abspath(output_vcf),
+            "bams": ";".join("{}:{}".format(s, ",".join(os.path.abspath(b) for b in bams)) for s, bams in input_bams.items()),
+            "mapping_quality_threshold": mapping_qual_thr,
+            "base_call_quality_threshold": base_call_qual_thr,
+            "purities": ";".join("{}:{}".format(s, p) for s, p in purities.items()),
+            "normal_ploidy": normal_ploidy,
+            "tumor_ploidy": (";".join("{}:{}".format(s, p.report_value) for s, p in tumor_ploidies.items())
+                             if tumor_ploidies else DEFAULT_PLOIDY),
+            "include_ambiguous_bases": include_ambiguous_bases,
+        }
+        self.vcf.add_to_header("##vafator_command_line={}".format(json.dumps(self.header)))
+        for a in Annotator._get_headers(input_bams):
+            self.vcf.add_info_to_header(a)
+        self.vcf_writer = VcfWriter(output_vcf, self.vcf)
+        self.bam_paths = input_bams
+        self.bam_readers = OrderedDict((s, [BamFile(b, "r") for b in bams]) for s, bams in input_bams.items())
+        self.engine = Engine(device, min_mapq=mapping_qual_thr, min_baseq=base_call_qual_thr,
+                             include_ambiguous=include_ambiguous_bases, fpr=fpr, error_rate=error_rate)
+
+    def run(self) -> None:
+        """Annotate every record of the input VCF and write the output VCF."""
+        variants = list(self.vcf)
+        for v in variants:
+            if not v.ALT:
+                raise ValueError("VCF record %s:%d has no ALT allele" % (v.CHROM, v.POS))
+        records = [(v.CHROM, v.POS, v.REF, v.ALT) for v in variants]
+        bams = OrderedDict((s, [r.read_batch() for r in readers]) for s, readers in self.bam_readers.items())
+        chroms = [r[0] for r in records]
+        positions = [r[1] for r in records]
+        eaf = {s: self.power.expected_vafs(s, chroms, positions) for s in bams}
+        infos = self.engine.annotate(records, bams, eaf)
+        batch = []
+        for v, info in zip(variants, infos):
+            v.INFO = info
+            batch.append(v)
+            if len(batch) >= BATCH_SIZE:
+                self._write_batch(batch)
+                batch.clear()
+        if batch:
+            self._write_batch(batch)
+        self.vcf_writer.close()
+        self.vcf.close()
+        self.engine.release_reads()
+        for readers in self.bam_readers.values():
+            for bam in readers:
+                bam.close()
+
+    def _write_batch(self, batch: list) -> None:
+        for v in batch:
+            self.vcf_writer.write_record(v)
+
+    @staticmethod
+    def _get_headers(input_bams: dict) -> list:
+        """INFO header entries for all samples and replicates (vafator/annotator.py:443-468)."""
+        headers = []
+        for s, bams in input_bams.items():
+            for suffix, description, typ, number in _HEADER_TEMPLATES:
+                headers.append(Annotator._make_header(suffix, description, typ, number, sample=s))
+            if len(bams) > 1:
+                for i in range(1, len(bams) + 1):
+                    for suffix, description, typ, number in _REPLICATE_HEADER_TEMPLATES:
+                        headers.append(Annotator._make_header(suffix, description, typ, number, sample=s, index=i))
+        return headers
+
+    @staticmethod
+    def _make_header(suffix: str, description: str, typ: str, number: str, sample: str, index: int = None) -> dict:
+        header_id = "{}_{}".format(sample, suffix)
+        if index is not None:
+            header_id = "{}_{}".format(header_id, index)
+        return {"ID": header_id, "Description": description.format(sample=sample), "Type": typ, "Number": number}

@@ -41,7 +41,8 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     srcs = sorted(glob.glob(os.path.join(CSRC, "vfk_*.cu")))
     deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))
     if force or _stale(LIBVFK, deps):
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIBVFK] + srcs
+        extra = os.environ.get("VFK_NVCC_EXTRA", "").split()
+        cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIBVFK] + srcs
         subprocess.check_call(cmd)
     return LIBVFK
 

@@ -13,6 +13,10 @@ cudaError_t launch_pileup(const ReadsDev &R, const UnitsDev &V, const vfk_params
                           cudaStream_t stream, int *launches);
 cudaError_t launch_epilogue(int64_t n_units, const vfk_counts *counts, const double *eaf, double fpr, double error_rate,
                             vfk_stats *out, cudaStream_t stream, int *launches);
+cudaError_t launch_values(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, int32_t max_per_unit, uint32_t *values,
+                          int32_t *n_values, cudaStream_t stream, int *launches);
+cudaError_t launch_ranksum(int64_t n_pairs, const uint32_t *alt, const int64_t *alt_off, const uint32_t *ref,
+                           const int64_t *ref_off, unsigned long long *s2, cudaStream_t stream, int *launches);
 }  // namespace vfk
 
 static thread_local char g_err[512] = "";
@@ -193,6 +197,40 @@ extern "C" int vfk_epilogue(vfk_handle *h, int64_t n_units, const vfk_counts *co
     return VFK_OK;
 }
 
+extern "C" int vfk_pileup_values(vfk_handle *h, const vfk_read_batch *reads, const vfk_variant_batch *units,
+                                 const vfk_params *params, int32_t max_per_unit, uint32_t *values, int32_t *n_values,
+                                 void *stream) {
+    if (!h) return fail(VFK_EINVAL, "vfk_pileup_values: NULL handle");
+    int rc = check_batches(reads, units, params);
+    if (rc) return rc;
+    if (units->n_units == 0) return VFK_OK;
+    if (!values || !n_values || max_per_unit < 1) return fail(VFK_EINVAL, "vfk_pileup_values: bad output buffer");
+    CU(cudaSetDevice(h->device));
+    vfk::ReadsDev R;
+    vfk::UnitsDev V;
+    to_dev(reads, units, R, V);
+    int launches = 0;
+    cudaError_t e = vfk::launch_values(R, V, *params, max_per_unit, values, n_values, (cudaStream_t)stream, &launches);
+    h->launches += launches;
+    if (e != cudaSuccess) return fail(VFK_ECUDA, "values launch: %s", cudaGetErrorString(e));
+    return VFK_OK;
+}
+
+extern "C" int vfk_ranksum_values(vfk_handle *h, int64_t n_pairs, const uint32_t *alt, const int64_t *alt_off,
+                                  const uint32_t *ref, const int64_t *ref_off, uint64_t *s2, void *stream) {
+    if (!h) return fail(VFK_EINVAL, "vfk_ranksum_values: NULL handle");
+    if (n_pairs < 0) return fail(VFK_EINVAL, "vfk_ranksum_values: negative size");
+    if (n_pairs == 0) return VFK_OK;
+    if (!alt || !alt_off || !ref || !ref_off || !s2) return fail(VFK_EINVAL, "vfk_ranksum_values: NULL array");
+    CU(cudaSetDevice(h->device));
+    int launches = 0;
+    cudaError_t e = vfk::launch_ranksum(n_pairs, alt, alt_off, ref, ref_off, (unsigned long long *)s2, (cudaStream_t)stream,
+                                        &launches);
+    h->launches += launches;
+    if (e != cudaSuccess) return fail(VFK_ECUDA, "ranksum launch: %s", cudaGetErrorString(e));
+    return VFK_OK;
+}
+
 #define STAGE(buf, src, bytes)                                                                   \
     do {                                                                                         \
         size_t b_ = (size_t)(bytes);                                                             \
@@ -218,7 +256,22 @@ extern "C" int vfk_annotate_host(vfk_handle *h, const vfk_read_batch *reads, con
     STAGE(h->s_mate, reads->mate, (size_t)nr * 4);
     STAGE(h->s_sb, reads->sb, (size_t)nr * 8);
     STAGE(h->s_cigar, reads->cigar, (size_t)reads->n_cigar_words * 4);
-    STAGE(h->s_payload, reads->payload, (size_t)reads->n_sectors * 32);
+    // The payload is ~85 % of the batch but a sparse variant set touches a few percent of its
+    // sectors.  With VFK_ZERO_COPY_PAYLOAD=1 and a pinned (page-locked) payload buffer the kernel
+    // gathers those sectors straight from host memory over PCIe instead of staging everything.
+    const uint8_t *payload_dev = nullptr;
+    {
+        const char *zc = getenv("VFK_ZERO_COPY_PAYLOAD");
+        cudaPointerAttributes attr;
+        if (zc && zc[0] == '1' && cudaPointerGetAttributes(&attr, reads->payload) == cudaSuccess &&
+            attr.type == cudaMemoryTypeHost && attr.devicePointer)
+            payload_dev = (const uint8_t *)attr.devicePointer;
+        (void)cudaGetLastError();
+    }
+    if (!payload_dev) {
+        STAGE(h->s_payload, reads->payload, (size_t)reads->n_sectors * 32);
+        payload_dev = (const uint8_t *)h->s_payload.p;
+    }
     STAGE(h->s_tid, units->tid, (size_t)nu * 4);
     STAGE(h->s_pos, units->pos, (size_t)nu * 4);
     STAGE(h->s_meta, units->meta, (size_t)nu * 4);
@@ -238,7 +291,7 @@ extern "C" int vfk_annotate_host(vfk_handle *h, const vfk_read_batch *reads, con
     dr.mate = (const uint32_t *)h->s_mate.p;
     dr.sb = (const int32_t *)h->s_sb.p;
     dr.cigar = (const uint32_t *)h->s_cigar.p;
-    dr.payload = (const uint8_t *)h->s_payload.p;
+    dr.payload = payload_dev;
     vfk_variant_batch dv = *units;
     dv.tid = (const int32_t *)h->s_tid.p;
     dv.pos = (const int32_t *)h->s_pos.p;

@@ -66,6 +66,7 @@ struct Unit {
 // one read's contribution to a column
 struct Contribution {
     bool covers;   // the read spans the column (before any filter)
+    bool in_col;   // ... and is part of the htslib column (read filter passed, CIGAR covers it)
     bool in_dp;
     bool ambiguous;
     bool ref;      // value goes to the REF list
@@ -330,7 +331,7 @@ __device__ __forceinline__ uint32_t deletion_hits(const ReadsDev &R, const uint4
 __device__ __forceinline__ Contribution evaluate(const ReadsDev &R, const vfk_params &P, const Unit &U, int64_t i,
                                                  const uint4 &hot, uint32_t mw) {
     Contribution o;
-    o.covers = false; o.in_dp = false; o.ambiguous = false; o.ref = false; o.alt = 0; o.mq = 0; o.bq = 0; o.qpos = 0; o.pos_overflow = false;
+    o.covers = false; o.in_col = false; o.in_dp = false; o.ambiguous = false; o.ref = false; o.alt = 0; o.mq = 0; o.bq = 0; o.qpos = 0; o.pos_overflow = false;
     const int32_t rpos = (int32_t)hot.x;
     if (U.col < rpos || U.col >= rpos + (int32_t)hot.y) return o;
     o.covers = true;
@@ -347,6 +348,7 @@ __device__ __forceinline__ Contribution evaluate(const ReadsDev &R, const vfk_pa
         r = resolve_general(R, rpos, cold, U.col);
         if (!r.covered) return o;
     }
+    o.in_col = true;
     const int q = tweaked_quality(R, P, U, i, hot, mw, cold, general, r.qpos, r.l_qseq, !r.is_del);
     if (q < P.min_baseq) return o;  // pysam pileup_base_qual_skip
     o.mq = (int)((hot.z >> 16) & 0xFF);

@@ -17,6 +17,9 @@
 
 namespace vfk {
 
+#ifndef VFK_MIN_CTAS
+#define VFK_MIN_CTAS 4
+#endif
 constexpr int WARPS_PER_CTA = 8;
 constexpr int GRAB = 8;  // units a warp takes per visit to the global counter (<= 32)
 constexpr int WARP_PATH_MAX_CAND = 32767;  // u16 bins, weight <= 2 per read
@@ -150,13 +153,13 @@ __device__ __noinline__ void reduce_metric(const uint32_t *ref_slot, const uint3
 
 __device__ __forceinline__ void store_counts(vfk_counts *out, int dp, int n_amb, int ac_ref, int ac_alt,
                                              const int med2[3][2], const uint64_t s2[3], uint32_t status, uint32_t n_cand,
-                                             uint32_t n_cover) {
+                                             uint32_t n_cover, uint32_t n_col = 0u) {
     uint4 *o = reinterpret_cast<uint4 *>(out);
     o[0] = make_uint4((uint32_t)dp, (uint32_t)n_amb, (uint32_t)ac_ref, (uint32_t)ac_alt);
     o[1] = make_uint4((uint32_t)med2[0][0], (uint32_t)med2[0][1], (uint32_t)med2[1][0], (uint32_t)med2[1][1]);
     o[2] = make_uint4((uint32_t)med2[2][0], (uint32_t)med2[2][1], status, n_cand);
     o[3] = make_uint4((uint32_t)s2[0], (uint32_t)(s2[0] >> 32), (uint32_t)s2[1], (uint32_t)(s2[1] >> 32));
-    o[4] = make_uint4((uint32_t)s2[2], (uint32_t)(s2[2] >> 32), n_cover, 0u);
+    o[4] = make_uint4((uint32_t)s2[2], (uint32_t)(s2[2] >> 32), n_cover, n_col);
 }
 
 template <typename CT, int POSB>
@@ -188,20 +191,19 @@ __device__ __forceinline__ uint32_t pack(const Contribution &c) {
 }
 
 // For this lane's value v (NBITS wide): which contributing lanes hold a smaller value (lt) and
-// which an equal one (eq, itself included).  Walks the bits from the top; a bit on which all
-// contributing lanes agree cannot separate anything and is skipped (warp-uniform branch).
+// which an equal one (eq, itself included).  Walks the bits from the top, branch free; lanes that
+// do not contribute hold v == 0, so every ballot is already restricted to the contributing set.
 template <int NBITS>
 __device__ __forceinline__ void radix_compare(uint32_t v, uint32_t contributing, uint32_t &lt, uint32_t &eq) {
     lt = 0u;
     eq = contributing;
 #pragma unroll
     for (int bit = NBITS - 1; bit >= 0; --bit) {
-        const bool mine = (v >> bit) & 1u;
-        const uint32_t b = __ballot_sync(FULL, mine) & contributing;
-        if (b == 0u || b == contributing) continue;
-        const uint32_t zeros = eq & ~b;
-        lt |= mine ? zeros : 0u;
-        eq = mine ? (eq & b) : zeros;
+        const uint32_t mine = (v >> bit) & 1u;
+        const uint32_t b = __ballot_sync(FULL, mine);
+        const uint32_t m = 0u - mine;  // all ones when this lane's bit is set
+        lt |= eq & ~b & m;             // equal so far, their bit clear, mine set
+        eq &= b ^ ~m;                  // keep the lanes whose bit equals mine
     }
 }
 
@@ -243,7 +245,7 @@ __device__ __noinline__ void unit_by_histogram(const ReadsDev &R, const vfk_para
         for (int w = lane; w < (2 * WORDS) / 4; w += 32) z[w] = make_uint4(0, 0, 0, 0);
     }
     __syncwarp();
-    int dp = 0, n_amb = 0, ac_ref = 0, ac_alt = 0, n_cover = 0;
+    int dp = 0, n_amb = 0, ac_ref = 0, ac_alt = 0, n_cover = 0, n_col = 0;
     uint32_t status = U.kind;
     const bool with_bq = U.kind == VFK_KIND_SNV;
     for (int64_t b = U.lo; b < U.hi; b += 32) {
@@ -251,6 +253,7 @@ __device__ __noinline__ void unit_by_histogram(const ReadsDev &R, const vfk_para
         if (i < U.hi) {
             const Contribution c = evaluate(R, P, U, i);
             n_cover += c.covers ? 1 : 0;
+            n_col += c.in_col ? 1 : 0;
             dp += c.in_dp ? 1 : 0;
             n_amb += c.ambiguous ? 1 : 0;
             ac_ref += c.ref ? 1 : 0;
@@ -264,6 +267,7 @@ __device__ __noinline__ void unit_by_histogram(const ReadsDev &R, const vfk_para
     ac_ref = __reduce_add_sync(FULL, ac_ref);
     ac_alt = __reduce_add_sync(FULL, ac_alt);
     n_cover = __reduce_add_sync(FULL, n_cover);
+    n_col = __reduce_add_sync(FULL, n_col);
     status = __reduce_or_sync(FULL, status);
     int med2[3][2] = {{-1, -1}, {-1, -1}, {-1, -1}};
     uint64_t s2[3] = {0, 0, 0};
@@ -273,7 +277,8 @@ __device__ __noinline__ void unit_by_histogram(const ReadsDev &R, const vfk_para
         reduce_metric<uint16_t, POSB>(ref_slot, alt_slot, L::POS_OFF, lane, med2[2][0], med2[2][1], s2[2]);
     }
     if (U.kind == VFK_KIND_SNV && !P.include_ambiguous) dp -= n_amb;  // pileups.py:224-227
-    if (lane == 0) store_counts(out, dp, n_amb, ac_ref, ac_alt, med2, s2, status, (uint32_t)(U.hi - U.lo), (uint32_t)n_cover);
+    if (lane == 0) store_counts(out, dp, n_amb, ac_ref, ac_alt, med2, s2, status, (uint32_t)(U.hi - U.lo), (uint32_t)n_cover,
+                                (uint32_t)n_col);
     __syncwarp();
 }
 
@@ -281,7 +286,7 @@ __device__ __noinline__ void unit_by_histogram(const ReadsDev &R, const vfk_para
 // warp per unit
 // ------------------------------------------------------------------------------------------
 template <int POSB>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, VFK_MIN_CTAS)
 pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_units, const uint8_t *__restrict__ ins_seq,
                    vfk_params P, vfk_counts *__restrict__ out, unsigned long long *__restrict__ work_counter,
                    uint32_t *__restrict__ deferred, uint32_t *__restrict__ n_deferred) {
@@ -349,7 +354,7 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
             }
             // ---- shallow: at most two reads per lane ----
             Contribution c0, c1;
-            c0.covers = c0.in_dp = c0.ambiguous = c0.ref = false; c0.alt = 0; c0.mq = c0.bq = c0.qpos = 0;
+            c0.covers = c0.in_col = c0.in_dp = c0.ambiguous = c0.ref = false; c0.alt = 0; c0.mq = c0.bq = c0.qpos = 0;
             c1 = c0;
             if (lane < n_cand) c0 = evaluate(R, P, U, U.lo + lane, hot_c, mw_c);
             if (n_cand > 32 && lane + 32 < n_cand) c1 = evaluate(R, P, U, U.lo + 32 + lane);
@@ -363,6 +368,7 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
             int dp = __popc(__ballot_sync(FULL, c0.in_dp)) + __popc(__ballot_sync(FULL, c1.in_dp));
             const int n_amb = __popc(__ballot_sync(FULL, c0.ambiguous)) + __popc(__ballot_sync(FULL, c1.ambiguous));
             const int n_cover = __popc(__ballot_sync(FULL, c0.covers)) + __popc(__ballot_sync(FULL, c1.covers));
+            const int n_col = __popc(__ballot_sync(FULL, c0.in_col)) + __popc(__ballot_sync(FULL, c1.in_col));
             uint32_t pk = k0 ? pack(c0) : 0u;
             if (m1) {  // move the second chunk's contributions into lanes the first one left free
                 const int n1 = __popc(m1);
@@ -390,7 +396,8 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
                 radix_finish(qp, Rm, Am, is_ref, is_alt, lt, eq, med2[2][0], med2[2][1], s2[2]);
             }
             if (U.kind == VFK_KIND_SNV && !P.include_ambiguous) dp -= n_amb;  // pileups.py:224-227
-            if (lane == 0) store_counts(out + u, dp, n_amb, ac_ref, ac_alt, med2, s2, U.kind, (uint32_t)n_cand, (uint32_t)n_cover);
+            if (lane == 0) store_counts(out + u, dp, n_amb, ac_ref, ac_alt, med2, s2, U.kind, (uint32_t)n_cand, (uint32_t)n_cover,
+                                            (uint32_t)n_col);
         }
     }
 }
@@ -406,7 +413,7 @@ pileup_block_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, const uint
     using L = Layout<POSB>;
     constexpr int WORDS = L::BINS;  // u32 bins
     extern __shared__ __align__(16) uint32_t smem[];
-    __shared__ int red[5];
+    __shared__ int red[6];
     __shared__ uint32_t red_status;
     __shared__ int s_med2[3][2];
     __shared__ unsigned long long s_s2[3];
@@ -418,17 +425,18 @@ pileup_block_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, const uint
         Unit U;
         unit_from(res[u], ins_seq, U);
         for (int w = threadIdx.x; w < 2 * WORDS; w += blockDim.x) smem[w] = 0u;
-        if (threadIdx.x < 5) red[threadIdx.x] = 0;
+        if (threadIdx.x < 6) red[threadIdx.x] = 0;
         if (threadIdx.x == 0) red_status = U.kind;
         if (threadIdx.x < 6) s_med2[threadIdx.x >> 1][threadIdx.x & 1] = -1;
         if (threadIdx.x < 3) s_s2[threadIdx.x] = 0ull;
         __syncthreads();
-        int dp = 0, n_amb = 0, ac_ref = 0, ac_alt = 0, n_cover = 0;
+        int dp = 0, n_amb = 0, ac_ref = 0, ac_alt = 0, n_cover = 0, n_col = 0;
         uint32_t status = U.kind;
         const bool with_bq = U.kind == VFK_KIND_SNV;
         for (int64_t i = U.lo + threadIdx.x; i < U.hi; i += blockDim.x) {
             const Contribution c = evaluate(R, P, U, i);
             n_cover += c.covers ? 1 : 0;
+            n_col += c.in_col ? 1 : 0;
             dp += c.in_dp ? 1 : 0;
             n_amb += c.ambiguous ? 1 : 0;
             ac_ref += c.ref ? 1 : 0;
@@ -440,9 +448,11 @@ pileup_block_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, const uint
         ac_ref = __reduce_add_sync(FULL, ac_ref);
         ac_alt = __reduce_add_sync(FULL, ac_alt);
         n_cover = __reduce_add_sync(FULL, n_cover);
+        n_col = __reduce_add_sync(FULL, n_col);
         status = __reduce_or_sync(FULL, status);
         if (lane == 0) {
             atomicAdd(&red[4], n_cover);
+            atomicAdd(&red[5], n_col);
             atomicAdd(&red[0], dp); atomicAdd(&red[1], n_amb); atomicAdd(&red[2], ac_ref); atomicAdd(&red[3], ac_alt);
             atomicOr(&red_status, status);
         }
@@ -463,7 +473,7 @@ pileup_block_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, const uint
             int d_p = red[0];
             if (U.kind == VFK_KIND_SNV && !P.include_ambiguous) d_p -= red[1];
             store_counts(out + u, d_p, red[1], red[2], red[3], med2, s2, red_status & ~VFK_ST_DEFERRED, (uint32_t)(U.hi - U.lo),
-                         (uint32_t)red[4]);
+                         (uint32_t)red[4], (uint32_t)red[5]);
         }
         __syncthreads();
     }

@@ -1,0 +1,220 @@
+// vfkio_bam.cpp -- BGZF / BAM decoder on zlib: file -> canonical columnar batch.
+//
+// Stands where pysam.AlignmentFile / htslib stand in the reference (vafator/annotator.py:161-164);
+// htslib is not available on either box, so the container format is decoded here
+// from the SAM/BAM specification (SAMv1 section 4): BGZF = concatenated gzip members carrying a
+// 'BC' extra field with the block size; BAM = magic, header text, reference table, records.
+// Blocks are inflated in parallel (OpenMP), records are indexed in one sequential hop and then
+// converted to columns in parallel.  CRAM is not supported (the reference accepts it through
+// htslib; out of scope here and reported as an error).
+#include <zlib.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "vfk_io.h"
+
+int vfkio_fail(int code, const char *msg);
+
+struct vfkio_bam {
+    std::vector<uint8_t> data;  // inflated BAM stream
+    std::vector<std::string> names;
+    std::vector<int64_t> lengths;
+    std::string text;
+    std::vector<int64_t> rec_off;  // offset of every record's block_size field, placed reads only
+    int64_t n_unplaced = 0;
+    int64_t n_cigar = 0, n_seq = 0, n_qual = 0;
+    int32_t sorted = 1;
+};
+
+namespace {
+inline uint32_t le32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+inline uint16_t le16(const uint8_t *p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+
+int inflate_block(const uint8_t *src, size_t n, uint8_t *dst, size_t cap) {
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    if (inflateInit2(&zs, -15) != Z_OK) return -1;
+    zs.next_in = const_cast<uint8_t *>(src);
+    zs.avail_in = (uInt)n;
+    zs.next_out = dst;
+    zs.avail_out = (uInt)cap;
+    int rc = inflate(&zs, Z_FINISH);
+    inflateEnd(&zs);
+    return (rc == Z_STREAM_END && zs.avail_out == 0) ? 0 : -1;
+}
+}  // namespace
+
+extern "C" int vfkio_bam_open(const char *path, vfkio_bam **out) {
+    if (!path || !out) return vfkio_fail(VFK_EINVAL, "vfkio_bam_open: NULL argument");
+    FILE *f = fopen(path, "rb");
+    if (!f) return vfkio_fail(VFK_EINVAL, "cannot open alignment file");
+    fseek(f, 0, SEEK_END);
+    const long fsize = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    std::vector<uint8_t> raw((size_t)std::max<long>(fsize, 0));
+    if (fsize > 0 && fread(raw.data(), 1, (size_t)fsize, f) != (size_t)fsize) {
+        fclose(f);
+        return vfkio_fail(VFK_EINVAL, "short read on alignment file");
+    }
+    fclose(f);
+    if (raw.size() >= 4 && memcmp(raw.data(), "CRAM", 4) == 0)
+        return vfkio_fail(VFK_EUNSUPPORTED, "CRAM input is not supported by this build: convert to BAM");
+    // ---- BGZF block table
+    struct Blk { size_t src, n, dst, isize; };
+    std::vector<Blk> blocks;
+    size_t p = 0, total = 0;
+    while (p + 18 <= raw.size()) {
+        const uint8_t *h = raw.data() + p;
+        if (!(h[0] == 31 && h[1] == 139 && h[2] == 8 && (h[3] & 4))) return vfkio_fail(VFK_EINVAL, "not a BGZF/BAM file");
+        const uint16_t xlen = le16(h + 10);
+        size_t x = p + 12, xe = x + xlen;
+        int bsize = -1;
+        while (x + 4 <= xe && xe <= raw.size()) {
+            const uint16_t slen = le16(raw.data() + x + 2);
+            if (raw[x] == 'B' && raw[x + 1] == 'C' && slen == 2) bsize = le16(raw.data() + x + 4);
+            x += 4 + slen;
+        }
+        if (bsize < 0 || p + (size_t)bsize + 1 > raw.size()) return vfkio_fail(VFK_EINVAL, "corrupt BGZF block header");
+        const size_t blen = (size_t)bsize + 1;
+        const size_t isize = le32(raw.data() + p + blen - 4);
+        blocks.push_back({xe, blen - (xe - p) - 8, total, isize});
+        total += isize;
+        p += blen;
+    }
+    vfkio_bam *b = new vfkio_bam();
+    b->data.resize(total);
+    int bad = 0;
+#pragma omp parallel for schedule(dynamic, 16) reduction(| : bad)
+    for (int64_t i = 0; i < (int64_t)blocks.size(); ++i) {
+        const Blk &k = blocks[(size_t)i];
+        if (k.isize && inflate_block(raw.data() + k.src, k.n, b->data.data() + k.dst, k.isize)) bad |= 1;
+    }
+    if (bad) { delete b; return vfkio_fail(VFK_EINVAL, "BGZF block failed to inflate"); }
+    raw.clear();
+    raw.shrink_to_fit();
+    // ---- BAM header
+    const uint8_t *d = b->data.data();
+    const size_t n = b->data.size();
+    if (n < 12 || memcmp(d, "BAM\1", 4) != 0) { delete b; return vfkio_fail(VFK_EINVAL, "not a BAM file (bad magic)"); }
+    size_t q = 4;
+    const uint32_t l_text = le32(d + q); q += 4;
+    if (q + l_text + 4 > n) { delete b; return vfkio_fail(VFK_EINVAL, "truncated BAM header"); }
+    b->text.assign((const char *)d + q, l_text);
+    q += l_text;
+    const uint32_t n_ref = le32(d + q); q += 4;
+    for (uint32_t r = 0; r < n_ref; ++r) {
+        if (q + 4 > n) { delete b; return vfkio_fail(VFK_EINVAL, "truncated BAM reference table"); }
+        const uint32_t l_name = le32(d + q); q += 4;
+        if (q + l_name + 4 > n) { delete b; return vfkio_fail(VFK_EINVAL, "truncated BAM reference table"); }
+        b->names.emplace_back((const char *)d + q, l_name ? l_name - 1 : 0);
+        q += l_name;
+        b->lengths.push_back((int64_t)le32(d + q));
+        q += 4;
+    }
+    // ---- record index (sequential hop), placed reads only
+    int32_t last_tid = -1, last_pos = -1;
+    bool seen_unplaced = false;
+    while (q + 4 <= n) {
+        const uint32_t bs = le32(d + q);
+        if (bs < 32 || q + 4 + bs > n) { delete b; return vfkio_fail(VFK_EINVAL, "truncated BAM record"); }
+        const uint8_t *r = d + q + 4;
+        const int32_t tid = (int32_t)le32(r), pos = (int32_t)le32(r + 4);
+        if (tid >= 0 && tid < (int32_t)n_ref) {
+            if (seen_unplaced || tid < last_tid || (tid == last_tid && pos < last_pos)) b->sorted = 0;
+            last_tid = tid;
+            last_pos = pos;
+            b->rec_off.push_back((int64_t)q);
+            b->n_cigar += le16(r + 12);
+            const int64_t l_seq = (int64_t)le32(r + 16);
+            b->n_seq += (l_seq + 1) / 2;
+            b->n_qual += l_seq;
+        } else {
+            seen_unplaced = true;
+            ++b->n_unplaced;
+        }
+        q += 4 + bs;
+    }
+    *out = b;
+    return VFK_OK;
+}
+
+extern "C" void vfkio_bam_close(vfkio_bam *b) { delete b; }
+extern "C" int32_t vfkio_bam_n_contigs(const vfkio_bam *b) { return b ? (int32_t)b->names.size() : 0; }
+extern "C" const char *vfkio_bam_contig_name(const vfkio_bam *b, int32_t i) {
+    return (b && i >= 0 && i < (int32_t)b->names.size()) ? b->names[(size_t)i].c_str() : "";
+}
+extern "C" int64_t vfkio_bam_contig_length(const vfkio_bam *b, int32_t i) {
+    return (b && i >= 0 && i < (int32_t)b->lengths.size()) ? b->lengths[(size_t)i] : 0;
+}
+extern "C" const char *vfkio_bam_header_text(const vfkio_bam *b) { return b ? b->text.c_str() : ""; }
+extern "C" int32_t vfkio_bam_is_sorted(const vfkio_bam *b) { return b ? b->sorted : 0; }
+
+extern "C" int vfkio_bam_plan(const vfkio_bam *b, vfkio_synth_plan *plan) {
+    if (!b || !plan) return vfkio_fail(VFK_EINVAL, "vfkio_bam_plan: NULL argument");
+    plan->n_reads = (int64_t)b->rec_off.size();
+    plan->n_cigar = b->n_cigar;
+    plan->n_seq_bytes = b->n_seq;
+    plan->n_qual_bytes = b->n_qual;
+    return VFK_OK;
+}
+
+// khash X31 of the NUL-terminated name and a 64-bit FNV-1a used to group equal names
+static inline void name_hashes(const uint8_t *s, uint32_t l, uint32_t &x31, uint64_t &fnv) {
+    x31 = l ? s[0] : 0;
+    fnv = 0xCBF29CE484222325ull;
+    for (uint32_t i = 0; i < l; ++i) {
+        if (i) x31 = (x31 << 5) - x31 + s[i];
+        fnv = (fnv ^ s[i]) * 0x100000001B3ull;
+    }
+}
+
+extern "C" int vfkio_bam_fill(const vfkio_bam *b, vfkio_reads *out) {
+    if (!b || !out) return vfkio_fail(VFK_EINVAL, "vfkio_bam_fill: NULL argument");
+    if (!b->sorted) return vfkio_fail(VFK_EINVAL, "BAM file is not coordinate sorted");
+    const int64_t n = (int64_t)b->rec_off.size();
+    const uint8_t *d = b->data.data();
+    int32_t *tid = (int32_t *)out->tid, *pos = (int32_t *)out->pos, *lq = (int32_t *)out->l_qseq, *ncg = (int32_t *)out->n_cigar;
+    int32_t *mtid = (int32_t *)out->mtid, *mpos = (int32_t *)out->mpos, *isz = (int32_t *)out->isize;
+    uint16_t *flag = (uint16_t *)out->flag;
+    uint8_t *mapq = (uint8_t *)out->mapq, *seq = (uint8_t *)out->seq, *qual = (uint8_t *)out->qual;
+    int64_t *co = (int64_t *)out->cigar_off, *so = (int64_t *)out->seq_off, *qo = (int64_t *)out->qual_off;
+    uint32_t *cig = (uint32_t *)out->cigar, *qh = (uint32_t *)out->qname_hash;
+    uint64_t *qid = (uint64_t *)out->qname_id;
+    // offsets: serial prefix sums over the record index
+    int64_t c = 0, s = 0, q = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const uint8_t *r = d + b->rec_off[(size_t)i] + 4;
+        co[i] = c; so[i] = s; qo[i] = q;
+        const int64_t l_seq = (int64_t)le32(r + 16);
+        c += le16(r + 12);
+        s += (l_seq + 1) / 2;
+        q += l_seq;
+    }
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        const uint8_t *r = d + b->rec_off[(size_t)i] + 4;
+        tid[i] = (int32_t)le32(r);
+        pos[i] = (int32_t)le32(r + 4);
+        const uint32_t l_name = r[8];
+        mapq[i] = r[9];
+        ncg[i] = le16(r + 12);
+        flag[i] = le16(r + 14);
+        const int64_t l_seq = (int64_t)le32(r + 16);
+        lq[i] = (int32_t)l_seq;
+        mtid[i] = (int32_t)le32(r + 20);
+        mpos[i] = (int32_t)le32(r + 24);
+        isz[i] = (int32_t)le32(r + 28);
+        const uint8_t *name = r + 32;
+        name_hashes(name, l_name ? l_name - 1 : 0, qh[i], qid[i]);
+        const uint8_t *pc = name + l_name;
+        memcpy(cig + co[i], pc, (size_t)ncg[i] * 4);
+        const uint8_t *ps = pc + (size_t)ncg[i] * 4;
+        memcpy(seq + so[i], ps, (size_t)((l_seq + 1) / 2));
+        memcpy(qual + qo[i], ps + (l_seq + 1) / 2, (size_t)l_seq);
+    }
+    out->n = n;
+    out->n_contigs = (int32_t)b->names.size();
+    return VFK_OK;
+}

@@ -20,7 +20,7 @@ NO_MATE = 0xFFFFFFFF
 
 COUNTS_DTYPE = np.dtype([("dp", "<i4"), ("n_amb", "<i4"), ("ac_ref", "<i4"), ("ac_alt", "<i4"),
                          ("med2", "<i4", (3, 2)), ("status", "<u4"), ("n_cand", "<u4"), ("s2", "<u8", (3,)),
-                         ("n_cover", "<u4"), ("reserved", "<u4")])
+                         ("n_cover", "<u4"), ("n_col", "<u4")])
 STATS_DTYPE = np.dtype([("z", "<f8", (3,)), ("p", "<f8", (3,)), ("pu", "<f8"), ("pw", "<f8"), ("k", "<i4"),
                         ("pad", "<i4")])
 HOT_DTYPE = np.dtype([("pos", "<i4"), ("span", "<u4"), ("fmk", "<u4"), ("pay", "<u4")])
@@ -106,6 +106,10 @@ def libvfk():
         lib.vfk_epilogue.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                                      C.c_void_p, C.c_void_p]
         lib.vfk_pileup.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.vfk_pileup_values.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]
+        lib.vfk_ranksum_values.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p]
         lib.vfk_annotate_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                           C.c_double, C.c_void_p, C.c_void_p]
         _libvfk = lib
@@ -318,6 +322,42 @@ class Device:
         _check(self.lib.vfk_epilogue(self.h, n_units, C.c_void_p(counts.data_ptr()), C.c_void_p(eaf.data_ptr()),
                                      float(fpr), float(error_rate), C.c_void_p(out.data_ptr()), self._stream()))
         return out
+
+    def pileup_values(self, reads: "DeviceReads", units: "DeviceUnits", params: ParamsC, max_per_unit: int = 128):
+        """Per unit, the packed per-read values of the REF / ALT lists (vfk_pileup_values).  Returns
+        (values[n_units, max], n_values[n_units]) on the host, growing the buffer until everything fits."""
+        t = self.torch
+        n = units.n_units
+        while True:
+            vals = t.empty(max(n, 1) * max_per_unit, dtype=t.int32, device=self.device)
+            cnt = t.empty(max(n, 1), dtype=t.int32, device=self.device)
+            _check(self.lib.vfk_pileup_values(self.h, C.byref(reads.c), C.byref(units.c), C.byref(params),
+                                              C.c_int32(max_per_unit), C.c_void_p(vals.data_ptr()),
+                                              C.c_void_p(cnt.data_ptr()), self._stream()))
+            counts = cnt.cpu().numpy()[:n]
+            if n == 0 or counts.max() <= max_per_unit:
+                return vals.cpu().numpy().view(np.uint32).reshape(max(n, 1), max_per_unit)[:n], counts
+            max_per_unit = int(counts.max())
+
+    def ranksum_values(self, alt_lists, ref_lists) -> np.ndarray:
+        """s2[p][mq,bq,pos] for pairs of packed-value lists (vfk_ranksum_values)."""
+        t = self.torch
+        n = len(alt_lists)
+        if n == 0:
+            return np.zeros((0, 3), np.uint64)
+        a_off = np.zeros(n + 1, np.int64)
+        r_off = np.zeros(n + 1, np.int64)
+        a_off[1:] = np.cumsum([len(x) for x in alt_lists])
+        r_off[1:] = np.cumsum([len(x) for x in ref_lists])
+        a = np.concatenate([np.asarray(x, np.uint32) for x in alt_lists] + [np.zeros(1, np.uint32)])
+        r = np.concatenate([np.asarray(x, np.uint32) for x in ref_lists] + [np.zeros(1, np.uint32)])
+        dev = lambda x: t.from_numpy(x.view(np.uint8)).to(self.device)
+        da, dr, dao, dro = dev(a), dev(r), dev(a_off), dev(r_off)
+        out = t.empty(n * 3 * 8, dtype=t.uint8, device=self.device)
+        _check(self.lib.vfk_ranksum_values(self.h, C.c_int64(n), C.c_void_p(da.data_ptr()), C.c_void_p(dao.data_ptr()),
+                                           C.c_void_p(dr.data_ptr()), C.c_void_p(dro.data_ptr()),
+                                           C.c_void_p(out.data_ptr()), self._stream()))
+        return out.cpu().numpy().view(np.uint64).reshape(n, 3)
 
     def annotate_host(self, packed: PackedReads, units: VariantUnits, stop, params: ParamsC, eaf: np.ndarray,
                       fpr: float, error_rate: float, counts_out=None, stats_out=None):

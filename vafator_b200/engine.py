@@ -1,0 +1,397 @@
+"""Host-side composition of the annotation around the two device stages.
+
+    reads (ReadBatch) --pack--> HBM layout --vfk_pileup--> integer counts per unit
+    counts + expected VAF --vfk_epilogue--> FP64 z / p / pu / pw / k per reported row
+
+What stays on the host is what the reference also does in Python after its arithmetic
+(vafator/annotator.py:260-432): merging replicate BAMs, choosing which values a Counter / dict
+lookup would have returned, and turning numbers into INFO strings with the same rounding
+functions.  No statistic is computed here.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import device as _dev
+from .batch import KIND_SNV, ReadBatch, VariantUnits, build_units, variant_kind
+from .constants import AMBIGUOUS_BASES
+
+Record = Tuple[str, int, str, Sequence[str]]  # CHROM, POS, REF, [ALT...]
+METRICS = ("mq", "bq", "pos")  # order of the device record
+
+
+def chrom_groups(records: Sequence[Record]):
+    """Consecutive records of one chromosome, as the reference streams them
+    (vafator/pileups.py:83-103).  Returns (in_range mask, stop per record): the reference piles up
+    [first.POS-1, last.POS) of each group (vafator/pileups.py:137-138), so records outside that span
+    get no metrics, and `stop` bounds the reads it ever fetches."""
+    n = len(records)
+    in_range = np.ones(n, bool)
+    stop = np.zeros(n, np.int32)
+    i = 0
+    while i < n:
+        j = i
+        while j + 1 < n and records[j + 1][0] == records[i][0]:
+            j += 1
+        first, last = records[i][1], records[j][1]
+        for k in range(i, j + 1):
+            in_range[k] = first <= records[k][1] <= last
+            stop[k] = last
+        i = j + 1
+    return in_range, stop
+
+
+class RowTable:
+    """One row per (record, ALT allele) -- the granularity of the A-numbered INFO fields."""
+
+    def __init__(self, records: Sequence[Record]):
+        self.records = records
+        n_alt = np.asarray([len(r[3]) for r in records], np.int64)
+        self.first = np.concatenate([[0], np.cumsum(n_alt)]).astype(np.int64)
+        self.n_rows = int(self.first[-1])
+        self.rec = np.repeat(np.arange(len(records), dtype=np.int64), n_alt)
+        self.alt = (np.arange(self.n_rows, dtype=np.int64) - self.first[self.rec]) if self.n_rows else np.zeros(0, np.int64)
+        self.kind = np.asarray([(-1 if not r[3] or variant_kind(r[2], r[3][0]) is None else variant_kind(r[2], r[3][0]))
+                                for r in records], np.int64)
+
+
+class BamResult:
+    """Per-BAM values on the row table, straight from the device counts."""
+
+    def __init__(self, rows: RowTable, units: VariantUnits, counts: np.ndarray, in_range: np.ndarray):
+        records = rows.records
+        nrec, nrow = len(records), rows.n_rows
+        self.row_unit = np.full(nrow, -1, np.int64)
+        for (i, j), u in units.unit_of.items():
+            self.row_unit[rows.first[i] + j] = u
+        u0 = self.row_unit[np.minimum(rows.first[:-1], max(nrow - 1, 0))] if nrec and nrow else np.full(nrec, -1, np.int64)  # unit of ALT[0]
+        u0 = np.where(rows.first[:-1] < rows.first[1:], u0, -1) if nrec else u0
+        has_u0 = u0 >= 0
+        safe0 = np.where(has_u0, u0, 0)
+        z = counts[safe0] if len(counts) else np.zeros(nrec, _dev.COUNTS_DTYPE)
+        # the reference has metrics for the record iff a pileup column exists at POS (>= 1 read after
+        # the read-level filters) and the record lies inside its chromosome group's span
+        self.has = has_u0 & in_range & (z["n_col"] > 0) if nrec else np.zeros(0, bool)
+        self.dp = np.where(self.has, z["dp"], 0).astype(np.int64)
+        self.n_amb = np.where(self.has, z["n_amb"], 0).astype(np.int64)
+        self.ac_ref = np.where(self.has, z["ac_ref"], 0).astype(np.int64)
+        self.med2_ref = np.where(self.has[:, None], z["med2"][:, :, 0], -1).astype(np.int64) if nrec else np.zeros((0, 3), np.int64)
+        ru = self.row_unit
+        has_row = (ru >= 0) & self.has[rows.rec] if nrow else np.zeros(0, bool)
+        zr = counts[np.where(ru >= 0, ru, 0)] if len(counts) else np.zeros(nrow, _dev.COUNTS_DTYPE)
+        self.ac = np.where(has_row, zr["ac_alt"], 0).astype(np.int64)
+        self.med2_alt = np.where(has_row[:, None], zr["med2"][:, :, 1], -1).astype(np.int64) if nrow else np.zeros((0, 3), np.int64)
+        self.row_counts = zr.copy()
+        self.row_counts["dp"] = self.dp[rows.rec] if nrow else 0
+        self.row_counts["ac_alt"] = self.ac
+        for f in ("ac_ref", "n_amb"):
+            self.row_counts[f] = np.where(has_row, zr[f], 0)
+        self.row_counts["s2"] = np.where(has_row[:, None], zr["s2"], 0)
+        # the `n` field: ambiguous-base count (SNV); for indels the reference sums ac over the IUPAC
+        # letters too, which only bites when an ALT allele is itself one of those letters
+        self.n = self.n_amb.copy()
+        for i, r in enumerate(records):
+            if rows.kind[i] > 0:
+                f = rows.first[i]
+                if self.has[i] and r[3][0].upper() in AMBIGUOUS_BASES:
+                    self.n[i] = int(self.ac[f])
+                # indel counts are keyed ALT[0].upper() but looked up with the literal ALT text
+                # (vafator/pileups.py:253-261 vs annotator.py:382-383): a lower-case ALT reads 0
+                if r[3][0] != r[3][0].upper():
+                    self.ac[f] = 0
+                    self.row_counts["ac_alt"][f] = 0
+
+
+def _fmt_float(x: float) -> str:
+    return str(float(x))
+
+
+def _np_round_str(x: float, nd: int) -> str:
+    """str(round(np.float64(x), nd)) -- numpy's rounding, as the reference applies to z, p, pu, pw."""
+    return str(np.round(np.float64(x), nd))
+
+
+class SampleFormatter:
+    """Builds the ordered INFO fields of one record (vafator/annotator.py:304-420)."""
+
+    def __init__(self, rows: RowTable):
+        self.rows = rows
+
+    def key_state(self, i: int, res: BamResult):
+        """Per allele of record i in one BAM: (has_key, n_values, med2 per metric).  `has_key` says
+        whether the reference's dictionaries would contain the allele at all (a Counter miss prints
+        0, an empty list prints nan)."""
+        rows = self.rows
+        chrom, pos, ref, alts = rows.records[i]
+        kind = rows.kind[i]
+        out = []
+        if not res.has[i]:
+            return [(False, 0, (-1, -1, -1))] * (1 + len(alts))
+        if kind == KIND_SNV:
+            n = int(res.ac_ref[i])
+            out.append((n > 0, n, tuple(int(x) for x in res.med2_ref[i])))
+            for j in range(len(alts)):
+                r = rows.first[i] + j
+                n = int(res.ac[r])
+                out.append((n > 0, n, tuple(int(x) for x in res.med2_alt[r])))
+        else:
+            n = int(res.ac_ref[i])
+            out.append((True, n, tuple(int(x) for x in res.med2_ref[i])))  # REF key always present
+            for j, a in enumerate(alts):
+                r = rows.first[i] + j
+                present = a == a.upper()  # lists are keyed ALT.upper(), looked up with the literal
+                n = int(res.ac[r]) if (present and j == 0) else 0
+                out.append((present, n, tuple(int(x) for x in res.med2_alt[r]) if (present and j == 0) else (-1, -1, -1)))
+        return out
+
+
+def format_fields(prefix: str, suffix: str, with_eaf: bool, alts, kind, ac, dp, n, eaf, pu, pw, k, med, rs) -> "OrderedDict":
+    """ac[j], pu[j]: per ALT; med[metric] = list of strings (REF, ALT...); rs[metric] = ([z...], [p...])."""
+    o = OrderedDict()
+    key = lambda name: "{}_{}{}".format(prefix, name, suffix)
+    o[key("af")] = ",".join(str(round(float(a) / dp, 5) if dp > 0 else 0.0) for a in ac)
+    o[key("ac")] = ",".join(str(int(a)) for a in ac)
+    o[key("n")] = str(int(n))
+    o[key("dp")] = int(dp)
+    if with_eaf:
+        o[key("eaf")] = str(float(eaf))
+    o[key("pu")] = ",".join(_np_round_str(x, 5) for x in pu)
+    o[key("pw")] = _np_round_str(pw, 5)
+    o[key("k")] = str(int(k))
+    for name in ("bq", "mq", "pos"):
+        o[key(name)] = ",".join(med[name])
+    for name, tag in (("mq", "rsmq"), ("bq", "rsbq"), ("pos", "rspos")):
+        zs, ps = rs[name]
+        if zs:
+            o[key(tag)] = ",".join(zs)
+            o["{}_{}_pv{}".format(prefix, tag, suffix)] = ",".join(ps)
+    return o
+
+
+class Engine:
+    """Drives the device for a set of VCF records against a set of BAM read batches."""
+
+    def __init__(self, device_index: int = 0, min_mapq: int = 0, min_baseq: int = 29, include_ambiguous: bool = True,
+                 fpr: float = 5e-7, error_rate: float = 1e-3):
+        self.dev = _dev.Device(device_index)
+        self.params = _dev.make_params(min_mapq=min_mapq, min_baseq=min_baseq, include_ambiguous=include_ambiguous)
+        self.fpr, self.error_rate = fpr, error_rate
+
+    def close(self):
+        self.dev.close()
+
+    # ---- device stages on host arrays -------------------------------------------------------
+    def _device_reads(self, batch: ReadBatch):
+        cache = self.__dict__.setdefault("_dreads", {})
+        if id(batch) not in cache:
+            cache[id(batch)] = (batch, self.dev.upload_reads(_dev.pack_reads(batch, self.params)))
+        return cache[id(batch)][1]
+
+    def release_reads(self):
+        self.__dict__.pop("_dreads", None)
+
+    def pileup(self, batch: ReadBatch, units: VariantUnits, stop: np.ndarray) -> np.ndarray:
+        if units.n_units == 0:
+            return np.zeros(0, _dev.COUNTS_DTYPE)
+        dreads = self._device_reads(batch)
+        dunits = self.dev.upload_units(units, stop)
+        buf = self.dev.pileup(dreads, dunits, self.params)
+        return self.dev.to_host(buf, _dev.COUNTS_DTYPE, units.n_units)
+
+    def epilogue(self, counts: np.ndarray, eaf: np.ndarray) -> np.ndarray:
+        n = len(counts)
+        if n == 0:
+            return np.zeros(0, _dev.STATS_DTYPE)
+        import torch
+        c = torch.from_numpy(np.ascontiguousarray(counts).view(np.uint8).reshape(-1)).to(self.dev.device)
+        e = torch.from_numpy(np.ascontiguousarray(eaf, np.float64)).to(self.dev.device)
+        buf = self.dev.epilogue(n, c, e, self.fpr, self.error_rate)
+        return self.dev.to_host(buf, _dev.STATS_DTYPE, n)
+
+    def values(self, batch: ReadBatch, units: VariantUnits, stop: np.ndarray):
+        """Packed per-read values of the units' REF / ALT lists: list of uint32 arrays."""
+        if units.n_units == 0:
+            return []
+        vals, cnt = self.dev.pileup_values(self._device_reads(batch), self.dev.upload_units(units, stop), self.params)
+        return [vals[u, :cnt[u]] for u in range(units.n_units)]
+
+    def ranksum_s2(self, alt_lists, ref_lists) -> np.ndarray:
+        return self.dev.ranksum_values(alt_lists, ref_lists)
+
+    def _cross_bam(self, records, in_range, stop_rec, batches, needs, eaf_sample):
+        """Rank sums whose ALT values come from one replicate BAM and REF values from another
+        (vafator/annotator.py:285-287 dict.update semantics).  needs: [(i, j, b_ref, b_alt)]."""
+        out = {}
+        if not needs:
+            return out
+        lists = {}
+        for b in sorted({n[2] for n in needs} | {n[3] for n in needs}):
+            idx = sorted({(i, j) for i, j, br, ba in needs if b in (br, ba)})
+            sub = [(records[i][0], records[i][1], records[i][2], [records[i][3][j]]) for i, j in idx]
+            units = build_units(sub, batches[b].contigs)
+            vals = self.values(batches[b], units, np.asarray([stop_rec[i] for i, j in idx], np.int32)[units.rec])
+            for k, (i, j) in enumerate(idx):
+                lists[(b, i, j)] = vals[units.unit_of[(k, 0)]]
+        alt_lists = [lists[(ba, i, j)][(lists[(ba, i, j)] >> 29) & 1 == 1] for i, j, br, ba in needs]
+        ref_lists = [lists[(br, i, j)][(lists[(br, i, j)] >> 28) & 1 == 1] for i, j, br, ba in needs]
+        s2 = self.ranksum_s2(alt_lists, ref_lists)
+        c = np.zeros(len(needs), _dev.COUNTS_DTYPE)
+        c["ac_alt"] = [len(x) for x in alt_lists]
+        c["ac_ref"] = [len(x) for x in ref_lists]
+        c["s2"] = s2
+        st = self.epilogue(c, np.asarray([eaf_sample[i] for i, j, br, ba in needs], np.float64))
+        for n, row in zip(needs, st):
+            out[(n[0], n[1])] = row
+        return out
+
+    # ---- the annotation -----------------------------------------------------------------------
+    def annotate(self, records: Sequence[Record], bams: "OrderedDict[str, List[ReadBatch]]",
+                 eaf: Dict[str, np.ndarray]) -> List["OrderedDict"]:
+        """INFO fields (ordered) for every record.  `eaf[sample][i]` = expected VAF of record i."""
+        rows = RowTable(records)
+        in_range, stop_rec = chrom_groups(records)
+        fmt = SampleFormatter(rows)
+        per_sample = OrderedDict()
+        for sample, batches in bams.items():
+            eaf_row = np.asarray(eaf[sample], np.float64)[rows.rec] if rows.n_rows else np.zeros(0)
+            results, stats = [], []
+            for batch in batches:
+                recs_in = [r if ok else (r[0], r[1], "", []) for r, ok in zip(records, in_range)]
+                units = build_units(recs_in, batch.contigs)
+                counts = self.pileup(batch, units, stop_rec[units.rec] if units.n_units else np.zeros(0, np.int32))
+                bad = counts["status"] & _dev.ST_READLEN if len(counts) else np.zeros(0, np.uint32)
+                if len(counts) and bad.any():
+                    raise _dev.VfkError("a read position exceeded the histogram range (reads longer than supported)")
+                res = BamResult(rows, units, counts, in_range)
+                results.append(res)
+                stats.append(self.epilogue(res.row_counts, eaf_row))
+            merged_stats = None
+            if len(batches) > 1:
+                mc = np.zeros(rows.n_rows, _dev.COUNTS_DTYPE)
+                mc["dp"] = sum(r.dp for r in results)[rows.rec] if rows.n_rows else 0
+                mc["ac_alt"] = sum(r.ac for r in results)
+                merged_stats = self.epilogue(mc, eaf_row)
+            cross = {}
+            if len(batches) > 1:
+                needs = []
+                for i in range(len(records)):
+                    if rows.kind[i] != KIND_SNV:
+                        continue  # indel lists exist in every BAM that has a column: the last one wins for both
+                    states = [fmt.key_state(i, res) for res in results]
+                    b_ref = max([b for b in range(len(results)) if states[b][0][0]], default=-1)
+                    for j in range(len(records[i][3])):
+                        b_alt = max([b for b in range(len(results)) if states[b][1 + j][0]], default=-1)
+                        if b_ref >= 0 and b_alt >= 0 and b_ref != b_alt:
+                            needs.append((i, j, b_ref, b_alt))
+                cross = self._cross_bam(records, in_range, stop_rec, batches, needs, np.asarray(eaf[sample], np.float64))
+            per_sample[sample] = (results, stats, merged_stats, cross)
+        out = []
+        for i, (chrom, pos, ref, alts) in enumerate(records):
+            info = OrderedDict()
+            r0, r1 = int(rows.first[i]), int(rows.first[i + 1])
+            kind = int(rows.kind[i])
+            for sample, (results, stats, merged_stats, cross) in per_sample.items():
+                e = float(eaf[sample][i])
+                states = [fmt.key_state(i, res) for res in results]
+                nb = len(results)
+                if nb > 1:
+                    for b, (res, st) in enumerate(zip(results, stats)):
+                        info.update(self._one(sample, "_%d" % (b + 1), False, alts, kind, res, st, states[b], i, r0, r1, e))
+                    info.update(self._merged(sample, alts, kind, results, stats, merged_stats, states, i, r0, r1, e, cross))
+                else:
+                    info.update(self._one(sample, "", True, alts, kind, results[0], stats[0], states[0], i, r0, r1, e))
+            out.append(info)
+        return out
+
+    @staticmethod
+    def _median_strings(kind, state_ref, state_alts):
+        med = {}
+        for mi, name in enumerate(METRICS):
+            vals = []
+            for has_key, n, m2 in [state_ref] + list(state_alts):
+                if name == "bq" and kind != KIND_SNV:
+                    vals.append("0")  # indel metrics carry no base qualities (pileups.py:301,304)
+                elif not has_key:
+                    vals.append("0")  # Counter miss
+                elif n == 0:
+                    vals.append("nan")  # key present, empty list
+                else:
+                    vals.append(_fmt_float(m2[mi] / 2.0))
+            med[name] = vals
+        return med
+
+    @staticmethod
+    def _ranksum_strings(kind, state_ref, state_alts, st_rows):
+        rs = {}
+        for mi, name in enumerate(METRICS):
+            zs, ps = [], []
+            if not (name == "bq" and kind != KIND_SNV):
+                for (has_key, n, _), st in zip(state_alts, st_rows):
+                    if has_key and n > 0 and state_ref[0] and state_ref[1] > 0:
+                        z, p = float(st["z"][mi]), float(st["p"][mi])
+                        if not (math.isnan(z) or math.isnan(p)):
+                            zs.append(_np_round_str(z, 3))
+                            ps.append(_np_round_str(p, 5))
+            rs[name] = (zs, ps)
+        return rs
+
+    def _one(self, sample, suffix, with_eaf, alts, kind, res, st, state, i, r0, r1, e):
+        ac = [int(res.ac[r]) for r in range(r0, r1)]
+        dp = int(res.dp[i])
+        pu = [float(st["pu"][r]) for r in range(r0, r1)]
+        pw, k = (float(st["pw"][r0]), int(st["k"][r0])) if r1 > r0 else (0.0, 1)
+        med = self._median_strings(kind, state[0], state[1:])
+        rs = self._ranksum_strings(kind, state[0], state[1:], [st[r] for r in range(r0, r1)])
+        return format_fields(sample, suffix, with_eaf, alts, kind, ac, dp, int(res.n[i]), e, pu, pw, k, med, rs)
+
+    def _merged(self, sample, alts, kind, results, stats, merged_stats, states, i, r0, r1, e, cross):
+        """Sample-level fields over replicate BAMs (vafator/annotator.py:277-302): counts and depth add,
+        MEDIANS ADD (Counter.update), distributions are replaced allele by allele by the last BAM that
+        has the allele (dict.update), so the rank sums describe that BAM only."""
+        nb = len(results)
+        ac = [int(sum(res.ac[r] for res in results)) for r in range(r0, r1)]
+        dp = int(sum(res.dp[i] for res in results))
+        n = int(sum(res.n[i] for res in results))
+        pu = [float(merged_stats["pu"][r]) for r in range(r0, r1)]
+        pw, k = (float(merged_stats["pw"][r0]), int(merged_stats["k"][r0])) if r1 > r0 else (0.0, 1)
+        med = {}
+        for mi, name in enumerate(METRICS):
+            vals = []
+            for a in range(1 + len(alts)):
+                total, seen = 0.0, False
+                for b in range(nb):
+                    has_key, cnt, m2 = states[b][a]
+                    if name == "bq" and kind != KIND_SNV:
+                        has_key = False
+                    if has_key:
+                        seen = True
+                        total = total + (m2[mi] / 2.0 if cnt > 0 else math.nan)
+                vals.append(_fmt_float(total) if seen else "0")
+            med[name] = vals
+        rs = {}
+        for mi, name in enumerate(METRICS):
+            zs, ps = [], []
+            if not (name == "bq" and kind != KIND_SNV):
+                def last_with(a):
+                    for b in range(nb - 1, -1, -1):
+                        if states[b][a][0]:
+                            return b
+                    return -1
+                b_ref = last_with(0)
+                for j in range(len(alts)):
+                    b_alt = last_with(1 + j)
+                    if b_ref < 0 or b_alt < 0:
+                        continue
+                    if states[b_ref][0][1] == 0 or states[b_alt][1 + j][1] == 0:
+                        continue
+                    st = cross[(i, j)] if b_ref != b_alt else stats[b_alt][r0 + j]
+                    z, p = float(st["z"][mi]), float(st["p"][mi])
+                    if not (math.isnan(z) or math.isnan(p)):
+                        zs.append(_np_round_str(z, 3))
+                        ps.append(_np_round_str(p, 5))
+            rs[name] = (zs, ps)
+        return format_fields(sample, "", True, alts, kind, ac, dp, n, e, pu, pw, k, med, rs)

@@ -1,0 +1,112 @@
+"""Minimal text VCF reader / writer (plain, gzip or BGZF) -- stands where cyvcf2's VCF / Writer
+stand in the reference (vafator/annotator.py:121-158, :434-441).  Records keep their original
+columns; annotations are appended to (or replace keys of) the INFO column, exactly what
+htslib's bcf_update_info does for string / integer values."""
+from __future__ import annotations
+
+import gzip
+import io
+from typing import Dict, Iterator, List, Optional
+
+
+class VcfRecord:
+    __slots__ = ("fields", "CHROM", "POS", "REF", "ALT", "INFO")
+
+    def __init__(self, fields: List[str]):
+        if len(fields) < 8:
+            raise ValueError("malformed VCF record: fewer than 8 columns")
+        self.fields = fields
+        self.CHROM = fields[0]
+        self.POS = int(fields[1])
+        self.REF = fields[3]
+        self.ALT = [] if fields[4] == "." else fields[4].split(",")
+        self.INFO: Dict[str, object] = {}  # annotations to add, in insertion order
+
+    def line(self) -> str:
+        f = list(self.fields)
+        if self.INFO:
+            old = [] if f[7] in (".", "") else f[7].split(";")
+            keys = {kv.split("=", 1)[0]: i for i, kv in enumerate(old)}
+            for k, v in self.INFO.items():
+                kv = "%s=%s" % (k, v)
+                if k in keys:
+                    old[keys[k]] = kv
+                else:
+                    old.append(kv)
+            f[7] = ";".join(old)
+        return "\t".join(f)
+
+
+class VcfReader:
+    def __init__(self, path: str):
+        self.path = path
+        with open(path, "rb") as fh:
+            magic = fh.read(2)
+        self._fh = gzip.open(path, "rt") if magic == b"\x1f\x8b" else open(path, "rt")
+        self.header_lines: List[str] = []
+        self.column_line: Optional[str] = None
+        for line in self._fh:
+            line = line.rstrip("\n").rstrip("\r")
+            if line.startswith("##"):
+                self.header_lines.append(line)
+            elif line.startswith("#"):
+                self.column_line = line
+                break
+            else:
+                raise ValueError("%s: VCF record before the #CHROM header line" % path)
+        if self.column_line is None:
+            raise ValueError("%s: no #CHROM header line" % path)
+        self.extra_header: List[str] = []
+
+    def add_to_header(self, line: str) -> None:
+        self.extra_header.append(line)
+
+    def add_info_to_header(self, d: dict) -> None:
+        self.extra_header.append('##INFO=<ID={ID},Number={Number},Type={Type},Description="{Description}">'.format(**d))
+
+    def __iter__(self) -> Iterator[VcfRecord]:
+        for line in self._fh:
+            line = line.rstrip("\n").rstrip("\r")
+            if line:
+                yield VcfRecord(line.split("\t"))
+
+    def close(self) -> None:
+        self._fh.close()
+
+
+class VcfWriter:
+    def __init__(self, path: str, template: VcfReader):
+        self.path = path
+        if path.endswith(".gz"):
+            self._raw = open(path, "wb")
+            self._buf = io.StringIO()
+            self._bgzf = True
+        else:
+            self._raw = open(path, "w")
+            self._bgzf = False
+        self._emit("\n".join(template.header_lines + template.extra_header + [template.column_line]) + "\n")
+
+    def _emit(self, text: str) -> None:
+        if not self._bgzf:
+            self._raw.write(text)
+            return
+        from .bamio import _bgzf_block
+        self._buf.write(text)
+        data = self._buf.getvalue().encode()
+        while len(data) >= 0xFF00:
+            self._raw.write(_bgzf_block(data[:0xFF00]))
+            data = data[0xFF00:]
+        self._buf = io.StringIO()
+        self._buf.write(data.decode())
+
+    def write_record(self, rec: VcfRecord) -> None:
+        self._emit(rec.line() + "\n")
+
+    def close(self) -> None:
+        if self._bgzf:
+            from .bamio import _bgzf_block, _BGZF_EOF
+            data = self._buf.getvalue().encode()
+            if data:
+                self._raw.write(_bgzf_block(data))
+            self._raw.write(_BGZF_EOF)
+        self._raw.close()
