@@ -18,16 +18,49 @@ __device__ __forceinline__ double log_binom_pmf(int64_t k, int64_t n, double log
            (double)(n - k) * log1mp;
 }
 
+__device__ bool dyadic_binom(int64_t k, int64_t n, double p, bool want_cdf, double &out);
+
 __device__ double binom_pmf(int64_t k, int64_t n, double p) {
+    double exact;
+    if (dyadic_binom(k, n, p, false, exact)) return exact;
     if (k < 0 || k > n) return 0.0;
     if (p <= 0.0) return k == 0 ? 1.0 : 0.0;
     if (p >= 1.0) return k == n ? 1.0 : 0.0;
     return exp(log_binom_pmf(k, n, log(p), log1p(-p)));
 }
 
+// Exact evaluation when p = a / 2^b and the numerators fit in 64 bits (b * n <= 62): the result is
+// then the correctly rounded dyadic rational.  This matters for presentation, not for accuracy:
+// with the default expected VAF of 0.5 values such as 1/64 sit exactly on a rounding tie of the
+// 5-decimal INFO fields, and the reference (scipy/Boost) returns them exactly.
+__device__ bool dyadic_binom(int64_t k, int64_t n, double p, bool want_cdf, double &out) {
+    if (!(p > 0.0 && p < 1.0) || n < 0 || n > 62) return false;
+    int b = 0;
+    double a = p;
+    while (b <= 10 && a != floor(a)) { a *= 2.0; ++b; }
+    if (b > 10 || b == 0 || (int64_t)b * n > 62) return false;
+    const uint64_t A = (uint64_t)a, B = (1ull << b) - A;
+    if (k < 0) { out = 0.0; return true; }
+    if (k > n) { out = want_cdf ? 1.0 : 0.0; return true; }
+    uint64_t sum = 0, c = 1;  // c = C(n, i)
+    for (int64_t i = 0; i <= k; ++i) {
+        if (want_cdf || i == k) {
+            uint64_t t = c;
+            for (int64_t j = 0; j < i; ++j) t *= A;
+            for (int64_t j = 0; j < n - i; ++j) t *= B;
+            sum += t;
+        }
+        c = c * (uint64_t)(n - i) / (uint64_t)(i + 1);
+    }
+    out = ldexp((double)sum, -(int)(b * n));
+    return true;
+}
+
 // lower tail P[X <= k] by direct summation of the probability mass, starting from the largest
 // term of the tail that is summed so that every further term is smaller (no cancellation).
 __device__ double binom_cdf(int64_t k, int64_t n, double p) {
+    double exact;
+    if (dyadic_binom(k, n, p, true, exact)) return exact;
     if (k < 0) return 0.0;
     if (k >= n) return 1.0;
     if (p <= 0.0) return 1.0;
