@@ -158,6 +158,19 @@ int vfk_annotate_host(vfk_handle *h, const vfk_read_batch *reads, const vfk_vari
                       const vfk_params *params, const double *eaf, double fpr, double error_rate,
                       vfk_counts *counts_out, vfk_stats *stats_out);
 
+/* Double-buffered variant: returns once the batch is enqueued on one of the handle's two staging
+ * slots; *ticket (0 or 1) names the slot.  Submitting a third batch waits for the slot it reuses.
+ * The host buffers (inputs and outputs) must stay valid until vfk_wait(h, ticket) returns.  When the
+ * payload / cold / cigar buffers are page-locked and the variant set is sparse, the kernel gathers
+ * the sectors it needs directly from host memory instead of copying those arrays
+ * (VFK_ZERO_COPY_PAYLOAD=0/1 in the environment forces the choice).                               */
+int vfk_annotate_host_async(vfk_handle *h, const vfk_read_batch *reads, const vfk_variant_batch *units,
+                            const vfk_params *params, const double *eaf, double fpr, double error_rate,
+                            vfk_counts *counts_out, vfk_stats *stats_out, int *ticket);
+int vfk_wait(vfk_handle *h, int ticket);
+/* how many batches of this handle took the zero-copy route */
+int64_t vfk_zero_copy_batches(vfk_handle *h);
+
 /* ---- list-shaped auxiliaries (DEVICE pointers) ------------------------------------------------
  * vfk_pileup_values: per unit, the per-read values the reference keeps in all_mqs / all_bqs /
  * all_positions (vafator/pileups.py:214-216), one packed word each:

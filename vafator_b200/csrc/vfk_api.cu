@@ -11,6 +11,11 @@ namespace vfk {
 cudaError_t launch_pileup(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, int max_l_qseq, vfk_counts *out,
                           void *resolved_scratch, unsigned long long *work_counter, uint32_t *deferred, uint32_t *n_deferred, int sm_count,
                           cudaStream_t stream, int *launches);
+cudaError_t launch_locate(const ReadsDev &R, const UnitsDev &V, void *resolved, unsigned long long *cand_sum, cudaStream_t stream,
+                          int *launches);
+cudaError_t launch_pileup_resolved(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, int max_l_qseq, vfk_counts *out,
+                                   void *resolved, unsigned long long *work_counter, uint32_t *deferred, uint32_t *n_deferred,
+                                   int sm_count, cudaStream_t stream, int *launches);
 cudaError_t launch_epilogue(int64_t n_units, const vfk_counts *counts, const double *eaf, double fpr, double error_rate,
                             vfk_stats *out, cudaStream_t stream, int *launches);
 cudaError_t launch_values(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, int32_t max_per_unit, uint32_t *values,
@@ -52,18 +57,38 @@ struct DevBuf {
     }
 };
 
+// One of the two staging slots of the host entry point: its own stream, device staging buffers and
+// scratch, so that the copies of one batch overlap the kernels of the previous one (double buffering).
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    bool busy = false;
+    void *counters = nullptr;             // 32 B: work counter, deferred count, candidate sum
+    unsigned long long *h_cand = nullptr;  // pinned host word for the candidate sum
+    DevBuf deferred, resolved;
+    DevBuf contig, hot, cold, mate, sb, cigar, payload;
+    DevBuf tid, pos, meta, len, soff, ins, stop, eaf, counts, stats;
+    void release() {
+        DevBuf *bufs[] = {&deferred, &resolved, &contig, &hot, &cold, &mate, &sb, &cigar, &payload, &tid, &pos, &meta, &len,
+                          &soff, &ins, &stop, &eaf, &counts, &stats};
+        for (DevBuf *b : bufs) b->release();
+        if (counters) cudaFree(counters);
+        if (h_cand) cudaFreeHost(h_cand);
+        if (done) cudaEventDestroy(done);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
 struct vfk_handle {
     int device = 0;
     int sm_count = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t done = nullptr;
-    unsigned long long *work_counter = nullptr;  // 8 B + n_deferred 4 B
+    unsigned long long *work_counter = nullptr;  // scratch of the device-pointer API: 8 B + n_deferred 4 B
     uint32_t *n_deferred = nullptr;
     DevBuf deferred, resolved;  // per-launch scratch: deep-unit list, located units (32 B each)
     int64_t launches = 0;
-    // staging for vfk_annotate_host
-    DevBuf s_contig, s_hot, s_cold, s_mate, s_sb, s_cigar, s_payload;
-    DevBuf s_tid, s_pos, s_meta, s_len, s_soff, s_ins, s_stop, s_eaf, s_counts, s_stats;
+    Slot slot[2];
+    int next_slot = 0;
+    int64_t zero_copy_batches = 0;
 };
 
 extern "C" int vfk_version(void) { return VFK_VERSION; }
@@ -90,8 +115,12 @@ extern "C" int vfk_create(int device, vfk_handle **out) {
         if (gran == 32 || gran == 64 || gran == 128) (void)cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
         (void)cudaGetLastError();
     }
-    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CU(cudaEventCreateWithFlags(&h->done, cudaEventDisableTiming));
+    for (Slot &s : h->slot) {
+        CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        CU(cudaMalloc(&s.counters, 32));
+        CU(cudaMallocHost((void **)&s.h_cand, sizeof(unsigned long long)));
+    }
     void *p = nullptr;
     CU(cudaMalloc(&p, 16));
     h->work_counter = (unsigned long long *)p;
@@ -103,14 +132,11 @@ extern "C" int vfk_create(int device, vfk_handle **out) {
 extern "C" int vfk_destroy(vfk_handle *h) {
     if (!h) return VFK_OK;
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
-    DevBuf *bufs[] = {&h->deferred, &h->resolved, &h->s_contig, &h->s_hot, &h->s_cold, &h->s_mate, &h->s_sb, &h->s_cigar,
-                      &h->s_payload, &h->s_tid, &h->s_pos, &h->s_meta, &h->s_len, &h->s_soff, &h->s_ins, &h->s_stop,
-                      &h->s_eaf, &h->s_counts, &h->s_stats};
-    for (DevBuf *b : bufs) b->release();
+    cudaDeviceSynchronize();
+    for (Slot &s : h->slot) s.release();
+    h->deferred.release();
+    h->resolved.release();
     if (h->work_counter) cudaFree(h->work_counter);
-    if (h->done) cudaEventDestroy(h->done);
-    if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return VFK_OK;
 }
@@ -239,74 +265,137 @@ extern "C" int vfk_ranksum_values(vfk_handle *h, int64_t n_pairs, const uint32_t
         if (b_) CU(cudaMemcpyAsync((buf).p, (src), b_, cudaMemcpyHostToDevice, st));             \
     } while (0)
 
-extern "C" int vfk_annotate_host(vfk_handle *h, const vfk_read_batch *reads, const vfk_variant_batch *units,
-                                 const vfk_params *params, const double *eaf, double fpr, double error_rate,
-                                 vfk_counts *counts_out, vfk_stats *stats_out) {
+// device-visible alias of a page-locked host buffer, or NULL
+static const void *pinned_alias(const void *host) {
+    cudaPointerAttributes attr;
+    const void *dev = nullptr;
+    if (host && cudaPointerGetAttributes(&attr, host) == cudaSuccess && attr.type == cudaMemoryTypeHost) dev = attr.devicePointer;
+    (void)cudaGetLastError();
+    return dev;
+}
+
+extern "C" int vfk_wait(vfk_handle *h, int ticket) {
+    if (!h || ticket < 0 || ticket > 1) return fail(VFK_EINVAL, "vfk_wait: bad handle or ticket");
+    Slot &s = h->slot[ticket];
+    if (!s.busy) return VFK_OK;
+    CU(cudaSetDevice(h->device));
+    CU(cudaEventSynchronize(s.done));
+    s.busy = false;
+    return VFK_OK;
+}
+
+extern "C" int vfk_annotate_host_async(vfk_handle *h, const vfk_read_batch *reads, const vfk_variant_batch *units,
+                                       const vfk_params *params, const double *eaf, double fpr, double error_rate,
+                                       vfk_counts *counts_out, vfk_stats *stats_out, int *ticket) {
     if (!h) return fail(VFK_EINVAL, "vfk_annotate_host: NULL handle");
     int rc = check_batches(reads, units, params);
     if (rc) return rc;
     const int64_t nu = units->n_units, nr = reads->n_reads;
+    const int si = h->next_slot;
+    if (ticket) *ticket = si;
     if (nu == 0) return VFK_OK;
     if (!eaf || !counts_out || !stats_out) return fail(VFK_EINVAL, "vfk_annotate_host: NULL array");
-    CU(cudaSetDevice(h->device));
-    cudaStream_t st = h->stream;
-    STAGE(h->s_contig, reads->contig_off, (size_t)(reads->n_contigs + 1) * sizeof(int64_t));
-    STAGE(h->s_hot, reads->hot, (size_t)nr * sizeof(vfk_read_hot));
-    STAGE(h->s_cold, reads->cold, (size_t)nr * sizeof(vfk_read_cold));
-    STAGE(h->s_mate, reads->mate, (size_t)nr * 4);
-    STAGE(h->s_sb, reads->sb, (size_t)nr * 8);
-    STAGE(h->s_cigar, reads->cigar, (size_t)reads->n_cigar_words * 4);
-    // The payload is ~85 % of the batch but a sparse variant set touches a few percent of its
-    // sectors.  With VFK_ZERO_COPY_PAYLOAD=1 and a pinned (page-locked) payload buffer the kernel
-    // gathers those sectors straight from host memory over PCIe instead of staging everything.
-    const uint8_t *payload_dev = nullptr;
-    {
-        const char *zc = getenv("VFK_ZERO_COPY_PAYLOAD");
-        cudaPointerAttributes attr;
-        if (zc && zc[0] == '1' && cudaPointerGetAttributes(&attr, reads->payload) == cudaSuccess &&
-            attr.type == cudaMemoryTypeHost && attr.devicePointer)
-            payload_dev = (const uint8_t *)attr.devicePointer;
-        (void)cudaGetLastError();
-    }
-    if (!payload_dev) {
-        STAGE(h->s_payload, reads->payload, (size_t)reads->n_sectors * 32);
-        payload_dev = (const uint8_t *)h->s_payload.p;
-    }
-    STAGE(h->s_tid, units->tid, (size_t)nu * 4);
-    STAGE(h->s_pos, units->pos, (size_t)nu * 4);
-    STAGE(h->s_meta, units->meta, (size_t)nu * 4);
-    STAGE(h->s_len, units->length, (size_t)nu * 4);
-    STAGE(h->s_soff, units->seq_off, (size_t)nu * 4);
-    STAGE(h->s_ins, units->ins_seq, (size_t)(units->n_ins_seq > 0 ? units->n_ins_seq : 1));
-    if (units->stop) STAGE(h->s_stop, units->stop, (size_t)nu * 4);
-    STAGE(h->s_eaf, eaf, (size_t)nu * sizeof(double));
-    rc = h->s_counts.reserve((size_t)nu * sizeof(vfk_counts));
+    rc = vfk_wait(h, si);  // the slot's previous batch must have left it
     if (rc) return rc;
-    rc = h->s_stats.reserve((size_t)nu * sizeof(vfk_stats));
+    h->next_slot ^= 1;
+    CU(cudaSetDevice(h->device));
+    Slot &S = h->slot[si];
+    cudaStream_t st = S.stream;
+    unsigned long long *work_counter = (unsigned long long *)S.counters;
+    uint32_t *n_deferred = (uint32_t *)((char *)S.counters + 8);
+    unsigned long long *cand_sum = (unsigned long long *)((char *)S.counters + 16);
+    // ---- stage 1: what the locate pass needs
+    STAGE(S.contig, reads->contig_off, (size_t)(reads->n_contigs + 1) * sizeof(int64_t));
+    STAGE(S.sb, reads->sb, (size_t)nr * 8);
+    STAGE(S.tid, units->tid, (size_t)nu * 4);
+    STAGE(S.pos, units->pos, (size_t)nu * 4);
+    STAGE(S.meta, units->meta, (size_t)nu * 4);
+    STAGE(S.len, units->length, (size_t)nu * 4);
+    STAGE(S.soff, units->seq_off, (size_t)nu * 4);
+    STAGE(S.ins, units->ins_seq, (size_t)(units->n_ins_seq > 0 ? units->n_ins_seq : 1));
+    if (units->stop) STAGE(S.stop, units->stop, (size_t)nu * 4);
+    rc = S.deferred.reserve((size_t)nu * sizeof(uint32_t));
+    if (rc) return rc;
+    rc = S.resolved.reserve((size_t)nu * 32);
     if (rc) return rc;
     vfk_read_batch dr = *reads;
-    dr.contig_off = (const int64_t *)h->s_contig.p;
-    dr.hot = (const vfk_read_hot *)h->s_hot.p;
-    dr.cold = (const vfk_read_cold *)h->s_cold.p;
-    dr.mate = (const uint32_t *)h->s_mate.p;
-    dr.sb = (const int32_t *)h->s_sb.p;
-    dr.cigar = (const uint32_t *)h->s_cigar.p;
-    dr.payload = payload_dev;
+    dr.contig_off = (const int64_t *)S.contig.p;
+    dr.sb = (const int32_t *)S.sb.p;
     vfk_variant_batch dv = *units;
-    dv.tid = (const int32_t *)h->s_tid.p;
-    dv.pos = (const int32_t *)h->s_pos.p;
-    dv.meta = (const uint32_t *)h->s_meta.p;
-    dv.length = (const int32_t *)h->s_len.p;
-    dv.seq_off = (const uint32_t *)h->s_soff.p;
-    dv.ins_seq = (const uint8_t *)h->s_ins.p;
-    dv.stop = units->stop ? (const int32_t *)h->s_stop.p : nullptr;
-    rc = vfk_pileup(h, &dr, &dv, params, (vfk_counts *)h->s_counts.p, st);
+    dv.tid = (const int32_t *)S.tid.p;
+    dv.pos = (const int32_t *)S.pos.p;
+    dv.meta = (const uint32_t *)S.meta.p;
+    dv.length = (const int32_t *)S.len.p;
+    dv.seq_off = (const uint32_t *)S.soff.p;
+    dv.ins_seq = (const uint8_t *)S.ins.p;
+    dv.stop = units->stop ? (const int32_t *)S.stop.p : nullptr;
+    vfk::ReadsDev R;
+    vfk::UnitsDev V;
+    to_dev(&dr, &dv, R, V);
+    int launches = 0;
+    CU(cudaMemsetAsync(S.counters, 0, 32, st));
+    cudaError_t e = vfk::launch_locate(R, V, S.resolved.p, cand_sum, st, &launches);
+    if (e != cudaSuccess) return fail(VFK_ECUDA, "locate launch: %s", cudaGetErrorString(e));
+    // ---- transfer strategy for the bulk of the batch (payload ~84 %, cold records + CIGARs ~6 %):
+    // a sparse variant set touches a few percent of those bytes, so when the caller's buffers are
+    // page-locked the kernel gathers the sectors it needs straight from host memory over PCIe
+    // ("zero copy") instead of staging everything.  Decided from the located candidate count.
+    const void *z_payload = pinned_alias(reads->payload), *z_cold = pinned_alias(reads->cold),
+               *z_cigar = reads->n_cigar_words ? pinned_alias(reads->cigar) : reads->cigar;
+    bool zero_copy = z_payload && z_cold && (z_cigar || reads->n_cigar_words == 0);
+    if (const char *env = getenv("VFK_ZERO_COPY_PAYLOAD")) zero_copy = zero_copy && env[0] == '1';
+    if (zero_copy && !getenv("VFK_ZERO_COPY_PAYLOAD")) {
+        CU(cudaMemcpyAsync(S.h_cand, cand_sum, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        // ~64 bytes cross the bus per candidate read when gathering; staging moves everything once
+        const double gathered = (double)*S.h_cand * 64.0;
+        const double staged = (double)reads->n_sectors * 32.0 + (double)nr * 16.0 + (double)reads->n_cigar_words * 4.0;
+        zero_copy = gathered * 4.0 < staged;
+    }
+    // ---- stage 2
+    STAGE(S.hot, reads->hot, (size_t)nr * sizeof(vfk_read_hot));
+    STAGE(S.mate, reads->mate, (size_t)nr * 4);
+    STAGE(S.eaf, eaf, (size_t)nu * sizeof(double));
+    if (zero_copy) {
+        R.cold = (const uint4 *)z_cold;
+        R.cigar = (const uint32_t *)z_cigar;
+        R.payload = (const uint8_t *)z_payload;
+        ++h->zero_copy_batches;
+    } else {
+        STAGE(S.cold, reads->cold, (size_t)nr * sizeof(vfk_read_cold));
+        STAGE(S.cigar, reads->cigar, (size_t)reads->n_cigar_words * 4);
+        STAGE(S.payload, reads->payload, (size_t)reads->n_sectors * 32);
+        R.cold = (const uint4 *)S.cold.p;
+        R.cigar = (const uint32_t *)S.cigar.p;
+        R.payload = (const uint8_t *)S.payload.p;
+    }
+    R.hot = (const uint4 *)S.hot.p;
+    R.mate = (const uint32_t *)S.mate.p;
+    rc = S.counts.reserve((size_t)nu * sizeof(vfk_counts));
     if (rc) return rc;
-    rc = vfk_epilogue(h, nu, (const vfk_counts *)h->s_counts.p, (const double *)h->s_eaf.p, fpr, error_rate,
-                      (vfk_stats *)h->s_stats.p, st);
+    rc = S.stats.reserve((size_t)nu * sizeof(vfk_stats));
     if (rc) return rc;
-    CU(cudaMemcpyAsync(counts_out, h->s_counts.p, (size_t)nu * sizeof(vfk_counts), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(stats_out, h->s_stats.p, (size_t)nu * sizeof(vfk_stats), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    e = vfk::launch_pileup_resolved(R, V, *params, reads->max_l_qseq, (vfk_counts *)S.counts.p, S.resolved.p, work_counter,
+                                    (uint32_t *)S.deferred.p, n_deferred, h->sm_count, st, &launches);
+    if (e != cudaSuccess) return fail(VFK_ECUDA, "pileup launch: %s", cudaGetErrorString(e));
+    e = vfk::launch_epilogue(nu, (const vfk_counts *)S.counts.p, (const double *)S.eaf.p, fpr, error_rate, (vfk_stats *)S.stats.p,
+                             st, &launches);
+    if (e != cudaSuccess) return fail(VFK_ECUDA, "epilogue launch: %s", cudaGetErrorString(e));
+    h->launches += launches;
+    CU(cudaMemcpyAsync(counts_out, S.counts.p, (size_t)nu * sizeof(vfk_counts), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(stats_out, S.stats.p, (size_t)nu * sizeof(vfk_stats), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(S.done, st));
+    S.busy = true;
     return VFK_OK;
 }
+
+extern "C" int vfk_annotate_host(vfk_handle *h, const vfk_read_batch *reads, const vfk_variant_batch *units,
+                                 const vfk_params *params, const double *eaf, double fpr, double error_rate,
+                                 vfk_counts *counts_out, vfk_stats *stats_out) {
+    int ticket = 0;
+    int rc = vfk_annotate_host_async(h, reads, units, params, eaf, fpr, error_rate, counts_out, stats_out, &ticket);
+    if (rc) return rc;
+    return vfk_wait(h, ticket);
+}
+
+extern "C" int64_t vfk_zero_copy_batches(vfk_handle *h) { return h ? h->zero_copy_batches : 0; }

@@ -42,7 +42,7 @@ struct Layout {
 //        no earlier read can overlap the column
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-locate_kernel(ReadsDev R, UnitsDev V, ResolvedUnit *__restrict__ res) {
+locate_kernel(ReadsDev R, UnitsDev V, ResolvedUnit *__restrict__ res, unsigned long long *__restrict__ cand_sum) {
     const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= V.n) return;
     const int32_t tid = __ldg(V.tid + u);
@@ -66,6 +66,12 @@ locate_kernel(ReadsDev R, UnitsDev V, ResolvedUnit *__restrict__ res) {
     const uint4 *q = reinterpret_cast<const uint4 *>(&r);
     o[0] = q[0];
     o[1] = q[1];
+    if (cand_sum) {  // total candidate reads of the batch: lets the host entry pick its transfer strategy
+        const unsigned active = __activemask();
+        const unsigned mine = r.hi - r.lo;
+        const unsigned tot = __reduce_add_sync(active, mine);
+        if ((threadIdx.x & 31) == (__ffs(active) - 1)) atomicAdd(cand_sum, (unsigned long long)tot);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -482,6 +488,14 @@ pileup_block_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, const uint
 // ------------------------------------------------------------------------------------------
 // host-side launchers (called from vfk_api.cu)
 // ------------------------------------------------------------------------------------------
+cudaError_t launch_locate(const ReadsDev &R, const UnitsDev &V, void *resolved, unsigned long long *cand_sum, cudaStream_t stream,
+                          int *launches) {
+    if (V.n <= 0) return cudaSuccess;
+    locate_kernel<<<(unsigned)((V.n + 255) / 256), 256, 0, stream>>>(R, V, (ResolvedUnit *)resolved, cand_sum);
+    ++*launches;
+    return cudaGetLastError();
+}
+
 template <int POSB>
 static cudaError_t launch_posb(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, vfk_counts *out, ResolvedUnit *res,
                                unsigned long long *work_counter, uint32_t *deferred, uint32_t *n_deferred, int sm_count,
@@ -504,10 +518,6 @@ static cudaError_t launch_posb(const ReadsDev &R, const UnitsDev &V, const vfk_p
     if (want < grid) grid = want < 1 ? 1 : want;
     e = cudaMemsetAsync(work_counter, 0, 16, stream);  // work counter and deferred-unit count share one allocation
     if (e != cudaSuccess) return e;
-    locate_kernel<<<(unsigned)((V.n + 255) / 256), 256, 0, stream>>>(R, V, res);
-    ++*launches;
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
     pileup_warp_kernel<POSB><<<(unsigned)grid, WARPS_PER_CTA * 32, smem_warp, stream>>>(R, res, V.n, V.ins_seq, P, out, work_counter,
                                                                                         deferred, n_deferred);
     ++*launches;
@@ -522,14 +532,25 @@ static cudaError_t launch_posb(const ReadsDev &R, const UnitsDev &V, const vfk_p
     return e;
 }
 
-cudaError_t launch_pileup(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, int max_l_qseq, vfk_counts *out,
-                          void *resolved_scratch, unsigned long long *work_counter, uint32_t *deferred, uint32_t *n_deferred, int sm_count,
-                          cudaStream_t stream, int *launches) {
+// the pileup kernels on units that launch_locate has resolved
+cudaError_t launch_pileup_resolved(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, int max_l_qseq, vfk_counts *out,
+                                   void *resolved, unsigned long long *work_counter, uint32_t *deferred, uint32_t *n_deferred,
+                                   int sm_count, cudaStream_t stream, int *launches) {
+    ResolvedUnit *res = (ResolvedUnit *)resolved;
     // read positions run 0 .. l_qseq (a read hanging in a trailing deletion reports l_qseq)
-    if (max_l_qseq < 256) return launch_posb<256>(R, V, P, out, (ResolvedUnit *)resolved_scratch, work_counter, deferred, n_deferred, sm_count, stream, launches);
-    if (max_l_qseq < 512) return launch_posb<512>(R, V, P, out, (ResolvedUnit *)resolved_scratch, work_counter, deferred, n_deferred, sm_count, stream, launches);
-    if (max_l_qseq < 1024) return launch_posb<1024>(R, V, P, out, (ResolvedUnit *)resolved_scratch, work_counter, deferred, n_deferred, sm_count, stream, launches);
-    return launch_posb<4096>(R, V, P, out, (ResolvedUnit *)resolved_scratch, work_counter, deferred, n_deferred, sm_count, stream, launches);
+    if (max_l_qseq < 256) return launch_posb<256>(R, V, P, out, res, work_counter, deferred, n_deferred, sm_count, stream, launches);
+    if (max_l_qseq < 512) return launch_posb<512>(R, V, P, out, res, work_counter, deferred, n_deferred, sm_count, stream, launches);
+    if (max_l_qseq < 1024) return launch_posb<1024>(R, V, P, out, res, work_counter, deferred, n_deferred, sm_count, stream, launches);
+    return launch_posb<4096>(R, V, P, out, res, work_counter, deferred, n_deferred, sm_count, stream, launches);
+}
+
+cudaError_t launch_pileup(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, int max_l_qseq, vfk_counts *out,
+                          void *resolved_scratch, unsigned long long *work_counter, uint32_t *deferred, uint32_t *n_deferred,
+                          int sm_count, cudaStream_t stream, int *launches) {
+    cudaError_t e = launch_locate(R, V, resolved_scratch, nullptr, stream, launches);
+    if (e != cudaSuccess) return e;
+    return launch_pileup_resolved(R, V, P, max_l_qseq, out, resolved_scratch, work_counter, deferred, n_deferred, sm_count, stream,
+                                  launches);
 }
 
 }  // namespace vfk

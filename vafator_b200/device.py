@@ -110,6 +110,11 @@ def libvfk():
                                           C.c_void_p]
         lib.vfk_ranksum_values.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p]
+        lib.vfk_annotate_host_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+                                                C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.vfk_wait.argtypes = [C.c_void_p, C.c_int]
+        lib.vfk_zero_copy_batches.restype = C.c_int64
+        lib.vfk_zero_copy_batches.argtypes = [C.c_void_p]
         lib.vfk_annotate_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                           C.c_double, C.c_void_p, C.c_void_p]
         _libvfk = lib
@@ -373,6 +378,29 @@ class Device:
                                           C.c_void_p(eaf.ctypes.data), float(fpr), float(error_rate),
                                           C.c_void_p(counts.ctypes.data), C.c_void_p(stats.ctypes.data)))
         return counts, stats
+
+    def annotate_host_async(self, packed: PackedReads, units: VariantUnits, stop, params: ParamsC, eaf: np.ndarray,
+                            fpr: float, error_rate: float, counts_out: np.ndarray, stats_out: np.ndarray):
+        """Enqueue one batch on one of the two staging slots; returns a ticket for `wait`.  All host
+        arrays (inputs and outputs) must stay alive and untouched until `wait(ticket)` returns."""
+        eaf = np.ascontiguousarray(eaf, np.float64)
+        stop = None if stop is None else np.ascontiguousarray(stop, np.int32)
+        rc = packed.c_struct()
+        uc = units_c_struct(units, stop)
+        ticket = C.c_int(0)
+        _check(self.lib.vfk_annotate_host_async(self.h, C.byref(rc), C.byref(uc), C.byref(params),
+                                                C.c_void_p(eaf.ctypes.data), float(fpr), float(error_rate),
+                                                C.c_void_p(counts_out.ctypes.data), C.c_void_p(stats_out.ctypes.data),
+                                                C.byref(ticket)))
+        self.__dict__.setdefault("_inflight", {})[ticket.value] = (packed, units, stop, eaf, counts_out, stats_out)
+        return ticket.value
+
+    def wait(self, ticket: int):
+        _check(self.lib.vfk_wait(self.h, C.c_int(ticket)))
+        self.__dict__.get("_inflight", {}).pop(ticket, None)
+
+    def zero_copy_batches(self) -> int:
+        return int(self.lib.vfk_zero_copy_batches(self.h))
 
     def to_host(self, buf, dtype, n):
         return buf.cpu().numpy().view(dtype)[:n].copy()
