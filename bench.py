@@ -29,6 +29,11 @@ import sys
 import threading
 import time
 
+# torchrun pins OMP_NUM_THREADS=1 for its children; the host-side batch builder (OpenMP) should use
+# this rank's share of the host cores instead.  Must happen before any OpenMP runtime is loaded.
+if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    os.environ["OMP_NUM_THREADS"] = str(max(2, (os.cpu_count() or 2) // int(os.environ["WORLD_SIZE"])))
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
