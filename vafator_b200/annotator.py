@@ -25,9 +25,9 @@ class Annotator(object):
                  mapping_qual_thr: int = 0, base_call_qual_thr: int = 29, tumor_ploidies: dict = None,
                  normal_ploidy: int = 2, fpr: float = DEFAULT_FPR, error_rate: float = DEFAULT_ERROR_RATE,
                  include_ambiguous_bases: bool = True, num_processes: int = 1, device: int = 0):
-        """Arguments as vafator/annotator.py:70-98.  `num_processes` is accepted for compatibility (the
-        reference forks one CPU worker per chromosome); here all chromosomes go to the GPU in one batch.
-        `device`: CUDA device index."""
+        """Arguments as vafator/annotator.py:70-98.  `num_processes`: the reference forks that many CPU
+        workers, one chromosome each; here it is the number of GPUs (from `device` upwards, as many as the
+        box has) the interval x BAM shards are spread over.  `device`: first CUDA device index."""
         purities = {} if purities is None else purities
         tumor_ploidies = {} if tumor_ploidies is None else tumor_ploidies
         self.mapping_quality_threshold = mapping_qual_thr
@@ -63,7 +63,9 @@ class Annotator(object):
         self.vcf_writer = VcfWriter(output_vcf, self.vcf)
         self.bam_paths = input_bams
         self.bam_readers = OrderedDict((s, [BamFile(b, "r") for b in bams]) for s, bams in input_bams.items())
-        self.engine = Engine(device, min_mapq=mapping_qual_thr, min_baseq=base_call_qual_thr,
+        import torch
+        n_dev = max(1, min(int(num_processes), torch.cuda.device_count() - device)) if torch.cuda.is_available() else 1
+        self.engine = Engine(device, devices=list(range(device, device + n_dev)), min_mapq=mapping_qual_thr, min_baseq=base_call_qual_thr,
                              include_ambiguous=include_ambiguous_bases, fpr=fpr, error_rate=error_rate)
 
     def run(self) -> None:

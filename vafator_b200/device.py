@@ -199,8 +199,19 @@ def link_mates(batch: ReadBatch, params: ParamsC) -> np.ndarray:
     return mate
 
 
-def pack_reads(batch: ReadBatch, params: ParamsC, pinned: bool = False) -> PackedReads:
-    """Canonical batch -> HBM layout (+ mate links under `params`)."""
+def read_passes(batch: ReadBatch, params: ParamsC) -> np.ndarray:
+    """Which reads the reference would push into its pileup under `params` (flag filter, MAPQ, orphans)."""
+    f = batch.flag.astype(np.uint32)
+    ok = (f & (params.flag_filter | 0x4)) == 0
+    ok &= batch.mapq.astype(np.int64) >= params.min_mapq
+    if params.ignore_orphans:
+        ok &= ~(((f & 1) != 0) & ((f & 2) == 0))
+    return ok & (batch.tid >= 0)
+
+
+def pack_reads(batch: ReadBatch, params: ParamsC, pinned: bool = False, mate: np.ndarray = None) -> PackedReads:
+    """Canonical batch -> HBM layout (+ mate links under `params`, unless given: a slice of a larger batch
+    must carry the links computed on the whole batch)."""
     s, keep = _io_reads(batch)
     plan = _PlanC()
     _io_check(libio().vfkio_pack_plan(C.byref(s), C.byref(plan)))
@@ -215,8 +226,12 @@ def pack_reads(batch: ReadBatch, params: ParamsC, pinned: bool = False) -> Packe
                                  C.c_void_p(hot.ctypes.data), C.c_void_p(cold.ctypes.data),
                                  C.c_void_p(sb.ctypes.data),
                                  C.c_void_p(cigar.ctypes.data), C.c_void_p(payload.ctypes.data)))
-    mate = _empty(n, np.uint32, pinned)
-    _io_check(libio().vfkio_link_mates(C.byref(s), C.byref(params), C.c_void_p(mate.ctypes.data)))
+    mate_out = _empty(n, np.uint32, pinned)
+    if mate is None:
+        _io_check(libio().vfkio_link_mates(C.byref(s), C.byref(params), C.c_void_p(mate_out.ctypes.data)))
+    else:
+        mate_out[:] = np.asarray(mate, np.uint32)[:n]
+    mate = mate_out
     return PackedReads(list(batch.contigs), contig_off, hot, cold, mate, sb.reshape(-1, 2), cigar, payload,
                        int(plan.max_l_qseq))
 

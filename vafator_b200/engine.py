@@ -176,13 +176,18 @@ class Engine:
     """Drives the device for a set of VCF records against a set of BAM read batches."""
 
     def __init__(self, device_index: int = 0, min_mapq: int = 0, min_baseq: int = 29, include_ambiguous: bool = True,
-                 fpr: float = 5e-7, error_rate: float = 1e-3):
+                 fpr: float = 5e-7, error_rate: float = 1e-3, devices: Optional[Sequence[int]] = None):
+        """`devices`: CUDA device indexes to shard the pileup over (interval x BAM shards, one host
+        thread per device, no collective); default: just `device_index`."""
         self.dev = _dev.Device(device_index)
+        self.extra_devs = [_dev.Device(d) for d in (devices or [])[1:]] if devices and len(devices) > 1 else []
         self.params = _dev.make_params(min_mapq=min_mapq, min_baseq=min_baseq, include_ambiguous=include_ambiguous)
         self.fpr, self.error_rate = fpr, error_rate
 
     def close(self):
         self.dev.close()
+        for d in self.extra_devs:
+            d.close()
 
     # ---- device stages on host arrays -------------------------------------------------------
     def _device_reads(self, batch: ReadBatch):
@@ -194,9 +199,34 @@ class Engine:
     def release_reads(self):
         self.__dict__.pop("_dreads", None)
 
+    def _pileup_sharded(self, batch: ReadBatch, units: VariantUnits, stop: np.ndarray) -> np.ndarray:
+        """Interval shards of one BAM over several devices (vafator_b200/sharding.py)."""
+        from concurrent.futures import ThreadPoolExecutor
+        from . import sharding
+        devs = [self.dev] + self.extra_devs
+        mate = _dev.link_mates(batch, self.params)
+        passes = _dev.read_passes(batch, self.params)
+        shards = sharding.plan_shards(batch, units, len(devs), passes, stop)
+
+        def work(k):
+            sh, dev = shards[k], devs[k % len(devs)]
+            sub, sub_mate = sharding.slice_reads(batch, mate, sh.read_lo, sh.read_hi)
+            su = sharding.slice_units(units, sh.unit_lo, sh.unit_hi)
+            dreads = dev.upload_reads(_dev.pack_reads(sub, self.params, mate=sub_mate))
+            buf = dev.pileup(dreads, dev.upload_units(su, stop[sh.unit_lo:sh.unit_hi]), self.params)
+            return dev.to_host(buf, _dev.COUNTS_DTYPE, su.n_units)
+
+        with ThreadPoolExecutor(len(devs)) as pool:
+            parts = list(pool.map(work, range(len(shards))))
+        return np.concatenate(parts)
+
     def pileup(self, batch: ReadBatch, units: VariantUnits, stop: np.ndarray) -> np.ndarray:
         if units.n_units == 0:
             return np.zeros(0, _dev.COUNTS_DTYPE)
+        if self.extra_devs and units.n_units >= 2 * (1 + len(self.extra_devs)):
+            in_order = np.all((units.tid[1:] > units.tid[:-1]) | ((units.tid[1:] == units.tid[:-1]) & (units.pos[1:] >= units.pos[:-1])))
+            if in_order:
+                return self._pileup_sharded(batch, units, stop)
         dreads = self._device_reads(batch)
         dunits = self.dev.upload_units(units, stop)
         buf = self.dev.pileup(dreads, dunits, self.params)
