@@ -61,9 +61,10 @@ typedef struct {
     uint32_t reserved;
 } vfk_read_cold;
 
-/* payload: read i owns ceil(l_qseq/21) sectors from hot.pay; sector s holds query positions
- * 21s .. 21s+20: bytes 0-20 base qualities, bytes 21-31 the 4-bit base codes (position 21s+r in
- * byte 21 + r/2, high nibble when r is even).  One (read, column) lookup = one 32-byte sector. */
+/* payload: read i owns ceil(l_qseq/20) sectors of 32 bytes from hot.pay.  A sector is four 8-byte
+ * little-endian granules; granule g of the read holds query positions 5g .. 5g+4, 12 bits each:
+ * bits [12r, 12r+8) base quality, bits [12r+8, 12r+12) BAM 4-bit base code.  One (read, column)
+ * lookup = one 64-bit load = one 32-byte DRAM sector (BAM's split seq / qual arrays cost two).      */
 typedef struct {
     int64_t n_reads;
     int32_t n_contigs;

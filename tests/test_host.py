@@ -35,12 +35,12 @@ def test_pack_layout_round_trips(path):
             assert (pk.hot["fmk"][i] & 0xFFFF) == r["flag"] and ((pk.hot["fmk"][i] >> 16) & 0xFF) == r["mapq"]
             lq = len(r["seq"])
             base = int(pk.hot["pay"][i]) * 32
+            gran = pk.payload[base:base + 32 * ((lq + 19) // 20)].view(np.uint64)
             for q in range(lq):
-                s, rr = divmod(q, 21)
-                assert pk.payload[base + 32 * s + rr] == ord(r["qual"][q]) - 33
-                b = pk.payload[base + 32 * s + 21 + rr // 2]
-                code = (b & 15) if rr & 1 else (b >> 4)
-                assert SEQ_CHARS[code] == r["seq"][q]
+                g, rr = divmod(q, 5)
+                w = (int(gran[g]) >> (12 * rr)) & 0xFFF
+                assert (w & 0xFF) == ord(r["qual"][q]) - 33
+                assert SEQ_CHARS[w >> 8] == r["seq"][q]
             ops = re.findall(r"(\d+)([MIDNSHP=X])", r["cigar"])
             span = sum(int(n) for n, o in ops if o in "MDN=X")
             assert pk.hot["span"][i] == span

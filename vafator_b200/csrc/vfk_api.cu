@@ -9,13 +9,13 @@
 
 namespace vfk {
 cudaError_t launch_pileup(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, int max_l_qseq, vfk_counts *out,
-                          void *resolved_scratch, unsigned long long *work_counter, uint32_t *deferred, uint32_t *n_deferred, int sm_count,
-                          cudaStream_t stream, int *launches);
+                          void *resolved_scratch, void *counters, uint32_t *lists, int sm_count, cudaStream_t stream,
+                          int *launches);
 cudaError_t launch_locate(const ReadsDev &R, const UnitsDev &V, void *resolved, unsigned long long *cand_sum, cudaStream_t stream,
                           int *launches);
 cudaError_t launch_pileup_resolved(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, int max_l_qseq, vfk_counts *out,
-                                   void *resolved, unsigned long long *work_counter, uint32_t *deferred, uint32_t *n_deferred,
-                                   int sm_count, cudaStream_t stream, int *launches);
+                                   void *resolved, void *counters, uint32_t *lists, int sm_count, cudaStream_t stream,
+                                   int *launches);
 cudaError_t launch_epilogue(int64_t n_units, const vfk_counts *counts, const double *eaf, double fpr, double error_rate,
                             vfk_stats *out, cudaStream_t stream, int *launches);
 cudaError_t launch_values(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, int32_t max_per_unit, uint32_t *values,
@@ -82,8 +82,7 @@ struct Slot {
 struct vfk_handle {
     int device = 0;
     int sm_count = 0;
-    unsigned long long *work_counter = nullptr;  // scratch of the device-pointer API: 8 B + n_deferred 4 B
-    uint32_t *n_deferred = nullptr;
+    void *counters = nullptr;  // 32-byte scratch of the device-pointer API (layout: vfk_pileup.cu launch_posb)
     DevBuf deferred, resolved;  // per-launch scratch: deep-unit list, located units (32 B each)
     int64_t launches = 0;
     Slot slot[2];
@@ -121,10 +120,7 @@ extern "C" int vfk_create(int device, vfk_handle **out) {
         CU(cudaMalloc(&s.counters, 32));
         CU(cudaMallocHost((void **)&s.h_cand, sizeof(unsigned long long)));
     }
-    void *p = nullptr;
-    CU(cudaMalloc(&p, 16));
-    h->work_counter = (unsigned long long *)p;
-    h->n_deferred = (uint32_t *)((char *)p + 8);
+    CU(cudaMalloc(&h->counters, 32));
     *out = h;
     return VFK_OK;
 }
@@ -136,7 +132,7 @@ extern "C" int vfk_destroy(vfk_handle *h) {
     for (Slot &s : h->slot) s.release();
     h->deferred.release();
     h->resolved.release();
-    if (h->work_counter) cudaFree(h->work_counter);
+    if (h->counters) cudaFree(h->counters);
     delete h;
     return VFK_OK;
 }
@@ -192,7 +188,7 @@ extern "C" int vfk_pileup(vfk_handle *h, const vfk_read_batch *reads, const vfk_
     if (!out) return fail(VFK_EINVAL, "vfk_pileup: out is NULL");
     CU(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;  // NULL = the CUDA default stream
-    rc = h->deferred.reserve((size_t)units->n_units * sizeof(uint32_t));
+    rc = h->deferred.reserve((size_t)units->n_units * 2 * sizeof(uint32_t));
     if (rc) return rc;
     rc = h->resolved.reserve((size_t)units->n_units * 32);
     if (rc) return rc;
@@ -200,8 +196,8 @@ extern "C" int vfk_pileup(vfk_handle *h, const vfk_read_batch *reads, const vfk_
     vfk::UnitsDev V;
     to_dev(reads, units, R, V);
     int launches = 0;
-    cudaError_t e = vfk::launch_pileup(R, V, *params, reads->max_l_qseq, out, h->resolved.p, h->work_counter, (uint32_t *)h->deferred.p,
-                                       h->n_deferred, h->sm_count, st, &launches);
+    cudaError_t e = vfk::launch_pileup(R, V, *params, reads->max_l_qseq, out, h->resolved.p, h->counters, (uint32_t *)h->deferred.p,
+                                       h->sm_count, st, &launches);
     h->launches += launches;
     if (e != cudaSuccess) return fail(VFK_ECUDA, "pileup launch: %s", cudaGetErrorString(e));
     return VFK_OK;
@@ -301,9 +297,7 @@ extern "C" int vfk_annotate_host_async(vfk_handle *h, const vfk_read_batch *read
     CU(cudaSetDevice(h->device));
     Slot &S = h->slot[si];
     cudaStream_t st = S.stream;
-    unsigned long long *work_counter = (unsigned long long *)S.counters;
-    uint32_t *n_deferred = (uint32_t *)((char *)S.counters + 8);
-    unsigned long long *cand_sum = (unsigned long long *)((char *)S.counters + 16);
+    unsigned long long *cand_sum = (unsigned long long *)((char *)S.counters + 24);
     // ---- stage 1: what the locate pass needs
     STAGE(S.contig, reads->contig_off, (size_t)(reads->n_contigs + 1) * sizeof(int64_t));
     STAGE(S.sb, reads->sb, (size_t)nr * 8);
@@ -314,7 +308,7 @@ extern "C" int vfk_annotate_host_async(vfk_handle *h, const vfk_read_batch *read
     STAGE(S.soff, units->seq_off, (size_t)nu * 4);
     STAGE(S.ins, units->ins_seq, (size_t)(units->n_ins_seq > 0 ? units->n_ins_seq : 1));
     if (units->stop) STAGE(S.stop, units->stop, (size_t)nu * 4);
-    rc = S.deferred.reserve((size_t)nu * sizeof(uint32_t));
+    rc = S.deferred.reserve((size_t)nu * 2 * sizeof(uint32_t));
     if (rc) return rc;
     rc = S.resolved.reserve((size_t)nu * 32);
     if (rc) return rc;
@@ -375,8 +369,8 @@ extern "C" int vfk_annotate_host_async(vfk_handle *h, const vfk_read_batch *read
     if (rc) return rc;
     rc = S.stats.reserve((size_t)nu * sizeof(vfk_stats));
     if (rc) return rc;
-    e = vfk::launch_pileup_resolved(R, V, *params, reads->max_l_qseq, (vfk_counts *)S.counts.p, S.resolved.p, work_counter,
-                                    (uint32_t *)S.deferred.p, n_deferred, h->sm_count, st, &launches);
+    e = vfk::launch_pileup_resolved(R, V, *params, reads->max_l_qseq, (vfk_counts *)S.counts.p, S.resolved.p, S.counters,
+                                    (uint32_t *)S.deferred.p, h->sm_count, st, &launches);
     if (e != cudaSuccess) return fail(VFK_ECUDA, "pileup launch: %s", cudaGetErrorString(e));
     e = vfk::launch_epilogue(nu, (const vfk_counts *)S.counts.p, (const double *)S.eaf.p, fpr, error_rate, (vfk_stats *)S.stats.p,
                              st, &launches);

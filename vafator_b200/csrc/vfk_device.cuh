@@ -78,22 +78,16 @@ struct Contribution {
 __device__ __forceinline__ bool is_ref_op(int op) { return op == OP_M || op == OP_D || op == OP_N || op == OP_EQ || op == OP_X; }
 __device__ __forceinline__ bool is_aln_op(int op) { return op == OP_M || op == OP_EQ || op == OP_X; }
 
-// ---- payload sector addressing: 21 (quality, base) pairs per 32-byte sector ----
-__device__ __forceinline__ void sector_of(uint32_t q, uint32_t &s, uint32_t &r) {
-    s = q / 21u;
-    r = q - s * 21u;
+// ---- payload addressing: 8-byte granules of 5 query positions, 12 bits each (quality in the low 8
+// bits, BAM base code in the next 4); 4 granules per 32-byte sector.  One (read, column) lookup is ONE
+// 64-bit load of one sector.
+__device__ __forceinline__ uint32_t pay_lookup(const uint8_t *__restrict__ payload, uint32_t pay, uint32_t q) {
+    const uint32_t g = q / 5u, r = q - g * 5u;
+    const unsigned long long w = __ldg(reinterpret_cast<const unsigned long long *>(payload + ((size_t)pay << 5)) + g);
+    return (uint32_t)(w >> (12u * r)) & 0xFFFu;
 }
-__device__ __forceinline__ int pay_qual(const uint8_t *__restrict__ payload, uint32_t pay, uint32_t q) {
-    uint32_t s, r;
-    sector_of(q, s, r);
-    return __ldg(payload + ((size_t)(pay + s) << 5) + r);
-}
-__device__ __forceinline__ int pay_base(const uint8_t *__restrict__ payload, uint32_t pay, uint32_t q) {
-    uint32_t s, r;
-    sector_of(q, s, r);
-    int b = __ldg(payload + ((size_t)(pay + s) << 5) + 21u + (r >> 1));
-    return (r & 1u) ? (b & 15) : (b >> 4);
-}
+__device__ __forceinline__ int word_qual(uint32_t w) { return (int)(w & 0xFFu); }
+__device__ __forceinline__ int word_base(uint32_t w) { return (int)(w >> 8); }
 
 __device__ __forceinline__ uint32_t wang_hash(uint32_t k) {
     k += ~(k << 15); k ^= (k >> 10); k += (k << 3); k ^= (k >> 6); k += ~(k << 11); k ^= (k >> 16);
@@ -219,9 +213,9 @@ __device__ __forceinline__ int64_t next_pushed(const ReadsDev &R, const vfk_para
 // starts at or before `col` or is the first pushed record after it (bam_plp_auto reads one ahead).
 __device__ __forceinline__ int tweaked_quality(const ReadsDev &R, const vfk_params &P, const Unit &U, int64_t i,
                                                const uint4 &hot, uint32_t mw, const uint4 &cold_if_general, bool general,
-                                               int q, int l_qseq, bool q_is_column_base) {
+                                               int q, int l_qseq, bool q_is_column_base, uint32_t my_word) {
     if (q >= l_qseq) return 0;
-    int qi = pay_qual(R.payload, hot.w, (uint32_t)q);
+    int qi = word_qual(my_word);
     uint32_t flag = hot.z & 0xFFFFu;
     if (!P.ignore_overlaps || !(flag & F_PROPER) || (flag & F_MUNMAP)) return qi;
     if (mw == VFK_NO_MATE) return qi;
@@ -248,9 +242,10 @@ __device__ __forceinline__ int tweaked_quality(const ReadsDev &R, const vfk_para
         ml = mr.l_qseq;
     }
     if (mq_index >= ml) return qi;
-    int qm = pay_qual(R.payload, mh.w, (uint32_t)mq_index);
-    int bm = pay_base(R.payload, mh.w, (uint32_t)mq_index);
-    int bi = pay_base(R.payload, hot.w, (uint32_t)q);
+    const uint32_t mate_word = pay_lookup(R.payload, mh.w, (uint32_t)mq_index);
+    int qm = word_qual(mate_word);
+    int bm = word_base(mate_word);
+    int bi = word_base(my_word);
     bool i_first = i < m;  // the earlier record holds the hash slot ("a" in htslib)
     uint32_t mymul = i_first ? sel : (1u - sel);
     if (bi == bm) {
@@ -299,7 +294,7 @@ __device__ __forceinline__ uint32_t insertion_hits(const ReadsDev &R, const uint
             // and any leading soft clip) against ALT[0][1:]  -- SURVEY.md A.5
             bool ok = rel + U.len <= qlen;
             for (int t = 0; ok && t < U.len; ++t)
-                ok = pay_base(R.payload, hot.w, (uint32_t)(qs + rel + t)) == (int)U.ins[t];
+                ok = word_base(pay_lookup(R.payload, hot.w, (uint32_t)(qs + rel + t))) == (int)U.ins[t];
             hits += ok ? 1u : 0u;
         }
     }
@@ -349,7 +344,8 @@ __device__ __forceinline__ Contribution evaluate(const ReadsDev &R, const vfk_pa
         if (!r.covered) return o;
     }
     o.in_col = true;
-    const int q = tweaked_quality(R, P, U, i, hot, mw, cold, general, r.qpos, r.l_qseq, !r.is_del);
+    const uint32_t my_word = r.qpos < r.l_qseq ? pay_lookup(R.payload, hot.w, (uint32_t)r.qpos) : 0u;
+    const int q = tweaked_quality(R, P, U, i, hot, mw, cold, general, r.qpos, r.l_qseq, !r.is_del, my_word);
     if (q < P.min_baseq) return o;  // pysam pileup_base_qual_skip
     o.mq = (int)((hot.z >> 16) & 0xFF);
     o.bq = q;
@@ -358,7 +354,7 @@ __device__ __forceinline__ Contribution evaluate(const ReadsDev &R, const vfk_pa
         if (r.is_refskip) return o;
         o.in_dp = true;
         if (r.is_del) return o;  // counted in DP as the "" allele, belongs to no reported list
-        int code = pay_base(R.payload, hot.w, (uint32_t)r.qpos);
+        int code = word_base(my_word);
         o.ambiguous = code_is_ambiguous(code);
         o.ref = (uint32_t)code == U.ref_code;
         o.alt = ((uint32_t)code == U.alt_code) ? 1u : 0u;

@@ -5,14 +5,17 @@
 // MQ / BQ / read-position distributions to integers: counts, twice-the-median, and twice the
 // ALT mid-rank sum that scipy.stats.ranksums would compute (vafator/rank_sum_test.py:11).
 //
-// pileup_warp_kernel : one warp per unit, lanes = candidate reads.  Persistent grid, units handed
-//                      out in small contiguous grabs from a global counter.  Two ways to reduce
-//                      the distributions:
-//     shallow  (<= 64 candidates, <= 32 of them contributing): values stay in registers, ranks
-//              come from a bit-sliced (radix) comparison built on warp ballots -- no shared
-//              memory traffic, no atomics;
-//     deep     histograms in shared memory (u16 counters, two per word) + warp scans.
-// pileup_block_kernel: one CTA per unit for the (rare) columns too deep for u16 counters.
+// locate_kernel       : one thread per unit, binary search of the position index.
+// pileup_warp_kernel  : one warp per unit, lanes = candidate reads.  Persistent grid, units handed out
+//                       in small contiguous grabs from a global counter.  Handles the shallow columns
+//                       (<= 64 candidates, <= 32 of them contributing -- every 30x / 60x column): values
+//                       stay in registers, ranks come from a bit-sliced (radix) comparison built on warp
+//                       ballots.  No shared-memory histograms, no atomics, no calls, no stack.  Anything
+//                       else is appended to one of two device-side lists:
+// pileup_deep_kernel  : one warp per listed unit, histograms in shared memory (u16 counters, two per
+//                       word) + warp scans;
+// pileup_block_kernel : one CTA per listed unit, u32 counters, for columns with > 32767 candidates.
+#include <algorithm>
 #include "vfk_device.cuh"
 
 namespace vfk {
@@ -106,7 +109,7 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 // mid-rank sum over the pooled ranking.  Executed by one full warp.
 //   2*rank_sum(ALT) = sum_v alt[v] * (2*below(v) + ties(v) + 1)
 template <typename CT, int B>
-__device__ __noinline__ void reduce_metric(const uint32_t *ref_slot, const uint32_t *alt_slot, int off, int lane,
+__device__ __forceinline__ void reduce_metric(const uint32_t *ref_slot, const uint32_t *alt_slot, int off, int lane,
                                            int &med2_ref, int &med2_alt, uint64_t &s2) {
     constexpr int BPL = B / 32;  // consecutive bins per lane
     const int b0 = off + lane * BPL;
@@ -242,7 +245,7 @@ __device__ __forceinline__ void radix_finish(uint32_t v, uint32_t R, uint32_t A,
 // deep path of the warp kernel: shared-memory histograms
 // ------------------------------------------------------------------------------------------
 template <int POSB>
-__device__ __noinline__ void unit_by_histogram(const ReadsDev &R, const vfk_params &P, const Unit &U, uint32_t *ref_slot,
+__device__ __forceinline__ void unit_by_histogram(const ReadsDev &R, const vfk_params &P, const Unit &U, uint32_t *ref_slot,
                                                uint32_t *alt_slot, int lane, vfk_counts *out) {
     using L = Layout<POSB>;
     constexpr int WORDS = L::BINS / 2;
@@ -295,14 +298,13 @@ template <int POSB>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, VFK_MIN_CTAS)
 pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_units, const uint8_t *__restrict__ ins_seq,
                    vfk_params P, vfk_counts *__restrict__ out, unsigned long long *__restrict__ work_counter,
-                   uint32_t *__restrict__ deferred, uint32_t *__restrict__ n_deferred) {
+                   uint32_t *__restrict__ block_list, uint32_t *__restrict__ n_block, uint32_t *__restrict__ warp_list,
+                   uint32_t *__restrict__ n_warp) {
     using L = Layout<POSB>;
-    constexpr int WORDS = L::BINS / 2;  // u16 bins
-    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ uint32_t stage_all[WARPS_PER_CTA][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    uint32_t *ref_slot = smem + (size_t)warp * 2 * WORDS;
-    uint32_t *alt_slot = ref_slot + WORDS;
+    uint32_t *stage = stage_all[warp];
 
     for (;;) {
         unsigned long long base = 0;
@@ -347,15 +349,12 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
                 if (lane == 0) store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind, 0u, 0u);
                 continue;
             }
-            if (n_cand > WARP_PATH_MAX_CAND) {
+            if (n_cand > 64) {  // deep: handed to the histogram kernels through a device-side list
                 if (lane == 0) {
-                    deferred[atomicAdd(n_deferred, 1u)] = (uint32_t)u;
+                    if (n_cand > WARP_PATH_MAX_CAND) block_list[atomicAdd(n_block, 1u)] = (uint32_t)u;
+                    else warp_list[atomicAdd(n_warp, 1u)] = (uint32_t)u;
                     store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind | VFK_ST_DEFERRED, (uint32_t)n_cand, 0u);
                 }
-                continue;
-            }
-            if (n_cand > 64) {
-                unit_by_histogram<POSB>(R, P, U, ref_slot, alt_slot, lane, out + u);
                 continue;
             }
             // ---- shallow: at most two reads per lane ----
@@ -368,7 +367,10 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
             const uint32_t m0 = __ballot_sync(FULL, k0), m1 = __ballot_sync(FULL, k1);
             const bool heavy = __any_sync(FULL, c0.alt > 1u || c1.alt > 1u || c0.qpos >= POSB || c1.qpos >= POSB);
             if (heavy || __popc(m0) + __popc(m1) > 32) {  // rare: re-done through the histograms
-                unit_by_histogram<POSB>(R, P, U, ref_slot, alt_slot, lane, out + u);
+                if (lane == 0) {
+                    warp_list[atomicAdd(n_warp, 1u)] = (uint32_t)u;
+                    store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind | VFK_ST_DEFERRED, (uint32_t)n_cand, 0u);
+                }
                 continue;
             }
             int dp = __popc(__ballot_sync(FULL, c0.in_dp)) + __popc(__ballot_sync(FULL, c1.in_dp));
@@ -378,11 +380,11 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
             uint32_t pk = k0 ? pack(c0) : 0u;
             if (m1) {  // move the second chunk's contributions into lanes the first one left free
                 const int n1 = __popc(m1);
-                if (k1) ref_slot[__popc(m1 & lt_mask)] = pack(c1);
+                if (k1) stage[__popc(m1 & lt_mask)] = pack(c1);
                 __syncwarp();
                 if (!k0) {
                     const int f = __popc(~m0 & lt_mask);
-                    if (f < n1) pk = ref_slot[f];
+                    if (f < n1) pk = stage[f];
                 }
                 __syncwarp();
             }
@@ -405,6 +407,33 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
             if (lane == 0) store_counts(out + u, dp, n_amb, ac_ref, ac_alt, med2, s2, U.kind, (uint32_t)n_cand, (uint32_t)n_cover,
                                             (uint32_t)n_col);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// warp per listed unit, shared-memory histograms
+// ------------------------------------------------------------------------------------------
+template <int POSB>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+pileup_deep_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, const uint8_t *__restrict__ ins_seq, vfk_params P,
+                   vfk_counts *__restrict__ out, const uint32_t *__restrict__ warp_list, const uint32_t *__restrict__ n_warp,
+                   uint32_t *__restrict__ deep_work) {
+    using L = Layout<POSB>;
+    constexpr int WORDS = L::BINS / 2;  // u16 bins
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *ref_slot = smem + (size_t)warp * 2 * WORDS;
+    uint32_t *alt_slot = ref_slot + WORDS;
+    const uint32_t n = *n_warp;
+    for (;;) {
+        uint32_t k = 0;
+        if (lane == 0) k = atomicAdd(deep_work, 1u);
+        k = __shfl_sync(FULL, k, 0);
+        if (k >= n) break;
+        const int64_t u = warp_list[k];
+        Unit U;
+        unit_from(res[u], ins_seq, U);
+        unit_by_histogram<POSB>(R, P, U, ref_slot, alt_slot, lane, out + u);
     }
 }
 
@@ -496,36 +525,51 @@ cudaError_t launch_locate(const ReadsDev &R, const UnitsDev &V, void *resolved, 
     return cudaGetLastError();
 }
 
+// scratch words (32 bytes, device): @0 u64 unit work counter, @8 u32 block-list length, @12 u32 warp-list
+// length, @16 u32 deep-kernel work counter, @24 u64 candidate sum (locate pass).  lists: 2 * n_units u32.
 template <int POSB>
 static cudaError_t launch_posb(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, vfk_counts *out, ResolvedUnit *res,
-                               unsigned long long *work_counter, uint32_t *deferred, uint32_t *n_deferred, int sm_count,
-                               cudaStream_t stream, int *launches) {
+                               void *counters, uint32_t *lists, int sm_count, cudaStream_t stream, int *launches) {
     using L = Layout<POSB>;
-    const size_t smem_warp = (size_t)WARPS_PER_CTA * 2 * (L::BINS / 2) * sizeof(uint32_t);
+    const size_t smem_deep = (size_t)WARPS_PER_CTA * 2 * (L::BINS / 2) * sizeof(uint32_t);
     const size_t smem_block = (size_t)2 * L::BINS * sizeof(uint32_t);
+    unsigned long long *work = (unsigned long long *)counters;
+    uint32_t *n_block = (uint32_t *)((char *)counters + 8), *n_warp = (uint32_t *)((char *)counters + 12);
+    uint32_t *deep_work = (uint32_t *)((char *)counters + 16);
+    uint32_t *block_list = lists, *warp_list = lists + V.n;
     cudaError_t e;
-    if (smem_warp > 48 * 1024) {  // opt in to large dynamic shared memory (long-read instantiation only)
-        e = cudaFuncSetAttribute(pileup_warp_kernel<POSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_warp);
+    if (smem_deep > 48 * 1024) {  // opt in to large dynamic shared memory (long-read instantiation only)
+        e = cudaFuncSetAttribute(pileup_deep_kernel<POSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_deep);
         if (e != cudaSuccess) return e;
     }
     int ctas_per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pileup_warp_kernel<POSB>, WARPS_PER_CTA * 32, smem_warp);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pileup_warp_kernel<POSB>, WARPS_PER_CTA * 32, 0);
     if (e != cudaSuccess) return e;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     // persistent grid: a whole number of waves, never more CTAs than there is work
     int64_t want = (V.n + (int64_t)GRAB * WARPS_PER_CTA - 1) / ((int64_t)GRAB * WARPS_PER_CTA);
     int64_t grid = (int64_t)sm_count * ctas_per_sm;
     if (want < grid) grid = want < 1 ? 1 : want;
-    e = cudaMemsetAsync(work_counter, 0, 16, stream);  // work counter and deferred-unit count share one allocation
+    e = cudaMemsetAsync(counters, 0, 24, stream);
     if (e != cudaSuccess) return e;
-    pileup_warp_kernel<POSB><<<(unsigned)grid, WARPS_PER_CTA * 32, smem_warp, stream>>>(R, res, V.n, V.ins_seq, P, out, work_counter,
-                                                                                        deferred, n_deferred);
+    pileup_warp_kernel<POSB><<<(unsigned)grid, WARPS_PER_CTA * 32, 0, stream>>>(R, res, V.n, V.ins_seq, P, out, work, block_list,
+                                                                                n_block, warp_list, n_warp);
     ++*launches;
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    if (R.n_reads > WARP_PATH_MAX_CAND) {  // only then can a column be too deep for the warp path
-        pileup_block_kernel<POSB><<<(unsigned)sm_count, WARPS_PER_CTA * 32, smem_block, stream>>>(R, res, V.ins_seq, P, out, deferred,
-                                                                                                  n_deferred);
+    int deep_ctas = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&deep_ctas, pileup_deep_kernel<POSB>, WARPS_PER_CTA * 32, smem_deep);
+    if (e != cudaSuccess) return e;
+    if (deep_ctas < 1) deep_ctas = 1;
+    int64_t deep_grid = std::min<int64_t>((int64_t)sm_count * deep_ctas, (V.n + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
+    pileup_deep_kernel<POSB><<<(unsigned)deep_grid, WARPS_PER_CTA * 32, smem_deep, stream>>>(R, res, V.ins_seq, P, out, warp_list,
+                                                                                             n_warp, deep_work);
+    ++*launches;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (R.n_reads > WARP_PATH_MAX_CAND) {  // only then can a column be too deep for the warp kernels
+        pileup_block_kernel<POSB><<<(unsigned)sm_count, WARPS_PER_CTA * 32, smem_block, stream>>>(R, res, V.ins_seq, P, out,
+                                                                                                  block_list, n_block);
         ++*launches;
         e = cudaGetLastError();
     }
@@ -534,23 +578,22 @@ static cudaError_t launch_posb(const ReadsDev &R, const UnitsDev &V, const vfk_p
 
 // the pileup kernels on units that launch_locate has resolved
 cudaError_t launch_pileup_resolved(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, int max_l_qseq, vfk_counts *out,
-                                   void *resolved, unsigned long long *work_counter, uint32_t *deferred, uint32_t *n_deferred,
-                                   int sm_count, cudaStream_t stream, int *launches) {
+                                   void *resolved, void *counters, uint32_t *lists, int sm_count, cudaStream_t stream,
+                                   int *launches) {
     ResolvedUnit *res = (ResolvedUnit *)resolved;
     // read positions run 0 .. l_qseq (a read hanging in a trailing deletion reports l_qseq)
-    if (max_l_qseq < 256) return launch_posb<256>(R, V, P, out, res, work_counter, deferred, n_deferred, sm_count, stream, launches);
-    if (max_l_qseq < 512) return launch_posb<512>(R, V, P, out, res, work_counter, deferred, n_deferred, sm_count, stream, launches);
-    if (max_l_qseq < 1024) return launch_posb<1024>(R, V, P, out, res, work_counter, deferred, n_deferred, sm_count, stream, launches);
-    return launch_posb<4096>(R, V, P, out, res, work_counter, deferred, n_deferred, sm_count, stream, launches);
+    if (max_l_qseq < 256) return launch_posb<256>(R, V, P, out, res, counters, lists, sm_count, stream, launches);
+    if (max_l_qseq < 512) return launch_posb<512>(R, V, P, out, res, counters, lists, sm_count, stream, launches);
+    if (max_l_qseq < 1024) return launch_posb<1024>(R, V, P, out, res, counters, lists, sm_count, stream, launches);
+    return launch_posb<4096>(R, V, P, out, res, counters, lists, sm_count, stream, launches);
 }
 
 cudaError_t launch_pileup(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, int max_l_qseq, vfk_counts *out,
-                          void *resolved_scratch, unsigned long long *work_counter, uint32_t *deferred, uint32_t *n_deferred,
-                          int sm_count, cudaStream_t stream, int *launches) {
+                          void *resolved_scratch, void *counters, uint32_t *lists, int sm_count, cudaStream_t stream,
+                          int *launches) {
     cudaError_t e = launch_locate(R, V, resolved_scratch, nullptr, stream, launches);
     if (e != cudaSuccess) return e;
-    return launch_pileup_resolved(R, V, P, max_l_qseq, out, resolved_scratch, work_counter, deferred, n_deferred, sm_count, stream,
-                                  launches);
+    return launch_pileup_resolved(R, V, P, max_l_qseq, out, resolved_scratch, counters, lists, sm_count, stream, launches);
 }
 
 }  // namespace vfk

@@ -31,7 +31,7 @@ inline Shape shape_of(const vfkio_reads *r, int64_t i) {
     bool simple = n == 1 && is_match(c[0] & 15u) && (int64_t)(c[0] >> 4) == (int64_t)r->l_qseq[i];
     return {span, simple};
 }
-inline int64_t sectors_of(int32_t l_qseq) { return ((int64_t)l_qseq + 20) / 21; }
+inline int64_t sectors_of(int32_t l_qseq) { return ((int64_t)l_qseq + 19) / 20; }  // 4 granules x 5 positions
 }  // namespace
 
 extern "C" int vfkio_pack_plan(const vfkio_reads *r, vfkio_plan *plan) {
@@ -96,20 +96,21 @@ extern "C" int vfkio_pack(const vfkio_reads *r, const vfkio_plan *plan, int64_t 
         cold[i].reserved = 0;
         sb[2 * i] = r->pos[i];
         if (!sh.simple) memcpy(cigar + cig[i], r->cigar + r->cigar_off[i], (size_t)r->n_cigar[i] * 4);
-        // payload sectors: 21 qualities + 21 nibbles each
+        // payload: 8-byte granules of 5 positions x 12 bits (quality | base << 8), 4 granules per sector
         const int32_t l = r->l_qseq[i];
         const uint8_t *q = r->qual + r->qual_off[i];
         const uint8_t *sq = r->seq + r->seq_off[i];
-        uint8_t *dst = payload + ((size_t)pay[i] << 5);
-        for (int32_t base = 0; base < l; base += 21, dst += 32) {
-            const int32_t m = std::min(21, l - base);
-            memcpy(dst, q + base, (size_t)m);
-            memset(dst + m, 0, (size_t)(32 - m));
-            for (int32_t t = 0; t < m; ++t) {
-                const int32_t j = base + t;
-                const uint8_t code = (j & 1) ? (sq[j >> 1] & 15) : (sq[j >> 1] >> 4);
-                dst[21 + (t >> 1)] |= (t & 1) ? code : (uint8_t)(code << 4);
+        uint64_t *dst = reinterpret_cast<uint64_t *>(payload + ((size_t)pay[i] << 5));
+        const int64_t n_gran = sectors_of(l) * 4;
+        for (int64_t g = 0; g < n_gran; ++g) {
+            uint64_t w = 0;
+            for (int t = 0; t < 5; ++t) {
+                const int64_t j = g * 5 + t;
+                if (j >= l) break;
+                const uint64_t code = (j & 1) ? (sq[j >> 1] & 15) : (sq[j >> 1] >> 4);
+                w |= ((uint64_t)q[j] | (code << 8)) << (12 * t);
             }
+            dst[g] = w;
         }
     }
     // back pointers: with pmax[j] the running maximum of the reference end inside the contig,
