@@ -81,9 +81,30 @@ __device__ __forceinline__ bool is_aln_op(int op) { return op == OP_M || op == O
 // ---- payload addressing: 8-byte granules of 5 query positions, 12 bits each (quality in the low 8
 // bits, BAM base code in the next 4); 4 granules per 32-byte sector.  One (read, column) lookup is ONE
 // 64-bit load of one sector.
+#ifndef VFK_GATHER_LD
+#define VFK_GATHER_LD 0
+#endif
+// 64-bit gather load; the variants exist to measure how the cache policy changes DRAM traffic
+__device__ __forceinline__ unsigned long long gather_ld64(const unsigned long long *p) {
+#if VFK_GATHER_LD == 1
+    unsigned long long v;
+    asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+#elif VFK_GATHER_LD == 2
+    return __ldcs(p);
+#elif VFK_GATHER_LD == 3
+    return __ldcv(p);
+#elif VFK_GATHER_LD == 4
+    unsigned long long v;
+    asm volatile("ld.global.L1::no_allocate.L2::evict_first.b64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
 __device__ __forceinline__ uint32_t pay_lookup(const uint8_t *__restrict__ payload, uint32_t pay, uint32_t q) {
     const uint32_t g = q / 5u, r = q - g * 5u;
-    const unsigned long long w = __ldg(reinterpret_cast<const unsigned long long *>(payload + ((size_t)pay << 5)) + g);
+    const unsigned long long w = gather_ld64(reinterpret_cast<const unsigned long long *>(payload + ((size_t)pay << 5)) + g);
     return (uint32_t)(w >> (12u * r)) & 0xFFFu;
 }
 __device__ __forceinline__ int word_qual(uint32_t w) { return (int)(w & 0xFFu); }

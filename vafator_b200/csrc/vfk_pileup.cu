@@ -50,7 +50,8 @@ locate_kernel(ReadsDev R, UnitsDev V, ResolvedUnit *__restrict__ res, unsigned l
     if (u >= V.n) return;
     const int32_t tid = __ldg(V.tid + u);
     const int32_t col = __ldg(V.pos + u);
-    const int64_t c0 = __ldg(R.contig_off + tid), c1 = __ldg(R.contig_off + tid + 1);
+    const bool known = tid >= 0 && tid < R.n_contigs;  // an unknown contig gets an empty read range
+    const int64_t c0 = known ? __ldg(R.contig_off + tid) : 0, c1 = known ? __ldg(R.contig_off + tid + 1) : 0;
     int64_t a = c0, b = c1;
     while (a < b) {
         const int64_t m = (a + b) >> 1;

@@ -19,7 +19,8 @@ values_kernel(ReadsDev R, UnitsDev V, vfk_params P, int32_t max_per_unit, uint32
     if (u >= V.n) return;
     // locate (one warp, lane 0 searches: this path is not performance critical)
     const int32_t tid = __ldg(V.tid + u), col = __ldg(V.pos + u);
-    const int64_t c0 = __ldg(R.contig_off + tid), c1 = __ldg(R.contig_off + tid + 1);
+    const bool known = tid >= 0 && tid < R.n_contigs;
+    const int64_t c0 = known ? __ldg(R.contig_off + tid) : 0, c1 = known ? __ldg(R.contig_off + tid + 1) : 0;
     int64_t a = c0, b = c1;
     while (a < b) {
         const int64_t m = (a + b) >> 1;
@@ -38,7 +39,7 @@ values_kernel(ReadsDev R, UnitsDev V, vfk_params P, int32_t max_per_unit, uint32
         Contribution c;
         c.ref = false; c.alt = 0; c.mq = c.bq = c.qpos = 0;
         if (i < U.hi) c = evaluate(R, P, U, i);
-        const uint32_t copies = (c.ref ? 1u : 0u) > c.alt ? 1u : (c.alt > 0u ? c.alt : (c.ref ? 1u : 0u));
+        const uint32_t copies = c.alt > 0u ? c.alt : (c.ref ? 1u : 0u);  // max(ref, alt multiplicity)
         // exclusive prefix of `copies` over the warp
         uint32_t incl = copies;
 #pragma unroll
