@@ -344,15 +344,19 @@ __device__ __forceinline__ uint32_t deletion_hits(const ReadsDev &R, const uint4
 
 // Everything one read contributes to one unit.  `hot` / `mw` are the read's header and mate word
 // (the caller loads them, possibly one unit ahead of use).
+// SIMPLE: the caller knows the read's CIGAR is one M/=/X op;  UNLINKED: ... and that it has no overlap
+// partner.  Both only prune code (the thread-per-unit kernel sorts its reads into those classes first).
+template <bool SIMPLE = false, bool UNLINKED = false>
 __device__ __forceinline__ Contribution evaluate(const ReadsDev &R, const vfk_params &P, const Unit &U, int64_t i,
-                                                 const uint4 &hot, uint32_t mw) {
+                                                 const uint4 &hot, uint32_t mw_in) {
+    const uint32_t mw = UNLINKED ? VFK_NO_MATE : mw_in;
     Contribution o;
     o.covers = false; o.in_col = false; o.in_dp = false; o.ambiguous = false; o.ref = false; o.alt = 0; o.mq = 0; o.bq = 0; o.qpos = 0; o.pos_overflow = false;
     const int32_t rpos = (int32_t)hot.x;
     if (U.col < rpos || U.col >= rpos + (int32_t)hot.y) return o;
     o.covers = true;
     if (!read_passes(hot.z, P)) return o;
-    const bool general = (hot.z >> 24) != 0u;
+    const bool general = SIMPLE ? false : (hot.z >> 24) != 0u;
     uint4 cold = make_uint4(0, 0, 0, 0);
     Resolved r;
     if (!general) {
@@ -393,7 +397,7 @@ __device__ __forceinline__ Contribution evaluate(const ReadsDev &R, const vfk_pa
 }
 
 __device__ __forceinline__ Contribution evaluate(const ReadsDev &R, const vfk_params &P, const Unit &U, int64_t i) {
-    return evaluate(R, P, U, i, __ldg(R.hot + i), __ldg(R.mate + i));
+    return evaluate<false, false>(R, P, U, i, __ldg(R.hot + i), __ldg(R.mate + i));
 }
 
 __device__ __forceinline__ void unit_from(const ResolvedUnit &r, const uint8_t *__restrict__ ins_seq, Unit &U) {
