@@ -94,7 +94,7 @@ def main():
             continue
         cands = [k for k, v in funcs.items() if len(v) == len(b)]
         # prefer the instantiation whose mangled name shares the template argument
-        key = next((k for k in cands if re.search(r"<\(int\)(\d+)>", name) and ("ILi%sE" % re.search(r"<\(int\)(\d+)>", name).group(1)) in k and "warp" in k), cands[0] if cands else None)
+        key = next((k for k in cands if re.search(r"<\(int\)(\d+)>", name) and ("ILi%sE" % re.search(r"<\(int\)(\d+)>", name).group(1)) in k and want.split("_")[-1] in k), cands[0] if cands else None)
         if key is None:
             print("   (could not match SASS to the in-tree cubin: rebuild differs from the profiled binary)")
             continue

@@ -413,157 +413,6 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
 }
 
 // ------------------------------------------------------------------------------------------
-// thread per unit (shallow columns): the lanes of a warp work on 32 different units.
-//
-// A warp-per-unit kernel pays every divergent path of the read evaluation once per warp call and
-// ~400 warp-collective instructions of ranking per unit.  Here a thread walks its own unit's
-// candidates in three passes -- (1) reads whose CIGAR is a single match and that have no overlap
-// partner: the short common path, (2) simple reads with a partner, (3) reads with a general CIGAR --
-// so the long paths run only as many iterations as the unit with the most such reads needs.  The
-// contributing values go to a per-thread list in shared memory (transposed: entry k of thread t at
-// [k][t], conflict free); medians and mid-rank sums come from three in-place insertion sorts.
-// Units with more than 64 candidates or more than T_CAP contributing values go to the deep list.
-// ------------------------------------------------------------------------------------------
-constexpr int T_THREADS = 128;
-constexpr int T_CAP = 48;
-
-__device__ __forceinline__ void t_append(uint32_t *list, int &n, const Contribution &c, bool &overflow) {
-    if (!(c.ref || c.alt)) return;
-    const uint32_t w = pack(c);
-    for (uint32_t k = 0; k < (c.alt > 1u ? c.alt : 1u); ++k) {
-        if (n >= T_CAP) { overflow = true; return; }
-        list[n * T_THREADS] = k == 0 ? w : (w & ~PK_REF);
-        ++n;
-    }
-}
-
-// in-place insertion sort of list[0..n) by bit field (shift, mask), then one scan:
-// medians of the REF / ALT members and twice the ALT mid-rank sum
-__device__ __forceinline__ void t_metric(uint32_t *list, int n, int shift, uint32_t mask, int n_ref, int n_alt, int &med2_ref,
-                                         int &med2_alt, uint64_t &s2) {
-    for (int a = 1; a < n; ++a) {
-        const uint32_t w = list[a * T_THREADS];
-        const uint32_t key = (w >> shift) & mask;
-        int b = a - 1;
-        while (b >= 0) {
-            const uint32_t x = list[b * T_THREADS];
-            if (((x >> shift) & mask) <= key) break;
-            list[(b + 1) * T_THREADS] = x;
-            --b;
-        }
-        list[(b + 1) * T_THREADS] = w;
-    }
-    const int r1 = (n_ref - 1) >> 1, r2 = n_ref >> 1, a1 = (n_alt - 1) >> 1, a2 = n_alt >> 1;
-    int seen_ref = 0, seen_alt = 0, vr1 = 0, vr2 = 0, va1 = 0, va2 = 0;
-    uint64_t acc = 0;
-    int a = 0;
-    while (a < n) {  // one group of equal values at a time
-        const uint32_t key = (list[a * T_THREADS] >> shift) & mask;
-        int g_ref = 0, g_alt = 0, b = a;
-        while (b < n) {
-            const uint32_t x = list[b * T_THREADS];
-            if (((x >> shift) & mask) != key) break;
-            g_ref += (x & PK_REF) ? 1 : 0;
-            g_alt += (x & PK_ALT) ? 1 : 0;
-            ++b;
-        }
-        acc += (uint64_t)g_alt * (uint64_t)(2 * (seen_ref + seen_alt) + g_ref + g_alt + 1);
-        if (r1 >= seen_ref && r1 < seen_ref + g_ref) vr1 = (int)key;
-        if (r2 >= seen_ref && r2 < seen_ref + g_ref) vr2 = (int)key;
-        if (a1 >= seen_alt && a1 < seen_alt + g_alt) va1 = (int)key;
-        if (a2 >= seen_alt && a2 < seen_alt + g_alt) va2 = (int)key;
-        seen_ref += g_ref;
-        seen_alt += g_alt;
-        a = b;
-    }
-    med2_ref = n_ref ? vr1 + vr2 : -1;
-    med2_alt = n_alt ? va1 + va2 : -1;
-    s2 = (n_ref && n_alt) ? acc : 0ull;
-}
-
-template <int POSB>
-__global__ void __launch_bounds__(T_THREADS, 8)
-pileup_thread_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_units, const uint8_t *__restrict__ ins_seq,
-                     vfk_params P, vfk_counts *__restrict__ out, uint32_t *__restrict__ block_list, uint32_t *__restrict__ n_block,
-                     uint32_t *__restrict__ warp_list, uint32_t *__restrict__ n_warp) {
-    __shared__ uint32_t lists[T_CAP * T_THREADS];
-    const int64_t u = (int64_t)blockIdx.x * T_THREADS + threadIdx.x;
-    if (u >= n_units) return;
-    uint32_t *list = lists + threadIdx.x;
-    Unit U;
-    {
-        const uint4 *q = reinterpret_cast<const uint4 *>(res + u);
-        const uint4 a = __ldg(q), b = __ldg(q + 1);
-        ResolvedUnit ru;
-        ru.col = (int32_t)a.x; ru.meta = a.y; ru.len = (int32_t)a.z; ru.ins_off = a.w;
-        ru.lo = b.x; ru.hi = b.y; ru.stop = (int32_t)b.z; ru.c1 = b.w;
-        unit_from(ru, ins_seq, U);
-    }
-    const int n_cand = (int)(U.hi - U.lo);
-    int med2[3][2] = {{-1, -1}, {-1, -1}, {-1, -1}};
-    uint64_t s2[3] = {0, 0, 0};
-    if (n_cand == 0) {
-        store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind, 0u, 0u);
-        return;
-    }
-    if (n_cand > 64) {
-        if (n_cand > WARP_PATH_MAX_CAND) block_list[atomicAdd(n_block, 1u)] = (uint32_t)u;
-        else warp_list[atomicAdd(n_warp, 1u)] = (uint32_t)u;
-        store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind | VFK_ST_DEFERRED, (uint32_t)n_cand, 0u);
-        return;
-    }
-    int n = 0, dp = 0, n_amb = 0, n_cover = 0, n_col = 0, ac_ref = 0, ac_alt = 0;
-    bool overflow = false;
-    unsigned long long linked = 0ull, general = 0ull;
-    // pass 1: single-match reads without an overlap partner; everything else is only classified
-    for (int k = 0; k < n_cand; ++k) {
-        const int64_t i = U.lo + k;
-        const uint4 hot = __ldg(R.hot + i);
-        if (U.col < (int32_t)hot.x || U.col >= (int32_t)hot.x + (int32_t)hot.y) continue;
-        if ((hot.z >> 24) != 0u) { general |= 1ull << k; continue; }
-        const uint32_t flag = hot.z & 0xFFFFu;
-        if (P.ignore_overlaps && (flag & F_PROPER) && !(flag & F_MUNMAP) && __ldg(R.mate + i) != VFK_NO_MATE) {
-            linked |= 1ull << k;
-            continue;
-        }
-        const Contribution c = evaluate<true, true>(R, P, U, i, hot, VFK_NO_MATE);
-        n_cover += c.covers; n_col += c.in_col; dp += c.in_dp; n_amb += c.ambiguous; ac_ref += c.ref; ac_alt += (int)c.alt;
-        t_append(list, n, c, overflow);
-    }
-    // pass 2: single-match reads with an overlap partner (mate-overlap quality adjustment)
-    while (linked) {
-        const int k = __ffsll((long long)linked) - 1;
-        linked &= linked - 1;
-        const int64_t i = U.lo + k;
-        const Contribution c = evaluate<true, false>(R, P, U, i, __ldg(R.hot + i), __ldg(R.mate + i));
-        n_cover += c.covers; n_col += c.in_col; dp += c.in_dp; n_amb += c.ambiguous; ac_ref += c.ref; ac_alt += (int)c.alt;
-        t_append(list, n, c, overflow);
-    }
-    // pass 3: reads with a general CIGAR
-    while (general) {
-        const int k = __ffsll((long long)general) - 1;
-        general &= general - 1;
-        const int64_t i = U.lo + k;
-        const Contribution c = evaluate<false, false>(R, P, U, i, __ldg(R.hot + i), __ldg(R.mate + i));
-        n_cover += c.covers; n_col += c.in_col; dp += c.in_dp; n_amb += c.ambiguous; ac_ref += c.ref; ac_alt += (int)c.alt;
-        if (c.qpos >= POSB && (c.ref || c.alt)) overflow = true;
-        t_append(list, n, c, overflow);
-    }
-    if (overflow) {  // too many contributing values for the per-thread list: redone by the histogram kernel
-        warp_list[atomicAdd(n_warp, 1u)] = (uint32_t)u;
-        store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind | VFK_ST_DEFERRED, (uint32_t)n_cand, 0u);
-        return;
-    }
-    if (n > 0) {
-        t_metric(list, n, 0, 0xFFu, ac_ref, ac_alt, med2[0][0], med2[0][1], s2[0]);
-        if (U.kind == VFK_KIND_SNV) t_metric(list, n, 8, 0xFFu, ac_ref, ac_alt, med2[1][0], med2[1][1], s2[1]);
-        t_metric(list, n, 16, 0xFFFu, ac_ref, ac_alt, med2[2][0], med2[2][1], s2[2]);
-    }
-    if (U.kind == VFK_KIND_SNV && !P.include_ambiguous) dp -= n_amb;  // pileups.py:224-227
-    store_counts(out + u, dp, n_amb, ac_ref, ac_alt, med2, s2, U.kind, (uint32_t)n_cand, (uint32_t)n_cover, (uint32_t)n_col);
-}
-
-// ------------------------------------------------------------------------------------------
 // warp per listed unit, shared-memory histograms
 // ------------------------------------------------------------------------------------------
 template <int POSB>
@@ -705,13 +554,8 @@ static cudaError_t launch_posb(const ReadsDev &R, const UnitsDev &V, const vfk_p
     if (want < grid) grid = want < 1 ? 1 : want;
     e = cudaMemsetAsync(counters, 0, 24, stream);
     if (e != cudaSuccess) return e;
-    static const int variant = [] { const char *v = getenv("VFK_SHALLOW_KERNEL"); return (v && v[0] == 'w') ? 0 : 1; }();
-    if (variant == 1)  // thread per unit (default); VFK_SHALLOW_KERNEL=warp selects the warp-per-unit kernel
-        pileup_thread_kernel<POSB><<<(unsigned)((V.n + T_THREADS - 1) / T_THREADS), T_THREADS, 0, stream>>>(
-            R, res, V.n, V.ins_seq, P, out, block_list, n_block, warp_list, n_warp);
-    else
-        pileup_warp_kernel<POSB><<<(unsigned)grid, WARPS_PER_CTA * 32, 0, stream>>>(R, res, V.n, V.ins_seq, P, out, work, block_list,
-                                                                                    n_block, warp_list, n_warp);
+    pileup_warp_kernel<POSB><<<(unsigned)grid, WARPS_PER_CTA * 32, 0, stream>>>(R, res, V.n, V.ins_seq, P, out, work, block_list,
+                                                                                n_block, warp_list, n_warp);
     ++*launches;
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
