@@ -218,28 +218,30 @@ __device__ __forceinline__ void radix_compare(uint32_t v, uint32_t contributing,
     }
 }
 
-// medians of the REF / ALT lists and the ALT mid-rank sum, from the lt / eq masks
+// medians of the REF / ALT lists and the ALT mid-rank sum, from the lt / eq masks.
+// The order statistic k of a list is held by every lane whose [below, below + ties) interval contains
+// k -- all of them carry the same value, so an OR reduction returns it; the (up to) four order
+// statistics of a metric travel in one word (FIELD bits each) and one REDUX.
+struct SlotShape {  // metric independent
+    int nr, na, r1, r2, a1, a2;
+};
+template <int FIELD>
 __device__ __forceinline__ void radix_finish(uint32_t v, uint32_t R, uint32_t A, bool is_ref, bool is_alt, uint32_t lt,
-                                             uint32_t eq, int &med2_ref, int &med2_alt, uint64_t &s2) {
-    const int nr = __popc(R), na = __popc(A);
+                                             uint32_t eq, const SlotShape &sh, int &med2_ref, int &med2_alt, uint64_t &s2) {
+    const int br = __popc(lt & R), tr = __popc(eq & R), ba = __popc(lt & A), ta = __popc(eq & A);
     // the pooled sample is the concatenation of both lists: a lane in both counts twice
-    const int below = __popc(lt & R) + __popc(lt & A), ties = __popc(eq & R) + __popc(eq & A);
-    s2 = (nr && na) ? (uint64_t)__reduce_add_sync(FULL, is_alt ? (unsigned)(2 * below + ties + 1) : 0u) : 0ull;
-    if (nr) {
-        const int br = __popc(lt & R), tr = __popc(eq & R), k1 = (nr - 1) >> 1, k2 = nr >> 1;
-        const int v1 = __reduce_max_sync(FULL, (is_ref && br <= k1 && k1 < br + tr) ? (int)v : -1);
-        const int v2 = __reduce_max_sync(FULL, (is_ref && br <= k2 && k2 < br + tr) ? (int)v : -1);
-        med2_ref = v1 + v2;
+    s2 = (sh.nr && sh.na) ? (uint64_t)__reduce_add_sync(FULL, is_alt ? (unsigned)(2 * (br + ba) + tr + ta + 1) : 0u) : 0ull;
+    const bool h_r1 = is_ref && br <= sh.r1 && sh.r1 < br + tr, h_r2 = is_ref && br <= sh.r2 && sh.r2 < br + tr;
+    const bool h_a1 = is_alt && ba <= sh.a1 && sh.a1 < ba + ta, h_a2 = is_alt && ba <= sh.a2 && sh.a2 < ba + ta;
+    if (FIELD <= 8) {
+        const uint32_t w = __reduce_or_sync(FULL, (h_r1 ? v : 0u) | (h_r2 ? v << 8 : 0u) | (h_a1 ? v << 16 : 0u) | (h_a2 ? v << 24 : 0u));
+        med2_ref = sh.nr ? (int)((w & 0xFFu) + ((w >> 8) & 0xFFu)) : -1;
+        med2_alt = sh.na ? (int)(((w >> 16) & 0xFFu) + (w >> 24)) : -1;
     } else {
-        med2_ref = -1;
-    }
-    if (na) {
-        const int ba = __popc(lt & A), ta = __popc(eq & A), k1 = (na - 1) >> 1, k2 = na >> 1;
-        const int v1 = __reduce_max_sync(FULL, (is_alt && ba <= k1 && k1 < ba + ta) ? (int)v : -1);
-        const int v2 = __reduce_max_sync(FULL, (is_alt && ba <= k2 && k2 < ba + ta) ? (int)v : -1);
-        med2_alt = v1 + v2;
-    } else {
-        med2_alt = -1;
+        const uint32_t wr = __reduce_or_sync(FULL, (h_r1 ? v : 0u) | (h_r2 ? v << 16 : 0u));
+        const uint32_t wa = __reduce_or_sync(FULL, (h_a1 ? v : 0u) | (h_a2 ? v << 16 : 0u));
+        med2_ref = sh.nr ? (int)((wr & 0xFFFFu) + (wr >> 16)) : -1;
+        med2_alt = sh.na ? (int)((wa & 0xFFFFu) + (wa >> 16)) : -1;
     }
 }
 
@@ -367,7 +369,8 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
             if (n_cand > 32 && lane + 32 < n_cand) c1 = evaluate(R, P, U, U.lo + 32 + lane);
             const bool k0 = c0.ref || c0.alt, k1 = c1.ref || c1.alt;
             const uint32_t m0 = __ballot_sync(FULL, k0), m1 = __ballot_sync(FULL, k1);
-            const bool heavy = __any_sync(FULL, c0.alt > 1u || c1.alt > 1u || c0.qpos >= POSB || c1.qpos >= POSB);
+            // a read can support an insertion more than once (pileups.py:267-290): such units take the deep path
+            const bool heavy = U.kind == VFK_KIND_INS && __any_sync(FULL, c0.alt > 1u || c1.alt > 1u);
             if (heavy || __popc(m0) + __popc(m1) > 32) {  // rare: re-done through the histograms
                 if (lane == 0) {
                     warp_list[atomicAdd(n_warp, 1u)] = (uint32_t)u;
@@ -375,10 +378,13 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
                 }
                 continue;
             }
-            int dp = __popc(__ballot_sync(FULL, c0.in_dp)) + __popc(__ballot_sync(FULL, c1.in_dp));
-            const int n_amb = __popc(__ballot_sync(FULL, c0.ambiguous)) + __popc(__ballot_sync(FULL, c1.ambiguous));
-            const int n_cover = __popc(__ballot_sync(FULL, c0.covers)) + __popc(__ballot_sync(FULL, c1.covers));
-            const int n_col = __popc(__ballot_sync(FULL, c0.in_col)) + __popc(__ballot_sync(FULL, c1.in_col));
+            // four counters (each <= 64) in the byte lanes of one word, one reduction
+            const uint32_t tally = __reduce_add_sync(FULL, ((uint32_t)c0.in_dp + (uint32_t)c1.in_dp) |
+                                                               (((uint32_t)c0.ambiguous + (uint32_t)c1.ambiguous) << 8) |
+                                                               (((uint32_t)c0.covers + (uint32_t)c1.covers) << 16) |
+                                                               (((uint32_t)c0.in_col + (uint32_t)c1.in_col) << 24));
+            int dp = (int)(tally & 0xFFu);
+            const int n_amb = (int)((tally >> 8) & 0xFFu), n_cover = (int)((tally >> 16) & 0xFFu), n_col = (int)(tally >> 24);
             uint32_t pk = k0 ? pack(c0) : 0u;
             if (m1) {  // move the second chunk's contributions into lanes the first one left free
                 const int n1 = __popc(m1);
@@ -396,14 +402,17 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
             if (Rm | Am) {
                 uint32_t lt, eq;
                 const uint32_t mq = pk & 0xFFu, bq = (pk >> 8) & 0xFFu, qp = (pk >> 16) & 0xFFFu;
+                SlotShape sh;
+                sh.nr = ac_ref; sh.na = ac_alt;
+                sh.r1 = (ac_ref - 1) >> 1; sh.r2 = ac_ref >> 1; sh.a1 = (ac_alt - 1) >> 1; sh.a2 = ac_alt >> 1;
                 radix_compare<8>(mq, Rm | Am, lt, eq);
-                radix_finish(mq, Rm, Am, is_ref, is_alt, lt, eq, med2[0][0], med2[0][1], s2[0]);
+                radix_finish<8>(mq, Rm, Am, is_ref, is_alt, lt, eq, sh, med2[0][0], med2[0][1], s2[0]);
                 if (U.kind == VFK_KIND_SNV) {
                     radix_compare<8>(bq, Rm | Am, lt, eq);
-                    radix_finish(bq, Rm, Am, is_ref, is_alt, lt, eq, med2[1][0], med2[1][1], s2[1]);
+                    radix_finish<8>(bq, Rm, Am, is_ref, is_alt, lt, eq, sh, med2[1][0], med2[1][1], s2[1]);
                 }
                 radix_compare<L::POS_BITS>(qp, Rm | Am, lt, eq);
-                radix_finish(qp, Rm, Am, is_ref, is_alt, lt, eq, med2[2][0], med2[2][1], s2[2]);
+                radix_finish<L::POS_BITS>(qp, Rm, Am, is_ref, is_alt, lt, eq, sh, med2[2][0], med2[2][1], s2[2]);
             }
             if (U.kind == VFK_KIND_SNV && !P.include_ambiguous) dp -= n_amb;  // pileups.py:224-227
             if (lane == 0) store_counts(out + u, dp, n_amb, ac_ref, ac_alt, med2, s2, U.kind, (uint32_t)n_cand, (uint32_t)n_cover,
