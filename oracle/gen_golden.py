@@ -289,6 +289,73 @@ def random_scenario(seed, n_bams=1, n_pairs=260, read_len=60, G=1500, replicates
                 samples=samples, purities=purities, ploidies=ploidies)
 
 
+def testx_scenario():
+    """REAL alignments: the two BAMs the reference ships (vafator/tests/resources/TESTX_S1_L00{1,2}.bam;
+    bwa, 101 bp, proper pairs / orphans / soft clips / indels, MAPQ 0-60), decoded with the product's
+    BAM decoder (the container format is not what is under test here).  Read names are replaced by
+    surrogates that preserve which records share a name.  Variants: SNVs at covered positions and the
+    insertions / deletions the reads themselves carry."""
+    from vafator_b200 import bamio
+    res = os.path.join(REF_ROOT, "vafator", "tests", "resources")
+    bams, contigs, seen = [], None, {}
+    for name in ("TESTX_S1_L001.bam", "TESTX_S1_L002.bam"):
+        f = bamio.BamFile(os.path.join(res, name))
+        contigs = f.contigs
+        b = f.read_batch()
+        recs = hp.recs_from_soa(b.as_dict())
+        out = []
+        for r in recs:
+            out.append(rec_dict("q%016x" % int(r.name_key[0]), r.flag, r.tid, r.pos, r.mapq,
+                                "".join("%d%s" % (l, hp.CIGAR_CHARS[op]) for op, l in r.cigar) or "0M", r.seq, list(r.qual),
+                                r.mtid, r.mpos, r.isize))
+            if r.flag & 4:
+                out[-1]["cigar"] = ""
+        bams.append(out)
+    rng = random.Random(5)
+    variants = {}
+    for recs in bams:
+        for r in recs:
+            if r["flag"] & 4 or not r["cigar"]:
+                continue
+            ref_pos, q = r["pos"], 0
+            ops = hp.parse_cigar(r["cigar"])
+            for k, (op, l) in enumerate(ops):
+                if op in (0, 7, 8):
+                    if rng.random() < 0.12:
+                        off = rng.randrange(l)
+                        base = r["seq"][q + off]
+                        if base in "ACGT":
+                            alt = rng.choice([x for x in "ACGT" if x != base])
+                            variants.setdefault((r["tid"], ref_pos + off + 1, base), [alt])
+                    ref_pos += l
+                    q += l
+                elif op == 1:
+                    if q > 0 and k > 0 and ops[k - 1][0] in (0, 7, 8):
+                        anchor = r["seq"][q - 1]
+                        variants.setdefault((r["tid"], ref_pos, anchor), [anchor + r["seq"][q:q + l]])
+                        variants.setdefault((r["tid"], ref_pos, anchor + "~"), [anchor + r["seq"][q + l:q + 2 * l]])
+                    q += l
+                elif op == 2:
+                    if q > 0 and k > 0 and ops[k - 1][0] in (0, 7, 8):
+                        anchor = r["seq"][q - 1]
+                        variants.setdefault((r["tid"], ref_pos, anchor + "N" * l), [anchor])
+                    ref_pos += l
+                elif op == 3:
+                    ref_pos += l
+                elif op == 4:
+                    q += l
+    V = []
+    for (tid, pos1, ref), alts in variants.items():
+        alts = [a for a in alts if len(a) >= 1]
+        V.append((tid, pos1, ref.replace("~", ""), alts))
+    V = [v for v in V if len(v[2]) >= 1 and all(len(a) > 0 and a != v[2] for a in v[3]) and len(v[3][0]) != 0]
+    V = [v for v in V if not (len(v[2]) == 1 and len(v[3][0]) == 1 and v[2] == v[3][0])]
+    V.sort(key=lambda v: (v[0], v[1], v[2]))
+    return dict(name="testx_real", contigs=contigs, bams=bams,
+                variants=[dict(chrom=contigs[t], pos=p, ref=r, alts=a) for t, p, r, a in V],
+                samples=OrderedDict([("tumor", [0]), ("normal", [1])]), purities={"tumor": 0.6}, ploidies={"tumor": 3.0})
+
+
 # ---------------------------------------------------------------------------
 # run the reference on a scenario
 # ---------------------------------------------------------------------------
@@ -362,6 +429,8 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
     scenarios = [handmade(), random_scenario(11), random_scenario(12, n_bams=2),
                  random_scenario(13, n_bams=3, replicates=True), random_scenario(14, n_pairs=900, read_len=40, G=700)]
+    if os.path.exists(os.path.join(REF_ROOT, "vafator", "tests", "resources", "TESTX_S1_L001.bam")):
+        scenarios.append(testx_scenario())
     for sc in scenarios:
         sc["runs"] = [run_reference(sc, p, mods) for p in PARAM_SETS]
         path = os.path.join(out_dir, "pileup_%s.json" % sc["name"])
