@@ -248,9 +248,17 @@ __device__ __forceinline__ void radix_finish(uint32_t v, uint32_t R, uint32_t A,
 // ------------------------------------------------------------------------------------------
 // deep path of the warp kernel: shared-memory histograms
 // ------------------------------------------------------------------------------------------
-template <int POSB>
+// Per-warp staging ring of the deep kernel: two stages of 32 read headers, filled by bulk async
+// copies (one elected lane issues them) and consumed from shared memory.
+struct StageRing {
+    uint4 *hot;       // [2][32]
+    uint64_t *bar;    // [2]
+    uint32_t parity;  // bit s = phase the next wait on stage s expects
+};
+
+template <int POSB, bool STAGED>
 __device__ __forceinline__ void unit_by_histogram(const ReadsDev &R, const vfk_params &P, const Unit &U, uint32_t *ref_slot,
-                                               uint32_t *alt_slot, int lane, vfk_counts *out) {
+                                               uint32_t *alt_slot, int lane, vfk_counts *out, StageRing *ring = nullptr) {
     using L = Layout<POSB>;
     constexpr int WORDS = L::BINS / 2;
     {
@@ -261,17 +269,55 @@ __device__ __forceinline__ void unit_by_histogram(const ReadsDev &R, const vfk_p
     int dp = 0, n_amb = 0, ac_ref = 0, ac_alt = 0, n_cover = 0, n_col = 0;
     uint32_t status = U.kind;
     const bool with_bq = U.kind == VFK_KIND_SNV;
-    for (int64_t b = U.lo; b < U.hi; b += 32) {
-        const int64_t i = b + lane;
-        if (i < U.hi) {
-            const Contribution c = evaluate(R, P, U, i);
-            n_cover += c.covers ? 1 : 0;
-            n_col += c.in_col ? 1 : 0;
-            dp += c.in_dp ? 1 : 0;
-            n_amb += c.ambiguous ? 1 : 0;
-            ac_ref += c.ref ? 1 : 0;
-            ac_alt += (int)c.alt;
-            accumulate<uint16_t, POSB>(ref_slot, alt_slot, c, with_bq, status);
+    if (STAGED) {
+        // chunk c of 32 candidates lives in stage c & 1; chunk c+1 is in flight while c is evaluated
+        const int64_t n_cand = U.hi - U.lo;
+        const int n_chunks = (int)((n_cand + 31) >> 5);
+        auto issue = [&](int c) {
+            const int s = c & 1;
+            const int64_t first = U.lo + ((int64_t)c << 5);
+            const uint32_t bytes = (uint32_t)min((int64_t)32, U.hi - first) * 16u;
+            if (lane == 0) {
+                mbar_expect_tx(ring->bar + s, bytes);
+                bulk_copy_g2s(ring->hot + s * 32, R.hot + first, bytes, ring->bar + s);
+            }
+        };
+        issue(0);
+        uint32_t mw_next = (U.lo + lane < U.hi) ? __ldg(R.mate + U.lo + lane) : VFK_NO_MATE;
+        for (int c = 0; c < n_chunks; ++c) {
+            const int s = c & 1;
+            const int64_t i = U.lo + ((int64_t)c << 5) + lane;
+            if (c + 1 < n_chunks) issue(c + 1);
+            const uint32_t mw = mw_next;
+            if (c + 1 < n_chunks && i + 32 < U.hi) mw_next = __ldg(R.mate + i + 32);
+            mbar_wait(ring->bar + s, (ring->parity >> s) & 1u);
+            ring->parity ^= 1u << s;
+            if (i < U.hi) {
+                const uint4 hot = ring->hot[s * 32 + lane];
+                const Contribution c1 = evaluate<false, false>(R, P, U, i, hot, mw);
+                n_cover += c1.covers ? 1 : 0;
+                n_col += c1.in_col ? 1 : 0;
+                dp += c1.in_dp ? 1 : 0;
+                n_amb += c1.ambiguous ? 1 : 0;
+                ac_ref += c1.ref ? 1 : 0;
+                ac_alt += (int)c1.alt;
+                accumulate<uint16_t, POSB>(ref_slot, alt_slot, c1, with_bq, status);
+            }
+            __syncwarp();  // every lane has consumed stage s before it is refilled two chunks later
+        }
+    } else {
+        for (int64_t b = U.lo; b < U.hi; b += 32) {
+            const int64_t i = b + lane;
+            if (i < U.hi) {
+                const Contribution c = evaluate(R, P, U, i);
+                n_cover += c.covers ? 1 : 0;
+                n_col += c.in_col ? 1 : 0;
+                dp += c.in_dp ? 1 : 0;
+                n_amb += c.ambiguous ? 1 : 0;
+                ac_ref += c.ref ? 1 : 0;
+                ac_alt += (int)c.alt;
+                accumulate<uint16_t, POSB>(ref_slot, alt_slot, c, with_bq, status);
+            }
         }
     }
     __syncwarp();
@@ -435,6 +481,18 @@ pileup_deep_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, const uint8
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *ref_slot = smem + (size_t)warp * 2 * WORDS;
     uint32_t *alt_slot = ref_slot + WORDS;
+    __shared__ __align__(128) uint4 s_hot[WARPS_PER_CTA][2][32];
+    __shared__ __align__(8) uint64_t s_bar[WARPS_PER_CTA][2];
+    StageRing ring;
+    ring.hot = &s_hot[warp][0][0];
+    ring.bar = &s_bar[warp][0];
+    ring.parity = 0u;
+    if (lane == 0) {
+        mbar_init(ring.bar + 0, 1);
+        mbar_init(ring.bar + 1, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
     const uint32_t n = *n_warp;
     for (;;) {
         uint32_t k = 0;
@@ -444,7 +502,7 @@ pileup_deep_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, const uint8
         const int64_t u = warp_list[k];
         Unit U;
         unit_from(res[u], ins_seq, U);
-        unit_by_histogram<POSB>(R, P, U, ref_slot, alt_slot, lane, out + u);
+        unit_by_histogram<POSB, true>(R, P, U, ref_slot, alt_slot, lane, out + u, &ring);
     }
 }
 
