@@ -13,20 +13,30 @@
 
 namespace vfk {
 
-__device__ __forceinline__ double log_binom_pmf(int64_t k, int64_t n, double logp, double log1mp) {
-    return lgamma((double)n + 1.0) - lgamma((double)k + 1.0) - lgamma((double)(n - k) + 1.0) + (double)k * logp +
-           (double)(n - k) * log1mp;
+// log(k!) for k <= 20 exactly as lgamma(k + 1) returns it (integers up to 20! are exact doubles)
+__device__ __forceinline__ double log_factorial(int64_t k) {
+    if (k <= 20) {
+        double f = 1.0;
+        for (int64_t j = 2; j <= k; ++j) f *= (double)j;
+        return log(f);
+    }
+    return lgamma((double)k + 1.0);
+}
+
+// every thread evaluates several binomial terms for the same n (its depth): log(n!) is computed once
+__device__ __forceinline__ double log_binom_pmf(int64_t k, int64_t n, double logp, double log1mp, double lg_n1) {
+    return lg_n1 - log_factorial(k) - log_factorial(n - k) + (double)k * logp + (double)(n - k) * log1mp;
 }
 
 __device__ bool dyadic_binom(int64_t k, int64_t n, double p, bool want_cdf, double &out);
 
-__device__ double binom_pmf(int64_t k, int64_t n, double p) {
+__device__ double binom_pmf(int64_t k, int64_t n, double p, double lg_n1) {
     double exact;
     if (dyadic_binom(k, n, p, false, exact)) return exact;
     if (k < 0 || k > n) return 0.0;
     if (p <= 0.0) return k == 0 ? 1.0 : 0.0;
     if (p >= 1.0) return k == n ? 1.0 : 0.0;
-    return exp(log_binom_pmf(k, n, log(p), log1p(-p)));
+    return exp(log_binom_pmf(k, n, log(p), log1p(-p), lg_n1));
 }
 
 // Exact evaluation when p = a / 2^b and the numerators fit in 64 bits (b * n <= 62): the result is
@@ -58,7 +68,7 @@ __device__ bool dyadic_binom(int64_t k, int64_t n, double p, bool want_cdf, doub
 
 // lower tail P[X <= k] by direct summation of the probability mass, starting from the largest
 // term of the tail that is summed so that every further term is smaller (no cancellation).
-__device__ double binom_cdf(int64_t k, int64_t n, double p) {
+__device__ double binom_cdf(int64_t k, int64_t n, double p, double lg_n1) {
     double exact;
     if (dyadic_binom(k, n, p, true, exact)) return exact;
     if (k < 0) return 0.0;
@@ -69,7 +79,7 @@ __device__ double binom_cdf(int64_t k, int64_t n, double p) {
     const double odds = p / (1.0 - p);
     if ((double)k < (double)(n + 1) * p) {
         // k below the mode: sum k, k-1, ... downwards
-        double term = exp(log_binom_pmf(k, n, logp, log1mp));
+        double term = exp(log_binom_pmf(k, n, logp, log1mp, lg_n1));
         double sum = term;
         for (int64_t i = k; i > 0; --i) {
             term *= ((double)i / (double)(n - i + 1)) / odds;
@@ -79,7 +89,7 @@ __device__ double binom_cdf(int64_t k, int64_t n, double p) {
         return sum;
     }
     // upper tail k+1, k+2, ... then complement
-    double term = exp(log_binom_pmf(k + 1, n, logp, log1mp));
+    double term = exp(log_binom_pmf(k + 1, n, logp, log1mp, lg_n1));
     double sum = term;
     for (int64_t i = k + 1; i < n; ++i) {
         term *= ((double)(n - i) / (double)(i + 1)) * odds;
@@ -90,8 +100,8 @@ __device__ double binom_cdf(int64_t k, int64_t n, double p) {
 }
 
 // vafator/power.py:84-93 -- P(m, n) = 1 - binom.cdf(m-1, n, err/3), 1 when m < 1
-__device__ __forceinline__ double carter_p(int64_t m, int64_t n, double e3) {
-    return m >= 1 ? 1.0 - binom_cdf(m - 1, n, e3) : 1.0;
+__device__ __forceinline__ double carter_p(int64_t m, int64_t n, double e3, double lg_n1) {
+    return m >= 1 ? 1.0 - binom_cdf(m - 1, n, e3, lg_n1) : 1.0;
 }
 
 __global__ void __launch_bounds__(128)
@@ -121,18 +131,19 @@ epilogue_kernel(int64_t n_units, const vfk_counts *__restrict__ counts, const do
     }
     const int64_t dp = c.dp;
     const double f = eaf[u];
-    s.pu = binom_cdf(c.ac_alt, dp, f);
+    const double lg_n1 = log_factorial(dp);
+    s.pu = binom_cdf(c.ac_alt, dp, f, lg_n1);
     // k = min{k >= 1 : P(k, dp) <= fpr}   (vafator/power.py:106-114)
     const double e3 = error_rate / 3.0;
     int64_t k = 1;
-    double pk = carter_p(1, dp, e3), pk_1 = 1.0;
+    double pk = carter_p(1, dp, e3, lg_n1), pk_1 = 1.0;
     while (pk > fpr) {
         ++k;
         pk_1 = pk;
-        pk = carter_p(k, dp, e3);
+        pk = carter_p(k, dp, e3, lg_n1);
     }
     const double d = (fpr - pk) / (pk_1 - pk);
-    s.pw = 1.0 - binom_cdf(k - 1, dp, f) + d * binom_pmf(k, dp, f);
+    s.pw = 1.0 - binom_cdf(k - 1, dp, f, lg_n1) + d * binom_pmf(k, dp, f, lg_n1);
     s.k = (int32_t)k;
     s.pad = 0;
     out[u] = s;
