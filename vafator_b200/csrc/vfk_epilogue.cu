@@ -13,15 +13,9 @@
 
 namespace vfk {
 
-// log(k!) for k <= 20 exactly as lgamma(k + 1) returns it (integers up to 20! are exact doubles)
-__device__ __forceinline__ double log_factorial(int64_t k) {
-    if (k <= 20) {
-        double f = 1.0;
-        for (int64_t j = 2; j <= k; ++j) f *= (double)j;
-        return log(f);
-    }
-    return lgamma((double)k + 1.0);
-}
+// log(k!) -- a table for k <= 20 (20! is the largest factorial that is an exact double), lgamma beyond
+__constant__ double LOG_FACTORIAL[21] = {0.0, 0.0, 0.6931471805599453, 1.791759469228055, 3.1780538303479458, 4.787491742782046, 6.579251212010101, 8.525161361065415, 10.60460290274525, 12.801827480081469, 15.104412573075516, 17.502307845873887, 19.987214495661885, 22.552163853123425, 25.19122118273868, 27.89927138384089, 30.671860106080672, 33.50507345013689, 36.39544520803305, 39.339884187199495, 42.335616460753485};
+__device__ __forceinline__ double log_factorial(int64_t k) { return k <= 20 ? LOG_FACTORIAL[k] : lgamma((double)k + 1.0); }
 
 // every thread evaluates several binomial terms for the same n (its depth): log(n!) is computed once
 __device__ __forceinline__ double log_binom_pmf(int64_t k, int64_t n, double logp, double log1mp, double lg_n1) {
