@@ -17,7 +17,9 @@ cudaError_t launch_pileup_resolved(const ReadsDev &R, const UnitsDev &V, const v
                                    void *resolved, void *counters, uint32_t *lists, int sm_count, cudaStream_t stream,
                                    int *launches);
 cudaError_t launch_epilogue(int64_t n_units, const vfk_counts *counts, const double *eaf, double fpr, double error_rate,
-                            vfk_stats *out, cudaStream_t stream, int *launches);
+                            const void *table, int32_t n_table, vfk_stats *out, cudaStream_t stream, int *launches);
+cudaError_t launch_carter_table(int32_t n_table, double fpr, double error_rate, void *table, cudaStream_t stream, int *launches);
+size_t carter_entry_size();
 cudaError_t launch_values(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, int32_t max_per_unit, uint32_t *values,
                           int32_t *n_values, cudaStream_t stream, int *launches);
 cudaError_t launch_ranksum(int64_t n_pairs, const uint32_t *alt, const int64_t *alt_off, const uint32_t *ref,
@@ -88,7 +90,33 @@ struct vfk_handle {
     Slot slot[2];
     int next_slot = 0;
     int64_t zero_copy_batches = 0;
+    // Carter k / d per depth for the last (fpr, error_rate) seen, depths [0, CARTER_DEPTHS)
+    DevBuf carter;
+    double carter_fpr = -1.0, carter_err = -1.0;
+    cudaEvent_t carter_ready = nullptr;
 };
+
+static const int32_t CARTER_DEPTHS = 4096;
+
+// make sure the table matches (fpr, error_rate); work on `st` is ordered after its fill
+static int ensure_carter(vfk_handle *h, double fpr, double error_rate, cudaStream_t st) {
+    if (!h->carter_ready) CU(cudaEventCreateWithFlags(&h->carter_ready, cudaEventDisableTiming));
+    if (h->carter_fpr != fpr || h->carter_err != error_rate || !h->carter.p) {
+        CU(cudaDeviceSynchronize());  // rare: launches still reading the previous table must finish first
+        int rc = h->carter.reserve((size_t)CARTER_DEPTHS * vfk::carter_entry_size());
+        if (rc) return rc;
+        int launches = 0;
+        cudaError_t e = vfk::launch_carter_table(CARTER_DEPTHS, fpr, error_rate, h->carter.p, st, &launches);
+        h->launches += launches;
+        if (e != cudaSuccess) return fail(VFK_ECUDA, "carter table launch: %s", cudaGetErrorString(e));
+        CU(cudaEventRecord(h->carter_ready, st));
+        h->carter_fpr = fpr;
+        h->carter_err = error_rate;
+    } else {
+        CU(cudaStreamWaitEvent(st, h->carter_ready, 0));
+    }
+    return VFK_OK;
+}
 
 extern "C" int vfk_version(void) { return VFK_VERSION; }
 extern "C" const char *vfk_last_error(void) { return g_err; }
@@ -132,6 +160,8 @@ extern "C" int vfk_destroy(vfk_handle *h) {
     for (Slot &s : h->slot) s.release();
     h->deferred.release();
     h->resolved.release();
+    h->carter.release();
+    if (h->carter_ready) cudaEventDestroy(h->carter_ready);
     if (h->counters) cudaFree(h->counters);
     delete h;
     return VFK_OK;
@@ -212,8 +242,10 @@ extern "C" int vfk_epilogue(vfk_handle *h, int64_t n_units, const vfk_counts *co
     if (!(fpr >= 0.0) || !(error_rate >= 0.0)) return fail(VFK_EINVAL, "vfk_epilogue: fpr / error_rate must be >= 0");
     CU(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;  // NULL = the CUDA default stream
+    int rc = ensure_carter(h, fpr, error_rate, st);
+    if (rc) return rc;
     int launches = 0;
-    cudaError_t e = vfk::launch_epilogue(n_units, counts, eaf, fpr, error_rate, out, st, &launches);
+    cudaError_t e = vfk::launch_epilogue(n_units, counts, eaf, fpr, error_rate, h->carter.p, CARTER_DEPTHS, out, st, &launches);
     h->launches += launches;
     if (e != cudaSuccess) return fail(VFK_ECUDA, "epilogue launch: %s", cudaGetErrorString(e));
     return VFK_OK;
@@ -372,8 +404,10 @@ extern "C" int vfk_annotate_host_async(vfk_handle *h, const vfk_read_batch *read
     e = vfk::launch_pileup_resolved(R, V, *params, reads->max_l_qseq, (vfk_counts *)S.counts.p, S.resolved.p, S.counters,
                                     (uint32_t *)S.deferred.p, h->sm_count, st, &launches);
     if (e != cudaSuccess) return fail(VFK_ECUDA, "pileup launch: %s", cudaGetErrorString(e));
-    e = vfk::launch_epilogue(nu, (const vfk_counts *)S.counts.p, (const double *)S.eaf.p, fpr, error_rate, (vfk_stats *)S.stats.p,
-                             st, &launches);
+    rc = ensure_carter(h, fpr, error_rate, st);
+    if (rc) return rc;
+    e = vfk::launch_epilogue(nu, (const vfk_counts *)S.counts.p, (const double *)S.eaf.p, fpr, error_rate, h->carter.p, CARTER_DEPTHS,
+                             (vfk_stats *)S.stats.p, st, &launches);
     if (e != cudaSuccess) return fail(VFK_ECUDA, "epilogue launch: %s", cudaGetErrorString(e));
     h->launches += launches;
     CU(cudaMemcpyAsync(counts_out, S.counts.p, (size_t)nu * sizeof(vfk_counts), cudaMemcpyDeviceToHost, st));

@@ -98,9 +98,41 @@ __device__ __forceinline__ double carter_p(int64_t m, int64_t n, double e3, doub
     return m >= 1 ? 1.0 - binom_cdf(m - 1, n, e3, lg_n1) : 1.0;
 }
 
+// Carter-2012 k and d depend on the depth only (given FPR and error rate): the reference caches k per
+// depth (vafator/power.py:106-114); here a table over depths [0, n_table) is filled once per
+// (fpr, error_rate) and reused by every epilogue launch.
+struct CarterEntry {
+    double d;
+    int32_t k;
+    int32_t pad;
+};
+
+__device__ __forceinline__ CarterEntry carter_kd(int64_t dp, double fpr, double e3, double lg_n1) {
+    // k = min{k >= 1 : P(k, dp) <= fpr}   (vafator/power.py:106-114), d as in :95-104
+    int64_t k = 1;
+    double pk = carter_p(1, dp, e3, lg_n1), pk_1 = 1.0;
+    while (pk > fpr) {
+        ++k;
+        pk_1 = pk;
+        pk = carter_p(k, dp, e3, lg_n1);
+    }
+    CarterEntry e;
+    e.d = (fpr - pk) / (pk_1 - pk);
+    e.k = (int32_t)k;
+    e.pad = 0;
+    return e;
+}
+
+__global__ void __launch_bounds__(128)
+carter_table_kernel(int32_t n_table, double fpr, double error_rate, CarterEntry *__restrict__ table) {
+    const int64_t dp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (dp >= n_table) return;
+    table[dp] = carter_kd(dp, fpr, error_rate / 3.0, log_factorial(dp));
+}
+
 __global__ void __launch_bounds__(128)
 epilogue_kernel(int64_t n_units, const vfk_counts *__restrict__ counts, const double *__restrict__ eaf, double fpr,
-                double error_rate, vfk_stats *__restrict__ out) {
+                double error_rate, const CarterEntry *__restrict__ table, int32_t n_table, vfk_stats *__restrict__ out) {
     const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n_units) return;
     const vfk_counts c = counts[u];
@@ -127,28 +159,29 @@ epilogue_kernel(int64_t n_units, const vfk_counts *__restrict__ counts, const do
     const double f = eaf[u];
     const double lg_n1 = log_factorial(dp);
     s.pu = binom_cdf(c.ac_alt, dp, f, lg_n1);
-    // k = min{k >= 1 : P(k, dp) <= fpr}   (vafator/power.py:106-114)
-    const double e3 = error_rate / 3.0;
-    int64_t k = 1;
-    double pk = carter_p(1, dp, e3, lg_n1), pk_1 = 1.0;
-    while (pk > fpr) {
-        ++k;
-        pk_1 = pk;
-        pk = carter_p(k, dp, e3, lg_n1);
-    }
-    const double d = (fpr - pk) / (pk_1 - pk);
-    s.pw = 1.0 - binom_cdf(k - 1, dp, f, lg_n1) + d * binom_pmf(k, dp, f, lg_n1);
+    const CarterEntry kd = (table && dp < n_table) ? table[dp] : carter_kd(dp, fpr, error_rate / 3.0, lg_n1);
+    const int64_t k = kd.k;
+    s.pw = 1.0 - binom_cdf(k - 1, dp, f, lg_n1) + kd.d * binom_pmf(k, dp, f, lg_n1);
     s.k = (int32_t)k;
     s.pad = 0;
     out[u] = s;
 }
 
+size_t carter_entry_size() { return sizeof(CarterEntry); }
+
+cudaError_t launch_carter_table(int32_t n_table, double fpr, double error_rate, void *table, cudaStream_t stream, int *launches) {
+    carter_table_kernel<<<(unsigned)((n_table + 127) / 128), 128, 0, stream>>>(n_table, fpr, error_rate, (CarterEntry *)table);
+    ++*launches;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_epilogue(int64_t n_units, const vfk_counts *counts, const double *eaf, double fpr, double error_rate,
-                            vfk_stats *out, cudaStream_t stream, int *launches) {
+                            const void *table, int32_t n_table, vfk_stats *out, cudaStream_t stream, int *launches) {
     if (n_units <= 0) return cudaSuccess;
     const int block = 128;
     const int64_t grid = (n_units + block - 1) / block;
-    epilogue_kernel<<<(unsigned)grid, block, 0, stream>>>(n_units, counts, eaf, fpr, error_rate, out);
+    epilogue_kernel<<<(unsigned)grid, block, 0, stream>>>(n_units, counts, eaf, fpr, error_rate, (const CarterEntry *)table, n_table,
+                                                           out);
     ++*launches;
     return cudaGetLastError();
 }
