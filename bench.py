@@ -33,6 +33,9 @@ import time
 # this rank's share of the host cores instead.  Must happen before any OpenMP runtime is loaded.
 if int(os.environ.get("WORLD_SIZE", "1")) > 1:
     os.environ["OMP_NUM_THREADS"] = str(max(2, (os.cpu_count() or 2) // int(os.environ["WORLD_SIZE"])))
+    # rank 0 prints exactly one line on stdout: keep NCCL's version banner out of it
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
 
 import numpy as np
 
