@@ -151,3 +151,37 @@ def test_interval_sharding_on_device():
         assert np.array_equal(a[f], b[f]), f
     one.close()
     two.close()
+
+
+@pytest.mark.parametrize("read_len", [300, 600, 1500])
+def test_longer_reads_use_wider_position_range(dev, read_len):
+    """Read positions beyond 255 select the 512 / 1024 / 4096-bin instantiations (and 9 / 10 / 12-bit ranking)."""
+    cfg = synth.wes(n_tiles=1100, read_len=read_len, frag_mean=2.2 * read_len, frag_sd=0.2 * read_len, tile_len=2 * read_len,
+                    var_lo=read_len, var_hi=3 * read_len, snv_period=200, indel_period=1500, pairs_per_tile=40)
+    batch, recs, units, stop, ounits = _setup(cfg)
+    assert batch.l_qseq.max() == read_len and units.n_units > 200
+    want = c_oracle.pileup(batch.as_dict(), ounits, c_oracle.params(min_mapq=1, min_baseq=30))
+    got = _gpu(dev, batch, units, stop, 1, 30)
+    _compare(got, want)
+    assert int(want["med2"][:, 2, :].max()) > 2 * 255  # medians of read positions beyond one byte
+
+
+def test_degenerate_inputs(dev):
+    """Empty read batch, contig without reads, column 0, every read filtered out."""
+    from vafator_b200.batch import ReadBatch
+    params = device.make_params(min_mapq=1, min_baseq=30)
+    empty = ReadBatch.from_records([], ["c1", "c2"])
+    units = build_units([("c1", 1, "A", ["T"]), ("c2", 500, "AT", ["A"])], empty.contigs)
+    buf = dev.pileup(dev.upload_reads(device.pack_reads(empty, params)), dev.upload_units(units, None), params)
+    dev.sync()
+    got = dev.to_host(buf, device.COUNTS_DTYPE, units.n_units)
+    assert got["dp"].tolist() == [0, 0] and got["n_col"].tolist() == [0, 0] and got["med2"].max() == -1
+    recs = [dict(qname="a", flag=1024, tid=0, pos=0, mapq=60, cigar="10M", seq="ACGTACGTAC", qual=[40] * 10),
+            dict(qname="b", flag=0, tid=0, pos=0, mapq=0, cigar="10M", seq="ACGTACGTAC", qual=[40] * 10),
+            dict(qname="c", flag=0, tid=0, pos=0, mapq=60, cigar="10M", seq="ACGTACGTAC", qual=[40] * 10)]
+    b = ReadBatch.from_records(recs, ["c1", "c2"])
+    units = build_units([("c1", 1, "A", ["T"]), ("c1", 10, "C", ["G"]), ("c1", 11, "A", ["T"]), ("c2", 1, "A", ["T"])], b.contigs)
+    buf = dev.pileup(dev.upload_reads(device.pack_reads(b, params)), dev.upload_units(units, None), params)
+    dev.sync()
+    got = dev.to_host(buf, device.COUNTS_DTYPE, units.n_units)
+    assert got["dp"].tolist() == [1, 1, 0, 0] and got["n_cover"].tolist() == [3, 3, 0, 0] and got["ac_ref"].tolist() == [1, 1, 0, 0]

@@ -313,7 +313,7 @@ void gen_tile(const vfkio_synth_cfg *c, int32_t tid, int64_t k, std::vector<Read
 
 int check_cfg(const vfkio_synth_cfg *c) {
     if (!c) return vfkio_fail(VFK_EINVAL, "synth: NULL config");
-    if (c->n_contigs < 1 || c->read_len < 30 || c->read_len > 1000 || c->tile_len < 1 || c->tile_stride < c->tile_len ||
+    if (c->n_contigs < 1 || c->read_len < 30 || c->read_len > 4000 || c->tile_len < 1 || c->tile_stride < c->tile_len ||
         c->tiles_per_contig < 1 || c->pairs_per_tile < 0)
         return vfkio_fail(VFK_EINVAL, "synth: bad geometry");
     // a second mate may start at most read_len+700-read_len = 700 bases after the first: it must
