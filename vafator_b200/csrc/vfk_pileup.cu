@@ -607,9 +607,15 @@ static cudaError_t launch_posb(const ReadsDev &R, const UnitsDev &V, const vfk_p
     uint32_t *deep_work = (uint32_t *)((char *)counters + 16);
     uint32_t *block_list = lists, *warp_list = lists + V.n;
     cudaError_t e;
-    if (smem_deep > 48 * 1024) {  // opt in to large dynamic shared memory (long-read instantiation only)
-        e = cudaFuncSetAttribute(pileup_deep_kernel<POSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_deep);
+    {
+        // static (staging ring) + dynamic (histograms) shared memory beyond 48 KB needs an opt-in
+        cudaFuncAttributes fa;
+        e = cudaFuncGetAttributes(&fa, pileup_deep_kernel<POSB>);
         if (e != cudaSuccess) return e;
+        if (smem_deep + fa.sharedSizeBytes > 48 * 1024) {
+            e = cudaFuncSetAttribute(pileup_deep_kernel<POSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_deep);
+            if (e != cudaSuccess) return e;
+        }
     }
     int ctas_per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pileup_warp_kernel<POSB>, WARPS_PER_CTA * 32, 0);
