@@ -115,6 +115,19 @@ def _np_round_str(x: float, nd: int) -> str:
     return str(np.round(np.float64(x), nd))
 
 
+class RoundedStats:
+    """Device statistics of one context, rounded once for the whole array with numpy's rounding (the
+    reference rounds np.float64 scalars: same multiply / rint / divide) and held as Python floats, whose
+    str() is the same shortest representation numpy prints."""
+
+    def __init__(self, st: np.ndarray):
+        self.pu = np.round(st["pu"], 5).tolist()
+        self.pw = np.round(st["pw"], 5).tolist()
+        self.k = st["k"].tolist()
+        self.z = np.round(st["z"], 3).tolist()
+        self.p = np.round(st["p"], 5).tolist()
+
+
 class SampleFormatter:
     """Builds the ordered INFO fields of one record (vafator/annotator.py:304-420)."""
 
@@ -159,8 +172,8 @@ def format_fields(prefix: str, suffix: str, with_eaf: bool, alts, kind, ac, dp, 
     o[key("dp")] = int(dp)
     if with_eaf:
         o[key("eaf")] = str(float(eaf))
-    o[key("pu")] = ",".join(_np_round_str(x, 5) for x in pu)
-    o[key("pw")] = _np_round_str(pw, 5)
+    o[key("pu")] = ",".join(str(x) for x in pu)  # already rounded (RoundedStats)
+    o[key("pw")] = str(pw)
     o[key("k")] = str(int(k))
     for name in ("bq", "mq", "pos"):
         o[key(name)] = ",".join(med[name])
@@ -273,9 +286,9 @@ class Engine:
         c["ac_alt"] = [len(x) for x in alt_lists]
         c["ac_ref"] = [len(x) for x in ref_lists]
         c["s2"] = s2
-        st = self.epilogue(c, np.asarray([eaf_sample[i] for i, j, br, ba in needs], np.float64))
-        for n, row in zip(needs, st):
-            out[(n[0], n[1])] = row
+        st = RoundedStats(self.epilogue(c, np.asarray([eaf_sample[i] for i, j, br, ba in needs], np.float64)))
+        for q, n in enumerate(needs):
+            out[(n[0], n[1])] = (st.z[q], st.p[q])
         return out
 
     # ---- the annotation -----------------------------------------------------------------------
@@ -298,13 +311,13 @@ class Engine:
                     raise _dev.VfkError("a read position exceeded the histogram range (reads longer than supported)")
                 res = BamResult(rows, units, counts, in_range)
                 results.append(res)
-                stats.append(self.epilogue(res.row_counts, eaf_row))
+                stats.append(RoundedStats(self.epilogue(res.row_counts, eaf_row)))
             merged_stats = None
             if len(batches) > 1:
                 mc = np.zeros(rows.n_rows, _dev.COUNTS_DTYPE)
                 mc["dp"] = sum(r.dp for r in results)[rows.rec] if rows.n_rows else 0
                 mc["ac_alt"] = sum(r.ac for r in results)
-                merged_stats = self.epilogue(mc, eaf_row)
+                merged_stats = RoundedStats(self.epilogue(mc, eaf_row))
             cross = {}
             if len(batches) > 1:
                 needs = []
@@ -355,27 +368,27 @@ class Engine:
         return med
 
     @staticmethod
-    def _ranksum_strings(kind, state_ref, state_alts, st_rows):
+    def _ranksum_strings(kind, state_ref, state_alts, st, r0):
         rs = {}
         for mi, name in enumerate(METRICS):
             zs, ps = [], []
             if not (name == "bq" and kind != KIND_SNV):
-                for (has_key, n, _), st in zip(state_alts, st_rows):
+                for j, (has_key, n, _) in enumerate(state_alts):
                     if has_key and n > 0 and state_ref[0] and state_ref[1] > 0:
-                        z, p = float(st["z"][mi]), float(st["p"][mi])
-                        if not (math.isnan(z) or math.isnan(p)):
-                            zs.append(_np_round_str(z, 3))
-                            ps.append(_np_round_str(p, 5))
+                        z, p = st.z[r0 + j][mi], st.p[r0 + j][mi]
+                        if not (z != z or p != p):
+                            zs.append(str(z))
+                            ps.append(str(p))
             rs[name] = (zs, ps)
         return rs
 
     def _one(self, sample, suffix, with_eaf, alts, kind, res, st, state, i, r0, r1, e):
         ac = [int(res.ac[r]) for r in range(r0, r1)]
         dp = int(res.dp[i])
-        pu = [float(st["pu"][r]) for r in range(r0, r1)]
-        pw, k = (float(st["pw"][r0]), int(st["k"][r0])) if r1 > r0 else (0.0, 1)
+        pu = st.pu[r0:r1]
+        pw, k = (st.pw[r0], st.k[r0]) if r1 > r0 else (0.0, 1)
         med = self._median_strings(kind, state[0], state[1:])
-        rs = self._ranksum_strings(kind, state[0], state[1:], [st[r] for r in range(r0, r1)])
+        rs = self._ranksum_strings(kind, state[0], state[1:], st, r0)
         return format_fields(sample, suffix, with_eaf, alts, kind, ac, dp, int(res.n[i]), e, pu, pw, k, med, rs)
 
     def _merged(self, sample, alts, kind, results, stats, merged_stats, states, i, r0, r1, e, cross):
@@ -386,8 +399,8 @@ class Engine:
         ac = [int(sum(res.ac[r] for res in results)) for r in range(r0, r1)]
         dp = int(sum(res.dp[i] for res in results))
         n = int(sum(res.n[i] for res in results))
-        pu = [float(merged_stats["pu"][r]) for r in range(r0, r1)]
-        pw, k = (float(merged_stats["pw"][r0]), int(merged_stats["k"][r0])) if r1 > r0 else (0.0, 1)
+        pu = merged_stats.pu[r0:r1]
+        pw, k = (merged_stats.pw[r0], merged_stats.k[r0]) if r1 > r0 else (0.0, 1)
         med = {}
         for mi, name in enumerate(METRICS):
             vals = []
@@ -418,10 +431,10 @@ class Engine:
                         continue
                     if states[b_ref][0][1] == 0 or states[b_alt][1 + j][1] == 0:
                         continue
-                    st = cross[(i, j)] if b_ref != b_alt else stats[b_alt][r0 + j]
-                    z, p = float(st["z"][mi]), float(st["p"][mi])
-                    if not (math.isnan(z) or math.isnan(p)):
-                        zs.append(_np_round_str(z, 3))
-                        ps.append(_np_round_str(p, 5))
+                    zz, pp = cross[(i, j)] if b_ref != b_alt else (stats[b_alt].z[r0 + j], stats[b_alt].p[r0 + j])
+                    z, p = zz[mi], pp[mi]
+                    if not (z != z or p != p):
+                        zs.append(str(z))
+                        ps.append(str(p))
             rs[name] = (zs, ps)
         return format_fields(sample, "", True, alts, kind, ac, dp, n, e, pu, pw, k, med, rs)
