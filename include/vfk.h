@@ -41,6 +41,13 @@ enum {
 
 #define VFK_MAX_READ_LEN 4095 /* longest l_qseq the read-position histograms cover */
 #define VFK_NO_MATE 0xFFFFFFFFu
+#define VFK_SHAPE_SIMPLE 0u
+#define VFK_SHAPE_GENERAL 1u
+#define VFK_SHAPE_ONE_EVENT 2u
+#define VFK_EV_NONE 0
+#define VFK_EV_INS 1
+#define VFK_EV_DEL 2
+#define VFK_EV_SKIP 3
 #define VFK_CODE_NONE 0xFFu
 
 /* ---- read batch, HBM layout (DESIGN.md "Data layout") -------------------------------------
@@ -49,8 +56,12 @@ typedef struct {
     int32_t pos;   /* 0-based leftmost reference position                                      */
     uint32_t span; /* reference bases consumed by the CIGAR (M,D,N,=,X); end = pos + span       */
     uint32_t fmk;  /* flag (bits 0-15) | mapq << 16 | shape << 24;
-                      shape 0: the CIGAR is one M/=/X op (qpos = column - pos, l_qseq = span),
-                      shape 1: general, see the cold record                                    */
+                      shape 0 (VFK_SHAPE_SIMPLE): the CIGAR is one M/=/X op (qpos = column - pos,
+                              l_qseq = span); the cold record is never read,
+                      shape 1 (VFK_SHAPE_GENERAL): any CIGAR, walked op by op,
+                      shape 2 (VFK_SHAPE_ONE_EVENT): [H][S] M [ I|D|N  M ] [S][H] -- clips and at most
+                              one event between two aligned blocks; resolved without a loop from
+                              cold.event (the CIGAR words are kept for the indel-support tests)  */
     uint32_t pay;  /* payload offset, in 32-byte sectors                                       */
 } vfk_read_hot;
 
@@ -58,7 +69,8 @@ typedef struct {
     uint32_t cigar_off; /* index into cigar[] (BAM encoding len<<4|op)                         */
     uint32_t n_cigar;
     uint32_t l_qseq;
-    uint32_t reserved;
+    uint32_t event; /* shape 2: leading soft clip | first block length << 12 | VFK_EV_* << 24 |
+                       event length << 26 (lengths < 4096 / < 64, else the read is shape 1); 0 otherwise */
 } vfk_read_cold;
 
 /* payload: read i owns ceil(l_qseq/20) sectors of 32 bytes from hot.pay.  A sector is four 8-byte

@@ -22,6 +22,18 @@ def test_quality_scaling_is_integer_exact():
         assert int(0.8 * q) == (4 * q) // 5
 
 
+def one_event_word(ops, l_qseq):
+    """include/vfk.h VFK_SHAPE_ONE_EVENT: [H][S] M [ I|D|N M ] [S][H] -> lead | m1 << 12 | event << 24 | len << 26."""
+    m = re.fullmatch(r"(?:\d+H)*(?:(\d+)S)?(\d+)[M=X](?:(\d+)([IDN])(\d+)[M=X])?(?:\d+S)?(?:\d+H)*", "".join(n + o for n, o in ops))
+    if not m:
+        return None
+    lead, m1 = int(m.group(1) or 0), int(m.group(2))
+    ev, ln = ("IDN".index(m.group(4)) + 1, int(m.group(3))) if m.group(4) else (0, 0)
+    if m1 == 0 or m1 >= 4096 or lead >= 4096 or ln >= 64 or l_qseq > 4095 or (m.group(4) and (ln == 0 or int(m.group(5)) == 0)):
+        return None
+    return lead | (m1 << 12) | (ev << 24) | (ln << 26)
+
+
 @pytest.mark.parametrize("path", SCENARIOS, ids=[os.path.basename(p) for p in SCENARIOS])
 def test_pack_layout_round_trips(path):
     sc = H.load_scenario(path)
@@ -45,7 +57,9 @@ def test_pack_layout_round_trips(path):
             span = sum(int(n) for n, o in ops if o in "MDN=X")
             assert pk.hot["span"][i] == span
             simple = len(ops) == 1 and ops[0][1] in "M=X"
-            assert (pk.hot["fmk"][i] >> 24) == (0 if simple else 1)
+            event = None if simple else one_event_word(ops, lq)
+            assert (pk.hot["fmk"][i] >> 24) == (0 if simple else 1 if event is None else 2)
+            assert pk.cold["event"][i] == (event or 0)
             if not simple:
                 co, nc = int(pk.cold["cigar_off"][i]), int(pk.cold["n_cigar"][i])
                 assert [(int(w) >> 4, "MIDNSHP=X"[int(w) & 15]) for w in pk.cigar[co:co + nc]] == [(int(n), o) for n, o in ops]

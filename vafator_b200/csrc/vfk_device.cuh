@@ -63,7 +63,17 @@ struct Unit {
     int64_t lo, hi;
 };
 
-// one read's contribution to a column
+// One read's contribution to a column, as two words (what the shallow kernel reduces directly):
+//   pk : mq | bq << 8 | qpos << 16 | PK_REF | PK_ALT   -- non-zero iff the read's values enter a reported list
+//   fl : one counter per byte, ready to be summed over reads: covers | in_col << 8 | in_dp << 16 | ambiguous << 24
+//   alt: how many times the values enter the ALT list (an insertion can be supported more than once)
+constexpr uint32_t PK_REF = 1u << 28, PK_ALT = 1u << 29;
+constexpr uint32_t FL_COVERS = 1u, FL_IN_COL = 1u << 8, FL_IN_DP = 1u << 16, FL_AMBIGUOUS = 1u << 24;
+struct Eval {
+    uint32_t pk, fl, alt;
+};
+
+// decoded view used by the histogram kernels
 struct Contribution {
     bool covers;   // the read spans the column (before any filter)
     bool in_col;   // ... and is part of the htslib column (read filter passed, CIGAR covers it)
@@ -72,8 +82,15 @@ struct Contribution {
     bool ref;      // value goes to the REF list
     uint32_t alt;  // how many times the value goes to the ALT list
     int mq, bq, qpos;
-    bool pos_overflow;
 };
+__device__ __forceinline__ Contribution decode(const Eval &e) {
+    Contribution c;
+    c.covers = e.fl & FL_COVERS; c.in_col = e.fl & FL_IN_COL; c.in_dp = e.fl & FL_IN_DP; c.ambiguous = e.fl & FL_AMBIGUOUS;
+    c.ref = e.pk & PK_REF;
+    c.alt = e.alt;
+    c.mq = (int)(e.pk & 0xFFu); c.bq = (int)((e.pk >> 8) & 0xFFu); c.qpos = (int)((e.pk >> 16) & 0xFFFu);
+    return c;
+}
 
 __device__ __forceinline__ bool is_ref_op(int op) { return op == OP_M || op == OP_D || op == OP_N || op == OP_EQ || op == OP_X; }
 __device__ __forceinline__ bool is_aln_op(int op) { return op == OP_M || op == OP_EQ || op == OP_X; }
@@ -110,11 +127,6 @@ __device__ __forceinline__ uint32_t pay_lookup(const uint8_t *__restrict__ paylo
 __device__ __forceinline__ int word_qual(uint32_t w) { return (int)(w & 0xFFu); }
 __device__ __forceinline__ int word_base(uint32_t w) { return (int)(w >> 8); }
 
-__device__ __forceinline__ uint32_t wang_hash(uint32_t k) {
-    k += ~(k << 15); k ^= (k >> 10); k += (k << 3); k ^= (k >> 6); k += ~(k << 11); k ^= (k >> 16);
-    return k;
-}
-
 // BAM 4-bit codes "=ACMGRSVTWYHKDBN": everything but = A C G T is IUPAC-ambiguous (vafator/constants.py:5)
 __device__ __forceinline__ bool code_is_ambiguous(int c) { return ((0x0117u >> c) & 1u) == 0u; }
 
@@ -136,7 +148,7 @@ struct Resolved {
     int l_qseq;
 };
 
-// general CIGAR walk for a shape-1 read (cold record needed)
+// general CIGAR walk (shape 1; also correct for shape 2, which keeps its CIGAR)
 __device__ __forceinline__ Resolved resolve_general(const ReadsDev &R, int32_t rpos, const uint4 &cold, int32_t col) {
     Resolved o;
     o.covered = false; o.is_del = false; o.is_refskip = false; o.qpos = 0; o.indel = 0; o.l_qseq = (int)cold.z;
@@ -198,7 +210,28 @@ __device__ __forceinline__ Resolved resolve_general(const ReadsDev &R, int32_t r
     return o;
 }
 
-// reference position aligned to query index q of a shape-1 read, -1 if q is not in an M/=/X op
+// shape-2 read: [H][S lead] M m1 [ (I|D|N) e  M m2 ] [S][H] -- at most one event between two aligned blocks.
+// cold.w = lead | m1 << 12 | event << 24 | e << 26 (vfk.h); same answers as resolve_general, no loop.
+__device__ __forceinline__ Resolved resolve_one_event(int32_t rpos, const uint4 &cold, int32_t col) {
+    Resolved o;
+    const int lead = (int)(cold.w & 0xFFFu), m1 = (int)((cold.w >> 12) & 0xFFFu), ev = (int)((cold.w >> 24) & 3u), e = (int)(cold.w >> 26);
+    const int d = col - rpos;                   // 0 <= d < span (the caller checked)
+    const int gap = ev >= VFK_EV_DEL ? e : 0;   // D / N consume reference
+    o.covered = true; o.l_qseq = (int)cold.z; o.is_del = false; o.is_refskip = false; o.indel = 0;
+    if (d < m1) {
+        o.qpos = lead + d;
+        if (d == m1 - 1) o.indel = ev == VFK_EV_INS ? e : ev == VFK_EV_DEL ? -e : 0;
+    } else if (d < m1 + gap) {
+        o.qpos = lead + m1;
+        o.is_del = true;
+        o.is_refskip = ev == VFK_EV_SKIP;
+    } else {
+        o.qpos = lead + m1 + (ev == VFK_EV_INS ? e : 0) + (d - m1 - gap);
+    }
+    return o;
+}
+
+// reference position aligned to query index q of a general read, -1 if q is not in an M/=/X op
 __device__ __forceinline__ int32_t refpos_of_query(const ReadsDev &R, int32_t rpos, const uint4 &cold, int q) {
     const uint32_t *__restrict__ c = R.cigar + cold.x;
     int32_t x = rpos, y = 0;
@@ -257,7 +290,8 @@ __device__ __forceinline__ int tweaked_quality(const ReadsDev &R, const vfk_para
         ml = (int)mh.y;
     } else {
         uint4 mc = __ldg(R.cold + m);
-        Resolved mr = resolve_general(R, (int32_t)mh.x, mc, rp);
+        Resolved mr = (mh.z >> 24) == VFK_SHAPE_ONE_EVENT ? resolve_one_event((int32_t)mh.x, mc, rp)
+                                                          : resolve_general(R, (int32_t)mh.x, mc, rp);
         if (!mr.covered || mr.is_del) return qi;
         mq_index = mr.qpos;
         ml = mr.l_qseq;
@@ -344,19 +378,16 @@ __device__ __forceinline__ uint32_t deletion_hits(const ReadsDev &R, const uint4
 
 // Everything one read contributes to one unit.  `hot` / `mw` are the read's header and mate word
 // (the caller loads them, possibly one unit ahead of use).
-// SIMPLE: the caller knows the read's CIGAR is one M/=/X op;  UNLINKED: ... and that it has no overlap
-// partner.  Both only prune code (the thread-per-unit kernel sorts its reads into those classes first).
-template <bool SIMPLE = false, bool UNLINKED = false>
-__device__ __forceinline__ Contribution evaluate(const ReadsDev &R, const vfk_params &P, const Unit &U, int64_t i,
-                                                 const uint4 &hot, uint32_t mw_in) {
-    const uint32_t mw = UNLINKED ? VFK_NO_MATE : mw_in;
-    Contribution o;
-    o.covers = false; o.in_col = false; o.in_dp = false; o.ambiguous = false; o.ref = false; o.alt = 0; o.mq = 0; o.bq = 0; o.qpos = 0; o.pos_overflow = false;
+__device__ __forceinline__ Eval evaluate_packed(const ReadsDev &R, const vfk_params &P, const Unit &U, int64_t i, const uint4 &hot,
+                                                uint32_t mw) {
+    Eval o;
+    o.pk = 0u; o.fl = 0u; o.alt = 0u;
     const int32_t rpos = (int32_t)hot.x;
-    if (U.col < rpos || U.col >= rpos + (int32_t)hot.y) return o;
-    o.covers = true;
+    if ((uint32_t)(U.col - rpos) >= hot.y) return o;  // col < pos wraps to a huge unsigned
+    o.fl = FL_COVERS;
     if (!read_passes(hot.z, P)) return o;
-    const bool general = SIMPLE ? false : (hot.z >> 24) != 0u;
+    const uint32_t shape = hot.z >> 24;
+    const bool general = shape != VFK_SHAPE_SIMPLE;
     uint4 cold = make_uint4(0, 0, 0, 0);
     Resolved r;
     if (!general) {
@@ -365,39 +396,46 @@ __device__ __forceinline__ Contribution evaluate(const ReadsDev &R, const vfk_pa
         r.l_qseq = (int)hot.y;
     } else {
         cold = __ldg(R.cold + i);
-        r = resolve_general(R, rpos, cold, U.col);
-        if (!r.covered) return o;
+        if (shape == VFK_SHAPE_ONE_EVENT) {
+            r = resolve_one_event(rpos, cold, U.col);
+        } else {
+            r = resolve_general(R, rpos, cold, U.col);
+            if (!r.covered) return o;
+        }
     }
-    o.in_col = true;
+    o.fl |= FL_IN_COL;
     const uint32_t my_word = r.qpos < r.l_qseq ? pay_lookup(R.payload, hot.w, (uint32_t)r.qpos) : 0u;
     const int q = tweaked_quality(R, P, U, i, hot, mw, cold, general, r.qpos, r.l_qseq, !r.is_del, my_word);
     if (q < P.min_baseq) return o;  // pysam pileup_base_qual_skip
-    o.mq = (int)((hot.z >> 16) & 0xFF);
-    o.bq = q;
-    o.qpos = r.qpos;
+    const uint32_t mq_pos = ((hot.z >> 16) & 0xFFu) | ((uint32_t)r.qpos << 16);
     if (U.kind == VFK_KIND_SNV) {
         if (r.is_refskip) return o;
-        o.in_dp = true;
+        o.fl |= FL_IN_DP;
         if (r.is_del) return o;  // counted in DP as the "" allele, belongs to no reported list
-        int code = word_base(my_word);
-        o.ambiguous = code_is_ambiguous(code);
-        o.ref = (uint32_t)code == U.ref_code;
-        o.alt = ((uint32_t)code == U.alt_code) ? 1u : 0u;
+        const uint32_t code = (uint32_t)word_base(my_word);
+        if (code_is_ambiguous((int)code)) o.fl |= FL_AMBIGUOUS;
+        const uint32_t lists = (code == U.ref_code ? PK_REF : 0u) | (code == U.alt_code ? PK_ALT : 0u);
+        if (lists) o.pk = mq_pos | ((uint32_t)q << 8) | lists;
+        o.alt = code == U.alt_code ? 1u : 0u;
     } else {
-        o.in_dp = true;
-        o.bq = 0;
+        o.fl |= FL_IN_DP;
         if (r.indel == 0) {
-            o.ref = true;  // "considers all reads without indels to be the reference" (pileups.py:291-294)
+            o.pk = mq_pos | PK_REF;  // "considers all reads without indels to be the reference" (pileups.py:291-294)
         } else if (general) {
             if (U.kind == VFK_KIND_INS && r.indel > 0) o.alt = insertion_hits(R, hot, cold, U);
             else if (U.kind == VFK_KIND_DEL && r.indel < 0) o.alt = deletion_hits(R, hot, cold, U);
+            if (o.alt) o.pk = mq_pos | PK_ALT;
         }
     }
     return o;
 }
 
+__device__ __forceinline__ Contribution evaluate(const ReadsDev &R, const vfk_params &P, const Unit &U, int64_t i, const uint4 &hot,
+                                                 uint32_t mw) {
+    return decode(evaluate_packed(R, P, U, i, hot, mw));
+}
 __device__ __forceinline__ Contribution evaluate(const ReadsDev &R, const vfk_params &P, const Unit &U, int64_t i) {
-    return evaluate<false, false>(R, P, U, i, __ldg(R.hot + i), __ldg(R.mate + i));
+    return evaluate(R, P, U, i, __ldg(R.hot + i), __ldg(R.mate + i));
 }
 
 // ---- bulk asynchronous copies (TMA, cp.async.bulk) completed on an mbarrier ----

@@ -195,12 +195,6 @@ __device__ __forceinline__ void accumulate(uint32_t *ref_slot, uint32_t *alt_slo
 // ------------------------------------------------------------------------------------------
 // shallow path: one value per lane, ranks from bit-sliced comparisons
 // ------------------------------------------------------------------------------------------
-// packed contribution: mq | bq << 8 | qpos << 16 | ref << 28 | alt << 29
-constexpr uint32_t PK_REF = 1u << 28, PK_ALT = 1u << 29;
-__device__ __forceinline__ uint32_t pack(const Contribution &c) {
-    return (uint32_t)c.mq | ((uint32_t)c.bq << 8) | ((uint32_t)c.qpos << 16) | (c.ref ? PK_REF : 0u) | (c.alt ? PK_ALT : 0u);
-}
-
 // For this lane's value v (NBITS wide): which contributing lanes hold a smaller value (lt) and
 // which an equal one (eq, itself included).  Walks the bits from the top, branch free; lanes that
 // do not contribute hold v == 0, so every ballot is already restricted to the contributing set.
@@ -218,31 +212,33 @@ __device__ __forceinline__ void radix_compare(uint32_t v, uint32_t contributing,
     }
 }
 
-// medians of the REF / ALT lists and the ALT mid-rank sum, from the lt / eq masks.
-// The order statistic k of a list is held by every lane whose [below, below + ties) interval contains
-// k -- all of them carry the same value, so an OR reduction returns it; the (up to) four order
-// statistics of a metric travel in one word (FIELD bits each) and one REDUX.
+// Medians of the REF / ALT lists and this lane's share of the ALT mid-rank sum, from the lt / eq masks.
+//
+// Median: ties are broken by lane id, so every member of a list owns exactly one 0-based position of
+// the sorted list, pos = #smaller + #equal-in-lower-lanes.  The member(s) at the middle position(s)
+// contribute value * weight (weight 2 when the count is odd, 1 + 1 when it is even) and ONE additive
+// reduction returns twice the median of both lists: REF in the low half-word, ALT in the high one.
+//
+// Rank sum: scipy ranks the pooled sample; with b(a) / t(a) the REF values below / equal to an ALT value a,
+//   2 * rank_sum(ALT) = sum_a (2 * below(a) + ties(a) + 1) = na^2 + na + sum_a (2 * b(a) + t(a))
+// because the ALT-vs-ALT part of the sum is na^2 whatever the values are.  The lane returns
+// 2 * b + t (<= 2 * nr; summed over na lanes <= 2 * 16 * 16 = 512 while nr + na <= 32): the three metrics'
+// terms share one reduction, 10 bits each.
 struct SlotShape {  // metric independent
-    int nr, na, r1, r2, a1, a2;
+    uint32_t R, A;          // list membership (lanes)
+    uint32_t R_low, A_low;  // ... restricted to the lanes below this one
+    int r1, a1;             // lower middle position
+    uint32_t dr, da;        // upper middle position - lower (0: odd count, 1: even)
+    uint32_t sh_r, sh_a;    // weight shift (+16 for ALT)
+    bool is_ref, is_alt;
 };
-template <int FIELD>
-__device__ __forceinline__ void radix_finish(uint32_t v, uint32_t R, uint32_t A, bool is_ref, bool is_alt, uint32_t lt,
-                                             uint32_t eq, const SlotShape &sh, int &med2_ref, int &med2_alt, uint64_t &s2) {
-    const int br = __popc(lt & R), tr = __popc(eq & R), ba = __popc(lt & A), ta = __popc(eq & A);
-    // the pooled sample is the concatenation of both lists: a lane in both counts twice
-    s2 = (sh.nr && sh.na) ? (uint64_t)__reduce_add_sync(FULL, is_alt ? (unsigned)(2 * (br + ba) + tr + ta + 1) : 0u) : 0ull;
-    const bool h_r1 = is_ref && br <= sh.r1 && sh.r1 < br + tr, h_r2 = is_ref && br <= sh.r2 && sh.r2 < br + tr;
-    const bool h_a1 = is_alt && ba <= sh.a1 && sh.a1 < ba + ta, h_a2 = is_alt && ba <= sh.a2 && sh.a2 < ba + ta;
-    if (FIELD <= 8) {
-        const uint32_t w = __reduce_or_sync(FULL, (h_r1 ? v : 0u) | (h_r2 ? v << 8 : 0u) | (h_a1 ? v << 16 : 0u) | (h_a2 ? v << 24 : 0u));
-        med2_ref = sh.nr ? (int)((w & 0xFFu) + ((w >> 8) & 0xFFu)) : -1;
-        med2_alt = sh.na ? (int)(((w >> 16) & 0xFFu) + (w >> 24)) : -1;
-    } else {
-        const uint32_t wr = __reduce_or_sync(FULL, (h_r1 ? v : 0u) | (h_r2 ? v << 16 : 0u));
-        const uint32_t wa = __reduce_or_sync(FULL, (h_a1 ? v : 0u) | (h_a2 ? v << 16 : 0u));
-        med2_ref = sh.nr ? (int)((wr & 0xFFFFu) + (wr >> 16)) : -1;
-        med2_alt = sh.na ? (int)((wa & 0xFFFFu) + (wa >> 16)) : -1;
-    }
+__device__ __forceinline__ uint32_t radix_finish(uint32_t v, uint32_t lt, uint32_t eq, const SlotShape &sh, uint32_t &med2_sum) {
+    const uint32_t br = __popc(lt & sh.R), tr = __popc(eq & sh.R);
+    const uint32_t pos_r = br + __popc(eq & sh.R_low), pos_a = __popc(lt & sh.A) + __popc(eq & sh.A_low);
+    const bool mid_r = sh.is_ref && (uint32_t)(pos_r - (uint32_t)sh.r1) <= sh.dr;
+    const bool mid_a = sh.is_alt && (uint32_t)(pos_a - (uint32_t)sh.a1) <= sh.da;
+    med2_sum = __reduce_add_sync(FULL, (mid_r ? v << sh.sh_r : 0u) + (mid_a ? v << sh.sh_a : 0u));
+    return sh.is_alt ? 2u * br + tr : 0u;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -294,7 +290,7 @@ __device__ __forceinline__ void unit_by_histogram(const ReadsDev &R, const vfk_p
             ring->parity ^= 1u << s;
             if (i < U.hi) {
                 const uint4 hot = ring->hot[s * 32 + lane];
-                const Contribution c1 = evaluate<false, false>(R, P, U, i, hot, mw);
+                const Contribution c1 = evaluate(R, P, U, i, hot, mw);
                 n_cover += c1.covers ? 1 : 0;
                 n_col += c1.in_col ? 1 : 0;
                 dp += c1.in_dp ? 1 : 0;
@@ -407,34 +403,54 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
                 }
                 continue;
             }
-            // ---- shallow: at most two reads per lane ----
-            Contribution c0, c1;
-            c0.covers = c0.in_col = c0.in_dp = c0.ambiguous = c0.ref = false; c0.alt = 0; c0.mq = c0.bq = c0.qpos = 0;
-            c1 = c0;
-            if (lane < n_cand) c0 = evaluate<false, false>(R, P, U, U.lo + lane, hot_c, mw_c);
-            if (n_cand > 32 && lane + 32 < n_cand) c1 = evaluate(R, P, U, U.lo + 32 + lane);
-            const bool k0 = c0.ref || c0.alt, k1 = c1.ref || c1.alt;
+            // ---- shallow: the reads that span the column are packed into the lanes (first chunk in place,
+            // second chunk into the lanes the first one leaves free) and evaluated in one pass; a second
+            // pass only runs for the overflow when more than 32 reads span the column ----
+            bool act = lane < n_cand && (uint32_t)(U.col - (int32_t)hot_c.x) < hot_c.y;
+            int64_t i_a = U.lo + lane;
+            uint4 hot_a = hot_c;
+            uint32_t mw_a = mw_c;
+            Eval e0, e1;
+            e0.pk = e0.fl = e0.alt = 0u;
+            e1 = e0;
+            if (n_cand > 32) {
+                const bool has1 = lane + 32 < n_cand;
+                uint4 hot_1 = make_uint4(0, 0, 0, 0);
+                uint32_t mw_1 = VFK_NO_MATE;
+                if (has1) { hot_1 = __ldg(R.hot + i_a + 32); mw_1 = __ldg(R.mate + i_a + 32); }
+                const bool cov1 = has1 && (uint32_t)(U.col - (int32_t)hot_1.x) < hot_1.y;
+                const uint32_t c0m = __ballot_sync(FULL, act), c1m = __ballot_sync(FULL, cov1);
+                const int n_free = 32 - __popc(c0m), idx1 = __popc(c1m & lt_mask);
+                const int n_move = min(n_free, __popc(c1m));
+                if (cov1 && idx1 < n_move) stage[idx1] = (uint32_t)lane;
+                __syncwarp();
+                const int slot = __popc(~c0m & lt_mask);  // this lane's rank among the free lanes
+                const bool adopt = !act && slot < n_move;
+                const int src = adopt ? (int)stage[slot] : lane;
+                __syncwarp();
+                const uint32_t hx = __shfl_sync(FULL, hot_1.x, src), hy = __shfl_sync(FULL, hot_1.y, src);
+                const uint32_t hz = __shfl_sync(FULL, hot_1.z, src), hw = __shfl_sync(FULL, hot_1.w, src);
+                const uint32_t hm = __shfl_sync(FULL, mw_1, src);
+                if (adopt) {
+                    hot_a = make_uint4(hx, hy, hz, hw);
+                    mw_a = hm;
+                    i_a = U.lo + 32 + src;
+                    act = true;
+                }
+                const bool over = cov1 && idx1 >= n_move;
+                if (__any_sync(FULL, over)) {
+                    if (over) e1 = evaluate_packed(R, P, U, U.lo + 32 + lane, hot_1, mw_1);
+                }
+            }
+            if (act) e0 = evaluate_packed(R, P, U, i_a, hot_a, mw_a);
+            const bool k0 = e0.pk != 0u, k1 = e1.pk != 0u;
             const uint32_t m0 = __ballot_sync(FULL, k0), m1 = __ballot_sync(FULL, k1);
             // a read can support an insertion more than once (pileups.py:267-290): such units take the deep path
-            const bool heavy = U.kind == VFK_KIND_INS && __any_sync(FULL, c0.alt > 1u || c1.alt > 1u);
-            if (heavy || __popc(m0) + __popc(m1) > 32) {  // rare: re-done through the histograms
-                if (lane == 0) {
-                    warp_list[atomicAdd(n_warp, 1u)] = (uint32_t)u;
-                    store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind | VFK_ST_DEFERRED, (uint32_t)n_cand, 0u);
-                }
-                continue;
-            }
-            // four counters (each <= 64) in the byte lanes of one word, one reduction
-            const uint32_t tally = __reduce_add_sync(FULL, ((uint32_t)c0.in_dp + (uint32_t)c1.in_dp) |
-                                                               (((uint32_t)c0.ambiguous + (uint32_t)c1.ambiguous) << 8) |
-                                                               (((uint32_t)c0.covers + (uint32_t)c1.covers) << 16) |
-                                                               (((uint32_t)c0.in_col + (uint32_t)c1.in_col) << 24));
-            int dp = (int)(tally & 0xFFu);
-            const int n_amb = (int)((tally >> 8) & 0xFFu), n_cover = (int)((tally >> 16) & 0xFFu), n_col = (int)(tally >> 24);
-            uint32_t pk = k0 ? pack(c0) : 0u;
-            if (m1) {  // move the second chunk's contributions into lanes the first one left free
+            const bool heavy = U.kind == VFK_KIND_INS && __any_sync(FULL, e0.alt > 1u || e1.alt > 1u);
+            uint32_t pk = e0.pk;
+            if (m1) {  // move the overflow pass's contributions into lanes the first pass left free
                 const int n1 = __popc(m1);
-                if (k1) stage[__popc(m1 & lt_mask)] = pack(c1);
+                if (k1) stage[__popc(m1 & lt_mask)] = e1.pk;
                 __syncwarp();
                 if (!k0) {
                     const int f = __popc(~m0 & lt_mask);
@@ -442,23 +458,50 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
                 }
                 __syncwarp();
             }
-            const bool is_ref = pk & PK_REF, is_alt = pk & PK_ALT;
-            const uint32_t Rm = __ballot_sync(FULL, is_ref), Am = __ballot_sync(FULL, is_alt);
-            const int ac_ref = __popc(Rm), ac_alt = __popc(Am);
-            if (Rm | Am) {
-                uint32_t lt, eq;
-                const uint32_t mq = pk & 0xFFu, bq = (pk >> 8) & 0xFFu, qp = (pk >> 16) & 0xFFFu;
-                SlotShape sh;
-                sh.nr = ac_ref; sh.na = ac_alt;
-                sh.r1 = (ac_ref - 1) >> 1; sh.r2 = ac_ref >> 1; sh.a1 = (ac_alt - 1) >> 1; sh.a2 = ac_alt >> 1;
-                radix_compare<8>(mq, Rm | Am, lt, eq);
-                radix_finish<8>(mq, Rm, Am, is_ref, is_alt, lt, eq, sh, med2[0][0], med2[0][1], s2[0]);
-                if (U.kind == VFK_KIND_SNV) {
-                    radix_compare<8>(bq, Rm | Am, lt, eq);
-                    radix_finish<8>(bq, Rm, Am, is_ref, is_alt, lt, eq, sh, med2[1][0], med2[1][1], s2[1]);
+            SlotShape sh;
+            sh.is_ref = pk & PK_REF;
+            sh.is_alt = pk & PK_ALT;
+            sh.R = __ballot_sync(FULL, sh.is_ref);
+            sh.A = __ballot_sync(FULL, sh.is_alt);
+            // rare: more contributions than lanes, a multiply supported insertion, or REF == ALT (a read in
+            // both lists) -- re-done through the histograms
+            if (heavy || __popc(m0) + __popc(m1) > 32 || (sh.R & sh.A)) {
+                if (lane == 0) {
+                    warp_list[atomicAdd(n_warp, 1u)] = (uint32_t)u;
+                    store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind | VFK_ST_DEFERRED, (uint32_t)n_cand, 0u);
                 }
-                radix_compare<L::POS_BITS>(qp, Rm | Am, lt, eq);
-                radix_finish<L::POS_BITS>(qp, Rm, Am, is_ref, is_alt, lt, eq, sh, med2[2][0], med2[2][1], s2[2]);
+                continue;
+            }
+            // four counters (each <= 64) in the byte lanes of one word, one reduction
+            const uint32_t tally = __reduce_add_sync(FULL, e0.fl + e1.fl);
+            const int n_cover = (int)(tally & 0xFFu), n_col = (int)((tally >> 8) & 0xFFu), n_amb = (int)(tally >> 24);
+            int dp = (int)((tally >> 16) & 0xFFu);
+            const int ac_ref = __popc(sh.R), ac_alt = __popc(sh.A);
+            if (sh.R | sh.A) {
+                uint32_t lt, eq, w;
+                const uint32_t mq = pk & 0xFFu, bq = (pk >> 8) & 0xFFu, qp = (pk >> 16) & 0xFFFu;
+                sh.R_low = sh.R & lt_mask; sh.A_low = sh.A & lt_mask;
+                sh.r1 = (ac_ref - 1) >> 1; sh.a1 = (ac_alt - 1) >> 1;
+                sh.dr = (uint32_t)(ac_ref >> 1) - (uint32_t)sh.r1; sh.da = (uint32_t)(ac_alt >> 1) - (uint32_t)sh.a1;
+                sh.sh_r = 1u - sh.dr; sh.sh_a = 17u - sh.da;
+                radix_compare<8>(mq, sh.R | sh.A, lt, eq);
+                uint32_t term = radix_finish(mq, lt, eq, sh, w);
+                med2[0][0] = ac_ref ? (int)(w & 0xFFFFu) : -1; med2[0][1] = ac_alt ? (int)(w >> 16) : -1;
+                if (U.kind == VFK_KIND_SNV) {
+                    radix_compare<8>(bq, sh.R | sh.A, lt, eq);
+                    term |= radix_finish(bq, lt, eq, sh, w) << 10;
+                    med2[1][0] = ac_ref ? (int)(w & 0xFFFFu) : -1; med2[1][1] = ac_alt ? (int)(w >> 16) : -1;
+                }
+                radix_compare<L::POS_BITS>(qp, sh.R | sh.A, lt, eq);
+                term |= radix_finish(qp, lt, eq, sh, w) << 20;
+                med2[2][0] = ac_ref ? (int)(w & 0xFFFFu) : -1; med2[2][1] = ac_alt ? (int)(w >> 16) : -1;
+                if (ac_ref && ac_alt) {
+                    const uint32_t sums = __reduce_add_sync(FULL, term);
+                    const uint64_t base2 = (uint64_t)(ac_alt * ac_alt + ac_alt);
+                    s2[0] = base2 + (sums & 0x3FFu);
+                    if (U.kind == VFK_KIND_SNV) s2[1] = base2 + ((sums >> 10) & 0x3FFu);
+                    s2[2] = base2 + (sums >> 20);
+                }
             }
             if (U.kind == VFK_KIND_SNV && !P.include_ambiguous) dp -= n_amb;  // pileups.py:224-227
             if (lane == 0) store_counts(out + u, dp, n_amb, ac_ref, ac_alt, med2, s2, U.kind, (uint32_t)n_cand, (uint32_t)n_cover,

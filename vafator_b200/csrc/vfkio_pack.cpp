@@ -20,16 +20,45 @@ inline bool is_match(unsigned op) { return op == 0 || op == 7 || op == 8; }
 
 struct Shape {
     uint32_t span;
-    bool simple;  // one M/=/X op spanning the whole read
+    bool simple;     // one M/=/X op spanning the whole read
+    uint32_t event;  // non-zero flag word of a one-event read (vfk.h VFK_SHAPE_ONE_EVENT), else 0
+    bool one_event;
 };
+// [H*][S] M [ (I|D|N) M ] [S][H*] with every length in range -> the packed event word
+inline bool one_event_word(const uint32_t *c, int n, int32_t l_qseq, uint32_t *word) {
+    int k = 0, e = n;
+    while (k < e && (c[k] & 15u) == 5u) ++k;      // leading H
+    while (e > k && (c[e - 1] & 15u) == 5u) --e;  // trailing H
+    uint32_t lead = 0;
+    if (k < e && (c[k] & 15u) == 4u) lead = c[k++] >> 4;
+    if (e > k && (c[e - 1] & 15u) == 4u) --e;  // trailing S only lengthens the query
+    const int ops = e - k;
+    if (ops != 1 && ops != 3) return false;
+    if (!is_match(c[k] & 15u)) return false;
+    const uint32_t m1 = c[k] >> 4;
+    uint32_t ev = VFK_EV_NONE, len = 0;
+    if (ops == 3) {
+        const uint32_t op = c[k + 1] & 15u;
+        ev = op == 1u ? VFK_EV_INS : op == 2u ? VFK_EV_DEL : op == 3u ? VFK_EV_SKIP : VFK_EV_NONE;
+        len = c[k + 1] >> 4;
+        if (ev == VFK_EV_NONE || !is_match(c[k + 2] & 15u) || (c[k + 2] >> 4) == 0u || len == 0u) return false;
+    }
+    if (m1 == 0u || m1 >= 4096u || lead >= 4096u || len >= 64u || l_qseq > VFK_MAX_READ_LEN) return false;
+    *word = lead | (m1 << 12) | (ev << 24) | (len << 26);
+    return true;
+}
 inline Shape shape_of(const vfkio_reads *r, int64_t i) {
     const uint32_t *c = r->cigar + r->cigar_off[i];
     const int n = r->n_cigar[i];
     uint32_t span = 0;
     for (int k = 0; k < n; ++k)
         if (consumes_ref(c[k] & 15u)) span += c[k] >> 4;
-    bool simple = n == 1 && is_match(c[0] & 15u) && (int64_t)(c[0] >> 4) == (int64_t)r->l_qseq[i];
-    return {span, simple};
+    Shape sh;
+    sh.span = span;
+    sh.simple = n == 1 && is_match(c[0] & 15u) && (int64_t)(c[0] >> 4) == (int64_t)r->l_qseq[i];
+    sh.event = 0;
+    sh.one_event = !sh.simple && one_event_word(c, n, r->l_qseq[i], &sh.event);
+    return sh;
 }
 inline int64_t sectors_of(int32_t l_qseq) { return ((int64_t)l_qseq + 19) / 20; }  // 4 granules x 5 positions
 }  // namespace
@@ -88,12 +117,13 @@ extern "C" int vfkio_pack(const vfkio_reads *r, const vfkio_plan *plan, int64_t 
         const Shape sh = shape_of(r, i);
         hot[i].pos = r->pos[i];
         hot[i].span = sh.span;
-        hot[i].fmk = (uint32_t)r->flag[i] | ((uint32_t)r->mapq[i] << 16) | ((sh.simple ? 0u : 1u) << 24);
+        const uint32_t shape = sh.simple ? VFK_SHAPE_SIMPLE : sh.one_event ? VFK_SHAPE_ONE_EVENT : VFK_SHAPE_GENERAL;
+        hot[i].fmk = (uint32_t)r->flag[i] | ((uint32_t)r->mapq[i] << 16) | (shape << 24);
         hot[i].pay = pay[i];
         cold[i].cigar_off = sh.simple ? 0u : cig[i];
         cold[i].n_cigar = (uint32_t)r->n_cigar[i];
         cold[i].l_qseq = (uint32_t)r->l_qseq[i];
-        cold[i].reserved = 0;
+        cold[i].event = sh.one_event ? sh.event : 0u;
         sb[2 * i] = r->pos[i];
         if (!sh.simple) memcpy(cigar + cig[i], r->cigar + r->cigar_off[i], (size_t)r->n_cigar[i] * 4);
         // payload: 8-byte granules of 5 positions x 12 bits (quality | base << 8), 4 granules per sector

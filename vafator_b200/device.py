@@ -24,7 +24,7 @@ COUNTS_DTYPE = np.dtype([("dp", "<i4"), ("n_amb", "<i4"), ("ac_ref", "<i4"), ("a
 STATS_DTYPE = np.dtype([("z", "<f8", (3,)), ("p", "<f8", (3,)), ("pu", "<f8"), ("pw", "<f8"), ("k", "<i4"),
                         ("pad", "<i4")])
 HOT_DTYPE = np.dtype([("pos", "<i4"), ("span", "<u4"), ("fmk", "<u4"), ("pay", "<u4")])
-COLD_DTYPE = np.dtype([("cigar_off", "<u4"), ("n_cigar", "<u4"), ("l_qseq", "<u4"), ("reserved", "<u4")])
+COLD_DTYPE = np.dtype([("cigar_off", "<u4"), ("n_cigar", "<u4"), ("l_qseq", "<u4"), ("event", "<u4")])
 assert COUNTS_DTYPE.itemsize == 80 and STATS_DTYPE.itemsize == 72
 
 ST_KIND_MASK, ST_DEFERRED, ST_READLEN = 0x3, 0x10, 0x20
