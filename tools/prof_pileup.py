@@ -17,8 +17,9 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--tiles", type=int, default=200_000)
 ap.add_argument("--launches", type=int, default=6)
 ap.add_argument("--workload", default="wes")
+ap.add_argument("--snv-period", type=int, default=500, help="wes: one SNV per this many target bases (small = L2-resident reads, many units)")
 a = ap.parse_args()
-cfg = {"wes": lambda: synth.wes(n_tiles=a.tiles), "wgs": lambda: synth.wgs(contig_len=a.tiles * 4096 // 10),
+cfg = {"wes": lambda: synth.wes(n_tiles=a.tiles, snv_period=a.snv_period), "wgs": lambda: synth.wgs(contig_len=a.tiles * 4096 // 10),
        "amplicon": lambda: synth.amplicon(n_tiles=max(a.tiles // 100, 10))}[a.workload]()
 t0 = time.time()
 batch = synth.reads(cfg)

@@ -119,10 +119,22 @@ __device__ __forceinline__ unsigned long long gather_ld64(const unsigned long lo
     return __ldg(p);
 #endif
 }
-__device__ __forceinline__ uint32_t pay_lookup(const uint8_t *__restrict__ payload, uint32_t pay, uint32_t q) {
+// The load and the extraction are separate so that a caller can have several lookups in flight before
+// it consumes the first one (own base + mate base: one DRAM round trip instead of two).
+struct PayLoad {
+    unsigned long long granule;
+    uint32_t shift;
+};
+__device__ __forceinline__ PayLoad pay_issue(const uint8_t *__restrict__ payload, uint32_t pay, uint32_t q) {
     const uint32_t g = q / 5u, r = q - g * 5u;
-    const unsigned long long w = gather_ld64(reinterpret_cast<const unsigned long long *>(payload + ((size_t)pay << 5)) + g);
-    return (uint32_t)(w >> (12u * r)) & 0xFFFu;
+    PayLoad l;
+    l.granule = gather_ld64(reinterpret_cast<const unsigned long long *>(payload + ((size_t)pay << 5)) + g);
+    l.shift = 12u * r;
+    return l;
+}
+__device__ __forceinline__ uint32_t pay_word(const PayLoad &l) { return (uint32_t)(l.granule >> l.shift) & 0xFFFu; }
+__device__ __forceinline__ uint32_t pay_lookup(const uint8_t *__restrict__ payload, uint32_t pay, uint32_t q) {
+    return pay_word(pay_issue(payload, pay, q));
 }
 __device__ __forceinline__ int word_qual(uint32_t w) { return (int)(w & 0xFFu); }
 __device__ __forceinline__ int word_base(uint32_t w) { return (int)(w >> 8); }
@@ -265,45 +277,53 @@ __device__ __forceinline__ int64_t next_pushed(const ReadsDev &R, const vfk_para
 // Quality of query base q of read i as the reference sees it when column `col` is emitted:
 // htslib tweak_overlap_quality has run for the pair iff the second mate has been pushed, i.e. it
 // starts at or before `col` or is the first pushed record after it (bam_plp_auto reads one ahead).
+// `own` is the read's own payload lookup, already issued; it is consumed only after the mate's lookup
+// has been issued too.  Returns the quality; `my_word` receives the read's own payload word.
 __device__ __forceinline__ int tweaked_quality(const ReadsDev &R, const vfk_params &P, const Unit &U, int64_t i,
                                                const uint4 &hot, uint32_t mw, const uint4 &cold_if_general, bool general,
-                                               int q, int l_qseq, bool q_is_column_base, uint32_t my_word) {
+                                               int q, int l_qseq, bool q_is_column_base, const PayLoad &own, uint32_t &my_word) {
+    my_word = 0u;
     if (q >= l_qseq) return 0;
-    int qi = word_qual(my_word);
-    uint32_t flag = hot.z & 0xFFFFu;
-    if (!P.ignore_overlaps || !(flag & F_PROPER) || (flag & F_MUNMAP)) return qi;
-    if (mw == VFK_NO_MATE) return qi;
-    int64_t m = (int64_t)(mw & 0x7FFFFFFFu);
-    uint32_t sel = mw >> 31;
-    uint4 mh = __ldg(R.hot + m);
-    if (m > i && (int32_t)mh.x > U.col) {
-        if (q_is_column_base) return qi;  // the mate cannot cover this column
-        if (next_pushed(R, P, U.hi, U.c1, U.stop) != m) return qi;
+    const uint32_t flag = hot.z & 0xFFFFu;
+    bool paired = P.ignore_overlaps && (flag & F_PROPER) && !(flag & F_MUNMAP) && mw != VFK_NO_MATE;
+    PayLoad mate;
+    mate.granule = 0ull; mate.shift = 0u;
+    int64_t m = 0;
+    if (paired) {
+        m = (int64_t)(mw & 0x7FFFFFFFu);
+        const uint4 mh = __ldg(R.hot + m);
+        if (m > i && (int32_t)mh.x > U.col)  // the mate starts beyond the column: it can only matter to a base further on
+            paired = !q_is_column_base && next_pushed(R, P, U.hi, U.c1, U.stop) == m;
+        int32_t rp = -1;
+        if (paired) rp = q_is_column_base ? U.col : (general ? refpos_of_query(R, (int32_t)hot.x, cold_if_general, q)
+                                                             : (int32_t)hot.x + q);
+        paired = paired && rp >= (int32_t)mh.x && rp < (int32_t)mh.x + (int32_t)mh.y;  // rp < 0: not an aligned base
+        if (paired) {
+            int mq_index, ml;
+            if ((mh.z >> 24) == VFK_SHAPE_SIMPLE) {
+                mq_index = rp - (int32_t)mh.x;
+                ml = (int)mh.y;
+            } else {
+                const uint4 mc = __ldg(R.cold + m);
+                const Resolved mr = (mh.z >> 24) == VFK_SHAPE_ONE_EVENT ? resolve_one_event((int32_t)mh.x, mc, rp)
+                                                                        : resolve_general(R, (int32_t)mh.x, mc, rp);
+                paired = mr.covered && !mr.is_del;
+                mq_index = mr.qpos;
+                ml = mr.l_qseq;
+            }
+            paired = paired && mq_index < ml;
+            if (paired) mate = pay_issue(R.payload, mh.w, (uint32_t)mq_index);
+        }
     }
-    int32_t rp = q_is_column_base ? U.col : (general ? refpos_of_query(R, (int32_t)hot.x, cold_if_general, q)
-                                                     : (int32_t)hot.x + q);
-    if (rp < 0) return qi;
-    if (rp < (int32_t)mh.x || rp >= (int32_t)mh.x + (int32_t)mh.y) return qi;
-    int mq_index, ml;
-    if ((mh.z >> 24) == 0u) {
-        mq_index = rp - (int32_t)mh.x;
-        ml = (int)mh.y;
-    } else {
-        uint4 mc = __ldg(R.cold + m);
-        Resolved mr = (mh.z >> 24) == VFK_SHAPE_ONE_EVENT ? resolve_one_event((int32_t)mh.x, mc, rp)
-                                                          : resolve_general(R, (int32_t)mh.x, mc, rp);
-        if (!mr.covered || mr.is_del) return qi;
-        mq_index = mr.qpos;
-        ml = mr.l_qseq;
-    }
-    if (mq_index >= ml) return qi;
-    const uint32_t mate_word = pay_lookup(R.payload, mh.w, (uint32_t)mq_index);
-    int qm = word_qual(mate_word);
-    int bm = word_base(mate_word);
-    int bi = word_base(my_word);
-    bool i_first = i < m;  // the earlier record holds the hash slot ("a" in htslib)
-    uint32_t mymul = i_first ? sel : (1u - sel);
-    if (bi == bm) {
+    my_word = pay_word(own);
+    const int qi = word_qual(my_word);
+    if (!paired) return qi;
+    const uint32_t mate_word = pay_word(mate);
+    const int qm = word_qual(mate_word);
+    const bool i_first = i < m;  // the earlier record holds the hash slot ("a" in htslib)
+    const uint32_t sel = mw >> 31;
+    const uint32_t mymul = i_first ? sel : (1u - sel);
+    if (word_base(my_word) == word_base(mate_word)) {
         int s = qi + qm;
         if (s > 200) s = 200;
         return mymul ? s : 0;
@@ -404,8 +424,11 @@ __device__ __forceinline__ Eval evaluate_packed(const ReadsDev &R, const vfk_par
         }
     }
     o.fl |= FL_IN_COL;
-    const uint32_t my_word = r.qpos < r.l_qseq ? pay_lookup(R.payload, hot.w, (uint32_t)r.qpos) : 0u;
-    const int q = tweaked_quality(R, P, U, i, hot, mw, cold, general, r.qpos, r.l_qseq, !r.is_del, my_word);
+    PayLoad own;
+    own.granule = 0ull; own.shift = 0u;
+    if (r.qpos < r.l_qseq) own = pay_issue(R.payload, hot.w, (uint32_t)r.qpos);
+    uint32_t my_word;
+    const int q = tweaked_quality(R, P, U, i, hot, mw, cold, general, r.qpos, r.l_qseq, !r.is_del, own, my_word);
     if (q < P.min_baseq) return o;  // pysam pileup_base_qual_skip
     const uint32_t mq_pos = ((hot.z >> 16) & 0xFFu) | ((uint32_t)r.qpos << 16);
     if (U.kind == VFK_KIND_SNV) {

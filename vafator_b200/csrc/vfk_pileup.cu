@@ -196,20 +196,30 @@ __device__ __forceinline__ void accumulate(uint32_t *ref_slot, uint32_t *alt_slo
 // shallow path: one value per lane, ranks from bit-sliced comparisons
 // ------------------------------------------------------------------------------------------
 // For this lane's value v (NBITS wide): which contributing lanes hold a smaller value (lt) and
-// which an equal one (eq, itself included).  Walks the bits from the top, branch free; lanes that
-// do not contribute hold v == 0, so every ballot is already restricted to the contributing set.
+// which an equal one (eq, itself included).  Walks the bits from the top; lanes that do not contribute
+// hold v == 0, so every ballot is already restricted to the contributing set.  One step is a
+// predicate, a ballot and three predicated logic ops (written in PTX: the compiler's own lowering of the
+// same C++ spends eight instructions per bit on materialising the lane's bit as a mask).
+__device__ __forceinline__ void radix_step(uint32_t v, uint32_t bit_mask, uint32_t &lt, uint32_t &eq) {
+    asm("{\n"
+        ".reg .pred p;\n"
+        ".reg .b32 b, t;\n"
+        "and.b32 t, %2, %3;\n"
+        "setp.ne.u32 p, t, 0;\n"
+        "vote.sync.ballot.b32 b, p, 0xffffffff;\n"
+        "@p lop3.b32 %0, %0, %1, b, 0xF4;\n"  // mine set:   lt |= eq & ~b   (equal so far, their bit clear)
+        "@p and.b32 %1, %1, b;\n"             //             eq &= b
+        "@!p lop3.b32 %1, %1, b, 0, 0x30;\n"  // mine clear: eq &= ~b
+        "}\n"
+        : "+r"(lt), "+r"(eq)
+        : "r"(v), "r"(bit_mask));
+}
 template <int NBITS>
 __device__ __forceinline__ void radix_compare(uint32_t v, uint32_t contributing, uint32_t &lt, uint32_t &eq) {
     lt = 0u;
     eq = contributing;
 #pragma unroll
-    for (int bit = NBITS - 1; bit >= 0; --bit) {
-        const uint32_t mine = (v >> bit) & 1u;
-        const uint32_t b = __ballot_sync(FULL, mine);
-        const uint32_t m = 0u - mine;  // all ones when this lane's bit is set
-        lt |= eq & ~b & m;             // equal so far, their bit clear, mine set
-        eq &= b ^ ~m;                  // keep the lanes whose bit equals mine
-    }
+    for (int bit = NBITS - 1; bit >= 0; --bit) radix_step(v, 1u << bit, lt, eq);
 }
 
 // Medians of the REF / ALT lists and this lane's share of the ALT mid-rank sum, from the lt / eq masks.
