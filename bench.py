@@ -322,22 +322,30 @@ def main():
         for _ in range(2):
             e2e_step()
         barrier()
+        ts0 = dev.transfer_stats()
         t0 = time.perf_counter()
         n_e2e = max(3, min(args.steps, 5))
         for _ in range(n_e2e):
             e2e_step()
         torch.cuda.synchronize()
         dt_e2e = (time.perf_counter() - t0) / n_e2e
+        ts1 = dev.transfer_stats()
         assert np.array_equal(c_out["tumor"]["dp"], c_host["dp"]) and np.array_equal(c_out["tumor"]["ac_alt"], c_host["ac_alt"])
-        zc = dev.zero_copy_batches() > 0
-        if zc:  # payload / cold / cigar stay in pinned host memory and are gathered on demand: count what crossed
-            staged = sum(w["packed"][s].hot.nbytes + w["packed"][s].mate.nbytes + w["packed"][s].sb.nbytes for s in samples)
-            gathered = int(len(samples) * nu * n_cand * 64)  # one payload sector + cold/partner share per candidate read
-            h2d = staged + gathered + len(samples) * (nu * (5 * 4 + 8) + units.ins_seq.nbytes)
-        else:
-            h2d = sum(w["packed"][s].nbytes() for s in samples) + len(samples) * (nu * (5 * 4 + 8) + units.ins_seq.nbytes)
+        n_batches = n_e2e * len(samples)
+        zc = (ts1["zero_copy_batches"] - ts0["zero_copy_batches"]) / n_batches
+        zc_hot = (ts1["zero_copy_hot_batches"] - ts0["zero_copy_hot_batches"]) / n_batches
+        host_loc = (ts1["host_located_batches"] - ts0["host_located_batches"]) / n_batches
+        # bytes the library copied in bulk (counted by the library) + what the kernels gathered from pinned host
+        # memory: per candidate read one 32-byte payload sector plus the overlap partner's / cold record's share
+        # (~64 B), and its 20-byte header when the hot / mate arrays are gathered too
+        h2d = (ts1["staged_bytes"] - ts0["staged_bytes"]) / n_e2e
+        h2d += len(samples) * nu * n_cand * (64.0 * zc + 20.0 * zc_hot)
+        transfer = ("units located %s; headers %s; payload + cold + CIGAR %s; two batches in flight (double buffered)" % (
+            "on the host (32 B per unit copied, no index transfer)" if host_loc > 0.5 else "by the locate kernel (index staged)",
+            "gathered by the kernel from pinned host memory" if zc_hot > 0.5 else "staged by async copies",
+            "gathered by the kernel from pinned host memory (zero copy)" if zc > 0.5 else "staged by async copies"))
         d2h = len(samples) * nu * (device.COUNTS_DTYPE.itemsize + device.STATS_DTYPE.itemsize)
-        e2e = (dt_e2e, h2d, d2h, zc)
+        e2e = (dt_e2e, h2d, d2h, transfer)
 
     # ---- max over ranks ----
     if dist is not None:
@@ -385,10 +393,7 @@ def main():
             "e2e": None if e2e is None else {"value": units_total_per_step / e2e[0], "unit": "units/s",
                                             "h2d_bytes_per_step": int(e2e[1]), "d2h_bytes_per_step": int(e2e[2]),
                                             "ms_per_step": 1e3 * e2e[0],
-                                            "transfer": "hot/mate/index arrays staged by async copies from pinned memory, "
-                                                        "double buffered; payload + cold + CIGAR sectors gathered by the "
-                                                        "kernel from pinned host memory (zero copy)" if e2e[3] else
-                                                        "whole batch staged by async copies from pinned memory, double buffered"},
+                                            "transfer": e2e[3]},
             "gpu_launches": int(launches), "clocks": clk,
         }
         print(json.dumps(line))

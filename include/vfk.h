@@ -173,16 +173,26 @@ int vfk_annotate_host(vfk_handle *h, const vfk_read_batch *reads, const vfk_vari
 
 /* Double-buffered variant: returns once the batch is enqueued on one of the handle's two staging
  * slots; *ticket (0 or 1) names the slot.  Submitting a third batch waits for the slot it reuses.
- * The host buffers (inputs and outputs) must stay valid until vfk_wait(h, ticket) returns.  When the
- * payload / cold / cigar buffers are page-locked and the variant set is sparse, the kernel gathers
- * the sectors it needs directly from host memory instead of copying those arrays
- * (VFK_ZERO_COPY_PAYLOAD=0/1 in the environment forces the choice).                               */
+ * The host buffers (inputs and outputs) must stay valid until vfk_wait(h, ticket) returns.
+ * How a batch crosses the bus is chosen per batch:
+ *  - sparse variant set (n_units * 64 <= n_reads): the units are located on the host from the
+ *    caller's position index, 32 bytes per unit are copied and the index is not; otherwise the
+ *    index is copied and the locate kernel runs            (VFK_HOST_LOCATE=0/1 forces the choice);
+ *  - page-locked payload / cold / cigar buffers and few candidate reads: the kernel gathers the
+ *    sectors it needs straight from host memory instead of copying those arrays
+ *    (VFK_ZERO_COPY_PAYLOAD=0/1), and so it does for the hot / mate arrays if they are page-locked
+ *    too (VFK_ZERO_COPY_HOT=0 keeps copying them).
+ * Results are identical whichever way is taken.                                                   */
 int vfk_annotate_host_async(vfk_handle *h, const vfk_read_batch *reads, const vfk_variant_batch *units,
                             const vfk_params *params, const double *eaf, double fpr, double error_rate,
                             vfk_counts *counts_out, vfk_stats *stats_out, int *ticket);
 int vfk_wait(vfk_handle *h, int ticket);
 /* how many batches of this handle took the zero-copy route */
 int64_t vfk_zero_copy_batches(vfk_handle *h);
+/* transfer accounting of the host entry point since vfk_create: out[0] bytes copied host -> device by
+ * bulk copies, out[1] batches whose payload was gathered (zero copy), out[2] batches whose hot / mate
+ * headers were gathered too, out[3] batches located on the host                                    */
+int vfk_transfer_stats(vfk_handle *h, int64_t out[4]);
 
 /* ---- list-shaped auxiliaries (DEVICE pointers) ------------------------------------------------
  * vfk_pileup_values: per unit, the per-read values the reference keeps in all_mqs / all_bqs /

@@ -185,3 +185,40 @@ def test_degenerate_inputs(dev):
     dev.sync()
     got = dev.to_host(buf, device.COUNTS_DTYPE, units.n_units)
     assert got["dp"].tolist() == [1, 1, 0, 0] and got["n_cover"].tolist() == [3, 3, 0, 0] and got["ac_ref"].tolist() == [1, 1, 0, 0]
+
+
+@pytest.mark.parametrize("pinned", [False, True], ids=["pageable", "pinned"])
+def test_host_entry_point_transfer_strategies(dev, pinned, monkeypatch):
+    """vfk_annotate_host moves a batch in one of several ways (units located on the host or by the locate
+    kernel; headers / payload staged or gathered from page-locked memory): every combination returns
+    exactly what the device-pointer entry points return, for VCF-ordered and for shuffled units."""
+    from dataclasses import replace
+    cfg = synth.wes(n_tiles=3000, indel_period=700, multiallelic_pct=5)
+    batch, recs, units, stop, _ = _setup(cfg)
+    rng = np.random.default_rng(11)
+    perm = rng.permutation(units.n_units)
+    shuffled = replace(units, tid=units.tid[perm], pos=units.pos[perm], meta=units.meta[perm], length=units.length[perm],
+                       seq_off=units.seq_off[perm], rec=units.rec[perm], alt_index=units.alt_index[perm])
+    params = device.make_params(min_mapq=1, min_baseq=30)
+    packed = device.pack_reads(batch, params, pinned=pinned)
+    dreads = dev.upload_reads(packed)
+    eaf = np.full(units.n_units, 0.4)
+    for u, s in ((units, stop), (shuffled, stop[perm])):
+        counts_dev = dev.pileup(dreads, dev.upload_units(u, s), params)
+        stats_dev = dev.epilogue(u.n_units, counts_dev, dev.torch.as_tensor(eaf, device=dev.device), 5e-7, 1e-3)
+        dev.sync()
+        want_c = dev.to_host(counts_dev, device.COUNTS_DTYPE, u.n_units)
+        want_s = dev.to_host(stats_dev, device.STATS_DTYPE, u.n_units)
+        modes = [dict(VFK_HOST_LOCATE=a, VFK_ZERO_COPY_PAYLOAD=b, VFK_ZERO_COPY_HOT=c)
+                 for a in "01" for b in "01" for c in "01"] + [dict()]
+        for env in modes:
+            for k in ("VFK_HOST_LOCATE", "VFK_ZERO_COPY_PAYLOAD", "VFK_ZERO_COPY_HOT"):
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            before = dev.zero_copy_batches()
+            got_c, got_s = dev.annotate_host(packed, u, s, params, eaf, 5e-7, 1e-3)
+            assert got_c.tobytes() == want_c.tobytes(), env
+            assert got_s.tobytes() == want_s.tobytes(), env
+            if env.get("VFK_ZERO_COPY_PAYLOAD") == "1":
+                assert (dev.zero_copy_batches() > before) == pinned

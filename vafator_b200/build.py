@@ -19,7 +19,7 @@ LIBVFK = os.path.join(PKG, "libvfk.so")
 LIBVFKIO = os.path.join(PKG, "libvfkio.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "-I", INCLUDE]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-shared", "-I", INCLUDE]
 CXX_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-I", INCLUDE]
 
 
@@ -42,7 +42,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))
     if force or _stale(LIBVFK, deps):
         extra = os.environ.get("VFK_NVCC_EXTRA", "").split()
-        cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIBVFK] + srcs
+        cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIBVFK] + srcs + ["-lgomp"]
         subprocess.check_call(cmd)
     return LIBVFK
 

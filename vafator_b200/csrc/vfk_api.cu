@@ -5,6 +5,9 @@
 #include <string.h>
 #include <new>
 #include "vfk.h"
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include "vfk_device.cuh"
 
 namespace vfk {
@@ -59,6 +62,27 @@ struct DevBuf {
     }
 };
 
+struct PinBuf {  // page-locked host scratch
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return VFK_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e != cudaSuccess) return fail(VFK_ENOMEM, "cudaHostAlloc: %s", cudaGetErrorString(e));
+        cap = want;
+        return VFK_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
 // One of the two staging slots of the host entry point: its own stream, device staging buffers and
 // scratch, so that the copies of one batch overlap the kernels of the previous one (double buffering).
 struct Slot {
@@ -68,12 +92,14 @@ struct Slot {
     void *counters = nullptr;             // 32 B: work counter, deferred count, candidate sum
     unsigned long long *h_cand = nullptr;  // pinned host word for the candidate sum
     DevBuf deferred, resolved;
+    PinBuf h_resolved;  // units located on the host (sparse variant sets), copied to `resolved`
     DevBuf contig, hot, cold, mate, sb, cigar, payload;
     DevBuf tid, pos, meta, len, soff, ins, stop, eaf, counts, stats;
     void release() {
         DevBuf *bufs[] = {&deferred, &resolved, &contig, &hot, &cold, &mate, &sb, &cigar, &payload, &tid, &pos, &meta, &len,
                           &soff, &ins, &stop, &eaf, &counts, &stats};
         for (DevBuf *b : bufs) b->release();
+        h_resolved.release();
         if (counters) cudaFree(counters);
         if (h_cand) cudaFreeHost(h_cand);
         if (done) cudaEventDestroy(done);
@@ -89,7 +115,7 @@ struct vfk_handle {
     int64_t launches = 0;
     Slot slot[2];
     int next_slot = 0;
-    int64_t zero_copy_batches = 0;
+    int64_t zero_copy_batches = 0, zero_copy_hot_batches = 0, host_located_batches = 0, staged_bytes = 0;
     // Carter k / d per depth for the last (fpr, error_rate) seen, depths [0, CARTER_DEPTHS)
     DevBuf carter;
     double carter_fpr = -1.0, carter_err = -1.0;
@@ -291,6 +317,7 @@ extern "C" int vfk_ranksum_values(vfk_handle *h, int64_t n_pairs, const uint32_t
         int rc_ = (buf).reserve(b_ ? b_ : 16);                                                   \
         if (rc_) return rc_;                                                                     \
         if (b_) CU(cudaMemcpyAsync((buf).p, (src), b_, cudaMemcpyHostToDevice, st));             \
+        h->staged_bytes += (int64_t)b_;                                                          \
     } while (0)
 
 // device-visible alias of a page-locked host buffer, or NULL
@@ -300,6 +327,61 @@ static const void *pinned_alias(const void *host) {
     if (host && cudaPointerGetAttributes(&attr, host) == cudaSuccess && attr.type == cudaMemoryTypeHost) dev = attr.devicePointer;
     (void)cudaGetLastError();
     return dev;
+}
+
+// Host twin of locate_kernel (vfk_pileup.cu) for the host entry point: when the variant set is sparse the
+// position index (8 bytes per read) is not worth shipping -- the units are located here, from the
+// caller's host arrays, and only the 32-byte records cross the bus.  VCF order makes consecutive units
+// neighbours in the index, so each search gallops forward from the previous answer.
+static unsigned long long locate_host(const vfk_read_batch *r, const vfk_variant_batch *v, vfk::ResolvedUnit *out) {
+    const int64_t nu = v->n_units;
+    const int32_t *sb = r->sb;
+    unsigned long long total = 0;
+#pragma omp parallel reduction(+ : total)
+    {
+        int nt = 1, me = 0;
+#ifdef _OPENMP
+        nt = omp_get_num_threads();
+        me = omp_get_thread_num();
+#endif
+        const int64_t u0 = nu * me / nt, u1 = nu * (me + 1) / nt;
+        int32_t prev_tid = -1, prev_col = 0;
+        int64_t prev_a = 0;
+        for (int64_t u = u0; u < u1; ++u) {
+            const int32_t tid = v->tid[u], col = v->pos[u];
+            const bool known = tid >= 0 && tid < r->n_contigs;
+            const int64_t c0 = known ? r->contig_off[tid] : 0, c1 = known ? r->contig_off[tid + 1] : 0;
+            int64_t a = c0, b = c1;  // first read of the contig starting beyond the column lies in [a, b]
+            if (known && tid == prev_tid && col >= prev_col) {
+                a = prev_a;
+                int64_t step = 32;
+                while (a + step < c1 && sb[2 * (a + step)] <= col) {
+                    a += step;
+                    step <<= 1;
+                }
+                b = a + step < c1 ? a + step : c1;
+            }
+            while (a < b) {
+                const int64_t m = (a + b) >> 1;
+                if (sb[2 * m] > col) b = m; else a = m + 1;
+            }
+            vfk::ResolvedUnit q;
+            q.col = col;
+            q.meta = v->meta[u];
+            q.len = v->length[u];
+            q.ins_off = v->seq_off[u];
+            q.hi = (uint32_t)a;
+            q.lo = a > c0 ? (uint32_t)sb[2 * (a - 1) + 1] : (uint32_t)a;
+            q.stop = v->stop ? v->stop[u] : 0x7FFFFFFF;
+            q.c1 = (uint32_t)c1;
+            out[u] = q;
+            total += q.hi - q.lo;
+            prev_tid = known ? tid : -1;
+            prev_col = col;
+            prev_a = a;
+        }
+    }
+    return total;
 }
 
 extern "C" int vfk_wait(vfk_handle *h, int ticket) {
@@ -330,40 +412,55 @@ extern "C" int vfk_annotate_host_async(vfk_handle *h, const vfk_read_batch *read
     Slot &S = h->slot[si];
     cudaStream_t st = S.stream;
     unsigned long long *cand_sum = (unsigned long long *)((char *)S.counters + 24);
-    // ---- stage 1: what the locate pass needs
-    STAGE(S.contig, reads->contig_off, (size_t)(reads->n_contigs + 1) * sizeof(int64_t));
-    STAGE(S.sb, reads->sb, (size_t)nr * 8);
-    STAGE(S.tid, units->tid, (size_t)nu * 4);
-    STAGE(S.pos, units->pos, (size_t)nu * 4);
-    STAGE(S.meta, units->meta, (size_t)nu * 4);
-    STAGE(S.len, units->length, (size_t)nu * 4);
-    STAGE(S.soff, units->seq_off, (size_t)nu * 4);
-    STAGE(S.ins, units->ins_seq, (size_t)(units->n_ins_seq > 0 ? units->n_ins_seq : 1));
-    if (units->stop) STAGE(S.stop, units->stop, (size_t)nu * 4);
+    // ---- locate.  Sparse variant set (the usual case: a VCF against a whole BAM): on the host, no index
+    // transfer; otherwise the index and the unit arrays are staged and the locate kernel runs.
     rc = S.deferred.reserve((size_t)nu * 2 * sizeof(uint32_t));
     if (rc) return rc;
-    rc = S.resolved.reserve((size_t)nu * 32);
+    rc = S.resolved.reserve((size_t)nu * sizeof(vfk::ResolvedUnit));
     if (rc) return rc;
+    STAGE(S.ins, units->ins_seq, (size_t)(units->n_ins_seq > 0 ? units->n_ins_seq : 1));
     vfk_read_batch dr = *reads;
-    dr.contig_off = (const int64_t *)S.contig.p;
-    dr.sb = (const int32_t *)S.sb.p;
     vfk_variant_batch dv = *units;
-    dv.tid = (const int32_t *)S.tid.p;
-    dv.pos = (const int32_t *)S.pos.p;
-    dv.meta = (const uint32_t *)S.meta.p;
-    dv.length = (const int32_t *)S.len.p;
-    dv.seq_off = (const uint32_t *)S.soff.p;
     dv.ins_seq = (const uint8_t *)S.ins.p;
-    dv.stop = units->stop ? (const int32_t *)S.stop.p : nullptr;
+    int launches = 0;
+    CU(cudaMemsetAsync(S.counters, 0, 32, st));
+    const char *env_loc = getenv("VFK_HOST_LOCATE");
+    const bool host_locate = env_loc ? env_loc[0] == '1' : nu * 64 <= nr;
+    unsigned long long candidates = 0;
+    if (host_locate) {
+        rc = S.h_resolved.reserve((size_t)nu * sizeof(vfk::ResolvedUnit));
+        if (rc) return rc;
+        candidates = locate_host(reads, units, (vfk::ResolvedUnit *)S.h_resolved.p);
+        CU(cudaMemcpyAsync(S.resolved.p, S.h_resolved.p, (size_t)nu * sizeof(vfk::ResolvedUnit), cudaMemcpyHostToDevice, st));
+        h->staged_bytes += (int64_t)nu * (int64_t)sizeof(vfk::ResolvedUnit);
+        ++h->host_located_batches;
+    } else {
+        STAGE(S.contig, reads->contig_off, (size_t)(reads->n_contigs + 1) * sizeof(int64_t));
+        STAGE(S.sb, reads->sb, (size_t)nr * 8);
+        STAGE(S.tid, units->tid, (size_t)nu * 4);
+        STAGE(S.pos, units->pos, (size_t)nu * 4);
+        STAGE(S.meta, units->meta, (size_t)nu * 4);
+        STAGE(S.len, units->length, (size_t)nu * 4);
+        STAGE(S.soff, units->seq_off, (size_t)nu * 4);
+        if (units->stop) STAGE(S.stop, units->stop, (size_t)nu * 4);
+        dr.contig_off = (const int64_t *)S.contig.p;
+        dr.sb = (const int32_t *)S.sb.p;
+        dv.tid = (const int32_t *)S.tid.p;
+        dv.pos = (const int32_t *)S.pos.p;
+        dv.meta = (const uint32_t *)S.meta.p;
+        dv.length = (const int32_t *)S.len.p;
+        dv.seq_off = (const uint32_t *)S.soff.p;
+        dv.stop = units->stop ? (const int32_t *)S.stop.p : nullptr;
+    }
     vfk::ReadsDev R;
     vfk::UnitsDev V;
     to_dev(&dr, &dv, R, V);
-    int launches = 0;
-    CU(cudaMemsetAsync(S.counters, 0, 32, st));
-    cudaError_t e = vfk::launch_locate(R, V, S.resolved.p, cand_sum, st, &launches);
-    if (e != cudaSuccess) return fail(VFK_ECUDA, "locate launch: %s", cudaGetErrorString(e));
-    // ---- transfer strategy for the bulk of the batch (payload ~84 %, cold records + CIGARs ~6 %):
-    // a sparse variant set touches a few percent of those bytes, so when the caller's buffers are
+    if (!host_locate) {
+        cudaError_t e = vfk::launch_locate(R, V, S.resolved.p, cand_sum, st, &launches);
+        if (e != cudaSuccess) return fail(VFK_ECUDA, "locate launch: %s", cudaGetErrorString(e));
+    }
+    // ---- transfer strategy for the bulk of the batch (payload ~84 %, headers ~10 %, cold records + CIGARs
+    // ~6 %): a sparse variant set touches a few percent of those bytes, so when the caller's buffers are
     // page-locked the kernel gathers the sectors it needs straight from host memory over PCIe
     // ("zero copy") instead of staging everything.  Decided from the located candidate count.
     const void *z_payload = pinned_alias(reads->payload), *z_cold = pinned_alias(reads->cold),
@@ -371,22 +468,31 @@ extern "C" int vfk_annotate_host_async(vfk_handle *h, const vfk_read_batch *read
     bool zero_copy = z_payload && z_cold && (z_cigar || reads->n_cigar_words == 0);
     if (const char *env = getenv("VFK_ZERO_COPY_PAYLOAD")) zero_copy = zero_copy && env[0] == '1';
     if (zero_copy && !getenv("VFK_ZERO_COPY_PAYLOAD")) {
-        CU(cudaMemcpyAsync(S.h_cand, cand_sum, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+        if (!host_locate) {
+            CU(cudaMemcpyAsync(S.h_cand, cand_sum, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            candidates = *S.h_cand;
+        }
         // ~64 bytes cross the bus per candidate read when gathering; staging moves everything once
-        const double gathered = (double)*S.h_cand * 64.0;
+        const double gathered = (double)candidates * 64.0;
         const double staged = (double)reads->n_sectors * 32.0 + (double)nr * 16.0 + (double)reads->n_cigar_words * 4.0;
         zero_copy = gathered * 4.0 < staged;
     }
     // ---- stage 2
-    STAGE(S.hot, reads->hot, (size_t)nr * sizeof(vfk_read_hot));
-    STAGE(S.mate, reads->mate, (size_t)nr * 4);
+    const void *z_hot = pinned_alias(reads->hot), *z_mate = pinned_alias(reads->mate);
+    const char *env_hot = getenv("VFK_ZERO_COPY_HOT");  // the 20-byte headers follow the payload unless told otherwise
+    const bool zero_copy_hot = zero_copy && z_hot && z_mate && !(env_hot && env_hot[0] == '0');
+    if (!zero_copy_hot) {
+        STAGE(S.hot, reads->hot, (size_t)nr * sizeof(vfk_read_hot));
+        STAGE(S.mate, reads->mate, (size_t)nr * 4);
+    }
     STAGE(S.eaf, eaf, (size_t)nu * sizeof(double));
     if (zero_copy) {
         R.cold = (const uint4 *)z_cold;
         R.cigar = (const uint32_t *)z_cigar;
         R.payload = (const uint8_t *)z_payload;
         ++h->zero_copy_batches;
+        if (zero_copy_hot) ++h->zero_copy_hot_batches;
     } else {
         STAGE(S.cold, reads->cold, (size_t)nr * sizeof(vfk_read_cold));
         STAGE(S.cigar, reads->cigar, (size_t)reads->n_cigar_words * 4);
@@ -395,14 +501,14 @@ extern "C" int vfk_annotate_host_async(vfk_handle *h, const vfk_read_batch *read
         R.cigar = (const uint32_t *)S.cigar.p;
         R.payload = (const uint8_t *)S.payload.p;
     }
-    R.hot = (const uint4 *)S.hot.p;
-    R.mate = (const uint32_t *)S.mate.p;
+    R.hot = zero_copy_hot ? (const uint4 *)z_hot : (const uint4 *)S.hot.p;
+    R.mate = zero_copy_hot ? (const uint32_t *)z_mate : (const uint32_t *)S.mate.p;
     rc = S.counts.reserve((size_t)nu * sizeof(vfk_counts));
     if (rc) return rc;
     rc = S.stats.reserve((size_t)nu * sizeof(vfk_stats));
     if (rc) return rc;
-    e = vfk::launch_pileup_resolved(R, V, *params, reads->max_l_qseq, (vfk_counts *)S.counts.p, S.resolved.p, S.counters,
-                                    (uint32_t *)S.deferred.p, h->sm_count, st, &launches);
+    cudaError_t e = vfk::launch_pileup_resolved(R, V, *params, reads->max_l_qseq, (vfk_counts *)S.counts.p, S.resolved.p, S.counters,
+                                                (uint32_t *)S.deferred.p, h->sm_count, st, &launches);
     if (e != cudaSuccess) return fail(VFK_ECUDA, "pileup launch: %s", cudaGetErrorString(e));
     rc = ensure_carter(h, fpr, error_rate, st);
     if (rc) return rc;
@@ -427,3 +533,11 @@ extern "C" int vfk_annotate_host(vfk_handle *h, const vfk_read_batch *reads, con
 }
 
 extern "C" int64_t vfk_zero_copy_batches(vfk_handle *h) { return h ? h->zero_copy_batches : 0; }
+extern "C" int vfk_transfer_stats(vfk_handle *h, int64_t out[4]) {
+    if (!h || !out) return fail(VFK_EINVAL, "vfk_transfer_stats: NULL argument");
+    out[0] = h->staged_bytes;
+    out[1] = h->zero_copy_batches;
+    out[2] = h->zero_copy_hot_batches;
+    out[3] = h->host_located_batches;
+    return VFK_OK;
+}

@@ -115,6 +115,8 @@ def libvfk():
         lib.vfk_wait.argtypes = [C.c_void_p, C.c_int]
         lib.vfk_zero_copy_batches.restype = C.c_int64
         lib.vfk_zero_copy_batches.argtypes = [C.c_void_p]
+        lib.vfk_transfer_stats.restype = C.c_int
+        lib.vfk_transfer_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         lib.vfk_annotate_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                           C.c_double, C.c_void_p, C.c_void_p]
         _libvfk = lib
@@ -416,6 +418,13 @@ class Device:
 
     def zero_copy_batches(self) -> int:
         return int(self.lib.vfk_zero_copy_batches(self.h))
+
+    def transfer_stats(self) -> Dict[str, int]:
+        """Host entry point accounting since the handle was created (vfk_transfer_stats)."""
+        out = (C.c_int64 * 4)()
+        _check(self.lib.vfk_transfer_stats(self.h, out))
+        return dict(staged_bytes=int(out[0]), zero_copy_batches=int(out[1]), zero_copy_hot_batches=int(out[2]),
+                    host_located_batches=int(out[3]))
 
     def to_host(self, buf, dtype, n):
         return buf.cpu().numpy().view(dtype)[:n].copy()
