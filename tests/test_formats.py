@@ -115,3 +115,38 @@ def test_decoder_on_the_references_real_bams():
     assert (ops[2], ops[1], ops[4]) == (34, 18, 124)  # D / I / S operations
     assert int(np.count_nonzero((r.flag & 4) == 0)) == 638 and set(np.unique(r.l_qseq)) == {101}
     r.check_sorted()
+
+
+# ---- multiallelics-filter against the reference run on the same inputs ----
+def test_multiallelic_filter_matches_reference_golden(tmp_path):
+    """tests/golden/multiallelic.json: outputs of the UNMODIFIED reference filter (oracle/gen_golden_multiallelic.py)."""
+    import json
+    import os
+    from vafator_b200.multiallelic_filter import MultiallelicFilter
+    golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "multiallelic.json")))
+    assert len(golden) >= 9
+    for name, case in golden.items():
+        src, dst = tmp_path / (name + ".vcf"), tmp_path / (name + ".out.vcf")
+        src.write_text(case["input"])
+        MultiallelicFilter(input_vcf=str(src), output_vcf=str(dst), tumor_sample_name=case["sample"]).run()
+        got = [l for l in dst.read_text().split("\n") if l and not l.startswith("##vafator_command_line=")]
+        assert got == case["output"], name
+        assert any(l.startswith("##vafator_command_line=") for l in dst.read_text().split("\n"))
+    # the float32 widening and the leading comma of a first annotation are what the reference emits
+    pairs = [l for l in golden["pairs"]["output"] if l.startswith("chr4\t1235")]
+    assert len(pairs) == 1 and pairs[0].endswith("multiallelic=,T,0.10000000149011612")
+
+
+def test_multiallelic_filter_cli_and_empty_input(tmp_path):
+    from vafator_b200.command_line import multiallelics_filter
+    src, dst = tmp_path / "in.vcf", tmp_path / "out.vcf.gz"
+    src.write_text("##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n"
+                   "1\t5\t.\tA\tC\t.\t.\tt_af=0.5\n1\t5\t.\tA\tG\t.\t.\tt_af=0.75\n")
+    multiallelics_filter(["--input-vcf", str(src), "--output-vcf", str(dst), "--tumor-sample-name", "t"])
+    import gzip
+    body = [l for l in gzip.open(dst, "rt").read().split("\n") if l and not l.startswith("#")]
+    assert body == ["1\t5\t.\tA\tG\t.\t.\tt_af=0.75;multiallelic=,C,0.5"]
+    empty = tmp_path / "empty.vcf"
+    empty.write_text("##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n")
+    multiallelics_filter(["--input-vcf", str(empty), "--output-vcf", str(tmp_path / "e.out.vcf")])
+    assert [l for l in (tmp_path / "e.out.vcf").read_text().split("\n") if l and not l.startswith("#")] == []

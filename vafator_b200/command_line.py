@@ -94,5 +94,21 @@ def annotator(argv=None):
     logging.info("Vafator finished!")
 
 
+def multiallelics_filter(argv=None):
+    """`multiallelics-filter` (vafator/command_line.py:208-247): a host-only pass over the annotated VCF."""
+    import vafator_b200
+    parser = argparse.ArgumentParser(description="vafator v{}".format(vafator_b200.VERSION),
+                                     formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    parser.add_argument("--input-vcf", dest="input_vcf", action="store", help="The VCF to annotate", required=True)
+    parser.add_argument("--output-vcf", dest="output_vcf", action="store", help="The annotated VCF", required=True)
+    parser.add_argument("--tumor-sample-name", dest="tumor_sample_name", action="store", default="tumor",
+                        help="The tumor sample name (will look for annotation ${SAMPLE_NAME}_af)")
+    args = parser.parse_args(argv)
+    logging.info("Vafator multiallelic filter starting...")
+    from vafator_b200.multiallelic_filter import MultiallelicFilter
+    MultiallelicFilter(input_vcf=args.input_vcf, output_vcf=args.output_vcf, tumor_sample_name=args.tumor_sample_name).run()
+    logging.info("Vafator multiallelic filter finished!")
+
+
 if __name__ == "__main__":
     annotator()
