@@ -25,7 +25,13 @@ namespace vfk {
 #define VFK_MIN_CTAS 4
 #endif
 constexpr int WARPS_PER_CTA = 8;
-constexpr int GRAB = 8;  // units a warp takes per visit to the global counter (<= 32)
+#ifndef VFK_GRAB
+#define VFK_GRAB 8
+#endif
+// Units a warp takes per visit to the global counter (<= 32).  A launch hands every warp only ~20 units, so
+// the grabs shrink towards the end of the unit list (guided self-scheduling): GRAB while more than 16 units
+// per warp are left, 2 below that, 1 for the last 4 per warp -- the tail is then a unit, not a grab, long.
+constexpr int GRAB = VFK_GRAB;
 constexpr int WARP_PATH_MAX_CAND = 32767;  // u16 bins, weight <= 2 per read
 
 template <int POSB>
@@ -361,13 +367,18 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t *stage = stage_all[warp];
+    const int64_t n_warps = (int64_t)gridDim.x * WARPS_PER_CTA;
+    int64_t last_base = 0;
 
     for (;;) {
         unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(work_counter, (unsigned long long)GRAB);
+        const int64_t left = n_units - last_base;  // as of this warp's previous visit
+        const int grab = left > 16 * n_warps ? GRAB : left > 4 * n_warps ? 2 : 1;
+        if (lane == 0) base = atomicAdd(work_counter, (unsigned long long)grab);
         base = __shfl_sync(FULL, base, 0);
         if ((int64_t)base >= n_units) break;
-        const int n_here = (int)min((int64_t)GRAB, n_units - (int64_t)base);
+        last_base = (int64_t)base;
+        const int n_here = (int)min((int64_t)grab, n_units - (int64_t)base);
         // lane j keeps the record of unit base+j; one coalesced read for the whole grab
         uint4 ra = make_uint4(0, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
         if (lane < n_here) {
