@@ -17,8 +17,11 @@
  * library keeps no reference to them after the stream work it enqueued has completed.  Calls
  * are asynchronous with respect to the host until vfk_sync() (except vfk_annotate_host, which
  * returns after its results are in host memory).  `stream` is a cudaStream_t passed as void*
- * (NULL = the CUDA default stream; the handle's own stream is used by vfk_annotate_host only).  One handle per device; different handles may be driven
- * from different host threads.
+ * (NULL = the CUDA default stream; the handle's own streams are used by vfk_annotate_host only).
+ * A handle belongs to one device and owns per-launch scratch (located units, deferred-unit lists):
+ * drive it from one host thread at a time and keep the vfk_pileup calls of one handle on one stream
+ * (stream order is what protects the scratch); use one handle per stream / per host thread for
+ * concurrency.  Different handles are independent.
  */
 #ifndef VFK_H
 #define VFK_H
