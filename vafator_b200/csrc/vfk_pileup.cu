@@ -44,9 +44,9 @@ struct Layout {
 };
 
 // ------------------------------------------------------------------------------------------
-// locate pass: one THREAD per unit.  A binary search is a chain of dependent loads; with one
-// thread per unit every unit's chain is in flight at once, which a warp-cooperative search
-// cannot offer.  Emits the 32-byte ResolvedUnit records the pileup kernels consume.
+// locate pass: one THREAD per unit.  A search is a chain of dependent loads; with one thread per
+// unit every unit's chain is in flight at once, which a warp-cooperative search cannot offer.
+// Emits the 32-byte ResolvedUnit records the pileup kernels consume.
 //   hi = first read of the contig starting beyond the column
 //   lo = back[hi-1] = first read whose running-maximum end exceeds start[hi-1] (<= col):
 //        no earlier read can overlap the column
@@ -59,10 +59,27 @@ locate_kernel(ReadsDev R, UnitsDev V, ResolvedUnit *__restrict__ res, unsigned l
     const int32_t col = __ldg(V.pos + u);
     const bool known = tid >= 0 && tid < R.n_contigs;  // an unknown contig gets an empty read range
     const int64_t c0 = known ? __ldg(R.contig_off + tid) : 0, c1 = known ? __ldg(R.contig_off + tid + 1) : 0;
+    // first read of the contig starting beyond the column, in [a, b]: an 8-ary search -- seven independent probes
+    // per step, so the chain of dependent loads is 8 long for a 14 M-read batch instead of 24
     int64_t a = c0, b = c1;
-    while (a < b) {
-        const int64_t m = (a + b) >> 1;
-        if (__ldg(&R.sb[m].x) > col) b = m; else a = m + 1;
+    while (b - a > 8) {
+        const int64_t step = (b - a) >> 3;
+        int32_t v[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) v[j] = __ldg(&R.sb[a + (j + 1) * step].x);
+        int c = 0;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) c += v[j] <= col ? 1 : 0;  // sorted: the first c probes start at or before col
+        const int64_t a0 = a;
+        if (c < 7) b = a0 + (c + 1) * step;
+        if (c > 0) a = a0 + c * step + 1;
+    }
+    {
+        int c = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (a + j < b) c += __ldg(&R.sb[a + j].x) <= col ? 1 : 0;
+        a += c;
     }
     ResolvedUnit r;
     r.col = col;
@@ -204,9 +221,11 @@ __device__ __forceinline__ void accumulate(uint32_t *ref_slot, uint32_t *alt_slo
 // For this lane's value v (NBITS wide): which contributing lanes hold a smaller value (lt) and
 // which an equal one (eq, itself included).  Walks the bits from the top; lanes that do not contribute
 // hold v == 0, so every ballot is already restricted to the contributing set.  One step is a
-// predicate, a ballot and three predicated logic ops (written in PTX: the compiler's own lowering of the
-// same C++ spends eight instructions per bit on materialising the lane's bit as a mask).
-__device__ __forceinline__ void radix_step(uint32_t v, uint32_t bit_mask, uint32_t &lt, uint32_t &eq) {
+// predicate, a ballot and three predicated logic ops (ptxas fuses the bit tests of a value into one R2P and
+// lowers a step to six instructions; the compiler's own lowering of the same C++ spends eight to ten, and
+// a least-significant-bit-first recurrence with two LOP3 per step costs registers the kernel does not have).
+template <int BIT>
+__device__ __forceinline__ void radix_step(uint32_t v, uint32_t &lt, uint32_t &eq) {
     asm("{\n"
         ".reg .pred p;\n"
         ".reg .b32 b, t;\n"
@@ -218,14 +237,18 @@ __device__ __forceinline__ void radix_step(uint32_t v, uint32_t bit_mask, uint32
         "@!p lop3.b32 %1, %1, b, 0, 0x30;\n"  // mine clear: eq &= ~b
         "}\n"
         : "+r"(lt), "+r"(eq)
-        : "r"(v), "r"(bit_mask));
+        : "r"(v), "r"(1u << BIT));
+}
+template <int NBITS, int BIT = NBITS - 1>
+__device__ __forceinline__ void radix_steps(uint32_t v, uint32_t &lt, uint32_t &eq) {
+    radix_step<BIT>(v, lt, eq);
+    if constexpr (BIT > 0) radix_steps<NBITS, BIT - 1>(v, lt, eq);
 }
 template <int NBITS>
 __device__ __forceinline__ void radix_compare(uint32_t v, uint32_t contributing, uint32_t &lt, uint32_t &eq) {
     lt = 0u;
     eq = contributing;
-#pragma unroll
-    for (int bit = NBITS - 1; bit >= 0; --bit) radix_step(v, 1u << bit, lt, eq);
+    radix_steps<NBITS>(v, lt, eq);
 }
 
 // Medians of the REF / ALT lists and this lane's share of the ALT mid-rank sum, from the lt / eq masks.
@@ -558,15 +581,17 @@ pileup_deep_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, const uint8
     }
     __syncwarp();
     const uint32_t n = *n_warp;
+    // listed unit k goes to warp k first (no atomics when the list is short or empty), the rest through a counter
+    const uint32_t n_warps = gridDim.x * WARPS_PER_CTA;
+    uint32_t k = blockIdx.x * WARPS_PER_CTA + warp;
     for (;;) {
-        uint32_t k = 0;
-        if (lane == 0) k = atomicAdd(deep_work, 1u);
-        k = __shfl_sync(FULL, k, 0);
         if (k >= n) break;
         const int64_t u = warp_list[k];
         Unit U;
         unit_from(res[u], ins_seq, U);
         unit_by_histogram<POSB, true>(R, P, U, ref_slot, alt_slot, lane, out + u, &ring);
+        if (lane == 0) k = n_warps + atomicAdd(deep_work, 1u);
+        k = __shfl_sync(FULL, k, 0);
     }
 }
 
