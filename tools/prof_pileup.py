@@ -39,6 +39,18 @@ for i in range(a.launches):
     e1.record()
     evs.append((e0, e1))
 torch.cuda.synchronize()
+# the FP64 epilogue on the counts of the last launch
+eaf = torch.full((units.n_units,), 0.4, dtype=torch.float64, device=dev.device)
+stats = dev.alloc_stats(units.n_units)
+eps = []
+for i in range(a.launches):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    dev.epilogue(units.n_units, out, eaf, 5e-7, 1e-3, out=stats)
+    e1.record()
+    eps.append((e0, e1))
+torch.cuda.synchronize()
+print("epilogue ms per launch:", " ".join("%.3f" % x.elapsed_time(y) for x, y in eps))
 ms = [x.elapsed_time(y) for x, y in evs]
 c = dev.to_host(out, device.COUNTS_DTYPE, units.n_units)
 print("pileup ms per launch:", " ".join("%.3f" % m for m in ms), "| mean n_cover %.2f n_cand %.2f dp %.2f" % (
