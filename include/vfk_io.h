@@ -63,6 +63,11 @@ typedef struct {
     int64_t n_reads, n_cigar, n_seq_bytes, n_qual_bytes;
 } vfkio_synth_plan; /* also the size plan of the synthetic generator below */
 int vfkio_bam_open(const char *path, vfkio_bam **out);
+/* Indexed access (path.bai): only the records overlapping the regions [beg, end) (0-based, half open; sorted
+ * by contig order of the BAM and start, disjoint) are decoded -- what the reference fetches per chromosome
+ * group through pysam (vafator/pileups.py:71-80, :137-138).  n_regions == 0 reads the header only.           */
+int vfkio_bam_open_regions(const char *path, const char *index_path, int32_t n_regions, const char *const *contig,
+                           const int32_t *beg, const int32_t *end, vfkio_bam **out);
 void vfkio_bam_close(vfkio_bam *b);
 int32_t vfkio_bam_n_contigs(const vfkio_bam *b);
 const char *vfkio_bam_contig_name(const vfkio_bam *b, int32_t i);

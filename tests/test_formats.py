@@ -117,6 +117,87 @@ def test_decoder_on_the_references_real_bams():
     r.check_sorted()
 
 
+def _overlapping(whole, tid, beg, end):
+    span = np.zeros(whole.n_reads, np.int64)
+    for i in range(whole.n_reads):
+        c = whole.cigar[whole.cigar_off[i]:whole.cigar_off[i] + whole.n_cigar[i]]
+        span[i] = sum(int(w) >> 4 for w in c if (int(w) & 15) in (0, 2, 3, 7, 8))
+    return (whole.tid == tid) & (whole.pos < end) & (whole.pos + np.maximum(span, 1) > beg)
+
+
+def _same_reads(sub, whole, keep):
+    assert sub.n_reads == int(keep.sum())
+    for k in ("tid", "pos", "flag", "mapq", "l_qseq", "n_cigar", "mtid", "mpos", "isize", "qname_id", "qname_hash"):
+        assert np.array_equal(getattr(sub, k), getattr(whole, k)[keep]), k
+    idx = np.nonzero(keep)[0]
+    for j, i in enumerate(idx[:200]):
+        assert np.array_equal(sub.cigar[sub.cigar_off[j]:sub.cigar_off[j] + sub.n_cigar[j]],
+                              whole.cigar[whole.cigar_off[i]:whole.cigar_off[i] + whole.n_cigar[i]])
+        assert np.array_equal(sub.qual[sub.qual_off[j]:sub.qual_off[j] + sub.l_qseq[j]],
+                              whole.qual[whole.qual_off[i]:whole.qual_off[i] + whole.l_qseq[i]])
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_RES, "TESTX_S1_L001.bam.bai")), reason="reference checkout not present")
+def test_indexed_fetch_on_the_references_real_bam_and_samtools_index():
+    """Region reads through the samtools-built .bai the reference ships == the whole-file decode, filtered."""
+    path = os.path.join(REF_RES, "TESTX_S1_L001.bam")
+    whole = bamio.BamFile(path, use_index=False).read_batch()
+    b = bamio.BamFile(path)
+    assert b.index_path and b.contigs == ["chr1", "chr2", "chr3", "chr4"]
+    rng = np.random.default_rng(3)
+    for tid, name in enumerate(b.contigs):
+        pos = whole.pos[whole.tid == tid]
+        spans = [(0, 1 << 29), (int(pos.min()), int(pos.min()) + 1), (int(pos.max()) + 5000, int(pos.max()) + 6000)]
+        spans += [tuple(sorted(int(x) for x in rng.integers(0, 1_000_000, 2))) for _ in range(12)]
+        for a, e in spans:
+            if e > a:
+                _same_reads(b.read_batch([(name, a, e)]), whole, _overlapping(whole, tid, a, e))
+    # several regions in one call, given out of order and with an unknown contig
+    got = b.read_batch([("chr3", 500_000, 700_000), ("chrZ", 1, 2), ("chr1", 0, 400_000)])
+    _same_reads(got, whole, _overlapping(whole, 0, 0, 400_000) | _overlapping(whole, 2, 500_000, 700_000))
+    assert b.read_batch().n_reads == whole.n_reads  # no regions: the whole file
+
+
+def test_indexed_fetch_with_the_in_tree_index_writer(tmp_path):
+    """write_bam(index=True) -> region reads == whole-file decode, filtered; long reads spanning several 16-kbp
+    windows, empty windows and a contig without reads exercise the linear index."""
+    rng = np.random.default_rng(5)
+    recs = []
+    for tid, n in ((0, 1500), (2, 600)):
+        pos = np.sort(np.concatenate([rng.integers(1000, 60_000, n // 2), rng.integers(400_000, 420_000, n - n // 2)]))
+        for k, p in enumerate(pos):
+            if k % 97 == 0:
+                cigar, l = "50M30000N50M", 100  # spans two or three windows
+            elif k % 5 == 0:
+                cigar, l = "10S80M2D10M", 100
+            else:
+                cigar, l = "100M", 100
+            recs.append(dict(qname="r%d_%d" % (tid, k), flag=0, tid=tid, pos=int(p), mapq=60, cigar=cigar,
+                             seq="".join("ACGT"[(k + j) & 3] for j in range(l)), qual="I" * l, mtid=-1, mpos=-1, isize=0))
+    recs.sort(key=lambda r: (r["tid"], r["pos"]))
+    path = str(tmp_path / "x.bam")
+    bamio.write_bam(path, recs, ["c1", "c2", "c3"], [1 << 20] * 3, index=True)
+    whole = bamio.BamFile(path, use_index=False).read_batch()
+    assert whole.n_reads == len(recs)
+    b = bamio.BamFile(path)
+    assert b.index_path == path + ".bai"
+    for tid, name in ((0, "c1"), (1, "c2"), (2, "c3")):
+        spans = [(0, 1 << 20), (30_500, 30_501), (100_000, 300_000), (399_000, 400_500), (59_990, 405_000)]
+        spans += [tuple(sorted(int(x) for x in rng.integers(0, 450_000, 2))) for _ in range(15)]
+        for a, e in spans:
+            if e > a:
+                _same_reads(b.read_batch([(name, a, e)]), whole, _overlapping(whole, tid, a, e))
+    with pytest.raises(ValueError):
+        b._lib  # regions are merged per contig by read_batch; the C entry rejects unsorted input
+        import ctypes as C
+        names = (C.c_char_p * 2)(b"c3", b"c1")
+        beg, end = np.asarray([0, 0], np.int32), np.asarray([10, 10], np.int32)
+        h = C.c_void_p()
+        from vafator_b200 import device as _dev
+        _dev._io_check(b._lib.vfkio_bam_open_regions(path.encode(), (path + ".bai").encode(), 2, names,
+                                                     C.c_void_p(beg.ctypes.data), C.c_void_p(end.ctypes.data), C.byref(h)))
+
+
 # ---- multiallelics-filter (SURVEY.md 8(f) rank 4) against the reference run on the same inputs ----
 def test_multiallelic_filter_matches_reference_golden(tmp_path):
     """tests/golden/multiallelic.json: outputs of the UNMODIFIED reference filter (oracle/gen_golden_multiallelic.py)."""

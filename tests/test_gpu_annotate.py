@@ -46,9 +46,11 @@ def test_engine_info_strings_match_reference(path):
                 assert str(g[k]) == str(w[k]), (sc["name"], prm, records[i], k, g[k], w[k])
 
 
+@pytest.mark.parametrize("indexed", [False, True], ids=["whole_file", "bai_regions"])
 @pytest.mark.parametrize("name", ["pileup_random_13.json", "pileup_handmade.json"])
-def test_cli_on_files_matches_reference(tmp_path, name):
-    """vafator --input-vcf ... --bam ... on BAM/VCF/BED files: every INFO key=value of the reference."""
+def test_cli_on_files_matches_reference(tmp_path, name, indexed):
+    """vafator --input-vcf ... --bam ... on BAM/VCF/BED files: every INFO key=value of the reference; with a
+    .bai next to the BAMs only the regions the reference would fetch are decoded -- same output."""
     sc = H.load_scenario(os.path.join(H.GOLDEN, name))
     run = sc["runs"][3]  # thresholds 30/13, fpr/error-rate/normal-ploidy set, ambiguous bases excluded
     prm = run["params"]
@@ -67,7 +69,8 @@ def test_cli_on_files_matches_reference(tmp_path, name):
     for s, idx in sc["samples"].items():
         for b in idx:
             p = tmp_path / ("bam%d.bam" % b)
-            bamio.write_bam(str(p), sc["bams"][b], sc["contigs"])
+            bamio.write_bam(str(p), sc["bams"][b], sc["contigs"], index=indexed)
+            assert os.path.exists(str(p) + ".bai") == indexed
             argv += ["--bam", s, str(p)]
     for s, pur in sc["purities"].items():
         argv += ["--purity", s, str(pur)]

@@ -75,7 +75,15 @@ class Annotator(object):
             if not v.ALT:
                 raise ValueError("VCF record %s:%d has no ALT allele" % (v.CHROM, v.POS))
         records = [(v.CHROM, v.POS, v.REF, v.ALT) for v in variants]
-        bams = OrderedDict((s, [r.read_batch() for r in readers]) for s, readers in self.bam_readers.items())
+        # what the reference fetches: [first.POS-1, last.POS) of every chromosome group (vafator/pileups.py:137-138);
+        # an indexed BAM is decoded for those regions only
+        regions = []
+        for chrom, pos in ((r[0], r[1]) for r in records):
+            if regions and regions[-1][0] == chrom:
+                regions[-1][1], regions[-1][2] = min(regions[-1][1], pos - 1), max(regions[-1][2], pos)
+            else:
+                regions.append([chrom, pos - 1, pos])
+        bams = OrderedDict((s, [r.read_batch(regions) for r in readers]) for s, readers in self.bam_readers.items())
         chroms = [r[0] for r in records]
         positions = [r[1] for r in records]
         eaf = {s: self.power.expected_vafs(s, chroms, positions) for s in bams}

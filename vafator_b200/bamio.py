@@ -29,19 +29,36 @@ def _lib():
     lib.vfkio_bam_header_text.restype = C.c_char_p
     lib.vfkio_bam_contig_length.restype = C.c_int64
     lib.vfkio_bam_close.restype = None
+    lib.vfkio_bam_close.argtypes = [C.c_void_p]
+    lib.vfkio_bam_open_regions.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p,
+                                           C.POINTER(C.c_void_p)]
     return lib
 
 
 class BamFile:
-    """A decoded BAM: `.contigs`, `.lengths`, `.read_batch()`."""
+    """A BAM file: `.contigs`, `.lengths`, `.read_batch()`.
 
-    def __init__(self, path: str, mode: str = "r"):
+    With an index next to it (`x.bam.bai` or `x.bai`) only the header is read on open and
+    `read_batch(regions)` decodes just the records overlapping the regions -- the reads the reference
+    fetches for [first.POS-1, last.POS) of a chromosome group (vafator/pileups.py:71-80, :137-138).
+    Without an index (or without regions) the whole file is decoded once and cached."""
+
+    def __init__(self, path: str, mode: str = "r", use_index: bool = True):
         if not os.path.exists(path):
             raise FileNotFoundError("could not open alignment file `%s`: No such file or directory" % path)
         self.path = path
         self._lib = _lib()
+        self.index_path: Optional[str] = None
+        if use_index:
+            for cand in (path + ".bai", os.path.splitext(path)[0] + ".bai"):
+                if os.path.exists(cand):
+                    self.index_path = cand
+                    break
         h = C.c_void_p()
-        _dev._io_check(self._lib.vfkio_bam_open(path.encode(), C.byref(h)))
+        if self.index_path:
+            _dev._io_check(self._lib.vfkio_bam_open_regions(path.encode(), self.index_path.encode(), 0, None, None, None, C.byref(h)))
+        else:
+            _dev._io_check(self._lib.vfkio_bam_open(path.encode(), C.byref(h)))
         self._h = h
         n = self._lib.vfkio_bam_n_contigs(h)
         self.contigs: List[str] = [self._lib.vfkio_bam_contig_name(h, i).decode() for i in range(n)]
@@ -49,27 +66,56 @@ class BamFile:
         self.header_text = self._lib.vfkio_bam_header_text(h).decode(errors="replace")
         self._batch: Optional[ReadBatch] = None
 
-    def read_batch(self) -> ReadBatch:
+    def _fill(self, h) -> ReadBatch:
+        if not self._lib.vfkio_bam_is_sorted(h):
+            raise ValueError("%s is not coordinate sorted" % self.path)
+        plan = _PlanC()
+        _dev._io_check(self._lib.vfkio_bam_plan(h, C.byref(plan)))
+        n = plan.n_reads
+        arr = dict(tid=np.empty(n, np.int32), pos=np.empty(n, np.int32), flag=np.empty(n, np.uint16),
+                   mapq=np.empty(n, np.uint8), l_qseq=np.empty(n, np.int32), n_cigar=np.empty(n, np.int32),
+                   cigar_off=np.empty(n, np.int64), seq_off=np.empty(n, np.int64), qual_off=np.empty(n, np.int64),
+                   cigar=np.empty(max(plan.n_cigar, 1), np.uint32), seq=np.empty(max(plan.n_seq_bytes, 1), np.uint8),
+                   qual=np.empty(max(plan.n_qual_bytes, 1), np.uint8), mtid=np.empty(n, np.int32),
+                   mpos=np.empty(n, np.int32), isize=np.empty(n, np.int32), qname_id=np.empty(n, np.uint64),
+                   qname_hash=np.empty(n, np.uint32))
+        s = _dev._IoReadsC()
+        s.n, s.n_contigs = n, len(self.contigs)
+        for k, a in arr.items():
+            setattr(s, k, a.ctypes.data)
+        _dev._io_check(self._lib.vfkio_bam_fill(h, C.byref(s)))
+        arr["cigar"], arr["seq"], arr["qual"] = arr["cigar"][:plan.n_cigar], arr["seq"][:plan.n_seq_bytes], arr["qual"][:plan.n_qual_bytes]
+        return ReadBatch(contigs=list(self.contigs), contig_lengths=self.lengths, **arr)
+
+    def read_batch(self, regions: Optional[Sequence[tuple]] = None) -> ReadBatch:
+        """regions: [(contig, start, stop)] 0-based half open; merged per contig and put in file order.  Ignored
+        (the whole file is returned) when the file has no index."""
+        if self.index_path and regions is not None:
+            order = {c: i for i, c in enumerate(self.contigs)}
+            span = {}
+            for c, a, b in regions:
+                if c in order:
+                    lo, hi = span.get(c, (a, b))
+                    span[c] = (min(lo, a), max(hi, b))
+            todo = sorted(span.items(), key=lambda kv: order[kv[0]])
+            n = len(todo)
+            names = (C.c_char_p * max(n, 1))(*[c.encode() for c, _ in todo])
+            beg = np.asarray([max(0, a) for _, (a, _b) in todo], np.int32)
+            end = np.asarray([b for _, (_a, b) in todo], np.int32)
+            h = C.c_void_p()
+            _dev._io_check(self._lib.vfkio_bam_open_regions(self.path.encode(), self.index_path.encode(), n, names,
+                                                            C.c_void_p(beg.ctypes.data), C.c_void_p(end.ctypes.data), C.byref(h)))
+            try:
+                return self._fill(h)
+            finally:
+                self._lib.vfkio_bam_close(h)
         if self._batch is None:
-            if not self._lib.vfkio_bam_is_sorted(self._h):
-                raise ValueError("%s is not coordinate sorted" % self.path)
-            plan = _PlanC()
-            _dev._io_check(self._lib.vfkio_bam_plan(self._h, C.byref(plan)))
-            n = plan.n_reads
-            arr = dict(tid=np.empty(n, np.int32), pos=np.empty(n, np.int32), flag=np.empty(n, np.uint16),
-                       mapq=np.empty(n, np.uint8), l_qseq=np.empty(n, np.int32), n_cigar=np.empty(n, np.int32),
-                       cigar_off=np.empty(n, np.int64), seq_off=np.empty(n, np.int64), qual_off=np.empty(n, np.int64),
-                       cigar=np.empty(max(plan.n_cigar, 1), np.uint32), seq=np.empty(max(plan.n_seq_bytes, 1), np.uint8),
-                       qual=np.empty(max(plan.n_qual_bytes, 1), np.uint8), mtid=np.empty(n, np.int32),
-                       mpos=np.empty(n, np.int32), isize=np.empty(n, np.int32), qname_id=np.empty(n, np.uint64),
-                       qname_hash=np.empty(n, np.uint32))
-            s = _dev._IoReadsC()
-            s.n, s.n_contigs = n, len(self.contigs)
-            for k, a in arr.items():
-                setattr(s, k, a.ctypes.data)
-            _dev._io_check(self._lib.vfkio_bam_fill(self._h, C.byref(s)))
-            arr["cigar"], arr["seq"], arr["qual"] = arr["cigar"][:plan.n_cigar], arr["seq"][:plan.n_seq_bytes], arr["qual"][:plan.n_qual_bytes]
-            self._batch = ReadBatch(contigs=list(self.contigs), contig_lengths=self.lengths, **arr)
+            if self.index_path:  # header-only handle: decode the file now
+                h = C.c_void_p()
+                _dev._io_check(self._lib.vfkio_bam_open(self.path.encode(), C.byref(h)))
+                self._lib.vfkio_bam_close(self._h)
+                self._h = h
+            self._batch = self._fill(self._h)
         return self._batch
 
     def close(self):
@@ -108,14 +154,16 @@ def _reg2bin(beg: int, end: int) -> int:
 
 
 def write_bam(path: str, records: Sequence[dict], contigs: Sequence[str], lengths: Optional[Sequence[int]] = None,
-              sort_order: str = "coordinate") -> None:
-    """records: SAM-view dicts (see ReadBatch.from_records), already in the order to be written."""
+              sort_order: str = "coordinate", index: bool = False) -> None:
+    """records: SAM-view dicts (see ReadBatch.from_records), already in the order to be written.
+    index=True also writes `path + ".bai"` (bins + linear index, SAMv1 5.2) for coordinate-sorted records."""
     lengths = list(lengths) if lengths is not None else [1 << 28] * len(contigs)
     text = "@HD\tVN:1.6\tSO:%s\n" % sort_order + "".join("@SQ\tSN:%s\tLN:%d\n" % (c, l) for c, l in zip(contigs, lengths))
     out = bytearray(b"BAM\1" + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", len(contigs)))
     for c, l in zip(contigs, lengths):
         out += struct.pack("<i", len(c) + 1) + c.encode() + b"\0" + struct.pack("<i", l)
     code = {ch: i for i, ch in enumerate(SEQ_CHARS)}
+    placed = []  # (tid, pos, end, bin, offset of the record in the uncompressed stream, offset of its end)
     for r in records:
         cig = r["cigar"]
         if isinstance(cig, str):
@@ -139,8 +187,46 @@ def write_bam(path: str, records: Sequence[dict], contigs: Sequence[str], length
                            _reg2bin(r["pos"], r["pos"] + max(span, 1)) if r["tid"] >= 0 else 4680, len(ops), r["flag"],
                            len(seq), r.get("mtid", -1), r.get("mpos", -1), r.get("isize", 0))
         body += name + b"".join(struct.pack("<I", (l << 4) | op) for op, l in ops) + packed + qual
+        if r["tid"] >= 0:
+            e = r["pos"] + max(span, 1)
+            placed.append((r["tid"], r["pos"], e, _reg2bin(r["pos"], e), len(out), len(out) + 4 + len(body)))
         out += struct.pack("<i", len(body)) + body
+    block_at = []  # file offset of every BGZF block
     with open(path, "wb") as fh:
         for i in range(0, len(out), 0xFF00):
+            block_at.append(fh.tell())
             fh.write(_bgzf_block(bytes(out[i:i + 0xFF00])))
+        block_at.append(fh.tell())
         fh.write(_BGZF_EOF)
+    if index:
+        def voff(u):
+            return (block_at[u // 0xFF00] << 16) | (u % 0xFF00)
+        bai = bytearray(b"BAI\1" + struct.pack("<i", len(contigs)))
+        for t in range(len(contigs)):
+            bins, linear = {}, []
+            for tid, pos, e, b, u0, u1 in placed:
+                if tid != t:
+                    continue
+                chunks = bins.setdefault(b, [])
+                if chunks and chunks[-1][1] == voff(u0):
+                    chunks[-1][1] = voff(u1)
+                else:
+                    chunks.append([voff(u0), voff(u1)])
+                for w in range(pos >> 14, ((e - 1) >> 14) + 1):
+                    while len(linear) <= w:
+                        linear.append(0)
+                    if linear[w] == 0:
+                        linear[w] = voff(u0)
+            for w in range(1, len(linear)):  # htslib fills the windows no read overlaps with the entry before
+                if linear[w] == 0:
+                    linear[w] = linear[w - 1]
+            bai += struct.pack("<i", len(bins))
+            for b in sorted(bins):
+                bai += struct.pack("<Ii", b, len(bins[b]))
+                for c0, c1 in bins[b]:
+                    bai += struct.pack("<QQ", c0, c1)
+            bai += struct.pack("<i", len(linear))
+            for v in linear:
+                bai += struct.pack("<Q", v)
+        with open(path + ".bai", "wb") as fh:
+            fh.write(bytes(bai))

@@ -140,6 +140,257 @@ extern "C" int vfkio_bam_open(const char *path, vfkio_bam **out) {
     return VFK_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Indexed access: decode only the records overlapping a list of regions, the way the reference
+// fetches [first.POS-1, last.POS) of every chromosome group through pysam (vafator/pileups.py:71-80,
+// :137-138).  The BAI linear index (SAMv1 5.1.3/5.2: one virtual offset per 16 kbp window = the
+// first record overlapping that window) gives a lower bound; records are then read sequentially until
+// one starts at or beyond the region end.  BGZF blocks are read and inflated in batches (OpenMP).
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct BlockReader {  // sequential BGZF reader over an open file, from a compressed offset
+    FILE *f = nullptr;
+    std::vector<uint8_t> raw;   // compressed bytes not yet consumed
+    long file_pos = 0;          // file offset of raw[0]
+    bool eof = false;
+
+    bool refill(size_t want) {
+        while (!eof && raw.size() < want) {
+            const size_t old = raw.size();
+            raw.resize(old + (1u << 22));
+            const size_t got = fread(raw.data() + old, 1, 1u << 22, f);
+            raw.resize(old + got);
+            if (got == 0) eof = true;
+        }
+        return raw.size() >= want;
+    }
+    // inflate up to max_blocks blocks, appending to `out`; returns number of blocks, -1 on corruption
+    int next_batch(std::vector<uint8_t> &out, int max_blocks) {
+        struct Blk { size_t src, n, dst, isize; };
+        std::vector<Blk> blocks;
+        size_t p = 0, total = out.size();
+        while ((int)blocks.size() < max_blocks) {
+            if (!refill(p + 18)) break;
+            const uint8_t *h = raw.data() + p;
+            if (!(h[0] == 31 && h[1] == 139 && h[2] == 8 && (h[3] & 4))) return -1;
+            const uint16_t xlen = le16(h + 10);
+            if (!refill(p + 12 + xlen)) return -1;
+            size_t x = p + 12;
+            const size_t xe = x + xlen;
+            int bsize = -1;
+            while (x + 4 <= xe) {
+                const uint16_t slen = le16(raw.data() + x + 2);
+                if (raw[x] == 'B' && raw[x + 1] == 'C' && slen == 2) bsize = le16(raw.data() + x + 4);
+                x += 4 + slen;
+            }
+            if (bsize < 0) return -1;
+            const size_t blen = (size_t)bsize + 1;
+            if (!refill(p + blen)) return -1;
+            const size_t isize = le32(raw.data() + p + blen - 4);
+            blocks.push_back({xe, blen - (xe - p) - 8, total, isize});
+            total += isize;
+            p += blen;
+        }
+        out.resize(total);
+        int bad = 0;
+#pragma omp parallel for schedule(dynamic, 8) reduction(| : bad)
+        for (int64_t i = 0; i < (int64_t)blocks.size(); ++i) {
+            const Blk &k = blocks[(size_t)i];
+            if (k.isize && inflate_block(raw.data() + k.src, k.n, out.data() + k.dst, k.isize)) bad |= 1;
+        }
+        if (bad) return -1;
+        raw.erase(raw.begin(), raw.begin() + (long)p);
+        file_pos += (long)p;
+        return (int)blocks.size();
+    }
+    bool seek(long coffset) {
+        raw.clear();
+        eof = false;
+        file_pos = coffset;
+        return fseek(f, coffset, SEEK_SET) == 0;
+    }
+};
+
+inline bool consumes_ref_op(uint32_t op) { return op == 0 || op == 2 || op == 3 || op == 7 || op == 8; }
+
+// header text + reference table from the start of an inflated stream; returns bytes consumed, 0 = need more data
+size_t parse_header(const std::vector<uint8_t> &d, vfkio_bam *b, bool *bad) {
+    *bad = false;
+    const size_t n = d.size();
+    if (n < 12) return 0;
+    if (memcmp(d.data(), "BAM\1", 4) != 0) { *bad = true; return 0; }
+    size_t q = 4;
+    const uint32_t l_text = le32(d.data() + q); q += 4;
+    if (q + l_text + 4 > n) return 0;
+    const size_t text_at = q;
+    q += l_text;
+    const uint32_t n_ref = le32(d.data() + q); q += 4;
+    std::vector<std::string> names;
+    std::vector<int64_t> lengths;
+    for (uint32_t r = 0; r < n_ref; ++r) {
+        if (q + 4 > n) return 0;
+        const uint32_t l_name = le32(d.data() + q); q += 4;
+        if (q + l_name + 4 > n) return 0;
+        names.emplace_back((const char *)d.data() + q, l_name ? l_name - 1 : 0);
+        q += l_name;
+        lengths.push_back((int64_t)le32(d.data() + q));
+        q += 4;
+    }
+    b->text.assign((const char *)d.data() + text_at, l_text);
+    b->names.swap(names);
+    b->lengths.swap(lengths);
+    return q;
+}
+}  // namespace
+
+extern "C" int vfkio_bam_open_regions(const char *path, const char *index_path, int32_t n_regions, const char *const *contig,
+                                      const int32_t *beg, const int32_t *end, vfkio_bam **out) {
+    if (!path || !index_path || !out || n_regions < 0 || (n_regions > 0 && (!contig || !beg || !end)))
+        return vfkio_fail(VFK_EINVAL, "vfkio_bam_open_regions: bad argument");
+    BlockReader rd;
+    rd.f = fopen(path, "rb");
+    if (!rd.f) return vfkio_fail(VFK_EINVAL, "cannot open alignment file");
+    struct Closer { FILE *f; ~Closer() { if (f) fclose(f); } } closer{rd.f};
+    vfkio_bam *b = new vfkio_bam();
+    // ---- header
+    {
+        std::vector<uint8_t> head;
+        bool bad = false;
+        size_t used = 0;
+        while (used == 0) {
+            const int nb = rd.next_batch(head, 16);
+            if (nb < 0) { delete b; return vfkio_fail(VFK_EINVAL, "not a BGZF/BAM file"); }
+            used = parse_header(head, b, &bad);
+            if (bad) { delete b; return vfkio_fail(VFK_EINVAL, "not a BAM file (bad magic)"); }
+            if (used == 0 && nb == 0) { delete b; return vfkio_fail(VFK_EINVAL, "truncated BAM header"); }
+        }
+    }
+    if (n_regions == 0) { *out = b; return VFK_OK; }
+    // ---- the BAI: per contig the binning index (bin -> chunks of virtual offsets) and the linear index
+    struct Chunk { uint64_t beg, end; };
+    std::vector<std::vector<std::pair<uint32_t, Chunk>>> bins(b->names.size());
+    std::vector<std::vector<uint64_t>> linear(b->names.size());
+    auto le64 = [](const uint8_t *p8) { return (uint64_t)le32(p8) | ((uint64_t)le32(p8 + 4) << 32); };
+    {
+        FILE *fi = fopen(index_path, "rb");
+        if (!fi) { delete b; return vfkio_fail(VFK_EINVAL, "cannot open the BAM index"); }
+        fseek(fi, 0, SEEK_END);
+        const long isz = ftell(fi);
+        fseek(fi, 0, SEEK_SET);
+        std::vector<uint8_t> ix((size_t)std::max<long>(isz, 0));
+        const bool ok = isz > 0 && fread(ix.data(), 1, (size_t)isz, fi) == (size_t)isz;
+        fclose(fi);
+        if (!ok || ix.size() < 8 || memcmp(ix.data(), "BAI\1", 4) != 0) { delete b; return vfkio_fail(VFK_EINVAL, "not a BAI index"); }
+        size_t q = 4;
+        const uint32_t n_ref = le32(ix.data() + q); q += 4;
+        if (n_ref != b->names.size()) { delete b; return vfkio_fail(VFK_EINVAL, "BAM index does not match the BAM header"); }
+        for (uint32_t r = 0; r < n_ref; ++r) {
+            if (q + 4 > ix.size()) { delete b; return vfkio_fail(VFK_EINVAL, "truncated BAM index"); }
+            const uint32_t n_bin = le32(ix.data() + q); q += 4;
+            for (uint32_t k = 0; k < n_bin; ++k) {
+                if (q + 8 > ix.size()) { delete b; return vfkio_fail(VFK_EINVAL, "truncated BAM index"); }
+                const uint32_t bin = le32(ix.data() + q), n_chunk = le32(ix.data() + q + 4);
+                q += 8;
+                if (q + (size_t)n_chunk * 16 > ix.size()) { delete b; return vfkio_fail(VFK_EINVAL, "truncated BAM index"); }
+                for (uint32_t c = 0; c < n_chunk; ++c, q += 16)
+                    if (bin < 37450u) bins[r].push_back({bin, {le64(ix.data() + q), le64(ix.data() + q + 8)}});  // 37450: metadata
+            }
+            if (q + 4 > ix.size()) { delete b; return vfkio_fail(VFK_EINVAL, "truncated BAM index"); }
+            const uint32_t n_intv = le32(ix.data() + q); q += 4;
+            if (q + (size_t)n_intv * 8 > ix.size()) { delete b; return vfkio_fail(VFK_EINVAL, "truncated BAM index"); }
+            linear[r].resize(n_intv);
+            for (uint32_t k = 0; k < n_intv; ++k) linear[r][k] = le64(ix.data() + q + (size_t)k * 8);
+            q += (size_t)n_intv * 8;
+        }
+    }
+    // ---- regions, in file order
+    int32_t last_tid = -1, last_pos = -1, last_end = -1;
+    for (int32_t g = 0; g < n_regions; ++g) {
+        int32_t tid = -1;
+        for (size_t t = 0; t < b->names.size(); ++t)
+            if (b->names[t] == contig[g]) tid = (int32_t)t;
+        if (tid < 0) continue;  // a contig the BAM does not know has no reads
+        if (tid < last_tid || (tid == last_tid && beg[g] < last_end)) {
+            delete b;
+            return vfkio_fail(VFK_EINVAL, "vfkio_bam_open_regions: regions must be sorted and disjoint");
+        }
+        last_end = end[g];
+        const std::vector<uint64_t> &lin = linear[(size_t)tid];
+        const int32_t r_beg = std::max(beg[g], 0), r_end = end[g];
+        if (lin.empty() || r_end <= r_beg) { last_tid = tid; continue; }
+        size_t w = std::min<size_t>((size_t)(r_beg >> 14), lin.size() - 1);
+        uint64_t min_off = lin[w];
+        // an empty window carries 0 (or the value of the window before it): every read overlapping the region
+        // then overlaps a later window, whose entry is a valid lower bound
+        while (min_off == 0 && w + 1 < lin.size()) min_off = lin[++w];
+        if (min_off == 0) { last_tid = tid; continue; }
+        // Start of the scan: the earliest chunk of a bin overlapping the region that is not entirely before the
+        // linear-index bound (the linear index only knows mapped reads; a placed unmapped mate in front of the
+        // first mapped read of a window is reachable through its bin only).  From there the file is read in order.
+        uint64_t voff = min_off;
+        {
+            const int64_t e1 = (int64_t)r_end - 1;
+            for (const auto &bc : bins[(size_t)tid]) {
+                const uint32_t bin = bc.first;
+                bool hit = bin == 0;
+                for (int lvl = 1, shift = 26; lvl <= 5 && !hit; ++lvl, shift -= 3) {
+                    const uint32_t base = ((1u << (3 * lvl)) - 1) / 7;
+                    hit = bin >= base + (uint32_t)(r_beg >> shift) && bin <= base + (uint32_t)(e1 >> shift);
+                }
+                if (hit && bc.second.end > min_off && bc.second.beg < voff) voff = bc.second.beg;
+            }
+        }
+        if (!rd.seek((long)(voff >> 16))) { delete b; return vfkio_fail(VFK_EINVAL, "seek failed on alignment file"); }
+        std::vector<uint8_t> buf;
+        size_t q = (size_t)(voff & 0xFFFF);
+        bool done = false;
+        while (!done) {
+            const int nb = rd.next_batch(buf, 64);
+            if (nb < 0) { delete b; return vfkio_fail(VFK_EINVAL, "BGZF block failed to inflate"); }
+            while (q + 4 <= buf.size()) {
+                const uint32_t bs = le32(buf.data() + q);
+                if (bs < 32) { delete b; return vfkio_fail(VFK_EINVAL, "corrupt BAM record"); }
+                if (q + 4 + bs > buf.size()) break;  // the record continues in the next batch
+                const uint8_t *r = buf.data() + q + 4;
+                const int32_t rt = (int32_t)le32(r), rp = (int32_t)le32(r + 4);
+                if (rt != tid || rp >= r_end) {
+                    if (rt > tid || rt < 0 || (rt == tid && rp >= r_end)) { done = true; break; }
+                    q += 4 + bs;  // still on an earlier contig (lower bound of the index): skip
+                    continue;
+                }
+                const uint32_t l_name = r[8], n_cig = le16(r + 12);
+                const uint8_t *pc = r + 32 + l_name;
+                int64_t span = 0;
+                for (uint32_t k = 0; k < n_cig; ++k) {
+                    const uint32_t cw = le32(pc + 4 * k);
+                    if (consumes_ref_op(cw & 15u)) span += cw >> 4;
+                }
+                if ((int64_t)rp + std::max<int64_t>(span, 1) > (int64_t)r_beg) {  // overlaps the region (bam_endpos semantics)
+                    if (rt < last_tid || (rt == last_tid && rp < last_pos)) b->sorted = 0;
+                    last_tid = rt;
+                    last_pos = rp;
+                    b->rec_off.push_back((int64_t)b->data.size());
+                    b->data.insert(b->data.end(), buf.data() + q, buf.data() + q + 4 + bs);
+                    b->n_cigar += n_cig;
+                    const int64_t l_seq = (int64_t)le32(r + 16);
+                    b->n_seq += (l_seq + 1) / 2;
+                    b->n_qual += l_seq;
+                }
+                q += 4 + bs;
+            }
+            if (!done) {
+                if (nb == 0) break;  // end of file
+                buf.erase(buf.begin(), buf.begin() + (long)q);  // keep the partial record
+                q = 0;
+            }
+        }
+        last_tid = std::max(last_tid, tid);
+    }
+    *out = b;
+    return VFK_OK;
+}
+
 extern "C" void vfkio_bam_close(vfkio_bam *b) { delete b; }
 extern "C" int32_t vfkio_bam_n_contigs(const vfkio_bam *b) { return b ? (int32_t)b->names.size() : 0; }
 extern "C" const char *vfkio_bam_contig_name(const vfkio_bam *b, int32_t i) {
