@@ -33,9 +33,13 @@ import time
 # this rank's share of the host cores instead.  Must happen before any OpenMP runtime is loaded.
 if int(os.environ.get("WORLD_SIZE", "1")) > 1:
     os.environ["OMP_NUM_THREADS"] = str(max(2, (os.cpu_count() or 2) // int(os.environ["WORLD_SIZE"])))
-    # rank 0 prints exactly one line on stdout: keep NCCL's version banner out of it
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+
+# Rank 0 prints exactly ONE line on stdout.  Libraries write there too (NCCL prints its version banner with
+# printf at NCCL_DEBUG=VERSION/WARN): file descriptor 1 is pointed at stderr for the rest of the process and the
+# JSON line goes through a private duplicate of the original stdout.
+sys.stdout.flush()
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
 
 import numpy as np
 
@@ -49,6 +53,39 @@ PURITY, PLOIDY = {"tumor": 0.8, "normal": 1.0}, {"tumor": 2.0, "normal": 2.0}
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+def pin_to_gpu_numa_node(local_rank: int):
+    """Multi-GPU runs: keep this rank's host threads -- and with them its pinned buffers (first touch) -- on the
+    NUMA node its GPU hangs off, so that eight ranks do not all pull their batches through one memory
+    controller / PCIe root.  Best effort: returns the node, or None when the topology cannot be read."""
+    try:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = local_rank
+        if vis:
+            ids = [x.strip() for x in vis.split(",") if x.strip()]
+            if local_rank < len(ids) and ids[local_rank].isdigit():
+                idx = int(ids[local_rank])
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(idx)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if not bus:
+            return None
+        dom, rest = bus.split(":", 1)
+        path = "/sys/bus/pci/devices/%s:%s/numa_node" % (dom[-4:], rest)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        cpus = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
 
 
 def measured_peak():
@@ -233,9 +270,10 @@ def main():
             "config": {"workload": workload, "sample": sample},
             "cpu_baseline": {"value": val, "unit": "units/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "units/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}))
+            "gpu_launches": 0}), file=_RESULT_OUT, flush=True)
         return
 
+    numa = pin_to_gpu_numa_node(local_rank) if world > 1 else None
     import torch
     from vafator_b200 import device
     if not torch.cuda.is_available():
@@ -385,7 +423,8 @@ def main():
                        "mean_depth_raw": round(d_raw, 2), "mean_candidates": round(n_cand, 2),
                        "l2": "inputs (%.1f GB of read batches per GPU) exceed L2; tumour and normal batches alternate" % (
                            sum(w["packed"][s].nbytes() for s in samples) / 1e9),
-                       "sharding": "one independent interval shard per GPU, no collective"},
+                       "sharding": "one independent interval shard per GPU, no collective",
+                       "numa_node_rank0": numa},
             "roofline": {"bound": "hbm", "kernel": "pileup_warp_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_unit": b_unit, "units_per_launch": nu, "kernel_ms": k_ms},
@@ -396,7 +435,7 @@ def main():
                                             "transfer": e2e[3]},
             "gpu_launches": int(launches), "clocks": clk,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=_RESULT_OUT, flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
