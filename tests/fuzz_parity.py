@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Randomised GPU-vs-oracle parity campaign: many seeds x read / variant mixes x filter thresholds.
-    python tools/fuzz_parity.py [--seconds 300] [--seed0 1]
+"""Test infrastructure (not collected by pytest): randomised GPU-vs-oracle parity campaign: many seeds x read / variant mixes x filter thresholds.
+    python tests/fuzz_parity.py [--seconds 300] [--seed0 1]
 Every integer field of every unit must match the C oracle bit for bit; exits non-zero on the first
 mismatch and prints the configuration that produced it."""
 import argparse
