@@ -5,13 +5,14 @@
 // MQ / BQ / read-position distributions to integers: counts, twice-the-median, and twice the
 // ALT mid-rank sum that scipy.stats.ranksums would compute (vafator/rank_sum_test.py:11).
 //
-// locate_kernel       : one thread per unit, binary search of the position index.
-// pileup_warp_kernel  : one warp per unit, lanes = candidate reads.  Persistent grid, units handed out
-//                       in small contiguous grabs from a global counter.  Handles the shallow columns
-//                       (<= 64 candidates, <= 32 of them contributing -- every 30x / 60x column): values
-//                       stay in registers, ranks come from a bit-sliced (radix) comparison built on warp
-//                       ballots.  No shared-memory histograms, no atomics, no calls, no stack.  Anything
-//                       else is appended to one of two device-side lists:
+// locate_kernel       : one thread per unit, 8-ary search of the position index.
+// pileup_warp_kernel  : one warp per unit, lanes = reads spanning the column.  Persistent grid, units handed
+//                       out in contiguous grabs from a global counter (shrinking towards the end).  Handles
+//                       the shallow columns (<= 64 candidates, <= 32 of them contributing -- nearly every
+//                       30x / 60x column): values stay in registers, ranks come from a bit-sliced (radix)
+//                       comparison built on warp ballots.  No shared-memory histograms, no atomics, no
+//                       calls, no stack.  Anything else (about 1 % of 30x units: more than 32 contributing
+//                       reads) is appended to one of two device-side lists:
 // pileup_deep_kernel  : one warp per listed unit, histograms in shared memory (u16 counters, two per
 //                       word) + warp scans;
 // pileup_block_kernel : one CTA per listed unit, u32 counters, for columns with > 32767 candidates.
