@@ -11,8 +11,8 @@
 //                       the shallow columns (<= 64 candidates, <= 32 of them contributing -- nearly every
 //                       30x / 60x column): values stay in registers, ranks come from a bit-sliced (radix)
 //                       comparison built on warp ballots.  No shared-memory histograms, no atomics, no
-//                       calls, no stack.  Anything else (about 1 % of 30x units: more than 32 contributing
-//                       reads) is appended to one of two device-side lists:
+//                       calls, no stack.  Anything else (at 30x: the 3-4 units in 10 000 with more than 32
+//                       contributing reads) is appended to one of two device-side lists:
 // pileup_deep_kernel  : one warp per listed unit, histograms in shared memory (u16 counters, two per
 //                       word) + warp scans;
 // pileup_block_kernel : one CTA per listed unit, u32 counters, for columns with > 32767 candidates.
