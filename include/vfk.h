@@ -80,6 +80,27 @@ typedef struct {
  * little-endian granules; granule g of the read holds query positions 5g .. 5g+4, 12 bits each:
  * bits [12r, 12r+8) base quality, bits [12r+8, 12r+12) BAM 4-bit base code.  One (read, column)
  * lookup = one 64-bit load = one 32-byte DRAM sector (BAM's split seq / qual arrays cost two).      */
+/* ---- column store (optional; built by vfkio_columns_*, include/vfk_io.h) --------------------------------
+ * The reference cut into windows of VFK_COL_WIDTH positions; every read leaves one 32-byte sector in every
+ * window it overlaps, the sectors of a window stored together in read order:
+ *   col_wbase[t]            first window of contig t; window of (t, pos) = col_wbase[t] + pos / VFK_COL_WIDTH
+ *                           (contig t has col_wbase[t+1] - col_wbase[t] windows: up to its last covered base)
+ *   col_off[w], col_off[w+1] the sectors of window w
+ *   sector                  12 entries of 16 bits (position p of the window in entry p): base quality |
+ *                           BAM base code << 8 | state << 12, state 0 = not covered, 1 = aligned base,
+ *                           2 = deletion, 3 = reference skip; then two header words:
+ *     h0  query position at the first covered position of the window (12 bits) | MAPQ << 12 |
+ *         signed sector offset of the overlap partner inside the window << 20 (0 = none) |
+ *         read passes the read filter << 28 | tie-break bit << 29 | read precedes its partner << 30 |
+ *         sector cannot be used (two insertions in the window, partner out of reach) << 31
+ *     h1  aligned-position mask (12 bits) | position the insertion follows << 12 | its length << 16 |
+ *         has insertion << 28;  query position of entry p = h0.qpos + popcount(mask below p) + (insertion
+ *         before p ? length : 0)
+ * The read filter verdict and the partner links depend on vfk_params: build the store with the parameters
+ * the kernels are called with.  With a column store present SNV units are evaluated from it (one contiguous
+ * read per column); units it cannot serve go to the read-major path.                                      */
+#define VFK_COL_WIDTH 12
+
 typedef struct {
     int64_t n_reads;
     int32_t n_contigs;
@@ -95,6 +116,12 @@ typedef struct {
     const uint8_t *payload;       /* [n_sectors * 32], 32-byte aligned                          */
     int64_t n_cigar_words;
     int64_t n_sectors;
+    /* column store, all NULL / 0 when absent */
+    const int64_t *col_wbase;     /* [n_contigs+1]                                              */
+    const uint32_t *col_off;      /* [n_col_windows+1]                                          */
+    const uint8_t *col_sectors;   /* [n_col_sectors * 32], 32-byte aligned                      */
+    int64_t n_col_windows;
+    int64_t n_col_sectors;
 } vfk_read_batch;
 
 /* ---- variant units: one per (VCF record, ALT allele) that needs a column evaluation --------- */

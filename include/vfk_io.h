@@ -54,6 +54,16 @@ int vfkio_pack(const vfkio_reads *r, const vfkio_plan *plan, int64_t *contig_off
  * tie_break << 31 or VFK_NO_MATE, for the reads the reference would push under `params`. */
 int vfkio_link_mates(const vfkio_reads *r, const vfk_params *params, uint32_t *mate /*[n_placed]*/);
 
+/* ---- column store (include/vfk.h): plan sizes, then fill caller-allocated arrays.  `mate` is the output of
+ * vfkio_link_mates for the same parameters. */
+typedef struct {
+    int64_t n_windows;
+    int64_t n_sectors;
+} vfkio_col_plan;
+int vfkio_columns_plan(const vfkio_reads *r, int64_t *wbase /*[n_contigs+1]*/, vfkio_col_plan *plan);
+int vfkio_columns_fill(const vfkio_reads *r, const vfk_params *params, const uint32_t *mate, const int64_t *wbase,
+                       const vfkio_col_plan *plan, uint32_t *woff /*[n_windows+1]*/, uint8_t *sectors /*[n_sectors*32]*/);
+
 /* ---- BGZF / BAM decoding (coordinate-sorted BAM; CRAM is reported as unsupported) -----------
  * vfkio_bam_open inflates the file (blocks in parallel) and indexes its placed records;
  * vfkio_bam_fill writes them, in file order, into caller-allocated canonical arrays sized by

@@ -122,3 +122,82 @@ def test_cabi_library_exports_every_declared_symbol():
     assert np.dtype(device.COUNTS_DTYPE).itemsize == 80
     sass = subprocess.run(["cuobjdump", "-lelf", libvfk], capture_output=True, text=True).stdout
     assert "sm_100a" in sass
+
+
+# ---- column store (include/vfk.h): every sector against an independent CIGAR walk ----
+def _walk(read):
+    """[(ref_pos, state, base_char, qual, qpos)] for every reference position the read covers; states as in vfk.h."""
+    ops = re.findall(r"(\d+)([MIDNSHP=X])", read["cigar"])
+    x, y, out = read["pos"], 0, []
+    for n, o in ops:
+        n = int(n)
+        if o in "M=X":
+            for _ in range(n):
+                out.append((x, 1, read["seq"][y], ord(read["qual"][y]) - 33, y))
+                x += 1
+                y += 1
+        elif o in "DN":
+            for _ in range(n):
+                out.append((x, 2 if o == "D" else 3, None, 0, y))
+                x += 1
+        elif o in "IS":
+            y += n
+    return out
+
+
+@pytest.mark.parametrize("path", SCENARIOS, ids=[os.path.basename(p) for p in SCENARIOS])
+def test_column_store_matches_cigar_walk(path):
+    sc = H.load_scenario(path)
+    W = 12
+    for recs, batch in zip(sc["bams"], H.scenario_batches(sc)):
+        for mq, orphans in ((0, True), (20, False)):
+            params = device.make_params(min_mapq=mq, ignore_orphans=orphans)
+            pk = device.pack_reads(batch, params, columns=True)
+            passes = device.read_passes(batch, params)
+            sectors = pk.col_sectors.reshape(-1, 32)
+            entries = sectors[:, :24].copy().view("<u2").reshape(-1, 12)
+            h0, h1 = sectors[:, 24:28].copy().view("<u4").ravel(), sectors[:, 28:32].copy().view("<u4").ravel()
+            walks = [_walk(r) for r in recs]
+            n_seen = 0
+            for t in range(len(sc["contigs"])):
+                n_win = int(pk.col_wbase[t + 1] - pk.col_wbase[t])
+                members = [[] for _ in range(n_win)]
+                for i, (r, wk) in enumerate(zip(recs, walks)):
+                    if r["tid"] == t and wk:
+                        for w in range(wk[0][0] // W, wk[-1][0] // W + 1):
+                            members[w].append(i)
+                for w in range(n_win):
+                    a, b = int(pk.col_off[pk.col_wbase[t] + w]), int(pk.col_off[pk.col_wbase[t] + w + 1])
+                    assert b - a == len(members[w])
+                    for s, i in zip(range(a, b), members[w]):
+                        n_seen += 1
+                        by_pos = {x: (st, ch, q, y) for x, st, ch, q, y in walks[i]}
+                        complex_ = bool(h0[s] >> 31)
+                        assert bool((h0[s] >> 28) & 1) == bool(passes[i]) and ((h0[s] >> 12) & 0xFF) == recs[i]["mapq"]
+                        mask, has_ins = int(h1[s]) & 0xFFF, bool((h1[s] >> 28) & 1)
+                        ins_at, ins_len = (int(h1[s]) >> 12) & 15, (int(h1[s]) >> 16) & 0xFFF
+                        for p in range(W):
+                            x = w * W + p
+                            e = int(entries[s, p])
+                            st = (e >> 12) & 3
+                            if x not in by_pos:
+                                assert e == 0
+                                continue
+                            want_st, ch, q, y = by_pos[x]
+                            assert st == want_st
+                            if st == 1:
+                                assert (e & 0xFF) == q and SEQ_CHARS[(e >> 8) & 15] == ch and (mask >> p) & 1
+                                if not complex_:
+                                    qpos = (int(h0[s]) & 0xFFF) + bin(mask & ((1 << p) - 1)).count("1") + (ins_len if has_ins and p > ins_at else 0)
+                                    assert qpos == y, (i, x, recs[i]["cigar"])
+                        # overlap partner: the sector `off` away belongs to the linked read and points back
+                        off = (int(h0[s]) >> 20) & 0xFF
+                        off = off - 256 if off >= 128 else off
+                        linked = pk.mate[i] != 0xFFFFFFFF and (recs[i]["flag"] & 2) and not (recs[i]["flag"] & 8)
+                        if off:
+                            m = int(pk.mate[i] & 0x7FFFFFFF)
+                            assert linked and members[w][s - a + off] == m
+                            assert bool((h0[s] >> 30) & 1) == (i < m) and bool((h0[s] >> 29) & 1) == bool(pk.mate[i] >> 31)
+                        elif linked and not complex_:
+                            assert int(pk.mate[i] & 0x7FFFFFFF) not in members[w]
+            assert n_seen == sectors.shape[0]

@@ -1,0 +1,196 @@
+// vfkio_columns.cpp -- the reference-anchored column store (host side).
+//
+// The read-major HBM layout (vfkio_pack.cpp) makes a pileup column a gather: one header per candidate
+// read, one 32-byte payload sector per read somewhere else, the overlap partner's header and sector
+// somewhere else again.  This builder transposes the batch once: the reference is cut into windows of
+// VFK_COL_WIDTH (12) positions and every read leaves one 32-byte sector in every window it overlaps,
+// the sectors of a window stored together in read order.  A sector holds everything an SNV column
+// needs from that read at those 12 positions (include/vfk.h "column store"):
+//   12 entries of 16 bits   base quality | BAM base code << 8 | state << 12
+//                           (state 0 the read does not cover the position, 1 aligned base, 2 deletion,
+//                            3 reference skip -- htslib resolve_cigar2's is_del / is_refskip)
+//   header word 0           query position at the window start, MAPQ, offset of the overlap partner's
+//                           sector inside the same window (htslib overlap_push pairing, vfkio_link_mates),
+//                           read filter verdict (pysam __advance_samtools), tie-break and order bits
+//   header word 1           which positions hold aligned bases, and the one insertion inside the window
+// so that a column is ONE contiguous read of (depth x 32) bytes, the mate-overlap adjustment a register
+// exchange between two lanes, and no CIGAR is walked on the device.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+#include "vfk_io.h"
+
+int vfkio_fail(int code, const char *msg);
+
+namespace {
+constexpr int W = VFK_COL_WIDTH;
+inline bool consumes_ref(unsigned op) { return op == 0 || op == 2 || op == 3 || op == 7 || op == 8; }
+inline bool is_match(unsigned op) { return op == 0 || op == 7 || op == 8; }
+
+inline int64_t ref_span(const vfkio_reads *r, int64_t i) {
+    const uint32_t *c = r->cigar + r->cigar_off[i];
+    int64_t span = 0;
+    for (int k = 0; k < r->n_cigar[i]; ++k)
+        if (consumes_ref(c[k] & 15u)) span += c[k] >> 4;
+    return span;
+}
+inline bool passes(const vfkio_reads *r, int64_t i, const vfk_params *p) {
+    const uint32_t flag = r->flag[i];
+    if (flag & (p->flag_filter | 4u)) return false;
+    if ((int)r->mapq[i] < p->min_mapq) return false;
+    if (p->ignore_orphans && (flag & 1u) && !(flag & 2u)) return false;
+    return true;
+}
+int64_t placed_reads(const vfkio_reads *r) {
+    int64_t n = 0;
+    while (n < r->n && r->tid[n] >= 0) ++n;
+    return n;
+}
+
+struct Sector {
+    uint16_t e[W];
+    uint32_t h0, h1;
+};
+static_assert(sizeof(Sector) == 32, "a column-store sector is 32 bytes");
+}  // namespace
+
+extern "C" int vfkio_columns_plan(const vfkio_reads *r, int64_t *wbase /*[n_contigs+1]*/, vfkio_col_plan *plan) {
+    if (!r || !wbase || !plan) return vfkio_fail(VFK_EINVAL, "vfkio_columns_plan: NULL argument");
+    const int64_t n = placed_reads(r);
+    std::vector<int64_t> extent((size_t)r->n_contigs, 0);
+    int64_t sectors = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t span = ref_span(r, i);
+        if (span <= 0) continue;
+        const int64_t beg = r->pos[i], end = beg + span;
+        extent[(size_t)r->tid[i]] = std::max(extent[(size_t)r->tid[i]], end);
+        sectors += (end - 1) / W - beg / W + 1;
+    }
+    wbase[0] = 0;
+    for (int32_t t = 0; t < r->n_contigs; ++t) wbase[t + 1] = wbase[t] + (extent[(size_t)t] + W - 1) / W;
+    if (sectors >= ((int64_t)1 << 32)) return vfkio_fail(VFK_EUNSUPPORTED, "column store exceeds 2^32 sectors: split the batch");
+    plan->n_windows = wbase[r->n_contigs];
+    plan->n_sectors = sectors;
+    return VFK_OK;
+}
+
+extern "C" int vfkio_columns_fill(const vfkio_reads *r, const vfk_params *params, const uint32_t *mate, const int64_t *wbase,
+                                  const vfkio_col_plan *plan, uint32_t *woff /*[n_windows+1]*/, uint8_t *sectors_out) {
+    if (!r || !params || !mate || !wbase || !plan || !woff || (!sectors_out && plan->n_sectors))
+        return vfkio_fail(VFK_EINVAL, "vfkio_columns_fill: NULL argument");
+    const int64_t n = placed_reads(r);
+    const int64_t nw = plan->n_windows;
+    Sector *sec = reinterpret_cast<Sector *>(sectors_out);
+    // ---- sectors per window, offsets
+    std::vector<uint32_t> count((size_t)nw + 1, 0);
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t span = ref_span(r, i);
+        if (span <= 0) continue;
+        const int64_t w0 = wbase[r->tid[i]] + r->pos[i] / W, w1 = wbase[r->tid[i]] + (r->pos[i] + span - 1) / W;
+        for (int64_t w = w0; w <= w1; ++w) ++count[(size_t)w];
+    }
+    {
+        uint64_t acc = 0;
+        for (int64_t w = 0; w < nw; ++w) {
+            woff[w] = (uint32_t)acc;
+            acc += count[(size_t)w];
+        }
+        woff[nw] = (uint32_t)acc;
+        if ((int64_t)acc != plan->n_sectors) return vfkio_fail(VFK_EINVAL, "vfkio_columns_fill: plan does not match the batch");
+    }
+    // ---- fill, contig by contig (windows of different contigs are disjoint), reads in index order so that the
+    // sectors of a window are sorted by read
+    std::vector<uint32_t> sec_read((size_t)plan->n_sectors);  // owner of every sector, for the partner offsets
+    std::vector<int64_t> first_read((size_t)r->n_contigs + 1, n);
+    {
+        int64_t i = 0;
+        for (int32_t t = 0; t <= r->n_contigs; ++t) {
+            while (i < n && r->tid[i] < t) ++i;
+            first_read[(size_t)t] = i;
+        }
+    }
+    std::fill(count.begin(), count.end(), 0u);  // now the per-window cursor
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int32_t t = 0; t < r->n_contigs; ++t) {
+        for (int64_t i = first_read[(size_t)t]; i < first_read[(size_t)t + 1]; ++i) {
+            const uint32_t *c = r->cigar + r->cigar_off[i];
+            const int nc = r->n_cigar[i];
+            const uint8_t *q = r->qual + r->qual_off[i], *sq = r->seq + r->seq_off[i];
+            const bool pass = passes(r, i, params);
+            const uint32_t flag = r->flag[i];
+            const bool linked = params->ignore_overlaps && (flag & 2u) && !(flag & 8u) && mate[i] != VFK_NO_MATE;
+            const uint32_t m = mate[i] & 0x7FFFFFFFu;
+            const uint32_t h0_fixed = ((uint32_t)r->mapq[i] << 12) | (pass ? 1u << 28 : 0u) |
+                                      (linked && (mate[i] >> 31) ? 1u << 29 : 0u) | (linked && (uint32_t)i < m ? 1u << 30 : 0u);
+            int64_t x = r->pos[i], y = 0;
+            Sector cur;
+            int64_t cur_w = -1;
+            uint32_t qpos0 = 0, mask = 0, ins_at = 0, ins_len = 0;
+            bool has_ins = false, complex = false;
+            auto flush = [&]() {
+                if (cur_w < 0) return;
+                if (qpos0 >= 4096u || ins_len >= 4096u) complex = true;
+                cur.h0 = h0_fixed | (qpos0 & 0xFFFu) | (complex ? 1u << 31 : 0u);
+                cur.h1 = mask | (ins_at << 12) | ((ins_len & 0xFFFu) << 16) | (has_ins ? 1u << 28 : 0u);
+                const int64_t w = wbase[t] + cur_w;
+                const uint32_t at = woff[w] + count[(size_t)w]++;
+                sec[at] = cur;
+                sec_read[at] = (uint32_t)i;
+            };
+            auto enter = [&](int64_t w) {
+                flush();
+                cur_w = w;
+                memset(&cur, 0, sizeof(cur));
+                qpos0 = (uint32_t)y;
+                mask = 0; ins_at = 0; ins_len = 0;
+                has_ins = false; complex = false;
+            };
+            for (int k = 0; k < nc; ++k) {
+                const uint32_t op = c[k] & 15u;
+                const int64_t l = c[k] >> 4;
+                if (consumes_ref(op)) {
+                    for (int64_t j = 0; j < l; ++j, ++x) {
+                        if (x / W != cur_w) enter(x / W);
+                        const int p = (int)(x % W);
+                        if (is_match(op)) {
+                            const uint32_t code = (y & 1) ? (sq[y >> 1] & 15u) : (sq[y >> 1] >> 4);
+                            cur.e[p] = (uint16_t)(q[y] | (code << 8) | (1u << 12));
+                            mask |= 1u << p;
+                            ++y;
+                        } else {
+                            cur.e[p] = (uint16_t)((op == 3 ? 3u : 2u) << 12);
+                        }
+                    }
+                } else if (op == 1) {  // insertion: follows reference position x-1
+                    if (cur_w >= 0 && (x - 1) / W == cur_w && x % W != 0) {
+                        if (has_ins) complex = true;
+                        has_ins = true;
+                        ins_at = (uint32_t)((x - 1) % W);
+                        ins_len = (uint32_t)std::min<int64_t>(l, 4096);
+                    }
+                    y += l;
+                } else if (op == 4) {
+                    y += l;
+                }
+            }
+            flush();
+        }
+    }
+    // ---- partner offsets: the partner's sector inside the same window, found by read index (runs are sorted)
+#pragma omp parallel for schedule(dynamic, 4096)
+    for (int64_t w = 0; w < nw; ++w) {
+        const uint32_t a = woff[w], b = woff[w + 1];
+        for (uint32_t s = a; s < b; ++s) {
+            const int64_t i = sec_read[s];
+            const uint32_t flag = r->flag[i];
+            if (!(params->ignore_overlaps && (flag & 2u) && !(flag & 8u) && mate[i] != VFK_NO_MATE)) continue;
+            const uint32_t m = mate[i] & 0x7FFFFFFFu;
+            const uint32_t *lo = std::lower_bound(sec_read.data() + a, sec_read.data() + b, m);
+            if (lo == sec_read.data() + b || *lo != m) continue;  // the partner does not reach this window
+            const int64_t off = (int64_t)(lo - sec_read.data()) - (int64_t)s;
+            if (off < -127 || off > 127) sec[s].h0 |= 1u << 31;  // out of reach for one byte: leave the unit to the read-major path
+            else sec[s].h0 |= ((uint32_t)off & 0xFFu) << 20;
+        }
+    }
+    return VFK_OK;
+}

@@ -38,7 +38,13 @@ class _ReadBatchC(C.Structure):
     _fields_ = [("n_reads", C.c_int64), ("n_contigs", C.c_int32), ("max_l_qseq", C.c_int32),
                 ("contig_off", C.c_void_p), ("hot", C.c_void_p), ("cold", C.c_void_p), ("mate", C.c_void_p),
                 ("sb", C.c_void_p), ("cigar", C.c_void_p), ("payload", C.c_void_p),
-                ("n_cigar_words", C.c_int64), ("n_sectors", C.c_int64)]
+                ("n_cigar_words", C.c_int64), ("n_sectors", C.c_int64),
+                ("col_wbase", C.c_void_p), ("col_off", C.c_void_p), ("col_sectors", C.c_void_p),
+                ("n_col_windows", C.c_int64), ("n_col_sectors", C.c_int64)]
+
+
+class _ColPlanC(C.Structure):
+    _fields_ = [("n_windows", C.c_int64), ("n_sectors", C.c_int64)]
 
 
 class _VariantBatchC(C.Structure):
@@ -169,6 +175,14 @@ class PackedReads:
     cigar: np.ndarray
     payload: np.ndarray
     max_l_qseq: int
+    # column store (include/vfk.h), optional
+    col_wbase: Optional[np.ndarray] = None
+    col_off: Optional[np.ndarray] = None
+    col_sectors: Optional[np.ndarray] = None
+
+    @property
+    def has_columns(self) -> bool:
+        return self.col_off is not None
 
     @property
     def starts(self):
@@ -178,16 +192,20 @@ class PackedReads:
     def n_reads(self):
         return int(self.hot.shape[0])
 
+    def array_names(self):
+        base = ("contig_off", "hot", "cold", "mate", "sb", "cigar", "payload")
+        return base + (("col_wbase", "col_off", "col_sectors") if self.has_columns else ())
+
     def nbytes(self) -> int:
-        return int(sum(a.nbytes for a in (self.contig_off, self.hot, self.cold, self.mate, self.sb, self.cigar,
-                                          self.payload)))
+        return int(sum(getattr(self, k).nbytes for k in self.array_names()))
 
     def c_struct(self, arrays: Optional[Dict[str, int]] = None) -> _ReadBatchC:
-        p = arrays or {k: getattr(self, k).ctypes.data for k in
-                       ("contig_off", "hot", "cold", "mate", "sb", "cigar", "payload")}
+        p = arrays or {k: getattr(self, k).ctypes.data for k in self.array_names()}
         s = _ReadBatchC()
         s.n_reads, s.n_contigs, s.max_l_qseq = self.n_reads, len(self.contigs), self.max_l_qseq
         s.n_cigar_words, s.n_sectors = int(self.cigar.shape[0]), int(self.payload.shape[0] // 32)
+        if self.has_columns:
+            s.n_col_windows, s.n_col_sectors = int(self.col_off.shape[0] - 1), int(self.col_sectors.shape[0] // 32)
         for k, v in p.items():
             setattr(s, k, v)
         return s
@@ -211,9 +229,11 @@ def read_passes(batch: ReadBatch, params: ParamsC) -> np.ndarray:
     return ok & (batch.tid >= 0)
 
 
-def pack_reads(batch: ReadBatch, params: ParamsC, pinned: bool = False, mate: np.ndarray = None) -> PackedReads:
+def pack_reads(batch: ReadBatch, params: ParamsC, pinned: bool = False, mate: np.ndarray = None,
+               columns: bool = False) -> PackedReads:
     """Canonical batch -> HBM layout (+ mate links under `params`, unless given: a slice of a larger batch
-    must carry the links computed on the whole batch)."""
+    must carry the links computed on the whole batch).  columns=True also builds the reference-anchored column
+    store (include/vfk.h) the SNV kernel reads; it bakes in the read filter of `params`."""
     s, keep = _io_reads(batch)
     plan = _PlanC()
     _io_check(libio().vfkio_pack_plan(C.byref(s), C.byref(plan)))
@@ -234,8 +254,19 @@ def pack_reads(batch: ReadBatch, params: ParamsC, pinned: bool = False, mate: np
     else:
         mate_out[:] = np.asarray(mate, np.uint32)[:n]
     mate = mate_out
-    return PackedReads(list(batch.contigs), contig_off, hot, cold, mate, sb.reshape(-1, 2), cigar, payload,
-                       int(plan.max_l_qseq))
+    packed = PackedReads(list(batch.contigs), contig_off, hot, cold, mate, sb.reshape(-1, 2), cigar, payload,
+                         int(plan.max_l_qseq))
+    if columns:
+        wbase = np.empty(len(batch.contigs) + 1, np.int64)
+        cp = _ColPlanC()
+        _io_check(libio().vfkio_columns_plan(C.byref(s), C.c_void_p(wbase.ctypes.data), C.byref(cp)))
+        woff = _empty(cp.n_windows + 1, np.uint32, pinned)
+        sectors = _empty(cp.n_sectors * 32, np.uint8, pinned)
+        _io_check(libio().vfkio_columns_fill(C.byref(s), C.byref(params), C.c_void_p(mate.ctypes.data),
+                                             C.c_void_p(wbase.ctypes.data), C.byref(cp), C.c_void_p(woff.ctypes.data),
+                                             C.c_void_p(sectors.ctypes.data)))
+        packed.col_wbase, packed.col_off, packed.col_sectors = wbase, woff, sectors
+    return packed
 
 
 def units_c_struct(u: VariantUnits, stop: Optional[np.ndarray], ptrs: Optional[Dict[str, int]] = None) -> _VariantBatchC:
@@ -258,7 +289,7 @@ class DeviceReads:
         import torch
         self.packed = packed
         self.t = {}
-        for k in ("contig_off", "hot", "cold", "mate", "sb", "cigar", "payload"):
+        for k in packed.array_names():
             a = getattr(packed, k)
             h = torch.from_numpy(a.view(np.uint8).reshape(-1)) if a.size else torch.zeros(16, dtype=torch.uint8)
             self.t[k] = h.to(device, non_blocking=non_blocking) if a.size else h.to(device)
