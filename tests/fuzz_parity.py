@@ -19,6 +19,7 @@ from vafator_b200.batch import build_units  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--seconds", type=float, default=300)
 ap.add_argument("--seed0", type=int, default=1)
+ap.add_argument("--columns", action="store_true", help="evaluate SNV units from the column store")
 a = ap.parse_args()
 dev = device.Device(0)
 t_end = time.time() + a.seconds
@@ -58,7 +59,7 @@ while time.time() < t_end:
           for i, j in zip(units.rec, units.alt_index)]
     want = c_oracle.pileup(batch.as_dict(), ou, c_oracle.params(min_mapq=mq, min_baseq=bq))
     params = device.make_params(min_mapq=mq, min_baseq=bq, include_ambiguous=amb)
-    buf = dev.pileup(dev.upload_reads(device.pack_reads(batch, params)), dev.upload_units(units, stop), params)
+    buf = dev.pileup(dev.upload_reads(device.pack_reads(batch, params, columns=a.columns)), dev.upload_units(units, stop), params)
     dev.sync()
     got = dev.to_host(buf, device.COUNTS_DTYPE, units.n_units)
     snv = (got["status"] & 3) == 0

@@ -17,6 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--tiles", type=int, default=200_000)
 ap.add_argument("--launches", type=int, default=6)
 ap.add_argument("--workload", default="wes")
+ap.add_argument("--columns", action="store_true", help="evaluate SNV units from the column store")
 ap.add_argument("--snv-period", type=int, default=500, help="wes: one SNV per this many target bases (small = L2-resident reads, many units)")
 a = ap.parse_args()
 cfg = {"wes": lambda: synth.wes(n_tiles=a.tiles, snv_period=a.snv_period), "wgs": lambda: synth.wgs(contig_len=a.tiles * 4096 // 10),
@@ -27,7 +28,7 @@ recs = synth.variant_records(cfg)
 units = build_units(recs, cfg.contigs)
 params = device.make_params(min_mapq=1, min_baseq=30)
 dev = device.Device(0)
-dreads = dev.upload_reads(device.pack_reads(batch, params))
+dreads = dev.upload_reads(device.pack_reads(batch, params, columns=a.columns))
 dunits = dev.upload_units(units, None)
 out = dev.alloc_counts(units.n_units)
 print("setup %.1f s: %d reads, %d units" % (time.time() - t0, batch.n_reads, units.n_units), flush=True)

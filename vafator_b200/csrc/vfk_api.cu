@@ -225,6 +225,10 @@ static void to_dev(const vfk_read_batch *r, const vfk_variant_batch *v, vfk::Rea
     R.contig_off = r->contig_off;
     R.n_reads = r->n_reads;
     R.n_contigs = r->n_contigs;
+    const bool columns = r->col_off && r->col_wbase && r->col_sectors;
+    R.col_wbase = columns ? r->col_wbase : nullptr;
+    R.col_off = columns ? r->col_off : nullptr;
+    R.col_sectors = columns ? (const uint32_t *)r->col_sectors : nullptr;
     V.n = v->n_units;
     V.tid = v->tid;
     V.pos = v->pos;
@@ -246,7 +250,7 @@ extern "C" int vfk_pileup(vfk_handle *h, const vfk_read_batch *reads, const vfk_
     cudaStream_t st = (cudaStream_t)stream;  // NULL = the CUDA default stream
     rc = h->deferred.reserve((size_t)units->n_units * 2 * sizeof(uint32_t));
     if (rc) return rc;
-    rc = h->resolved.reserve((size_t)units->n_units * 32);
+    rc = h->resolved.reserve((size_t)units->n_units * 48);  // located unit + column unit
     if (rc) return rc;
     vfk::ReadsDev R;
     vfk::UnitsDev V;
@@ -416,10 +420,13 @@ extern "C" int vfk_annotate_host_async(vfk_handle *h, const vfk_read_batch *read
     // transfer; otherwise the index and the unit arrays are staged and the locate kernel runs.
     rc = S.deferred.reserve((size_t)nu * 2 * sizeof(uint32_t));
     if (rc) return rc;
-    rc = S.resolved.reserve((size_t)nu * sizeof(vfk::ResolvedUnit));
+    rc = S.resolved.reserve((size_t)nu * 48);  // located unit + column unit
     if (rc) return rc;
     STAGE(S.ins, units->ins_seq, (size_t)(units->n_ins_seq > 0 ? units->n_ins_seq : 1));
     vfk_read_batch dr = *reads;
+    dr.col_wbase = nullptr;  // the host entry point reads the read-major arrays only
+    dr.col_off = nullptr;
+    dr.col_sectors = nullptr;
     vfk_variant_batch dv = *units;
     dv.ins_seq = (const uint8_t *)S.ins.p;
     int launches = 0;

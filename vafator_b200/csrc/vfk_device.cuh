@@ -28,6 +28,10 @@ struct ReadsDev {
     const int64_t *__restrict__ contig_off;
     int64_t n_reads;
     int32_t n_contigs;
+    // column store (vfk.h), nullptr when absent
+    const int64_t *__restrict__ col_wbase;
+    const uint32_t *__restrict__ col_off;
+    const uint32_t *__restrict__ col_sectors;  // 8 words per sector
 };
 
 struct UnitsDev {

@@ -53,7 +53,8 @@ struct Layout {
 //        no earlier read can overlap the column
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-locate_kernel(ReadsDev R, UnitsDev V, ResolvedUnit *__restrict__ res, unsigned long long *__restrict__ cand_sum) {
+locate_kernel(ReadsDev R, UnitsDev V, ResolvedUnit *__restrict__ res, uint4 *__restrict__ cunits,
+              unsigned long long *__restrict__ cand_sum) {
     const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= V.n) return;
     const int32_t tid = __ldg(V.tid + u);
@@ -95,6 +96,18 @@ locate_kernel(ReadsDev R, UnitsDev V, ResolvedUnit *__restrict__ res, unsigned l
     const uint4 *q = reinterpret_cast<const uint4 *>(&r);
     o[0] = q[0];
     o[1] = q[1];
+    if (cunits) {  // column store: the window of the column -> its run of sectors
+        const int32_t w = col / VFK_COL_WIDTH;
+        uint32_t off = 0, cnt = 0;
+        if (known && col >= 0) {
+            const int64_t w0 = __ldg(R.col_wbase + tid), w1 = __ldg(R.col_wbase + tid + 1);
+            if (w0 + w < w1) {
+                off = __ldg(R.col_off + w0 + w);
+                cnt = __ldg(R.col_off + w0 + w + 1) - off;
+            }
+        }
+        cunits[u] = make_uint4(off, cnt, (uint32_t)(col - w * VFK_COL_WIDTH), r.meta);
+    }
     if (cand_sum) {  // total candidate reads of the batch: lets the host entry pick its transfer strategy
         const unsigned active = __activemask();
         const unsigned mine = r.hi - r.lo;
@@ -556,6 +569,208 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
 }
 
 // ------------------------------------------------------------------------------------------
+// warp per unit on the column store (SNV units): the reads of a column are ONE contiguous run of
+// 32-byte sectors -- lane = sector, one 4-byte entry word + the 8-byte header per lane -- the read filter
+// verdict, the query position and the overlap partner's whereabouts come with the sector, and the
+// partner's base is a register of another lane.  No header gather, no CIGAR, no dependent loads.
+// What it cannot serve goes to the read-major kernels through the same device-side lists: units that are
+// not SNVs, windows deeper than 64 sectors, a passing read inside a deletion at the column (its
+// base-quality filter looks at the next base and at the push timing of its mate), a sector flagged unusable.
+// ------------------------------------------------------------------------------------------
+#ifndef VFK_COL_MIN_CTAS
+#define VFK_COL_MIN_CTAS 5
+#endif
+struct ColRead {  // one sector as a lane holds it
+    uint32_t e;   // the 16-bit entry of the column
+    uint32_t h0, h1;
+};
+__device__ __forceinline__ ColRead load_col_read(const uint32_t *__restrict__ sectors, uint32_t sector, uint32_t p) {
+    const uint32_t *w = sectors + (size_t)sector * 8u;
+    ColRead c;
+    c.e = (__ldg(w + (p >> 1)) >> ((p & 1u) * 16u)) & 0xFFFFu;
+    const uint2 h = __ldg(reinterpret_cast<const uint2 *>(w + 6));
+    c.h0 = h.x;
+    c.h1 = h.y;
+    return c;
+}
+// htslib tweak_overlap_quality at one position (both reads show an aligned base): the quality this read keeps
+__device__ __forceinline__ int overlap_quality(uint32_t mine, uint32_t theirs, uint32_t h0) {
+    const int qi = (int)(mine & 0xFFu), qm = (int)(theirs & 0xFFu);
+    const uint32_t sel = (h0 >> 29) & 1u;
+    const uint32_t mymul = (h0 >> 30) & 1u ? sel : 1u - sel;  // the earlier record holds the hash slot
+    if (((mine ^ theirs) & 0xF00u) == 0u) {
+        const int s = min(qi + qm, 200);
+        return mymul ? s : 0;
+    }
+    if (qi > qm) return (qi * 4) / 5;
+    if (qi < qm) return 0;
+    return mymul ? (qi * 4) / 5 : 0;
+}
+// one sector -> the packed contribution (Eval.pk / Eval.fl); `partner` is the partner's entry or 0
+__device__ __forceinline__ void col_evaluate(const ColRead &c, uint32_t partner, uint32_t p, const vfk_params &P, uint32_t ref_code,
+                                             uint32_t alt_code, uint32_t &pk, uint32_t &fl) {
+    pk = 0u;
+    fl = 0u;
+    const uint32_t state = (c.e >> 12) & 3u;
+    if (state == 0u) return;
+    fl = FL_COVERS;
+    if (!((c.h0 >> 28) & 1u)) return;
+    fl |= FL_IN_COL;
+    if (state != 1u) return;  // reference skip: in the column, nothing else (deletions never get here)
+    int q = (int)(c.e & 0xFFu);
+    if (((partner >> 12) & 3u) == 1u) q = overlap_quality(c.e, partner, c.h0);
+    if (q < P.min_baseq) return;  // pysam pileup_base_qual_skip
+    fl |= FL_IN_DP;
+    const uint32_t code = (c.e >> 8) & 15u;
+    if (code_is_ambiguous((int)code)) fl |= FL_AMBIGUOUS;
+    const uint32_t lists = (code == ref_code ? PK_REF : 0u) | (code == alt_code ? PK_ALT : 0u);
+    if (lists) {
+        const uint32_t below = c.h1 & 0xFFFu & ((1u << p) - 1u);
+        const uint32_t ins = ((c.h1 >> 28) & 1u) && p > ((c.h1 >> 12) & 15u) ? (c.h1 >> 16) & 0xFFFu : 0u;
+        const uint32_t qpos = (c.h0 & 0xFFFu) + (uint32_t)__popc(below) + ins;
+        pk = ((c.h0 >> 12) & 0xFFu) | ((uint32_t)q << 8) | (qpos << 16) | lists;
+    }
+}
+
+template <int POSB>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, VFK_COL_MIN_CTAS)
+pileup_column_kernel(ReadsDev R, const uint4 *__restrict__ cunits, const ResolvedUnit *__restrict__ res, int64_t n_units, vfk_params P,
+                     vfk_counts *__restrict__ out,
+                     unsigned long long *__restrict__ work_counter, uint32_t *__restrict__ block_list,
+                     uint32_t *__restrict__ n_block, uint32_t *__restrict__ warp_list, uint32_t *__restrict__ n_warp) {
+    using L = Layout<POSB>;
+    __shared__ uint32_t stage_all[WARPS_PER_CTA][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t *stage = stage_all[warp];
+    const int64_t n_warps = (int64_t)gridDim.x * WARPS_PER_CTA;
+    int64_t last_base = 0;
+    const uint32_t *__restrict__ sectors = R.col_sectors;
+
+    for (;;) {
+        unsigned long long base = 0;
+        const int64_t left = n_units - last_base;  // as of this warp's previous visit
+        const int grab = left > 16 * n_warps ? GRAB : left > 4 * n_warps ? 2 : 1;
+        if (lane == 0) base = atomicAdd(work_counter, (unsigned long long)grab);
+        base = __shfl_sync(FULL, base, 0);
+        if ((int64_t)base >= n_units) break;
+        last_base = (int64_t)base;
+        const int n_here = (int)min((int64_t)grab, n_units - (int64_t)base);
+        uint4 cu = make_uint4(0, 0, 0, 0);  // lane j keeps the column unit of unit base+j
+        if (lane < n_here) cu = __ldg(cunits + base + lane);
+        // software pipeline: the first 32 sectors of the NEXT unit are requested before the current one is processed
+        ColRead next;
+        next.e = next.h0 = next.h1 = 0u;
+        {
+            const uint32_t off0 = __shfl_sync(FULL, cu.x, 0), cnt0 = __shfl_sync(FULL, cu.y, 0), p0 = __shfl_sync(FULL, cu.z, 0);
+            if ((uint32_t)lane < cnt0) next = load_col_read(sectors, off0 + lane, p0);
+        }
+        for (int j = 0; j < n_here; ++j) {
+            const int64_t u = (int64_t)base + j;
+            const uint32_t off = __shfl_sync(FULL, cu.x, j), cnt = __shfl_sync(FULL, cu.y, j), p = __shfl_sync(FULL, cu.z, j);
+            const uint32_t meta = __shfl_sync(FULL, cu.w, j);
+            const uint32_t kind = meta & 3u, ref_code = (meta >> 8) & 0xFFu, alt_code = (meta >> 16) & 0xFFu;
+            ColRead c0 = next;
+            if (j + 1 < n_here) {
+                const uint32_t off1 = __shfl_sync(FULL, cu.x, j + 1), cnt1 = __shfl_sync(FULL, cu.y, j + 1);
+                const uint32_t p1 = __shfl_sync(FULL, cu.z, j + 1);
+                if ((uint32_t)lane < cnt1) next = load_col_read(sectors, off1 + lane, p1);
+            }
+            int med2[3][2] = {{-1, -1}, {-1, -1}, {-1, -1}};
+            uint64_t s2[3] = {0, 0, 0};
+            if (kind != VFK_KIND_SNV || cnt > 64u) {  // not for this kernel: the read-major kernels take it
+                if (lane == 0) {
+                    const uint32_t n_cand = __ldg(&res[u].hi) - __ldg(&res[u].lo);
+                    if (n_cand > (uint32_t)WARP_PATH_MAX_CAND) block_list[atomicAdd(n_block, 1u)] = (uint32_t)u;
+                    else warp_list[atomicAdd(n_warp, 1u)] = (uint32_t)u;
+                    store_counts(out + u, 0, 0, 0, 0, med2, s2, kind | VFK_ST_DEFERRED, cnt, 0u);
+                }
+                continue;
+            }
+            if (cnt == 0u) {
+                if (lane == 0) store_counts(out + u, 0, 0, 0, 0, med2, s2, kind, 0u, 0u);
+                continue;
+            }
+            if ((uint32_t)lane >= cnt) c0.e = c0.h0 = c0.h1 = 0u;
+            ColRead c1;
+            c1.e = c1.h0 = c1.h1 = 0u;
+            if (cnt > 32u && (uint32_t)lane + 32u < cnt) c1 = load_col_read(sectors, off + 32u + lane, p);
+            // overlap partners: sector k + offset of the same run, i.e. an entry another lane holds
+            const int off0 = (int)(int8_t)((c0.h0 >> 20) & 0xFFu), off1 = (int)(int8_t)((c1.h0 >> 20) & 0xFFu);
+            const int k0p = lane + off0, k1p = 32 + lane + off1;
+            const uint32_t a0 = __shfl_sync(FULL, c0.e, k0p & 31), b0 = __shfl_sync(FULL, c1.e, k0p & 31);
+            uint32_t partner0 = off0 ? (k0p < 32 ? a0 : b0) : 0u, partner1 = 0u;
+            if (cnt > 32u) {
+                const uint32_t a1 = __shfl_sync(FULL, c0.e, k1p & 31), b1 = __shfl_sync(FULL, c1.e, k1p & 31);
+                partner1 = off1 ? (k1p < 32 ? a1 : b1) : 0u;
+            }
+            // a passing read inside a deletion, or an unusable sector: the read-major path decides
+            const bool in0 = ((c0.e >> 12) & 3u) != 0u && ((c0.h0 >> 28) & 1u), in1 = ((c1.e >> 12) & 3u) != 0u && ((c1.h0 >> 28) & 1u);
+            const bool hard = (in0 && (((c0.e >> 12) & 3u) == 2u || (c0.h0 >> 31))) || (in1 && (((c1.e >> 12) & 3u) == 2u || (c1.h0 >> 31)));
+            Eval e0, e1;
+            e0.alt = e1.alt = 0u;
+            col_evaluate(c0, partner0, p, P, ref_code, alt_code, e0.pk, e0.fl);
+            col_evaluate(c1, partner1, p, P, ref_code, alt_code, e1.pk, e1.fl);
+            const bool k0 = e0.pk != 0u, k1 = e1.pk != 0u;
+            const uint32_t m0 = __ballot_sync(FULL, k0), m1 = __ballot_sync(FULL, k1);
+            uint32_t pk = e0.pk;
+            if (m1) {  // move the second chunk's contributions into lanes the first one left free
+                const int n1 = __popc(m1);
+                if (k1) stage[__popc(m1 & lt_mask)] = e1.pk;
+                __syncwarp();
+                if (!k0) {
+                    const int f = __popc(~m0 & lt_mask);
+                    if (f < n1) pk = stage[f];
+                }
+                __syncwarp();
+            }
+            SlotShape sh;
+            sh.is_ref = pk & PK_REF;
+            sh.is_alt = pk & PK_ALT;
+            sh.R = __ballot_sync(FULL, sh.is_ref);
+            sh.A = __ballot_sync(FULL, sh.is_alt);
+            if (__any_sync(FULL, hard) || __popc(m0) + __popc(m1) > 32 || (sh.R & sh.A)) {
+                if (lane == 0) {
+                    warp_list[atomicAdd(n_warp, 1u)] = (uint32_t)u;
+                    store_counts(out + u, 0, 0, 0, 0, med2, s2, kind | VFK_ST_DEFERRED, cnt, 0u);
+                }
+                continue;
+            }
+            const uint32_t tally = __reduce_add_sync(FULL, e0.fl + e1.fl);
+            const int n_cover = (int)(tally & 0xFFu), n_col = (int)((tally >> 8) & 0xFFu), n_amb = (int)(tally >> 24);
+            int dp = (int)((tally >> 16) & 0xFFu);
+            const int ac_ref = __popc(sh.R), ac_alt = __popc(sh.A);
+            if (sh.R | sh.A) {
+                uint32_t lt, eq, w;
+                const uint32_t mq = pk & 0xFFu, bq = (pk >> 8) & 0xFFu, qp = (pk >> 16) & 0xFFFu;
+                sh.R_low = sh.R & lt_mask; sh.A_low = sh.A & lt_mask;
+                sh.r1 = (ac_ref - 1) >> 1; sh.a1 = (ac_alt - 1) >> 1;
+                sh.dr = (uint32_t)(ac_ref >> 1) - (uint32_t)sh.r1; sh.da = (uint32_t)(ac_alt >> 1) - (uint32_t)sh.a1;
+                sh.sh_r = 1u - sh.dr; sh.sh_a = 17u - sh.da;
+                radix_compare<8>(mq, sh.R | sh.A, lt, eq);
+                uint32_t term = radix_finish(mq, lt, eq, sh, w);
+                med2[0][0] = ac_ref ? (int)(w & 0xFFFFu) : -1; med2[0][1] = ac_alt ? (int)(w >> 16) : -1;
+                radix_compare<8>(bq, sh.R | sh.A, lt, eq);
+                term |= radix_finish(bq, lt, eq, sh, w) << 10;
+                med2[1][0] = ac_ref ? (int)(w & 0xFFFFu) : -1; med2[1][1] = ac_alt ? (int)(w >> 16) : -1;
+                radix_compare<L::POS_BITS>(qp, sh.R | sh.A, lt, eq);
+                term |= radix_finish(qp, lt, eq, sh, w) << 20;
+                med2[2][0] = ac_ref ? (int)(w & 0xFFFFu) : -1; med2[2][1] = ac_alt ? (int)(w >> 16) : -1;
+                if (ac_ref && ac_alt) {
+                    const uint32_t sums = __reduce_add_sync(FULL, term);
+                    const uint64_t base2 = (uint64_t)(ac_alt * ac_alt + ac_alt);
+                    s2[0] = base2 + (sums & 0x3FFu);
+                    s2[1] = base2 + ((sums >> 10) & 0x3FFu);
+                    s2[2] = base2 + (sums >> 20);
+                }
+            }
+            if (!P.include_ambiguous) dp -= n_amb;  // pileups.py:224-227
+            if (lane == 0) store_counts(out + u, dp, n_amb, ac_ref, ac_alt, med2, s2, kind, cnt, (uint32_t)n_cover, (uint32_t)n_col);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // warp per listed unit, shared-memory histograms
 // ------------------------------------------------------------------------------------------
 template <int POSB>
@@ -679,7 +894,8 @@ pileup_block_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, const uint
 cudaError_t launch_locate(const ReadsDev &R, const UnitsDev &V, void *resolved, unsigned long long *cand_sum, cudaStream_t stream,
                           int *launches) {
     if (V.n <= 0) return cudaSuccess;
-    locate_kernel<<<(unsigned)((V.n + 255) / 256), 256, 0, stream>>>(R, V, (ResolvedUnit *)resolved, cand_sum);
+    uint4 *cunits = R.col_off ? reinterpret_cast<uint4 *>((char *)resolved + (size_t)V.n * sizeof(ResolvedUnit)) : nullptr;
+    locate_kernel<<<(unsigned)((V.n + 255) / 256), 256, 0, stream>>>(R, V, (ResolvedUnit *)resolved, cunits, cand_sum);
     ++*launches;
     return cudaGetLastError();
 }
@@ -717,8 +933,19 @@ static cudaError_t launch_posb(const ReadsDev &R, const UnitsDev &V, const vfk_p
     if (want < grid) grid = want < 1 ? 1 : want;
     e = cudaMemsetAsync(counters, 0, 24, stream);
     if (e != cudaSuccess) return e;
-    pileup_warp_kernel<POSB><<<(unsigned)grid, WARPS_PER_CTA * 32, 0, stream>>>(R, res, V.n, V.ins_seq, P, out, work, block_list,
-                                                                                n_block, warp_list, n_warp);
+    if (R.col_off) {  // column store: SNV units from contiguous sector runs, the rest through the lists
+        int col_ctas = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&col_ctas, pileup_column_kernel<POSB>, WARPS_PER_CTA * 32, 0);
+        if (e != cudaSuccess) return e;
+        int64_t col_grid = (int64_t)sm_count * std::max(col_ctas, 1);
+        if (want < col_grid) col_grid = want < 1 ? 1 : want;
+        const uint4 *cunits = reinterpret_cast<const uint4 *>((const char *)res + (size_t)V.n * sizeof(ResolvedUnit));
+        pileup_column_kernel<POSB><<<(unsigned)col_grid, WARPS_PER_CTA * 32, 0, stream>>>(R, cunits, res, V.n, P, out, work,
+                                                                                        block_list, n_block, warp_list, n_warp);
+    } else {
+        pileup_warp_kernel<POSB><<<(unsigned)grid, WARPS_PER_CTA * 32, 0, stream>>>(R, res, V.n, V.ins_seq, P, out, work, block_list,
+                                                                                    n_block, warp_list, n_warp);
+    }
     ++*launches;
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
