@@ -223,6 +223,9 @@ int64_t vfk_zero_copy_batches(vfk_handle *h);
  * bulk copies, out[1] batches whose payload was gathered (zero copy), out[2] batches whose hot / mate
  * headers were gathered too, out[3] batches located on the host                                    */
 int vfk_transfer_stats(vfk_handle *h, int64_t out[4]);
+/* how many batches of the host entry point evaluated their SNV units from the column store (page-locked
+ * buffers, units located on the host; VFK_HOST_COLUMNS=0 keeps to the read-major arrays)               */
+int64_t vfk_column_batches(vfk_handle *h);
 
 /* ---- list-shaped auxiliaries (DEVICE pointers) ------------------------------------------------
  * vfk_pileup_values: per unit, the per-read values the reference keeps in all_mqs / all_bqs /

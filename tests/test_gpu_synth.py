@@ -234,3 +234,58 @@ def test_short_parity_campaign():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "fuzz ok" in r.stdout
+
+
+@pytest.mark.parametrize("name", ["wes", "wgs_indels", "amplicon_1000x", "noisy_cigars"])
+def test_column_store_kernel_matches_read_major_kernels(dev, name):
+    """With a column store in the batch SNV units are evaluated from contiguous sector runs (pileup_column_kernel);
+    every field but the diagnostic n_cand equals what the read-major kernels return, and both equal the oracle."""
+    make, thresholds = CASES[name]
+    batch, recs, units, stop, ounits = _setup(make())
+    for mq, bq in thresholds[:2]:
+        params = device.make_params(min_mapq=mq, min_baseq=bq)
+        got = {}
+        for columns in (False, True):
+            dreads = dev.upload_reads(device.pack_reads(batch, params, columns=columns))
+            buf = dev.pileup(dreads, dev.upload_units(units, stop), params)
+            dev.sync()
+            got[columns] = dev.to_host(buf, device.COUNTS_DTYPE, units.n_units)
+        both = (got[False]["ac_ref"] > 0) & (got[False]["ac_alt"] > 0)  # the rank sums exist only then
+        for f in got[True].dtype.names:
+            if f == "s2":
+                assert np.array_equal(got[True][f][both], got[False][f][both]), f
+            elif f != "n_cand":
+                assert np.array_equal(got[True][f], got[False][f]), f
+        _compare(got[True], c_oracle.pileup(batch.as_dict(), ounits, c_oracle.params(min_mapq=mq, min_baseq=bq)))
+
+
+def test_host_entry_point_reads_the_column_store_in_place(dev, monkeypatch):
+    """Page-locked batch with a column store: vfk_annotate_host gathers the sector runs straight from host memory and
+    returns exactly what the device-resident call returns; VFK_HOST_COLUMNS=0 falls back to the read-major arrays."""
+    for k in ("VFK_HOST_LOCATE", "VFK_ZERO_COPY_PAYLOAD", "VFK_ZERO_COPY_HOT", "VFK_HOST_COLUMNS"):
+        monkeypatch.delenv(k, raising=False)
+    cfg = synth.wes(n_tiles=3000, indel_period=700, multiallelic_pct=5)
+    batch, recs, units, stop, _ = _setup(cfg)
+    params = device.make_params(min_mapq=1, min_baseq=30)
+    packed = device.pack_reads(batch, params, pinned=True, columns=True)
+    dreads = dev.upload_reads(packed)
+    eaf = np.full(units.n_units, 0.4)
+    counts_dev = dev.pileup(dreads, dev.upload_units(units, stop), params)
+    stats_dev = dev.epilogue(units.n_units, counts_dev, dev.torch.as_tensor(eaf, device=dev.device), 5e-7, 1e-3)
+    dev.sync()
+    want_c = dev.to_host(counts_dev, device.COUNTS_DTYPE, units.n_units)
+    want_s = dev.to_host(stats_dev, device.STATS_DTYPE, units.n_units)
+    before = dev.column_batches()
+    got_c, got_s = dev.annotate_host(packed, units, stop, params, eaf, 5e-7, 1e-3)
+    assert dev.column_batches() == before + 1
+    assert got_c.tobytes() == want_c.tobytes() and got_s.tobytes() == want_s.tobytes()
+    monkeypatch.setenv("VFK_HOST_COLUMNS", "0")
+    alt_c, alt_s = dev.annotate_host(packed, units, stop, params, eaf, 5e-7, 1e-3)
+    assert dev.column_batches() == before + 1
+    both = (want_c["ac_ref"] > 0) & (want_c["ac_alt"] > 0)
+    for f in alt_c.dtype.names:
+        if f == "s2":
+            assert np.array_equal(alt_c[f][both], want_c[f][both]), f
+        elif f != "n_cand":
+            assert np.array_equal(alt_c[f], want_c[f]), f
+    assert alt_s.tobytes() == want_s.tobytes()

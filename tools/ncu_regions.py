@@ -36,7 +36,7 @@ def functions_of(path):
 
 def main():
     rep, n_units = sys.argv[1], float(sys.argv[2])
-    want = "pileup_warp_kernel"
+    want = sys.argv[3] if len(sys.argv) > 3 and not sys.argv[3].startswith("--") else "pileup_warp_kernel"
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "vafator_b200", "libvfk.so")], cwd=tmp, capture_output=True)
     cubin = [f for f in os.listdir(tmp) if f.startswith("vfk_pileup") and f.endswith(".cubin")][0]

@@ -115,7 +115,7 @@ struct vfk_handle {
     int64_t launches = 0;
     Slot slot[2];
     int next_slot = 0;
-    int64_t zero_copy_batches = 0, zero_copy_hot_batches = 0, host_located_batches = 0, staged_bytes = 0;
+    int64_t zero_copy_batches = 0, zero_copy_hot_batches = 0, host_located_batches = 0, staged_bytes = 0, column_batches = 0;
     // Carter k / d per depth for the last (fpr, error_rate) seen, depths [0, CARTER_DEPTHS)
     DevBuf carter;
     double carter_fpr = -1.0, carter_err = -1.0;
@@ -337,7 +337,7 @@ static const void *pinned_alias(const void *host) {
 // position index (8 bytes per read) is not worth shipping -- the units are located here, from the
 // caller's host arrays, and only the 32-byte records cross the bus.  VCF order makes consecutive units
 // neighbours in the index, so each search gallops forward from the previous answer.
-static unsigned long long locate_host(const vfk_read_batch *r, const vfk_variant_batch *v, vfk::ResolvedUnit *out) {
+static unsigned long long locate_host(const vfk_read_batch *r, const vfk_variant_batch *v, vfk::ResolvedUnit *out, uint4 *cunits) {
     const int64_t nu = v->n_units;
     const int32_t *sb = r->sb;
     unsigned long long total = 0;
@@ -379,6 +379,15 @@ static unsigned long long locate_host(const vfk_read_batch *r, const vfk_variant
             q.stop = v->stop ? v->stop[u] : 0x7FFFFFFF;
             q.c1 = (uint32_t)c1;
             out[u] = q;
+            if (cunits) {  // column store: the run of sectors of the column's window (as locate_kernel does)
+                const int32_t w = col / VFK_COL_WIDTH;
+                uint32_t off = 0, cnt = 0;
+                if (known && col >= 0 && r->col_wbase[tid] + w < r->col_wbase[tid + 1]) {
+                    off = r->col_off[r->col_wbase[tid] + w];
+                    cnt = r->col_off[r->col_wbase[tid] + w + 1] - off;
+                }
+                cunits[u] = make_uint4(off, cnt, (uint32_t)(col - w * VFK_COL_WIDTH), q.meta);
+            }
             total += q.hi - q.lo;
             prev_tid = known ? tid : -1;
             prev_col = col;
@@ -434,12 +443,21 @@ extern "C" int vfk_annotate_host_async(vfk_handle *h, const vfk_read_batch *read
     const char *env_loc = getenv("VFK_HOST_LOCATE");
     const bool host_locate = env_loc ? env_loc[0] == '1' : nu * 64 <= nr;
     unsigned long long candidates = 0;
+    // The column store takes part when it can be gathered in place: units located on the host (its window table
+    // is a host array) and every buffer the kernels touch page-locked.
+    const void *z_col = (reads->col_wbase && reads->col_off && reads->col_sectors) ? pinned_alias(reads->col_sectors) : nullptr;
+    const char *env_col = getenv("VFK_HOST_COLUMNS");
+    const bool host_columns = host_locate && z_col && pinned_alias(reads->payload) && pinned_alias(reads->cold) &&
+                              pinned_alias(reads->hot) && pinned_alias(reads->mate) && !(env_col && env_col[0] == '0') &&
+                              !getenv("VFK_ZERO_COPY_PAYLOAD") && !getenv("VFK_ZERO_COPY_HOT");
     if (host_locate) {
-        rc = S.h_resolved.reserve((size_t)nu * sizeof(vfk::ResolvedUnit));
+        const size_t per_unit = sizeof(vfk::ResolvedUnit) + (host_columns ? sizeof(uint4) : 0);
+        rc = S.h_resolved.reserve((size_t)nu * per_unit);
         if (rc) return rc;
-        candidates = locate_host(reads, units, (vfk::ResolvedUnit *)S.h_resolved.p);
-        CU(cudaMemcpyAsync(S.resolved.p, S.h_resolved.p, (size_t)nu * sizeof(vfk::ResolvedUnit), cudaMemcpyHostToDevice, st));
-        h->staged_bytes += (int64_t)nu * (int64_t)sizeof(vfk::ResolvedUnit);
+        uint4 *h_cunits = host_columns ? reinterpret_cast<uint4 *>((char *)S.h_resolved.p + (size_t)nu * sizeof(vfk::ResolvedUnit)) : nullptr;
+        candidates = locate_host(reads, units, (vfk::ResolvedUnit *)S.h_resolved.p, h_cunits);
+        CU(cudaMemcpyAsync(S.resolved.p, S.h_resolved.p, (size_t)nu * per_unit, cudaMemcpyHostToDevice, st));
+        h->staged_bytes += (int64_t)nu * (int64_t)per_unit;
         ++h->host_located_batches;
     } else {
         STAGE(S.contig, reads->contig_off, (size_t)(reads->n_contigs + 1) * sizeof(int64_t));
@@ -484,6 +502,14 @@ extern "C" int vfk_annotate_host_async(vfk_handle *h, const vfk_read_batch *read
         const double gathered = (double)candidates * 64.0;
         const double staged = (double)reads->n_sectors * 32.0 + (double)nr * 16.0 + (double)reads->n_cigar_words * 4.0;
         zero_copy = gathered * 4.0 < staged;
+    }
+    const bool use_columns = host_columns && zero_copy;
+    if (use_columns) {  // SNV units: one contiguous run of sectors per column, read in place; the rest as before
+        R.col_wbase = reads->col_wbase;  // not dereferenced on the device (the units are located)
+        R.col_off = (const uint32_t *)pinned_alias(reads->col_off);
+        if (!R.col_off) R.col_off = (const uint32_t *)z_col;  // only its presence matters to the launcher
+        R.col_sectors = (const uint32_t *)z_col;
+        ++h->column_batches;
     }
     // ---- stage 2
     const void *z_hot = pinned_alias(reads->hot), *z_mate = pinned_alias(reads->mate);
@@ -540,6 +566,7 @@ extern "C" int vfk_annotate_host(vfk_handle *h, const vfk_read_batch *reads, con
 }
 
 extern "C" int64_t vfk_zero_copy_batches(vfk_handle *h) { return h ? h->zero_copy_batches : 0; }
+extern "C" int64_t vfk_column_batches(vfk_handle *h) { return h ? h->column_batches : 0; }
 extern "C" int vfk_transfer_stats(vfk_handle *h, int64_t out[4]) {
     if (!h || !out) return fail(VFK_EINVAL, "vfk_transfer_stats: NULL argument");
     out[0] = h->staged_bytes;

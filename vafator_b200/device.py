@@ -121,6 +121,8 @@ def libvfk():
         lib.vfk_wait.argtypes = [C.c_void_p, C.c_int]
         lib.vfk_zero_copy_batches.restype = C.c_int64
         lib.vfk_zero_copy_batches.argtypes = [C.c_void_p]
+        lib.vfk_column_batches.restype = C.c_int64
+        lib.vfk_column_batches.argtypes = [C.c_void_p]
         lib.vfk_transfer_stats.restype = C.c_int
         lib.vfk_transfer_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         lib.vfk_annotate_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
@@ -449,6 +451,9 @@ class Device:
 
     def zero_copy_batches(self) -> int:
         return int(self.lib.vfk_zero_copy_batches(self.h))
+
+    def column_batches(self) -> int:
+        return int(self.lib.vfk_column_batches(self.h))
 
     def transfer_stats(self) -> Dict[str, int]:
         """Host entry point accounting since the handle was created (vfk_transfer_stats)."""
