@@ -104,7 +104,7 @@ def eaf_of(sample):
 # --------------------------------------------------------------------------------------------
 # workload
 # --------------------------------------------------------------------------------------------
-def build_workload(n_tiles: int, rank: int, pinned: bool):
+def build_workload(n_tiles: int, rank: int, pinned: bool, no_columns: bool = False):
     """Tumour + normal batch over the same targets / sites; returns packed host batches + units."""
     from vafator_b200 import device, synth
     from vafator_b200.batch import build_units
@@ -126,7 +126,7 @@ def build_workload(n_tiles: int, rank: int, pinned: bool):
         cfg = synth.wes(n_tiles=n_tiles, seed=seed, normal=normal)
         batch = synth.reads(cfg)
         n_reads += batch.n_reads
-        packed[sample] = device.pack_reads(batch, params, pinned=pinned)
+        packed[sample] = device.pack_reads(batch, params, pinned=pinned, columns=not no_columns)
         del batch
     log("[bench] rank %d workload: %d tiles, %d reads, %d records, %d units/BAM, %.1f s" %
         (rank, n_tiles, n_reads, len(recs), units.n_units, time.time() - t0))
@@ -245,6 +245,7 @@ def main():
     ap.add_argument("--cpu-tiles", type=int, default=20_000, help="targets in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-columns", action="store_true", help="read-major kernels only (no column store in the batches)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -290,7 +291,7 @@ def main():
         torch.cuda.synchronize()
 
     dev = device.Device(local_rank)
-    w = build_workload(args.tiles, rank, pinned=not args.no_e2e)
+    w = build_workload(args.tiles, rank, pinned=not args.no_e2e, no_columns=args.no_columns)
     units, stop, params = w["units"], w["stop"], w["params"]
     nu = units.n_units
     samples = ("tumor", "normal")
@@ -361,6 +362,7 @@ def main():
             e2e_step()
         barrier()
         ts0 = dev.transfer_stats()
+        cb0 = dev.column_batches()
         t0 = time.perf_counter()
         n_e2e = max(3, min(args.steps, 5))
         for _ in range(n_e2e):
@@ -373,12 +375,19 @@ def main():
         zc = (ts1["zero_copy_batches"] - ts0["zero_copy_batches"]) / n_batches
         zc_hot = (ts1["zero_copy_hot_batches"] - ts0["zero_copy_hot_batches"]) / n_batches
         host_loc = (ts1["host_located_batches"] - ts0["host_located_batches"]) / n_batches
+        col = (dev.column_batches() - cb0) / n_batches
         # bytes the library copied in bulk (counted by the library) + what the kernels gathered from pinned host
         # memory: per candidate read one 32-byte payload sector plus the overlap partner's / cold record's share
         # (~64 B), and its 20-byte header when the hot / mate arrays are gathered too
         h2d = (ts1["staged_bytes"] - ts0["staged_bytes"]) / n_e2e
-        h2d += len(samples) * nu * n_cand * (64.0 * zc + 20.0 * zc_hot)
-        transfer = ("units located %s; headers %s; payload + cold + CIGAR %s; two batches in flight (double buffered)" % (
+        if col > 0.5:
+            # column store: one contiguous run of 32-byte sectors per unit (n_cand = sectors of the column's window);
+            # the few units left to the read-major kernels (~2 %) gather ~84 B per candidate read as before
+            h2d += len(samples) * nu * n_cand * (32.0 + 0.02 * 84.0)
+        else:
+            h2d += len(samples) * nu * n_cand * (64.0 * zc + 20.0 * zc_hot)
+        transfer = ("column store: SNV units read one contiguous sector run each from pinned host memory; " if col > 0.5 else "") + (
+            "units located %s; headers %s; payload + cold + CIGAR %s; two batches in flight (double buffered)" % (
             "on the host (32 B per unit copied, no index transfer)" if host_loc > 0.5 else "by the locate kernel (index staged)",
             "gathered by the kernel from pinned host memory" if zc_hot > 0.5 else "staged by async copies",
             "gathered by the kernel from pinned host memory (zero copy)" if zc > 0.5 else "staged by async copies"))
@@ -403,11 +412,12 @@ def main():
         # B_unit = 16 (variant) + 8 (index bounds) + 32 * D_raw + 160 (outputs), biallelic
         b_unit = 16 + 8 + 32.0 * d_raw + 160
         achieved = nu * b_unit / (k_ms * 1e-3) / 1e9
+        top_kernel = "pileup_warp_kernel" if args.no_columns else "pileup_column_kernel"
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             with open(tp) as fh:
-                traffic = json.load(fh).get("pileup_warp_kernel_dram_bytes_per_launch")
+                traffic = json.load(fh).get("%s_dram_bytes_per_launch" % top_kernel)
         cpu = None
         if not args.no_cpu_baseline:
             n_cpu, times, cores = run_cpu_arm(args.cpu_tiles, 0, repeats=1)
@@ -425,7 +435,7 @@ def main():
                            sum(w["packed"][s].nbytes() for s in samples) / 1e9),
                        "sharding": "one independent interval shard per GPU, no collective",
                        "numa_node_rank0": numa},
-            "roofline": {"bound": "hbm", "kernel": "pileup_warp_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": top_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_unit": b_unit, "units_per_launch": nu, "kernel_ms": k_ms},
             "cpu_baseline": cpu,

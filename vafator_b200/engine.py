@@ -189,9 +189,11 @@ class Engine:
     """Drives the device for a set of VCF records against a set of BAM read batches."""
 
     def __init__(self, device_index: int = 0, min_mapq: int = 0, min_baseq: int = 29, include_ambiguous: bool = True,
-                 fpr: float = 5e-7, error_rate: float = 1e-3, devices: Optional[Sequence[int]] = None):
+                 fpr: float = 5e-7, error_rate: float = 1e-3, devices: Optional[Sequence[int]] = None, columns: bool = True):
         """`devices`: CUDA device indexes to shard the pileup over (interval x BAM shards, one host
-        thread per device, no collective); default: just `device_index`."""
+        thread per device, no collective); default: just `device_index`.  `columns`: also build the
+        reference-anchored column store of every batch (include/vfk.h) -- SNV units are then evaluated from it."""
+        self.columns = columns
         self.dev = _dev.Device(device_index)
         self.extra_devs = [_dev.Device(d) for d in (devices or [])[1:]] if devices and len(devices) > 1 else []
         self.params = _dev.make_params(min_mapq=min_mapq, min_baseq=min_baseq, include_ambiguous=include_ambiguous)
@@ -206,7 +208,7 @@ class Engine:
     def _device_reads(self, batch: ReadBatch):
         cache = self.__dict__.setdefault("_dreads", {})
         if id(batch) not in cache:
-            cache[id(batch)] = (batch, self.dev.upload_reads(_dev.pack_reads(batch, self.params)))
+            cache[id(batch)] = (batch, self.dev.upload_reads(_dev.pack_reads(batch, self.params, columns=self.columns)))
         return cache[id(batch)][1]
 
     def release_reads(self):
@@ -225,7 +227,7 @@ class Engine:
             sh, dev = shards[k], devs[k % len(devs)]
             sub, sub_mate = sharding.slice_reads(batch, mate, sh.read_lo, sh.read_hi)
             su = sharding.slice_units(units, sh.unit_lo, sh.unit_hi)
-            dreads = dev.upload_reads(_dev.pack_reads(sub, self.params, mate=sub_mate))
+            dreads = dev.upload_reads(_dev.pack_reads(sub, self.params, mate=sub_mate, columns=self.columns))
             buf = dev.pileup(dreads, dev.upload_units(su, stop[sh.unit_lo:sh.unit_hi]), self.params)
             return dev.to_host(buf, _dev.COUNTS_DTYPE, su.n_units)
 
