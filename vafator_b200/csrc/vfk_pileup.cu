@@ -52,11 +52,7 @@ struct Layout {
 //   lo = back[hi-1] = first read whose running-maximum end exceeds start[hi-1] (<= col):
 //        no earlier read can overlap the column
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-locate_kernel(ReadsDev R, UnitsDev V, ResolvedUnit *__restrict__ res, uint4 *__restrict__ cunits,
-              unsigned long long *__restrict__ cand_sum) {
-    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= V.n) return;
+__device__ __forceinline__ ResolvedUnit locate_unit(const ReadsDev &R, const UnitsDev &V, int64_t u) {
     const int32_t tid = __ldg(V.tid + u);
     const int32_t col = __ldg(V.pos + u);
     const bool known = tid >= 0 && tid < R.n_contigs;  // an unknown contig gets an empty read range
@@ -92,22 +88,36 @@ locate_kernel(ReadsDev R, UnitsDev V, ResolvedUnit *__restrict__ res, uint4 *__r
     r.lo = a > c0 ? (uint32_t)__ldg(&R.sb[a - 1].y) : (uint32_t)a;
     r.stop = V.stop ? __ldg(V.stop + u) : 0x7FFFFFFF;
     r.c1 = (uint32_t)c1;
-    uint4 *o = reinterpret_cast<uint4 *>(res + u);
+    return r;
+}
+__device__ __forceinline__ void store_resolved(ResolvedUnit *dst, const ResolvedUnit &r) {
+    uint4 *o = reinterpret_cast<uint4 *>(dst);
     const uint4 *q = reinterpret_cast<const uint4 *>(&r);
     o[0] = q[0];
     o[1] = q[1];
-    if (cunits) {  // column store: the window of the column -> its run of sectors
-        const int32_t w = col / VFK_COL_WIDTH;
-        uint32_t off = 0, cnt = 0;
-        if (known && col >= 0) {
-            const int64_t w0 = __ldg(R.col_wbase + tid), w1 = __ldg(R.col_wbase + tid + 1);
-            if (w0 + w < w1) {
-                off = __ldg(R.col_off + w0 + w);
-                cnt = __ldg(R.col_off + w0 + w + 1) - off;
-            }
+}
+// column store: the window of the column -> its run of sectors
+__device__ __forceinline__ uint4 column_unit(const ReadsDev &R, int32_t tid, int32_t col, uint32_t meta) {
+    const int32_t w = col / VFK_COL_WIDTH;
+    uint32_t off = 0, cnt = 0;
+    if (tid >= 0 && tid < R.n_contigs && col >= 0) {
+        const int64_t w0 = __ldg(R.col_wbase + tid), w1 = __ldg(R.col_wbase + tid + 1);
+        if (w0 + w < w1) {
+            off = __ldg(R.col_off + w0 + w);
+            cnt = __ldg(R.col_off + w0 + w + 1) - off;
         }
-        cunits[u] = make_uint4(off, cnt, (uint32_t)(col - w * VFK_COL_WIDTH), r.meta);
     }
+    return make_uint4(off, cnt, (uint32_t)(col - w * VFK_COL_WIDTH), meta);
+}
+
+__global__ void __launch_bounds__(256)
+locate_kernel(ReadsDev R, UnitsDev V, ResolvedUnit *__restrict__ res, uint4 *__restrict__ cunits,
+              unsigned long long *__restrict__ cand_sum) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= V.n) return;
+    const ResolvedUnit r = locate_unit(R, V, u);
+    store_resolved(res + u, r);
+    if (cunits) cunits[u] = column_unit(R, __ldg(V.tid + u), r.col, r.meta);
     if (cand_sum) {  // total candidate reads of the batch: lets the host entry pick its transfer strategy
         const unsigned active = __activemask();
         const unsigned mine = r.hi - r.lo;
@@ -331,7 +341,7 @@ __device__ __forceinline__ void unit_by_histogram(const ReadsDev &R, const vfk_p
                 bulk_copy_g2s(ring->hot + s * 32, R.hot + first, bytes, ring->bar + s);
             }
         };
-        issue(0);
+        if (n_chunks > 0) issue(0);  // a unit without candidates must not touch the ring: its phase would run ahead
         uint32_t mw_next = (U.lo + lane < U.hi) ? __ldg(R.mate + U.lo + lane) : VFK_NO_MATE;
         for (int c = 0; c < n_chunks; ++c) {
             const int s = c & 1;
@@ -578,7 +588,7 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
 // base-quality filter looks at the next base and at the push timing of its mate), a sector flagged unusable.
 // ------------------------------------------------------------------------------------------
 #ifndef VFK_COL_MIN_CTAS
-#define VFK_COL_MIN_CTAS 5
+#define VFK_COL_MIN_CTAS 8
 #endif
 struct ColRead {  // one sector as a lane holds it
     uint32_t e;   // the 16-bit entry of the column
@@ -968,7 +978,7 @@ static cudaError_t launch_posb(const ReadsDev &R, const UnitsDev &V, const vfk_p
     return e;
 }
 
-// the pileup kernels on units that launch_locate has resolved
+// the pileup kernels on units that launch_locate (or the host) has resolved
 cudaError_t launch_pileup_resolved(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, int max_l_qseq, vfk_counts *out,
                                    void *resolved, void *counters, uint32_t *lists, int sm_count, cudaStream_t stream,
                                    int *launches) {
