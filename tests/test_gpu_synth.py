@@ -289,3 +289,38 @@ def test_host_entry_point_reads_the_column_store_in_place(dev, monkeypatch):
         elif f != "n_cand":
             assert np.array_equal(alt_c[f], want_c[f]), f
     assert alt_s.tobytes() == want_s.tobytes()
+
+
+def test_listed_units_without_candidate_reads(dev):
+    """Indel units always reach the histogram kernel when the batch has a column store; one that lies where no read
+    is (between two targets) must not disturb the units processed after it by the same warp (regression: it used to
+    arm the TMA staging ring without consuming it)."""
+    cfg = synth.wes(n_tiles=1200, indel_period=60, snv_period=200)
+    batch, recs, units, stop, ounits = _setup(cfg)
+    contig = cfg.contigs[0]
+    tile0 = min(p for c, p, r, a in recs if c == contig)
+    # uncovered positions: far before the first target of the contig and in the gaps between targets
+    gaps = [(contig, tile0 + 900 + 2048 * k, "A", ["ATT"]) for k in range(0, 400, 7)] + \
+           [(contig, tile0 + 901 + 2048 * k, "ACG", ["A"]) for k in range(3, 400, 11)]
+    recs2 = sorted(recs + gaps, key=lambda r: (cfg.contigs.index(r[0]), r[1]))
+    units2 = build_units(recs2, cfg.contigs)
+    last = {}
+    for c, p, r, a in recs2:
+        last[c] = p
+    stop2 = np.asarray([last[recs2[i][0]] for i in units2.rec], np.int32)
+    params = device.make_params(min_mapq=1, min_baseq=30)
+    got = {}
+    for columns in (False, True):
+        for rep in range(3):  # the staging ring state carries over between launches of a persistent warp only within one
+            dreads = dev.upload_reads(device.pack_reads(batch, params, columns=columns))
+            buf = dev.pileup(dreads, dev.upload_units(units2, stop2), params)
+            dev.sync()
+            got[columns] = dev.to_host(buf, device.COUNTS_DTYPE, units2.n_units)
+    empty = got[False]["n_cover"] == 0
+    assert int(empty.sum()) >= 50 and int((got[False]["status"] & 3 != 0).sum()) > 100
+    both = (got[False]["ac_ref"] > 0) & (got[False]["ac_alt"] > 0)
+    for f in got[True].dtype.names:
+        if f == "s2":
+            assert np.array_equal(got[True][f][both], got[False][f][both])
+        elif f != "n_cand":
+            assert np.array_equal(got[True][f], got[False][f]), f
