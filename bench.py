@@ -111,6 +111,18 @@ def build_workload(n_tiles: int, rank: int, pinned: bool, no_columns: bool = Fal
     params = device.make_params(min_mapq=MIN_MAPQ, min_baseq=MIN_BASEQ, include_ambiguous=True)
     seed = synth.BASE_SEED + 2 + 1000 * rank
     t0 = time.time()
+    if not no_columns:
+        # both layouts of the two BAMs are ~23 GB of (page-locked) host memory per rank, plus ~12 GB while a batch is
+        # being built: on a host that cannot give every rank that much the run keeps to the read-major layout
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available / max(int(os.environ.get("WORLD_SIZE", "1")), 1)
+            need = 40e9 * n_tiles / 200_000
+            if avail < need:
+                log("[bench] rank %d: %.0f GB of host memory per rank < %.0f GB: no column store" % (rank, avail / 1e9, need / 1e9))
+                no_columns = True
+        except ImportError:
+            pass
     cfg_t = synth.wes(n_tiles=n_tiles, seed=seed, normal=False)
     recs = synth.variant_records(cfg_t)
     units = build_units(recs, cfg_t.contigs)
@@ -130,7 +142,7 @@ def build_workload(n_tiles: int, rank: int, pinned: bool, no_columns: bool = Fal
         del batch
     log("[bench] rank %d workload: %d tiles, %d reads, %d records, %d units/BAM, %.1f s" %
         (rank, n_tiles, n_reads, len(recs), units.n_units, time.time() - t0))
-    return dict(params=params, recs=recs, units=units, stop=stop, packed=packed, n_reads=n_reads)
+    return dict(params=params, recs=recs, units=units, stop=stop, packed=packed, n_reads=n_reads, columns=not no_columns)
 
 
 def cpu_sample(n_tiles: int, rank: int):
@@ -412,7 +424,7 @@ def main():
         # B_unit = 16 (variant) + 8 (index bounds) + 32 * D_raw + 160 (outputs), biallelic
         b_unit = 16 + 8 + 32.0 * d_raw + 160
         achieved = nu * b_unit / (k_ms * 1e-3) / 1e9
-        top_kernel = "pileup_warp_kernel" if args.no_columns else "pileup_column_kernel"
+        top_kernel = "pileup_column_kernel" if w["columns"] else "pileup_warp_kernel"
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
@@ -433,6 +445,7 @@ def main():
                        "mean_depth_raw": round(d_raw, 2), "mean_candidates": round(n_cand, 2),
                        "l2": "inputs (%.1f GB of read batches per GPU) exceed L2; tumour and normal batches alternate" % (
                            sum(w["packed"][s].nbytes() for s in samples) / 1e9),
+                       "layout": "read-major + column store" if w["columns"] else "read-major",
                        "sharding": "one independent interval shard per GPU, no collective",
                        "numa_node_rank0": numa},
             "roofline": {"bound": "hbm", "kernel": top_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
