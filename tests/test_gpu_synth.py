@@ -224,14 +224,15 @@ def test_host_entry_point_transfer_strategies(dev, pinned, monkeypatch):
                 assert (dev.zero_copy_batches() > before) == pinned
 
 
-def test_short_parity_campaign():
-    """tests/fuzz_parity.py for a quarter of a minute: random read / CIGAR / pairing / variant mixes x thresholds."""
+@pytest.mark.parametrize("layout", ["read_major", "columns"])
+def test_short_parity_campaign(layout):
+    """tests/fuzz_parity.py for ten seconds per layout: random read / CIGAR / pairing / variant mixes x thresholds."""
     import os
     import subprocess
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
-    r = subprocess.run([sys.executable, os.path.join(here, "fuzz_parity.py"), "--seconds", "15", "--seed0", "5000"],
-                       capture_output=True, text=True, timeout=600)
+    cmd = [sys.executable, os.path.join(here, "fuzz_parity.py"), "--seconds", "10", "--seed0", "5000"]
+    r = subprocess.run(cmd + (["--columns"] if layout == "columns" else []), capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "fuzz ok" in r.stdout
 
