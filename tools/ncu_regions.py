@@ -3,7 +3,7 @@
 (SASS counters joined with nvdisasm line info of the in-tree libvfk.so; the library must be the
 build that was profiled).
 
-    python tools/ncu_regions.py gpurun_out/prof.ncu-rep N_UNITS [--lines]
+    python tools/ncu_regions.py gpurun_out/prof.ncu-rep N_UNITS [kernel-substring] [--lines]
 """
 import collections
 import csv
