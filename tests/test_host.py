@@ -201,3 +201,68 @@ def test_column_store_matches_cigar_walk(path):
                         elif linked and not complex_:
                             assert int(pk.mate[i] & 0x7FFFFFFF) not in members[w]
             assert n_seen == sectors.shape[0]
+
+
+def test_column_store_on_noisy_synthetic_reads():
+    """Same check on generated reads with many clips / indels / skips / dense pairing: the sectors the builder flags
+    unusable are rare, everything else decodes to the CIGAR walk, and partner offsets point at the linked read."""
+    from vafator_b200 import synth
+    cfg = synth.wes(n_tiles=40, indel_period=40, snv_period=30, p_softclip=0.3, p_del=0.2, p_ins=0.2, p_skip=0.08,
+                    frag_mean=180.0, frag_sd=30.0, pairs_per_tile=60)
+    batch = synth.reads(cfg)
+    params = device.make_params(min_mapq=1)
+    pk = device.pack_reads(batch, params, columns=True)
+    W = 12
+    sectors = pk.col_sectors.reshape(-1, 32)
+    entries = sectors[:, :24].copy().view("<u2").reshape(-1, 12)
+    h0, h1 = sectors[:, 24:28].copy().view("<u4").ravel(), sectors[:, 28:32].copy().view("<u4").ravel()
+    n = pk.n_reads
+    spans, cov = np.zeros(n, np.int64), []
+    for i in range(n):
+        c = batch.cigar[batch.cigar_off[i]:batch.cigar_off[i] + batch.n_cigar[i]]
+        x, y, states = int(batch.pos[i]), 0, {}
+        for w_ in c:
+            op, l = int(w_) & 15, int(w_) >> 4
+            if op in (0, 7, 8):
+                for _ in range(l):
+                    states[x] = (1, y)
+                    x += 1
+                    y += 1
+            elif op in (2, 3):
+                for _ in range(l):
+                    states[x] = (2 if op == 2 else 3, y)
+                    x += 1
+            elif op in (1, 4):
+                y += l
+        cov.append(states)
+        spans[i] = x - int(batch.pos[i])
+    members = {}
+    for i in range(n):
+        if spans[i] > 0:
+            t = int(batch.tid[i])
+            for w_ in range(int(batch.pos[i]) // W, (int(batch.pos[i]) + int(spans[i]) - 1) // W + 1):
+                members.setdefault((t, w_), []).append(i)
+    assert sum(len(v) for v in members.values()) == sectors.shape[0]
+    n_complex = 0
+    for (t, w_), reads in members.items():
+        a = int(pk.col_off[pk.col_wbase[t] + w_])
+        assert int(pk.col_off[pk.col_wbase[t] + w_ + 1]) - a == len(reads)
+        for k, i in enumerate(reads):
+            s = a + k
+            complex_ = bool(h0[s] >> 31)
+            n_complex += complex_
+            mask, has_ins = int(h1[s]) & 0xFFF, bool((h1[s] >> 28) & 1)
+            ins_at, ins_len = (int(h1[s]) >> 12) & 15, (int(h1[s]) >> 16) & 0xFFF
+            for p in range(W):
+                st = (int(entries[s, p]) >> 12) & 3
+                want = cov[i].get(w_ * W + p)
+                assert st == (want[0] if want else 0)
+                if st == 1 and not complex_:
+                    q = (int(h0[s]) & 0xFFF) + bin(mask & ((1 << p) - 1)).count("1") + (ins_len if has_ins and p > ins_at else 0)
+                    assert q == want[1]
+                    assert (int(entries[s, p]) & 0xFF) == int(batch.qual[batch.qual_off[i] + want[1]])
+            off = (int(h0[s]) >> 20) & 0xFF
+            off = off - 256 if off >= 128 else off
+            if off:
+                assert reads[k + off] == int(pk.mate[i] & 0x7FFFFFFF)
+    assert n_complex < 0.02 * sectors.shape[0]
