@@ -162,7 +162,8 @@ typedef struct {
     int32_t ac_alt;     /* reads supporting this unit's ALT                                       */
     int32_t med2[3][2]; /* [mq,bq,pos][ref,alt]: twice the median, -1 when the list is empty      */
     uint32_t status;
-    uint32_t n_cand;    /* candidate reads inspected                                              */
+    uint32_t n_cand;    /* reads inspected for the unit (diagnostic): candidate reads of the position index on
+                           the read-major path, sectors of the column's window on the column-store path      */
     uint64_t s2[3];     /* [mq,bq,pos]: twice the sum of the ALT mid-ranks in the pooled ranking   */
     uint32_t n_cover;   /* reads overlapping the column before any filter (D_raw of SURVEY.md 8d)   */
     uint32_t n_col;     /* reads in the htslib column (read filter passed) BEFORE the base-quality filter:
