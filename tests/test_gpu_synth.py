@@ -33,9 +33,9 @@ def _setup(cfg):
     return batch, recs, units, stop, ounits
 
 
-def _gpu(dev, batch, units, stop, mq, bq, amb=True):
+def _gpu(dev, batch, units, stop, mq, bq, amb=True, columns=False):
     params = device.make_params(min_mapq=mq, min_baseq=bq, include_ambiguous=amb)
-    dreads = dev.upload_reads(device.pack_reads(batch, params))
+    dreads = dev.upload_reads(device.pack_reads(batch, params, columns=columns))
     buf = dev.pileup(dreads, dev.upload_units(units, stop), params)
     dev.sync()
     return dev.to_host(buf, device.COUNTS_DTYPE, units.n_units)
@@ -78,11 +78,13 @@ def test_gpu_matches_c_oracle(dev, name):
     assert want["ac_alt"].sum() > 0 and want["n_amb"].sum() >= 0
 
 
-def test_deep_column_block_path(dev):
-    """Columns deeper than the warp path's u16 bins (> 32767 candidate reads) take the CTA-per-unit kernel."""
+@pytest.mark.parametrize("columns", [False, True], ids=["read_major", "columns"])
+def test_deep_column_block_path(dev, columns):
+    """Columns deeper than the warp path's u16 bins (> 32767 candidate reads) take the CTA-per-unit kernel -- also when
+    the units come off the column kernel's list and are located afterwards."""
     cfg = synth.amplicon(n_tiles=2, depth_pairs=30000, snv_period=60, indel_period=120)
     batch, recs, units, stop, ounits = _setup(cfg)
-    got = _gpu(dev, batch, units, stop, 1, 30)
+    got = _gpu(dev, batch, units, stop, 1, 30, columns=columns)
     assert int(got["n_cand"].max()) > 32767
     want = c_oracle.pileup(batch.as_dict(), ounits, c_oracle.params(min_mapq=1, min_baseq=30))
     _compare(got, want)

@@ -126,6 +126,29 @@ locate_kernel(ReadsDev R, UnitsDev V, ResolvedUnit *__restrict__ res, uint4 *__r
     }
 }
 
+// Column-store launches locate lazily: every unit only needs its window (no search) ...
+__global__ void __launch_bounds__(256) column_units_kernel(ReadsDev R, UnitsDev V, uint4 *__restrict__ cunits) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= V.n) return;
+    cunits[u] = column_unit(R, __ldg(V.tid + u), __ldg(V.pos + u), __ldg(V.meta + u));
+}
+// ... and only the units the column kernel left on the list are searched in the position index; columns too deep
+// for the warp-per-unit histogram kernel move on to the block list (their slot is voided)
+constexpr uint32_t LIST_VOID = 0xFFFFFFFFu;
+__global__ void __launch_bounds__(256)
+locate_list_kernel(ReadsDev R, UnitsDev V, ResolvedUnit *__restrict__ res, uint32_t *__restrict__ warp_list,
+                   const uint32_t *__restrict__ n_warp, uint32_t *__restrict__ block_list, uint32_t *__restrict__ n_block) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)*n_warp) return;
+    const uint32_t u = warp_list[i];
+    const ResolvedUnit r = locate_unit(R, V, u);
+    store_resolved(res + u, r);
+    if (r.hi - r.lo > (uint32_t)WARP_PATH_MAX_CAND) {
+        block_list[atomicAdd(n_block, 1u)] = u;
+        warp_list[i] = LIST_VOID;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // histogram access.  CT = uint16_t: two bins per 32-bit word; CT = uint32_t: one bin per word.
 // ------------------------------------------------------------------------------------------
@@ -690,7 +713,8 @@ pileup_column_kernel(ReadsDev R, const uint4 *__restrict__ cunits, const Resolve
             uint64_t s2[3] = {0, 0, 0};
             if (kind != VFK_KIND_SNV || cnt > 64u) {  // not for this kernel: the read-major kernels take it
                 if (lane == 0) {
-                    const uint32_t n_cand = __ldg(&res[u].hi) - __ldg(&res[u].lo);
+                    // located units (host entry point) are routed here, the others by locate_list_kernel
+                    const uint32_t n_cand = res ? __ldg(&res[u].hi) - __ldg(&res[u].lo) : 0u;
                     if (n_cand > (uint32_t)WARP_PATH_MAX_CAND) block_list[atomicAdd(n_block, 1u)] = (uint32_t)u;
                     else warp_list[atomicAdd(n_warp, 1u)] = (uint32_t)u;
                     store_counts(out + u, 0, 0, 0, 0, med2, s2, kind | VFK_ST_DEFERRED, cnt, 0u);
@@ -812,10 +836,12 @@ pileup_deep_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, const uint8
     uint32_t k = blockIdx.x * WARPS_PER_CTA + warp;
     for (;;) {
         if (k >= n) break;
-        const int64_t u = warp_list[k];
-        Unit U;
-        unit_from(res[u], ins_seq, U);
-        unit_by_histogram<POSB, true>(R, P, U, ref_slot, alt_slot, lane, out + u, &ring);
+        const uint32_t u = warp_list[k];
+        if (u != LIST_VOID) {
+            Unit U;
+            unit_from(res[u], ins_seq, U);
+            unit_by_histogram<POSB, true>(R, P, U, ref_slot, alt_slot, lane, out + u, &ring);
+        }
         if (lane == 0) k = n_warps + atomicAdd(deep_work, 1u);
         k = __shfl_sync(FULL, k, 0);
     }
@@ -914,7 +940,7 @@ cudaError_t launch_locate(const ReadsDev &R, const UnitsDev &V, void *resolved, 
 // length, @16 u32 deep-kernel work counter, @24 u64 candidate sum (locate pass).  lists: 2 * n_units u32.
 template <int POSB>
 static cudaError_t launch_posb(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, vfk_counts *out, ResolvedUnit *res,
-                               void *counters, uint32_t *lists, int sm_count, cudaStream_t stream, int *launches) {
+                               void *counters, uint32_t *lists, int sm_count, cudaStream_t stream, int *launches, bool located) {
     using L = Layout<POSB>;
     const size_t smem_deep = (size_t)WARPS_PER_CTA * 2 * (L::BINS / 2) * sizeof(uint32_t);
     const size_t smem_block = (size_t)2 * L::BINS * sizeof(uint32_t);
@@ -949,9 +975,17 @@ static cudaError_t launch_posb(const ReadsDev &R, const UnitsDev &V, const vfk_p
         if (e != cudaSuccess) return e;
         int64_t col_grid = (int64_t)sm_count * std::max(col_ctas, 1);
         if (want < col_grid) col_grid = want < 1 ? 1 : want;
-        const uint4 *cunits = reinterpret_cast<const uint4 *>((const char *)res + (size_t)V.n * sizeof(ResolvedUnit));
-        pileup_column_kernel<POSB><<<(unsigned)col_grid, WARPS_PER_CTA * 32, 0, stream>>>(R, cunits, res, V.n, P, out, work,
-                                                                                        block_list, n_block, warp_list, n_warp);
+        uint4 *cunits = reinterpret_cast<uint4 *>((char *)res + (size_t)V.n * sizeof(ResolvedUnit));
+        if (!located) {  // lazy locate: every unit gets its window now, only the listed ones are searched afterwards
+            column_units_kernel<<<(unsigned)((V.n + 255) / 256), 256, 0, stream>>>(R, V, cunits);
+            ++*launches;
+        }
+        pileup_column_kernel<POSB><<<(unsigned)col_grid, WARPS_PER_CTA * 32, 0, stream>>>(R, cunits, located ? res : nullptr, V.n, P, out,
+                                                                                        work, block_list, n_block, warp_list, n_warp);
+        if (!located) {
+            ++*launches;
+            locate_list_kernel<<<(unsigned)((V.n + 255) / 256), 256, 0, stream>>>(R, V, res, warp_list, n_warp, block_list, n_block);
+        }
     } else {
         pileup_warp_kernel<POSB><<<(unsigned)grid, WARPS_PER_CTA * 32, 0, stream>>>(R, res, V.n, V.ins_seq, P, out, work, block_list,
                                                                                     n_block, warp_list, n_warp);
@@ -978,21 +1012,30 @@ static cudaError_t launch_posb(const ReadsDev &R, const UnitsDev &V, const vfk_p
     return e;
 }
 
+static cudaError_t launch_pileup_sized(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, int max_l_qseq, vfk_counts *out,
+                                       void *resolved, void *counters, uint32_t *lists, int sm_count, cudaStream_t stream,
+                                       int *launches, bool located) {
+    ResolvedUnit *res = (ResolvedUnit *)resolved;
+    // read positions run 0 .. l_qseq (a read hanging in a trailing deletion reports l_qseq)
+    if (max_l_qseq < 256) return launch_posb<256>(R, V, P, out, res, counters, lists, sm_count, stream, launches, located);
+    if (max_l_qseq < 512) return launch_posb<512>(R, V, P, out, res, counters, lists, sm_count, stream, launches, located);
+    if (max_l_qseq < 1024) return launch_posb<1024>(R, V, P, out, res, counters, lists, sm_count, stream, launches, located);
+    return launch_posb<4096>(R, V, P, out, res, counters, lists, sm_count, stream, launches, located);
+}
+
 // the pileup kernels on units that launch_locate (or the host) has resolved
 cudaError_t launch_pileup_resolved(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, int max_l_qseq, vfk_counts *out,
                                    void *resolved, void *counters, uint32_t *lists, int sm_count, cudaStream_t stream,
                                    int *launches) {
-    ResolvedUnit *res = (ResolvedUnit *)resolved;
-    // read positions run 0 .. l_qseq (a read hanging in a trailing deletion reports l_qseq)
-    if (max_l_qseq < 256) return launch_posb<256>(R, V, P, out, res, counters, lists, sm_count, stream, launches);
-    if (max_l_qseq < 512) return launch_posb<512>(R, V, P, out, res, counters, lists, sm_count, stream, launches);
-    if (max_l_qseq < 1024) return launch_posb<1024>(R, V, P, out, res, counters, lists, sm_count, stream, launches);
-    return launch_posb<4096>(R, V, P, out, res, counters, lists, sm_count, stream, launches);
+    return launch_pileup_sized(R, V, P, max_l_qseq, out, resolved, counters, lists, sm_count, stream, launches, true);
 }
 
 cudaError_t launch_pileup(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, int max_l_qseq, vfk_counts *out,
                           void *resolved_scratch, void *counters, uint32_t *lists, int sm_count, cudaStream_t stream,
                           int *launches) {
+    if (V.n <= 0) return cudaSuccess;
+    if (R.col_off && !getenv("VFK_EAGER_LOCATE"))  // column store: the position index is searched for the listed units only
+        return launch_pileup_sized(R, V, P, max_l_qseq, out, resolved_scratch, counters, lists, sm_count, stream, launches, false);
     cudaError_t e = launch_locate(R, V, resolved_scratch, nullptr, stream, launches);
     if (e != cudaSuccess) return e;
     return launch_pileup_resolved(R, V, P, max_l_qseq, out, resolved_scratch, counters, lists, sm_count, stream, launches);
