@@ -261,7 +261,13 @@ def pack_reads(batch: ReadBatch, params: ParamsC, pinned: bool = False, mate: np
     if columns:
         wbase = np.empty(len(batch.contigs) + 1, np.int64)
         cp = _ColPlanC()
-        _io_check(libio().vfkio_columns_plan(C.byref(s), C.c_void_p(wbase.ctypes.data), C.byref(cp)))
+        rc = libio().vfkio_columns_plan(C.byref(s), C.c_void_p(wbase.ctypes.data), C.byref(cp))
+        if rc == -4:  # VFK_EUNSUPPORTED: more than 2^32 sectors -- the batch keeps its read-major layout only
+            import warnings
+            warnings.warn("column store not built (%s): SNV units take the read-major kernels" %
+                          libio().vfkio_last_error().decode())
+            return packed
+        _io_check(rc)
         woff = _empty(cp.n_windows + 1, np.uint32, pinned)
         sectors = _empty(cp.n_sectors * 32, np.uint8, pinned)
         _io_check(libio().vfkio_columns_fill(C.byref(s), C.byref(params), C.c_void_p(mate.ctypes.data),
