@@ -106,3 +106,88 @@ def test_info_strings_match_reference(path):
             assert list(g.keys()) == list(w.keys()), (sc["name"], prm, records[i], list(g.keys()), list(w.keys()))
             for k in w:
                 assert str(g[k]) == str(w[k]), (sc["name"], prm, records[i], k, g[k], w[k])
+
+
+class FileOracleEngine(OracleEngine):
+    """Constructor of engine.Engine, device stages of OracleEngine -- stands in for Engine inside Annotator."""
+    calls = []
+
+    def __init__(self, device_index=0, min_mapq=0, min_baseq=29, include_ambiguous=True, fpr=5e-7, error_rate=1e-3,
+                 devices=None, columns=True):
+        OracleEngine.__init__(self, min_mapq, min_baseq, include_ambiguous, fpr, error_rate)
+        self.released = 0
+
+    def annotate(self, records, bams, eaf):
+        self._records = records
+        FileOracleEngine.calls.append((records[0][0], len(records), [b.n_reads for bs in bams.values() for b in bs]))
+        return OracleEngine.annotate(self, records, bams, eaf)
+
+    def release_reads(self):
+        self.released += 1
+
+
+def _write_inputs(tmp_path, sc, indexed):
+    from vafator_b200 import bamio
+    vcf = tmp_path / "in.vcf"
+    with open(vcf, "w") as fh:
+        fh.write("##fileformat=VCFv4.2\n" + "".join("##contig=<ID=%s>\n" % c for c in sc["contigs"]))
+        fh.write("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n")
+        for k, v in enumerate(sc["variants"]):
+            fh.write("%s\t%d\t.\t%s\t%s\t.\tPASS\t%s\n" % (v["chrom"], v["pos"], v["ref"], ",".join(v["alts"]),
+                                                              "." if k % 2 else "OLD=1;DP=7"))
+    bams = OrderedDict()
+    for s, idx in sc["samples"].items():
+        for b in idx:
+            p = tmp_path / ("bam%d.bam" % b)
+            bamio.write_bam(str(p), sc["bams"][b], sc["contigs"], index=indexed)
+            bams.setdefault(s, []).append(str(p))
+    return str(vcf), bams
+
+
+@pytest.mark.parametrize("indexed", [False, True], ids=["whole_file", "bai_regions"])
+@pytest.mark.parametrize("name", ["pileup_random_13.json", "pileup_handmade.json", "pileup_testx_real.json"])
+def test_annotator_streams_chromosome_groups(tmp_path, monkeypatch, name, indexed):
+    """Annotator.run on files (VCF reader, BAM decoder, region fetch, chromosome-group streaming, INFO append, VCF
+    writer) with the device stages doubled by the oracle: every INFO key=value of the unmodified reference, one
+    engine call per chromosome group, region batches released between groups."""
+    from vafator_b200 import annotator as ann
+    from vafator_b200.ploidies import PloidyManager
+    sc = H.load_scenario(os.path.join(H.GOLDEN, name))
+    run = sc["runs"][3] if len(sc["runs"]) > 3 else sc["runs"][-1]
+    prm = run["params"]
+    vcf, bams = _write_inputs(tmp_path, sc, indexed)
+    ploidies = {}
+    for s, pl in sc["ploidies"].items():
+        if isinstance(pl, list):
+            bed = tmp_path / ("%s.bed" % s)
+            with open(bed, "w") as fh:
+                for row in pl:
+                    fh.write("\t".join(map(str, row)) + "\n")
+            ploidies[s] = PloidyManager(local_copy_numbers=str(bed))
+        else:
+            ploidies[s] = PloidyManager(genome_wide_ploidy=float(pl))
+    monkeypatch.setattr(ann, "Engine", FileOracleEngine)
+    FileOracleEngine.calls = []
+    a = ann.Annotator(input_vcf=vcf, output_vcf=str(tmp_path / "out.vcf"), input_bams=bams, purities=dict(sc["purities"]),
+                      mapping_qual_thr=prm["min_mq"], base_call_qual_thr=prm["min_bq"], tumor_ploidies=ploidies,
+                      normal_ploidy=prm.get("normal_ploidy", 2), fpr=prm.get("fpr", 5e-7), error_rate=prm.get("error_rate", 1e-3),
+                      include_ambiguous_bases=prm["include_ambiguous"])
+    a.run()
+    body = [l.rstrip("\n") for l in open(tmp_path / "out.vcf") if not l.startswith("#")]
+    assert len(body) == len(sc["variants"])
+    for k, (line, want) in enumerate(zip(body, run["info"])):
+        info = line.split("\t")[7].split(";")
+        if k % 2 == 0:
+            assert info[:2] == ["OLD=1", "DP=7"]
+            info = info[2:]
+        assert info == ["%s=%s" % (key, val) for key, val in want], (k, sc["variants"][k])
+    # one engine call per run of consecutive records of one chromosome
+    chroms = [v["chrom"] for v in sc["variants"]]
+    groups = [c for i, c in enumerate(chroms) if i == 0 or chroms[i - 1] != c]
+    assert [c[0] for c in FileOracleEngine.calls] == groups
+    assert sum(c[1] for c in FileOracleEngine.calls) == len(chroms)
+    assert a.engine.released == (len(groups) + 1 if indexed else 1)
+    if indexed and len(groups) > 1:  # a group's batches hold that chromosome's region only
+        whole = [len([r for r in sc["bams"][b] if r["tid"] >= 0]) for idx in sc["samples"].values() for b in idx]
+        assert all(n <= w for c in FileOracleEngine.calls for n, w in zip(c[2], whole))
+        assert any(n < w for c in FileOracleEngine.calls for n, w in zip(c[2], whole))

@@ -69,24 +69,38 @@ class Annotator(object):
                              include_ambiguous=include_ambiguous_bases, fpr=fpr, error_rate=error_rate)
 
     def run(self) -> None:
-        """Annotate every record of the input VCF and write the output VCF."""
-        variants = list(self.vcf)
-        for v in variants:
+        """Annotate every record of the input VCF and write the output VCF.
+
+        The VCF is streamed one chromosome group at a time -- consecutive records of one CHROM, the unit the
+        reference piles up (stream_variants_by_chrom, vafator/pileups.py:83-103) -- so the host never holds more
+        than the reads of one chromosome: with an indexed BAM only [first.POS-1, last.POS) of the group is decoded
+        (what the reference fetches, vafator/pileups.py:137-138) and the batch is dropped, on the host and on the
+        device, before the next group is read.  A BAM without an index is decoded once and stays resident."""
+        group = []
+        for v in self.vcf:
             if not v.ALT:
                 raise ValueError("VCF record %s:%d has no ALT allele" % (v.CHROM, v.POS))
+            if group and v.CHROM != group[0].CHROM:
+                self._annotate_group(group)
+                group = []
+            group.append(v)
+        if group:
+            self._annotate_group(group)
+        self.vcf_writer.close()
+        self.vcf.close()
+        self.engine.release_reads()
+        for readers in self.bam_readers.values():
+            for bam in readers:
+                bam.close()
+
+    def _annotate_group(self, variants: list) -> None:
+        """One chromosome group: decode its reads, annotate, write, release."""
         records = [(v.CHROM, v.POS, v.REF, v.ALT) for v in variants]
-        # what the reference fetches: [first.POS-1, last.POS) of every chromosome group (vafator/pileups.py:137-138);
-        # an indexed BAM is decoded for those regions only
-        regions = []
-        for chrom, pos in ((r[0], r[1]) for r in records):
-            if regions and regions[-1][0] == chrom:
-                regions[-1][1], regions[-1][2] = min(regions[-1][1], pos - 1), max(regions[-1][2], pos)
-            else:
-                regions.append([chrom, pos - 1, pos])
-        bams = OrderedDict((s, [r.read_batch(regions) for r in readers]) for s, readers in self.bam_readers.items())
-        chroms = [r[0] for r in records]
+        chrom = records[0][0]
         positions = [r[1] for r in records]
-        eaf = {s: self.power.expected_vafs(s, chroms, positions) for s in bams}
+        regions = [(chrom, min(positions) - 1, max(positions))]
+        bams = OrderedDict((s, [r.read_batch(regions) for r in readers]) for s, readers in self.bam_readers.items())
+        eaf = {s: self.power.expected_vafs(s, [chrom] * len(records), positions) for s in bams}
         infos = self.engine.annotate(records, bams, eaf)
         batch = []
         for v, info in zip(variants, infos):
@@ -97,12 +111,10 @@ class Annotator(object):
                 batch.clear()
         if batch:
             self._write_batch(batch)
-        self.vcf_writer.close()
-        self.vcf.close()
-        self.engine.release_reads()
-        for readers in self.bam_readers.values():
-            for bam in readers:
-                bam.close()
+        # region batches are transient (a new object per call); the whole-file batch of an unindexed BAM is
+        # cached by its reader and keeps its device copy for the next group
+        if any(r.index_path for readers in self.bam_readers.values() for r in readers):
+            self.engine.release_reads()
 
     def _write_batch(self, batch: list) -> None:
         for v in batch:
