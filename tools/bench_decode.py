@@ -1,0 +1,78 @@
+"""Host-side timing of the file path around the kernels (no GPU): BGZF/BAM decode, packing into the HBM
+layout, mate linking, column-store build -- on a synthetic coordinate-sorted BAM written here.
+
+    python tools/bench_decode.py [--mbp 3] [--threads N]
+"""
+import argparse
+import os
+import struct
+import sys
+import time
+import zlib
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from vafator_b200 import bamio, device, synth  # noqa: E402
+
+
+def write_bam_from_batch(path, b, lengths):
+    """ReadBatch -> BAM (+ .bai through the fixture writer's index code is not needed here)."""
+    text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join("@SQ\tSN:%s\tLN:%d\n" % (c, l) for c, l in zip(b.contigs, lengths))
+    out = bytearray(b"BAM\1" + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", len(b.contigs)))
+    for c, l in zip(b.contigs, lengths):
+        out += struct.pack("<i", len(c) + 1) + c.encode() + b"\0" + struct.pack("<i", int(l))
+    cig, seq, qual = b.cigar.tobytes(), b.seq.tobytes(), b.qual.tobytes()
+    for i in range(b.n_reads):
+        name = b"q%x\0" % int(b.qname_id[i])
+        nc, lq = int(b.n_cigar[i]), int(b.l_qseq[i])
+        co, so, qo = int(b.cigar_off[i]) * 4, int(b.seq_off[i]), int(b.qual_off[i])
+        body = struct.pack("<iiBBHHHiiii", int(b.tid[i]), int(b.pos[i]), len(name), int(b.mapq[i]), 4680, nc, int(b.flag[i]), lq,
+                           int(b.mtid[i]), int(b.mpos[i]), int(b.isize[i]))
+        body += name + cig[co:co + 4 * nc] + seq[so:so + (lq + 1) // 2] + qual[qo:qo + lq]
+        out += struct.pack("<i", len(body)) + body
+    with open(path, "wb") as fh:
+        for i in range(0, len(out), 0xFF00):
+            data = bytes(out[i:i + 0xFF00])
+            comp = zlib.compressobj(1, zlib.DEFLATED, -15)
+            z = comp.compress(data) + comp.flush()
+            fh.write(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(z) + 25) + z +
+                     struct.pack("<II", zlib.crc32(data) & 0xFFFFFFFF, len(data)))
+        fh.write(bamio._BGZF_EOF)
+    return len(out)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mbp", type=float, default=3.0, help="contig length of the 30x WGS-like BAM, in Mbp")
+    ap.add_argument("--out", default="/tmp/vfk_bench_decode.bam")
+    ap.add_argument("--reps", type=int, default=3)
+    args = ap.parse_args()
+    cfg = synth.wgs(n_contigs=1, contig_len=int(args.mbp * 1e6))
+    batch = synth.reads(cfg)
+    raw = write_bam_from_batch(args.out, batch, [int(args.mbp * 1e6) + 1000])
+    size = os.path.getsize(args.out)
+    print("BAM: %d reads, %.1f MB raw, %.1f MB on disk, %d host threads" % (batch.n_reads, raw / 1e6, size / 1e6, os.cpu_count()))
+
+    def best(f):
+        ts = []
+        for _ in range(args.reps):
+            t = time.perf_counter()
+            r = f()
+            ts.append(time.perf_counter() - t)
+        return min(ts), r
+
+    t, got = best(lambda: bamio.BamFile(args.out, use_index=False).read_batch())
+    assert got.n_reads == batch.n_reads and np.array_equal(got.pos, batch.pos) and np.array_equal(got.qual, batch.qual)
+    print("decode          %.3f s  %.2f M reads/s  %.0f MB/s inflated" % (t, got.n_reads / t / 1e6, raw / t / 1e6))
+    params = device.make_params(min_mapq=1, min_baseq=30)
+    t, mate = best(lambda: device.link_mates(got, params))
+    print("link_mates      %.3f s  %.2f M reads/s" % (t, got.n_reads / t / 1e6))
+    t, _ = best(lambda: device.pack_reads(got, params, mate=mate, columns=False))
+    print("pack            %.3f s  %.2f M reads/s" % (t, got.n_reads / t / 1e6))
+    t, _ = best(lambda: device.pack_reads(got, params, mate=mate, columns=True))
+    print("pack + columns  %.3f s  %.2f M reads/s" % (t, got.n_reads / t / 1e6))
+
+
+if __name__ == "__main__":
+    main()

@@ -7,10 +7,15 @@
 // Blocks are inflated in parallel (OpenMP), records are indexed in one sequential hop and then
 // converted to columns in parallel.  CRAM is not supported (the reference accepts it through
 // htslib; out of scope here and reported as an error).
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 #include "vfk_io.h"
@@ -18,7 +23,10 @@
 int vfkio_fail(int code, const char *msg);
 
 struct vfkio_bam {
-    std::vector<uint8_t> data;  // inflated BAM stream
+    std::vector<uint8_t> data;           // region fetch: the records kept, appended one by one
+    std::unique_ptr<uint8_t[]> stream;   // whole file: the inflated BAM stream (allocated uninitialised: the
+    size_t stream_size = 0;              //   inflating threads touch its pages first, in parallel)
+    const uint8_t *bytes() const { return stream ? stream.get() : data.data(); }
     std::vector<std::string> names;
     std::vector<int64_t> lengths;
     std::string text;
@@ -32,35 +40,55 @@ namespace {
 inline uint32_t le32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 inline uint16_t le16(const uint8_t *p) { return (uint16_t)(p[0] | (p[1] << 8)); }
 
-int inflate_block(const uint8_t *src, size_t n, uint8_t *dst, size_t cap) {
+// one raw-deflate stream per thread, reset between blocks (inflateInit2 allocates the 32 KB window every time)
+struct Inflater {
     z_stream zs;
-    memset(&zs, 0, sizeof(zs));
-    if (inflateInit2(&zs, -15) != Z_OK) return -1;
-    zs.next_in = const_cast<uint8_t *>(src);
-    zs.avail_in = (uInt)n;
-    zs.next_out = dst;
-    zs.avail_out = (uInt)cap;
-    int rc = inflate(&zs, Z_FINISH);
-    inflateEnd(&zs);
-    return (rc == Z_STREAM_END && zs.avail_out == 0) ? 0 : -1;
-}
+    bool ok;
+    Inflater() {
+        memset(&zs, 0, sizeof(zs));
+        ok = inflateInit2(&zs, -15) == Z_OK;
+    }
+    ~Inflater() { if (ok) inflateEnd(&zs); }
+    int block(const uint8_t *src, size_t n, uint8_t *dst, size_t cap) {
+        if (!ok || inflateReset(&zs) != Z_OK) return -1;
+        zs.next_in = const_cast<uint8_t *>(src);
+        zs.avail_in = (uInt)n;
+        zs.next_out = dst;
+        zs.avail_out = (uInt)cap;
+        const int rc = inflate(&zs, Z_FINISH);
+        return (rc == Z_STREAM_END && zs.avail_out == 0) ? 0 : -1;
+    }
+};
+// the compressed file, mapped read-only
+struct Mapped {
+    const uint8_t *p = nullptr;
+    size_t n = 0;
+    ~Mapped() { if (p && n) munmap(const_cast<uint8_t *>(p), n); }
+    bool open(const char *path) {
+        const int fd = ::open(path, O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) != 0) { ::close(fd); return false; }
+        n = (size_t)st.st_size;
+        if (n) {
+            void *m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m == MAP_FAILED) { ::close(fd); n = 0; return false; }
+            madvise(m, n, MADV_SEQUENTIAL);
+            p = (const uint8_t *)m;
+        }
+        ::close(fd);
+        return true;
+    }
+    const uint8_t *data() const { return p; }
+    size_t size() const { return n; }
+    uint8_t operator[](size_t i) const { return p[i]; }
+};
 }  // namespace
 
 extern "C" int vfkio_bam_open(const char *path, vfkio_bam **out) {
     if (!path || !out) return vfkio_fail(VFK_EINVAL, "vfkio_bam_open: NULL argument");
-    FILE *f = fopen(path, "rb");
-    if (!f) return vfkio_fail(VFK_EINVAL, "cannot open alignment file");
-    fseek(f, 0, SEEK_END);
-    const long fsize = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    std::vector<uint8_t> raw((size_t)std::max<long>(fsize, 0));
-    if (fsize > 0 && fread(raw.data(), 1, (size_t)fsize, f) != (size_t)fsize) {
-        fclose(f);
-        return vfkio_fail(VFK_EINVAL, "short read on alignment file");
-    }
-    fclose(f);
-    if (raw.size() >= 4 && memcmp(raw.data(), "CRAM", 4) == 0)
-        return vfkio_fail(VFK_EUNSUPPORTED, "CRAM input is not supported by this build: convert to BAM");
+    Mapped raw;
+    if (!raw.open(path)) return vfkio_fail(VFK_EINVAL, "cannot open alignment file");
     // ---- BGZF block table
     struct Blk { size_t src, n, dst, isize; };
     std::vector<Blk> blocks;
@@ -84,19 +112,22 @@ extern "C" int vfkio_bam_open(const char *path, vfkio_bam **out) {
         p += blen;
     }
     vfkio_bam *b = new vfkio_bam();
-    b->data.resize(total);
+    b->stream.reset(new uint8_t[std::max<size_t>(total, 1)]);
+    b->stream_size = total;
     int bad = 0;
-#pragma omp parallel for schedule(dynamic, 16) reduction(| : bad)
-    for (int64_t i = 0; i < (int64_t)blocks.size(); ++i) {
-        const Blk &k = blocks[(size_t)i];
-        if (k.isize && inflate_block(raw.data() + k.src, k.n, b->data.data() + k.dst, k.isize)) bad |= 1;
+#pragma omp parallel reduction(| : bad)
+    {
+        Inflater inf;
+#pragma omp for schedule(dynamic, 16)
+        for (int64_t i = 0; i < (int64_t)blocks.size(); ++i) {
+            const Blk &k = blocks[(size_t)i];
+            if (k.isize && inf.block(raw.data() + k.src, k.n, b->stream.get() + k.dst, k.isize)) bad |= 1;
+        }
     }
     if (bad) { delete b; return vfkio_fail(VFK_EINVAL, "BGZF block failed to inflate"); }
-    raw.clear();
-    raw.shrink_to_fit();
     // ---- BAM header
-    const uint8_t *d = b->data.data();
-    const size_t n = b->data.size();
+    const uint8_t *d = b->stream.get();
+    const size_t n = b->stream_size;
     if (n < 12 || memcmp(d, "BAM\1", 4) != 0) { delete b; return vfkio_fail(VFK_EINVAL, "not a BAM file (bad magic)"); }
     size_t q = 4;
     const uint32_t l_text = le32(d + q); q += 4;
@@ -194,10 +225,14 @@ struct BlockReader {  // sequential BGZF reader over an open file, from a compre
         }
         out.resize(total);
         int bad = 0;
-#pragma omp parallel for schedule(dynamic, 8) reduction(| : bad)
-        for (int64_t i = 0; i < (int64_t)blocks.size(); ++i) {
-            const Blk &k = blocks[(size_t)i];
-            if (k.isize && inflate_block(raw.data() + k.src, k.n, out.data() + k.dst, k.isize)) bad |= 1;
+#pragma omp parallel reduction(| : bad)
+        {
+            Inflater inf;
+#pragma omp for schedule(dynamic, 8)
+            for (int64_t i = 0; i < (int64_t)blocks.size(); ++i) {
+                const Blk &k = blocks[(size_t)i];
+                if (k.isize && inf.block(raw.data() + k.src, k.n, out.data() + k.dst, k.isize)) bad |= 1;
+            }
         }
         if (bad) return -1;
         raw.erase(raw.begin(), raw.begin() + (long)p);
@@ -425,7 +460,7 @@ extern "C" int vfkio_bam_fill(const vfkio_bam *b, vfkio_reads *out) {
     if (!b || !out) return vfkio_fail(VFK_EINVAL, "vfkio_bam_fill: NULL argument");
     if (!b->sorted) return vfkio_fail(VFK_EINVAL, "BAM file is not coordinate sorted");
     const int64_t n = (int64_t)b->rec_off.size();
-    const uint8_t *d = b->data.data();
+    const uint8_t *d = b->bytes();
     int32_t *tid = (int32_t *)out->tid, *pos = (int32_t *)out->pos, *lq = (int32_t *)out->l_qseq, *ncg = (int32_t *)out->n_cigar;
     int32_t *mtid = (int32_t *)out->mtid, *mpos = (int32_t *)out->mpos, *isz = (int32_t *)out->isize;
     uint16_t *flag = (uint16_t *)out->flag;

@@ -16,6 +16,7 @@
 // so that a column is ONE contiguous read of (depth x 32) bytes, the mate-overlap adjustment a register
 // exchange between two lanes, and no CIGAR is walked on the device.
 #include <algorithm>
+#include <climits>
 #include <cstring>
 #include <vector>
 #include "vfk_io.h"
@@ -81,15 +82,47 @@ extern "C" int vfkio_columns_fill(const vfkio_reads *r, const vfk_params *params
     const int64_t n = placed_reads(r);
     const int64_t nw = plan->n_windows;
     Sector *sec = reinterpret_cast<Sector *>(sectors_out);
-    // ---- sectors per window, offsets
-    std::vector<uint32_t> count((size_t)nw + 1, 0);
-    for (int64_t i = 0; i < n; ++i) {
-        const int64_t span = ref_span(r, i);
-        if (span <= 0) continue;
-        const int64_t w0 = wbase[r->tid[i]] + r->pos[i] / W, w1 = wbase[r->tid[i]] + (r->pos[i] + span - 1) / W;
-        for (int64_t w = w0; w <= w1; ++w) ++count[(size_t)w];
+    // ---- read chunks.  The global index of a read's first window (wbase[tid] + pos / W) never decreases along the
+    // sorted batch, so a contiguous chunk of reads touches one contiguous range of windows [lo, hi]; chunks are
+    // processed in parallel and meet only in the few windows their ranges share.
+    const int64_t n_chunks = std::max<int64_t>(1, std::min<int64_t>(512, n / 2048));
+    struct Chunk {
+        int64_t r0, r1;   // reads
+        int64_t lo, hi;   // windows touched (hi < lo: none)
+        std::vector<uint32_t> cnt;  // sectors this chunk leaves in window lo + k
+    };
+    std::vector<Chunk> chunks((size_t)n_chunks);
+    std::vector<int32_t> span_of((size_t)n);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t t = 0; t < n_chunks; ++t) {
+        Chunk &ck = chunks[(size_t)t];
+        ck.r0 = n * t / n_chunks;
+        ck.r1 = n * (t + 1) / n_chunks;
+        ck.lo = 0;
+        ck.hi = -1;
+        bool any = false;
+        for (int64_t i = ck.r0; i < ck.r1; ++i) {
+            const int64_t span = ref_span(r, i);
+            span_of[(size_t)i] = (int32_t)std::min<int64_t>(span, INT32_MAX);
+            if (span <= 0) continue;
+            const int64_t w0 = wbase[r->tid[i]] + r->pos[i] / W, w1 = wbase[r->tid[i]] + (r->pos[i] + span - 1) / W;
+            if (!any) { ck.lo = w0; any = true; }
+            ck.hi = std::max(ck.hi, w1);
+        }
+        if (!any) continue;
+        ck.cnt.assign((size_t)(ck.hi - ck.lo + 1), 0u);
+        for (int64_t i = ck.r0; i < ck.r1; ++i) {
+            const int64_t span = span_of[(size_t)i];
+            if (span <= 0) continue;
+            const int64_t w0 = wbase[r->tid[i]] + r->pos[i] / W, w1 = wbase[r->tid[i]] + (r->pos[i] + span - 1) / W;
+            for (int64_t w = w0; w <= w1; ++w) ++ck.cnt[(size_t)(w - ck.lo)];
+        }
     }
+    // ---- sectors per window, offsets
     {
+        std::vector<uint32_t> count((size_t)nw + 1, 0);
+        for (const Chunk &ck : chunks)
+            for (size_t k = 0; k < ck.cnt.size(); ++k) count[(size_t)ck.lo + k] += ck.cnt[k];
         uint64_t acc = 0;
         for (int64_t w = 0; w < nw; ++w) {
             woff[w] = (uint32_t)acc;
@@ -98,21 +131,22 @@ extern "C" int vfkio_columns_fill(const vfkio_reads *r, const vfk_params *params
         woff[nw] = (uint32_t)acc;
         if ((int64_t)acc != plan->n_sectors) return vfkio_fail(VFK_EINVAL, "vfkio_columns_fill: plan does not match the batch");
     }
-    // ---- fill, contig by contig (windows of different contigs are disjoint), reads in index order so that the
-    // sectors of a window are sorted by read
+    // ---- fill: reads in index order inside a chunk, a chunk's first slot in a window = what the chunks before it
+    // left there, so that the sectors of a window are sorted by read
     std::vector<uint32_t> sec_read((size_t)plan->n_sectors);  // owner of every sector, for the partner offsets
-    std::vector<int64_t> first_read((size_t)r->n_contigs + 1, n);
-    {
-        int64_t i = 0;
-        for (int32_t t = 0; t <= r->n_contigs; ++t) {
-            while (i < n && r->tid[i] < t) ++i;
-            first_read[(size_t)t] = i;
-        }
-    }
-    std::fill(count.begin(), count.end(), 0u);  // now the per-window cursor
 #pragma omp parallel for schedule(dynamic, 1)
-    for (int32_t t = 0; t < r->n_contigs; ++t) {
-        for (int64_t i = first_read[(size_t)t]; i < first_read[(size_t)t + 1]; ++i) {
+    for (int64_t t = 0; t < n_chunks; ++t) {
+        const Chunk &ck = chunks[(size_t)t];
+        if (ck.hi < ck.lo) continue;
+        std::vector<uint32_t> cursor(ck.cnt.size(), 0u);
+        for (int64_t s2 = 0; s2 < t; ++s2) {
+            const Chunk &e = chunks[(size_t)s2];
+            const int64_t a = std::max(e.lo, ck.lo), b = std::min(e.hi, ck.hi);
+            for (int64_t w = a; w <= b; ++w) cursor[(size_t)(w - ck.lo)] += e.cnt[(size_t)(w - e.lo)];
+        }
+        for (int64_t i = ck.r0; i < ck.r1; ++i) {
+            if (span_of[(size_t)i] <= 0) continue;
+            const int64_t wb = wbase[r->tid[i]];
             const uint32_t *c = r->cigar + r->cigar_off[i];
             const int nc = r->n_cigar[i];
             const uint8_t *q = r->qual + r->qual_off[i], *sq = r->seq + r->seq_off[i];
@@ -122,50 +156,62 @@ extern "C" int vfkio_columns_fill(const vfkio_reads *r, const vfk_params *params
             const uint32_t m = mate[i] & 0x7FFFFFFFu;
             const uint32_t h0_fixed = ((uint32_t)r->mapq[i] << 12) | (pass ? 1u << 28 : 0u) |
                                       (linked && (mate[i] >> 31) ? 1u << 29 : 0u) | (linked && (uint32_t)i < m ? 1u << 30 : 0u);
-            int64_t x = r->pos[i], y = 0;
+            int64_t y = 0;
+            int64_t cur_w = r->pos[i] / W;       // window (of the contig) holding the next reference position
+            int p = (int)(r->pos[i] - cur_w * W);  // ... and the slot of that position inside it
             Sector cur;
-            int64_t cur_w = -1;
+            bool open = false;  // `cur` holds entries of window cur_w
             uint32_t qpos0 = 0, mask = 0, ins_at = 0, ins_len = 0;
             bool has_ins = false, complex = false;
             auto flush = [&]() {
-                if (cur_w < 0) return;
+                if (!open) return;
                 if (qpos0 >= 4096u || ins_len >= 4096u) complex = true;
                 cur.h0 = h0_fixed | (qpos0 & 0xFFFu) | (complex ? 1u << 31 : 0u);
                 cur.h1 = mask | (ins_at << 12) | ((ins_len & 0xFFFu) << 16) | (has_ins ? 1u << 28 : 0u);
-                const int64_t w = wbase[t] + cur_w;
-                const uint32_t at = woff[w] + count[(size_t)w]++;
+                const int64_t w = wb + cur_w;
+                const uint32_t at = woff[w] + cursor[(size_t)(w - ck.lo)]++;
                 sec[at] = cur;
                 sec_read[at] = (uint32_t)i;
+                open = false;
             };
-            auto enter = [&](int64_t w) {
-                flush();
-                cur_w = w;
+            auto enter = [&]() {  // the first entry of window cur_w is about to be written
                 memset(&cur, 0, sizeof(cur));
                 qpos0 = (uint32_t)y;
                 mask = 0; ins_at = 0; ins_len = 0;
                 has_ins = false; complex = false;
+                open = true;
             };
             for (int k = 0; k < nc; ++k) {
                 const uint32_t op = c[k] & 15u;
-                const int64_t l = c[k] >> 4;
+                int64_t l = c[k] >> 4;
                 if (consumes_ref(op)) {
-                    for (int64_t j = 0; j < l; ++j, ++x) {
-                        if (x / W != cur_w) enter(x / W);
-                        const int p = (int)(x % W);
-                        if (is_match(op)) {
-                            const uint32_t code = (y & 1) ? (sq[y >> 1] & 15u) : (sq[y >> 1] >> 4);
-                            cur.e[p] = (uint16_t)(q[y] | (code << 8) | (1u << 12));
-                            mask |= 1u << p;
-                            ++y;
+                    const bool match = is_match(op);
+                    const uint16_t gap = (uint16_t)((op == 3 ? 3u : 2u) << 12);
+                    while (l > 0) {
+                        if (!open) enter();
+                        const int run = (int)std::min<int64_t>(l, W - p);
+                        if (match) {
+                            for (int j = 0; j < run; ++j, ++y) {
+                                const uint32_t code = (y & 1) ? (sq[y >> 1] & 15u) : (sq[y >> 1] >> 4);
+                                cur.e[p + j] = (uint16_t)(q[y] | (code << 8) | (1u << 12));
+                            }
+                            mask |= ((1u << run) - 1u) << p;
                         } else {
-                            cur.e[p] = (uint16_t)((op == 3 ? 3u : 2u) << 12);
+                            for (int j = 0; j < run; ++j) cur.e[p + j] = gap;
+                        }
+                        p += run;
+                        l -= run;
+                        if (p == W) {
+                            flush();
+                            p = 0;
+                            ++cur_w;
                         }
                     }
-                } else if (op == 1) {  // insertion: follows reference position x-1
-                    if (cur_w >= 0 && (x - 1) / W == cur_w && x % W != 0) {
+                } else if (op == 1) {  // insertion: follows the reference position before (cur_w, p)
+                    if (open && p != 0) {  // that position lies in the open window
                         if (has_ins) complex = true;
                         has_ins = true;
-                        ins_at = (uint32_t)((x - 1) % W);
+                        ins_at = (uint32_t)(p - 1);
                         ins_len = (uint32_t)std::min<int64_t>(l, 4096);
                     }
                     y += l;
