@@ -23,7 +23,9 @@ def write_bam_from_batch(path, b, lengths):
     for c, l in zip(b.contigs, lengths):
         out += struct.pack("<i", len(c) + 1) + c.encode() + b"\0" + struct.pack("<i", int(l))
     cig, seq, qual = b.cigar.tobytes(), b.seq.tobytes(), b.qual.tobytes()
+    rec_at = np.zeros(b.n_reads + 1, np.int64)
     for i in range(b.n_reads):
+        rec_at[i] = len(out)
         name = b"q%x\0" % int(b.qname_id[i])
         nc, lq = int(b.n_cigar[i]), int(b.l_qseq[i])
         co, so, qo = int(b.cigar_off[i]) * 4, int(b.seq_off[i]), int(b.qual_off[i])
@@ -31,14 +33,60 @@ def write_bam_from_batch(path, b, lengths):
                            int(b.mtid[i]), int(b.mpos[i]), int(b.isize[i]))
         body += name + cig[co:co + 4 * nc] + seq[so:so + (lq + 1) // 2] + qual[qo:qo + lq]
         out += struct.pack("<i", len(body)) + body
+    rec_at[b.n_reads] = len(out)
+    block_at = []
     with open(path, "wb") as fh:
         for i in range(0, len(out), 0xFF00):
+            block_at.append(fh.tell())
             data = bytes(out[i:i + 0xFF00])
             comp = zlib.compressobj(1, zlib.DEFLATED, -15)
             z = comp.compress(data) + comp.flush()
             fh.write(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(z) + 25) + z +
                      struct.pack("<II", zlib.crc32(data) & 0xFFFFFFFF, len(data)))
+        block_at.append(fh.tell())
         fh.write(bamio._BGZF_EOF)
+    # .bai (SAMv1 5.2): binning index with one chunk per bin + linear index
+    block_at = np.asarray(block_at, np.int64)
+    voff = (block_at[rec_at // 0xFF00] << 16) | (rec_at % 0xFF00)
+    from vafator_b200.sharding import _ref_span
+    end = b.pos.astype(np.int64) + np.maximum(_ref_span(b), 1)
+    bai = bytearray(b"BAI\1" + struct.pack("<i", len(b.contigs)))
+    for t in range(len(b.contigs)):
+        idx = np.nonzero(b.tid == t)[0]
+        if len(idx) == 0:
+            bai += struct.pack("<ii", 0, 0)
+            continue
+        beg_t, end_t = b.pos[idx].astype(np.int64), end[idx] - 1
+        bins = np.zeros(len(idx), np.int64)
+        done = np.zeros(len(idx), bool)
+        for shift, base in ((14, 4681), (17, 585), (20, 73), (23, 9), (26, 1)):  # reg2bin, SAMv1 5.3
+            hit = ~done & ((beg_t >> shift) == (end_t >> shift))
+            bins[hit] = base + (beg_t[hit] >> shift)
+            done |= hit
+        ub = np.unique(bins)
+        bai += struct.pack("<i", len(ub))
+        for bn in ub:  # one chunk per bin, first to last record filed under it
+            members = idx[bins == bn]
+            bai += struct.pack("<Ii", int(bn), 1) + struct.pack("<QQ", int(voff[members[0]]), int(voff[members[-1] + 1]))
+        n_win = int((end[idx].max() - 1) >> 14) + 1
+        linear = np.zeros(n_win, np.int64)
+        first = np.full(n_win, -1, np.int64)
+        w0, w1 = b.pos[idx] >> 14, (end[idx] - 1) >> 14
+        for k in range(int((w1 - w0).max()) + 1):  # reads span few windows
+            w = np.minimum(w0 + k, w1)
+            order = np.argsort(w, kind="stable")
+            ww, ii = w[order], idx[order]
+            keep = np.concatenate([[True], ww[1:] != ww[:-1]])
+            cand = np.full(n_win, np.iinfo(np.int64).max)
+            cand[ww[keep]] = ii[keep]
+            first = np.where((first < 0) | (cand < first), np.where(cand == np.iinfo(np.int64).max, first, cand), first)
+        linear = np.where(first >= 0, voff[np.maximum(first, 0)], 0)
+        for w in range(1, n_win):
+            if linear[w] == 0:
+                linear[w] = linear[w - 1]
+        bai += struct.pack("<i", n_win) + linear.astype("<u8").tobytes()
+    with open(path + ".bai", "wb") as fh:
+        fh.write(bytes(bai))
     return len(out)
 
 
@@ -65,6 +113,12 @@ def main():
     t, got = best(lambda: bamio.BamFile(args.out, use_index=False).read_batch())
     assert got.n_reads == batch.n_reads and np.array_equal(got.pos, batch.pos) and np.array_equal(got.qual, batch.qual)
     print("decode          %.3f s  %.2f M reads/s  %.0f MB/s inflated" % (t, got.n_reads / t / 1e6, raw / t / 1e6))
+    L = int(args.mbp * 1e6)
+    t, reg = best(lambda: bamio.BamFile(args.out).read_batch([(batch.contigs[0], 0, L + 1000)]))
+    assert reg.n_reads == batch.n_reads and np.array_equal(reg.qual, batch.qual)
+    print("decode (.bai, whole contig as one region)  %.3f s  %.2f M reads/s" % (t, reg.n_reads / t / 1e6))
+    t, reg = best(lambda: bamio.BamFile(args.out).read_batch([(batch.contigs[0], L // 2, L // 2 + L // 10)]))
+    print("decode (.bai, a tenth of the contig)       %.3f s  %.2f M reads/s (%d reads)" % (t, reg.n_reads / t / 1e6, reg.n_reads))
     params = device.make_params(min_mapq=1, min_baseq=30)
     t, mate = best(lambda: device.link_mates(got, params))
     print("link_mates      %.3f s  %.2f M reads/s" % (t, got.n_reads / t / 1e6))

@@ -23,14 +23,13 @@
 int vfkio_fail(int code, const char *msg);
 
 struct vfkio_bam {
-    std::vector<uint8_t> data;           // region fetch: the records kept, appended one by one
-    std::unique_ptr<uint8_t[]> stream;   // whole file: the inflated BAM stream (allocated uninitialised: the
-    size_t stream_size = 0;              //   inflating threads touch its pages first, in parallel)
-    const uint8_t *bytes() const { return stream ? stream.get() : data.data(); }
+    // inflated BAM bytes: the whole stream (vfkio_bam_open) or one arena per batch of blocks of a region scan
+    // (vfkio_bam_open_regions).  Allocated uninitialised: the inflating threads touch the pages first, in parallel.
+    std::vector<std::unique_ptr<uint8_t[]>> arenas;
     std::vector<std::string> names;
     std::vector<int64_t> lengths;
     std::string text;
-    std::vector<int64_t> rec_off;  // offset of every record's block_size field, placed reads only
+    std::vector<const uint8_t *> rec;  // every placed record (its block_size field), in file order, inside an arena
     int64_t n_unplaced = 0;
     int64_t n_cigar = 0, n_seq = 0, n_qual = 0;
     int32_t sorted = 1;
@@ -83,51 +82,75 @@ struct Mapped {
     size_t size() const { return n; }
     uint8_t operator[](size_t i) const { return p[i]; }
 };
+
+struct Blk { size_t src, n, dst, isize; };  // deflate payload [src, src+n) of the file -> [dst, dst+isize) of the arena
+// BGZF member at file offset p (SAMv1 4.1): 1 = parsed (payload -> blk.src / blk.n / blk.isize, member length -> blen),
+// 0 = clean end of file, -1 = not BGZF / truncated
+int bgzf_member(const Mapped &raw, size_t p, Blk &blk, size_t &blen) {
+    if (p == raw.size()) return 0;
+    if (p + 18 > raw.size()) return -1;
+    const uint8_t *h = raw.data() + p;
+    if (!(h[0] == 31 && h[1] == 139 && h[2] == 8 && (h[3] & 4))) return -1;
+    const uint16_t xlen = le16(h + 10);
+    size_t x = p + 12;
+    const size_t xe = x + xlen;
+    if (xe > raw.size()) return -1;
+    int bsize = -1;
+    while (x + 4 <= xe) {
+        const uint16_t slen = le16(raw.data() + x + 2);
+        if (raw[x] == 'B' && raw[x + 1] == 'C' && slen == 2) bsize = le16(raw.data() + x + 4);
+        x += 4 + slen;
+    }
+    if (bsize < 0) return -1;
+    blen = (size_t)bsize + 1;
+    if (p + blen > raw.size() || blen < (xe - p) + 8) return -1;
+    blk.src = xe;
+    blk.n = blen - (xe - p) - 8;
+    blk.isize = le32(raw.data() + p + blen - 4);
+    return 1;
+}
+// inflate a table of blocks into `dst` (all cores); false on a corrupt block
+bool inflate_blocks(const Mapped &raw, const std::vector<Blk> &blocks, uint8_t *dst) {
+    int bad = 0;
+#pragma omp parallel reduction(| : bad)
+    {
+        Inflater inf;
+#pragma omp for schedule(dynamic, 8)
+        for (int64_t i = 0; i < (int64_t)blocks.size(); ++i) {
+            const Blk &k = blocks[(size_t)i];
+            if (k.isize && inf.block(raw.data() + k.src, k.n, dst + k.dst, k.isize)) bad |= 1;
+        }
+    }
+    return !bad;
+}
 }  // namespace
 
 extern "C" int vfkio_bam_open(const char *path, vfkio_bam **out) {
     if (!path || !out) return vfkio_fail(VFK_EINVAL, "vfkio_bam_open: NULL argument");
     Mapped raw;
     if (!raw.open(path)) return vfkio_fail(VFK_EINVAL, "cannot open alignment file");
+    if (raw.size() >= 4 && memcmp(raw.data(), "CRAM", 4) == 0)
+        return vfkio_fail(VFK_EUNSUPPORTED, "CRAM input is not supported by this build: convert to BAM");
     // ---- BGZF block table
-    struct Blk { size_t src, n, dst, isize; };
     std::vector<Blk> blocks;
     size_t p = 0, total = 0;
-    while (p + 18 <= raw.size()) {
-        const uint8_t *h = raw.data() + p;
-        if (!(h[0] == 31 && h[1] == 139 && h[2] == 8 && (h[3] & 4))) return vfkio_fail(VFK_EINVAL, "not a BGZF/BAM file");
-        const uint16_t xlen = le16(h + 10);
-        size_t x = p + 12, xe = x + xlen;
-        int bsize = -1;
-        while (x + 4 <= xe && xe <= raw.size()) {
-            const uint16_t slen = le16(raw.data() + x + 2);
-            if (raw[x] == 'B' && raw[x + 1] == 'C' && slen == 2) bsize = le16(raw.data() + x + 4);
-            x += 4 + slen;
-        }
-        if (bsize < 0 || p + (size_t)bsize + 1 > raw.size()) return vfkio_fail(VFK_EINVAL, "corrupt BGZF block header");
-        const size_t blen = (size_t)bsize + 1;
-        const size_t isize = le32(raw.data() + p + blen - 4);
-        blocks.push_back({xe, blen - (xe - p) - 8, total, isize});
-        total += isize;
+    for (;;) {
+        Blk k;
+        size_t blen = 0;
+        const int rc = bgzf_member(raw, p, k, blen);
+        if (rc == 0) break;
+        if (rc < 0) return vfkio_fail(VFK_EINVAL, blocks.empty() ? "not a BGZF/BAM file" : "corrupt BGZF block header");
+        k.dst = total;
+        blocks.push_back(k);
+        total += k.isize;
         p += blen;
     }
     vfkio_bam *b = new vfkio_bam();
-    b->stream.reset(new uint8_t[std::max<size_t>(total, 1)]);
-    b->stream_size = total;
-    int bad = 0;
-#pragma omp parallel reduction(| : bad)
-    {
-        Inflater inf;
-#pragma omp for schedule(dynamic, 16)
-        for (int64_t i = 0; i < (int64_t)blocks.size(); ++i) {
-            const Blk &k = blocks[(size_t)i];
-            if (k.isize && inf.block(raw.data() + k.src, k.n, b->stream.get() + k.dst, k.isize)) bad |= 1;
-        }
-    }
-    if (bad) { delete b; return vfkio_fail(VFK_EINVAL, "BGZF block failed to inflate"); }
+    b->arenas.emplace_back(new uint8_t[std::max<size_t>(total, 1)]);
+    if (!inflate_blocks(raw, blocks, b->arenas[0].get())) { delete b; return vfkio_fail(VFK_EINVAL, "BGZF block failed to inflate"); }
     // ---- BAM header
-    const uint8_t *d = b->stream.get();
-    const size_t n = b->stream_size;
+    const uint8_t *d = b->arenas[0].get();
+    const size_t n = total;
     if (n < 12 || memcmp(d, "BAM\1", 4) != 0) { delete b; return vfkio_fail(VFK_EINVAL, "not a BAM file (bad magic)"); }
     size_t q = 4;
     const uint32_t l_text = le32(d + q); q += 4;
@@ -156,7 +179,7 @@ extern "C" int vfkio_bam_open(const char *path, vfkio_bam **out) {
             if (seen_unplaced || tid < last_tid || (tid == last_tid && pos < last_pos)) b->sorted = 0;
             last_tid = tid;
             last_pos = pos;
-            b->rec_off.push_back((int64_t)q);
+            b->rec.push_back(d + q);
             b->n_cigar += le16(r + 12);
             const int64_t l_seq = (int64_t)le32(r + 16);
             b->n_seq += (l_seq + 1) / 2;
@@ -177,76 +200,10 @@ extern "C" int vfkio_bam_open(const char *path, vfkio_bam **out) {
 // fetches [first.POS-1, last.POS) of every chromosome group through pysam (vafator/pileups.py:71-80,
 // :137-138).  The BAI linear index (SAMv1 5.1.3/5.2: one virtual offset per 16 kbp window = the
 // first record overlapping that window) gives a lower bound; records are then read sequentially until
-// one starts at or beyond the region end.  BGZF blocks are read and inflated in batches (OpenMP).
+// one starts at or beyond the region end.  The file is mapped; BGZF blocks are inflated in growing batches (OpenMP)
+// into arenas the kept records then live in (no per-record copy).
 // ---------------------------------------------------------------------------------------------
 namespace {
-struct BlockReader {  // sequential BGZF reader over an open file, from a compressed offset
-    FILE *f = nullptr;
-    std::vector<uint8_t> raw;   // compressed bytes not yet consumed
-    long file_pos = 0;          // file offset of raw[0]
-    bool eof = false;
-
-    bool refill(size_t want) {
-        while (!eof && raw.size() < want) {
-            const size_t old = raw.size();
-            raw.resize(old + (1u << 22));
-            const size_t got = fread(raw.data() + old, 1, 1u << 22, f);
-            raw.resize(old + got);
-            if (got == 0) eof = true;
-        }
-        return raw.size() >= want;
-    }
-    // inflate up to max_blocks blocks, appending to `out`; returns number of blocks, -1 on corruption
-    int next_batch(std::vector<uint8_t> &out, int max_blocks) {
-        struct Blk { size_t src, n, dst, isize; };
-        std::vector<Blk> blocks;
-        size_t p = 0, total = out.size();
-        while ((int)blocks.size() < max_blocks) {
-            if (!refill(p + 18)) break;
-            const uint8_t *h = raw.data() + p;
-            if (!(h[0] == 31 && h[1] == 139 && h[2] == 8 && (h[3] & 4))) return -1;
-            const uint16_t xlen = le16(h + 10);
-            if (!refill(p + 12 + xlen)) return -1;
-            size_t x = p + 12;
-            const size_t xe = x + xlen;
-            int bsize = -1;
-            while (x + 4 <= xe) {
-                const uint16_t slen = le16(raw.data() + x + 2);
-                if (raw[x] == 'B' && raw[x + 1] == 'C' && slen == 2) bsize = le16(raw.data() + x + 4);
-                x += 4 + slen;
-            }
-            if (bsize < 0) return -1;
-            const size_t blen = (size_t)bsize + 1;
-            if (!refill(p + blen)) return -1;
-            const size_t isize = le32(raw.data() + p + blen - 4);
-            blocks.push_back({xe, blen - (xe - p) - 8, total, isize});
-            total += isize;
-            p += blen;
-        }
-        out.resize(total);
-        int bad = 0;
-#pragma omp parallel reduction(| : bad)
-        {
-            Inflater inf;
-#pragma omp for schedule(dynamic, 8)
-            for (int64_t i = 0; i < (int64_t)blocks.size(); ++i) {
-                const Blk &k = blocks[(size_t)i];
-                if (k.isize && inf.block(raw.data() + k.src, k.n, out.data() + k.dst, k.isize)) bad |= 1;
-            }
-        }
-        if (bad) return -1;
-        raw.erase(raw.begin(), raw.begin() + (long)p);
-        file_pos += (long)p;
-        return (int)blocks.size();
-    }
-    bool seek(long coffset) {
-        raw.clear();
-        eof = false;
-        file_pos = coffset;
-        return fseek(f, coffset, SEEK_SET) == 0;
-    }
-};
-
 inline bool consumes_ref_op(uint32_t op) { return op == 0 || op == 2 || op == 3 || op == 7 || op == 8; }
 
 // header text + reference table from the start of an inflated stream; returns bytes consumed, 0 = need more data
@@ -283,22 +240,35 @@ extern "C" int vfkio_bam_open_regions(const char *path, const char *index_path, 
                                       const int32_t *beg, const int32_t *end, vfkio_bam **out) {
     if (!path || !index_path || !out || n_regions < 0 || (n_regions > 0 && (!contig || !beg || !end)))
         return vfkio_fail(VFK_EINVAL, "vfkio_bam_open_regions: bad argument");
-    BlockReader rd;
-    rd.f = fopen(path, "rb");
-    if (!rd.f) return vfkio_fail(VFK_EINVAL, "cannot open alignment file");
-    struct Closer { FILE *f; ~Closer() { if (f) fclose(f); } } closer{rd.f};
+    Mapped raw;
+    if (!raw.open(path)) return vfkio_fail(VFK_EINVAL, "cannot open alignment file");
+    if (raw.size() >= 4 && memcmp(raw.data(), "CRAM", 4) == 0)
+        return vfkio_fail(VFK_EUNSUPPORTED, "CRAM input is not supported by this build: convert to BAM");
     vfkio_bam *b = new vfkio_bam();
-    // ---- header
+    // ---- header: inflate leading blocks until the text and the reference table are complete
     {
         std::vector<uint8_t> head;
-        bool bad = false;
-        size_t used = 0;
+        size_t cp = 0, used = 0;
         while (used == 0) {
-            const int nb = rd.next_batch(head, 16);
-            if (nb < 0) { delete b; return vfkio_fail(VFK_EINVAL, "not a BGZF/BAM file"); }
+            std::vector<Blk> blocks;
+            size_t total = head.size();
+            for (int k = 0; k < 16; ++k) {
+                Blk blk;
+                size_t blen = 0;
+                const int rc = bgzf_member(raw, cp, blk, blen);
+                if (rc < 0) { delete b; return vfkio_fail(VFK_EINVAL, "not a BGZF/BAM file"); }
+                if (rc == 0) break;
+                blk.dst = total;
+                blocks.push_back(blk);
+                total += blk.isize;
+                cp += blen;
+            }
+            head.resize(total);
+            if (!inflate_blocks(raw, blocks, head.data())) { delete b; return vfkio_fail(VFK_EINVAL, "not a BGZF/BAM file"); }
+            bool bad = false;
             used = parse_header(head, b, &bad);
             if (bad) { delete b; return vfkio_fail(VFK_EINVAL, "not a BAM file (bad magic)"); }
-            if (used == 0 && nb == 0) { delete b; return vfkio_fail(VFK_EINVAL, "truncated BAM header"); }
+            if (used == 0 && blocks.empty()) { delete b; return vfkio_fail(VFK_EINVAL, "truncated BAM header"); }
         }
     }
     if (n_regions == 0) { *out = b; return VFK_OK; }
@@ -376,18 +346,36 @@ extern "C" int vfkio_bam_open_regions(const char *path, const char *index_path, 
                 if (hit && bc.second.end > min_off && bc.second.beg < voff) voff = bc.second.beg;
             }
         }
-        if (!rd.seek((long)(voff >> 16))) { delete b; return vfkio_fail(VFK_EINVAL, "seek failed on alignment file"); }
-        std::vector<uint8_t> buf;
-        size_t q = (size_t)(voff & 0xFFFF);
+        size_t cp = (size_t)(voff >> 16);      // file offset of the next BGZF member
+        size_t q = (size_t)(voff & 0xFFFF);    // scan position inside the current arena
+        std::vector<uint8_t> carry;            // head of a record that continues in the next batch
+        size_t batch_blocks = 64;              // grows: a short region stops early, a chromosome keeps every core busy
         bool done = false;
         while (!done) {
-            const int nb = rd.next_batch(buf, 64);
-            if (nb < 0) { delete b; return vfkio_fail(VFK_EINVAL, "BGZF block failed to inflate"); }
-            while (q + 4 <= buf.size()) {
-                const uint32_t bs = le32(buf.data() + q);
+            std::vector<Blk> blocks;
+            size_t total = carry.size();
+            while (blocks.size() < batch_blocks) {
+                Blk blk;
+                size_t blen = 0;
+                const int rc = bgzf_member(raw, cp, blk, blen);
+                if (rc < 0) { delete b; return vfkio_fail(VFK_EINVAL, "BGZF block failed to inflate"); }
+                if (rc == 0) break;
+                blk.dst = total;
+                blocks.push_back(blk);
+                total += blk.isize;
+                cp += blen;
+            }
+            std::unique_ptr<uint8_t[]> arena(new uint8_t[std::max<size_t>(total, 1)]);
+            if (!carry.empty()) memcpy(arena.get(), carry.data(), carry.size());
+            if (!inflate_blocks(raw, blocks, arena.get())) { delete b; return vfkio_fail(VFK_EINVAL, "BGZF block failed to inflate"); }
+            const uint8_t *buf = arena.get();
+            if (q > total) { delete b; return vfkio_fail(VFK_EINVAL, "BAM index points beyond a BGZF block"); }
+            bool kept = false;
+            while (q + 4 <= total) {
+                const uint32_t bs = le32(buf + q);
                 if (bs < 32) { delete b; return vfkio_fail(VFK_EINVAL, "corrupt BAM record"); }
-                if (q + 4 + bs > buf.size()) break;  // the record continues in the next batch
-                const uint8_t *r = buf.data() + q + 4;
+                if (q + 4 + bs > total) break;  // the record continues in the next batch
+                const uint8_t *r = buf + q + 4;
                 const int32_t rt = (int32_t)le32(r), rp = (int32_t)le32(r + 4);
                 if (rt != tid || rp >= r_end) {
                     if (rt > tid || rt < 0 || (rt == tid && rp >= r_end)) { done = true; break; }
@@ -395,6 +383,7 @@ extern "C" int vfkio_bam_open_regions(const char *path, const char *index_path, 
                     continue;
                 }
                 const uint32_t l_name = r[8], n_cig = le16(r + 12);
+                if (32 + (size_t)l_name + 4 * (size_t)n_cig > bs) { delete b; return vfkio_fail(VFK_EINVAL, "corrupt BAM record"); }
                 const uint8_t *pc = r + 32 + l_name;
                 int64_t span = 0;
                 for (uint32_t k = 0; k < n_cig; ++k) {
@@ -405,8 +394,8 @@ extern "C" int vfkio_bam_open_regions(const char *path, const char *index_path, 
                     if (rt < last_tid || (rt == last_tid && rp < last_pos)) b->sorted = 0;
                     last_tid = rt;
                     last_pos = rp;
-                    b->rec_off.push_back((int64_t)b->data.size());
-                    b->data.insert(b->data.end(), buf.data() + q, buf.data() + q + 4 + bs);
+                    b->rec.push_back(buf + q);
+                    kept = true;
                     b->n_cigar += n_cig;
                     const int64_t l_seq = (int64_t)le32(r + 16);
                     b->n_seq += (l_seq + 1) / 2;
@@ -415,10 +404,12 @@ extern "C" int vfkio_bam_open_regions(const char *path, const char *index_path, 
                 q += 4 + bs;
             }
             if (!done) {
-                if (nb == 0) break;  // end of file
-                buf.erase(buf.begin(), buf.begin() + (long)q);  // keep the partial record
+                if (blocks.empty()) done = true;  // end of file
+                else carry.assign(buf + q, buf + total);  // keep the partial record
                 q = 0;
             }
+            if (kept) b->arenas.push_back(std::move(arena));
+            batch_blocks = std::min<size_t>(batch_blocks * 2, 4096);
         }
         last_tid = std::max(last_tid, tid);
     }
@@ -439,7 +430,7 @@ extern "C" int32_t vfkio_bam_is_sorted(const vfkio_bam *b) { return b ? b->sorte
 
 extern "C" int vfkio_bam_plan(const vfkio_bam *b, vfkio_synth_plan *plan) {
     if (!b || !plan) return vfkio_fail(VFK_EINVAL, "vfkio_bam_plan: NULL argument");
-    plan->n_reads = (int64_t)b->rec_off.size();
+    plan->n_reads = (int64_t)b->rec.size();
     plan->n_cigar = b->n_cigar;
     plan->n_seq_bytes = b->n_seq;
     plan->n_qual_bytes = b->n_qual;
@@ -459,8 +450,7 @@ static inline void name_hashes(const uint8_t *s, uint32_t l, uint32_t &x31, uint
 extern "C" int vfkio_bam_fill(const vfkio_bam *b, vfkio_reads *out) {
     if (!b || !out) return vfkio_fail(VFK_EINVAL, "vfkio_bam_fill: NULL argument");
     if (!b->sorted) return vfkio_fail(VFK_EINVAL, "BAM file is not coordinate sorted");
-    const int64_t n = (int64_t)b->rec_off.size();
-    const uint8_t *d = b->bytes();
+    const int64_t n = (int64_t)b->rec.size();
     int32_t *tid = (int32_t *)out->tid, *pos = (int32_t *)out->pos, *lq = (int32_t *)out->l_qseq, *ncg = (int32_t *)out->n_cigar;
     int32_t *mtid = (int32_t *)out->mtid, *mpos = (int32_t *)out->mpos, *isz = (int32_t *)out->isize;
     uint16_t *flag = (uint16_t *)out->flag;
@@ -471,7 +461,7 @@ extern "C" int vfkio_bam_fill(const vfkio_bam *b, vfkio_reads *out) {
     // offsets: serial prefix sums over the record index
     int64_t c = 0, s = 0, q = 0;
     for (int64_t i = 0; i < n; ++i) {
-        const uint8_t *r = d + b->rec_off[(size_t)i] + 4;
+        const uint8_t *r = b->rec[(size_t)i] + 4;
         co[i] = c; so[i] = s; qo[i] = q;
         const int64_t l_seq = (int64_t)le32(r + 16);
         c += le16(r + 12);
@@ -480,7 +470,7 @@ extern "C" int vfkio_bam_fill(const vfkio_bam *b, vfkio_reads *out) {
     }
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n; ++i) {
-        const uint8_t *r = d + b->rec_off[(size_t)i] + 4;
+        const uint8_t *r = b->rec[(size_t)i] + 4;
         tid[i] = (int32_t)le32(r);
         pos[i] = (int32_t)le32(r + 4);
         const uint32_t l_name = r[8];
