@@ -231,3 +231,42 @@ def test_multiallelic_filter_cli_and_empty_input(tmp_path):
     empty.write_text("##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n")
     multiallelics_filter(["--input-vcf", str(empty), "--output-vcf", str(tmp_path / "e.out.vcf")])
     assert [l for l in (tmp_path / "e.out.vcf").read_text().split("\n") if l and not l.startswith("#")] == []
+
+
+def test_decoder_rejects_damaged_files(tmp_path):
+    """Neither entry point of the decoder may crash on a file that is not a sound BAM: CRAM magic, plain text,
+    a file cut inside a BGZF member, a member whose deflate payload is damaged, an index of another file."""
+    import helpers as H
+    sc = H.load_scenario(os.path.join(H.GOLDEN, "pileup_random_11.json"))
+    good = tmp_path / "good.bam"
+    bamio.write_bam(str(good), sc["bams"][0], sc["contigs"], index=True)
+    raw = open(good, "rb").read()
+    n_good = bamio.BamFile(str(good), use_index=False).read_batch().n_reads
+    assert n_good > 0
+
+    def attempt(name, data, index=None):
+        p = tmp_path / name
+        p.write_bytes(data)
+        if index is not None:
+            (tmp_path / (name + ".bai")).write_bytes(index)
+        outcomes = []
+        for use_index in (False, True) if index is not None else (False,):
+            try:
+                f = bamio.BamFile(str(p), use_index=use_index)
+                b = f.read_batch([(sc["contigs"][0], 0, 1 << 28)] if use_index else None)
+                outcomes.append(b.n_reads)
+            except ValueError as e:
+                outcomes.append(str(e))
+        return outcomes
+
+    bai = open(str(good) + ".bai", "rb").read()
+    assert all("CRAM" in str(o) for o in attempt("x.cram.bam", b"CRAM" + raw[4:], bai))
+    assert all(isinstance(o, str) for o in attempt("text.bam", b"@HD\tVN:1.6\n" * 50, bai))
+    for o in attempt("cut.bam", raw[:len(raw) // 2], bai):  # ends inside a member: an error, never a short batch
+        assert isinstance(o, str), o
+    damaged = bytearray(raw)
+    damaged[len(raw) // 2] ^= 0xFF
+    damaged[len(raw) // 2 + 1] ^= 0xFF
+    for o in attempt("flip.bam", bytes(damaged), bai):  # either zlib notices or the records stop parsing; never more reads
+        assert isinstance(o, str) or o <= n_good
+    assert all(isinstance(o, str) for o in attempt("noindex.bam", raw, b"BAI\1" + b"\0" * 3)[1:])

@@ -83,6 +83,11 @@ struct Mapped {
     uint8_t operator[](size_t i) const { return p[i]; }
 };
 
+// fixed fields + name + CIGAR + sequence + qualities must lie inside the record (nothing verifies the BGZF CRC)
+inline bool record_fits(const uint8_t *r, uint32_t block_size) {
+    const uint64_t l_name = r[8], n_cig = le16(r + 12), l_seq = le32(r + 16);
+    return 32 + l_name + 4 * n_cig + (l_seq + 1) / 2 + l_seq <= block_size;
+}
 struct Blk { size_t src, n, dst, isize; };  // deflate payload [src, src+n) of the file -> [dst, dst+isize) of the arena
 // BGZF member at file offset p (SAMv1 4.1): 1 = parsed (payload -> blk.src / blk.n / blk.isize, member length -> blen),
 // 0 = clean end of file, -1 = not BGZF / truncated
@@ -175,6 +180,7 @@ extern "C" int vfkio_bam_open(const char *path, vfkio_bam **out) {
         if (bs < 32 || q + 4 + bs > n) { delete b; return vfkio_fail(VFK_EINVAL, "truncated BAM record"); }
         const uint8_t *r = d + q + 4;
         const int32_t tid = (int32_t)le32(r), pos = (int32_t)le32(r + 4);
+        if (!record_fits(r, bs)) { delete b; return vfkio_fail(VFK_EINVAL, "corrupt BAM record"); }
         if (tid >= 0 && tid < (int32_t)n_ref) {
             if (seen_unplaced || tid < last_tid || (tid == last_tid && pos < last_pos)) b->sorted = 0;
             last_tid = tid;
@@ -383,7 +389,7 @@ extern "C" int vfkio_bam_open_regions(const char *path, const char *index_path, 
                     continue;
                 }
                 const uint32_t l_name = r[8], n_cig = le16(r + 12);
-                if (32 + (size_t)l_name + 4 * (size_t)n_cig > bs) { delete b; return vfkio_fail(VFK_EINVAL, "corrupt BAM record"); }
+                if (!record_fits(r, bs)) { delete b; return vfkio_fail(VFK_EINVAL, "corrupt BAM record"); }
                 const uint8_t *pc = r + 32 + l_name;
                 int64_t span = 0;
                 for (uint32_t k = 0; k < n_cig; ++k) {
