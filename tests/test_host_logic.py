@@ -191,3 +191,62 @@ def test_annotator_streams_chromosome_groups(tmp_path, monkeypatch, name, indexe
         whole = [len([r for r in sc["bams"][b] if r["tid"] >= 0]) for idx in sc["samples"].values() for b in idx]
         assert all(n <= w for c in FileOracleEngine.calls for n, w in zip(c[2], whole))
         assert any(n < w for c in FileOracleEngine.calls for n, w in zip(c[2], whole))
+
+
+class RandomCountsEngine(engine.Engine):
+    """Device stages replaced by seeded random records: exercises the formatting paths on combinations no BAM
+    scenario reaches (empty lists next to full ones, NaN statistics, uncovered records)."""
+
+    def __init__(self, seed):
+        self.params = device.make_params(min_mapq=1, min_baseq=30)
+        self.fpr, self.error_rate = 5e-7, 1e-3
+        self.rng = np.random.default_rng(seed)
+
+    def pileup(self, batch, units, stop):
+        n, rng = units.n_units, self.rng
+        c = np.zeros(n, device.COUNTS_DTYPE)
+        c["dp"] = rng.integers(0, 40, n)
+        c["n_amb"] = rng.integers(0, 3, n)
+        c["ac_ref"] = rng.integers(0, 3, n) * rng.integers(0, 12, n)
+        c["ac_alt"] = rng.integers(0, 3, n) * rng.integers(0, 12, n)
+        c["n_col"] = rng.integers(0, 4, n)
+        c["med2"] = rng.integers(0, 400, (n, 3, 2))
+        c["s2"] = rng.integers(0, 500, (n, 3))
+        c["status"] = units.meta & 3
+        return c
+
+    def epilogue(self, counts, eaf):
+        n, rng = len(counts), self.rng
+        st = np.zeros(n, device.STATS_DTYPE)
+        st["z"] = np.where(rng.random((n, 3)) < 0.1, np.nan, rng.normal(size=(n, 3)) * 3)
+        st["p"] = np.where(np.isnan(st["z"]), np.nan, rng.random((n, 3)))
+        st["pu"], st["pw"], st["k"] = rng.random(n), rng.random(n) * 1.0001, rng.integers(1, 9, n)
+        return st
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_columnwise_formatting_equals_record_by_record(seed):
+    """SingleBamColumns (all records at once) == Engine._one (record by record), field for field."""
+    rng = np.random.default_rng(100 + seed)
+    alleles = ["A", "C", "G", "T", "a", "N", "R", "AT", "ACG", "TTTT", "at", "GGc"]
+    records = []
+    pos = 100
+    for _ in range(1500):
+        pos += int(rng.integers(0, 30))
+        ref = alleles[rng.integers(0, len(alleles))]
+        alts = [alleles[rng.integers(0, len(alleles))] for _ in range(int(rng.choice([1, 1, 1, 2, 3])))]
+        records.append(("chr1" if pos < 20000 else "chr2", pos, ref, alts))
+
+    class B:
+        contigs = ["chr1", "chr2"]
+    bams = OrderedDict([("tumor", [B()]), ("normal", [B()])])  # replicate samples always go record by record
+    eaf = {s: rng.random(len(records)) for s in bams}
+    outs = []
+    for vectorised in (True, False):
+        eng = RandomCountsEngine(seed)
+        eng.vectorised_format = vectorised
+        outs.append(eng.annotate(records, bams, eaf))
+    for i, (a, b) in enumerate(zip(*outs)):
+        assert list(a.items()) == list(b.items()), (records[i], a, b)
+    assert any("tumor_rsmq" in a for a in outs[0]) and any("tumor_rsmq" not in a for a in outs[0])
+    assert any("nan" in str(a["tumor_mq"]) for a in outs[0])

@@ -185,8 +185,111 @@ def format_fields(prefix: str, suffix: str, with_eaf: bool, alts, kind, ac, dp, 
     return o
 
 
+_SINGLE_KEYS = ("af", "ac", "n", "dp", "eaf", "pu", "pw", "k", "bq", "mq", "pos")
+_RS_TAGS = (("mq", "rsmq"), ("bq", "rsbq"), ("pos", "rspos"))  # emission order (vafator/annotator.py:350-376)
+
+
+class SingleBamColumns:
+    """The INFO fields of one sample backed by ONE BAM, for all records at once -- the common case, and the same
+    strings `Engine._one` builds record by record (which stays the path of replicate BAMs): every value is
+    stringified column-wise, a record then only picks its tuple.  `keys[mask]` / `values[i]`: mask bit m set
+    when the rank-sum pair of _RS_TAGS[m] is present."""
+
+    def __init__(self, sample: str, rows: RowTable, res: BamResult, st: RoundedStats, eaf: np.ndarray):
+        recs = rows.records
+        n_rec, n_row = len(recs), rows.n_rows
+        first = rows.first.tolist()
+        rec_of = rows.rec
+        kind_rec = rows.kind
+        snv_row = (kind_rec[rec_of] == KIND_SNV) if n_row else np.zeros(0, bool)
+        has_rec = res.has
+        has_row = has_rec[rec_of] if n_row else np.zeros(0, bool)
+        dp_rec = res.dp.tolist()
+        ac_row = res.ac.tolist()
+        dp_row = res.dp[rec_of].tolist() if n_row else []
+        af_row = [str(round(float(a) / d, 5)) if d > 0 else "0.0" for a, d in zip(ac_row, dp_row)]
+        acs_row = list(map(str, ac_row))
+        pu_row = list(map(str, st.pu))
+        pw_row = list(map(str, st.pw))
+        k_row = list(map(str, st.k))
+        # ---- medians: "0" = the reference's Counter misses the allele, "nan" = key present with an empty list
+        ref_ok = has_rec & (res.ac_ref > 0)
+        alt_ok = (res.ac > 0) & has_row
+        indel_rec = has_rec & (kind_rec > KIND_SNV)
+        # an indel ALT list is keyed ALT.upper() and looked up with the literal text (engine.SampleFormatter.key_state)
+        present_row = np.asarray([a == a.upper() for r in recs for a in r[3]], bool) if n_row else np.zeros(0, bool)
+        indel_row = indel_rec[rec_of] if n_row else np.zeros(0, bool)
+        med_ref, med_alt = {}, {}
+        for mi, name in enumerate(METRICS):
+            vals = list(map(str, (res.med2_ref[:, mi] / 2.0).tolist())) if n_rec else []
+            code = np.where(ref_ok, 2, 0)                                      # SNV: value or "0"
+            code = np.where(indel_rec, np.where(res.ac_ref > 0, 2, 1), code)     # indel: the REF key always exists
+            if name == "bq":
+                code = np.where(kind_rec != KIND_SNV, 0, code)
+            med_ref[name] = [v if c == 2 else ("nan" if c == 1 else "0") for v, c in zip(vals, code.tolist())]
+            vals = list(map(str, (res.med2_alt[:, mi] / 2.0).tolist())) if n_row else []
+            code = np.where(alt_ok, 2, 0)
+            if n_row:
+                code = np.where(indel_row, np.where(present_row, np.where(alt_ok & (rows.alt == 0), 2, 1), 0), code)
+                if name == "bq":
+                    code = np.where(~snv_row, 0, code)
+            med_alt[name] = [v if c == 2 else ("nan" if c == 1 else "0") for v, c in zip(vals, code.tolist())]
+        # ---- rank sums: reported when both lists hold values and the statistic is a number
+        z_arr = np.asarray(st.z, np.float64).reshape(n_row, 3)
+        p_arr = np.asarray(st.p, np.float64).reshape(n_row, 3)
+        rs_ok, rs_z, rs_p = {}, {}, {}
+        for mi, name in enumerate(METRICS):
+            ok = alt_ok & (ref_ok[rec_of] if n_row else alt_ok) & ~np.isnan(z_arr[:, mi]) & ~np.isnan(p_arr[:, mi])
+            if name == "bq":
+                ok = ok & snv_row
+            rs_ok[name] = ok.tolist()
+            rs_z[name] = [str(z[mi]) for z in st.z]
+            rs_p[name] = [str(q[mi]) for q in st.p]
+        n_str = list(map(str, res.n.tolist()))
+        eaf_str = list(map(str, np.asarray(eaf, np.float64).tolist()))
+        values = []
+        masks = []
+        for i in range(n_rec):
+            r0, r1 = first[i], first[i + 1]
+            if r1 - r0 == 1:
+                fixed = (af_row[r0], acs_row[r0], n_str[i], dp_rec[i], eaf_str[i], pu_row[r0], pw_row[r0], k_row[r0],
+                         med_ref["bq"][i] + "," + med_alt["bq"][r0], med_ref["mq"][i] + "," + med_alt["mq"][r0],
+                         med_ref["pos"][i] + "," + med_alt["pos"][r0])
+                mask = 0
+                extra = ()
+                for m, (name, _tag) in enumerate(_RS_TAGS):
+                    if rs_ok[name][r0]:
+                        mask |= 1 << m
+                        extra += (rs_z[name][r0], rs_p[name][r0])
+            else:
+                rr = range(r0, r1)
+                fixed = (",".join(af_row[r0:r1]), ",".join(acs_row[r0:r1]), n_str[i], dp_rec[i], eaf_str[i],
+                         ",".join(pu_row[r0:r1]), pw_row[r0] if r1 > r0 else "0.0", k_row[r0] if r1 > r0 else "1",
+                         ",".join([med_ref["bq"][i]] + med_alt["bq"][r0:r1]), ",".join([med_ref["mq"][i]] + med_alt["mq"][r0:r1]),
+                         ",".join([med_ref["pos"][i]] + med_alt["pos"][r0:r1]))
+                mask = 0
+                extra = ()
+                for m, (name, _tag) in enumerate(_RS_TAGS):
+                    zs = [rs_z[name][r] for r in rr if rs_ok[name][r]]
+                    if zs:
+                        mask |= 1 << m
+                        extra += (",".join(zs), ",".join(rs_p[name][r] for r in rr if rs_ok[name][r]))
+            values.append(fixed + extra)
+            masks.append(mask)
+        self.values, self.masks = values, masks
+        base = tuple("{}_{}".format(sample, k) for k in _SINGLE_KEYS)
+        self.keys = []
+        for mask in range(8):
+            ks = base
+            for m, (_name, tag) in enumerate(_RS_TAGS):
+                if mask >> m & 1:
+                    ks += ("{}_{}".format(sample, tag), "{}_{}_pv".format(sample, tag))
+            self.keys.append(ks)
+
+
 class Engine:
     """Drives the device for a set of VCF records against a set of BAM read batches."""
+    vectorised_format = True  # single-BAM samples are formatted column-wise (SingleBamColumns); False: record by record
 
     def __init__(self, device_index: int = 0, min_mapq: int = 0, min_baseq: int = 29, include_ambiguous: bool = True,
                  fpr: float = 5e-7, error_rate: float = 1e-3, devices: Optional[Sequence[int]] = None, columns: bool = True):
@@ -301,12 +404,16 @@ class Engine:
         in_range, stop_rec = chrom_groups(records)
         fmt = SampleFormatter(rows)
         per_sample = OrderedDict()
+        units_of_header = {}
         for sample, batches in bams.items():
             eaf_row = np.asarray(eaf[sample], np.float64)[rows.rec] if rows.n_rows else np.zeros(0)
             results, stats = [], []
             for batch in batches:
-                recs_in = [r if ok else (r[0], r[1], "", []) for r, ok in zip(records, in_range)]
-                units = build_units(recs_in, batch.contigs)
+                contigs_key = tuple(batch.contigs)
+                if contigs_key not in units_of_header:  # BAMs of one run nearly always share their reference
+                    recs_in = records if in_range.all() else [r if ok else (r[0], r[1], "", []) for r, ok in zip(records, in_range)]
+                    units_of_header[contigs_key] = build_units(recs_in, batch.contigs)
+                units = units_of_header[contigs_key]
                 counts = self.pileup(batch, units, stop_rec[units.rec] if units.n_units else np.zeros(0, np.int32))
                 bad = counts["status"] & _dev.ST_READLEN if len(counts) else np.zeros(0, np.uint32)
                 if len(counts) and bad.any():
@@ -334,12 +441,29 @@ class Engine:
                             needs.append((i, j, b_ref, b_alt))
                 cross = self._cross_bam(records, in_range, stop_rec, batches, needs, np.asarray(eaf[sample], np.float64))
             per_sample[sample] = (results, stats, merged_stats, cross)
+        columns = {}
+        if self.vectorised_format:
+            columns = {sample: SingleBamColumns(sample, rows, results[0], stats[0], eaf[sample])
+                       for sample, (results, stats, _m, _c) in per_sample.items() if len(results) == 1}
         out = []
+        if len(columns) == len(per_sample):  # every sample has a single BAM: nothing is left to do record by record
+            cols = list(columns.values())
+            for i in range(len(records)):
+                info = OrderedDict()
+                for col in cols:
+                    info.update(zip(col.keys[col.masks[i]], col.values[i]))
+                out.append(info)
+            return out
+        first, kinds = rows.first.tolist(), rows.kind.tolist()
         for i, (chrom, pos, ref, alts) in enumerate(records):
             info = OrderedDict()
-            r0, r1 = int(rows.first[i]), int(rows.first[i + 1])
-            kind = int(rows.kind[i])
+            r0, r1 = first[i], first[i + 1]
+            kind = kinds[i]
             for sample, (results, stats, merged_stats, cross) in per_sample.items():
+                col = columns.get(sample)
+                if col is not None:
+                    info.update(zip(col.keys[col.masks[i]], col.values[i]))
+                    continue
                 e = float(eaf[sample][i])
                 states = [fmt.key_state(i, res) for res in results]
                 nb = len(results)

@@ -23,18 +23,25 @@ class VcfRecord:
         self.INFO: Dict[str, object] = {}  # annotations to add, in insertion order
 
     def line(self) -> str:
-        f = list(self.fields)
-        if self.INFO:
-            old = [] if f[7] in (".", "") else f[7].split(";")
+        f = self.fields
+        if not self.INFO:
+            return "\t".join(f)
+        if f[7] in (".", ""):
+            info = ";".join(["%s=%s" % kv for kv in self.INFO.items()])
+        else:
+            old = f[7].split(";")
             keys = {kv.split("=", 1)[0]: i for i, kv in enumerate(old)}
-            for k, v in self.INFO.items():
-                kv = "%s=%s" % (k, v)
-                if k in keys:
-                    old[keys[k]] = kv
-                else:
-                    old.append(kv)
-            f[7] = ";".join(old)
-        return "\t".join(f)
+            if keys.keys().isdisjoint(self.INFO):
+                info = f[7] + ";" + ";".join(["%s=%s" % kv for kv in self.INFO.items()])
+            else:  # an annotation replaces the value of a key the record already carries, in place
+                for k, v in self.INFO.items():
+                    kv = "%s=%s" % (k, v)
+                    if k in keys:
+                        old[keys[k]] = kv
+                    else:
+                        old.append(kv)
+                info = ";".join(old)
+        return "\t".join(f[:7] + [info] + f[8:])
 
 
 class VcfReader:
