@@ -63,11 +63,17 @@ def write_bam_from_batch(path, b, lengths):
             hit = ~done & ((beg_t >> shift) == (end_t >> shift))
             bins[hit] = base + (beg_t[hit] >> shift)
             done |= hit
-        ub = np.unique(bins)
+        # chunks: runs of consecutive records filed under the same bin
+        starts = np.nonzero(np.concatenate([[True], bins[1:] != bins[:-1]]))[0]
+        stops = np.concatenate([starts[1:], [len(idx)]])
+        order = np.argsort(bins[starts], kind="stable")
+        ub, first_of = np.unique(bins[starts][order], return_index=True)
         bai += struct.pack("<i", len(ub))
-        for bn in ub:  # one chunk per bin, first to last record filed under it
-            members = idx[bins == bn]
-            bai += struct.pack("<Ii", int(bn), 1) + struct.pack("<QQ", int(voff[members[0]]), int(voff[members[-1] + 1]))
+        for k, bn in enumerate(ub):
+            runs = order[first_of[k]:(first_of[k + 1] if k + 1 < len(ub) else len(order))]
+            bai += struct.pack("<Ii", int(bn), len(runs))
+            for rj in runs:
+                bai += struct.pack("<QQ", int(voff[idx[starts[rj]]]), int(voff[idx[stops[rj] - 1] + 1]))
         n_win = int((end[idx].max() - 1) >> 14) + 1
         linear = np.zeros(n_win, np.int64)
         first = np.full(n_win, -1, np.int64)

@@ -88,16 +88,18 @@ class BamFile:
         return ReadBatch(contigs=list(self.contigs), contig_lengths=self.lengths, **arr)
 
     def read_batch(self, regions: Optional[Sequence[tuple]] = None) -> ReadBatch:
-        """regions: [(contig, start, stop)] 0-based half open; merged per contig and put in file order.  Ignored
-        (the whole file is returned) when the file has no index."""
+        """regions: [(contig, start, stop)] 0-based half open, any order; overlapping ones are merged.  A read
+        overlapping several regions is delivered once; the batch is in file order.  Ignored (the whole file is
+        returned) when the file has no index."""
         if self.index_path and regions is not None:
             order = {c: i for i, c in enumerate(self.contigs)}
-            span = {}
-            for c, a, b in regions:
-                if c in order:
-                    lo, hi = span.get(c, (a, b))
-                    span[c] = (min(lo, a), max(hi, b))
-            todo = sorted(span.items(), key=lambda kv: order[kv[0]])
+            todo = []  # per contig in file order: sorted, overlapping or touching regions merged
+            for c, a, b in sorted((r for r in regions if r[0] in order), key=lambda r: (order[r[0]], r[1], r[2])):
+                a = max(0, a)
+                if todo and todo[-1][0] == c and a <= todo[-1][1][1]:
+                    todo[-1][1][1] = max(todo[-1][1][1], b)
+                else:
+                    todo.append((c, [a, b]))
             n = len(todo)
             names = (C.c_char_p * max(n, 1))(*[c.encode() for c, _ in todo])
             beg = np.asarray([max(0, a) for _, (a, _b) in todo], np.int32)

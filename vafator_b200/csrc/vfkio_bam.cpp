@@ -8,11 +8,13 @@
 // converted to columns in parallel.  CRAM is not supported (the reference accepts it through
 // htslib; out of scope here and reported as an error).
 #include <fcntl.h>
+#include <omp.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
 #include <algorithm>
+#include <climits>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -120,7 +122,7 @@ bool inflate_blocks(const Mapped &raw, const std::vector<Blk> &blocks, uint8_t *
 #pragma omp parallel reduction(| : bad)
     {
         Inflater inf;
-#pragma omp for schedule(dynamic, 8)
+#pragma omp for schedule(dynamic, 1)
         for (int64_t i = 0; i < (int64_t)blocks.size(); ++i) {
             const Blk &k = blocks[(size_t)i];
             if (k.isize && inf.block(raw.data() + k.src, k.n, dst + k.dst, k.isize)) bad |= 1;
@@ -310,6 +312,8 @@ extern "C" int vfkio_bam_open_regions(const char *path, const char *index_path, 
             if (q + 4 > ix.size()) { delete b; return vfkio_fail(VFK_EINVAL, "truncated BAM index"); }
             const uint32_t n_intv = le32(ix.data() + q); q += 4;
             if (q + (size_t)n_intv * 8 > ix.size()) { delete b; return vfkio_fail(VFK_EINVAL, "truncated BAM index"); }
+            std::stable_sort(bins[r].begin(), bins[r].end(),
+                             [](const std::pair<uint32_t, Chunk> &x, const std::pair<uint32_t, Chunk> &y) { return x.first < y.first; });
             linear[r].resize(n_intv);
             for (uint32_t k = 0; k < n_intv; ++k) linear[r][k] = le64(ix.data() + q + (size_t)k * 8);
             q += (size_t)n_intv * 8;
@@ -317,6 +321,7 @@ extern "C" int vfkio_bam_open_regions(const char *path, const char *index_path, 
     }
     // ---- regions, in file order
     int32_t last_tid = -1, last_pos = -1, last_end = -1;
+    int32_t scanned_tid = -1, scanned_end = 0;  // the region scanned before this one
     for (int32_t g = 0; g < n_regions; ++g) {
         int32_t tid = -1;
         for (size_t t = 0; t < b->names.size(); ++t)
@@ -342,20 +347,30 @@ extern "C" int vfkio_bam_open_regions(const char *path, const char *index_path, 
         uint64_t voff = min_off;
         {
             const int64_t e1 = (int64_t)r_end - 1;
-            for (const auto &bc : bins[(size_t)tid]) {
-                const uint32_t bin = bc.first;
-                bool hit = bin == 0;
-                for (int lvl = 1, shift = 26; lvl <= 5 && !hit; ++lvl, shift -= 3) {
-                    const uint32_t base = ((1u << (3 * lvl)) - 1) / 7;
-                    hit = bin >= base + (uint32_t)(r_beg >> shift) && bin <= base + (uint32_t)(e1 >> shift);
-                }
-                if (hit && bc.second.end > min_off && bc.second.beg < voff) voff = bc.second.beg;
+            const auto &bv = bins[(size_t)tid];  // sorted by bin number
+            auto consider = [&](uint32_t first_bin, uint32_t last_bin) {
+                auto it = std::lower_bound(bv.begin(), bv.end(), first_bin,
+                                           [](const std::pair<uint32_t, Chunk> &x, uint32_t v) { return x.first < v; });
+                for (; it != bv.end() && it->first <= last_bin; ++it)
+                    if (it->second.end > min_off && it->second.beg < voff) voff = it->second.beg;
+            };
+            consider(0u, 0u);
+            for (int lvl = 1, shift = 26; lvl <= 5; ++lvl, shift -= 3) {
+                const uint32_t base = ((1u << (3 * lvl)) - 1) / 7;
+                consider(base + (uint32_t)(r_beg >> shift), base + (uint32_t)(e1 >> shift));
             }
         }
+        // a record starting before the end of the previous region of this contig and reaching into this one was kept
+        // there (it overlaps both): every record is delivered once, in file order
+        const int32_t keep_from = tid == scanned_tid ? scanned_end : INT32_MIN;
+        scanned_tid = tid;
+        scanned_end = r_end;
         size_t cp = (size_t)(voff >> 16);      // file offset of the next BGZF member
         size_t q = (size_t)(voff & 0xFFFF);    // scan position inside the current arena
         std::vector<uint8_t> carry;            // head of a record that continues in the next batch
-        size_t batch_blocks = 64;              // grows: a short region stops early, a chromosome keeps every core busy
+        // blocks per batch: one per core to begin with (a window around one variant needs the few blocks between the
+        // 16 kbp index point and its last read), doubling, so that a chromosome-long region soon runs in large batches
+        size_t batch_blocks = (size_t)std::max(4, omp_get_max_threads());
         bool done = false;
         while (!done) {
             std::vector<Blk> blocks;
@@ -388,6 +403,7 @@ extern "C" int vfkio_bam_open_regions(const char *path, const char *index_path, 
                     q += 4 + bs;  // still on an earlier contig (lower bound of the index): skip
                     continue;
                 }
+                if (rp < keep_from) { q += 4 + bs; continue; }
                 const uint32_t l_name = r[8], n_cig = le16(r + 12);
                 if (!record_fits(r, bs)) { delete b; return vfkio_fail(VFK_EINVAL, "corrupt BAM record"); }
                 const uint8_t *pc = r + 32 + l_name;
