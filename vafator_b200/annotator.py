@@ -14,6 +14,7 @@ import vafator_b200
 from .bamio import BamFile
 from .constants import BATCH_SIZE, _HEADER_TEMPLATES, _REPLICATE_HEADER_TEMPLATES
 from .engine import Engine
+from .fetch import fetch_group
 from .ploidies import DEFAULT_PLOIDY
 from .power import DEFAULT_ERROR_RATE, DEFAULT_FPR, PowerCalculator
 from .vcf import VcfReader, VcfWriter
@@ -73,9 +74,9 @@ class Annotator(object):
 
         The VCF is streamed one chromosome group at a time -- consecutive records of one CHROM, the unit the
         reference piles up (stream_variants_by_chrom, vafator/pileups.py:83-103) -- so the host never holds more
-        than the reads of one chromosome: with an indexed BAM only [first.POS-1, last.POS) of the group is decoded
-        (what the reference fetches, vafator/pileups.py:137-138) and the batch is dropped, on the host and on the
-        device, before the next group is read.  A BAM without an index is decoded once and stays resident."""
+        than the reads of one chromosome: with an indexed BAM only the reads the group's columns depend on are decoded
+        (windows around the variants inside [first.POS-1, last.POS), the span the reference fetches; fetch.py) and
+        the batch is dropped, on the host and on the device, before the next group is read.  A BAM without an index is decoded once and stays resident."""
         group = []
         for v in self.vcf:
             if not v.ALT:
@@ -98,8 +99,10 @@ class Annotator(object):
         records = [(v.CHROM, v.POS, v.REF, v.ALT) for v in variants]
         chrom = records[0][0]
         positions = [r[1] for r in records]
-        regions = [(chrom, min(positions) - 1, max(positions))]
-        bams = OrderedDict((s, [r.read_batch(regions) for r in readers]) for s, readers in self.bam_readers.items())
+        # the reads the group's columns depend on: windows around the variants inside the span the reference fetches,
+        # [first.POS-1, last.POS) (vafator/pileups.py:137-138); a dense group gets the whole span (vafator_b200/fetch.py)
+        bams = OrderedDict((s, [fetch_group(r, chrom, positions[0], positions[-1], positions, self.engine.params) for r in readers])
+                           for s, readers in self.bam_readers.items())
         eaf = {s: self.power.expected_vafs(s, [chrom] * len(records), positions) for s in bams}
         infos = self.engine.annotate(records, bams, eaf)
         batch = []

@@ -232,3 +232,86 @@ def write_bam(path: str, records: Sequence[dict], contigs: Sequence[str], length
                 bai += struct.pack("<Q", v)
         with open(path + ".bai", "wb") as fh:
             fh.write(bytes(bai))
+
+
+def write_bam_batch(path: str, b: ReadBatch, lengths: Optional[Sequence[int]] = None, level: int = 1) -> int:
+    """A coordinate-sorted ReadBatch as BAM + `.bai` (binning index with one chunk per run of records of a bin,
+    linear index).  Read names are synthesised from `qname_id` (mates share it).  For fixtures and host-side
+    benchmarks of files too large for the record-dict writer above; returns the size of the uncompressed stream."""
+    lengths = list(lengths) if lengths is not None else (list(b.contig_lengths) if b.contig_lengths is not None else [1 << 28] * len(b.contigs))
+    text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join("@SQ\tSN:%s\tLN:%d\n" % (c, l) for c, l in zip(b.contigs, lengths))
+    out = bytearray(b"BAM\1" + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", len(b.contigs)))
+    for c, l in zip(b.contigs, lengths):
+        out += struct.pack("<i", len(c) + 1) + c.encode() + b"\0" + struct.pack("<i", int(l))
+    cig, seq, qual = b.cigar.tobytes(), b.seq.tobytes(), b.qual.tobytes()
+    rec_at = np.zeros(b.n_reads + 1, np.int64)
+    for i in range(b.n_reads):
+        rec_at[i] = len(out)
+        name = b"q%x\0" % int(b.qname_id[i])
+        nc, lq = int(b.n_cigar[i]), int(b.l_qseq[i])
+        co, so, qo = int(b.cigar_off[i]) * 4, int(b.seq_off[i]), int(b.qual_off[i])
+        body = struct.pack("<iiBBHHHiiii", int(b.tid[i]), int(b.pos[i]), len(name), int(b.mapq[i]), 4680, nc, int(b.flag[i]), lq,
+                           int(b.mtid[i]), int(b.mpos[i]), int(b.isize[i]))
+        body += name + cig[co:co + 4 * nc] + seq[so:so + (lq + 1) // 2] + qual[qo:qo + lq]
+        out += struct.pack("<i", len(body)) + body
+    rec_at[b.n_reads] = len(out)
+    block_at = []
+    with open(path, "wb") as fh:
+        for i in range(0, len(out), 0xFF00):
+            block_at.append(fh.tell())
+            data = bytes(out[i:i + 0xFF00])
+            comp = zlib.compressobj(level, zlib.DEFLATED, -15)
+            z = comp.compress(data) + comp.flush()
+            fh.write(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(z) + 25) + z +
+                     struct.pack("<II", zlib.crc32(data) & 0xFFFFFFFF, len(data)))
+        block_at.append(fh.tell())
+        fh.write(_BGZF_EOF)
+    # .bai (SAMv1 5.2): binning index with one chunk per bin + linear index
+    block_at = np.asarray(block_at, np.int64)
+    voff = (block_at[rec_at // 0xFF00] << 16) | (rec_at % 0xFF00)
+    from .sharding import _ref_span
+    end = b.pos.astype(np.int64) + np.maximum(_ref_span(b), 1)
+    bai = bytearray(b"BAI\1" + struct.pack("<i", len(b.contigs)))
+    for t in range(len(b.contigs)):
+        idx = np.nonzero(b.tid == t)[0]
+        if len(idx) == 0:
+            bai += struct.pack("<ii", 0, 0)
+            continue
+        beg_t, end_t = b.pos[idx].astype(np.int64), end[idx] - 1
+        bins = np.zeros(len(idx), np.int64)
+        done = np.zeros(len(idx), bool)
+        for shift, base in ((14, 4681), (17, 585), (20, 73), (23, 9), (26, 1)):  # reg2bin, SAMv1 5.3
+            hit = ~done & ((beg_t >> shift) == (end_t >> shift))
+            bins[hit] = base + (beg_t[hit] >> shift)
+            done |= hit
+        # chunks: runs of consecutive records filed under the same bin
+        starts = np.nonzero(np.concatenate([[True], bins[1:] != bins[:-1]]))[0]
+        stops = np.concatenate([starts[1:], [len(idx)]])
+        order = np.argsort(bins[starts], kind="stable")
+        ub, first_of = np.unique(bins[starts][order], return_index=True)
+        bai += struct.pack("<i", len(ub))
+        for k, bn in enumerate(ub):
+            runs = order[first_of[k]:(first_of[k + 1] if k + 1 < len(ub) else len(order))]
+            bai += struct.pack("<Ii", int(bn), len(runs))
+            for rj in runs:
+                bai += struct.pack("<QQ", int(voff[idx[starts[rj]]]), int(voff[idx[stops[rj] - 1] + 1]))
+        n_win = int((end[idx].max() - 1) >> 14) + 1
+        linear = np.zeros(n_win, np.int64)
+        first = np.full(n_win, -1, np.int64)
+        w0, w1 = b.pos[idx] >> 14, (end[idx] - 1) >> 14
+        for k in range(int((w1 - w0).max()) + 1):  # reads span few windows
+            w = np.minimum(w0 + k, w1)
+            order = np.argsort(w, kind="stable")
+            ww, ii = w[order], idx[order]
+            keep = np.concatenate([[True], ww[1:] != ww[:-1]])
+            cand = np.full(n_win, np.iinfo(np.int64).max)
+            cand[ww[keep]] = ii[keep]
+            first = np.where((first < 0) | (cand < first), np.where(cand == np.iinfo(np.int64).max, first, cand), first)
+        linear = np.where(first >= 0, voff[np.maximum(first, 0)], 0)
+        for w in range(1, n_win):
+            if linear[w] == 0:
+                linear[w] = linear[w - 1]
+        bai += struct.pack("<i", n_win) + linear.astype("<u8").tobytes()
+    with open(path + ".bai", "wb") as fh:
+        fh.write(bytes(bai))
+    return len(out)
