@@ -319,58 +319,79 @@ extern "C" int vfkio_bam_open_regions(const char *path, const char *index_path, 
             q += (size_t)n_intv * 8;
         }
     }
-    // ---- regions, in file order
-    int32_t last_tid = -1, last_pos = -1, last_end = -1;
-    int32_t scanned_tid = -1, scanned_end = 0;  // the region scanned before this one
-    for (int32_t g = 0; g < n_regions; ++g) {
-        int32_t tid = -1;
-        for (size_t t = 0; t < b->names.size(); ++t)
-            if (b->names[t] == contig[g]) tid = (int32_t)t;
-        if (tid < 0) continue;  // a contig the BAM does not know has no reads
-        if (tid < last_tid || (tid == last_tid && beg[g] < last_end)) {
-            delete b;
-            return vfkio_fail(VFK_EINVAL, "vfkio_bam_open_regions: regions must be sorted and disjoint");
-        }
-        last_end = end[g];
-        const std::vector<uint64_t> &lin = linear[(size_t)tid];
-        const int32_t r_beg = std::max(beg[g], 0), r_end = end[g];
-        if (lin.empty() || r_end <= r_beg) { last_tid = tid; continue; }
-        size_t w = std::min<size_t>((size_t)(r_beg >> 14), lin.size() - 1);
-        uint64_t min_off = lin[w];
-        // an empty window carries 0 (or the value of the window before it): every read overlapping the region
-        // then overlaps a later window, whose entry is a valid lower bound
-        while (min_off == 0 && w + 1 < lin.size()) min_off = lin[++w];
-        if (min_off == 0) { last_tid = tid; continue; }
-        // Start of the scan: the earliest chunk of a bin overlapping the region that is not entirely before the
-        // linear-index bound (the linear index only knows mapped reads; a placed unmapped mate in front of the
-        // first mapped read of a window is reachable through its bin only).  From there the file is read in order.
-        uint64_t voff = min_off;
-        {
-            const int64_t e1 = (int64_t)r_end - 1;
-            const auto &bv = bins[(size_t)tid];  // sorted by bin number
-            auto consider = [&](uint32_t first_bin, uint32_t last_bin) {
-                auto it = std::lower_bound(bv.begin(), bv.end(), first_bin,
-                                           [](const std::pair<uint32_t, Chunk> &x, uint32_t v) { return x.first < v; });
-                for (; it != bv.end() && it->first <= last_bin; ++it)
-                    if (it->second.end > min_off && it->second.beg < voff) voff = it->second.beg;
-            };
-            consider(0u, 0u);
-            for (int lvl = 1, shift = 26; lvl <= 5; ++lvl, shift -= 3) {
-                const uint32_t base = ((1u << (3 * lvl)) - 1) / 7;
-                consider(base + (uint32_t)(r_beg >> shift), base + (uint32_t)(e1 >> shift));
+    // ---- regions, in file order: validate, find each one's scan start, then scan.  Many regions (windows around
+    // sparse variants) are scanned in parallel, each with a serial inflate; a few long ones one after the other,
+    // each inflating its block batches on all cores.
+    struct Job {
+        int32_t tid, r_beg, r_end, keep_from;
+        uint64_t voff;
+        std::vector<std::unique_ptr<uint8_t[]>> arenas;
+        std::vector<const uint8_t *> rec;
+        int64_t n_cigar = 0, n_seq = 0, n_qual = 0;
+        const char *error = nullptr;
+    };
+    std::vector<Job> jobs;
+    {
+        int32_t prev_tid = -1, prev_end = -1;        // region order check
+        int32_t scanned_tid = -1, scanned_end = 0;   // the region scanned before this one
+        for (int32_t g = 0; g < n_regions; ++g) {
+            int32_t tid = -1;
+            for (size_t t = 0; t < b->names.size(); ++t)
+                if (b->names[t] == contig[g]) tid = (int32_t)t;
+            if (tid < 0) continue;  // a contig the BAM does not know has no reads
+            if (tid < prev_tid || (tid == prev_tid && beg[g] < prev_end)) {
+                delete b;
+                return vfkio_fail(VFK_EINVAL, "vfkio_bam_open_regions: regions must be sorted and disjoint");
             }
+            prev_tid = tid;
+            prev_end = end[g];
+            const std::vector<uint64_t> &lin = linear[(size_t)tid];
+            const int32_t r_beg = std::max(beg[g], 0), r_end = end[g];
+            if (lin.empty() || r_end <= r_beg) continue;
+            size_t w = std::min<size_t>((size_t)(r_beg >> 14), lin.size() - 1);
+            uint64_t min_off = lin[w];
+            // an empty window carries 0 (or the value of the window before it): every read overlapping the region
+            // then overlaps a later window, whose entry is a valid lower bound
+            while (min_off == 0 && w + 1 < lin.size()) min_off = lin[++w];
+            if (min_off == 0) continue;
+            // Start of the scan: the earliest chunk of a bin overlapping the region that is not entirely before the
+            // linear-index bound (the linear index only knows mapped reads; a placed unmapped mate in front of the
+            // first mapped read of a window is reachable through its bin only).  From there the file is read in order.
+            uint64_t voff = min_off;
+            {
+                const int64_t e1 = (int64_t)r_end - 1;
+                const auto &bv = bins[(size_t)tid];  // sorted by bin number
+                auto consider = [&](uint32_t first_bin, uint32_t last_bin) {
+                    auto it = std::lower_bound(bv.begin(), bv.end(), first_bin,
+                                               [](const std::pair<uint32_t, Chunk> &x, uint32_t v) { return x.first < v; });
+                    for (; it != bv.end() && it->first <= last_bin; ++it)
+                        if (it->second.end > min_off && it->second.beg < voff) voff = it->second.beg;
+                };
+                consider(0u, 0u);
+                for (int lvl = 1, shift = 26; lvl <= 5; ++lvl, shift -= 3) {
+                    const uint32_t base = ((1u << (3 * lvl)) - 1) / 7;
+                    consider(base + (uint32_t)(r_beg >> shift), base + (uint32_t)(e1 >> shift));
+                }
+            }
+            jobs.emplace_back();
+            Job &j = jobs.back();
+            j.tid = tid; j.r_beg = r_beg; j.r_end = r_end; j.voff = voff;
+            // a record starting before the end of the previous region of this contig and reaching into this one was
+            // kept there (it overlaps both): every record is delivered once, in file order
+            j.keep_from = tid == scanned_tid ? scanned_end : INT32_MIN;
+            scanned_tid = tid;
+            scanned_end = r_end;
         }
-        // a record starting before the end of the previous region of this contig and reaching into this one was kept
-        // there (it overlaps both): every record is delivered once, in file order
-        const int32_t keep_from = tid == scanned_tid ? scanned_end : INT32_MIN;
-        scanned_tid = tid;
-        scanned_end = r_end;
-        size_t cp = (size_t)(voff >> 16);      // file offset of the next BGZF member
-        size_t q = (size_t)(voff & 0xFFFF);    // scan position inside the current arena
-        std::vector<uint8_t> carry;            // head of a record that continues in the next batch
+    }
+    auto scan = [&raw](Job &j, bool parallel_inflate) {
+        const int32_t tid = j.tid, r_beg = j.r_beg, r_end = j.r_end;
+        size_t cp = (size_t)(j.voff >> 16);      // file offset of the next BGZF member
+        size_t q = (size_t)(j.voff & 0xFFFF);    // scan position inside the current arena
+        std::vector<uint8_t> carry;              // head of a record that continues in the next batch
         // blocks per batch: one per core to begin with (a window around one variant needs the few blocks between the
         // 16 kbp index point and its last read), doubling, so that a chromosome-long region soon runs in large batches
-        size_t batch_blocks = (size_t)std::max(4, omp_get_max_threads());
+        size_t batch_blocks = parallel_inflate ? (size_t)std::max(4, omp_get_max_threads()) : 2;
+        Inflater serial;
         bool done = false;
         while (!done) {
             std::vector<Blk> blocks;
@@ -379,7 +400,7 @@ extern "C" int vfkio_bam_open_regions(const char *path, const char *index_path, 
                 Blk blk;
                 size_t blen = 0;
                 const int rc = bgzf_member(raw, cp, blk, blen);
-                if (rc < 0) { delete b; return vfkio_fail(VFK_EINVAL, "BGZF block failed to inflate"); }
+                if (rc < 0) { j.error = "BGZF block failed to inflate"; return; }
                 if (rc == 0) break;
                 blk.dst = total;
                 blocks.push_back(blk);
@@ -388,13 +409,21 @@ extern "C" int vfkio_bam_open_regions(const char *path, const char *index_path, 
             }
             std::unique_ptr<uint8_t[]> arena(new uint8_t[std::max<size_t>(total, 1)]);
             if (!carry.empty()) memcpy(arena.get(), carry.data(), carry.size());
-            if (!inflate_blocks(raw, blocks, arena.get())) { delete b; return vfkio_fail(VFK_EINVAL, "BGZF block failed to inflate"); }
+            if (parallel_inflate) {
+                if (!inflate_blocks(raw, blocks, arena.get())) { j.error = "BGZF block failed to inflate"; return; }
+            } else {
+                for (const Blk &k : blocks)
+                    if (k.isize && serial.block(raw.data() + k.src, k.n, arena.get() + k.dst, k.isize)) {
+                        j.error = "BGZF block failed to inflate";
+                        return;
+                    }
+            }
             const uint8_t *buf = arena.get();
-            if (q > total) { delete b; return vfkio_fail(VFK_EINVAL, "BAM index points beyond a BGZF block"); }
+            if (q > total) { j.error = "BAM index points beyond a BGZF block"; return; }
             bool kept = false;
             while (q + 4 <= total) {
                 const uint32_t bs = le32(buf + q);
-                if (bs < 32) { delete b; return vfkio_fail(VFK_EINVAL, "corrupt BAM record"); }
+                if (bs < 32) { j.error = "corrupt BAM record"; return; }
                 if (q + 4 + bs > total) break;  // the record continues in the next batch
                 const uint8_t *r = buf + q + 4;
                 const int32_t rt = (int32_t)le32(r), rp = (int32_t)le32(r + 4);
@@ -403,9 +432,9 @@ extern "C" int vfkio_bam_open_regions(const char *path, const char *index_path, 
                     q += 4 + bs;  // still on an earlier contig (lower bound of the index): skip
                     continue;
                 }
-                if (rp < keep_from) { q += 4 + bs; continue; }
+                if (rp < j.keep_from) { q += 4 + bs; continue; }
                 const uint32_t l_name = r[8], n_cig = le16(r + 12);
-                if (!record_fits(r, bs)) { delete b; return vfkio_fail(VFK_EINVAL, "corrupt BAM record"); }
+                if (!record_fits(r, bs)) { j.error = "corrupt BAM record"; return; }
                 const uint8_t *pc = r + 32 + l_name;
                 int64_t span = 0;
                 for (uint32_t k = 0; k < n_cig; ++k) {
@@ -413,15 +442,12 @@ extern "C" int vfkio_bam_open_regions(const char *path, const char *index_path, 
                     if (consumes_ref_op(cw & 15u)) span += cw >> 4;
                 }
                 if ((int64_t)rp + std::max<int64_t>(span, 1) > (int64_t)r_beg) {  // overlaps the region (bam_endpos semantics)
-                    if (rt < last_tid || (rt == last_tid && rp < last_pos)) b->sorted = 0;
-                    last_tid = rt;
-                    last_pos = rp;
-                    b->rec.push_back(buf + q);
+                    j.rec.push_back(buf + q);
                     kept = true;
-                    b->n_cigar += n_cig;
+                    j.n_cigar += n_cig;
                     const int64_t l_seq = (int64_t)le32(r + 16);
-                    b->n_seq += (l_seq + 1) / 2;
-                    b->n_qual += l_seq;
+                    j.n_seq += (l_seq + 1) / 2;
+                    j.n_qual += l_seq;
                 }
                 q += 4 + bs;
             }
@@ -430,10 +456,36 @@ extern "C" int vfkio_bam_open_regions(const char *path, const char *index_path, 
                 else carry.assign(buf + q, buf + total);  // keep the partial record
                 q = 0;
             }
-            if (kept) b->arenas.push_back(std::move(arena));
+            if (kept) j.arenas.push_back(std::move(arena));
             batch_blocks = std::min<size_t>(batch_blocks * 2, 4096);
         }
-        last_tid = std::max(last_tid, tid);
+    };
+    const int64_t n_jobs = (int64_t)jobs.size();
+    if (n_jobs >= 2 * (int64_t)omp_get_max_threads()) {
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int64_t k = 0; k < n_jobs; ++k) scan(jobs[(size_t)k], false);
+    } else {
+        for (int64_t k = 0; k < n_jobs; ++k) scan(jobs[(size_t)k], true);
+    }
+    // ---- stitch the regions together in order
+    int32_t last_tid = -1, last_pos = -1;
+    for (Job &j : jobs) {
+        if (j.error) {
+            const char *msg = j.error;
+            delete b;
+            return vfkio_fail(VFK_EINVAL, msg);
+        }
+        for (const uint8_t *r : j.rec) {
+            const int32_t rt = (int32_t)le32(r + 4), rp = (int32_t)le32(r + 8);
+            if (rt < last_tid || (rt == last_tid && rp < last_pos)) b->sorted = 0;
+            last_tid = rt;
+            last_pos = rp;
+        }
+        b->rec.insert(b->rec.end(), j.rec.begin(), j.rec.end());
+        for (auto &a2 : j.arenas) b->arenas.push_back(std::move(a2));
+        b->n_cigar += j.n_cigar;
+        b->n_seq += j.n_seq;
+        b->n_qual += j.n_qual;
     }
     *out = b;
     return VFK_OK;
