@@ -74,19 +74,20 @@ class Annotator(object):
 
         The VCF is streamed one chromosome group at a time -- consecutive records of one CHROM, the unit the
         reference piles up (stream_variants_by_chrom, vafator/pileups.py:83-103) -- so the host never holds more
-        than the reads of one chromosome: with an indexed BAM only the reads the group's columns depend on are decoded
+        than the reads of two chromosome groups: with an indexed BAM only the reads the group's columns depend on are decoded
         (windows around the variants inside [first.POS-1, last.POS), the span the reference fetches; fetch.py) and
-        the batch is dropped, on the host and on the device, before the next group is read.  A BAM without an index is decoded once and stays resident."""
-        group = []
-        for v in self.vcf:
-            if not v.ALT:
-                raise ValueError("VCF record %s:%d has no ALT allele" % (v.CHROM, v.POS))
-            if group and v.CHROM != group[0].CHROM:
-                self._annotate_group(group)
-                group = []
-            group.append(v)
-        if group:
-            self._annotate_group(group)
+        the batch is dropped, on the host and on the device, when the group is written; the next group is decoded in
+        the background meanwhile.  A BAM without an index is decoded once and stays resident."""
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(1) as pool:  # decodes group k+1 (native code, GIL released) while group k is annotated
+            pending = None
+            for group in self._chromosome_groups():
+                fetched = pool.submit(self._fetch_group, group)
+                if pending is not None:
+                    self._annotate_group(pending[0], pending[1].result())
+                pending = (group, fetched)
+            if pending is not None:
+                self._annotate_group(pending[0], pending[1].result())
         self.vcf_writer.close()
         self.vcf.close()
         self.engine.release_reads()
@@ -94,15 +95,32 @@ class Annotator(object):
             for bam in readers:
                 bam.close()
 
-    def _annotate_group(self, variants: list) -> None:
-        """One chromosome group: decode its reads, annotate, write, release."""
+    def _chromosome_groups(self):
+        group = []
+        for v in self.vcf:
+            if not v.ALT:
+                raise ValueError("VCF record %s:%d has no ALT allele" % (v.CHROM, v.POS))
+            if group and v.CHROM != group[0].CHROM:
+                yield group
+                group = []
+            group.append(v)
+        if group:
+            yield group
+
+    def _fetch_group(self, variants: list) -> "OrderedDict":
+        """The read batches of one chromosome group: windows around the variants inside the span the reference
+        fetches, [first.POS-1, last.POS) (vafator/pileups.py:137-138); a dense group gets the whole span
+        (vafator_b200/fetch.py)."""
+        chrom = variants[0].CHROM
+        positions = [v.POS for v in variants]
+        return OrderedDict((s, [fetch_group(r, chrom, positions[0], positions[-1], positions, self.engine.params) for r in readers])
+                           for s, readers in self.bam_readers.items())
+
+    def _annotate_group(self, variants: list, bams: "OrderedDict") -> None:
+        """One chromosome group: annotate, write, release its reads."""
         records = [(v.CHROM, v.POS, v.REF, v.ALT) for v in variants]
         chrom = records[0][0]
         positions = [r[1] for r in records]
-        # the reads the group's columns depend on: windows around the variants inside the span the reference fetches,
-        # [first.POS-1, last.POS) (vafator/pileups.py:137-138); a dense group gets the whole span (vafator_b200/fetch.py)
-        bams = OrderedDict((s, [fetch_group(r, chrom, positions[0], positions[-1], positions, self.engine.params) for r in readers])
-                           for s, readers in self.bam_readers.items())
         eaf = {s: self.power.expected_vafs(s, [chrom] * len(records), positions) for s in bams}
         infos = self.engine.annotate(records, bams, eaf)
         batch = []
