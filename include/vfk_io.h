@@ -8,6 +8,7 @@
  */
 #ifndef VFK_IO_H
 #define VFK_IO_H
+#include <stddef.h>
 #include <stdint.h>
 #include "vfk.h"
 
@@ -63,6 +64,12 @@ typedef struct {
 int vfkio_columns_plan(const vfkio_reads *r, int64_t *wbase /*[n_contigs+1]*/, vfkio_col_plan *plan);
 int vfkio_columns_fill(const vfkio_reads *r, const vfk_params *params, const uint32_t *mate, const int64_t *wbase,
                        const vfkio_col_plan *plan, uint32_t *woff /*[n_windows+1]*/, uint8_t *sectors /*[n_sectors*32]*/);
+
+/* Raw DEFLATE (RFC 1951) of one whole stream into a buffer of exactly the inflated size -- the shape of a BGZF
+ * member (SAMv1 4.1), which is what the BAM decoder spends its time on.  Returns 0 when the stream ends after
+ * exactly out_n bytes; non-zero on anything else (malformed, truncated, or merely unusual input) without writing
+ * outside [out, out + out_n) -- the BAM decoder then asks zlib for the authoritative answer. */
+int vfkio_inflate_raw(const uint8_t *in, size_t in_n, uint8_t *out, size_t out_n);
 
 /* ---- BGZF / BAM decoding (coordinate-sorted BAM; CRAM is reported as unsupported) -----------
  * vfkio_bam_open inflates the file (blocks in parallel) and indexes its placed records;

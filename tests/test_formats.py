@@ -270,3 +270,69 @@ def test_decoder_rejects_damaged_files(tmp_path):
     for o in attempt("flip.bam", bytes(damaged), bai):  # either zlib notices or the records stop parsing; never more reads
         assert isinstance(o, str) or o <= n_good
     assert all(isinstance(o, str) for o in attempt("noindex.bam", raw, b"BAI\1" + b"\0" * 3)[1:])
+
+
+def test_inflate_matches_zlib():
+    """vfkio_inflate_raw (the decoder's own DEFLATE) against zlib: every compression level and strategy (stored,
+    fixed and dynamic codes, single-distance-code streams), text-like / run-heavy / random / BAM-like inputs, empty
+    input, sizes around the word-copy slack; wrong sizes, cut and damaged streams must be refused or decoded like
+    zlib -- never a write outside the buffer."""
+    import ctypes as C
+    import zlib
+    import helpers as H
+    from vafator_b200 import device
+    lib = device.libio()
+    lib.vfkio_inflate_raw.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    rng = np.random.default_rng(7)
+    GUARD = 64
+
+    def mine(stream, size):
+        buf = np.full(size + 2 * GUARD, 0xA5, np.uint8)
+        rc = lib.vfkio_inflate_raw(stream, len(stream), buf.ctypes.data + GUARD, size)
+        assert (buf[:GUARD] == 0xA5).all() and (buf[GUARD + size:] == 0xA5).all(), "wrote outside the buffer"
+        return rc, buf[GUARD:GUARD + size].tobytes()
+
+    def inputs():
+        yield b""
+        yield b"a"
+        yield b"abcabcabc" * 7000
+        yield bytes(rng.integers(0, 256, 70000, dtype=np.uint8))
+        yield bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), 65000))
+        yield bytes(np.repeat(rng.integers(30, 42, 900, dtype=np.uint8), rng.integers(1, 140, 900)))[:65280]
+        for n in (1, 7, 8, 9, 257, 258, 259, 265, 273, 274, 275, 300, 1000):
+            yield bytes(rng.integers(0, 4, n, dtype=np.uint8))
+        sc = H.load_scenario(os.path.join(H.GOLDEN, "pileup_random_12.json"))
+        yield b"".join((r["qname"] + r["seq"]).encode() + bytes(r["qual"] if not isinstance(r["qual"], str) else r["qual"].encode())
+                       for r in sc["bams"][0])[:65280]
+
+    n_ok = n_fallback = 0
+    for data in inputs():
+        for level in (0, 1, 4, 6, 9):
+            for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_RLE, zlib.Z_HUFFMAN_ONLY, zlib.Z_FILTERED):
+                c = zlib.compressobj(level, zlib.DEFLATED, -15, 9, strategy)
+                stream = c.compress(data) + c.flush()
+                rc, got = mine(stream, len(data))
+                if rc == 0:
+                    assert got == data
+                    n_ok += 1
+                else:
+                    n_fallback += 1  # allowed (zlib takes over), but must stay the exception
+                if len(data) > 0:
+                    assert mine(stream, len(data) - 1)[0] != 0 and mine(stream, len(data) + 1)[0] != 0
+                    assert mine(stream[:len(stream) // 2], len(data))[0] != 0
+    assert n_ok > 20 * n_fallback, (n_ok, n_fallback)
+    # damaged streams: whatever zlib says about them, a success here must carry zlib's bytes
+    data = bytes(rng.choice(np.frombuffer(b"ACGTN#<>AAAA", np.uint8), 40000))
+    stream = bytearray(zlib.compress(data, 6)[2:-4])
+    for _ in range(300):
+        bad = bytearray(stream)
+        for _k in range(int(rng.integers(1, 4))):
+            bad[int(rng.integers(0, len(bad)))] ^= 1 << int(rng.integers(0, 8))
+        rc, got = mine(bytes(bad), len(data))
+        if rc == 0:
+            d = zlib.decompressobj(-15)
+            try:
+                ref = d.decompress(bytes(bad))
+            except zlib.error:
+                ref = None
+            assert ref is not None and ref[:len(data)] == got and len(ref) == len(data)

@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <climits>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -51,6 +52,8 @@ struct Inflater {
     }
     ~Inflater() { if (ok) inflateEnd(&zs); }
     int block(const uint8_t *src, size_t n, uint8_t *dst, size_t cap) {
+        static const bool zlib_only = getenv("VFKIO_ZLIB") != nullptr;
+        if (!zlib_only && vfkio_inflate_raw(src, n, dst, cap) == 0) return 0;  // vfkio_inflate.cpp; zlib decides the rest
         if (!ok || inflateReset(&zs) != Z_OK) return -1;
         zs.next_in = const_cast<uint8_t *>(src);
         zs.avail_in = (uInt)n;
