@@ -65,6 +65,12 @@ int vfkio_columns_plan(const vfkio_reads *r, int64_t *wbase /*[n_contigs+1]*/, v
 int vfkio_columns_fill(const vfkio_reads *r, const vfk_params *params, const uint32_t *mate, const int64_t *wbase,
                        const vfkio_col_plan *plan, uint32_t *woff /*[n_windows+1]*/, uint8_t *sectors /*[n_sectors*32]*/);
 
+/* The same store with every window's run transposed: n header pairs {h0, h1}, then 12 rows of n 16-bit entries
+ * (row p = position p of the window) -- a column then reads 10 n contiguous-by-part bytes instead of 32 n.  Same
+ * offsets and sizes as the sector form (`out` holds woff[n_windows] * 32 bytes, must not alias `sectors`).
+ * Prepared for the next kernel revision: vfk_pileup reads the SECTOR form. */
+int vfkio_columns_transpose(const uint32_t *woff, int64_t n_windows, const uint8_t *sectors, uint8_t *out);
+
 /* Raw DEFLATE (RFC 1951) of one whole stream into a buffer of exactly the inflated size -- the shape of a BGZF
  * member (SAMv1 4.1), which is what the BAM decoder spends its time on.  Returns 0 when the stream ends after
  * exactly out_n bytes; non-zero on anything else (malformed, truncated, or merely unusual input) without writing

@@ -266,3 +266,34 @@ def test_column_store_on_noisy_synthetic_reads():
             if off:
                 assert reads[k + off] == int(pk.mate[i] & 0x7FFFFFFF)
     assert n_complex < 0.02 * sectors.shape[0]
+
+
+def test_column_store_window_transposed_form():
+    """vfkio_columns_transpose: header pairs first, then one row of entries per window position -- checked against
+    a numpy restatement, window by window, on noisy synthetic reads."""
+    import ctypes as C
+    from vafator_b200 import synth
+    batch = synth.reads(synth.wgs(n_contigs=2, contig_len=60_000, p_del=0.05, p_ins=0.05, p_skip=0.01))
+    params = device.make_params(min_mapq=1, min_baseq=30)
+    pk = device.pack_reads(batch, params, columns=True)
+    woff = np.ascontiguousarray(pk.col_off, np.uint32)
+    src = np.ascontiguousarray(pk.col_sectors, np.uint8)
+    out = np.full_like(src, 0xEE)
+    lib = device.libio()
+    lib.vfkio_columns_transpose.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    assert lib.vfkio_columns_transpose(woff.ctypes.data, len(woff) - 1, src.ctypes.data, out.ctypes.data) == 0
+    assert lib.vfkio_columns_transpose(woff.ctypes.data, len(woff) - 1, src.ctypes.data, src.ctypes.data) != 0  # not in place
+    sec = src.reshape(-1, 32)
+    entries = sec[:, :24].copy().view(np.uint16).reshape(-1, 12)
+    headers = sec[:, 24:].copy().view(np.uint32).reshape(-1, 2)
+    checked = 0
+    for w in np.random.default_rng(3).choice(len(woff) - 1, 400, replace=False):
+        a, b = int(woff[w]), int(woff[w + 1])
+        n = b - a
+        if n == 0:
+            continue
+        run = out[a * 32:b * 32]
+        assert np.array_equal(run[:8 * n].view(np.uint32).reshape(n, 2), headers[a:b])
+        assert np.array_equal(run[8 * n:].view(np.uint16).reshape(12, n), entries[a:b].T)
+        checked += n
+    assert checked > 1000

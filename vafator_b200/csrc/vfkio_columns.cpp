@@ -240,3 +240,34 @@ extern "C" int vfkio_columns_fill(const vfkio_reads *r, const vfk_params *params
     }
     return VFK_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Window-transposed form of the same store (prepared for the next kernel revision; the shipped kernels read the
+// sector form above).  A column needs 10 of the 32 bytes of each sector -- one entry and the two header words --
+// and the sector form makes the device (or, on the host entry point, PCIe) move all 32.  Transposed, the run of a
+// window with n sectors keeps its place and size (32 n bytes from byte 32 * woff[w]) but is laid out as
+//     n header pairs {h0, h1}            8 n bytes
+//     12 rows of n entries (u16)         row p = position p of the window: 2 n bytes each
+// so that a column reads one contiguous 8 n-byte block and one contiguous 2 n-byte row: 310 bytes instead of
+// 992 at n = 31.  Sector k of the run <-> header pair k and entry k of every row.
+// ---------------------------------------------------------------------------------------------
+extern "C" int vfkio_columns_transpose(const uint32_t *woff, int64_t n_windows, const uint8_t *sectors, uint8_t *out) {
+    if (!woff || n_windows < 0 || ((!sectors || !out) && n_windows && woff[n_windows])) return vfkio_fail(VFK_EINVAL, "vfkio_columns_transpose: NULL argument");
+    if (sectors == out) return vfkio_fail(VFK_EINVAL, "vfkio_columns_transpose: cannot work in place");
+#pragma omp parallel for schedule(dynamic, 4096)
+    for (int64_t w = 0; w < n_windows; ++w) {
+        const uint32_t a = woff[w], n = woff[w + 1] - a;
+        if (!n) continue;
+        const Sector *src = reinterpret_cast<const Sector *>(sectors) + a;
+        uint8_t *base = out + (size_t)a * 32u;
+        uint32_t *hdr = reinterpret_cast<uint32_t *>(base);
+        uint16_t *rows = reinterpret_cast<uint16_t *>(base + (size_t)n * 8u);
+        for (uint32_t k = 0; k < n; ++k) {
+            hdr[2 * k] = src[k].h0;
+            hdr[2 * k + 1] = src[k].h1;
+            for (int p = 0; p < W; ++p) rows[(size_t)p * n + k] = src[k].e[p];
+        }
+    }
+    return VFK_OK;
+}
+
