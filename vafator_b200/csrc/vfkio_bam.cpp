@@ -42,19 +42,21 @@ namespace {
 inline uint32_t le32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 inline uint16_t le16(const uint8_t *p) { return (uint16_t)(p[0] | (p[1] << 8)); }
 
-// one raw-deflate stream per thread, reset between blocks (inflateInit2 allocates the 32 KB window every time)
+// one inflater per thread: the own decoder first, a zlib stream (reset between blocks) when that one declines
 struct Inflater {
     z_stream zs;
-    bool ok;
-    Inflater() {
-        memset(&zs, 0, sizeof(zs));
-        ok = inflateInit2(&zs, -15) == Z_OK;
-    }
-    ~Inflater() { if (ok) inflateEnd(&zs); }
+    bool ready = false;
+    ~Inflater() { if (ready) inflateEnd(&zs); }
     int block(const uint8_t *src, size_t n, uint8_t *dst, size_t cap) {
         static const bool zlib_only = getenv("VFKIO_ZLIB") != nullptr;
         if (!zlib_only && vfkio_inflate_raw(src, n, dst, cap) == 0) return 0;  // vfkio_inflate.cpp; zlib decides the rest
-        if (!ok || inflateReset(&zs) != Z_OK) return -1;
+        if (!ready) {  // the zlib state (32 KB window and all) is only set up by a thread that needs it
+            memset(&zs, 0, sizeof(zs));
+            if (inflateInit2(&zs, -15) != Z_OK) return -1;
+            ready = true;
+        } else if (inflateReset(&zs) != Z_OK) {
+            return -1;
+        }
         zs.next_in = const_cast<uint8_t *>(src);
         zs.avail_in = (uInt)n;
         zs.next_out = dst;
@@ -157,50 +159,105 @@ extern "C" int vfkio_bam_open(const char *path, vfkio_bam **out) {
     }
     vfkio_bam *b = new vfkio_bam();
     b->arenas.emplace_back(new uint8_t[std::max<size_t>(total, 1)]);
-    if (!inflate_blocks(raw, blocks, b->arenas[0].get())) { delete b; return vfkio_fail(VFK_EINVAL, "BGZF block failed to inflate"); }
-    // ---- BAM header
-    const uint8_t *d = b->arenas[0].get();
-    const size_t n = total;
-    if (n < 12 || memcmp(d, "BAM\1", 4) != 0) { delete b; return vfkio_fail(VFK_EINVAL, "not a BAM file (bad magic)"); }
-    size_t q = 4;
-    const uint32_t l_text = le32(d + q); q += 4;
-    if (q + l_text + 4 > n) { delete b; return vfkio_fail(VFK_EINVAL, "truncated BAM header"); }
-    b->text.assign((const char *)d + q, l_text);
-    q += l_text;
-    const uint32_t n_ref = le32(d + q); q += 4;
-    for (uint32_t r = 0; r < n_ref; ++r) {
-        if (q + 4 > n) { delete b; return vfkio_fail(VFK_EINVAL, "truncated BAM reference table"); }
-        const uint32_t l_name = le32(d + q); q += 4;
-        if (q + l_name + 4 > n) { delete b; return vfkio_fail(VFK_EINVAL, "truncated BAM reference table"); }
-        b->names.emplace_back((const char *)d + q, l_name ? l_name - 1 : 0);
-        q += l_name;
-        b->lengths.push_back((int64_t)le32(d + q));
-        q += 4;
-    }
-    // ---- record index (sequential hop), placed reads only
-    int32_t last_tid = -1, last_pos = -1;
-    bool seen_unplaced = false;
-    while (q + 4 <= n) {
-        const uint32_t bs = le32(d + q);
-        if (bs < 32 || q + 4 + bs > n) { delete b; return vfkio_fail(VFK_EINVAL, "truncated BAM record"); }
-        const uint8_t *r = d + q + 4;
-        const int32_t tid = (int32_t)le32(r), pos = (int32_t)le32(r + 4);
-        if (!record_fits(r, bs)) { delete b; return vfkio_fail(VFK_EINVAL, "corrupt BAM record"); }
-        if (tid >= 0 && tid < (int32_t)n_ref) {
-            if (seen_unplaced || tid < last_tid || (tid == last_tid && pos < last_pos)) b->sorted = 0;
-            last_tid = tid;
-            last_pos = pos;
-            b->rec.push_back(d + q);
-            b->n_cigar += le16(r + 12);
-            const int64_t l_seq = (int64_t)le32(r + 16);
-            b->n_seq += (l_seq + 1) / 2;
-            b->n_qual += l_seq;
-        } else {
-            seen_unplaced = true;
-            ++b->n_unplaced;
+    uint8_t *const d = b->arenas[0].get();
+    // ---- BAM header, then the record index: a sequential hop from record to record (placed reads only) over the
+    // inflated prefix of the stream.  It runs on one thread while the others inflate the next batch of blocks.
+    struct {
+        size_t q = 0;
+        bool header = false;
+        uint32_t n_ref = 0;
+        int32_t last_tid = -1, last_pos = -1;
+        bool seen_unplaced = false;
+    } hs;
+    auto hop = [&](size_t avail, bool final) -> const char * {
+        if (!hs.header) {
+            if (avail < 12) return final ? "not a BAM file (bad magic)" : nullptr;
+            if (memcmp(d, "BAM\1", 4) != 0) return "not a BAM file (bad magic)";
+            size_t q = 4;
+            const uint32_t l_text = le32(d + q); q += 4;
+            if (q + l_text + 4 > avail) return final ? "truncated BAM header" : nullptr;
+            const size_t text_at = q;
+            q += l_text;
+            const uint32_t n_ref = le32(d + q); q += 4;
+            std::vector<std::string> names;
+            std::vector<int64_t> lengths;
+            for (uint32_t r = 0; r < n_ref; ++r) {
+                if (q + 4 > avail) return final ? "truncated BAM reference table" : nullptr;
+                const uint32_t l_name = le32(d + q); q += 4;
+                if (q + l_name + 4 > avail) return final ? "truncated BAM reference table" : nullptr;
+                names.emplace_back((const char *)d + q, l_name ? l_name - 1 : 0);
+                q += l_name;
+                lengths.push_back((int64_t)le32(d + q));
+                q += 4;
+            }
+            b->text.assign((const char *)d + text_at, l_text);
+            b->names.swap(names);
+            b->lengths.swap(lengths);
+            hs.n_ref = n_ref;
+            hs.q = q;
+            hs.header = true;
         }
-        q += 4 + bs;
+        while (hs.q + 4 <= avail) {
+            const size_t q = hs.q;
+            const uint32_t bs = le32(d + q);
+            if (bs < 32) return "truncated BAM record";
+            if (q + 4 + bs > avail) {  // the record ends in a block that is not inflated yet
+                if (final) return "truncated BAM record";
+                break;
+            }
+            const uint8_t *r = d + q + 4;
+            const int32_t tid = (int32_t)le32(r), pos = (int32_t)le32(r + 4);
+            if (!record_fits(r, bs)) return "corrupt BAM record";
+            if (tid >= 0 && tid < (int32_t)hs.n_ref) {
+                if (hs.seen_unplaced || tid < hs.last_tid || (tid == hs.last_tid && pos < hs.last_pos)) b->sorted = 0;
+                hs.last_tid = tid;
+                hs.last_pos = pos;
+                b->rec.push_back(d + q);
+                b->n_cigar += le16(r + 12);
+                const int64_t l_seq = (int64_t)le32(r + 16);
+                b->n_seq += (l_seq + 1) / 2;
+                b->n_qual += l_seq;
+            } else {
+                hs.seen_unplaced = true;
+                ++b->n_unplaced;
+            }
+            hs.q = q + 4 + bs;
+        }
+        return nullptr;
+    };
+    const char *err = nullptr;
+    int bad = 0;
+    constexpr size_t BATCH = 512, PER_TASK = 8;
+#pragma omp parallel
+#pragma omp single
+    {
+        size_t inflated = 0;  // length of the prefix every block of which has been inflated
+        for (size_t k0 = 0; k0 < blocks.size(); k0 += BATCH) {
+            const size_t k1 = std::min(blocks.size(), k0 + BATCH);
+            for (size_t i = k0; i < k1; i += PER_TASK) {
+#pragma omp task firstprivate(i) shared(bad, blocks, raw)
+                {
+                    Inflater inf;
+                    for (size_t j = i; j < std::min(k1, i + PER_TASK); ++j) {
+                        const Blk &k = blocks[j];
+                        if (k.isize && inf.block(raw.data() + k.src, k.n, d + k.dst, k.isize)) {
+#pragma omp atomic write
+                            bad = 1;
+                        }
+                    }
+                }
+            }
+            if (!err) err = hop(inflated, false);  // the batch before this one, while this one inflates
+#pragma omp taskwait
+            inflated = blocks[k1 - 1].dst + blocks[k1 - 1].isize;
+        }
+        int failed;
+#pragma omp atomic read
+        failed = bad;
+        if (!err && !failed) err = hop(total, true);
     }
+    if (bad) { delete b; return vfkio_fail(VFK_EINVAL, "BGZF block failed to inflate"); }
+    if (err) { delete b; return vfkio_fail(VFK_EINVAL, err); }
     *out = b;
     return VFK_OK;
 }
