@@ -336,3 +336,37 @@ def test_inflate_matches_zlib():
             except zlib.error:
                 ref = None
             assert ref is not None and ref[:len(data)] == got and len(ref) == len(data)
+
+
+def test_multi_region_fetch_equals_filter_of_the_whole_file(tmp_path):
+    """Many regions in one call (sparse windows, touching windows, a window inside a long reference skip): the
+    batch is exactly the reads of the whole file that overlap any region, each once, in file order -- for the
+    parallel per-region scan (many regions) and the sequential one (few)."""
+    from vafator_b200 import synth
+    from vafator_b200.sharding import _ref_span
+    cfg = synth.wgs(n_contigs=2, contig_len=300_000, p_skip=0.05, p_del=0.05)
+    batch = synth.reads(cfg)
+    p = tmp_path / "m.bam"
+    bamio.write_bam_batch(str(p), batch, [301_000, 301_000])
+    whole = bamio.BamFile(str(p), use_index=False).read_batch()
+    assert whole.n_reads == batch.n_reads
+    end = whole.pos.astype(np.int64) + np.maximum(_ref_span(whole), 1)
+    bam = bamio.BamFile(str(p))
+    rng = np.random.default_rng(5)
+    for n_regions in (1, 3, 40, 400):
+        regs = []
+        for _ in range(n_regions):
+            c = int(rng.integers(0, 2))
+            a = int(rng.integers(0, 299_000))
+            regs.append((bam.contigs[c], a, a + int(rng.choice([1, 50, 700, 5000]))))
+        regs.append((bam.contigs[0], 100_000, 100_500))
+        regs.append((bam.contigs[0], 100_500, 101_000))  # touches the one before
+        got = bam.read_batch(regs)
+        keep = np.zeros(whole.n_reads, bool)
+        for c, a, e in regs:
+            keep |= (whole.tid == bam.contigs.index(c)) & (whole.pos < e) & (end > a)
+        assert got.n_reads == int(keep.sum()), n_regions
+        for f in ("tid", "pos", "flag", "mapq", "qname_id", "mpos", "isize", "l_qseq", "n_cigar"):
+            assert np.array_equal(getattr(got, f), getattr(whole, f)[keep]), (n_regions, f)
+        assert np.array_equal(got.qual, np.concatenate([whole.qual[o:o + l] for o, l in zip(whole.qual_off[keep], whole.l_qseq[keep])]))
+    assert bam.read_batch([("no_such_contig", 0, 100)]).n_reads == 0
