@@ -297,3 +297,23 @@ def test_column_store_window_transposed_form():
         assert np.array_equal(run[8 * n:].view(np.uint16).reshape(12, n), entries[a:b].T)
         checked += n
     assert checked > 1000
+
+
+def test_column_store_is_skipped_for_splice_dominated_batches():
+    """RNA-like reads (most of them spanning kilobases of reference skip) would blow the column store up to many
+    times the size of the reads: pack_reads keeps such a batch read-major (with a warning), ordinary batches --
+    including skip-heavy test mixes -- get the store."""
+    import warnings
+    from vafator_b200.batch import ReadBatch
+    params = device.make_params(min_mapq=1, min_baseq=30)
+    recs = [dict(qname="r%d" % i, flag=0, tid=0, pos=100 + 7 * i, mapq=60, cigar="20M60000N30M", seq="ACGTA" * 10, qual=[35] * 50)
+            for i in range(40)]
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        pk = device.pack_reads(ReadBatch.from_records(recs, ["c1"]), params, columns=True)
+    assert not pk.has_columns and any("reference skips dominate" in str(x.message) for x in w)
+    from vafator_b200 import synth
+    noisy = synth.reads(synth.wes(n_tiles=300, p_skip=0.25, p_del=0.15))
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert device.pack_reads(noisy, params, columns=True).has_columns and not w

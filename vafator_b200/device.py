@@ -268,6 +268,14 @@ def pack_reads(batch: ReadBatch, params: ParamsC, pinned: bool = False, mate: np
                           libio().vfkio_last_error().decode())
             return packed
         _io_check(rc)
+        # Reads dominated by reference skips (RNA-seq: a spliced read leaves a sector in every window of every intron
+        # it spans) would make the store many times the size of the reads themselves; a fully aligned read leaves
+        # ~1.7 column sectors per payload sector.  Such a batch keeps its read-major layout only.
+        if cp.n_sectors > 16 * plan.n_sectors + 4 * n:
+            import warnings
+            warnings.warn("column store not built (%d sectors for %d reads: reference skips dominate): SNV units take "
+                          "the read-major kernels" % (cp.n_sectors, n))
+            return packed
         woff = _empty(cp.n_windows + 1, np.uint32, pinned)
         sectors = _empty(cp.n_sectors * 32, np.uint8, pinned)
         _io_check(libio().vfkio_columns_fill(C.byref(s), C.byref(params), C.c_void_p(mate.ctypes.data),
