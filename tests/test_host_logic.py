@@ -111,6 +111,7 @@ def test_info_strings_match_reference(path):
 class FileOracleEngine(OracleEngine):
     """Constructor of engine.Engine, device stages of OracleEngine -- stands in for Engine inside Annotator."""
     calls = []
+    prepacked = 0
 
     def __init__(self, device_index=0, min_mapq=0, min_baseq=29, include_ambiguous=True, fpr=5e-7, error_rate=1e-3,
                  devices=None, columns=True):
@@ -122,8 +123,14 @@ class FileOracleEngine(OracleEngine):
         FileOracleEngine.calls.append((records[0][0], len(records), [b.n_reads for bs in bams.values() for b in bs]))
         return OracleEngine.annotate(self, records, bams, eaf)
 
-    def release_reads(self):
+    def release_reads(self, batches=None):
         self.released += 1
+        engine.Engine.release_reads(self, batches)
+
+    def prepack(self, batch):
+        self.columns = True
+        engine.Engine.prepack(self, batch)
+        FileOracleEngine.prepacked += 1
 
 
 def _write_inputs(tmp_path, sc, indexed):
@@ -187,6 +194,7 @@ def test_annotator_streams_chromosome_groups(tmp_path, monkeypatch, name, indexe
     assert [c[0] for c in FileOracleEngine.calls] == groups
     assert sum(c[1] for c in FileOracleEngine.calls) == len(chroms)
     assert a.engine.released == (len(groups) + 1 if indexed else 1)
+    assert not a.engine.__dict__.get("_packed")  # prepacked host copies are gone with their group
     if indexed and len(groups) > 1:  # a group's batches hold that chromosome's region only
         whole = [len([r for r in sc["bams"][b] if r["tid"] >= 0]) for idx in sc["samples"].values() for b in idx]
         assert all(n <= w for c in FileOracleEngine.calls for n, w in zip(c[2], whole))

@@ -66,6 +66,7 @@ class Annotator(object):
         self.bam_readers = OrderedDict((s, [BamFile(b, "r") for b in bams]) for s, bams in input_bams.items())
         import torch
         n_dev = max(1, min(int(num_processes), torch.cuda.device_count() - device)) if torch.cuda.is_available() else 1
+        self._single_device = n_dev == 1
         self.engine = Engine(device, devices=list(range(device, device + n_dev)), min_mapq=mapping_qual_thr, min_baseq=base_call_qual_thr,
                              include_ambiguous=include_ambiguous_bases, fpr=fpr, error_rate=error_rate)
 
@@ -113,8 +114,16 @@ class Annotator(object):
         (vafator_b200/fetch.py)."""
         chrom = variants[0].CHROM
         positions = [v.POS for v in variants]
-        return OrderedDict((s, [fetch_group(r, chrom, positions[0], positions[-1], positions, self.engine.params) for r in readers])
+        bams = OrderedDict((s, [fetch_group(r, chrom, positions[0], positions[-1], positions, self.engine.params) for r in readers])
                            for s, readers in self.bam_readers.items())
+        # host-side packing too happens here, off the critical path -- for the transient batches of indexed BAMs (a
+        # whole-file batch is packed once, when first used) on a single device (sharded runs pack per shard)
+        if self._single_device:
+            for s, readers in self.bam_readers.items():
+                for r, b in zip(readers, bams[s]):
+                    if r.index_path and b.n_reads:
+                        self.engine.prepack(b)
+        return bams
 
     def _annotate_group(self, variants: list, bams: "OrderedDict") -> None:
         """One chromosome group: annotate, write, release its reads."""
@@ -135,7 +144,7 @@ class Annotator(object):
         # region batches are transient (a new object per call); the whole-file batch of an unindexed BAM is
         # cached by its reader and keeps its device copy for the next group
         if any(r.index_path for readers in self.bam_readers.values() for r in readers):
-            self.engine.release_reads()
+            self.engine.release_reads([b for batches in bams.values() for b in batches])
 
     def _write_batch(self, batch: list) -> None:
         for v in batch:

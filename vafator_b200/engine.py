@@ -308,14 +308,39 @@ class Engine:
             d.close()
 
     # ---- device stages on host arrays -------------------------------------------------------
-    def _device_reads(self, batch: ReadBatch):
-        cache = self.__dict__.setdefault("_dreads", {})
-        if id(batch) not in cache:
-            cache[id(batch)] = (batch, self.dev.upload_reads(_dev.pack_reads(batch, self.params, columns=self.columns)))
-        return cache[id(batch)][1]
+    def prepack(self, batch: ReadBatch) -> None:
+        """Pack `batch` into the HBM layout on the host now (native code, no CUDA call: safe on a helper thread
+        while the device works on another batch); `_device_reads` then only uploads it."""
+        packed = _dev.pack_reads(batch, self.params, columns=self.columns)
+        with self._cache_lock():
+            self.__dict__.setdefault("_packed", {})[id(batch)] = (batch, packed)
 
-    def release_reads(self):
-        self.__dict__.pop("_dreads", None)
+    def _cache_lock(self):
+        import threading
+        return self.__dict__.setdefault("_lock", threading.Lock())
+
+    def _device_reads(self, batch: ReadBatch):
+        with self._cache_lock():
+            cache = self.__dict__.setdefault("_dreads", {})
+            hit = cache.get(id(batch))
+            pre = self.__dict__.get("_packed", {}).pop(id(batch), None)
+        if hit is None:
+            packed = pre[1] if pre is not None else _dev.pack_reads(batch, self.params, columns=self.columns)
+            hit = (batch, self.dev.upload_reads(packed))
+            with self._cache_lock():
+                cache[id(batch)] = hit
+        return hit[1]
+
+    def release_reads(self, batches: Optional[Sequence[ReadBatch]] = None):
+        """Drop the device (and prepacked host) copies of `batches`, or of every batch."""
+        with self._cache_lock():
+            if batches is None:
+                self.__dict__.pop("_dreads", None)
+                self.__dict__.pop("_packed", None)
+            else:
+                for b in batches:
+                    self.__dict__.get("_dreads", {}).pop(id(b), None)
+                    self.__dict__.get("_packed", {}).pop(id(b), None)
 
     def _pileup_sharded(self, batch: ReadBatch, units: VariantUnits, stop: np.ndarray) -> np.ndarray:
         """Interval shards of one BAM over several devices (vafator_b200/sharding.py)."""
