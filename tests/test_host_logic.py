@@ -256,5 +256,11 @@ def test_columnwise_formatting_equals_record_by_record(seed):
         outs.append(eng.annotate(records, bams, eaf))
     for i, (a, b) in enumerate(zip(*outs)):
         assert list(a.items()) == list(b.items()), (records[i], a, b)
+    if seed == 1:  # ... and == the same columns formatted in chunks by worker processes
+        eng = RandomCountsEngine(seed)
+        eng.format_processes, eng.format_parallel_from = 2, 0
+        pooled = eng.annotate(records, bams, eaf)
+        assert [list(a.items()) for a in pooled] == [list(a.items()) for a in outs[0]]
+        assert engine._FORMAT_POOL is not None and engine._FORMAT_POOL[0] == 2  # the pool did start
     assert any("tumor_rsmq" in a for a in outs[0]) and any("tumor_rsmq" not in a for a in outs[0])
     assert any("nan" in str(a["tumor_mq"]) for a in outs[0])

@@ -121,11 +121,13 @@ class RoundedStats:
     str() is the same shortest representation numpy prints."""
 
     def __init__(self, st: np.ndarray):
-        self.pu = np.round(st["pu"], 5).tolist()
-        self.pw = np.round(st["pw"], 5).tolist()
-        self.k = st["k"].tolist()
-        self.z = np.round(st["z"], 3).tolist()
-        self.p = np.round(st["p"], 5).tolist()
+        self.pu_arr, self.pw_arr, self.k_arr = np.round(st["pu"], 5), np.round(st["pw"], 5), np.asarray(st["k"])
+        self.z_arr, self.p_arr = np.round(st["z"], 3).reshape(-1, 3), np.round(st["p"], 5).reshape(-1, 3)
+        self.pu = self.pu_arr.tolist()
+        self.pw = self.pw_arr.tolist()
+        self.k = self.k_arr.tolist()
+        self.z = self.z_arr.tolist()
+        self.p = self.p_arr.tolist()
 
 
 class SampleFormatter:
@@ -189,93 +191,148 @@ _SINGLE_KEYS = ("af", "ac", "n", "dp", "eaf", "pu", "pw", "k", "bq", "mq", "pos"
 _RS_TAGS = (("mq", "rsmq"), ("bq", "rsbq"), ("pos", "rspos"))  # emission order (vafator/annotator.py:350-376)
 
 
+def format_single_bam(first, kind_rec, alt_idx, present_row, has_rec, dp, n_amb, ac, ac_ref, med2_ref, med2_alt,
+                      pu, pw, k, z, p, eaf):
+    """INFO values of one single-BAM sample for a run of records, from plain arrays (so that a worker process can
+    do a chunk: nothing but numpy arrays crosses the process boundary).  Per record: `first[i] .. first[i+1]` are its
+    rows (one per ALT).  pu / pw / z / p are already rounded.  Returns (values, masks): values[i] = the strings of
+    _SINGLE_KEYS (dp stays an int) followed by the rank-sum pairs present, masks[i] = which of _RS_TAGS those are."""
+    first = np.asarray(first, np.int64)
+    n_rec = len(first) - 1
+    n_row = int(first[-1]) if n_rec else 0
+    rec_of = np.repeat(np.arange(n_rec, dtype=np.int64), np.diff(first)) if n_rec else np.zeros(0, np.int64)
+    first = first.tolist()
+    snv_row = kind_rec[rec_of] == KIND_SNV
+    has_row = has_rec[rec_of]
+    dp_rec = dp.tolist()
+    ac_row = ac.tolist()
+    dp_row = dp[rec_of].tolist()
+    af_row = [str(round(float(a) / d, 5)) if d > 0 else "0.0" for a, d in zip(ac_row, dp_row)]
+    acs_row = list(map(str, ac_row))
+    pu_row = list(map(str, pu.tolist()))
+    pw_row = list(map(str, pw.tolist()))
+    k_row = list(map(str, k.tolist()))
+    # ---- medians: "0" = the reference's Counter misses the allele, "nan" = key present with an empty list
+    ref_ok = has_rec & (ac_ref > 0)
+    alt_ok = (ac > 0) & has_row
+    indel_rec = has_rec & (kind_rec > KIND_SNV)
+    indel_row = indel_rec[rec_of]
+    med_ref, med_alt = {}, {}
+    for mi, name in enumerate(METRICS):
+        vals = list(map(str, (med2_ref[:, mi] / 2.0).tolist())) if n_rec else []
+        code = np.where(ref_ok, 2, 0)                                  # SNV: value or "0"
+        code = np.where(indel_rec, np.where(ac_ref > 0, 2, 1), code)     # indel: the REF key always exists
+        if name == "bq":
+            code = np.where(kind_rec != KIND_SNV, 0, code)
+        med_ref[name] = [v if c == 2 else ("nan" if c == 1 else "0") for v, c in zip(vals, code.tolist())]
+        vals = list(map(str, (med2_alt[:, mi] / 2.0).tolist())) if n_row else []
+        code = np.where(alt_ok, 2, 0)
+        # an indel ALT list is keyed ALT.upper() and looked up with the literal text (SampleFormatter.key_state)
+        code = np.where(indel_row, np.where(present_row, np.where(alt_ok & (alt_idx == 0), 2, 1), 0), code)
+        if name == "bq":
+            code = np.where(~snv_row, 0, code)
+        med_alt[name] = [v if c == 2 else ("nan" if c == 1 else "0") for v, c in zip(vals, code.tolist())]
+    # ---- rank sums: reported when both lists hold values and the statistic is a number
+    z = np.asarray(z, np.float64).reshape(n_row, 3)
+    p = np.asarray(p, np.float64).reshape(n_row, 3)
+    rs_ok, rs_z, rs_p = {}, {}, {}
+    for mi, name in enumerate(METRICS):
+        ok = alt_ok & ref_ok[rec_of] & ~np.isnan(z[:, mi]) & ~np.isnan(p[:, mi])
+        if name == "bq":
+            ok = ok & snv_row
+        rs_ok[name] = ok.tolist()
+        rs_z[name] = list(map(str, z[:, mi].tolist()))
+        rs_p[name] = list(map(str, p[:, mi].tolist()))
+    n_str = list(map(str, n_amb.tolist()))
+    eaf_str = list(map(str, np.asarray(eaf, np.float64).tolist()))
+    values = []
+    masks = []
+    for i in range(n_rec):
+        r0, r1 = first[i], first[i + 1]
+        if r1 - r0 == 1:
+            fixed = (af_row[r0], acs_row[r0], n_str[i], dp_rec[i], eaf_str[i], pu_row[r0], pw_row[r0], k_row[r0],
+                     med_ref["bq"][i] + "," + med_alt["bq"][r0], med_ref["mq"][i] + "," + med_alt["mq"][r0],
+                     med_ref["pos"][i] + "," + med_alt["pos"][r0])
+            mask = 0
+            extra = ()
+            for m, (name, _tag) in enumerate(_RS_TAGS):
+                if rs_ok[name][r0]:
+                    mask |= 1 << m
+                    extra += (rs_z[name][r0], rs_p[name][r0])
+        else:
+            rr = range(r0, r1)
+            fixed = (",".join(af_row[r0:r1]), ",".join(acs_row[r0:r1]), n_str[i], dp_rec[i], eaf_str[i],
+                     ",".join(pu_row[r0:r1]), pw_row[r0] if r1 > r0 else "0.0", k_row[r0] if r1 > r0 else "1",
+                     ",".join([med_ref["bq"][i]] + med_alt["bq"][r0:r1]), ",".join([med_ref["mq"][i]] + med_alt["mq"][r0:r1]),
+                     ",".join([med_ref["pos"][i]] + med_alt["pos"][r0:r1]))
+            mask = 0
+            extra = ()
+            for m, (name, _tag) in enumerate(_RS_TAGS):
+                zs = [rs_z[name][r] for r in rr if rs_ok[name][r]]
+                if zs:
+                    mask |= 1 << m
+                    extra += (",".join(zs), ",".join(rs_p[name][r] for r in rr if rs_ok[name][r]))
+        values.append(fixed + extra)
+        masks.append(mask)
+    return values, masks
+
+
+def _format_chunk(args):
+    return format_single_bam(*args)
+
+
+_FORMAT_POOL = None
+
+
+def _format_pool(n_procs: int):
+    """Worker processes for the formatting of very large record sets (spawned: they import this module and numpy,
+    never torch or the CUDA library)."""
+    global _FORMAT_POOL
+    if _FORMAT_POOL is None or _FORMAT_POOL[0] != n_procs:
+        import atexit
+        import multiprocessing
+        from concurrent.futures import ProcessPoolExecutor
+        if _FORMAT_POOL is not None:
+            _FORMAT_POOL[1].shutdown(wait=False)
+        pool = ProcessPoolExecutor(n_procs, mp_context=multiprocessing.get_context("spawn"))
+        atexit.register(pool.shutdown, wait=False)
+        _FORMAT_POOL = (n_procs, pool)
+    return _FORMAT_POOL[1]
+
+
 class SingleBamColumns:
     """The INFO fields of one sample backed by ONE BAM, for all records at once -- the common case, and the same
     strings `Engine._one` builds record by record (which stays the path of replicate BAMs): every value is
-    stringified column-wise, a record then only picks its tuple.  `keys[mask]` / `values[i]`: mask bit m set
-    when the rank-sum pair of _RS_TAGS[m] is present."""
+    stringified column-wise (format_single_bam), a record then only picks its tuple.  `keys[mask]` / `values[i]`:
+    mask bit m set when the rank-sum pair of _RS_TAGS[m] is present.  `processes` > 1: the records are cut into
+    chunks formatted by worker processes (worth it from some 10^5 records on)."""
 
-    def __init__(self, sample: str, rows: RowTable, res: BamResult, st: RoundedStats, eaf: np.ndarray):
+    def __init__(self, sample: str, rows: RowTable, res: BamResult, st: RoundedStats, eaf: np.ndarray, processes: int = 1):
         recs = rows.records
         n_rec, n_row = len(recs), rows.n_rows
-        first = rows.first.tolist()
-        rec_of = rows.rec
-        kind_rec = rows.kind
-        snv_row = (kind_rec[rec_of] == KIND_SNV) if n_row else np.zeros(0, bool)
-        has_rec = res.has
-        has_row = has_rec[rec_of] if n_row else np.zeros(0, bool)
-        dp_rec = res.dp.tolist()
-        ac_row = res.ac.tolist()
-        dp_row = res.dp[rec_of].tolist() if n_row else []
-        af_row = [str(round(float(a) / d, 5)) if d > 0 else "0.0" for a, d in zip(ac_row, dp_row)]
-        acs_row = list(map(str, ac_row))
-        pu_row = list(map(str, st.pu))
-        pw_row = list(map(str, st.pw))
-        k_row = list(map(str, st.k))
-        # ---- medians: "0" = the reference's Counter misses the allele, "nan" = key present with an empty list
-        ref_ok = has_rec & (res.ac_ref > 0)
-        alt_ok = (res.ac > 0) & has_row
-        indel_rec = has_rec & (kind_rec > KIND_SNV)
-        # an indel ALT list is keyed ALT.upper() and looked up with the literal text (engine.SampleFormatter.key_state)
         present_row = np.asarray([a == a.upper() for r in recs for a in r[3]], bool) if n_row else np.zeros(0, bool)
-        indel_row = indel_rec[rec_of] if n_row else np.zeros(0, bool)
-        med_ref, med_alt = {}, {}
-        for mi, name in enumerate(METRICS):
-            vals = list(map(str, (res.med2_ref[:, mi] / 2.0).tolist())) if n_rec else []
-            code = np.where(ref_ok, 2, 0)                                      # SNV: value or "0"
-            code = np.where(indel_rec, np.where(res.ac_ref > 0, 2, 1), code)     # indel: the REF key always exists
-            if name == "bq":
-                code = np.where(kind_rec != KIND_SNV, 0, code)
-            med_ref[name] = [v if c == 2 else ("nan" if c == 1 else "0") for v, c in zip(vals, code.tolist())]
-            vals = list(map(str, (res.med2_alt[:, mi] / 2.0).tolist())) if n_row else []
-            code = np.where(alt_ok, 2, 0)
-            if n_row:
-                code = np.where(indel_row, np.where(present_row, np.where(alt_ok & (rows.alt == 0), 2, 1), 0), code)
-                if name == "bq":
-                    code = np.where(~snv_row, 0, code)
-            med_alt[name] = [v if c == 2 else ("nan" if c == 1 else "0") for v, c in zip(vals, code.tolist())]
-        # ---- rank sums: reported when both lists hold values and the statistic is a number
-        z_arr = np.asarray(st.z, np.float64).reshape(n_row, 3)
-        p_arr = np.asarray(st.p, np.float64).reshape(n_row, 3)
-        rs_ok, rs_z, rs_p = {}, {}, {}
-        for mi, name in enumerate(METRICS):
-            ok = alt_ok & (ref_ok[rec_of] if n_row else alt_ok) & ~np.isnan(z_arr[:, mi]) & ~np.isnan(p_arr[:, mi])
-            if name == "bq":
-                ok = ok & snv_row
-            rs_ok[name] = ok.tolist()
-            rs_z[name] = [str(z[mi]) for z in st.z]
-            rs_p[name] = [str(q[mi]) for q in st.p]
-        n_str = list(map(str, res.n.tolist()))
-        eaf_str = list(map(str, np.asarray(eaf, np.float64).tolist()))
-        values = []
-        masks = []
-        for i in range(n_rec):
-            r0, r1 = first[i], first[i + 1]
-            if r1 - r0 == 1:
-                fixed = (af_row[r0], acs_row[r0], n_str[i], dp_rec[i], eaf_str[i], pu_row[r0], pw_row[r0], k_row[r0],
-                         med_ref["bq"][i] + "," + med_alt["bq"][r0], med_ref["mq"][i] + "," + med_alt["mq"][r0],
-                         med_ref["pos"][i] + "," + med_alt["pos"][r0])
-                mask = 0
-                extra = ()
-                for m, (name, _tag) in enumerate(_RS_TAGS):
-                    if rs_ok[name][r0]:
-                        mask |= 1 << m
-                        extra += (rs_z[name][r0], rs_p[name][r0])
-            else:
-                rr = range(r0, r1)
-                fixed = (",".join(af_row[r0:r1]), ",".join(acs_row[r0:r1]), n_str[i], dp_rec[i], eaf_str[i],
-                         ",".join(pu_row[r0:r1]), pw_row[r0] if r1 > r0 else "0.0", k_row[r0] if r1 > r0 else "1",
-                         ",".join([med_ref["bq"][i]] + med_alt["bq"][r0:r1]), ",".join([med_ref["mq"][i]] + med_alt["mq"][r0:r1]),
-                         ",".join([med_ref["pos"][i]] + med_alt["pos"][r0:r1]))
-                mask = 0
-                extra = ()
-                for m, (name, _tag) in enumerate(_RS_TAGS):
-                    zs = [rs_z[name][r] for r in rr if rs_ok[name][r]]
-                    if zs:
-                        mask |= 1 << m
-                        extra += (",".join(zs), ",".join(rs_p[name][r] for r in rr if rs_ok[name][r]))
-            values.append(fixed + extra)
-            masks.append(mask)
+        first = rows.first
+        per_rec = (rows.kind, res.has, res.dp, res.n, res.ac_ref, res.med2_ref, np.asarray(eaf, np.float64))
+        per_row = (rows.alt, present_row, res.ac, res.med2_alt, st.pu_arr, st.pw_arr, st.k_arr, st.z_arr, st.p_arr)
+
+        def args(i0, i1):
+            r0, r1 = int(first[i0]), int(first[i1])
+            kind, has, dp, n, ac_ref, med2_ref, e = (a[i0:i1] for a in per_rec)
+            alt, present, ac, med2_alt, pu, pw, k, z, p = (a[r0:r1] for a in per_row)
+            return (first[i0:i1 + 1] - r0, kind, alt, present, has, dp, n, ac, ac_ref, med2_ref, med2_alt, pu, pw, k, z, p, e)
+
+        values = masks = None
+        if processes > 1 and n_rec >= 2 * processes:
+            try:
+                cuts = [n_rec * c // (4 * processes) for c in range(4 * processes + 1)]
+                parts = list(_format_pool(processes).map(_format_chunk, [args(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]))
+                values = [v for part in parts for v in part[0]]
+                masks = [m for part in parts for m in part[1]]
+            except Exception as e:  # a pool that cannot start (no importable main module, ...) must not cost the run
+                import warnings
+                warnings.warn("parallel formatting unavailable (%s): formatting in process" % e)
+        if values is None:
+            values, masks = format_single_bam(*args(0, n_rec))
         self.values, self.masks = values, masks
         base = tuple("{}_{}".format(sample, k) for k in _SINGLE_KEYS)
         self.keys = []
@@ -290,6 +347,8 @@ class SingleBamColumns:
 class Engine:
     """Drives the device for a set of VCF records against a set of BAM read batches."""
     vectorised_format = True  # single-BAM samples are formatted column-wise (SingleBamColumns); False: record by record
+    format_processes = max(1, min(8, (__import__("os").cpu_count() or 1) // 2))  # worker processes for the formatting ...
+    format_parallel_from = 200_000                                               # ... of record sets at least this large
 
     def __init__(self, device_index: int = 0, min_mapq: int = 0, min_baseq: int = 29, include_ambiguous: bool = True,
                  fpr: float = 5e-7, error_rate: float = 1e-3, devices: Optional[Sequence[int]] = None, columns: bool = True):
@@ -468,7 +527,8 @@ class Engine:
             per_sample[sample] = (results, stats, merged_stats, cross)
         columns = {}
         if self.vectorised_format:
-            columns = {sample: SingleBamColumns(sample, rows, results[0], stats[0], eaf[sample])
+            procs = self.format_processes if len(records) >= self.format_parallel_from else 1
+            columns = {sample: SingleBamColumns(sample, rows, results[0], stats[0], eaf[sample], processes=procs)
                        for sample, (results, stats, _m, _c) in per_sample.items() if len(results) == 1}
         out = []
         if len(columns) == len(per_sample):  # every sample has a single BAM: nothing is left to do record by record
