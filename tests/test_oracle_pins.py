@@ -150,3 +150,43 @@ def test_epilogue_golden_restatement():
         pw = vr.Power(ploidy={"t": row["ploidy"]}, purity={"t": row["purity"]}, error_rate=row["error_rate"])
         got, k = pw.pw(int(row["dp"]), pw.eaf("t"))
         assert k == int(row["k"]) and abs(got - row["power"]) < 1e-12, row
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_two_formulations_agree_on_random_reads(seed):
+    """Beyond the golden scenarios: the streaming restatement (htslib_pileup.py push / next state machine under the
+    restated vafator column functions) and the direct per-pair C restatement on seeded synthetic reads with heavy
+    CIGAR noise, overlapping mates, duplicates / orphans / supplementary records -- every integer of every unit."""
+    from collections import namedtuple
+    from vafator_b200 import synth
+    rng = np.random.default_rng(seed)
+    cfg = synth.wes(n_tiles=10, seed=synth.BASE_SEED + 70 + seed, pairs_per_tile=int(rng.choice([8, 30])), snv_period=25, indel_period=60,
+                    multiallelic_pct=15, p_softclip=0.15, p_del=0.12, p_ins=0.12, p_skip=0.04, p_supp=0.05, p_orphan=0.05,
+                    p_n=0.02, frag_mean=float(rng.choice([170.0, 240.0])), frag_sd=40.0, read_len=int(rng.choice([75, 150])))
+    batch = synth.reads(cfg)
+    recs = synth.variant_records(cfg)
+    soa = batch.as_dict()
+    f = hp.AlignmentFile(hp.recs_from_soa(soa), batch.contigs)
+    V = namedtuple("V", "CHROM POS REF ALT")
+    mq, bq, amb = int(rng.choice([0, 1, 20])), int(rng.choice([0, 13, 30])), bool(rng.integers(0, 2))
+    n_checked = 0
+    for chrom in batch.contigs:
+        mine = [r for r in recs if r[0] == chrom]
+        if not mine:
+            continue
+        stream = vr.collect_metrics_for_chrom(chrom, [V(*r) for r in mine], f, bq, mq, amb)
+        units = [(batch.contigs.index(chrom), r[1], r[2], a, r[3][0], mine[-1][1]) for r in mine for a in r[3]
+                 if vr.variant_kind(r[2], r[3][0]) is not None and (vr.variant_kind(r[2], r[3][0]) == "snv" or a == r[3][0])]
+        direct = c_oracle.pileup(soa, units, c_oracle.params(min_mapq=mq, min_baseq=bq))
+        for rec, (tid, pos1, ref, alt, alt0, _stop) in zip(direct, units):
+            m = stream.get((pos1, ref, alt0))
+            as_json = None if m is None else dict(ac=dict(m.ac), dp=m.dp, all_bqs=m.dist["bq"], all_mqs=m.dist["mq"],
+                                                  all_positions=m.dist["pos"])
+            want = H.expected_record(as_json, ref, alt, alt0, amb)
+            ctx = (seed, chrom, pos1, ref, alt)
+            assert rec["dp"] == want["dp"] and rec["n_amb"] == want["n_amb"], ctx
+            assert rec["ac_ref"] == want["ac_ref"] and rec["ac_alt"] == want["ac_alt"], ctx
+            assert rec["med2"].tolist() == want["med2"] and rec["n_val"].tolist() == want["n_val"], ctx
+            assert [int(x) for x in rec["s2"]] == want["s2"], ctx
+            n_checked += 1
+    assert n_checked > 100
