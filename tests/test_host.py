@@ -317,3 +317,31 @@ def test_column_store_is_skipped_for_splice_dominated_batches():
     with warnings.catch_warnings(record=True) as w:
         warnings.simplefilter("always")
         assert device.pack_reads(noisy, params, columns=True).has_columns and not w
+
+
+def test_transposed_store_addressing_matches_the_sector_form(monkeypatch):
+    """VFK_COL_TRANSPOSED=1 (experimental): pack_reads hands out the window-transposed store; the addressing the
+    kernel's load_col_read<true> uses (header pair k of the run, entry k of row p) returns what the sector form
+    returns for sector off + k, position p."""
+    from vafator_b200 import synth
+    batch = synth.reads(synth.wgs(n_contigs=1, contig_len=40_000, p_del=0.05, p_ins=0.05))
+    params = device.make_params(min_mapq=1, min_baseq=30)
+    monkeypatch.delenv("VFK_COL_TRANSPOSED", raising=False)
+    a = device.pack_reads(batch, params, columns=True)
+    monkeypatch.setenv("VFK_COL_TRANSPOSED", "1")
+    t = device.pack_reads(batch, params, columns=True)
+    assert np.array_equal(a.col_off, t.col_off) and a.col_sectors.shape == t.col_sectors.shape
+    sa, st = np.asarray(a.col_sectors), np.asarray(t.col_sectors)
+    rng = np.random.default_rng(0)
+    n = 0
+    for w in rng.choice(len(a.col_off) - 1, 1500):
+        off, cnt = int(a.col_off[w]), int(a.col_off[w + 1] - a.col_off[w])
+        if cnt == 0:
+            continue
+        k, p = int(rng.integers(0, cnt)), int(rng.integers(0, 12))
+        sec = sa[(off + k) * 32:(off + k + 1) * 32]
+        run = st[off * 32:(off + cnt) * 32]
+        assert int(sec[:24].view(np.uint16)[p]) == int(run[8 * cnt:].view(np.uint16)[p * cnt + k])
+        assert np.array_equal(sec[24:].view(np.uint32), run[:8 * cnt].view(np.uint32).reshape(cnt, 2)[k])
+        n += 1
+    assert n > 1000

@@ -617,13 +617,26 @@ struct ColRead {  // one sector as a lane holds it
     uint32_t e;   // the 16-bit entry of the column
     uint32_t h0, h1;
 };
-__device__ __forceinline__ ColRead load_col_read(const uint32_t *__restrict__ sectors, uint32_t sector, uint32_t p) {
-    const uint32_t *w = sectors + (size_t)sector * 8u;
+// Sector k of the run [off, off + cnt) of a window, position p.  TR = false: the sector form (12 entries + 2 header
+// words per 32-byte sector).  TR = true: the window-transposed form of the same run (vfkio_columns_transpose: cnt
+// header pairs, then 12 rows of cnt entries) -- NOT YET VERIFIED ON A GPU; selected only by VFK_COL_TRANSPOSED=1
+// together with a store built under the same setting (vafator_b200/device.py).
+template <bool TR>
+__device__ __forceinline__ ColRead load_col_read(const uint32_t *__restrict__ sectors, uint32_t off, uint32_t cnt, uint32_t k, uint32_t p) {
     ColRead c;
-    c.e = (__ldg(w + (p >> 1)) >> ((p & 1u) * 16u)) & 0xFFFFu;
-    const uint2 h = __ldg(reinterpret_cast<const uint2 *>(w + 6));
-    c.h0 = h.x;
-    c.h1 = h.y;
+    if constexpr (TR) {
+        const unsigned char *run = reinterpret_cast<const unsigned char *>(sectors + (size_t)off * 8u);
+        const uint2 h = __ldg(reinterpret_cast<const uint2 *>(run) + k);
+        c.e = (uint32_t)__ldg(reinterpret_cast<const unsigned short *>(run + (size_t)cnt * 8u) + (size_t)p * cnt + k);
+        c.h0 = h.x;
+        c.h1 = h.y;
+    } else {
+        const uint32_t *w = sectors + (size_t)(off + k) * 8u;
+        c.e = (__ldg(w + (p >> 1)) >> ((p & 1u) * 16u)) & 0xFFFFu;
+        const uint2 h = __ldg(reinterpret_cast<const uint2 *>(w + 6));
+        c.h0 = h.x;
+        c.h1 = h.y;
+    }
     return c;
 }
 // htslib tweak_overlap_quality at one position (both reads show an aligned base): the quality this read keeps
@@ -665,7 +678,7 @@ __device__ __forceinline__ void col_evaluate(const ColRead &c, uint32_t partner,
     }
 }
 
-template <int POSB>
+template <int POSB, bool TR>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, VFK_COL_MIN_CTAS)
 pileup_column_kernel(ReadsDev R, const uint4 *__restrict__ cunits, const ResolvedUnit *__restrict__ res, int64_t n_units, vfk_params P,
                      vfk_counts *__restrict__ out,
@@ -696,7 +709,7 @@ pileup_column_kernel(ReadsDev R, const uint4 *__restrict__ cunits, const Resolve
         next.e = next.h0 = next.h1 = 0u;
         {
             const uint32_t off0 = __shfl_sync(FULL, cu.x, 0), cnt0 = __shfl_sync(FULL, cu.y, 0), p0 = __shfl_sync(FULL, cu.z, 0);
-            if ((uint32_t)lane < cnt0) next = load_col_read(sectors, off0 + lane, p0);
+            if ((uint32_t)lane < cnt0) next = load_col_read<TR>(sectors, off0, cnt0, (uint32_t)lane, p0);
         }
         for (int j = 0; j < n_here; ++j) {
             const int64_t u = (int64_t)base + j;
@@ -707,7 +720,7 @@ pileup_column_kernel(ReadsDev R, const uint4 *__restrict__ cunits, const Resolve
             if (j + 1 < n_here) {
                 const uint32_t off1 = __shfl_sync(FULL, cu.x, j + 1), cnt1 = __shfl_sync(FULL, cu.y, j + 1);
                 const uint32_t p1 = __shfl_sync(FULL, cu.z, j + 1);
-                if ((uint32_t)lane < cnt1) next = load_col_read(sectors, off1 + lane, p1);
+                if ((uint32_t)lane < cnt1) next = load_col_read<TR>(sectors, off1, cnt1, (uint32_t)lane, p1);
             }
             int med2[3][2] = {{-1, -1}, {-1, -1}, {-1, -1}};
             uint64_t s2[3] = {0, 0, 0};
@@ -728,7 +741,7 @@ pileup_column_kernel(ReadsDev R, const uint4 *__restrict__ cunits, const Resolve
             if ((uint32_t)lane >= cnt) c0.e = c0.h0 = c0.h1 = 0u;
             ColRead c1;
             c1.e = c1.h0 = c1.h1 = 0u;
-            if (cnt > 32u && (uint32_t)lane + 32u < cnt) c1 = load_col_read(sectors, off + 32u + lane, p);
+            if (cnt > 32u && (uint32_t)lane + 32u < cnt) c1 = load_col_read<TR>(sectors, off, cnt, 32u + (uint32_t)lane, p);
             // overlap partners: sector k + offset of the same run, i.e. an entry another lane holds
             const int off0 = (int)(int8_t)((c0.h0 >> 20) & 0xFFu), off1 = (int)(int8_t)((c1.h0 >> 20) & 0xFFu);
             const int k0p = lane + off0, k1p = 32 + lane + off1;
@@ -970,8 +983,11 @@ static cudaError_t launch_posb(const ReadsDev &R, const UnitsDev &V, const vfk_p
     e = cudaMemsetAsync(counters, 0, 24, stream);
     if (e != cudaSuccess) return e;
     if (R.col_off) {  // column store: SNV units from contiguous sector runs, the rest through the lists
+        // layout of the store the caller built: sector form unless both sides were told otherwise (see load_col_read)
+        static const bool transposed = getenv("VFK_COL_TRANSPOSED") && getenv("VFK_COL_TRANSPOSED")[0] == '1';
         int col_ctas = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&col_ctas, pileup_column_kernel<POSB>, WARPS_PER_CTA * 32, 0);
+        e = transposed ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&col_ctas, pileup_column_kernel<POSB, true>, WARPS_PER_CTA * 32, 0)
+                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&col_ctas, pileup_column_kernel<POSB, false>, WARPS_PER_CTA * 32, 0);
         if (e != cudaSuccess) return e;
         int64_t col_grid = (int64_t)sm_count * std::max(col_ctas, 1);
         if (want < col_grid) col_grid = want < 1 ? 1 : want;
@@ -980,8 +996,12 @@ static cudaError_t launch_posb(const ReadsDev &R, const UnitsDev &V, const vfk_p
             column_units_kernel<<<(unsigned)((V.n + 255) / 256), 256, 0, stream>>>(R, V, cunits);
             ++*launches;
         }
-        pileup_column_kernel<POSB><<<(unsigned)col_grid, WARPS_PER_CTA * 32, 0, stream>>>(R, cunits, located ? res : nullptr, V.n, P, out,
-                                                                                        work, block_list, n_block, warp_list, n_warp);
+        if (transposed)
+            pileup_column_kernel<POSB, true><<<(unsigned)col_grid, WARPS_PER_CTA * 32, 0, stream>>>(
+                R, cunits, located ? res : nullptr, V.n, P, out, work, block_list, n_block, warp_list, n_warp);
+        else
+            pileup_column_kernel<POSB, false><<<(unsigned)col_grid, WARPS_PER_CTA * 32, 0, stream>>>(
+                R, cunits, located ? res : nullptr, V.n, P, out, work, block_list, n_block, warp_list, n_warp);
         if (!located) {
             ++*launches;
             locate_list_kernel<<<(unsigned)((V.n + 255) / 256), 256, 0, stream>>>(R, V, res, warp_list, n_warp, block_list, n_block);

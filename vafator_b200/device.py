@@ -281,6 +281,13 @@ def pack_reads(batch: ReadBatch, params: ParamsC, pinned: bool = False, mate: np
         _io_check(libio().vfkio_columns_fill(C.byref(s), C.byref(params), C.c_void_p(mate.ctypes.data),
                                              C.c_void_p(wbase.ctypes.data), C.byref(cp), C.c_void_p(woff.ctypes.data),
                                              C.c_void_p(sectors.ctypes.data)))
+        if os.environ.get("VFK_COL_TRANSPOSED", "")[:1] == "1":
+            # EXPERIMENTAL, not yet verified on a GPU: the window-transposed form (a column reads 10 of 32 bytes per
+            # read); libvfk.so picks the matching kernel instantiation from the same variable (vfk_pileup.cu)
+            transposed = _empty(cp.n_sectors * 32, np.uint8, pinned)
+            _io_check(libio().vfkio_columns_transpose(C.c_void_p(woff.ctypes.data), C.c_int64(cp.n_windows),
+                                                      C.c_void_p(sectors.ctypes.data), C.c_void_p(transposed.ctypes.data)))
+            sectors = transposed
         packed.col_wbase, packed.col_off, packed.col_sectors = wbase, woff, sectors
     return packed
 
