@@ -426,7 +426,11 @@ __device__ __forceinline__ void unit_by_histogram(const ReadsDev &R, const vfk_p
 // ------------------------------------------------------------------------------------------
 // warp per unit
 // ------------------------------------------------------------------------------------------
-template <int POSB>
+// LISTED = false: units 0 .. n_units-1.  LISTED = true (EXPERIMENTAL, not yet verified on a GPU; VFK_LIST_SHALLOW=1):
+// the units the column kernel left on `warp_list` -- nearly all of them shallow columns it could not serve (a passing
+// read inside a deletion, an unusable sector) -- are evaluated here instead of by the histogram kernel: entry k of the
+// list is voided once its unit is done, what this kernel defers too (deep, heavy) stays for pileup_deep_kernel.
+template <int POSB, bool LISTED>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, VFK_MIN_CTAS)
 pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_units, const uint8_t *__restrict__ ins_seq,
                    vfk_params P, vfk_counts *__restrict__ out, unsigned long long *__restrict__ work_counter,
@@ -439,6 +443,7 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
     uint32_t *stage = stage_all[warp];
     const int64_t n_warps = (int64_t)gridDim.x * WARPS_PER_CTA;
     int64_t last_base = 0;
+    if constexpr (LISTED) n_units = (int64_t)*n_warp;
 
     for (;;) {
         unsigned long long base = 0;
@@ -451,10 +456,20 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
         const int n_here = (int)min((int64_t)grab, n_units - (int64_t)base);
         // lane j keeps the record of unit base+j; one coalesced read for the whole grab
         uint4 ra = make_uint4(0, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
+        uint32_t uid = LIST_VOID;  // LISTED: the unit behind list entry base + lane
         if (lane < n_here) {
-            const uint4 *q = reinterpret_cast<const uint4 *>(res + base + lane);
-            ra = __ldg(q);
-            rb = __ldg(q + 1);
+            if constexpr (LISTED) {
+                uid = warp_list[base + lane];
+                if (uid != LIST_VOID) {
+                    const uint4 *q = reinterpret_cast<const uint4 *>(res + uid);
+                    ra = q[0];  // written by locate_list_kernel (an earlier launch of this call)
+                    rb = q[1];
+                }
+            } else {
+                const uint4 *q = reinterpret_cast<const uint4 *>(res + base + lane);
+                ra = __ldg(q);
+                rb = __ldg(q + 1);
+            }
         }
         // software pipeline: the header + mate word of the NEXT unit's first 32 candidates are
         // requested before the current unit is processed
@@ -465,7 +480,8 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
             if (lo0 + lane < hi0) { hot_n = __ldg(R.hot + lo0 + lane); mw_n = __ldg(R.mate + lo0 + lane); }
         }
         for (int j = 0; j < n_here; ++j) {
-            const int64_t u = (int64_t)base + j;
+            int64_t u = (int64_t)base + j;
+            if constexpr (LISTED) u = (int64_t)__shfl_sync(FULL, uid, j);
             ResolvedUnit ru;
             ru.col = (int32_t)__shfl_sync(FULL, ra.x, j); ru.meta = __shfl_sync(FULL, ra.y, j);
             ru.len = (int32_t)__shfl_sync(FULL, ra.z, j); ru.ins_off = __shfl_sync(FULL, ra.w, j);
@@ -479,20 +495,28 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
                 const uint32_t lo1 = __shfl_sync(FULL, rb.x, j + 1), hi1 = __shfl_sync(FULL, rb.y, j + 1);
                 if (lo1 + lane < hi1) { hot_n = __ldg(R.hot + lo1 + lane); mw_n = __ldg(R.mate + lo1 + lane); }
             }
+            if constexpr (LISTED) {
+                if (u == (int64_t)LIST_VOID) continue;  // an entry locate_list_kernel moved to the block list
+            }
             const int64_t n_cand = U.hi - U.lo;
             int med2[3][2] = {{-1, -1}, {-1, -1}, {-1, -1}};
             uint64_t s2[3] = {0, 0, 0};
             if (n_cand == 0) {
-                if (lane == 0) store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind, 0u, 0u);
+                if (lane == 0) {
+                    store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind, 0u, 0u);
+                    if constexpr (LISTED) warp_list[base + j] = LIST_VOID;
+                }
                 continue;
             }
             if (n_cand > 64) {  // deep: handed to the histogram kernels through a device-side list
-                if (lane == 0) {
-                    if (n_cand > WARP_PATH_MAX_CAND) block_list[atomicAdd(n_block, 1u)] = (uint32_t)u;
-                    else warp_list[atomicAdd(n_warp, 1u)] = (uint32_t)u;
-                    store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind | VFK_ST_DEFERRED, (uint32_t)n_cand, 0u);
+                if constexpr (!LISTED) {
+                    if (lane == 0) {
+                        if (n_cand > WARP_PATH_MAX_CAND) block_list[atomicAdd(n_block, 1u)] = (uint32_t)u;
+                        else warp_list[atomicAdd(n_warp, 1u)] = (uint32_t)u;
+                        store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind | VFK_ST_DEFERRED, (uint32_t)n_cand, 0u);
+                    }
                 }
-                continue;
+                continue;  // LISTED: the entry stays on the list (its record already says deferred)
             }
             // ---- shallow: the reads that span the column are packed into the lanes (first chunk in place,
             // second chunk into the lanes the first one leaves free) and evaluated in one pass; a second
@@ -557,9 +581,11 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
             // rare: more contributions than lanes, a multiply supported insertion, or REF == ALT (a read in
             // both lists) -- re-done through the histograms
             if (heavy || __popc(m0) + __popc(m1) > 32 || (sh.R & sh.A)) {
-                if (lane == 0) {
-                    warp_list[atomicAdd(n_warp, 1u)] = (uint32_t)u;
-                    store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind | VFK_ST_DEFERRED, (uint32_t)n_cand, 0u);
+                if constexpr (!LISTED) {
+                    if (lane == 0) {
+                        warp_list[atomicAdd(n_warp, 1u)] = (uint32_t)u;
+                        store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind | VFK_ST_DEFERRED, (uint32_t)n_cand, 0u);
+                    }
                 }
                 continue;
             }
@@ -595,8 +621,10 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
                 }
             }
             if (U.kind == VFK_KIND_SNV && !P.include_ambiguous) dp -= n_amb;  // pileups.py:224-227
-            if (lane == 0) store_counts(out + u, dp, n_amb, ac_ref, ac_alt, med2, s2, U.kind, (uint32_t)n_cand, (uint32_t)n_cover,
-                                            (uint32_t)n_col);
+            if (lane == 0) {
+                store_counts(out + u, dp, n_amb, ac_ref, ac_alt, med2, s2, U.kind, (uint32_t)n_cand, (uint32_t)n_cover, (uint32_t)n_col);
+                if constexpr (LISTED) warp_list[base + j] = LIST_VOID;
+            }
         }
     }
 }
@@ -973,14 +1001,17 @@ static cudaError_t launch_posb(const ReadsDev &R, const UnitsDev &V, const vfk_p
         }
     }
     int ctas_per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pileup_warp_kernel<POSB>, WARPS_PER_CTA * 32, 0);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pileup_warp_kernel<POSB, false>, WARPS_PER_CTA * 32, 0);
     if (e != cudaSuccess) return e;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     // persistent grid: a whole number of waves, never more CTAs than there is work
     int64_t want = (V.n + (int64_t)GRAB * WARPS_PER_CTA - 1) / ((int64_t)GRAB * WARPS_PER_CTA);
     int64_t grid = (int64_t)sm_count * ctas_per_sm;
     if (want < grid) grid = want < 1 ? 1 : want;
-    e = cudaMemsetAsync(counters, 0, 24, stream);
+    // EXPERIMENTAL (VFK_LIST_SHALLOW=1): the column kernel's list goes through the shallow warp kernel first; its work
+    // counter is the u64 at byte 24 of the scratch words (the locate pass's candidate sum has been consumed by then)
+    static const bool list_shallow = getenv("VFK_LIST_SHALLOW") && getenv("VFK_LIST_SHALLOW")[0] == '1';
+    e = cudaMemsetAsync(counters, 0, list_shallow ? 32 : 24, stream);
     if (e != cudaSuccess) return e;
     if (R.col_off) {  // column store: SNV units from contiguous sector runs, the rest through the lists
         // layout of the store the caller built: sector form unless both sides were told otherwise (see load_col_read)
@@ -1006,9 +1037,14 @@ static cudaError_t launch_posb(const ReadsDev &R, const UnitsDev &V, const vfk_p
             ++*launches;
             locate_list_kernel<<<(unsigned)((V.n + 255) / 256), 256, 0, stream>>>(R, V, res, warp_list, n_warp, block_list, n_block);
         }
+        if (list_shallow) {
+            ++*launches;
+            pileup_warp_kernel<POSB, true><<<(unsigned)grid, WARPS_PER_CTA * 32, 0, stream>>>(
+                R, res, V.n, V.ins_seq, P, out, (unsigned long long *)((char *)counters + 24), block_list, n_block, warp_list, n_warp);
+        }
     } else {
-        pileup_warp_kernel<POSB><<<(unsigned)grid, WARPS_PER_CTA * 32, 0, stream>>>(R, res, V.n, V.ins_seq, P, out, work, block_list,
-                                                                                    n_block, warp_list, n_warp);
+        pileup_warp_kernel<POSB, false><<<(unsigned)grid, WARPS_PER_CTA * 32, 0, stream>>>(R, res, V.n, V.ins_seq, P, out, work,
+                                                                                           block_list, n_block, warp_list, n_warp);
     }
     ++*launches;
     e = cudaGetLastError();
