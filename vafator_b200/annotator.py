@@ -67,6 +67,9 @@ class Annotator(object):
         import torch
         n_dev = max(1, min(int(num_processes), torch.cuda.device_count() - device)) if torch.cuda.is_available() else 1
         self._single_device = n_dev == 1
+        # cumulative seconds per stage of run(): fetch (decode + pack, background thread), annotate (device stages +
+        # INFO formatting), write; wall = the whole run
+        self.timings = {"fetch": 0.0, "annotate": 0.0, "write": 0.0, "wall": 0.0, "records": 0, "reads": 0}
         self.engine = Engine(device, devices=list(range(device, device + n_dev)), min_mapq=mapping_qual_thr, min_baseq=base_call_qual_thr,
                              include_ambiguous=include_ambiguous_bases, fpr=fpr, error_rate=error_rate)
 
@@ -79,7 +82,9 @@ class Annotator(object):
         (windows around the variants inside [first.POS-1, last.POS), the span the reference fetches; fetch.py) and
         the batch is dropped, on the host and on the device, when the group is written; the next group is decoded in
         the background meanwhile.  A BAM without an index is decoded once and stays resident."""
+        import time
         from concurrent.futures import ThreadPoolExecutor
+        t_run = time.perf_counter()
         with ThreadPoolExecutor(1) as pool:  # decodes group k+1 (native code, GIL released) while group k is annotated
             pending = None
             for group in self._chromosome_groups():
@@ -95,6 +100,7 @@ class Annotator(object):
         for readers in self.bam_readers.values():
             for bam in readers:
                 bam.close()
+        self.timings["wall"] += time.perf_counter() - t_run
 
     def _chromosome_groups(self):
         group = []
@@ -112,6 +118,8 @@ class Annotator(object):
         """The read batches of one chromosome group: windows around the variants inside the span the reference
         fetches, [first.POS-1, last.POS) (vafator/pileups.py:137-138); a dense group gets the whole span
         (vafator_b200/fetch.py)."""
+        import time
+        t0 = time.perf_counter()
         chrom = variants[0].CHROM
         positions = [v.POS for v in variants]
         bams = OrderedDict((s, [fetch_group(r, chrom, positions[0], positions[-1], positions, self.engine.params) for r in readers])
@@ -123,6 +131,8 @@ class Annotator(object):
                 for r, b in zip(readers, bams[s]):
                     if r.index_path and b.n_reads:
                         self.engine.prepack(b)
+        self.timings["fetch"] += time.perf_counter() - t0
+        self.timings["reads"] += sum(b.n_reads for batches in bams.values() for b in batches)
         return bams
 
     def _annotate_group(self, variants: list, bams: "OrderedDict") -> None:
@@ -130,8 +140,11 @@ class Annotator(object):
         records = [(v.CHROM, v.POS, v.REF, v.ALT) for v in variants]
         chrom = records[0][0]
         positions = [r[1] for r in records]
+        import time
+        t0 = time.perf_counter()
         eaf = {s: self.power.expected_vafs(s, [chrom] * len(records), positions) for s in bams}
         infos = self.engine.annotate(records, bams, eaf)
+        t1 = time.perf_counter()
         batch = []
         for v, info in zip(variants, infos):
             v.INFO = info
@@ -145,6 +158,9 @@ class Annotator(object):
         # cached by its reader and keeps its device copy for the next group
         if any(r.index_path for readers in self.bam_readers.values() for r in readers):
             self.engine.release_reads([b for batches in bams.values() for b in batches])
+        self.timings["annotate"] += t1 - t0
+        self.timings["write"] += time.perf_counter() - t1
+        self.timings["records"] += len(records)
 
     def _write_batch(self, batch: list) -> None:
         for v in batch:
