@@ -370,3 +370,18 @@ def test_multi_region_fetch_equals_filter_of_the_whole_file(tmp_path):
             assert np.array_equal(getattr(got, f), getattr(whole, f)[keep]), (n_regions, f)
         assert np.array_equal(got.qual, np.concatenate([whole.qual[o:o + l] for o, l in zip(whole.qual_off[keep], whole.l_qseq[keep])]))
     assert bam.read_batch([("no_such_contig", 0, 100)]).n_reads == 0
+
+
+def test_vcf_record_info_as_text():
+    """Annotations handed over as finished text are appended, or -- when the record already carries one of the keys --
+    replace the old values in place, exactly like the {key: value} form."""
+    base = ["chr1", "100", ".", "A", "T", ".", "PASS"]
+    new = {"tumor_af": "0.5", "tumor_dp": 12, "tumor_bq": "30.0,31.5"}
+    text = ";".join("%s=%s" % kv for kv in new.items())
+    for old in (".", "", "DP=7;SOMATIC", "tumor_dp=3;DP=7", "SOMATIC;tumor_af=0.1;tumor_bq=1,2;X=tumor_dp", "Xtumor_dp=4"):
+        a, b = vcf.VcfRecord(base + [old, "GT", "0/1"]), vcf.VcfRecord(base + [old, "GT", "0/1"])
+        a.INFO, b.INFO = dict(new), text
+        assert a.line() == b.line(), old
+    r = vcf.VcfRecord(base + ["DP=7"])
+    r.INFO = text
+    assert r.line().split("\t")[7] == "DP=7;" + text

@@ -118,10 +118,10 @@ class FileOracleEngine(OracleEngine):
         OracleEngine.__init__(self, min_mapq, min_baseq, include_ambiguous, fpr, error_rate)
         self.released = 0
 
-    def annotate(self, records, bams, eaf):
+    def annotate(self, records, bams, eaf, as_text=False):
         self._records = records
         FileOracleEngine.calls.append((records[0][0], len(records), [b.n_reads for bs in bams.values() for b in bs]))
-        return OracleEngine.annotate(self, records, bams, eaf)
+        return OracleEngine.annotate(self, records, bams, eaf, as_text=as_text)
 
     def release_reads(self, batches=None):
         self.released += 1
@@ -256,11 +256,16 @@ def test_columnwise_formatting_equals_record_by_record(seed):
         outs.append(eng.annotate(records, bams, eaf))
     for i, (a, b) in enumerate(zip(*outs)):
         assert list(a.items()) == list(b.items()), (records[i], a, b)
+    text = RandomCountsEngine(seed).annotate(records, bams, eaf, as_text=True)  # ... == the finished INFO text
+    assert text == [";".join("%s=%s" % kv for kv in a.items()) for a in outs[0]]
     if seed == 1:  # ... and == the same columns formatted in chunks by worker processes
         eng = RandomCountsEngine(seed)
         eng.format_processes, eng.format_parallel_from = 2, 0
         pooled = eng.annotate(records, bams, eaf)
         assert [list(a.items()) for a in pooled] == [list(a.items()) for a in outs[0]]
+        eng = RandomCountsEngine(seed)  # (the double's random stream restarts with the engine)
+        eng.format_processes, eng.format_parallel_from = 2, 0
+        assert eng.annotate(records, bams, eaf, as_text=True) == text
         assert engine._FORMAT_POOL is not None and engine._FORMAT_POOL[0] == 2  # the pool did start
     assert any("tumor_rsmq" in a for a in outs[0]) and any("tumor_rsmq" not in a for a in outs[0])
     assert any("nan" in str(a["tumor_mq"]) for a in outs[0])

@@ -143,7 +143,7 @@ class Annotator(object):
         import time
         t0 = time.perf_counter()
         eaf = {s: self.power.expected_vafs(s, [chrom] * len(records), positions) for s in bams}
-        infos = self.engine.annotate(records, bams, eaf)
+        infos = self.engine.annotate(records, bams, eaf, as_text=True)
         t1 = time.perf_counter()
         batch = []
         for v, info in zip(variants, infos):

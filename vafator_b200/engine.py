@@ -192,11 +192,12 @@ _RS_TAGS = (("mq", "rsmq"), ("bq", "rsbq"), ("pos", "rspos"))  # emission order 
 
 
 def format_single_bam(first, kind_rec, alt_idx, present_row, has_rec, dp, n_amb, ac, ac_ref, med2_ref, med2_alt,
-                      pu, pw, k, z, p, eaf):
+                      pu, pw, k, z, p, eaf, templates=None):
     """INFO values of one single-BAM sample for a run of records, from plain arrays (so that a worker process can
     do a chunk: nothing but numpy arrays crosses the process boundary).  Per record: `first[i] .. first[i+1]` are its
     rows (one per ALT).  pu / pw / z / p are already rounded.  Returns (values, masks): values[i] = the strings of
-    _SINGLE_KEYS (dp stays an int) followed by the rank-sum pairs present, masks[i] = which of _RS_TAGS those are."""
+    _SINGLE_KEYS (dp stays an int) followed by the rank-sum pairs present, masks[i] = which of _RS_TAGS those are.
+    With `templates` (one "key=%s;key=%s..." string per mask, text_templates) values[i] is the finished INFO text."""
     first = np.asarray(first, np.int64)
     n_rec = len(first) - 1
     n_row = int(first[-1]) if n_rec else 0
@@ -272,9 +273,26 @@ def format_single_bam(first, kind_rec, alt_idx, present_row, has_rec, dp, n_amb,
                 if zs:
                     mask |= 1 << m
                     extra += (",".join(zs), ",".join(rs_p[name][r] for r in rr if rs_ok[name][r]))
-        values.append(fixed + extra)
+        values.append(fixed + extra if templates is None else templates[mask] % (fixed + extra))
         masks.append(mask)
     return values, masks
+
+
+def sample_keys(sample: str):
+    """Per mask (which rank-sum pairs are present) the INFO keys of a single-BAM sample, in emission order."""
+    base = tuple("{}_{}".format(sample, k) for k in _SINGLE_KEYS)
+    out = []
+    for mask in range(8):
+        ks = base
+        for m, (_name, tag) in enumerate(_RS_TAGS):
+            if mask >> m & 1:
+                ks += ("{}_{}".format(sample, tag), "{}_{}_pv".format(sample, tag))
+        out.append(ks)
+    return out
+
+
+def text_templates(sample: str):
+    return [";".join(k.replace("%", "%%") + "=%s" for k in ks) for ks in sample_keys(sample)]
 
 
 def _format_chunk(args):
@@ -307,7 +325,9 @@ class SingleBamColumns:
     mask bit m set when the rank-sum pair of _RS_TAGS[m] is present.  `processes` > 1: the records are cut into
     chunks formatted by worker processes (worth it from some 10^5 records on)."""
 
-    def __init__(self, sample: str, rows: RowTable, res: BamResult, st: RoundedStats, eaf: np.ndarray, processes: int = 1):
+    def __init__(self, sample: str, rows: RowTable, res: BamResult, st: RoundedStats, eaf: np.ndarray, processes: int = 1,
+                 as_text: bool = False):
+        """as_text: `values[i]` is the sample's finished INFO text ("key=value;...") instead of the value tuple."""
         recs = rows.records
         n_rec, n_row = len(recs), rows.n_rows
         present_row = np.asarray([a == a.upper() for r in recs for a in r[3]], bool) if n_row else np.zeros(0, bool)
@@ -319,7 +339,8 @@ class SingleBamColumns:
             r0, r1 = int(first[i0]), int(first[i1])
             kind, has, dp, n, ac_ref, med2_ref, e = (a[i0:i1] for a in per_rec)
             alt, present, ac, med2_alt, pu, pw, k, z, p = (a[r0:r1] for a in per_row)
-            return (first[i0:i1 + 1] - r0, kind, alt, present, has, dp, n, ac, ac_ref, med2_ref, med2_alt, pu, pw, k, z, p, e)
+            return (first[i0:i1 + 1] - r0, kind, alt, present, has, dp, n, ac, ac_ref, med2_ref, med2_alt, pu, pw, k, z, p, e,
+                    text_templates(sample) if as_text else None)
 
         values = masks = None
         if processes > 1 and n_rec >= 2 * processes:
@@ -334,14 +355,7 @@ class SingleBamColumns:
         if values is None:
             values, masks = format_single_bam(*args(0, n_rec))
         self.values, self.masks = values, masks
-        base = tuple("{}_{}".format(sample, k) for k in _SINGLE_KEYS)
-        self.keys = []
-        for mask in range(8):
-            ks = base
-            for m, (_name, tag) in enumerate(_RS_TAGS):
-                if mask >> m & 1:
-                    ks += ("{}_{}".format(sample, tag), "{}_{}_pv".format(sample, tag))
-            self.keys.append(ks)
+        self.keys = sample_keys(sample)
 
 
 class Engine:
@@ -482,8 +496,9 @@ class Engine:
 
     # ---- the annotation -----------------------------------------------------------------------
     def annotate(self, records: Sequence[Record], bams: "OrderedDict[str, List[ReadBatch]]",
-                 eaf: Dict[str, np.ndarray]) -> List["OrderedDict"]:
-        """INFO fields (ordered) for every record.  `eaf[sample][i]` = expected VAF of record i."""
+                 eaf: Dict[str, np.ndarray], as_text: bool = False) -> List["OrderedDict"]:
+        """INFO fields (ordered) for every record.  `eaf[sample][i]` = expected VAF of record i.
+        as_text: the same fields as one "key=value;key=value" string per record (what a VCF writer appends)."""
         rows = RowTable(records)
         in_range, stop_rec = chrom_groups(records)
         fmt = SampleFormatter(rows)
@@ -528,8 +543,14 @@ class Engine:
         columns = {}
         if self.vectorised_format:
             procs = self.format_processes if len(records) >= self.format_parallel_from else 1
+            all_single = all(len(results) == 1 for results, _s, _m, _c in per_sample.values())
+            if as_text and all_single:  # the text of every sample, concatenated per record
+                texts = [SingleBamColumns(sample, rows, results[0], stats[0], eaf[sample], processes=procs, as_text=True).values
+                         for sample, (results, stats, _m, _c) in per_sample.items()]
+                return list(texts[0]) if len(texts) == 1 else [";".join(t) for t in zip(*texts)]
             columns = {sample: SingleBamColumns(sample, rows, results[0], stats[0], eaf[sample], processes=procs)
                        for sample, (results, stats, _m, _c) in per_sample.items() if len(results) == 1}
+        as_wanted = (lambda infos: [";".join(["%s=%s" % kv for kv in info.items()]) for info in infos]) if as_text else (lambda infos: infos)
         out = []
         if len(columns) == len(per_sample):  # every sample has a single BAM: nothing is left to do record by record
             cols = list(columns.values())
@@ -538,7 +559,7 @@ class Engine:
                 for col in cols:
                     info.update(zip(col.keys[col.masks[i]], col.values[i]))
                 out.append(info)
-            return out
+            return as_wanted(out)
         first, kinds = rows.first.tolist(), rows.kind.tolist()
         for i, (chrom, pos, ref, alts) in enumerate(records):
             info = OrderedDict()
@@ -559,7 +580,7 @@ class Engine:
                 else:
                     info.update(self._one(sample, "", True, alts, kind, results[0], stats[0], states[0], i, r0, r1, e))
             out.append(info)
-        return out
+        return as_wanted(out)
 
     @staticmethod
     def _median_strings(kind, state_ref, state_alts):

@@ -20,12 +20,20 @@ class VcfRecord:
         self.POS = int(fields[1])
         self.REF = fields[3]
         self.ALT = [] if fields[4] == "." else fields[4].split(",")
-        self.INFO: Dict[str, object] = {}  # annotations to add, in insertion order
+        self.INFO = {}  # annotations to add: {key: value} in insertion order, or finished "key=value;..." text
 
     def line(self) -> str:
         f = self.fields
         if not self.INFO:
             return "\t".join(f)
+        if isinstance(self.INFO, str):  # finished "key=value;..." text (Engine.annotate(as_text=True))
+            if f[7] in (".", ""):
+                return "\t".join(f[:7] + [self.INFO] + f[8:])
+            # appended as it is unless the record already carries one of the keys (then: replaced in place, below);
+            # the substring test errs on the safe side only
+            if not any((kv.split("=", 1)[0] + "=") in self.INFO for kv in f[7].split(";")):
+                return "\t".join(f[:7] + [f[7] + ";" + self.INFO] + f[8:])
+            self.INFO = dict(kv.split("=", 1) if "=" in kv else (kv, "") for kv in self.INFO.split(";"))
         if f[7] in (".", ""):
             info = ";".join(["%s=%s" % kv for kv in self.INFO.items()])
         else:
