@@ -385,3 +385,22 @@ def test_vcf_record_info_as_text():
     r = vcf.VcfRecord(base + ["DP=7"])
     r.INFO = text
     assert r.line().split("\t")[7] == "DP=7;" + text
+
+
+def test_bgzf_vcf_writer_across_blocks(tmp_path):
+    """A .vcf.gz larger than several BGZF blocks reads back (gzip: concatenated members) line for line."""
+    src = tmp_path / "in.vcf"
+    lines = ["chr1\t%d\t.\tA\tT\t.\tPASS\tDP=%d;NOTE=%s" % (100 + i, i % 97, "x" * (i % 50)) for i in range(6000)]
+    src.write_text("##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n" + "\n".join(lines) + "\n")
+    rd = vcf.VcfReader(str(src))
+    out = tmp_path / "o.vcf.gz"
+    wr = vcf.VcfWriter(str(out), rd)
+    for rec in rd:
+        rec.INFO = "tumor_dp=%d" % rec.POS
+        wr.write_record(rec)
+    wr.close()
+    rd.close()
+    raw = out.read_bytes()
+    assert raw.count(b"\x1f\x8b\x08\x04") >= 4 and raw.endswith(bamio._BGZF_EOF)
+    got = [l for l in gzip.open(out, "rt").read().split("\n") if l and not l.startswith("#")]
+    assert got == ["%s;tumor_dp=%d" % (l, 100 + i) for i, l in enumerate(lines)]

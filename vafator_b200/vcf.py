@@ -5,7 +5,6 @@ htslib's bcf_update_info does for string / integer values."""
 from __future__ import annotations
 
 import gzip
-import io
 from typing import Dict, Iterator, List, Optional
 
 
@@ -92,13 +91,9 @@ class VcfReader:
 class VcfWriter:
     def __init__(self, path: str, template: VcfReader):
         self.path = path
-        if path.endswith(".gz"):
-            self._raw = open(path, "wb")
-            self._buf = io.StringIO()
-            self._bgzf = True
-        else:
-            self._raw = open(path, "w")
-            self._bgzf = False
+        self._bgzf = path.endswith(".gz")
+        self._raw = open(path, "wb" if self._bgzf else "w")
+        self._pending = bytearray()  # BGZF: bytes not yet written as a block
         self._emit("\n".join(template.header_lines + template.extra_header + [template.column_line]) + "\n")
 
     def _emit(self, text: str) -> None:
@@ -106,13 +101,10 @@ class VcfWriter:
             self._raw.write(text)
             return
         from .bamio import _bgzf_block
-        self._buf.write(text)
-        data = self._buf.getvalue().encode()
-        while len(data) >= 0xFF00:
-            self._raw.write(_bgzf_block(data[:0xFF00]))
-            data = data[0xFF00:]
-        self._buf = io.StringIO()
-        self._buf.write(data.decode())
+        self._pending += text.encode()
+        while len(self._pending) >= 0xFF00:
+            self._raw.write(_bgzf_block(bytes(self._pending[:0xFF00])))
+            del self._pending[:0xFF00]
 
     def write_record(self, rec: VcfRecord) -> None:
         self._emit(rec.line() + "\n")
@@ -120,8 +112,8 @@ class VcfWriter:
     def close(self) -> None:
         if self._bgzf:
             from .bamio import _bgzf_block, _BGZF_EOF
-            data = self._buf.getvalue().encode()
-            if data:
-                self._raw.write(_bgzf_block(data))
+            if self._pending:
+                self._raw.write(_bgzf_block(bytes(self._pending)))
+                self._pending.clear()
             self._raw.write(_BGZF_EOF)
         self._raw.close()
