@@ -147,3 +147,19 @@ def test_collect_metrics_for_chrom_call_site(tmp_path):
         for allele in m.mqs:
             want = g["mqs"].get(allele)
             assert (math.isnan(m.mqs[allele]) and want is None) or m.mqs[allele] == want
+
+
+@pytest.mark.skipif(not os.environ.get("VFK_TEST_STAGED"), reason="staged for the next round: not yet run on a GPU "
+                    "(set VFK_TEST_STAGED=1)")
+def test_nist_variant_set_on_the_device_equals_the_oracle_double(tmp_path_factory, monkeypatch):
+    """BASELINE config 1 on the device: the files of tests/test_integration_nist.py through the `vafator` command
+    line with the real engine == the same run with the device stages doubled by the oracle, line for line."""
+    import test_host_logic as T
+    import test_integration_nist as N
+    from vafator_b200 import annotator as ann
+    records, reads, bam, vcf, d = N.make_nist_files(tmp_path_factory)
+    cli(["--input-vcf", vcf, "--output-vcf", str(d / "gpu.vcf"), "--bam", "my_normal", bam, "--bam", "my_tumor", bam])
+    monkeypatch.setattr(ann, "Engine", T.FileOracleEngine)
+    cli(["--input-vcf", vcf, "--output-vcf", str(d / "oracle.vcf"), "--bam", "my_normal", bam, "--bam", "my_tumor", bam])
+    strip = lambda p: [l for l in open(p) if not l.startswith("##vafator_command_line")]
+    assert strip(d / "gpu.vcf") == strip(d / "oracle.vcf")

@@ -104,8 +104,7 @@ def simulate(records, seed=20261020, pairs_per_variant=45):
     return out
 
 
-@pytest.fixture(scope="module")
-def nist_files(tmp_path_factory):
+def make_nist_files(tmp_path_factory):
     d = tmp_path_factory.mktemp("nist")
     records = nist_records()
     reads = simulate(records)
@@ -117,6 +116,11 @@ def nist_files(tmp_path_factory):
         for c, p, r, a in records:
             fh.write("%s\t%d\t.\t%s\t%s\t50\tPASS\tAC=2;AF=0.5;DP=11\n" % (c, p, r, ",".join(a)))
     return records, reads, str(bam), str(vcf), d
+
+
+@pytest.fixture(scope="module")
+def nist_files(tmp_path_factory):
+    return make_nist_files(tmp_path_factory)
 
 
 def test_variant_set_is_the_references():
