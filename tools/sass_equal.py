@@ -2,8 +2,8 @@
 
     python tools/sass_equal.py old/libvfk.so vafator_b200/libvfk.so [--ignore REGEX]
 
-Compares `cuobjdump -sass` kernel by kernel (addresses and encodings stripped; a trailing `ELb0E` template argument
-of the pileup kernels is dropped from the names, so that a build that only ADDS opt-in instantiations -- `ELb1E` --
+Compares `cuobjdump -sass` kernel by kernel (addresses and encodings stripped; trailing `Lb0` (false) template arguments
+of the pileup kernels are dropped from the names, so that a build that only ADDS opt-in instantiations -- some `Lb1` --
 compares equal to the build before it).  Used to show that the staged, not-yet-verified kernel variants leave the
 GPU-verified default path untouched."""
 import re
@@ -17,7 +17,7 @@ def kernels(path):
     for line in out.splitlines():
         m = re.search(r"Function : (\S+)", line)
         if m:
-            name = re.sub(r"(pileup_(?:warp|column)_kernelILi\d+)ELb0E", r"\1E", m.group(1))
+            name = re.sub(r"(pileup_(?:warp|column)_kernelILi\d+)(?:ELb0)+E", r"\1E", m.group(1))
             body[name] = []
         elif name and re.match(r"\s+/\*[0-9a-f]{4}\*/", line):
             body[name].append(re.sub(r"/\*[0-9a-f]{4}\*/|/\* 0x[0-9a-f]+ \*/", "", line).strip())
@@ -26,7 +26,7 @@ def kernels(path):
 
 def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
-    ignore = re.compile(sys.argv[sys.argv.index("--ignore") + 1]) if "--ignore" in sys.argv else re.compile(r"ELb1E")
+    ignore = re.compile(sys.argv[sys.argv.index("--ignore") + 1]) if "--ignore" in sys.argv else re.compile(r"Lb1")
     if "--ignore" in sys.argv:
         args.remove(sys.argv[sys.argv.index("--ignore") + 1])
     a, b = kernels(args[0]), kernels(args[1])

@@ -298,6 +298,26 @@ __device__ __forceinline__ void radix_compare(uint32_t v, uint32_t contributing,
     radix_steps<NBITS>(v, lt, eq);
 }
 
+// The same lt / eq masks by selection: one round per DISTINCT value (smallest first) -- a warp minimum, a ballot of its
+// holders.  Cheaper than the radix walk when a column holds few distinct values, which is the rule for mapping
+// qualities (EXPERIMENTAL, not yet verified on a GPU: VFK_MQ_SELECT=1 uses it for the MQ metric of the column kernel).
+__device__ __forceinline__ void select_compare(uint32_t v, uint32_t contributing, uint32_t lane_bit, uint32_t &lt, uint32_t &eq) {
+    lt = 0u;
+    eq = contributing;
+    uint32_t rem = contributing, done = 0u;
+    while (rem) {  // uniform across the warp
+        const bool waiting = (rem & lane_bit) != 0u;
+        const uint32_t m = __reduce_min_sync(FULL, waiting ? v : 0xFFFFFFFFu);
+        const uint32_t g = __ballot_sync(FULL, waiting && v == m);
+        if (g & lane_bit) {
+            lt = done;
+            eq = g;
+        }
+        done |= g;
+        rem &= ~g;
+    }
+}
+
 // Medians of the REF / ALT lists and this lane's share of the ALT mid-rank sum, from the lt / eq masks.
 //
 // Median: ties are broken by lane id, so every member of a list owns exactly one 0-based position of
@@ -706,7 +726,7 @@ __device__ __forceinline__ void col_evaluate(const ColRead &c, uint32_t partner,
     }
 }
 
-template <int POSB, bool TR>
+template <int POSB, bool TR, bool MQS>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, VFK_COL_MIN_CTAS)
 pileup_column_kernel(ReadsDev R, const uint4 *__restrict__ cunits, const ResolvedUnit *__restrict__ res, int64_t n_units, vfk_params P,
                      vfk_counts *__restrict__ out,
@@ -822,7 +842,8 @@ pileup_column_kernel(ReadsDev R, const uint4 *__restrict__ cunits, const Resolve
                 sh.r1 = (ac_ref - 1) >> 1; sh.a1 = (ac_alt - 1) >> 1;
                 sh.dr = (uint32_t)(ac_ref >> 1) - (uint32_t)sh.r1; sh.da = (uint32_t)(ac_alt >> 1) - (uint32_t)sh.a1;
                 sh.sh_r = 1u - sh.dr; sh.sh_a = 17u - sh.da;
-                radix_compare<8>(mq, sh.R | sh.A, lt, eq);
+                if constexpr (MQS) select_compare(mq, sh.R | sh.A, 1u << lane, lt, eq);
+                else radix_compare<8>(mq, sh.R | sh.A, lt, eq);
                 uint32_t term = radix_finish(mq, lt, eq, sh, w);
                 med2[0][0] = ac_ref ? (int)(w & 0xFFFFu) : -1; med2[0][1] = ac_alt ? (int)(w >> 16) : -1;
                 radix_compare<8>(bq, sh.R | sh.A, lt, eq);
@@ -1017,8 +1038,12 @@ static cudaError_t launch_posb(const ReadsDev &R, const UnitsDev &V, const vfk_p
         // layout of the store the caller built: sector form unless both sides were told otherwise (see load_col_read)
         static const bool transposed = getenv("VFK_COL_TRANSPOSED") && getenv("VFK_COL_TRANSPOSED")[0] == '1';
         int col_ctas = 0;
-        e = transposed ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&col_ctas, pileup_column_kernel<POSB, true>, WARPS_PER_CTA * 32, 0)
-                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&col_ctas, pileup_column_kernel<POSB, false>, WARPS_PER_CTA * 32, 0);
+        static const bool mq_select = getenv("VFK_MQ_SELECT") && getenv("VFK_MQ_SELECT")[0] == '1';
+        auto column_kernel = pileup_column_kernel<POSB, false, false>;
+        if (transposed && mq_select) column_kernel = pileup_column_kernel<POSB, true, true>;
+        else if (transposed) column_kernel = pileup_column_kernel<POSB, true, false>;
+        else if (mq_select) column_kernel = pileup_column_kernel<POSB, false, true>;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&col_ctas, column_kernel, WARPS_PER_CTA * 32, 0);
         if (e != cudaSuccess) return e;
         int64_t col_grid = (int64_t)sm_count * std::max(col_ctas, 1);
         if (want < col_grid) col_grid = want < 1 ? 1 : want;
@@ -1027,12 +1052,8 @@ static cudaError_t launch_posb(const ReadsDev &R, const UnitsDev &V, const vfk_p
             column_units_kernel<<<(unsigned)((V.n + 255) / 256), 256, 0, stream>>>(R, V, cunits);
             ++*launches;
         }
-        if (transposed)
-            pileup_column_kernel<POSB, true><<<(unsigned)col_grid, WARPS_PER_CTA * 32, 0, stream>>>(
-                R, cunits, located ? res : nullptr, V.n, P, out, work, block_list, n_block, warp_list, n_warp);
-        else
-            pileup_column_kernel<POSB, false><<<(unsigned)col_grid, WARPS_PER_CTA * 32, 0, stream>>>(
-                R, cunits, located ? res : nullptr, V.n, P, out, work, block_list, n_block, warp_list, n_warp);
+        column_kernel<<<(unsigned)col_grid, WARPS_PER_CTA * 32, 0, stream>>>(R, cunits, located ? res : nullptr, V.n, P, out, work, block_list,
+                                                                             n_block, warp_list, n_warp);
         if (!located) {
             ++*launches;
             locate_list_kernel<<<(unsigned)((V.n + 255) / 256), 256, 0, stream>>>(R, V, res, warp_list, n_warp, block_list, n_block);
