@@ -395,7 +395,9 @@ def main():
         if col > 0.5:
             # column store: one contiguous run of 32-byte sectors per unit (n_cand = sectors of the column's window);
             # the few units left to the read-major kernels (~2 %) gather ~84 B per candidate read as before
-            h2d += len(samples) * nu * n_cand * (32.0 + 0.02 * 84.0)
+            # (staged VFK_COL_TRANSPOSED=1 layout: one 8-byte header pair and one 2-byte entry per sector of the run)
+            per_sector = 10.0 if os.environ.get("VFK_COL_TRANSPOSED", "")[:1] == "1" else 32.0
+            h2d += len(samples) * nu * n_cand * (per_sector + 0.02 * 84.0)
         else:
             h2d += len(samples) * nu * n_cand * (64.0 * zc + 20.0 * zc_hot)
         transfer = ("column store: SNV units read one contiguous sector run each from pinned host memory; " if col > 0.5 else "") + (
