@@ -118,6 +118,8 @@ class BamFile:
                 self._lib.vfkio_bam_close(self._h)
                 self._h = h
             self._batch = self._fill(self._h)
+            self._lib.vfkio_bam_close(self._h)  # the inflated stream has been copied into the batch: let it go
+            self._h = None
         return self._batch
 
     def close(self):
