@@ -345,3 +345,32 @@ def test_transposed_store_addressing_matches_the_sector_form(monkeypatch):
         assert np.array_equal(sec[24:].view(np.uint32), run[:8 * cnt].view(np.uint32).reshape(cnt, 2)[k])
         n += 1
     assert n > 1000
+
+
+def test_select_compare_emulation_matches_the_definition():
+    """The staged MQ ranking (vfk_pileup.cu select_compare: one round per distinct value -- warp minimum, ballot of
+    its holders) restated lane by lane: for every contributing lane, lt = the contributing lanes holding a smaller
+    value and eq = those holding an equal one -- what radix_compare delivers and radix_finish consumes."""
+    rng = np.random.default_rng(9)
+    for _ in range(300):
+        contributing = int(rng.integers(0, 1 << 32)) & int(rng.integers(0, 1 << 32)) if rng.random() < 0.7 else int(rng.integers(0, 1 << 32))
+        v = rng.choice([0, 1, 20, 29, 60, 60, 60, 255], 32).astype(np.uint32)
+        lanes = [k for k in range(32) if contributing >> k & 1]
+        lt = [0] * 32
+        eq = [contributing] * 32
+        rem, done = contributing, 0
+        rounds = 0
+        while rem:
+            waiting = [(rem >> k) & 1 for k in range(32)]
+            m = min(int(v[k]) if waiting[k] else 0xFFFFFFFF for k in range(32))       # __reduce_min_sync
+            g = sum(1 << k for k in range(32) if waiting[k] and int(v[k]) == m)        # __ballot_sync
+            for k in range(32):
+                if g >> k & 1:
+                    lt[k], eq[k] = done, g
+            done |= g
+            rem &= ~g
+            rounds += 1
+        assert rounds == len({int(v[k]) for k in lanes})
+        for k in lanes:
+            assert lt[k] == sum(1 << j for j in lanes if v[j] < v[k])
+            assert eq[k] == sum(1 << j for j in lanes if v[j] == v[k])
