@@ -998,6 +998,12 @@ cudaError_t launch_locate(const ReadsDev &R, const UnitsDev &V, void *resolved, 
     return cudaGetLastError();
 }
 
+// the staged variants are chosen per call (tools/ab_staged.py switches them inside one process)
+static bool env_flag(const char *name) {
+    const char *v = getenv(name);
+    return v && v[0] == '1';
+}
+
 // scratch words (32 bytes, device): @0 u64 unit work counter, @8 u32 block-list length, @12 u32 warp-list
 // length, @16 u32 deep-kernel work counter, @24 u64 candidate sum (locate pass).  lists: 2 * n_units u32.
 template <int POSB>
@@ -1031,14 +1037,14 @@ static cudaError_t launch_posb(const ReadsDev &R, const UnitsDev &V, const vfk_p
     if (want < grid) grid = want < 1 ? 1 : want;
     // EXPERIMENTAL (VFK_LIST_SHALLOW=1): the column kernel's list goes through the shallow warp kernel first; its work
     // counter is the u64 at byte 24 of the scratch words (the locate pass's candidate sum has been consumed by then)
-    static const bool list_shallow = getenv("VFK_LIST_SHALLOW") && getenv("VFK_LIST_SHALLOW")[0] == '1';
+    const bool list_shallow = env_flag("VFK_LIST_SHALLOW");
     e = cudaMemsetAsync(counters, 0, list_shallow ? 32 : 24, stream);
     if (e != cudaSuccess) return e;
     if (R.col_off) {  // column store: SNV units from contiguous sector runs, the rest through the lists
         // layout of the store the caller built: sector form unless both sides were told otherwise (see load_col_read)
-        static const bool transposed = getenv("VFK_COL_TRANSPOSED") && getenv("VFK_COL_TRANSPOSED")[0] == '1';
+        const bool transposed = env_flag("VFK_COL_TRANSPOSED");
         int col_ctas = 0;
-        static const bool mq_select = getenv("VFK_MQ_SELECT") && getenv("VFK_MQ_SELECT")[0] == '1';
+        const bool mq_select = env_flag("VFK_MQ_SELECT");
         auto column_kernel = pileup_column_kernel<POSB, false, false>;
         if (transposed && mq_select) column_kernel = pileup_column_kernel<POSB, true, true>;
         else if (transposed) column_kernel = pileup_column_kernel<POSB, true, false>;
