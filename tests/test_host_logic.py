@@ -269,3 +269,39 @@ def test_columnwise_formatting_equals_record_by_record(seed):
         assert engine._FORMAT_POOL is not None and engine._FORMAT_POOL[0] == 2  # the pool did start
     assert any("tumor_rsmq" in a for a in outs[0]) and any("tumor_rsmq" not in a for a in outs[0])
     assert any("nan" in str(a["tumor_mq"]) for a in outs[0])
+
+
+@pytest.mark.parametrize("indexed", [False, True], ids=["whole_file", "bai_windows"])
+def test_collect_metrics_for_chrom_call_site_on_cpu(tmp_path, monkeypatch, indexed):
+    """The reference's first call site (vafator/pileups.py:106) with the device stages doubled by the oracle: same
+    keys and values as the unmodified reference produced (tests/golden), also when an indexed BAM is fetched as
+    windows around the variants."""
+    import math
+    from vafator_b200 import bamio, pileups
+    from vafator_b200.pileup_utils import VariantRecord
+    sc = H.load_scenario(os.path.join(H.GOLDEN, "pileup_testx_real.json"))
+    run = sc["runs"][0]
+    prm = run["params"]
+    p = tmp_path / "a.bam"
+    bamio.write_bam(str(p), sc["bams"][0], sc["contigs"], index=indexed)
+    bam = bamio.BamFile(str(p))
+    gold = run["metrics"][0]
+    n_keys = 0
+    for chrom in sc["contigs"]:
+        mine = [v for v in sc["variants"] if v["chrom"] == chrom]
+        if not mine:
+            continue
+        variants = [VariantRecord(v["chrom"], v["pos"], v["ref"], v["alts"]) for v in mine]
+        eng = OracleEngine(prm["min_mq"], prm["min_bq"], True, 5e-7, 1e-3)
+        eng._records = [(chrom, v.POS, v.REF, list(v.ALT)) for v in variants]
+        monkeypatch.setattr(pileups, "_engine", lambda *a, **k: eng)
+        res = pileups.collect_metrics_for_chrom(chrom, variants, bam, prm["min_bq"], prm["min_mq"], True)
+        assert {"%s:%d:%s:%s" % ((chrom,) + k) for k in res} == {k for k in gold if k.startswith(chrom + ":")}
+        for (pos, ref, alt0), m in res.items():
+            g = gold["%s:%d:%s:%s" % (chrom, pos, ref, alt0)]
+            assert m.dp == g["dp"]
+            for allele in m.mqs:
+                want = g["mqs"].get(allele)
+                assert (math.isnan(m.mqs[allele]) and want is None) or m.mqs[allele] == want
+            n_keys += 1
+    assert n_keys > 150

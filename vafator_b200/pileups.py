@@ -46,7 +46,9 @@ def collect_metrics_for_chrom(chrom: str, variants: List, bam, min_base_quality:
     eng = _engine(min_base_quality, min_mapping_quality, include_ambiguous_bases)
     first, last = variants[0].POS, variants[-1].POS
     from .bamio import BamFile
-    batch = bam.read_batch([(chrom, first - 1, last)]) if isinstance(bam, BamFile) else bam.read_batch()
+    from .fetch import fetch_group
+    # the reads the columns depend on, out of the span the reference fetches (windows around the variants: fetch.py)
+    batch = fetch_group(bam, chrom, first, last, [v.POS for v in variants], eng.params) if isinstance(bam, BamFile) else bam.read_batch()
     records = [(chrom, v.POS, v.REF, list(v.ALT)) if first <= v.POS <= last else (chrom, v.POS, "", []) for v in variants]
     units = build_units(records, batch.contigs)
     counts = eng.pileup(batch, units, np.full(units.n_units, last, np.int32))
