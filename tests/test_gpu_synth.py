@@ -327,3 +327,23 @@ def test_listed_units_without_candidate_reads(dev):
             assert np.array_equal(got[True][f][both], got[False][f][both])
         elif f != "n_cand":
             assert np.array_equal(got[True][f], got[False][f]), f
+
+
+STAGED_FLAGS = ("VFK_COL_TRANSPOSED", "VFK_LIST_SHALLOW", "VFK_MQ_SELECT")
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("VFK_TEST_STAGED"), reason="staged kernel variants: not yet run on a GPU "
+                    "(set VFK_TEST_STAGED=1; DESIGN.md section 6)")
+@pytest.mark.parametrize("name", ["wes", "wgs_indels", "amplicon_1000x", "noisy_cigars"])
+@pytest.mark.parametrize("combo", [c for r in (1, 2, 3) for c in __import__("itertools").combinations(STAGED_FLAGS, r)],
+                         ids=lambda c: "+".join(x[4:] for x in c))
+def test_staged_variants_match_the_oracle(dev, monkeypatch, name, combo):
+    """Every combination of the staged switches (read per call by libvfk.so and by pack_reads) on the column-store
+    path: every field of every unit equals the C oracle."""
+    make, thresholds = CASES[name]
+    batch, recs, units, stop, ounits = _setup(make())
+    for f in STAGED_FLAGS:
+        monkeypatch.setenv(f, "1" if f in combo else "0")
+    for mq, bq in thresholds[:2]:
+        got = _gpu(dev, batch, units, stop, mq, bq, columns=True)
+        _compare(got, c_oracle.pileup(batch.as_dict(), ounits, c_oracle.params(min_mapq=mq, min_baseq=bq)))
