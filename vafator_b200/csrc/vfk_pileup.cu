@@ -16,6 +16,11 @@
 // pileup_deep_kernel  : one warp per listed unit, histograms in shared memory (u16 counters, two per
 //                       word) + warp scans;
 // pileup_block_kernel : one CTA per listed unit, u32 counters, for columns with > 32767 candidates.
+// pileup_column_kernel: (batches with a column store, the default) one warp per SNV unit, lane = sector of the column's
+//                       window run; what it cannot serve goes to the kernels above through the same lists.
+// Staged, opt-in, not yet run on a GPU (the default instantiations are untouched -- tools/sass_equal.py):
+// pileup_column_kernel<.., TR = true> (VFK_COL_TRANSPOSED), <.., MQS = true> (VFK_MQ_SELECT), pileup_warp_kernel<.., LISTED = true>
+// (VFK_LIST_SHALLOW).
 #include <algorithm>
 #include <cstdlib>
 #include "vfk_device.cuh"
