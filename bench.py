@@ -397,6 +397,8 @@ def main():
             # the few units left to the read-major kernels (~2 %) gather ~84 B per candidate read as before
             # (staged VFK_COL_TRANSPOSED=1 layout: one 8-byte header pair and one 2-byte entry per sector of the run)
             per_sector = 10.0 if os.environ.get("VFK_COL_TRANSPOSED", "")[:1] == "1" else 32.0
+            if os.environ.get("VFK_HOST_GATHER", "")[:1] == "1":
+                per_sector = 0.0  # staged: the runs are gathered on the host and bulk-copied (counted by the library)
             h2d += len(samples) * nu * n_cand * (per_sector + 0.02 * 84.0)
         else:
             h2d += len(samples) * nu * n_cand * (64.0 * zc + 20.0 * zc_hot)

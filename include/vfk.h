@@ -245,6 +245,13 @@ int vfk_ranksum_values(vfk_handle *h, int64_t n_pairs, const uint32_t *alt, cons
 /* Number of kernel launches issued through this handle since it was created. */
 int64_t vfk_launch_count(vfk_handle *h);
 
+/* Host-side helper of vfk_annotate_host (VFK_HOST_GATHER=1, staged): column units {first sector of the window's run,
+ * sectors, position, meta} [n][4] + the column store (sector form, or window-transposed when `transposed`) -> per unit a
+ * compact run (header pairs, then the entries of the unit's own position; 10 bytes per read, padded to 32) in `out`, and
+ * units pointing at those runs.  out == NULL: only *out_bytes is computed.  No CUDA call. */
+int vfk_host_gather_columns(const uint32_t *units_in, int64_t n_units, const uint8_t *sectors, int transposed,
+                            uint32_t *units_out, uint8_t *out, int64_t out_cap, int64_t *out_bytes);
+
 #ifdef __cplusplus
 }
 #endif

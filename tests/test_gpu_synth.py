@@ -347,3 +347,28 @@ def test_staged_variants_match_the_oracle(dev, monkeypatch, name, combo):
     for mq, bq in thresholds[:2]:
         got = _gpu(dev, batch, units, stop, mq, bq, columns=True)
         _compare(got, c_oracle.pileup(batch.as_dict(), ounits, c_oracle.params(min_mapq=mq, min_baseq=bq)))
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("VFK_TEST_STAGED"), reason="staged host gather: not yet run on a GPU "
+                    "(set VFK_TEST_STAGED=1; DESIGN.md section 6)")
+@pytest.mark.parametrize("transposed", ["0", "1"], ids=["sector_form", "transposed_form"])
+def test_staged_host_gather_matches_the_resident_call(dev, monkeypatch, transposed):
+    """VFK_HOST_GATHER=1: the host entry point gathers every unit's column run (10 bytes per read) into one bulk copy;
+    results equal the device-resident call on the same batch, field for field (the diagnostic n_cand aside)."""
+    for k in ("VFK_HOST_LOCATE", "VFK_ZERO_COPY_PAYLOAD", "VFK_ZERO_COPY_HOT", "VFK_HOST_COLUMNS", "VFK_LIST_SHALLOW", "VFK_MQ_SELECT"):
+        monkeypatch.delenv(k, raising=False)
+    monkeypatch.setenv("VFK_COL_TRANSPOSED", transposed)
+    cfg = synth.wes(n_tiles=3000, indel_period=700, multiallelic_pct=5)
+    batch, recs, units, stop, ounits = _setup(cfg)
+    params = device.make_params(min_mapq=1, min_baseq=30)
+    packed = device.pack_reads(batch, params, pinned=True, columns=True)
+    eaf = np.full(units.n_units, 0.4)
+    monkeypatch.setenv("VFK_HOST_GATHER", "0")
+    want_c, want_s = dev.annotate_host(packed, units, stop, params, eaf, 5e-7, 1e-3)
+    monkeypatch.setenv("VFK_HOST_GATHER", "1")
+    got_c, got_s = dev.annotate_host(packed, units, stop, params, eaf, 5e-7, 1e-3)
+    for f in got_c.dtype.names:
+        if f != "n_cand":
+            assert np.array_equal(got_c[f], want_c[f]), f
+    assert got_s.tobytes() == want_s.tobytes()
+    _compare(got_c, c_oracle.pileup(batch.as_dict(), ounits, c_oracle.params(min_mapq=1, min_baseq=30)))

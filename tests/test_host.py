@@ -374,3 +374,61 @@ def test_select_compare_emulation_matches_the_definition():
         for k in lanes:
             assert lt[k] == sum(1 << j for j in lanes if v[j] < v[k])
             assert eq[k] == sum(1 << j for j in lanes if v[j] == v[k])
+
+
+@pytest.mark.parametrize("transposed", [0, 1], ids=["sector_form", "transposed_form"])
+def test_host_gather_of_column_runs(monkeypatch, transposed):
+    """vfk_host_gather_columns (host half of the staged VFK_HOST_GATHER path, no CUDA call): for every unit the compact
+    run holds exactly what load_col_read<.., CP> will address -- header pair k at 8 k, entry k of the unit's own
+    position behind the header pairs -- and equals the sector form's sector off + k; units the column kernel does not
+    serve are left without a run."""
+    import ctypes as C
+    from vafator_b200 import synth
+    from vafator_b200.batch import build_units
+    cfg = synth.wes(n_tiles=400, indel_period=300, multiallelic_pct=10)
+    batch = synth.reads(cfg)
+    units = build_units(synth.variant_records(cfg), cfg.contigs)
+    params = device.make_params(min_mapq=1, min_baseq=30)
+    monkeypatch.delenv("VFK_COL_TRANSPOSED", raising=False)
+    ref = device.pack_reads(batch, params, columns=True)
+    if transposed:
+        monkeypatch.setenv("VFK_COL_TRANSPOSED", "1")
+    pk = device.pack_reads(batch, params, columns=True)
+    w = pk.col_wbase[units.tid] + units.pos // 12
+    cu = np.zeros((units.n_units, 4), np.uint32)
+    cu[:, 0] = pk.col_off[w]
+    cu[:, 1] = pk.col_off[w + 1] - pk.col_off[w]
+    cu[:, 2] = units.pos % 12
+    cu[:, 3] = units.meta
+    cu[5, 1] = 70  # a column too deep for the kernel
+    lib = device.libvfk()
+    lib.vfk_host_gather_columns.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    cu2 = np.zeros_like(cu)
+    need = C.c_int64(0)
+    sectors = np.ascontiguousarray(pk.col_sectors)
+    assert lib.vfk_host_gather_columns(cu.ctypes.data, len(cu), sectors.ctypes.data, transposed, cu2.ctypes.data, None, 0, C.byref(need)) == 0
+    out = np.full(need.value, 0xCD, np.uint8)
+    assert lib.vfk_host_gather_columns(cu.ctypes.data, len(cu), sectors.ctypes.data, transposed, cu2.ctypes.data, out.ctypes.data,
+                                       need.value, C.byref(need)) == 0
+    assert lib.vfk_host_gather_columns(cu.ctypes.data, len(cu), sectors.ctypes.data, transposed, cu2.ctypes.data, out.ctypes.data,
+                                       need.value - 32, C.byref(need)) != 0  # too small a buffer is refused
+    sa = np.asarray(ref.col_sectors)
+    kind = cu[:, 3] & 3
+    n_checked = 0
+    for u in range(len(cu)):
+        off, cnt, p = int(cu[u, 0]), int(cu[u, 1]), int(cu[u, 2])
+        assert cu2[u, 2] == p and cu2[u, 3] == cu[u, 3]
+        if kind[u] != 0:
+            assert cu2[u, 1] == 0
+            continue
+        if cnt > 64:
+            assert cu2[u, 1] == 65 and cu2[u, 0] == 0
+            continue
+        assert cu2[u, 1] == cnt
+        run = out[int(cu2[u, 0]) * 32:]
+        for k in range(cnt):
+            sec = sa[(off + k) * 32:(off + k + 1) * 32]
+            assert np.array_equal(run[8 * k:8 * k + 8], sec[24:32])                                  # header pair k
+            assert np.array_equal(run[8 * cnt + 2 * k:8 * cnt + 2 * k + 2], sec[2 * p:2 * p + 2])   # entry k of position p
+            n_checked += 1
+    assert n_checked > 3000 and need.value < 0.45 * 32 * cu[kind == 0, 1].sum()  # ~10 of every 32 bytes

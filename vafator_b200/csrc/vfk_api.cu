@@ -23,6 +23,7 @@ cudaError_t launch_epilogue(int64_t n_units, const vfk_counts *counts, const dou
                             const void *table, int32_t n_table, vfk_stats *out, cudaStream_t stream, int *launches);
 cudaError_t launch_carter_table(int32_t n_table, double fpr, double error_rate, void *table, cudaStream_t stream, int *launches);
 size_t carter_entry_size();
+extern thread_local bool column_runs_gathered;  // vfk_pileup.cu: the next column launch reads per-unit gathered runs
 cudaError_t launch_values(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, int32_t max_per_unit, uint32_t *values,
                           int32_t *n_values, cudaStream_t stream, int *launches);
 cudaError_t launch_ranksum(int64_t n_pairs, const uint32_t *alt, const int64_t *alt_off, const uint32_t *ref,
@@ -93,12 +94,17 @@ struct Slot {
     unsigned long long *h_cand = nullptr;  // pinned host word for the candidate sum
     DevBuf deferred, resolved;
     PinBuf h_resolved;  // units located on the host (sparse variant sets), copied to `resolved`
+    PinBuf h_col_gather, h_cunits2;  // VFK_HOST_GATHER=1: column runs gathered unit by unit, the units pointing at them
+    DevBuf col_gather;
     DevBuf contig, hot, cold, mate, sb, cigar, payload;
     DevBuf tid, pos, meta, len, soff, ins, stop, eaf, counts, stats;
     void release() {
         DevBuf *bufs[] = {&deferred, &resolved, &contig, &hot, &cold, &mate, &sb, &cigar, &payload, &tid, &pos, &meta, &len,
                           &soff, &ins, &stop, &eaf, &counts, &stats};
         for (DevBuf *b : bufs) b->release();
+        col_gather.release();
+        h_col_gather.release();
+        h_cunits2.release();
         h_resolved.release();
         if (counters) cudaFree(counters);
         if (h_cand) cudaFreeHost(h_cand);
@@ -397,6 +403,48 @@ static unsigned long long locate_host(const vfk_read_batch *r, const vfk_variant
     return total;
 }
 
+// Host half of VFK_HOST_GATHER (see vfk_annotate_host_async): per column unit {first sector of the window's run, sectors,
+// position in the window, meta} -> a compact run of its own: the header pairs of the run, then the entries of ITS
+// position (10 bytes per read instead of 32), padded to 32 bytes; units_out points the units at their compact runs.
+extern "C" int vfk_host_gather_columns(const uint32_t *units_in, int64_t n_units, const uint8_t *sectors, int transposed,
+                                       uint32_t *units_out, uint8_t *out, int64_t out_cap, int64_t *out_bytes) {
+    if (!units_in || !units_out || !out_bytes || n_units < 0 || (!sectors && n_units)) return fail(VFK_EINVAL, "vfk_host_gather_columns: NULL argument");
+    const uint4 *cu = reinterpret_cast<const uint4 *>(units_in);
+    uint4 *cu2 = reinterpret_cast<uint4 *>(units_out);
+    uint64_t acc = 0;  // in 32-byte sectors
+    for (int64_t u = 0; u < n_units; ++u) {
+        const uint32_t cnt = cu[u].y, kind = cu[u].w & 3u;
+        const uint32_t g = (kind == VFK_KIND_SNV && cnt <= 64u) ? cnt : 0u;
+        // not served by the column kernel: no run (other kinds), or a count that only says "too deep" (the kernel may
+        // still prefetch lanes of it: offset 0 is always backed by 4 KB)
+        cu2[u] = make_uint4(g ? (uint32_t)acc : 0u, kind != VFK_KIND_SNV ? 0u : (cnt <= 64u ? cnt : 65u), cu[u].z, cu[u].w);
+        acc += (10u * g + 31u) / 32u;
+    }
+    if (acc >= (1ull << 32)) return fail(VFK_EUNSUPPORTED, "gathered column runs exceed 2^32 sectors");
+    const int64_t bytes = (int64_t)(acc < 128 ? 128 : acc) * 32;
+    *out_bytes = bytes;
+    if (!out) return VFK_OK;  // sizing pass
+    if (out_cap < bytes) return fail(VFK_EINVAL, "vfk_host_gather_columns: output buffer too small");
+#pragma omp parallel for schedule(static)
+    for (int64_t u = 0; u < n_units; ++u) {
+        const uint32_t g = (cu2[u].y >= 1u && cu2[u].y <= 64u) ? cu2[u].y : 0u;
+        if (!g) continue;
+        const uint32_t p = cu[u].z;
+        const uint8_t *src = sectors + (size_t)cu[u].x * 32;
+        uint8_t *hdr = out + (size_t)cu2[u].x * 32, *ent = hdr + (size_t)g * 8;
+        if (transposed) {
+            memcpy(hdr, src, (size_t)g * 8);
+            memcpy(ent, src + (size_t)g * 8 + (size_t)p * g * 2, (size_t)g * 2);
+        } else {
+            for (uint32_t k = 0; k < g; ++k) {
+                memcpy(hdr + (size_t)k * 8, src + (size_t)k * 32 + 24, 8);
+                memcpy(ent + (size_t)k * 2, src + (size_t)k * 32 + 2 * p, 2);
+            }
+        }
+    }
+    return VFK_OK;
+}
+
 extern "C" int vfk_wait(vfk_handle *h, int ticket) {
     if (!h || ticket < 0 || ticket > 1) return fail(VFK_EINVAL, "vfk_wait: bad handle or ticket");
     Slot &s = h->slot[ticket];
@@ -511,6 +559,38 @@ extern "C" int vfk_annotate_host_async(vfk_handle *h, const vfk_read_batch *read
         R.col_sectors = (const uint32_t *)z_col;
         ++h->column_batches;
     }
+    // EXPERIMENTAL (VFK_HOST_GATHER=1, not yet verified on a GPU): instead of letting the column kernel read the sector
+    // runs in place over PCIe (32 bytes per read of the column, of which it uses 10), the host gathers, unit by unit,
+    // the header pairs of the run and the entries of the unit's own position into one compact page-locked buffer that
+    // crosses the bus as a single bulk copy; the units are re-pointed at their compact runs (pileup_column_kernel<.., CP>).
+    bool gathered = false;
+    {
+        const char *env_g = getenv("VFK_HOST_GATHER");
+        if (use_columns && env_g && env_g[0] == '1') {
+            const char *env_t = getenv("VFK_COL_TRANSPOSED");
+            const bool src_transposed = env_t && env_t[0] == '1';  // form of the caller's store (device.pack_reads)
+            const uint32_t *cu = reinterpret_cast<const uint32_t *>((const char *)S.h_resolved.p + (size_t)nu * sizeof(vfk::ResolvedUnit));
+            rc = S.h_cunits2.reserve((size_t)nu * sizeof(uint4));
+            if (rc) return rc;
+            int64_t need = 0;
+            rc = vfk_host_gather_columns(cu, nu, reads->col_sectors, src_transposed ? 1 : 0, (uint32_t *)S.h_cunits2.p, nullptr, 0, &need);
+            if (rc) return rc;
+            const size_t bytes = (size_t)need;
+            rc = S.h_col_gather.reserve(bytes);
+            if (rc) return rc;
+            rc = S.col_gather.reserve(bytes);
+            if (rc) return rc;
+            rc = vfk_host_gather_columns(cu, nu, reads->col_sectors, src_transposed ? 1 : 0, (uint32_t *)S.h_cunits2.p,
+                                         (uint8_t *)S.h_col_gather.p, need, &need);
+            if (rc) return rc;
+            CU(cudaMemcpyAsync(S.col_gather.p, S.h_col_gather.p, bytes, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync((char *)S.resolved.p + (size_t)nu * sizeof(vfk::ResolvedUnit), S.h_cunits2.p, (size_t)nu * sizeof(uint4),
+                               cudaMemcpyHostToDevice, st));  // after the copy of the located units: replaces their column part
+            h->staged_bytes += (int64_t)bytes + (int64_t)nu * (int64_t)sizeof(uint4);
+            R.col_sectors = (const uint32_t *)S.col_gather.p;
+            gathered = true;
+        }
+    }
     // ---- stage 2
     const void *z_hot = pinned_alias(reads->hot), *z_mate = pinned_alias(reads->mate);
     const char *env_hot = getenv("VFK_ZERO_COPY_HOT");  // the 20-byte headers follow the payload unless told otherwise
@@ -540,8 +620,10 @@ extern "C" int vfk_annotate_host_async(vfk_handle *h, const vfk_read_batch *read
     if (rc) return rc;
     rc = S.stats.reserve((size_t)nu * sizeof(vfk_stats));
     if (rc) return rc;
+    vfk::column_runs_gathered = gathered;
     cudaError_t e = vfk::launch_pileup_resolved(R, V, *params, reads->max_l_qseq, (vfk_counts *)S.counts.p, S.resolved.p, S.counters,
                                                 (uint32_t *)S.deferred.p, h->sm_count, st, &launches);
+    vfk::column_runs_gathered = false;
     if (e != cudaSuccess) return fail(VFK_ECUDA, "pileup launch: %s", cudaGetErrorString(e));
     rc = ensure_carter(h, fpr, error_rate, st);
     if (rc) return rc;

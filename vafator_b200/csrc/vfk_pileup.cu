@@ -674,10 +674,18 @@ struct ColRead {  // one sector as a lane holds it
 // words per 32-byte sector).  TR = true: the window-transposed form of the same run (vfkio_columns_transpose: cnt
 // header pairs, then 12 rows of cnt entries) -- NOT YET VERIFIED ON A GPU; selected only by VFK_COL_TRANSPOSED=1
 // together with a store built under the same setting (vafator_b200/device.py).
-template <bool TR>
+// CP = true (EXPERIMENTAL, VFK_HOST_GATHER=1, host entry point only): the run was gathered on the host for this very
+// unit -- cnt header pairs, then the cnt entries of the unit's OWN position (one row), see vfk_api.cu.
+template <bool TR, bool CP>
 __device__ __forceinline__ ColRead load_col_read(const uint32_t *__restrict__ sectors, uint32_t off, uint32_t cnt, uint32_t k, uint32_t p) {
     ColRead c;
-    if constexpr (TR) {
+    if constexpr (CP) {
+        const unsigned char *run = reinterpret_cast<const unsigned char *>(sectors + (size_t)off * 8u);
+        const uint2 h = __ldg(reinterpret_cast<const uint2 *>(run) + k);
+        c.e = (uint32_t)__ldg(reinterpret_cast<const unsigned short *>(run + (size_t)cnt * 8u) + k);
+        c.h0 = h.x;
+        c.h1 = h.y;
+    } else if constexpr (TR) {
         const unsigned char *run = reinterpret_cast<const unsigned char *>(sectors + (size_t)off * 8u);
         const uint2 h = __ldg(reinterpret_cast<const uint2 *>(run) + k);
         c.e = (uint32_t)__ldg(reinterpret_cast<const unsigned short *>(run + (size_t)cnt * 8u) + (size_t)p * cnt + k);
@@ -731,7 +739,7 @@ __device__ __forceinline__ void col_evaluate(const ColRead &c, uint32_t partner,
     }
 }
 
-template <int POSB, bool TR, bool MQS>
+template <int POSB, bool TR, bool MQS, bool CP>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, VFK_COL_MIN_CTAS)
 pileup_column_kernel(ReadsDev R, const uint4 *__restrict__ cunits, const ResolvedUnit *__restrict__ res, int64_t n_units, vfk_params P,
                      vfk_counts *__restrict__ out,
@@ -762,7 +770,7 @@ pileup_column_kernel(ReadsDev R, const uint4 *__restrict__ cunits, const Resolve
         next.e = next.h0 = next.h1 = 0u;
         {
             const uint32_t off0 = __shfl_sync(FULL, cu.x, 0), cnt0 = __shfl_sync(FULL, cu.y, 0), p0 = __shfl_sync(FULL, cu.z, 0);
-            if ((uint32_t)lane < cnt0) next = load_col_read<TR>(sectors, off0, cnt0, (uint32_t)lane, p0);
+            if ((uint32_t)lane < cnt0) next = load_col_read<TR, CP>(sectors, off0, cnt0, (uint32_t)lane, p0);
         }
         for (int j = 0; j < n_here; ++j) {
             const int64_t u = (int64_t)base + j;
@@ -773,7 +781,7 @@ pileup_column_kernel(ReadsDev R, const uint4 *__restrict__ cunits, const Resolve
             if (j + 1 < n_here) {
                 const uint32_t off1 = __shfl_sync(FULL, cu.x, j + 1), cnt1 = __shfl_sync(FULL, cu.y, j + 1);
                 const uint32_t p1 = __shfl_sync(FULL, cu.z, j + 1);
-                if ((uint32_t)lane < cnt1) next = load_col_read<TR>(sectors, off1, cnt1, (uint32_t)lane, p1);
+                if ((uint32_t)lane < cnt1) next = load_col_read<TR, CP>(sectors, off1, cnt1, (uint32_t)lane, p1);
             }
             int med2[3][2] = {{-1, -1}, {-1, -1}, {-1, -1}};
             uint64_t s2[3] = {0, 0, 0};
@@ -794,7 +802,7 @@ pileup_column_kernel(ReadsDev R, const uint4 *__restrict__ cunits, const Resolve
             if ((uint32_t)lane >= cnt) c0.e = c0.h0 = c0.h1 = 0u;
             ColRead c1;
             c1.e = c1.h0 = c1.h1 = 0u;
-            if (cnt > 32u && (uint32_t)lane + 32u < cnt) c1 = load_col_read<TR>(sectors, off, cnt, 32u + (uint32_t)lane, p);
+            if (cnt > 32u && (uint32_t)lane + 32u < cnt) c1 = load_col_read<TR, CP>(sectors, off, cnt, 32u + (uint32_t)lane, p);
             // overlap partners: sector k + offset of the same run, i.e. an entry another lane holds
             const int off0 = (int)(int8_t)((c0.h0 >> 20) & 0xFFu), off1 = (int)(int8_t)((c1.h0 >> 20) & 0xFFu);
             const int k0p = lane + off0, k1p = 32 + lane + off1;
@@ -1003,6 +1011,9 @@ cudaError_t launch_locate(const ReadsDev &R, const UnitsDev &V, void *resolved, 
     return cudaGetLastError();
 }
 
+// set by the host entry point (vfk_api.cu) around a launch whose column runs it has gathered unit by unit
+thread_local bool column_runs_gathered = false;
+
 // the staged variants are chosen per call (tools/ab_staged.py switches them inside one process)
 static bool env_flag(const char *name) {
     const char *v = getenv(name);
@@ -1050,10 +1061,12 @@ static cudaError_t launch_posb(const ReadsDev &R, const UnitsDev &V, const vfk_p
         const bool transposed = env_flag("VFK_COL_TRANSPOSED");
         int col_ctas = 0;
         const bool mq_select = env_flag("VFK_MQ_SELECT");
-        auto column_kernel = pileup_column_kernel<POSB, false, false>;
-        if (transposed && mq_select) column_kernel = pileup_column_kernel<POSB, true, true>;
-        else if (transposed) column_kernel = pileup_column_kernel<POSB, true, false>;
-        else if (mq_select) column_kernel = pileup_column_kernel<POSB, false, true>;
+        auto column_kernel = pileup_column_kernel<POSB, false, false, false>;
+        if (column_runs_gathered && mq_select) column_kernel = pileup_column_kernel<POSB, false, true, true>;
+        else if (column_runs_gathered) column_kernel = pileup_column_kernel<POSB, false, false, true>;
+        else if (transposed && mq_select) column_kernel = pileup_column_kernel<POSB, true, true, false>;
+        else if (transposed) column_kernel = pileup_column_kernel<POSB, true, false, false>;
+        else if (mq_select) column_kernel = pileup_column_kernel<POSB, false, true, false>;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&col_ctas, column_kernel, WARPS_PER_CTA * 32, 0);
         if (e != cudaSuccess) return e;
         int64_t col_grid = (int64_t)sm_count * std::max(col_ctas, 1);
