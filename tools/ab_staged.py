@@ -5,7 +5,8 @@ for, parity of every unit against the C oracle on a sample, then the CUDA-event 
     python tools/ab_staged.py [--tiles 200000] [--launches 20] [--oracle-tiles 3000]
 
 Needs a GPU.  The variants are environment switches read per call by libvfk.so / device.pack_reads:
-VFK_COL_TRANSPOSED (store layout: the batch is re-packed when it changes), VFK_LIST_SHALLOW, VFK_MQ_SELECT."""
+VFK_COL_TRANSPOSED (store layout: the batch is re-packed when it changes), VFK_LIST_SHALLOW, VFK_MQ_SELECT; --e2e adds
+the host entry point with and without VFK_HOST_GATHER."""
 import argparse
 import itertools
 import json
@@ -46,6 +47,7 @@ def main():
     ap.add_argument("--tiles", type=int, default=200_000)
     ap.add_argument("--oracle-tiles", type=int, default=3000)
     ap.add_argument("--launches", type=int, default=20)
+    ap.add_argument("--e2e", action="store_true", help="also time the host entry point: in place vs VFK_HOST_GATHER, both store forms")
     ap.add_argument("--only", default="", help="comma separated flag subsets, e.g. 'VFK_MQ_SELECT,VFK_COL_TRANSPOSED+VFK_MQ_SELECT'")
     a = ap.parse_args()
     params = device.make_params(min_mapq=1, min_baseq=30)
@@ -91,6 +93,32 @@ def main():
                           "pileup_ms_min": round(ms[0], 4), "units": int(big[1].n_units)}), flush=True)
     for f in FLAGS:
         os.environ.pop(f, None)
+    if a.e2e:  # the host entry point: store read in place (sector / transposed form) vs gathered per unit and bulk-copied
+        eaf = np.full(big[1].n_units, 0.5)
+        for layout in ("0", "1"):
+            os.environ["VFK_COL_TRANSPOSED"] = layout
+            pinned = device.pack_reads(big[0], params, pinned=True, columns=True)
+            ref = None
+            for gather in ("0", "1"):
+                os.environ["VFK_HOST_GATHER"] = gather
+                for _ in range(2):
+                    got = dev.annotate_host(pinned, big[1], big[2], params, eaf, 5e-7, 1e-3)
+                ts = []
+                for _ in range(a.launches):
+                    t0 = time.perf_counter()
+                    got = dev.annotate_host(pinned, big[1], big[2], params, eaf, 5e-7, 1e-3)
+                    ts.append(time.perf_counter() - t0)
+                ts.sort()
+                same = "n/a"
+                if ref is None:
+                    ref = got
+                else:
+                    same = "ok" if all(np.array_equal(got[0][f], ref[0][f]) for f in FIELDS) and got[1].tobytes() == ref[1].tobytes() else "DIFFERS"
+                print(json.dumps({"e2e": "annotate_host", "VFK_COL_TRANSPOSED": layout, "VFK_HOST_GATHER": gather,
+                                  "equal_to_in_place": same, "ms_median": round(1e3 * ts[len(ts) // 2], 3), "ms_min": round(1e3 * ts[0], 3),
+                                  "units": int(big[1].n_units)}), flush=True)
+        for f in ("VFK_COL_TRANSPOSED", "VFK_HOST_GATHER"):
+            os.environ.pop(f, None)
 
 
 if __name__ == "__main__":
