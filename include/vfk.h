@@ -12,15 +12,21 @@
  *     -> vfk_epilogue()                 FP64 z / p / pu / pw / k from those integers
  *   vfk_annotate_host() runs both with HOST buffers (pinned or pageable), copies included.
  *
+ * What crosses the boundary is the CANONICAL columnar read batch -- the fields of the decoded BAM records
+ * the reference hands to htslib at vafator/pileups.py:71-80 (start, flag, MAPQ, CIGAR, 4-bit sequence,
+ * qualities, mate position, template length, read name id / hash), untouched.  Everything derived from them
+ * -- reference spans, the position index, CIGAR shapes, the read filter, htslib's mate-overlap pairing --
+ * is computed by the library's kernels on the device, inside every call.
+ *
  * Conventions: every function returns 0 (VFK_OK) or a negative VFK_E* code and never throws or
  * aborts; vfk_last_error() gives the thread-local message.  All buffers are caller owned; the
  * library keeps no reference to them after the stream work it enqueued has completed.  Calls
  * are asynchronous with respect to the host until vfk_sync() (except vfk_annotate_host, which
  * returns after its results are in host memory).  `stream` is a cudaStream_t passed as void*
  * (NULL = the CUDA default stream; the handle's own streams are used by vfk_annotate_host only).
- * A handle belongs to one device and owns per-launch scratch (located units, deferred-unit lists):
- * drive it from one host thread at a time and keep the vfk_pileup calls of one handle on one stream
- * (stream order is what protects the scratch); use one handle per stream / per host thread for
+ * A handle belongs to one device and owns per-launch scratch (derived per-read words, located units,
+ * deferred-unit lists): drive it from one host thread at a time and keep the calls of one handle on one
+ * stream (stream order is what protects the scratch); use one handle per stream / per host thread for
  * concurrency.  Different handles are independent.
  */
 #ifndef VFK_H
@@ -31,7 +37,7 @@
 extern "C" {
 #endif
 
-#define VFK_VERSION 100 /* 0.1.0 */
+#define VFK_VERSION 200 /* 0.2.0 */
 
 enum {
     VFK_OK = 0,
@@ -44,84 +50,37 @@ enum {
 
 #define VFK_MAX_READ_LEN 4095 /* longest l_qseq the read-position histograms cover */
 #define VFK_NO_MATE 0xFFFFFFFFu
-#define VFK_SHAPE_SIMPLE 0u
-#define VFK_SHAPE_GENERAL 1u
-#define VFK_SHAPE_ONE_EVENT 2u
-#define VFK_EV_NONE 0
-#define VFK_EV_INS 1
-#define VFK_EV_DEL 2
-#define VFK_EV_SKIP 3
 #define VFK_CODE_NONE 0xFFu
 
-/* ---- read batch, HBM layout (DESIGN.md "Data layout") -------------------------------------
- * Reads are coordinate sorted (BAM order); unplaced reads are not part of the batch.          */
-typedef struct {
-    int32_t pos;   /* 0-based leftmost reference position                                      */
-    uint32_t span; /* reference bases consumed by the CIGAR (M,D,N,=,X); end = pos + span       */
-    uint32_t fmk;  /* flag (bits 0-15) | mapq << 16 | shape << 24;
-                      shape 0 (VFK_SHAPE_SIMPLE): the CIGAR is one M/=/X op (qpos = column - pos,
-                              l_qseq = span); the cold record is never read,
-                      shape 1 (VFK_SHAPE_GENERAL): any CIGAR, walked op by op,
-                      shape 2 (VFK_SHAPE_ONE_EVENT): [H][S] M [ I|D|N  M ] [S][H] -- clips and at most
-                              one event between two aligned blocks; resolved without a loop from
-                              cold.event (the CIGAR words are kept for the indel-support tests)  */
-    uint32_t pay;  /* payload offset, in 32-byte sectors                                       */
-} vfk_read_hot;
-
-typedef struct {
-    uint32_t cigar_off; /* index into cigar[] (BAM encoding len<<4|op)                         */
-    uint32_t n_cigar;
-    uint32_t l_qseq;
-    uint32_t event; /* shape 2: leading soft clip | first block length << 12 | VFK_EV_* << 24 |
-                       event length << 26 (lengths < 4096 / < 64, else the read is shape 1); 0 otherwise */
-} vfk_read_cold;
-
-/* payload: read i owns ceil(l_qseq/20) sectors of 32 bytes from hot.pay.  A sector is four 8-byte
- * little-endian granules; granule g of the read holds query positions 5g .. 5g+4, 12 bits each:
- * bits [12r, 12r+8) base quality, bits [12r+8, 12r+12) BAM 4-bit base code.  One (read, column)
- * lookup = one 64-bit load = one 32-byte DRAM sector (BAM's split seq / qual arrays cost two).      */
-/* ---- column store (optional; built by vfkio_columns_*, include/vfk_io.h) --------------------------------
- * The reference cut into windows of VFK_COL_WIDTH positions; every read leaves one 32-byte sector in every
- * window it overlaps, the sectors of a window stored together in read order:
- *   col_wbase[t]            first window of contig t; window of (t, pos) = col_wbase[t] + pos / VFK_COL_WIDTH
- *                           (contig t has col_wbase[t+1] - col_wbase[t] windows: up to its last covered base)
- *   col_off[w], col_off[w+1] the sectors of window w
- *   sector                  12 entries of 16 bits (position p of the window in entry p): base quality |
- *                           BAM base code << 8 | state << 12, state 0 = not covered, 1 = aligned base,
- *                           2 = deletion, 3 = reference skip; then two header words:
- *     h0  query position at the first covered position of the window (12 bits) | MAPQ << 12 |
- *         signed sector offset of the overlap partner inside the window << 20 (0 = none) |
- *         read passes the read filter << 28 | tie-break bit << 29 | read precedes its partner << 30 |
- *         sector cannot be used (two insertions in the window, partner out of reach) << 31
- *     h1  aligned-position mask (12 bits) | position the insertion follows << 12 | its length << 16 |
- *         has insertion << 28;  query position of entry p = h0.qpos + popcount(mask below p) + (insertion
- *         before p ? length : 0)
- * The read filter verdict and the partner links depend on vfk_params: build the store with the parameters
- * the kernels are called with.  With a column store present SNV units are evaluated from it (one contiguous
- * read per column); units it cannot serve go to the read-major path.                                      */
-#define VFK_COL_WIDTH 12
-
+/* ---- canonical columnar read batch --------------------------------------------------------------------
+ * The placed reads (tid >= 0) of one BAM, or of one interval shard of it, coordinate sorted (BAM order).
+ * Array by array what a BAM record holds (SAMv1 4.2); `contig_off`, `max_l_qseq` and the pool sizes are
+ * batch metadata every decoder has at hand when it finishes a batch.
+ *   pos        0-based leftmost reference position (>= 0)
+ *   cigar      BAM encoding len << 4 | op; read i owns cigar[cigar_off[i] .. + n_cigar[i])
+ *   seq        BAM 4-bit codes "=ACMGRSVTWYHKDBN", high nibble first, each read byte aligned:
+ *              base q of read i = nibble q of seq[seq_off[i] ...]
+ *   qual       one byte per base at qual[qual_off[i] + q]
+ *   mtid/mpos/isize   mate contig, mate start, template length (RNEXT / PNEXT / TLEN)
+ *   qname_id   any 64-bit id that is equal iff the read names are equal
+ *   qname_hash khash X31 of the read name (htslib's overlap tie-break hashes it)
+ * vfk_pileup: every pointer is a DEVICE pointer.  vfk_annotate_host: HOST pointers.                    */
 typedef struct {
     int64_t n_reads;
     int32_t n_contigs;
     int32_t max_l_qseq;
     const int64_t *contig_off;    /* [n_contigs+1] reads of contig t are [off[t], off[t+1])      */
-    const vfk_read_hot *hot;      /* [n_reads]                                                  */
-    const vfk_read_cold *cold;    /* [n_reads]                                                  */
-    const uint32_t *mate;         /* [n_reads] overlap partner | tie_break << 31, VFK_NO_MATE   */
-    const int32_t *sb;            /* [n_reads][2] {start, back}: the position index;
-                                     back[i] = first read of the contig whose running-maximum end
-                                     exceeds start[i], i.e. no earlier read can overlap it        */
-    const uint32_t *cigar;        /* [n_cigar_words]                                            */
-    const uint8_t *payload;       /* [n_sectors * 32], 32-byte aligned                          */
-    int64_t n_cigar_words;
-    int64_t n_sectors;
-    /* column store, all NULL / 0 when absent */
-    const int64_t *col_wbase;     /* [n_contigs+1]                                              */
-    const uint32_t *col_off;      /* [n_col_windows+1]                                          */
-    const uint8_t *col_sectors;   /* [n_col_sectors * 32], 32-byte aligned                      */
-    int64_t n_col_windows;
-    int64_t n_col_sectors;
+    const int32_t *pos;           /* [n_reads]                                                   */
+    const uint16_t *flag;
+    const uint8_t *mapq;
+    const int32_t *l_qseq, *n_cigar;
+    const int64_t *cigar_off, *seq_off, *qual_off;
+    const uint32_t *cigar;        /* [n_cigar_words]                                             */
+    const uint8_t *seq, *qual;    /* [n_seq_bytes], [n_qual_bytes]                               */
+    const int32_t *mtid, *mpos, *isize;
+    const uint64_t *qname_id;
+    const uint32_t *qname_hash;
+    int64_t n_cigar_words, n_seq_bytes, n_qual_bytes;
 } vfk_read_batch;
 
 /* ---- variant units: one per (VCF record, ALT allele) that needs a column evaluation --------- */
@@ -153,8 +112,10 @@ typedef struct {
 
 /* ---- pileup output: integers only ---------------------------------------------------------- */
 #define VFK_ST_KIND_MASK 0x3u
-#define VFK_ST_DEFERRED 0x10u  /* column deeper than the warp path handles; done by the block path */
+#define VFK_ST_DEFERRED 0x10u  /* never set in a finished record: the unit is waiting on a device-side list    */
 #define VFK_ST_READLEN 0x20u   /* a read position fell outside the histogram: result invalid      */
+#define VFK_ST_BADBATCH 0x40u  /* the read batch is malformed (unsorted, negative start, CIGAR outside its pool):
+                                  every record of the call carries the bit, results are invalid    */
 typedef struct {
     int32_t dp;         /* depth as vafator reports it (pileups.py:224-227, :264, :330)          */
     int32_t n_amb;      /* SNV: IUPAC-ambiguous bases in the column (annotator.py:386)           */
@@ -162,8 +123,7 @@ typedef struct {
     int32_t ac_alt;     /* reads supporting this unit's ALT                                       */
     int32_t med2[3][2]; /* [mq,bq,pos][ref,alt]: twice the median, -1 when the list is empty      */
     uint32_t status;
-    uint32_t n_cand;    /* reads inspected for the unit (diagnostic): candidate reads of the position index on
-                           the read-major path, sectors of the column's window on the column-store path      */
+    uint32_t n_cand;    /* reads inspected for the unit (diagnostic): candidate reads of the position index */
     uint64_t s2[3];     /* [mq,bq,pos]: twice the sum of the ALT mid-ranks in the pooled ranking   */
     uint32_t n_cover;   /* reads overlapping the column before any filter (D_raw of SURVEY.md 8d)   */
     uint32_t n_col;     /* reads in the htslib column (read filter passed) BEFORE the base-quality filter:
@@ -188,7 +148,8 @@ int vfk_create(int device, vfk_handle **out);
 int vfk_destroy(vfk_handle *h);
 int vfk_sync(vfk_handle *h);
 
-/* all pointers inside the batches and `out` are DEVICE pointers */
+/* all pointers inside the batches and `out` are DEVICE pointers.  One call = read preparation (reference
+ * spans, CIGAR shapes, position index) + locate + pileup kernels, all on `stream`. */
 int vfk_pileup(vfk_handle *h, const vfk_read_batch *reads, const vfk_variant_batch *units,
                const vfk_params *params, vfk_counts *out, void *stream);
 
@@ -196,37 +157,28 @@ int vfk_pileup(vfk_handle *h, const vfk_read_batch *reads, const vfk_variant_bat
 int vfk_epilogue(vfk_handle *h, int64_t n_units, const vfk_counts *counts, const double *eaf,
                  double fpr, double error_rate, vfk_stats *out, void *stream);
 
-/* Same path with HOST buffers: copies the batches to the device (staging memory owned by the
- * handle, grown on demand), runs both kernels and copies counts/stats back before returning.   */
+/* Same path with HOST buffers, results in host memory before it returns.
+ * Page-locked read arrays (cudaHostAlloc / cudaHostRegister, as vafator_b200.bamio and .synth allocate them):
+ * only what the position index is built from -- pos, n_cigar, cigar_off, l_qseq, the CIGAR pool: ~25 bytes per
+ * read -- is copied to the device; every other array (flags, qualities, bases, mate fields, name ids) is read
+ * IN PLACE by the kernels over PCIe, and only for the reads that overlap a variant column.
+ * Pageable arrays: everything is staged by asynchronous copies first.  Results are identical.          */
 int vfk_annotate_host(vfk_handle *h, const vfk_read_batch *reads, const vfk_variant_batch *units,
                       const vfk_params *params, const double *eaf, double fpr, double error_rate,
                       vfk_counts *counts_out, vfk_stats *stats_out);
 
 /* Double-buffered variant: returns once the batch is enqueued on one of the handle's two staging
  * slots; *ticket (0 or 1) names the slot.  Submitting a third batch waits for the slot it reuses.
- * The host buffers (inputs and outputs) must stay valid until vfk_wait(h, ticket) returns.
- * How a batch crosses the bus is chosen per batch:
- *  - sparse variant set (n_units * 64 <= n_reads): the units are located on the host from the
- *    caller's position index, 32 bytes per unit are copied and the index is not; otherwise the
- *    index is copied and the locate kernel runs            (VFK_HOST_LOCATE=0/1 forces the choice);
- *  - page-locked payload / cold / cigar buffers and few candidate reads: the kernel gathers the
- *    sectors it needs straight from host memory instead of copying those arrays
- *    (VFK_ZERO_COPY_PAYLOAD=0/1), and so it does for the hot / mate arrays if they are page-locked
- *    too (VFK_ZERO_COPY_HOT=0 keeps copying them).
- * Results are identical whichever way is taken.                                                   */
+ * The host buffers (inputs and outputs) must stay valid until vfk_wait(h, ticket) returns; vfk_wait
+ * returns VFK_EINVAL when the batch turned out to be malformed (VFK_ST_BADBATCH).                    */
 int vfk_annotate_host_async(vfk_handle *h, const vfk_read_batch *reads, const vfk_variant_batch *units,
                             const vfk_params *params, const double *eaf, double fpr, double error_rate,
                             vfk_counts *counts_out, vfk_stats *stats_out, int *ticket);
 int vfk_wait(vfk_handle *h, int ticket);
-/* how many batches of this handle took the zero-copy route */
-int64_t vfk_zero_copy_batches(vfk_handle *h);
 /* transfer accounting of the host entry point since vfk_create: out[0] bytes copied host -> device by
- * bulk copies, out[1] batches whose payload was gathered (zero copy), out[2] batches whose hot / mate
- * headers were gathered too, out[3] batches located on the host                                    */
+ * bulk copies, out[1] batches whose arrays were read in place (zero copy), out[2] batches staged in full,
+ * out[3] bytes copied device -> host                                                               */
 int vfk_transfer_stats(vfk_handle *h, int64_t out[4]);
-/* how many batches of the host entry point evaluated their SNV units from the column store (page-locked
- * buffers, units located on the host; VFK_HOST_COLUMNS=0 keeps to the read-major arrays)               */
-int64_t vfk_column_batches(vfk_handle *h);
 
 /* ---- list-shaped auxiliaries (DEVICE pointers) ------------------------------------------------
  * vfk_pileup_values: per unit, the per-read values the reference keeps in all_mqs / all_bqs /
@@ -244,13 +196,6 @@ int vfk_ranksum_values(vfk_handle *h, int64_t n_pairs, const uint32_t *alt, cons
 
 /* Number of kernel launches issued through this handle since it was created. */
 int64_t vfk_launch_count(vfk_handle *h);
-
-/* Host-side helper of vfk_annotate_host (VFK_HOST_GATHER=1, staged): column units {first sector of the window's run,
- * sectors, position, meta} [n][4] + the column store (sector form, or window-transposed when `transposed`) -> per unit a
- * compact run (header pairs, then the entries of the unit's own position; 10 bytes per read, padded to 32) in `out`, and
- * units pointing at those runs.  out == NULL: only *out_bytes is computed.  No CUDA call. */
-int vfk_host_gather_columns(const uint32_t *units_in, int64_t n_units, const uint8_t *sectors, int transposed,
-                            uint32_t *units_out, uint8_t *out, int64_t out_cap, int64_t *out_bytes);
 
 #ifdef __cplusplus
 }

@@ -1,10 +1,9 @@
 /* vfk_io.h -- host-side companion library (libvfkio.so, no CUDA dependency).
  *
- * Produces what include/vfk.h consumes: turns decoded BAM records (the canonical columnar
- * batch, vafator_b200/batch.py) into the HBM layout, emulates htslib's mate-overlap pairing,
- * decodes BGZF/BAM files and generates the synthetic benchmark batches of SURVEY.md 8(d).
- * It stands where pysam.AlignmentFile stands in the reference (vafator/annotator.py:161-164,
- * vafator/pileups.py:71-80).
+ * Produces the canonical columnar read batch include/vfk.h consumes: decodes BGZF/BAM files and generates the
+ * synthetic benchmark batches of SURVEY.md 8(d).  It stands where pysam.AlignmentFile stands in the reference
+ * (vafator/annotator.py:161-164, vafator/pileups.py:71-80).  Nothing here looks inside a CIGAR, filters a read or
+ * pairs mates: that is the kernels' work.
  */
 #ifndef VFK_IO_H
 #define VFK_IO_H
@@ -33,43 +32,7 @@ typedef struct {
     const uint32_t *qname_hash;
 } vfkio_reads;
 
-typedef struct {
-    int64_t n_placed;      /* reads with tid >= 0 (the packed batch holds exactly these) */
-    int64_t n_cigar_words; /* CIGAR words of the shape-1 reads */
-    int64_t n_sectors;     /* 32-byte payload sectors */
-    int32_t max_l_qseq;
-    int32_t pad;
-} vfkio_plan;
-
 const char *vfkio_last_error(void);
-
-/* sizes of the packed arrays */
-int vfkio_pack_plan(const vfkio_reads *r, vfkio_plan *plan);
-
-/* fill caller-allocated arrays sized by the plan (host memory, pinned or not) */
-int vfkio_pack(const vfkio_reads *r, const vfkio_plan *plan, int64_t *contig_off /*[n_contigs+1]*/,
-               vfk_read_hot *hot, vfk_read_cold *cold, int32_t *sb /*[n][2]*/, uint32_t *cigar,
-               uint8_t *payload);
-
-/* htslib overlap_push / overlap_remove emulation (sam.c): mate[i] = partner |
- * tie_break << 31 or VFK_NO_MATE, for the reads the reference would push under `params`. */
-int vfkio_link_mates(const vfkio_reads *r, const vfk_params *params, uint32_t *mate /*[n_placed]*/);
-
-/* ---- column store (include/vfk.h): plan sizes, then fill caller-allocated arrays.  `mate` is the output of
- * vfkio_link_mates for the same parameters. */
-typedef struct {
-    int64_t n_windows;
-    int64_t n_sectors;
-} vfkio_col_plan;
-int vfkio_columns_plan(const vfkio_reads *r, int64_t *wbase /*[n_contigs+1]*/, vfkio_col_plan *plan);
-int vfkio_columns_fill(const vfkio_reads *r, const vfk_params *params, const uint32_t *mate, const int64_t *wbase,
-                       const vfkio_col_plan *plan, uint32_t *woff /*[n_windows+1]*/, uint8_t *sectors /*[n_sectors*32]*/);
-
-/* The same store with every window's run transposed: n header pairs {h0, h1}, then 12 rows of n 16-bit entries
- * (row p = position p of the window) -- a column then reads 10 n contiguous-by-part bytes instead of 32 n.  Same
- * offsets and sizes as the sector form (`out` holds woff[n_windows] * 32 bytes, must not alias `sectors`).
- * Prepared for the next kernel revision: vfk_pileup reads the SECTOR form. */
-int vfkio_columns_transpose(const uint32_t *woff, int64_t n_windows, const uint8_t *sectors, uint8_t *out);
 
 /* Raw DEFLATE (RFC 1951) of one whole stream into a buffer of exactly the inflated size -- the shape of a BGZF
  * member (SAMv1 4.1), which is what the BAM decoder spends its time on.  Returns 0 when the stream ends after
@@ -120,9 +83,11 @@ typedef struct {
     float p_softclip, p_del, p_ins, p_skip;            /* private CIGAR noise per read */
     float p_dup, p_supp, p_secondary, p_qcfail, p_orphan;
     float p_mapq60, base_error, p_n;
+    int64_t g_first, g_count;   /* generate only the tiles [g_first, g_first + g_count) of the genome, global tile index =
+                                   contig * tiles_per_contig + tile (g_count 0 = all): an interval shard of the same input */
 } vfkio_synth_cfg;
 
-/* tile_sizes: [4 * n_contigs * tiles_per_contig] scratch filled by the plan pass and handed to the fill pass */
+/* tile_sizes: [4 * generated tiles] scratch filled by the plan pass and handed to the fill pass */
 int vfkio_synth_plan_reads(const vfkio_synth_cfg *cfg, vfkio_synth_plan *plan, int64_t *tile_sizes);
 /* fills caller-allocated canonical arrays (sizes from the plan); `out` points at writable arrays */
 int vfkio_synth_fill_reads(const vfkio_synth_cfg *cfg, const vfkio_synth_plan *plan, const int64_t *tile_sizes,

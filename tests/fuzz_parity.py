@@ -19,7 +19,7 @@ from vafator_b200.batch import build_units  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--seconds", type=float, default=300)
 ap.add_argument("--seed0", type=int, default=1)
-ap.add_argument("--columns", action="store_true", help="evaluate SNV units from the column store")
+ap.add_argument("--host", action="store_true", help="through vfk_annotate_host (host arrays in, results out) instead of vfk_pileup")
 a = ap.parse_args()
 dev = device.Device(0)
 t_end = time.time() + a.seconds
@@ -59,9 +59,12 @@ while time.time() < t_end:
           for i, j in zip(units.rec, units.alt_index)]
     want = c_oracle.pileup(batch.as_dict(), ou, c_oracle.params(min_mapq=mq, min_baseq=bq))
     params = device.make_params(min_mapq=mq, min_baseq=bq, include_ambiguous=amb)
-    buf = dev.pileup(dev.upload_reads(device.pack_reads(batch, params, columns=a.columns)), dev.upload_units(units, stop), params)
-    dev.sync()
-    got = dev.to_host(buf, device.COUNTS_DTYPE, units.n_units)
+    if a.host:
+        got = dev.annotate_host(device.host_reads(batch, pinned=bool(seed & 1)), units, stop, params, np.full(units.n_units, 0.5), 5e-7, 1e-3)[0]
+    else:
+        buf = dev.pileup(dev.upload_reads(batch), dev.upload_units(units, stop), params)
+        dev.sync()
+        got = dev.to_host(buf, device.COUNTS_DTYPE, units.n_units)
     snv = (got["status"] & 3) == 0
     dp = want["dp"] - (0 if amb else np.where(snv, want["n_amb"], 0))
     both = (want["ac_ref"] > 0) & (want["ac_alt"] > 0)

@@ -149,8 +149,6 @@ def test_collect_metrics_for_chrom_call_site(tmp_path):
             assert (math.isnan(m.mqs[allele]) and want is None) or m.mqs[allele] == want
 
 
-@pytest.mark.skipif(not os.environ.get("VFK_TEST_STAGED"), reason="staged for the next round: not yet run on a GPU "
-                    "(set VFK_TEST_STAGED=1)")
 def test_nist_variant_set_on_the_device_equals_the_oracle_double(tmp_path_factory, monkeypatch):
     """BASELINE config 1 on the device: the files of tests/test_integration_nist.py through the `vafator` command
     line with the real engine == the same run with the device stages doubled by the oracle, line for line."""

@@ -76,7 +76,7 @@ def test_pileup_kernel_matches_golden(dev, path):
         params = device.make_params(min_mapq=prm["min_mq"], min_baseq=prm["min_bq"],
                                     include_ambiguous=prm["include_ambiguous"])
         for b, batch in enumerate(H.scenario_batches(sc)):
-            dreads = dev.upload_reads(device.pack_reads(batch, params))
+            dreads = dev.upload_reads(batch)
             buf = dev.pileup(dreads, dunits, params)
             dev.sync()
             counts = dev.to_host(buf, device.COUNTS_DTYPE, units.n_units)
@@ -94,7 +94,7 @@ def test_host_entry_point_and_epilogue(dev, path):
     power = vr.Power(purity={"s": 0.8}, ploidy={"s": 3.0})
     eaf = np.full(units.n_units, power.eaf("s"))
     for b, batch in enumerate(H.scenario_batches(sc)):
-        packed = device.pack_reads(batch, params, pinned=True)
+        packed = device.host_reads(batch, pinned=True)
         counts, stats = dev.annotate_host(packed, units, stop, params, eaf, power.fpr, power.error_rate)
         _check_counts(sc, run, b, recs, units, counts)
         for u in range(units.n_units):

@@ -33,9 +33,9 @@ def _setup(cfg):
     return batch, recs, units, stop, ounits
 
 
-def _gpu(dev, batch, units, stop, mq, bq, amb=True, columns=False):
+def _gpu(dev, batch, units, stop, mq, bq, amb=True):
     params = device.make_params(min_mapq=mq, min_baseq=bq, include_ambiguous=amb)
-    dreads = dev.upload_reads(device.pack_reads(batch, params, columns=columns))
+    dreads = dev.upload_reads(batch)
     buf = dev.pileup(dreads, dev.upload_units(units, stop), params)
     dev.sync()
     return dev.to_host(buf, device.COUNTS_DTYPE, units.n_units)
@@ -78,13 +78,11 @@ def test_gpu_matches_c_oracle(dev, name):
     assert want["ac_alt"].sum() > 0 and want["n_amb"].sum() >= 0
 
 
-@pytest.mark.parametrize("columns", [False, True], ids=["read_major", "columns"])
-def test_deep_column_block_path(dev, columns):
-    """Columns deeper than the warp path's u16 bins (> 32767 candidate reads) take the CTA-per-unit kernel -- also when
-    the units come off the column kernel's list and are located afterwards."""
+def test_deep_column_block_path(dev):
+    """Columns deeper than the warp path's u16 bins (> 32767 candidate reads) take the CTA-per-unit kernel."""
     cfg = synth.amplicon(n_tiles=2, depth_pairs=30000, snv_period=60, indel_period=120)
     batch, recs, units, stop, ounits = _setup(cfg)
-    got = _gpu(dev, batch, units, stop, 1, 30, columns=columns)
+    got = _gpu(dev, batch, units, stop, 1, 30)
     assert int(got["n_cand"].max()) > 32767
     want = c_oracle.pileup(batch.as_dict(), ounits, c_oracle.params(min_mapq=1, min_baseq=30))
     _compare(got, want)
@@ -98,7 +96,7 @@ def test_properties_at_scale(dev):
     recs = synth.variant_records(cfg)
     units = build_units(recs, cfg.contigs)
     params = device.make_params(min_mapq=1, min_baseq=30)
-    dreads = dev.upload_reads(device.pack_reads(batch, params))
+    dreads = dev.upload_reads(batch)
     def run(u):
         buf = dev.pileup(dreads, dev.upload_units(u, None), params)
         dev.sync()
@@ -126,14 +124,27 @@ def test_error_paths(dev):
     batch = synth.reads(cfg)
     with pytest.raises(ValueError):
         build_units([("nope", 5, "A", ["T"])], cfg.contigs)
+    # a batch that is not coordinate sorted: refused on the host by check_sorted, flagged by the kernels (VFK_ST_BADBATCH on
+    # every record through the device-pointer call, ValueError from the host entry point)
     bad = synth.reads(cfg)
-    bad.pos = bad.pos[::-1].copy()
+    bad.pos[:] = bad.pos[::-1].copy()
     with pytest.raises(ValueError):
-        device.pack_reads(bad, device.make_params())
+        bad.check_sorted()
+    units1 = build_units(synth.variant_records(cfg)[:50], cfg.contigs)
+    params = device.make_params()
+    buf = dev.pileup(dev.upload_reads(bad), dev.upload_units(units1, None), params)
+    dev.sync()
+    got = dev.to_host(buf, device.COUNTS_DTYPE, units1.n_units)
+    assert np.all(got["status"] & device.ST_BADBATCH) and got["dp"].max() == 0
+    with pytest.raises(ValueError):
+        dev.annotate_host(device.host_reads(bad), units1, None, params, np.full(units1.n_units, 0.5), 5e-7, 1e-3)
+    # the handle stays usable
+    good = dev.annotate_host(device.host_reads(batch), units1, None, params, np.full(units1.n_units, 0.5), 5e-7, 1e-3)[0]
+    assert int((good["status"] & device.ST_BADBATCH).max()) == 0 and good["dp"].max() > 0
     # empty unit list and empty read batch are fine
     units = build_units([], cfg.contigs)
     params = device.make_params()
-    dreads = dev.upload_reads(device.pack_reads(batch, params))
+    dreads = dev.upload_reads(batch)
     dev.pileup(dreads, dev.upload_units(units, None), params)
     dev.sync()
 
@@ -174,7 +185,7 @@ def test_degenerate_inputs(dev):
     params = device.make_params(min_mapq=1, min_baseq=30)
     empty = ReadBatch.from_records([], ["c1", "c2"])
     units = build_units([("c1", 1, "A", ["T"]), ("c2", 500, "AT", ["A"])], empty.contigs)
-    buf = dev.pileup(dev.upload_reads(device.pack_reads(empty, params)), dev.upload_units(units, None), params)
+    buf = dev.pileup(dev.upload_reads(empty), dev.upload_units(units, None), params)
     dev.sync()
     got = dev.to_host(buf, device.COUNTS_DTYPE, units.n_units)
     assert got["dp"].tolist() == [0, 0] and got["n_col"].tolist() == [0, 0] and got["med2"].max() == -1
@@ -183,18 +194,21 @@ def test_degenerate_inputs(dev):
             dict(qname="c", flag=0, tid=0, pos=0, mapq=60, cigar="10M", seq="ACGTACGTAC", qual=[40] * 10)]
     b = ReadBatch.from_records(recs, ["c1", "c2"])
     units = build_units([("c1", 1, "A", ["T"]), ("c1", 10, "C", ["G"]), ("c1", 11, "A", ["T"]), ("c2", 1, "A", ["T"])], b.contigs)
-    buf = dev.pileup(dev.upload_reads(device.pack_reads(b, params)), dev.upload_units(units, None), params)
+    buf = dev.pileup(dev.upload_reads(b), dev.upload_units(units, None), params)
     dev.sync()
     got = dev.to_host(buf, device.COUNTS_DTYPE, units.n_units)
     assert got["dp"].tolist() == [1, 1, 0, 0] and got["n_cover"].tolist() == [3, 3, 0, 0] and got["ac_ref"].tolist() == [1, 1, 0, 0]
 
 
-@pytest.mark.parametrize("pinned", [False, True], ids=["pageable", "pinned"])
-def test_host_entry_point_transfer_strategies(dev, pinned, monkeypatch):
-    """vfk_annotate_host moves a batch in one of several ways (units located on the host or by the locate
-    kernel; headers / payload staged or gathered from page-locked memory): every combination returns
-    exactly what the device-pointer entry points return, for VCF-ordered and for shuffled units."""
+@pytest.mark.parametrize("mode", ["pageable", "pinned", "pinned_stage_all"])
+def test_host_entry_point_transfer_strategies(mode, monkeypatch):
+    """vfk_annotate_host moves a batch in one of two ways -- page-locked arrays: the position-index inputs are copied, the
+    rest is read in place over PCIe; pageable arrays (or VFK_HOST_STAGE_ALL=1 when the handle is created): everything is
+    staged -- and returns exactly what the device-pointer entry points return, for VCF-ordered and for shuffled units."""
     from dataclasses import replace
+    if mode == "pinned_stage_all":
+        monkeypatch.setenv("VFK_HOST_STAGE_ALL", "1")
+    dev = device.Device(0)
     cfg = synth.wes(n_tiles=3000, indel_period=700, multiallelic_pct=5)
     batch, recs, units, stop, _ = _setup(cfg)
     rng = np.random.default_rng(11)
@@ -202,8 +216,8 @@ def test_host_entry_point_transfer_strategies(dev, pinned, monkeypatch):
     shuffled = replace(units, tid=units.tid[perm], pos=units.pos[perm], meta=units.meta[perm], length=units.length[perm],
                        seq_off=units.seq_off[perm], rec=units.rec[perm], alt_index=units.alt_index[perm])
     params = device.make_params(min_mapq=1, min_baseq=30)
-    packed = device.pack_reads(batch, params, pinned=pinned)
-    dreads = dev.upload_reads(packed)
+    host = device.host_reads(batch, pinned=mode != "pageable")
+    dreads = dev.upload_reads(host)
     eaf = np.full(units.n_units, 0.4)
     for u, s in ((units, stop), (shuffled, stop[perm])):
         counts_dev = dev.pileup(dreads, dev.upload_units(u, s), params)
@@ -211,93 +225,66 @@ def test_host_entry_point_transfer_strategies(dev, pinned, monkeypatch):
         dev.sync()
         want_c = dev.to_host(counts_dev, device.COUNTS_DTYPE, u.n_units)
         want_s = dev.to_host(stats_dev, device.STATS_DTYPE, u.n_units)
-        modes = [dict(VFK_HOST_LOCATE=a, VFK_ZERO_COPY_PAYLOAD=b, VFK_ZERO_COPY_HOT=c)
-                 for a in "01" for b in "01" for c in "01"] + [dict()]
-        for env in modes:
-            for k in ("VFK_HOST_LOCATE", "VFK_ZERO_COPY_PAYLOAD", "VFK_ZERO_COPY_HOT"):
-                monkeypatch.delenv(k, raising=False)
-            for k, v in env.items():
-                monkeypatch.setenv(k, v)
-            before = dev.zero_copy_batches()
-            got_c, got_s = dev.annotate_host(packed, u, s, params, eaf, 5e-7, 1e-3)
-            assert got_c.tobytes() == want_c.tobytes(), env
-            assert got_s.tobytes() == want_s.tobytes(), env
-            if env.get("VFK_ZERO_COPY_PAYLOAD") == "1":
-                assert (dev.zero_copy_batches() > before) == pinned
+        before = dev.transfer_stats()
+        got_c, got_s = dev.annotate_host(host, u, s, params, eaf, 5e-7, 1e-3)
+        after = dev.transfer_stats()
+        assert got_c.tobytes() == want_c.tobytes()
+        assert got_s.tobytes() == want_s.tobytes()
+        assert (after["zero_copy_batches"] - before["zero_copy_batches"]) == (1 if mode == "pinned" else 0)
+        assert (after["staged_batches"] - before["staged_batches"]) == (0 if mode == "pinned" else 1)
+        # two batches in flight through the double-buffered entry
+        c2 = [np.empty(u.n_units, device.COUNTS_DTYPE) for _ in range(3)]
+        s2 = [np.empty(u.n_units, device.STATS_DTYPE) for _ in range(3)]
+        tickets = []
+        for k in range(3):
+            if k >= 2:
+                dev.wait(tickets[k - 2])
+            tickets.append(dev.annotate_host_async(host, u, s, params, eaf, 5e-7, 1e-3, c2[k], s2[k]))
+        for t in tickets[1:]:
+            dev.wait(t)
+        for k in range(3):
+            assert c2[k].tobytes() == want_c.tobytes() and s2[k].tobytes() == want_s.tobytes()
+    dev.close()
 
 
-@pytest.mark.parametrize("layout", ["read_major", "columns"])
-def test_short_parity_campaign(layout):
-    """tests/fuzz_parity.py for ten seconds per layout: random read / CIGAR / pairing / variant mixes x thresholds."""
+def test_short_parity_campaign():
+    """tests/fuzz_parity.py for twenty seconds: random read / CIGAR / pairing / variant mixes x thresholds."""
     import os
     import subprocess
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
-    cmd = [sys.executable, os.path.join(here, "fuzz_parity.py"), "--seconds", "10", "--seed0", "5000"]
-    r = subprocess.run(cmd + (["--columns"] if layout == "columns" else []), capture_output=True, text=True, timeout=600)
+    cmd = [sys.executable, os.path.join(here, "fuzz_parity.py"), "--seconds", "20", "--seed0", "5000"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "fuzz ok" in r.stdout
 
 
 @pytest.mark.parametrize("name", ["wes", "wgs_indels", "amplicon_1000x", "noisy_cigars"])
-def test_column_store_kernel_matches_read_major_kernels(dev, name):
-    """With a column store in the batch SNV units are evaluated from contiguous sector runs (pileup_column_kernel);
-    every field but the diagnostic n_cand equals what the read-major kernels return, and both equal the oracle."""
+def test_register_pairing_matches_the_link_kernels(dev, name, monkeypatch):
+    """The register kernel pairs the overlapping mates of a column in registers (MATCH.ANY over the read-name ids of its
+    candidate reads); the list path replays htslib's name hash through the link kernels.  VFK_DEBUG_LINK_ALL=1 (read when a
+    handle is created) sends every unit's pairing through the link kernels: both must return the same records."""
     make, thresholds = CASES[name]
     batch, recs, units, stop, ounits = _setup(make())
+    monkeypatch.setenv("VFK_DEBUG_LINK_ALL", "1")
+    dev2 = device.Device(0)
+    monkeypatch.delenv("VFK_DEBUG_LINK_ALL")
     for mq, bq in thresholds[:2]:
-        params = device.make_params(min_mapq=mq, min_baseq=bq)
-        got = {}
-        for columns in (False, True):
-            dreads = dev.upload_reads(device.pack_reads(batch, params, columns=columns))
-            buf = dev.pileup(dreads, dev.upload_units(units, stop), params)
-            dev.sync()
-            got[columns] = dev.to_host(buf, device.COUNTS_DTYPE, units.n_units)
-        both = (got[False]["ac_ref"] > 0) & (got[False]["ac_alt"] > 0)  # the rank sums exist only then
-        for f in got[True].dtype.names:
+        a = _gpu(dev, batch, units, stop, mq, bq)
+        b = _gpu(dev2, batch, units, stop, mq, bq)
+        both = (a["ac_ref"] > 0) & (a["ac_alt"] > 0)  # the rank sums exist only then
+        for f in a.dtype.names:
             if f == "s2":
-                assert np.array_equal(got[True][f][both], got[False][f][both]), f
-            elif f != "n_cand":
-                assert np.array_equal(got[True][f], got[False][f]), f
-        _compare(got[True], c_oracle.pileup(batch.as_dict(), ounits, c_oracle.params(min_mapq=mq, min_baseq=bq)))
-
-
-def test_host_entry_point_reads_the_column_store_in_place(dev, monkeypatch):
-    """Page-locked batch with a column store: vfk_annotate_host gathers the sector runs straight from host memory and
-    returns exactly what the device-resident call returns; VFK_HOST_COLUMNS=0 falls back to the read-major arrays."""
-    for k in ("VFK_HOST_LOCATE", "VFK_ZERO_COPY_PAYLOAD", "VFK_ZERO_COPY_HOT", "VFK_HOST_COLUMNS"):
-        monkeypatch.delenv(k, raising=False)
-    cfg = synth.wes(n_tiles=3000, indel_period=700, multiallelic_pct=5)
-    batch, recs, units, stop, _ = _setup(cfg)
-    params = device.make_params(min_mapq=1, min_baseq=30)
-    packed = device.pack_reads(batch, params, pinned=True, columns=True)
-    dreads = dev.upload_reads(packed)
-    eaf = np.full(units.n_units, 0.4)
-    counts_dev = dev.pileup(dreads, dev.upload_units(units, stop), params)
-    stats_dev = dev.epilogue(units.n_units, counts_dev, dev.torch.as_tensor(eaf, device=dev.device), 5e-7, 1e-3)
-    dev.sync()
-    want_c = dev.to_host(counts_dev, device.COUNTS_DTYPE, units.n_units)
-    want_s = dev.to_host(stats_dev, device.STATS_DTYPE, units.n_units)
-    before = dev.column_batches()
-    got_c, got_s = dev.annotate_host(packed, units, stop, params, eaf, 5e-7, 1e-3)
-    assert dev.column_batches() == before + 1
-    assert got_c.tobytes() == want_c.tobytes() and got_s.tobytes() == want_s.tobytes()
-    monkeypatch.setenv("VFK_HOST_COLUMNS", "0")
-    alt_c, alt_s = dev.annotate_host(packed, units, stop, params, eaf, 5e-7, 1e-3)
-    assert dev.column_batches() == before + 1
-    both = (want_c["ac_ref"] > 0) & (want_c["ac_alt"] > 0)
-    for f in alt_c.dtype.names:
-        if f == "s2":
-            assert np.array_equal(alt_c[f][both], want_c[f][both]), f
-        elif f != "n_cand":
-            assert np.array_equal(alt_c[f], want_c[f]), f
-    assert alt_s.tobytes() == want_s.tobytes()
+                assert np.array_equal(a[f][both], b[f][both]), f
+            else:
+                assert np.array_equal(a[f], b[f]), f
+        _compare(b, c_oracle.pileup(batch.as_dict(), ounits, c_oracle.params(min_mapq=mq, min_baseq=bq)))
+    dev2.close()
 
 
 def test_listed_units_without_candidate_reads(dev):
-    """Indel units always reach the histogram kernel when the batch has a column store; one that lies where no read
-    is (between two targets) must not disturb the units processed after it by the same warp (regression: it used to
-    arm the TMA staging ring without consuming it)."""
+    """A unit that lies where no read is (between two targets) must not disturb the units processed after it by the same
+    warp, on the register path and on the list path alike (regression of round 1)."""
     cfg = synth.wes(n_tiles=1200, indel_period=60, snv_period=200)
     batch, recs, units, stop, ounits = _setup(cfg)
     contig = cfg.contigs[0]
@@ -311,64 +298,37 @@ def test_listed_units_without_candidate_reads(dev):
     for c, p, r, a in recs2:
         last[c] = p
     stop2 = np.asarray([last[recs2[i][0]] for i in units2.rec], np.int32)
-    params = device.make_params(min_mapq=1, min_baseq=30)
-    got = {}
-    for columns in (False, True):
-        for rep in range(3):  # the staging ring state carries over between launches of a persistent warp only within one
-            dreads = dev.upload_reads(device.pack_reads(batch, params, columns=columns))
-            buf = dev.pileup(dreads, dev.upload_units(units2, stop2), params)
-            dev.sync()
-            got[columns] = dev.to_host(buf, device.COUNTS_DTYPE, units2.n_units)
-    empty = got[False]["n_cover"] == 0
-    assert int(empty.sum()) >= 50 and int((got[False]["status"] & 3 != 0).sum()) > 100
-    both = (got[False]["ac_ref"] > 0) & (got[False]["ac_alt"] > 0)
-    for f in got[True].dtype.names:
-        if f == "s2":
-            assert np.array_equal(got[True][f][both], got[False][f][both])
-        elif f != "n_cand":
-            assert np.array_equal(got[True][f], got[False][f]), f
+    tid_of = {c: i for i, c in enumerate(cfg.contigs)}
+    ou2 = [(tid_of[recs2[i][0]], recs2[i][1], recs2[i][2], recs2[i][3][j], recs2[i][3][0], last[recs2[i][0]])
+           for i, j in zip(units2.rec, units2.alt_index)]
+    want = c_oracle.pileup(batch.as_dict(), ou2, c_oracle.params(min_mapq=1, min_baseq=30))
+    for rep in range(3):
+        got = _gpu(dev, batch, units2, stop2, 1, 30)
+        _compare(got, want)
+    empty = got["n_cover"] == 0
+    assert int(empty.sum()) >= 50 and int((got["status"] & 3 != 0).sum()) > 100
 
 
-STAGED_FLAGS = ("VFK_COL_TRANSPOSED", "VFK_LIST_SHALLOW", "VFK_MQ_SELECT")
-
-
-@pytest.mark.skipif(not __import__("os").environ.get("VFK_TEST_STAGED"), reason="staged kernel variants: not yet run on a GPU "
-                    "(set VFK_TEST_STAGED=1; DESIGN.md section 6)")
-@pytest.mark.parametrize("name", ["wes", "wgs_indels", "amplicon_1000x", "noisy_cigars"])
-@pytest.mark.parametrize("combo", [c for r in (1, 2, 3) for c in __import__("itertools").combinations(STAGED_FLAGS, r)],
-                         ids=lambda c: "+".join(x[4:] for x in c))
-def test_staged_variants_match_the_oracle(dev, monkeypatch, name, combo):
-    """Every combination of the staged switches (read per call by libvfk.so and by pack_reads) on the column-store
-    path: every field of every unit equals the C oracle."""
-    make, thresholds = CASES[name]
-    batch, recs, units, stop, ounits = _setup(make())
-    for f in STAGED_FLAGS:
-        monkeypatch.setenv(f, "1" if f in combo else "0")
-    for mq, bq in thresholds[:2]:
-        got = _gpu(dev, batch, units, stop, mq, bq, columns=True)
-        _compare(got, c_oracle.pileup(batch.as_dict(), ounits, c_oracle.params(min_mapq=mq, min_baseq=bq)))
-
-
-@pytest.mark.skipif(not __import__("os").environ.get("VFK_TEST_STAGED"), reason="staged host gather: not yet run on a GPU "
-                    "(set VFK_TEST_STAGED=1; DESIGN.md section 6)")
-@pytest.mark.parametrize("transposed", ["0", "1"], ids=["sector_form", "transposed_form"])
-def test_staged_host_gather_matches_the_resident_call(dev, monkeypatch, transposed):
-    """VFK_HOST_GATHER=1: the host entry point gathers every unit's column run (10 bytes per read) into one bulk copy;
-    results equal the device-resident call on the same batch, field for field (the diagnostic n_cand aside)."""
-    for k in ("VFK_HOST_LOCATE", "VFK_ZERO_COPY_PAYLOAD", "VFK_ZERO_COPY_HOT", "VFK_HOST_COLUMNS", "VFK_LIST_SHALLOW", "VFK_MQ_SELECT"):
-        monkeypatch.delenv(k, raising=False)
-    monkeypatch.setenv("VFK_COL_TRANSPOSED", transposed)
-    cfg = synth.wes(n_tiles=3000, indel_period=700, multiallelic_pct=5)
-    batch, recs, units, stop, ounits = _setup(cfg)
-    params = device.make_params(min_mapq=1, min_baseq=30)
-    packed = device.pack_reads(batch, params, pinned=True, columns=True)
-    eaf = np.full(units.n_units, 0.4)
-    monkeypatch.setenv("VFK_HOST_GATHER", "0")
-    want_c, want_s = dev.annotate_host(packed, units, stop, params, eaf, 5e-7, 1e-3)
-    monkeypatch.setenv("VFK_HOST_GATHER", "1")
-    got_c, got_s = dev.annotate_host(packed, units, stop, params, eaf, 5e-7, 1e-3)
-    for f in got_c.dtype.names:
-        if f != "n_cand":
-            assert np.array_equal(got_c[f], want_c[f]), f
-    assert got_s.tobytes() == want_s.tobytes()
-    _compare(got_c, c_oracle.pileup(batch.as_dict(), ounits, c_oracle.params(min_mapq=1, min_baseq=30)))
+def test_three_alignments_of_one_name_take_the_general_protocol(dev):
+    """A pair plus a supplementary record of the same name inside one column's window: htslib's hash pairs the first two
+    arrivals and leaves the third alone.  The register kernel hands such a column to the list path (link kernels)."""
+    from vafator_b200.batch import ReadBatch
+    q = lambda n, v=30: "".join(chr(v + 33) for _ in range(n))
+    R = []
+    for k in range(40):  # filler pairs so that the column is shallow but not trivial
+        R.append(dict(qname="f%d" % k, flag=99, tid=0, pos=100 + k % 7, mapq=60, cigar="30M", seq="ACGTACGTACGTACGTACGTACGTACGTAC", qual=q(30),
+                      mtid=0, mpos=115 + k % 7, isize=45))
+        R.append(dict(qname="f%d" % k, flag=147, tid=0, pos=115 + k % 7, mapq=60, cigar="30M", seq="ACGTACGTACGTACGTACGTACGTACGTAC", qual=q(30),
+                      mtid=0, mpos=100 + k % 7, isize=-45))
+    R.append(dict(qname="tri", flag=99, tid=0, pos=108, mapq=60, cigar="30M", seq="CACGTACGTACGCACGTACGTACGCACGTA", qual=q(30), mtid=0, mpos=112, isize=34))
+    R.append(dict(qname="tri", flag=2048 | 99, tid=0, pos=110, mapq=60, cigar="4S8M18S", seq="GGGGCGTACGTAGGGGGGGGGGGGGGGGGG", qual=q(30), mtid=0, mpos=112, isize=34))
+    R.append(dict(qname="tri", flag=147, tid=0, pos=112, mapq=60, cigar="30M", seq="TACGTACGGGGGTACGTACGGGGGTACGTA", qual=q(30), mtid=0, mpos=108, isize=-34))
+    R.sort(key=lambda d: d["pos"])
+    batch = ReadBatch.from_records(R, ["c"])
+    recs = [("c", p, "A", ["C"]) for p in range(109, 140)]
+    units = build_units(recs, ["c"])
+    stop = np.full(units.n_units, 139, np.int32)
+    ou = [(0, r[1], r[2], r[3][0], r[3][0], 139) for r in recs]
+    for mq, bq in ((0, 0), (1, 30), (0, 41)):
+        want = c_oracle.pileup(batch.as_dict(), ou, c_oracle.params(min_mapq=mq, min_baseq=bq))
+        _compare(_gpu(dev, batch, units, stop, mq, bq), want)

@@ -36,6 +36,11 @@ class OracleEngine(engine.Engine):
         c["status"] = units.meta & 3
         return c
 
+    def submit(self, batch, units, stop, eaf_units):
+        """Test double of the fused device call (vfk_annotate_host_async): oracle counts + scipy statistics per unit."""
+        counts = self.pileup(batch, units, stop) if units.n_units else np.zeros(0, device.COUNTS_DTYPE)
+        return (None, counts, self.epilogue(counts, eaf_units))
+
     def values(self, batch, units, stop):
         """Test double of vfk_pileup_values: the per-read lists from the Python restatement."""
         from oracle import htslib_pileup as hp
@@ -111,10 +116,9 @@ def test_info_strings_match_reference(path):
 class FileOracleEngine(OracleEngine):
     """Constructor of engine.Engine, device stages of OracleEngine -- stands in for Engine inside Annotator."""
     calls = []
-    prepacked = 0
 
     def __init__(self, device_index=0, min_mapq=0, min_baseq=29, include_ambiguous=True, fpr=5e-7, error_rate=1e-3,
-                 devices=None, columns=True):
+                 devices=None):
         OracleEngine.__init__(self, min_mapq, min_baseq, include_ambiguous, fpr, error_rate)
         self.released = 0
 
@@ -126,11 +130,6 @@ class FileOracleEngine(OracleEngine):
     def release_reads(self, batches=None):
         self.released += 1
         engine.Engine.release_reads(self, batches)
-
-    def prepack(self, batch):
-        self.columns = True
-        engine.Engine.prepack(self, batch)
-        FileOracleEngine.prepacked += 1
 
 
 def _write_inputs(tmp_path, sc, indexed):
@@ -194,7 +193,7 @@ def test_annotator_streams_chromosome_groups(tmp_path, monkeypatch, name, indexe
     assert [c[0] for c in FileOracleEngine.calls] == groups
     assert sum(c[1] for c in FileOracleEngine.calls) == len(chroms)
     assert a.engine.released == (len(groups) + 1 if indexed else 1)
-    assert not a.engine.__dict__.get("_packed")  # prepacked host copies are gone with their group
+    assert not a.engine.__dict__.get("_hreads") or not indexed  # the wrappers of a group's batches are gone with the group
     if indexed and len(groups) > 1:  # a group's batches hold that chromosome's region only
         whole = [len([r for r in sc["bams"][b] if r["tid"] >= 0]) for idx in sc["samples"].values() for b in idx]
         assert all(n <= w for c in FileOracleEngine.calls for n, w in zip(c[2], whole))
@@ -222,6 +221,10 @@ class RandomCountsEngine(engine.Engine):
         c["s2"] = rng.integers(0, 500, (n, 3))
         c["status"] = units.meta & 3
         return c
+
+    def submit(self, batch, units, stop, eaf_units):
+        counts = self.pileup(batch, units, stop)
+        return (None, counts, self.epilogue(counts, eaf_units))
 
     def epilogue(self, counts, eaf):
         n, rng = len(counts), self.rng

@@ -30,23 +30,22 @@ def _case():
 
 
 def _oracle_compute(recs, contigs):
-    def compute(sub, sub_mate, sub_units, sub_stop):
+    def compute(sub, sub_units, sub_stop):
+        # every shard is a self-contained canonical batch: the mates are paired among the reads of the slice, as the kernels do
         ou = [(int(t), int(p) + 1, recs[i][2], recs[i][3][j], recs[i][3][0], int(s))
               for t, p, i, j, s in zip(sub_units.tid, sub_units.pos, sub_units.rec, sub_units.alt_index, sub_stop)]
-        partner = np.where(sub_mate == sharding.NO_MATE, -1, (sub_mate & 0x7FFFFFFF).astype(np.int64))
-        return c_oracle.pileup(sub.as_dict(), ou, c_oracle.params(min_mapq=1, min_baseq=30), mate=partner)
+        return c_oracle.pileup(sub.as_dict(), ou, c_oracle.params(min_mapq=1, min_baseq=30))
     return compute
 
 
 def test_sharded_equals_unsharded_single_process():
     cfg, batch, recs, units, stop = _case()
     prm = device.make_params(min_mapq=1, min_baseq=30)
-    mate = device.link_mates(batch, prm)
     passes = device.read_passes(batch, prm)
     compute = _oracle_compute(recs, cfg.contigs)
-    whole = compute(batch, mate, units, stop)
+    whole = compute(batch, units, stop)
     for n_shards in (1, 2, 7, 64):
-        got = sharding.run_sharded(batch, units, stop, mate, passes, n_shards, 0, 1, compute, lambda x: [x])
+        got = sharding.run_sharded(batch, units, stop, passes, n_shards, 0, 1, compute, lambda x: [x])
         assert got.tobytes() == whole.tobytes(), n_shards
     shards = sharding.plan_shards(batch, units, 8, passes, stop)
     assert shards[0].unit_lo == 0 and shards[-1].unit_hi == units.n_units
@@ -61,7 +60,6 @@ def _worker(rank, world, port, out_path):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     cfg, batch, recs, units, stop = _case()
     prm = device.make_params(min_mapq=1, min_baseq=30)
-    mate = device.link_mates(batch, prm)
     passes = device.read_passes(batch, prm)
 
     def gather(obj):
@@ -69,9 +67,9 @@ def _worker(rank, world, port, out_path):
         dist.gather_object(obj, box, dst=0)
         return box
 
-    got = sharding.run_sharded(batch, units, stop, mate, passes, 6, rank, world, _oracle_compute(recs, cfg.contigs), gather)
+    got = sharding.run_sharded(batch, units, stop, passes, 6, rank, world, _oracle_compute(recs, cfg.contigs), gather)
     if rank == 0:
-        whole = _oracle_compute(recs, cfg.contigs)(batch, mate, units, stop)
+        whole = _oracle_compute(recs, cfg.contigs)(batch, units, stop)
         np.save(out_path, np.asarray([got.tobytes() == whole.tobytes(), len(got)], np.int64))
     dist.barrier()
     dist.destroy_process_group()

@@ -67,7 +67,7 @@ class Annotator(object):
         import torch
         n_dev = max(1, min(int(num_processes), torch.cuda.device_count() - device)) if torch.cuda.is_available() else 1
         self._single_device = n_dev == 1
-        # cumulative seconds per stage of run(): fetch (decode + pack, background thread), annotate (device stages +
+        # cumulative seconds per stage of run(): fetch (decode, background thread), annotate (device stages +
         # INFO formatting), write; wall = the whole run
         self.timings = {"fetch": 0.0, "annotate": 0.0, "write": 0.0, "wall": 0.0, "records": 0, "reads": 0}
         self.engine = Engine(device, devices=list(range(device, device + n_dev)), min_mapq=mapping_qual_thr, min_baseq=base_call_qual_thr,
@@ -124,13 +124,6 @@ class Annotator(object):
         positions = [v.POS for v in variants]
         bams = OrderedDict((s, [fetch_group(r, chrom, positions[0], positions[-1], positions, self.engine.params) for r in readers])
                            for s, readers in self.bam_readers.items())
-        # host-side packing too happens here, off the critical path -- for the transient batches of indexed BAMs (a
-        # whole-file batch is packed once, when first used) on a single device (sharded runs pack per shard)
-        if self._single_device:
-            for s, readers in self.bam_readers.items():
-                for r, b in zip(readers, bams[s]):
-                    if r.index_path and b.n_reads:
-                        self.engine.prepack(b)
         self.timings["fetch"] += time.perf_counter() - t0
         self.timings["reads"] += sum(b.n_reads for batches in bams.values() for b in batches)
         return bams

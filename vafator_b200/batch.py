@@ -12,8 +12,8 @@
     qname_hash[n] u32 (khash X31 of the read name; htslib's overlap tie-break hashes it)
 
 It replaces what pysam.AlignmentFile hands to htslib's pileup engine at
-vafator/pileups.py:71-80.  `vafator_b200.device.pack_reads` turns it into the HBM layout the
-kernels read (DESIGN.md "Data layout").
+vafator/pileups.py:71-80, and it is what crosses the C ABI (include/vfk.h vfk_read_batch): the kernels derive
+everything else -- reference spans, the position index, CIGAR shapes, mate pairing -- on the device.
 
 `VariantUnits` is the device-facing form of the VCF records of vafator/pileups.py:133-151:
 one *unit* per (record, ALT allele) that needs its own column evaluation.
@@ -75,15 +75,50 @@ class ReadBatch:
     qname_id: np.ndarray
     qname_hash: np.ndarray
     contig_lengths: Optional[np.ndarray] = None
+    pinned: bool = False  # the arrays already live in page-locked memory (bamio / synth with pinned=True)
 
     @property
     def n_reads(self) -> int:
         return int(self.pos.shape[0])
 
+    # ---- batch metadata a decoder has at hand when it finishes a batch (computed once, cached) ----
+    def _meta(self):
+        m = self.__dict__.get("_meta_cache")
+        if m is None:
+            tid = self.tid
+            n = self.n_reads
+            n_placed = int(np.searchsorted(-(tid >= 0).astype(np.int8), 0, side="left")) if n else 0  # placed reads come first
+            if n and (np.any(tid[:n_placed] < 0) or np.any(tid[n_placed:] >= 0)):
+                raise ValueError("unplaced reads must come last in a coordinate-sorted batch")
+            t = tid[:n_placed]
+            if n_placed and np.any(t[1:] < t[:-1]):
+                raise ValueError("read batch is not coordinate sorted")
+            if n_placed and int(t[-1]) >= len(self.contigs):
+                raise ValueError("read tid outside the contig table")
+            contig_off = np.searchsorted(t, np.arange(len(self.contigs) + 1), side="left").astype(np.int64)
+            max_l = int(self.l_qseq[:n_placed].max()) if n_placed else 0
+            m = self.__dict__["_meta_cache"] = (n_placed, contig_off, max_l)
+        return m
+
+    @property
+    def n_placed(self) -> int:
+        return self._meta()[0]
+
+    @property
+    def contig_off(self) -> np.ndarray:
+        """[n_contigs + 1]: the reads of contig t are [off[t], off[t+1])."""
+        return self._meta()[1]
+
+    @property
+    def max_l_qseq(self) -> int:
+        return self._meta()[2]
+
     def as_dict(self) -> Dict[str, np.ndarray]:
         return {k: getattr(self, k) for k in _FIELDS}
 
     def check_sorted(self) -> None:
+        if self.n_reads and np.any(self.pos[self.tid >= 0] < 0):
+            raise ValueError("placed read with a negative start position")
         if self.n_reads < 2:
             return
         key = self.tid.astype(np.int64) * (1 << 32) + self.pos.astype(np.int64)
@@ -93,6 +128,8 @@ class ReadBatch:
             raise ValueError("read batch is not coordinate sorted")
         if np.any(~mapped[:-1] & mapped[1:]):
             raise ValueError("unplaced reads must come last in a coordinate-sorted batch")
+        if np.any(self.pos[mapped] < 0):
+            raise ValueError("placed read with a negative start position")
 
     @staticmethod
     def from_records(records: Sequence[dict], contigs: Sequence[str]) -> "ReadBatch":
@@ -118,6 +155,8 @@ class ReadBatch:
         qual = bytearray()
         for i, r in enumerate(records):
             tid[i], pos[i], flag[i], mapq[i] = r["tid"], r["pos"], r["flag"], r["mapq"]
+            if tid[i] >= 0 and pos[i] < 0:
+                raise ValueError("placed read %r with a negative start position" % (r.get("qname"),))
             mtid[i], mpos[i], isize[i] = r.get("mtid", -1), r.get("mpos", -1), r.get("isize", 0)
             c = r["cigar"]
             if isinstance(c, str):

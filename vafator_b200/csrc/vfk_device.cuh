@@ -1,4 +1,9 @@
-// vfk_device.cuh -- device-side building blocks shared by the pileup kernels (sm_100a).
+// vfk_device.cuh -- device-side building blocks shared by the kernels (sm_100a).
+//
+// The kernels read the CANONICAL columnar read batch (include/vfk.h: the fields of the decoded BAM records,
+// array by array) plus three words per read that prep_kernel (vfk_prep.cu) derives from it on the device in
+// every call: the reference end, the CIGAR shape word and -- per block of reads -- the running maximum of the
+// ends, which is the position index.  Nothing is prepared on the host.
 //
 // What is evaluated per (variant column, read) pair follows pysam 0.21.0 / htslib 1.17 as
 // vafator drives them (vafator/pileups.py:71-80, :184-362):
@@ -18,20 +23,45 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
 enum : int { OP_M = 0, OP_I = 1, OP_D = 2, OP_N = 3, OP_S = 4, OP_H = 5, OP_P = 6, OP_EQ = 7, OP_X = 8 };
 enum : unsigned { F_PAIRED = 1, F_PROPER = 2, F_UNMAP = 4, F_MUNMAP = 8 };
 
+// CIGAR shapes (the `ev` word prep_kernel writes per read):
+//   SHAPE_SIMPLE     ev == EV_SIMPLE: the CIGAR is one M/=/X op covering the whole read (qpos = column - pos)
+//   SHAPE_GENERAL    ev == EV_GENERAL: any CIGAR, walked op by op
+//   SHAPE_ONE_EVENT  [H][S] M [ I|D|N  M ] [S][H] -- clips and at most one event between two aligned blocks,
+//                    resolved without a loop from ev = leading soft clip | first block length << 12 |
+//                    EVK_* << 24 | event length << 26 (lengths < 4096 / < 64, else the read is GENERAL)
+constexpr uint32_t SHAPE_SIMPLE = 0u, SHAPE_GENERAL = 1u, SHAPE_ONE_EVENT = 2u;
+constexpr uint32_t EV_SIMPLE = 0u, EV_GENERAL = 0xFFFFFFFFu;
+constexpr int EVK_NONE = 0, EVK_INS = 1, EVK_DEL = 2, EVK_SKIP = 3;
+constexpr int PREP_BLOCK = 128;  // reads per entry of the block-level position index
+
 struct ReadsDev {
-    const uint4 *__restrict__ hot;
-    const uint4 *__restrict__ cold;
-    const uint32_t *__restrict__ mate;
-    const int2 *__restrict__ sb;  // {start, back}
+    // canonical arrays (device memory, or page-locked host memory read in place)
+    const int32_t *__restrict__ pos;  // device copy when the caller's array lives on the host (the locate pass searches it)
+    const uint16_t *__restrict__ flag;
+    const uint8_t *__restrict__ mapq;
+    const int32_t *__restrict__ l_qseq;
+    const int32_t *__restrict__ n_cigar;
+    const int64_t *__restrict__ cigar_off;
+    const int64_t *__restrict__ seq_off;
+    const int64_t *__restrict__ qual_off;
     const uint32_t *__restrict__ cigar;
-    const uint8_t *__restrict__ payload;
+    const uint8_t *__restrict__ seq;
+    const uint8_t *__restrict__ qual;
+    const int32_t *__restrict__ mtid;
+    const int32_t *__restrict__ mpos;
+    const int32_t *__restrict__ isize;
+    const uint64_t *__restrict__ qname_id;
+    const uint32_t *__restrict__ qname_hash;
     const int64_t *__restrict__ contig_off;
     int64_t n_reads;
+    int64_t n_cigar_words, n_seq_bytes, n_qual_bytes;
     int32_t n_contigs;
-    // column store (vfk.h), nullptr when absent
-    const int64_t *__restrict__ col_wbase;
-    const uint32_t *__restrict__ col_off;
-    const uint32_t *__restrict__ col_sectors;  // 8 words per sector
+    // derived per call by prep_kernel / scan_kernel (device memory)
+    const int32_t *__restrict__ end;       // pos + reference bases consumed
+    const uint32_t *__restrict__ ev;       // CIGAR shape word
+    const int64_t *__restrict__ blk_incl;  // [n_blocks + 1]: entry b + 1 = max over the reads of blocks 0..b of tid << 32 | end
+    // overlap partners of the reads inside the windows of listed units (link kernels): partner | tie_break << 31
+    const uint32_t *__restrict__ mate;
 };
 
 struct UnitsDev {
@@ -75,6 +105,8 @@ constexpr uint32_t PK_REF = 1u << 28, PK_ALT = 1u << 29;
 constexpr uint32_t FL_COVERS = 1u, FL_IN_COL = 1u << 8, FL_IN_DP = 1u << 16, FL_AMBIGUOUS = 1u << 24;
 struct Eval {
     uint32_t pk, fl, alt;
+    uint32_t hard;  // the read sits in a deletion / skip at the column: its base-quality filter looks at the NEXT read base, whose
+                    // overlap adjustment depends on the push timing of its mate -- only the list path (mate[] + next_pushed) decides
 };
 
 // decoded view used by the histogram kernels
@@ -99,49 +131,38 @@ __device__ __forceinline__ Contribution decode(const Eval &e) {
 __device__ __forceinline__ bool is_ref_op(int op) { return op == OP_M || op == OP_D || op == OP_N || op == OP_EQ || op == OP_X; }
 __device__ __forceinline__ bool is_aln_op(int op) { return op == OP_M || op == OP_EQ || op == OP_X; }
 
-// ---- payload addressing: 8-byte granules of 5 query positions, 12 bits each (quality in the low 8
-// bits, BAM base code in the next 4); 4 granules per 32-byte sector.  One (read, column) lookup is ONE
-// 64-bit load of one sector.
-#ifndef VFK_GATHER_LD
-#define VFK_GATHER_LD 0
-#endif
-// 64-bit gather load; the variants exist to measure how the cache policy changes DRAM traffic
-__device__ __forceinline__ unsigned long long gather_ld64(const unsigned long long *p) {
-#if VFK_GATHER_LD == 1
-    unsigned long long v;
-    asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(v) : "l"(p));
-    return v;
-#elif VFK_GATHER_LD == 2
-    return __ldcs(p);
-#elif VFK_GATHER_LD == 3
-    return __ldcv(p);
-#elif VFK_GATHER_LD == 4
-    unsigned long long v;
-    asm volatile("ld.global.L1::no_allocate.L2::evict_first.b64 %0, [%1];" : "=l"(v) : "l"(p));
-    return v;
-#else
-    return __ldg(p);
-#endif
-}
+// ---- base / quality lookup: word = quality | BAM 4-bit base code << 8, straight from the canonical qual / seq pools.
 // The load and the extraction are separate so that a caller can have several lookups in flight before
-// it consumes the first one (own base + mate base: one DRAM round trip instead of two).
+// it consumes the first one (own base + mate base: one round trip instead of two).
 struct PayLoad {
-    unsigned long long granule;
-    uint32_t shift;
+    uint32_t q, s;  // the quality byte, the sequence byte
+    uint32_t odd;
 };
-__device__ __forceinline__ PayLoad pay_issue(const uint8_t *__restrict__ payload, uint32_t pay, uint32_t q) {
-    const uint32_t g = q / 5u, r = q - g * 5u;
+__device__ __forceinline__ PayLoad pay_issue(const ReadsDev &R, uint32_t i, uint32_t q) {
     PayLoad l;
-    l.granule = gather_ld64(reinterpret_cast<const unsigned long long *>(payload + ((size_t)pay << 5)) + g);
-    l.shift = 12u * r;
+    l.q = (uint32_t)__ldg(R.qual + __ldg(R.qual_off + i) + q);
+    l.s = (uint32_t)__ldg(R.seq + __ldg(R.seq_off + i) + (q >> 1));
+    l.odd = q & 1u;
     return l;
 }
-__device__ __forceinline__ uint32_t pay_word(const PayLoad &l) { return (uint32_t)(l.granule >> l.shift) & 0xFFFu; }
-__device__ __forceinline__ uint32_t pay_lookup(const uint8_t *__restrict__ payload, uint32_t pay, uint32_t q) {
-    return pay_word(pay_issue(payload, pay, q));
-}
+__device__ __forceinline__ uint32_t pay_word(const PayLoad &l) { return l.q | ((l.odd ? (l.s & 15u) : (l.s >> 4)) << 8); }
+__device__ __forceinline__ uint32_t pay_lookup(const ReadsDev &R, uint32_t i, uint32_t q) { return pay_word(pay_issue(R, i, q)); }
 __device__ __forceinline__ int word_qual(uint32_t w) { return (int)(w & 0xFFu); }
 __device__ __forceinline__ int word_base(uint32_t w) { return (int)(w >> 8); }
+
+// ---- per-read records assembled from the arrays.  hot = {pos, span, flag | mapq << 16 | shape << 24, read index},
+// cold = {cigar_off, n_cigar, l_qseq, one-event word}: the shapes the evaluation code below is written against.
+__device__ __forceinline__ uint32_t shape_of_ev(uint32_t ev) { return ev == EV_SIMPLE ? SHAPE_SIMPLE : ev == EV_GENERAL ? SHAPE_GENERAL : SHAPE_ONE_EVENT; }
+__device__ __forceinline__ uint4 load_hot(const ReadsDev &R, int64_t i) {
+    const int32_t p = __ldg(R.pos + i);
+    const uint32_t fm = (uint32_t)__ldg(R.flag + i) | ((uint32_t)__ldg(R.mapq + i) << 16);
+    return make_uint4((uint32_t)p, (uint32_t)(__ldg(R.end + i) - p), fm | (shape_of_ev(__ldg(R.ev + i)) << 24), (uint32_t)i);
+}
+__device__ __forceinline__ uint4 load_cold(const ReadsDev &R, int64_t i) {
+    const uint32_t ev = __ldg(R.ev + i);
+    return make_uint4((uint32_t)__ldg(R.cigar_off + i), (uint32_t)__ldg(R.n_cigar + i), (uint32_t)__ldg(R.l_qseq + i),
+                      ev == EV_GENERAL ? 0u : ev);
+}
 
 // BAM 4-bit codes "=ACMGRSVTWYHKDBN": everything but = A C G T is IUPAC-ambiguous (vafator/constants.py:5)
 __device__ __forceinline__ bool code_is_ambiguous(int c) { return ((0x0117u >> c) & 1u) == 0u; }
@@ -232,17 +253,17 @@ __device__ __forceinline__ Resolved resolve_one_event(int32_t rpos, const uint4 
     Resolved o;
     const int lead = (int)(cold.w & 0xFFFu), m1 = (int)((cold.w >> 12) & 0xFFFu), ev = (int)((cold.w >> 24) & 3u), e = (int)(cold.w >> 26);
     const int d = col - rpos;                   // 0 <= d < span (the caller checked)
-    const int gap = ev >= VFK_EV_DEL ? e : 0;   // D / N consume reference
+    const int gap = ev >= EVK_DEL ? e : 0;   // D / N consume reference
     o.covered = true; o.l_qseq = (int)cold.z; o.is_del = false; o.is_refskip = false; o.indel = 0;
     if (d < m1) {
         o.qpos = lead + d;
-        if (d == m1 - 1) o.indel = ev == VFK_EV_INS ? e : ev == VFK_EV_DEL ? -e : 0;
+        if (d == m1 - 1) o.indel = ev == EVK_INS ? e : ev == EVK_DEL ? -e : 0;
     } else if (d < m1 + gap) {
         o.qpos = lead + m1;
         o.is_del = true;
-        o.is_refskip = ev == VFK_EV_SKIP;
+        o.is_refskip = ev == EVK_SKIP;
     } else {
-        o.qpos = lead + m1 + (ev == VFK_EV_INS ? e : 0) + (d - m1 - gap);
+        o.qpos = lead + m1 + (ev == EVK_INS ? e : 0) + (d - m1 - gap);
     }
     return o;
 }
@@ -271,12 +292,44 @@ __device__ __forceinline__ int32_t refpos_of_query(const ReadsDev &R, int32_t rp
 // first read at or after `from` (same contig, start < stop) that the reference would have pushed
 __device__ __forceinline__ int64_t next_pushed(const ReadsDev &R, const vfk_params &P, int64_t from, int64_t c1, int32_t stop) {
     for (int64_t j = from; j < c1; ++j) {
-        uint4 h = __ldg(R.hot + j);
-        if ((int32_t)h.x >= stop) break;
-        if (read_passes(h.z, P)) return j;
+        if (__ldg(R.pos + j) >= stop) break;
+        if (read_passes((uint32_t)__ldg(R.flag + j) | ((uint32_t)__ldg(R.mapq + j) << 16), P)) return j;
     }
     return -1;
 }
+
+// ---- htslib overlap_push (sam.c): which records reach the name hash, and which store themselves ----
+__device__ __forceinline__ uint32_t wang_hash(uint32_t k) {
+    k += ~(k << 15); k ^= (k >> 10); k += (k << 3); k ^= (k >> 6); k += ~(k << 11); k ^= (k >> 16);
+    return k;
+}
+__device__ __forceinline__ uint32_t fm_of(const ReadsDev &R, int64_t i) { return (uint32_t)__ldg(R.flag + i) | ((uint32_t)__ldg(R.mapq + i) << 16); }
+
+// the column the engine stands on while record i is pushed: the start of the record pushed just before it
+// (bam_plp_push appends iff end > that column); the first pushed record of a contig sees its own start
+__device__ __forceinline__ int32_t push_column(const ReadsDev &R, const vfk_params &P, int64_t i, int64_t c0) {
+    for (int64_t j = i - 1; j >= c0; --j)
+        if (read_passes(fm_of(R, j), P)) return __ldg(R.pos + j);
+    return __ldg(R.pos + i);
+}
+// does record i reach the name hash (overlap_push past its early exits)?
+__device__ __forceinline__ bool reaches_hash(const ReadsDev &R, const vfk_params &P, int64_t i, int32_t tid, int32_t column) {
+    const uint32_t fm = fm_of(R, i);
+    if (!read_passes(fm, P)) return false;
+    const int32_t end = __ldg(R.end + i);
+    if (end <= column) return false;  // never appended to the buffer
+    if ((fm & F_MUNMAP) || !(fm & F_PROPER)) return false;
+    const int32_t mt = __ldg(R.mtid + i);
+    if (mt >= 0 && mt != tid) return false;
+    const long long isz = (long long)__ldg(R.isize + i);
+    if ((isz < 0 ? -isz : isz) >= 2LL * __ldg(R.l_qseq + i) && __ldg(R.mpos + i) >= end) return false;
+    return true;
+}
+__device__ __forceinline__ bool stores_itself(const ReadsDev &R, int64_t i) {
+    const int32_t mp = __ldg(R.mpos + i);
+    return mp >= __ldg(R.pos + i) || ((__ldg(R.flag + i) & F_PAIRED) && mp == -1);
+}
+
 
 // Quality of query base q of read i as the reference sees it when column `col` is emitted:
 // htslib tweak_overlap_quality has run for the pair iff the second mate has been pushed, i.e. it
@@ -291,11 +344,11 @@ __device__ __forceinline__ int tweaked_quality(const ReadsDev &R, const vfk_para
     const uint32_t flag = hot.z & 0xFFFFu;
     bool paired = P.ignore_overlaps && (flag & F_PROPER) && !(flag & F_MUNMAP) && mw != VFK_NO_MATE;
     PayLoad mate;
-    mate.granule = 0ull; mate.shift = 0u;
+    mate.q = mate.s = mate.odd = 0u;
     int64_t m = 0;
     if (paired) {
         m = (int64_t)(mw & 0x7FFFFFFFu);
-        const uint4 mh = __ldg(R.hot + m);
+        const uint4 mh = load_hot(R, m);
         if (m > i && (int32_t)mh.x > U.col)  // the mate starts beyond the column: it can only matter to a base further on
             paired = !q_is_column_base && next_pushed(R, P, U.hi, U.c1, U.stop) == m;
         int32_t rp = -1;
@@ -304,19 +357,19 @@ __device__ __forceinline__ int tweaked_quality(const ReadsDev &R, const vfk_para
         paired = paired && rp >= (int32_t)mh.x && rp < (int32_t)mh.x + (int32_t)mh.y;  // rp < 0: not an aligned base
         if (paired) {
             int mq_index, ml;
-            if ((mh.z >> 24) == VFK_SHAPE_SIMPLE) {
+            if ((mh.z >> 24) == SHAPE_SIMPLE) {
                 mq_index = rp - (int32_t)mh.x;
                 ml = (int)mh.y;
             } else {
-                const uint4 mc = __ldg(R.cold + m);
-                const Resolved mr = (mh.z >> 24) == VFK_SHAPE_ONE_EVENT ? resolve_one_event((int32_t)mh.x, mc, rp)
+                const uint4 mc = load_cold(R, m);
+                const Resolved mr = (mh.z >> 24) == SHAPE_ONE_EVENT ? resolve_one_event((int32_t)mh.x, mc, rp)
                                                                         : resolve_general(R, (int32_t)mh.x, mc, rp);
                 paired = mr.covered && !mr.is_del;
                 mq_index = mr.qpos;
                 ml = mr.l_qseq;
             }
             paired = paired && mq_index < ml;
-            if (paired) mate = pay_issue(R.payload, mh.w, (uint32_t)mq_index);
+            if (paired) mate = pay_issue(R, mh.w, (uint32_t)mq_index);
         }
     }
     my_word = pay_word(own);
@@ -373,7 +426,7 @@ __device__ __forceinline__ uint32_t insertion_hits(const ReadsDev &R, const uint
             // and any leading soft clip) against ALT[0][1:]  -- SURVEY.md A.5
             bool ok = rel + U.len <= qlen;
             for (int t = 0; ok && t < U.len; ++t)
-                ok = word_base(pay_lookup(R.payload, hot.w, (uint32_t)(qs + rel + t))) == (int)U.ins[t];
+                ok = word_base(pay_lookup(R, hot.w, (uint32_t)(qs + rel + t))) == (int)U.ins[t];
             hits += ok ? 1u : 0u;
         }
     }
@@ -405,13 +458,13 @@ __device__ __forceinline__ uint32_t deletion_hits(const ReadsDev &R, const uint4
 __device__ __forceinline__ Eval evaluate_packed(const ReadsDev &R, const vfk_params &P, const Unit &U, int64_t i, const uint4 &hot,
                                                 uint32_t mw) {
     Eval o;
-    o.pk = 0u; o.fl = 0u; o.alt = 0u;
+    o.pk = 0u; o.fl = 0u; o.alt = 0u; o.hard = 0u;
     const int32_t rpos = (int32_t)hot.x;
     if ((uint32_t)(U.col - rpos) >= hot.y) return o;  // col < pos wraps to a huge unsigned
     o.fl = FL_COVERS;
     if (!read_passes(hot.z, P)) return o;
     const uint32_t shape = hot.z >> 24;
-    const bool general = shape != VFK_SHAPE_SIMPLE;
+    const bool general = shape != SHAPE_SIMPLE;
     uint4 cold = make_uint4(0, 0, 0, 0);
     Resolved r;
     if (!general) {
@@ -419,8 +472,8 @@ __device__ __forceinline__ Eval evaluate_packed(const ReadsDev &R, const vfk_par
         r.qpos = U.col - rpos;
         r.l_qseq = (int)hot.y;
     } else {
-        cold = __ldg(R.cold + i);
-        if (shape == VFK_SHAPE_ONE_EVENT) {
+        cold = load_cold(R, i);
+        if (shape == SHAPE_ONE_EVENT) {
             r = resolve_one_event(rpos, cold, U.col);
         } else {
             r = resolve_general(R, rpos, cold, U.col);
@@ -428,9 +481,10 @@ __device__ __forceinline__ Eval evaluate_packed(const ReadsDev &R, const vfk_par
         }
     }
     o.fl |= FL_IN_COL;
+    o.hard = (r.is_del && r.qpos < r.l_qseq) ? 1u : 0u;
     PayLoad own;
-    own.granule = 0ull; own.shift = 0u;
-    if (r.qpos < r.l_qseq) own = pay_issue(R.payload, hot.w, (uint32_t)r.qpos);
+    own.q = own.s = own.odd = 0u;
+    if (r.qpos < r.l_qseq) own = pay_issue(R, hot.w, (uint32_t)r.qpos);
     uint32_t my_word;
     const int q = tweaked_quality(R, P, U, i, hot, mw, cold, general, r.qpos, r.l_qseq, !r.is_del, own, my_word);
     if (q < P.min_baseq) return o;  // pysam pileup_base_qual_skip
@@ -462,7 +516,7 @@ __device__ __forceinline__ Contribution evaluate(const ReadsDev &R, const vfk_pa
     return decode(evaluate_packed(R, P, U, i, hot, mw));
 }
 __device__ __forceinline__ Contribution evaluate(const ReadsDev &R, const vfk_params &P, const Unit &U, int64_t i) {
-    return evaluate(R, P, U, i, __ldg(R.hot + i), __ldg(R.mate + i));
+    return evaluate(R, P, U, i, load_hot(R, i), __ldg(R.mate + i));
 }
 
 // ---- bulk asynchronous copies (TMA, cp.async.bulk) completed on an mbarrier ----

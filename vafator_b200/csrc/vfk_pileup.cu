@@ -4,23 +4,20 @@
 // column x ALT allele) find the overlapping reads, classify them, and reduce the per-allele
 // MQ / BQ / read-position distributions to integers: counts, twice-the-median, and twice the
 // ALT mid-rank sum that scipy.stats.ranksums would compute (vafator/rank_sum_test.py:11).
+// Every kernel reads the canonical read arrays (include/vfk.h) and the per-read words prep_kernel derived
+// from them in the same call (vfk_prep.cu); nothing has been prepared on the host.
 //
-// locate_kernel       : one thread per unit, 8-ary search of the position index.
+// locate_kernel       : one thread per unit: 8-ary search of the sorted starts for the end of the candidate range,
+//                       binary search of the block-level running maximum of the read ends + one block pass for its start.
 // pileup_warp_kernel  : one warp per unit, lanes = reads spanning the column.  Persistent grid, units handed
 //                       out in contiguous grabs from a global counter (shrinking towards the end).  Handles
 //                       the shallow columns (<= 64 candidates, <= 32 of them contributing -- nearly every
 //                       30x / 60x column): values stay in registers, ranks come from a bit-sliced (radix)
 //                       comparison built on warp ballots.  No shared-memory histograms, no atomics, no
-//                       calls, no stack.  Anything else (at 30x: the 3-4 units in 10 000 with more than 32
-//                       contributing reads) is appended to one of two device-side lists:
+//                       calls, no stack.  Anything else is appended to one of two device-side lists:
 // pileup_deep_kernel  : one warp per listed unit, histograms in shared memory (u16 counters, two per
 //                       word) + warp scans;
 // pileup_block_kernel : one CTA per listed unit, u32 counters, for columns with > 32767 candidates.
-// pileup_column_kernel: (batches with a column store, the default) one warp per SNV unit, lane = sector of the column's
-//                       window run; what it cannot serve goes to the kernels above through the same lists.
-// Staged, opt-in, not yet run on a GPU (the default instantiations are untouched -- tools/sass_equal.py):
-// pileup_column_kernel<.., TR = true> (VFK_COL_TRANSPOSED), <.., MQS = true> (VFK_MQ_SELECT), pileup_warp_kernel<.., LISTED = true>
-// (VFK_LIST_SHALLOW).
 #include <algorithm>
 #include <cstdlib>
 #include "vfk_device.cuh"
@@ -69,7 +66,7 @@ __device__ __forceinline__ ResolvedUnit locate_unit(const ReadsDev &R, const Uni
         const int64_t step = (b - a) >> 3;
         int32_t v[7];
 #pragma unroll
-        for (int j = 0; j < 7; ++j) v[j] = __ldg(&R.sb[a + (j + 1) * step].x);
+        for (int j = 0; j < 7; ++j) v[j] = __ldg(R.pos + a + (j + 1) * step);
         int c = 0;
 #pragma unroll
         for (int j = 0; j < 7; ++j) c += v[j] <= col ? 1 : 0;  // sorted: the first c probes start at or before col
@@ -81,8 +78,33 @@ __device__ __forceinline__ ResolvedUnit locate_unit(const ReadsDev &R, const Uni
         int c = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-            if (a + j < b) c += __ldg(&R.sb[a + j].x) <= col ? 1 : 0;
+            if (a + j < b) c += __ldg(R.pos + a + j) <= col ? 1 : 0;
         a += c;
+    }
+    // lo = first read of the contig whose end exceeds the column (no earlier read can overlap it).  blk_incl[b] is the
+    // maximum of tid << 32 | end over the reads of blocks 0 .. b-1: a binary search names the first block that holds
+    // such a read, one pass over that block finds it.  The block of read a-1 may also hold reads starting beyond the
+    // column (their ends exceed it trivially), so it is scanned directly instead of being judged by its maximum.
+    int64_t lo = a;
+    if (a > c0) {
+        const long long key = ((long long)tid << 32) | (long long)(uint32_t)col;
+        const int64_t b_first = c0 / PREP_BLOCK, b_last = (a - 1) / PREP_BLOCK;
+        int64_t from, to;
+        if (b_last > b_first && __ldg(R.blk_incl + b_last) > key) {
+            int64_t ba = b_first, bb = b_last - 1;  // smallest block with an inclusive maximum beyond the key
+            while (ba < bb) {
+                const int64_t m = (ba + bb) >> 1;
+                if (__ldg(R.blk_incl + m + 1) > key) bb = m; else ba = m + 1;
+            }
+            from = max(c0, ba * PREP_BLOCK);
+            to = (ba + 1) * PREP_BLOCK;  // the read is in [from, to)
+        } else {
+            from = max(c0, b_last * PREP_BLOCK);
+            to = a;
+        }
+        int64_t i = from;
+        while (i < to && __ldg(R.end + i) <= col) ++i;
+        lo = min(i, a);
     }
     ResolvedUnit r;
     r.col = col;
@@ -90,7 +112,7 @@ __device__ __forceinline__ ResolvedUnit locate_unit(const ReadsDev &R, const Uni
     r.len = __ldg(V.length + u);
     r.ins_off = __ldg(V.seq_off + u);
     r.hi = (uint32_t)a;
-    r.lo = a > c0 ? (uint32_t)__ldg(&R.sb[a - 1].y) : (uint32_t)a;
+    r.lo = (uint32_t)lo;
     r.stop = V.stop ? __ldg(V.stop + u) : 0x7FFFFFFF;
     r.c1 = (uint32_t)c1;
     return r;
@@ -101,58 +123,13 @@ __device__ __forceinline__ void store_resolved(ResolvedUnit *dst, const Resolved
     o[0] = q[0];
     o[1] = q[1];
 }
-// column store: the window of the column -> its run of sectors
-__device__ __forceinline__ uint4 column_unit(const ReadsDev &R, int32_t tid, int32_t col, uint32_t meta) {
-    const int32_t w = col / VFK_COL_WIDTH;
-    uint32_t off = 0, cnt = 0;
-    if (tid >= 0 && tid < R.n_contigs && col >= 0) {
-        const int64_t w0 = __ldg(R.col_wbase + tid), w1 = __ldg(R.col_wbase + tid + 1);
-        if (w0 + w < w1) {
-            off = __ldg(R.col_off + w0 + w);
-            cnt = __ldg(R.col_off + w0 + w + 1) - off;
-        }
-    }
-    return make_uint4(off, cnt, (uint32_t)(col - w * VFK_COL_WIDTH), meta);
-}
 
-__global__ void __launch_bounds__(256)
-locate_kernel(ReadsDev R, UnitsDev V, ResolvedUnit *__restrict__ res, uint4 *__restrict__ cunits,
-              unsigned long long *__restrict__ cand_sum) {
+__global__ void __launch_bounds__(256) locate_kernel(ReadsDev R, UnitsDev V, ResolvedUnit *__restrict__ res) {
     const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= V.n) return;
-    const ResolvedUnit r = locate_unit(R, V, u);
-    store_resolved(res + u, r);
-    if (cunits) cunits[u] = column_unit(R, __ldg(V.tid + u), r.col, r.meta);
-    if (cand_sum) {  // total candidate reads of the batch: lets the host entry pick its transfer strategy
-        const unsigned active = __activemask();
-        const unsigned mine = r.hi - r.lo;
-        const unsigned tot = __reduce_add_sync(active, mine);
-        if ((threadIdx.x & 31) == (__ffs(active) - 1)) atomicAdd(cand_sum, (unsigned long long)tot);
-    }
+    store_resolved(res + u, locate_unit(R, V, u));
 }
-
-// Column-store launches locate lazily: every unit only needs its window (no search) ...
-__global__ void __launch_bounds__(256) column_units_kernel(ReadsDev R, UnitsDev V, uint4 *__restrict__ cunits) {
-    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= V.n) return;
-    cunits[u] = column_unit(R, __ldg(V.tid + u), __ldg(V.pos + u), __ldg(V.meta + u));
-}
-// ... and only the units the column kernel left on the list are searched in the position index; columns too deep
-// for the warp-per-unit histogram kernel move on to the block list (their slot is voided)
 constexpr uint32_t LIST_VOID = 0xFFFFFFFFu;
-__global__ void __launch_bounds__(256)
-locate_list_kernel(ReadsDev R, UnitsDev V, ResolvedUnit *__restrict__ res, uint32_t *__restrict__ warp_list,
-                   const uint32_t *__restrict__ n_warp, uint32_t *__restrict__ block_list, uint32_t *__restrict__ n_block) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)*n_warp) return;
-    const uint32_t u = warp_list[i];
-    const ResolvedUnit r = locate_unit(R, V, u);
-    store_resolved(res + u, r);
-    if (r.hi - r.lo > (uint32_t)WARP_PATH_MAX_CAND) {
-        block_list[atomicAdd(n_block, 1u)] = u;
-        warp_list[i] = LIST_VOID;
-    }
-}
 
 // ------------------------------------------------------------------------------------------
 // histogram access.  CT = uint16_t: two bins per 32-bit word; CT = uint32_t: one bin per word.
@@ -303,26 +280,6 @@ __device__ __forceinline__ void radix_compare(uint32_t v, uint32_t contributing,
     radix_steps<NBITS>(v, lt, eq);
 }
 
-// The same lt / eq masks by selection: one round per DISTINCT value (smallest first) -- a warp minimum, a ballot of its
-// holders.  Cheaper than the radix walk when a column holds few distinct values, which is the rule for mapping
-// qualities (EXPERIMENTAL, not yet verified on a GPU: VFK_MQ_SELECT=1 uses it for the MQ metric of the column kernel).
-__device__ __forceinline__ void select_compare(uint32_t v, uint32_t contributing, uint32_t lane_bit, uint32_t &lt, uint32_t &eq) {
-    lt = 0u;
-    eq = contributing;
-    uint32_t rem = contributing, done = 0u;
-    while (rem) {  // uniform across the warp
-        const bool waiting = (rem & lane_bit) != 0u;
-        const uint32_t m = __reduce_min_sync(FULL, waiting ? v : 0xFFFFFFFFu);
-        const uint32_t g = __ballot_sync(FULL, waiting && v == m);
-        if (g & lane_bit) {
-            lt = done;
-            eq = g;
-        }
-        done |= g;
-        rem &= ~g;
-    }
-}
-
 // Medians of the REF / ALT lists and this lane's share of the ALT mid-rank sum, from the lt / eq masks.
 //
 // Median: ties are broken by lane id, so every member of a list owns exactly one 0-based position of
@@ -355,17 +312,9 @@ __device__ __forceinline__ uint32_t radix_finish(uint32_t v, uint32_t lt, uint32
 // ------------------------------------------------------------------------------------------
 // deep path of the warp kernel: shared-memory histograms
 // ------------------------------------------------------------------------------------------
-// Per-warp staging ring of the deep kernel: two stages of 32 read headers, filled by bulk async
-// copies (one elected lane issues them) and consumed from shared memory.
-struct StageRing {
-    uint4 *hot;       // [2][32]
-    uint64_t *bar;    // [2]
-    uint32_t parity;  // bit s = phase the next wait on stage s expects
-};
-
-template <int POSB, bool STAGED>
+template <int POSB>
 __device__ __forceinline__ void unit_by_histogram(const ReadsDev &R, const vfk_params &P, const Unit &U, uint32_t *ref_slot,
-                                               uint32_t *alt_slot, int lane, vfk_counts *out, StageRing *ring = nullptr) {
+                                               uint32_t *alt_slot, int lane, vfk_counts *out, uint32_t bad) {
     using L = Layout<POSB>;
     constexpr int WORDS = L::BINS / 2;
     {
@@ -374,45 +323,9 @@ __device__ __forceinline__ void unit_by_histogram(const ReadsDev &R, const vfk_p
     }
     __syncwarp();
     int dp = 0, n_amb = 0, ac_ref = 0, ac_alt = 0, n_cover = 0, n_col = 0;
-    uint32_t status = U.kind;
+    uint32_t status = U.kind | bad;
     const bool with_bq = U.kind == VFK_KIND_SNV;
-    if (STAGED) {
-        // chunk c of 32 candidates lives in stage c & 1; chunk c+1 is in flight while c is evaluated
-        const int64_t n_cand = U.hi - U.lo;
-        const int n_chunks = (int)((n_cand + 31) >> 5);
-        auto issue = [&](int c) {
-            const int s = c & 1;
-            const int64_t first = U.lo + ((int64_t)c << 5);
-            const uint32_t bytes = (uint32_t)min((int64_t)32, U.hi - first) * 16u;
-            if (lane == 0) {
-                mbar_expect_tx(ring->bar + s, bytes);
-                bulk_copy_g2s(ring->hot + s * 32, R.hot + first, bytes, ring->bar + s);
-            }
-        };
-        if (n_chunks > 0) issue(0);  // a unit without candidates must not touch the ring: its phase would run ahead
-        uint32_t mw_next = (U.lo + lane < U.hi) ? __ldg(R.mate + U.lo + lane) : VFK_NO_MATE;
-        for (int c = 0; c < n_chunks; ++c) {
-            const int s = c & 1;
-            const int64_t i = U.lo + ((int64_t)c << 5) + lane;
-            if (c + 1 < n_chunks) issue(c + 1);
-            const uint32_t mw = mw_next;
-            if (c + 1 < n_chunks && i + 32 < U.hi) mw_next = __ldg(R.mate + i + 32);
-            mbar_wait(ring->bar + s, (ring->parity >> s) & 1u);
-            ring->parity ^= 1u << s;
-            if (i < U.hi) {
-                const uint4 hot = ring->hot[s * 32 + lane];
-                const Contribution c1 = evaluate(R, P, U, i, hot, mw);
-                n_cover += c1.covers ? 1 : 0;
-                n_col += c1.in_col ? 1 : 0;
-                dp += c1.in_dp ? 1 : 0;
-                n_amb += c1.ambiguous ? 1 : 0;
-                ac_ref += c1.ref ? 1 : 0;
-                ac_alt += (int)c1.alt;
-                accumulate<uint16_t, POSB>(ref_slot, alt_slot, c1, with_bq, status);
-            }
-            __syncwarp();  // every lane has consumed stage s before it is refilled two chunks later
-        }
-    } else {
+    {
         for (int64_t b = U.lo; b < U.hi; b += 32) {
             const int64_t i = b + lane;
             if (i < U.hi) {
@@ -451,16 +364,114 @@ __device__ __forceinline__ void unit_by_histogram(const ReadsDev &R, const vfk_p
 // ------------------------------------------------------------------------------------------
 // warp per unit
 // ------------------------------------------------------------------------------------------
-// LISTED = false: units 0 .. n_units-1.  LISTED = true (EXPERIMENTAL, not yet verified on a GPU; VFK_LIST_SHALLOW=1):
-// the units the column kernel left on `warp_list` -- nearly all of them shallow columns it could not serve (a passing
-// read inside a deletion, an unusable sector) -- are evaluated here instead of by the histogram kernel: entry k of the
-// list is voided once its unit is done, what this kernel defers too (deep, heavy) stays for pileup_deep_kernel.
-template <int POSB, bool LISTED>
+// One candidate read as a lane holds it: the assembled header (vfk_device.cuh load_hot) and, after the pairing step,
+// its overlap partner word.
+struct Cand {
+    uint4 hot;
+    uint32_t mw;
+    uint32_t st;  // pairing state: ST_STORES = the record reached the name hash and stored itself (its mate still to come)
+};
+constexpr uint32_t ST_STORES = 1u;
+
+// htslib's mate-overlap pairing (sam.c overlap_push) for the candidate reads of ONE column, in registers.
+// Lane k holds candidate k (chunk A) and candidate 32 + k (chunk B).  A record reaches the name hash when it passes the
+// read filter, is a proper pair with a mapped mate on the same contig and is not "obviously non-overlapping"; two such
+// records with the same name pair up iff the earlier one stored itself (its mate still to come).  Names are matched with
+// MATCH.ANY inside a chunk and by a short loop across the chunks.  Returns false when the column needs the general
+// protocol (three records of one name, a zero-span record): the unit then goes to the list path, whose link kernels
+// replay the hash in full.
+__device__ __forceinline__ bool pair_in_registers(const ReadsDev &R, const vfk_params &P, int32_t tid, int lane, uint32_t lt_mask,
+                                                  bool validA, bool validB, int64_t iA, int64_t iB, Cand &A, Cand &B) {
+    A.mw = VFK_NO_MATE;
+    B.mw = VFK_NO_MATE;
+    A.st = B.st = 0u;
+    if (!P.ignore_overlaps) return true;
+    auto pre = [&](bool valid, const uint4 &h) {
+        return valid && read_passes(h.z, P) && (h.z & F_PROPER) && !(h.z & F_MUNMAP);
+    };
+    const bool preA = pre(validA, A.hot), preB = pre(validB, B.hot);
+    unsigned long long idA = 0ull, idB = 0ull;
+    int32_t mposA = 0, mposB = 0;
+    bool eligA = false, eligB = false, zero = false;
+    auto reaches = [&](int64_t i, const uint4 &h, unsigned long long &id, int32_t &mp) {
+        id = __ldg(R.qname_id + i);
+        mp = __ldg(R.mpos + i);
+        const int32_t mt = __ldg(R.mtid + i);
+        if (mt >= 0 && mt != tid) return false;
+        const int32_t end = (int32_t)h.x + (int32_t)h.y;
+        if (mp >= end) {
+            const long long isz = (long long)__ldg(R.isize + i);
+            const int lq = (h.z >> 24) == SHAPE_SIMPLE ? (int)h.y : __ldg(R.l_qseq + i);
+            if ((isz < 0 ? -isz : isz) >= 2LL * lq) return false;
+        }
+        return true;
+    };
+    if (preA) { eligA = reaches(iA, A.hot, idA, mposA); zero = eligA && A.hot.y == 0u; }
+    if (preB) { eligB = reaches(iB, B.hot, idB, mposB); zero = zero || (eligB && B.hot.y == 0u); }
+    const uint32_t mA = __ballot_sync(FULL, eligA), mB = __ballot_sync(FULL, eligB);
+    if (__any_sync(FULL, zero)) return false;  // bam_plp_push may not append it: push order decides
+    uint32_t gA = 0u, gB = 0u, xA = 0u, xB = 0u;  // same-name lanes: own chunk (self included) / other chunk
+    // (all lanes vote: a lane that is out holds a private key and is masked off the result)
+    gA = __match_any_sync(FULL, eligA ? idA : (unsigned long long)lane) & mA;
+    if (!eligA) gA = 0u;
+    if (mB) {
+        gB = __match_any_sync(FULL, eligB ? idB : (unsigned long long)lane) & mB;
+        if (!eligB) gB = 0u;
+        // every chunk-B record is looked up in chunk A (a few per column at 30x): its partner, or a third record of its name
+        uint32_t todo = mB;
+        while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const unsigned long long idj = __shfl_sync(FULL, idB, j);
+            const uint32_t m = __ballot_sync(FULL, eligA && idA == idj);
+            if (lane == j) xB = m;
+            if (eligA && idA == idj) xA |= 1u << j;
+        }
+    }
+    const int sizeA = __popc(gA) + __popc(xA), sizeB = __popc(gB) + __popc(xB);
+    if (__any_sync(FULL, sizeA > 2 || sizeB > 2)) return false;
+    // partner of a size-2 group; the earlier record (chunk A before chunk B, lower lane first) must have stored itself:
+    // mpos >= pos, or a paired record whose mate position is unset
+    const bool storesA = eligA && (mposA >= (int32_t)A.hot.x || ((A.hot.z & F_PAIRED) && mposA == -1));
+    const bool storesB = eligB && (mposB >= (int32_t)B.hot.x || ((B.hot.z & F_PAIRED) && mposB == -1));
+    const uint32_t sA = __ballot_sync(FULL, storesA), sB = __ballot_sync(FULL, storesB);
+    const uint32_t me = 1u << lane;
+    A.st = storesA ? ST_STORES : 0u;
+    B.st = storesB ? ST_STORES : 0u;
+    // name hashes of the two records are equal, so either one gives htslib's tie-break bit
+    if (sizeA == 2) {
+        if (xA) {  // partner in chunk B: this record is the earlier one
+            const int pl = __ffs(xA) - 1;
+            if (storesA) A.mw = ((uint32_t)(iA - lane) + 32u + (uint32_t)pl) | ((wang_hash(__ldg(R.qname_hash + iA)) & 1u) << 31);
+        } else {
+            const uint32_t other = gA & ~me;
+            const int pl = __ffs(other) - 1;
+            const bool first_stores = pl > lane ? storesA : ((sA >> pl) & 1u);
+            if (first_stores) A.mw = ((uint32_t)(iA - lane) + (uint32_t)pl) | ((wang_hash(__ldg(R.qname_hash + iA)) & 1u) << 31);
+        }
+    }
+    if (sizeB == 2) {
+        if (xB) {  // partner in chunk A: that record is the earlier one
+            const int pl = __ffs(xB) - 1;
+            if ((sA >> pl) & 1u) B.mw = ((uint32_t)(iB - 32 - lane) + (uint32_t)pl) | ((wang_hash(__ldg(R.qname_hash + iB)) & 1u) << 31);
+        } else {
+            const uint32_t other = gB & ~me;
+            const int pl = __ffs(other) - 1;
+            const bool first_stores = pl > lane ? storesB : ((sB >> pl) & 1u);
+            if (first_stores) B.mw = ((uint32_t)(iB - lane) + (uint32_t)pl) | ((wang_hash(__ldg(R.qname_hash + iB)) & 1u) << 31);
+        }
+    }
+    return true;
+}
+
+// INWARP = true: overlap partners are found in registers (pair_in_registers); false (debug hook, VFK_DEBUG_LINK_ALL=1 at
+// vfk_create): the link kernels have run over every unit and the partners come from R.mate, as on the list path.
+template <int POSB, bool INWARP>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, VFK_MIN_CTAS)
 pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_units, const uint8_t *__restrict__ ins_seq,
                    vfk_params P, vfk_counts *__restrict__ out, unsigned long long *__restrict__ work_counter,
                    uint32_t *__restrict__ block_list, uint32_t *__restrict__ n_block, uint32_t *__restrict__ warp_list,
-                   uint32_t *__restrict__ n_warp) {
+                   uint32_t *__restrict__ n_warp, const uint32_t *__restrict__ batch_status) {
     using L = Layout<POSB>;
     __shared__ uint32_t stage_all[WARPS_PER_CTA][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -468,7 +479,7 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
     uint32_t *stage = stage_all[warp];
     const int64_t n_warps = (int64_t)gridDim.x * WARPS_PER_CTA;
     int64_t last_base = 0;
-    if constexpr (LISTED) n_units = (int64_t)*n_warp;
+    const uint32_t bad = *batch_status;  // prep_kernel has finished: VFK_ST_BADBATCH or 0
 
     for (;;) {
         unsigned long long base = 0;
@@ -481,32 +492,20 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
         const int n_here = (int)min((int64_t)grab, n_units - (int64_t)base);
         // lane j keeps the record of unit base+j; one coalesced read for the whole grab
         uint4 ra = make_uint4(0, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
-        uint32_t uid = LIST_VOID;  // LISTED: the unit behind list entry base + lane
         if (lane < n_here) {
-            if constexpr (LISTED) {
-                uid = warp_list[base + lane];
-                if (uid != LIST_VOID) {
-                    const uint4 *q = reinterpret_cast<const uint4 *>(res + uid);
-                    ra = q[0];  // written by locate_list_kernel (an earlier launch of this call)
-                    rb = q[1];
-                }
-            } else {
-                const uint4 *q = reinterpret_cast<const uint4 *>(res + base + lane);
-                ra = __ldg(q);
-                rb = __ldg(q + 1);
-            }
+            const uint4 *q = reinterpret_cast<const uint4 *>(res + base + lane);
+            ra = q[0];  // written by locate_kernel (an earlier launch of this call)
+            rb = q[1];
         }
-        // software pipeline: the header + mate word of the NEXT unit's first 32 candidates are
-        // requested before the current unit is processed
+        // software pipeline: the header words of the NEXT unit's first 32 candidates are requested before the current
+        // unit is processed
         uint4 hot_n = make_uint4(0, 0, 0, 0);
-        uint32_t mw_n = VFK_NO_MATE;
         {
             const uint32_t lo0 = __shfl_sync(FULL, rb.x, 0), hi0 = __shfl_sync(FULL, rb.y, 0);
-            if (lo0 + lane < hi0) { hot_n = __ldg(R.hot + lo0 + lane); mw_n = __ldg(R.mate + lo0 + lane); }
+            if (!bad && lo0 + lane < hi0) hot_n = load_hot(R, (int64_t)lo0 + lane);
         }
         for (int j = 0; j < n_here; ++j) {
-            int64_t u = (int64_t)base + j;
-            if constexpr (LISTED) u = (int64_t)__shfl_sync(FULL, uid, j);
+            const int64_t u = (int64_t)base + j;
             ResolvedUnit ru;
             ru.col = (int32_t)__shfl_sync(FULL, ra.x, j); ru.meta = __shfl_sync(FULL, ra.y, j);
             ru.len = (int32_t)__shfl_sync(FULL, ra.z, j); ru.ins_off = __shfl_sync(FULL, ra.w, j);
@@ -514,51 +513,64 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
             ru.stop = (int32_t)__shfl_sync(FULL, rb.z, j); ru.c1 = __shfl_sync(FULL, rb.w, j);
             Unit U;
             unit_from(ru, ins_seq, U);
-            const uint4 hot_c = hot_n;
-            const uint32_t mw_c = mw_n;
+            Cand A;
+            A.hot = hot_n;
+            A.mw = VFK_NO_MATE;
+            A.st = 0u;
             if (j + 1 < n_here) {
                 const uint32_t lo1 = __shfl_sync(FULL, rb.x, j + 1), hi1 = __shfl_sync(FULL, rb.y, j + 1);
-                if (lo1 + lane < hi1) { hot_n = __ldg(R.hot + lo1 + lane); mw_n = __ldg(R.mate + lo1 + lane); }
-            }
-            if constexpr (LISTED) {
-                if (u == (int64_t)LIST_VOID) continue;  // an entry locate_list_kernel moved to the block list
+                if (!bad && lo1 + lane < hi1) hot_n = load_hot(R, (int64_t)lo1 + lane);
             }
             const int64_t n_cand = U.hi - U.lo;
             int med2[3][2] = {{-1, -1}, {-1, -1}, {-1, -1}};
             uint64_t s2[3] = {0, 0, 0};
-            if (n_cand == 0) {
-                if (lane == 0) {
-                    store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind, 0u, 0u);
-                    if constexpr (LISTED) warp_list[base + j] = LIST_VOID;
-                }
+            if (n_cand == 0 || bad) {
+                if (lane == 0) store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind | bad, 0u, 0u);
                 continue;
             }
             if (n_cand > 64) {  // deep: handed to the histogram kernels through a device-side list
-                if constexpr (!LISTED) {
-                    if (lane == 0) {
-                        if (n_cand > WARP_PATH_MAX_CAND) block_list[atomicAdd(n_block, 1u)] = (uint32_t)u;
-                        else warp_list[atomicAdd(n_warp, 1u)] = (uint32_t)u;
-                        store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind | VFK_ST_DEFERRED, (uint32_t)n_cand, 0u);
-                    }
+                if (lane == 0) {
+                    if (n_cand > WARP_PATH_MAX_CAND) block_list[atomicAdd(n_block, 1u)] = (uint32_t)u;
+                    else warp_list[atomicAdd(n_warp, 1u)] = (uint32_t)u;
+                    store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind | VFK_ST_DEFERRED, (uint32_t)n_cand, 0u);
                 }
-                continue;  // LISTED: the entry stays on the list (its record already says deferred)
+                continue;
             }
-            // ---- shallow: the reads that span the column are packed into the lanes (first chunk in place,
-            // second chunk into the lanes the first one leaves free) and evaluated in one pass; a second
-            // pass only runs for the overflow when more than 32 reads span the column ----
-            bool act = lane < n_cand && (uint32_t)(U.col - (int32_t)hot_c.x) < hot_c.y;
+            // ---- shallow ----
+            const bool validA = lane < n_cand, validB = lane + 32 < n_cand;
             int64_t i_a = U.lo + lane;
-            uint4 hot_a = hot_c;
-            uint32_t mw_a = mw_c;
+            const int64_t i_b = U.lo + 32 + lane;
+            Cand B;
+            B.hot = make_uint4(0, 0, 0, 0);
+            B.mw = VFK_NO_MATE;
+            B.st = 0u;
+            if (validB) B.hot = load_hot(R, i_b);
+            bool hard = false;
+            int32_t tid = 0;
+            if constexpr (INWARP) {
+                if (lane == 0) {  // contig of the column: the one whose read range ends at c1
+                    int32_t a = 0, b = R.n_contigs;
+                    while (b - a > 1) {
+                        const int32_t m = (a + b) >> 1;
+                        if (__ldg(R.contig_off + m) < (int64_t)U.c1) a = m; else b = m;
+                    }
+                    tid = a;
+                }
+                tid = __shfl_sync(FULL, tid, 0);
+                hard = !pair_in_registers(R, P, tid, lane, lt_mask, validA, validB, i_a, i_b, A, B);
+            } else {
+                if (validA) A.mw = __ldg(R.mate + i_a);
+                if (validB) B.mw = __ldg(R.mate + i_b);
+            }
+            // the reads that span the column are packed into the lanes (first chunk in place, second chunk into the
+            // lanes the first one leaves free) and evaluated in one pass; a second pass only runs for the overflow
+            // when more than 32 reads span the column
+            bool act = validA && (uint32_t)(U.col - (int32_t)A.hot.x) < A.hot.y;
             Eval e0, e1;
-            e0.pk = e0.fl = e0.alt = 0u;
+            e0.pk = e0.fl = e0.alt = e0.hard = 0u;
             e1 = e0;
-            if (n_cand > 32) {
-                const bool has1 = lane + 32 < n_cand;
-                uint4 hot_1 = make_uint4(0, 0, 0, 0);
-                uint32_t mw_1 = VFK_NO_MATE;
-                if (has1) { hot_1 = __ldg(R.hot + i_a + 32); mw_1 = __ldg(R.mate + i_a + 32); }
-                const bool cov1 = has1 && (uint32_t)(U.col - (int32_t)hot_1.x) < hot_1.y;
+            if (n_cand > 32 && !hard) {
+                const bool cov1 = validB && (uint32_t)(U.col - (int32_t)B.hot.x) < B.hot.y;
                 const uint32_t c0m = __ballot_sync(FULL, act), c1m = __ballot_sync(FULL, cov1);
                 const int n_free = 32 - __popc(c0m), idx1 = __popc(c1m & lt_mask);
                 const int n_move = min(n_free, __popc(c1m));
@@ -568,25 +580,50 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
                 const bool adopt = !act && slot < n_move;
                 const int src = adopt ? (int)stage[slot] : lane;
                 __syncwarp();
-                const uint32_t hx = __shfl_sync(FULL, hot_1.x, src), hy = __shfl_sync(FULL, hot_1.y, src);
-                const uint32_t hz = __shfl_sync(FULL, hot_1.z, src), hw = __shfl_sync(FULL, hot_1.w, src);
-                const uint32_t hm = __shfl_sync(FULL, mw_1, src);
+                const uint32_t hx = __shfl_sync(FULL, B.hot.x, src), hy = __shfl_sync(FULL, B.hot.y, src);
+                const uint32_t hz = __shfl_sync(FULL, B.hot.z, src), hw = __shfl_sync(FULL, B.hot.w, src);
+                const uint32_t hm = __shfl_sync(FULL, B.mw, src), hs = __shfl_sync(FULL, B.st, src);
                 if (adopt) {
-                    hot_a = make_uint4(hx, hy, hz, hw);
-                    mw_a = hm;
+                    A.hot = make_uint4(hx, hy, hz, hw);
+                    A.mw = hm;
+                    A.st = hs;
                     i_a = U.lo + 32 + src;
                     act = true;
                 }
                 const bool over = cov1 && idx1 >= n_move;
                 if (__any_sync(FULL, over)) {
-                    if (over) e1 = evaluate_packed(R, P, U, U.lo + 32 + lane, hot_1, mw_1);
+                    if (over) e1 = evaluate_packed(R, P, U, i_b, B.hot, B.mw);
                 }
             }
-            if (act) e0 = evaluate_packed(R, P, U, i_a, hot_a, mw_a);
+            if (act && !hard) e0 = evaluate_packed(R, P, U, i_a, A.hot, A.mw);
+            if constexpr (INWARP) {
+                // A read inside a deletion / skip at the column is filtered on its NEXT base, and the overlap adjustment of that
+                // base exists once the mate has been pushed -- which also holds for the first record pushed after the column
+                // (bam_plp_auto reads one ahead).  That record lies outside the candidate range: when such a read stored itself
+                // and found no partner among the candidates, the record after the column is tried, and the read re-evaluated.
+                const bool t0 = e0.hard && A.mw == VFK_NO_MATE && (A.st & ST_STORES), t1 = e1.hard && B.mw == VFK_NO_MATE && (B.st & ST_STORES);
+                if (__any_sync(FULL, t0 || t1)) {
+                    long long nx = -1;
+                    if (lane == 0) nx = next_pushed(R, P, U.hi, U.c1, U.stop);
+                    nx = __shfl_sync(FULL, nx, 0);
+                    if (nx >= 0 && __ldg(R.end + nx) > __ldg(R.pos + nx) && reaches_hash(R, P, nx, tid, INT32_MIN)) {
+                        const unsigned long long idn = __ldg(R.qname_id + nx);
+                        const uint32_t hn = __ldg(R.qname_hash + nx);
+                        if (t0 && __ldg(R.qname_id + i_a) == idn && __ldg(R.qname_hash + i_a) == hn) {
+                            A.mw = (uint32_t)nx | ((wang_hash(hn) & 1u) << 31);
+                            e0 = evaluate_packed(R, P, U, i_a, A.hot, A.mw);
+                        }
+                        if (t1 && __ldg(R.qname_id + i_b) == idn && __ldg(R.qname_hash + i_b) == hn) {
+                            B.mw = (uint32_t)nx | ((wang_hash(hn) & 1u) << 31);
+                            e1 = evaluate_packed(R, P, U, i_b, B.hot, B.mw);
+                        }
+                    }
+                }
+            }
             const bool k0 = e0.pk != 0u, k1 = e1.pk != 0u;
             const uint32_t m0 = __ballot_sync(FULL, k0), m1 = __ballot_sync(FULL, k1);
             // a read can support an insertion more than once (pileups.py:267-290): such units take the deep path
-            const bool heavy = U.kind == VFK_KIND_INS && __any_sync(FULL, e0.alt > 1u || e1.alt > 1u);
+            const bool heavy = hard || (U.kind == VFK_KIND_INS && __any_sync(FULL, e0.alt > 1u || e1.alt > 1u));
             uint32_t pk = e0.pk;
             if (m1) {  // move the overflow pass's contributions into lanes the first pass left free
                 const int n1 = __popc(m1);
@@ -603,14 +640,12 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
             sh.is_alt = pk & PK_ALT;
             sh.R = __ballot_sync(FULL, sh.is_ref);
             sh.A = __ballot_sync(FULL, sh.is_alt);
-            // rare: more contributions than lanes, a multiply supported insertion, or REF == ALT (a read in
-            // both lists) -- re-done through the histograms
+            // rare: more contributions than lanes, a multiply supported insertion, REF == ALT (a read in both lists), or a
+            // column whose pairing / base-quality filter needs the general protocol -- re-done through the histograms
             if (heavy || __popc(m0) + __popc(m1) > 32 || (sh.R & sh.A)) {
-                if constexpr (!LISTED) {
-                    if (lane == 0) {
-                        warp_list[atomicAdd(n_warp, 1u)] = (uint32_t)u;
-                        store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind | VFK_ST_DEFERRED, (uint32_t)n_cand, 0u);
-                    }
+                if (lane == 0) {
+                    warp_list[atomicAdd(n_warp, 1u)] = (uint32_t)u;
+                    store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind | VFK_ST_DEFERRED, (uint32_t)n_cand, 0u);
                 }
                 continue;
             }
@@ -646,235 +681,8 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
                 }
             }
             if (U.kind == VFK_KIND_SNV && !P.include_ambiguous) dp -= n_amb;  // pileups.py:224-227
-            if (lane == 0) {
+            if (lane == 0)
                 store_counts(out + u, dp, n_amb, ac_ref, ac_alt, med2, s2, U.kind, (uint32_t)n_cand, (uint32_t)n_cover, (uint32_t)n_col);
-                if constexpr (LISTED) warp_list[base + j] = LIST_VOID;
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// warp per unit on the column store (SNV units): the reads of a column are ONE contiguous run of
-// 32-byte sectors -- lane = sector, one 4-byte entry word + the 8-byte header per lane -- the read filter
-// verdict, the query position and the overlap partner's whereabouts come with the sector, and the
-// partner's base is a register of another lane.  No header gather, no CIGAR, no dependent loads.
-// What it cannot serve goes to the read-major kernels through the same device-side lists: units that are
-// not SNVs, windows deeper than 64 sectors, a passing read inside a deletion at the column (its
-// base-quality filter looks at the next base and at the push timing of its mate), a sector flagged unusable.
-// ------------------------------------------------------------------------------------------
-#ifndef VFK_COL_MIN_CTAS
-#define VFK_COL_MIN_CTAS 8
-#endif
-struct ColRead {  // one sector as a lane holds it
-    uint32_t e;   // the 16-bit entry of the column
-    uint32_t h0, h1;
-};
-// Sector k of the run [off, off + cnt) of a window, position p.  TR = false: the sector form (12 entries + 2 header
-// words per 32-byte sector).  TR = true: the window-transposed form of the same run (vfkio_columns_transpose: cnt
-// header pairs, then 12 rows of cnt entries) -- NOT YET VERIFIED ON A GPU; selected only by VFK_COL_TRANSPOSED=1
-// together with a store built under the same setting (vafator_b200/device.py).
-// CP = true (EXPERIMENTAL, VFK_HOST_GATHER=1, host entry point only): the run was gathered on the host for this very
-// unit -- cnt header pairs, then the cnt entries of the unit's OWN position (one row), see vfk_api.cu.
-template <bool TR, bool CP>
-__device__ __forceinline__ ColRead load_col_read(const uint32_t *__restrict__ sectors, uint32_t off, uint32_t cnt, uint32_t k, uint32_t p) {
-    ColRead c;
-    if constexpr (CP) {
-        const unsigned char *run = reinterpret_cast<const unsigned char *>(sectors + (size_t)off * 8u);
-        const uint2 h = __ldg(reinterpret_cast<const uint2 *>(run) + k);
-        c.e = (uint32_t)__ldg(reinterpret_cast<const unsigned short *>(run + (size_t)cnt * 8u) + k);
-        c.h0 = h.x;
-        c.h1 = h.y;
-    } else if constexpr (TR) {
-        const unsigned char *run = reinterpret_cast<const unsigned char *>(sectors + (size_t)off * 8u);
-        const uint2 h = __ldg(reinterpret_cast<const uint2 *>(run) + k);
-        c.e = (uint32_t)__ldg(reinterpret_cast<const unsigned short *>(run + (size_t)cnt * 8u) + (size_t)p * cnt + k);
-        c.h0 = h.x;
-        c.h1 = h.y;
-    } else {
-        const uint32_t *w = sectors + (size_t)(off + k) * 8u;
-        c.e = (__ldg(w + (p >> 1)) >> ((p & 1u) * 16u)) & 0xFFFFu;
-        const uint2 h = __ldg(reinterpret_cast<const uint2 *>(w + 6));
-        c.h0 = h.x;
-        c.h1 = h.y;
-    }
-    return c;
-}
-// htslib tweak_overlap_quality at one position (both reads show an aligned base): the quality this read keeps
-__device__ __forceinline__ int overlap_quality(uint32_t mine, uint32_t theirs, uint32_t h0) {
-    const int qi = (int)(mine & 0xFFu), qm = (int)(theirs & 0xFFu);
-    const uint32_t sel = (h0 >> 29) & 1u;
-    const uint32_t mymul = (h0 >> 30) & 1u ? sel : 1u - sel;  // the earlier record holds the hash slot
-    if (((mine ^ theirs) & 0xF00u) == 0u) {
-        const int s = min(qi + qm, 200);
-        return mymul ? s : 0;
-    }
-    if (qi > qm) return (qi * 4) / 5;
-    if (qi < qm) return 0;
-    return mymul ? (qi * 4) / 5 : 0;
-}
-// one sector -> the packed contribution (Eval.pk / Eval.fl); `partner` is the partner's entry or 0
-__device__ __forceinline__ void col_evaluate(const ColRead &c, uint32_t partner, uint32_t p, const vfk_params &P, uint32_t ref_code,
-                                             uint32_t alt_code, uint32_t &pk, uint32_t &fl) {
-    pk = 0u;
-    fl = 0u;
-    const uint32_t state = (c.e >> 12) & 3u;
-    if (state == 0u) return;
-    fl = FL_COVERS;
-    if (!((c.h0 >> 28) & 1u)) return;
-    fl |= FL_IN_COL;
-    if (state != 1u) return;  // reference skip: in the column, nothing else (deletions never get here)
-    int q = (int)(c.e & 0xFFu);
-    if (((partner >> 12) & 3u) == 1u) q = overlap_quality(c.e, partner, c.h0);
-    if (q < P.min_baseq) return;  // pysam pileup_base_qual_skip
-    fl |= FL_IN_DP;
-    const uint32_t code = (c.e >> 8) & 15u;
-    if (code_is_ambiguous((int)code)) fl |= FL_AMBIGUOUS;
-    const uint32_t lists = (code == ref_code ? PK_REF : 0u) | (code == alt_code ? PK_ALT : 0u);
-    if (lists) {
-        const uint32_t below = c.h1 & 0xFFFu & ((1u << p) - 1u);
-        const uint32_t ins = ((c.h1 >> 28) & 1u) && p > ((c.h1 >> 12) & 15u) ? (c.h1 >> 16) & 0xFFFu : 0u;
-        const uint32_t qpos = (c.h0 & 0xFFFu) + (uint32_t)__popc(below) + ins;
-        pk = ((c.h0 >> 12) & 0xFFu) | ((uint32_t)q << 8) | (qpos << 16) | lists;
-    }
-}
-
-template <int POSB, bool TR, bool MQS, bool CP>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, VFK_COL_MIN_CTAS)
-pileup_column_kernel(ReadsDev R, const uint4 *__restrict__ cunits, const ResolvedUnit *__restrict__ res, int64_t n_units, vfk_params P,
-                     vfk_counts *__restrict__ out,
-                     unsigned long long *__restrict__ work_counter, uint32_t *__restrict__ block_list,
-                     uint32_t *__restrict__ n_block, uint32_t *__restrict__ warp_list, uint32_t *__restrict__ n_warp) {
-    using L = Layout<POSB>;
-    __shared__ uint32_t stage_all[WARPS_PER_CTA][32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    uint32_t *stage = stage_all[warp];
-    const int64_t n_warps = (int64_t)gridDim.x * WARPS_PER_CTA;
-    int64_t last_base = 0;
-    const uint32_t *__restrict__ sectors = R.col_sectors;
-
-    for (;;) {
-        unsigned long long base = 0;
-        const int64_t left = n_units - last_base;  // as of this warp's previous visit
-        const int grab = left > 16 * n_warps ? GRAB : left > 4 * n_warps ? 2 : 1;
-        if (lane == 0) base = atomicAdd(work_counter, (unsigned long long)grab);
-        base = __shfl_sync(FULL, base, 0);
-        if ((int64_t)base >= n_units) break;
-        last_base = (int64_t)base;
-        const int n_here = (int)min((int64_t)grab, n_units - (int64_t)base);
-        uint4 cu = make_uint4(0, 0, 0, 0);  // lane j keeps the column unit of unit base+j
-        if (lane < n_here) cu = __ldg(cunits + base + lane);
-        // software pipeline: the first 32 sectors of the NEXT unit are requested before the current one is processed
-        ColRead next;
-        next.e = next.h0 = next.h1 = 0u;
-        {
-            const uint32_t off0 = __shfl_sync(FULL, cu.x, 0), cnt0 = __shfl_sync(FULL, cu.y, 0), p0 = __shfl_sync(FULL, cu.z, 0);
-            if ((uint32_t)lane < cnt0) next = load_col_read<TR, CP>(sectors, off0, cnt0, (uint32_t)lane, p0);
-        }
-        for (int j = 0; j < n_here; ++j) {
-            const int64_t u = (int64_t)base + j;
-            const uint32_t off = __shfl_sync(FULL, cu.x, j), cnt = __shfl_sync(FULL, cu.y, j), p = __shfl_sync(FULL, cu.z, j);
-            const uint32_t meta = __shfl_sync(FULL, cu.w, j);
-            const uint32_t kind = meta & 3u, ref_code = (meta >> 8) & 0xFFu, alt_code = (meta >> 16) & 0xFFu;
-            ColRead c0 = next;
-            if (j + 1 < n_here) {
-                const uint32_t off1 = __shfl_sync(FULL, cu.x, j + 1), cnt1 = __shfl_sync(FULL, cu.y, j + 1);
-                const uint32_t p1 = __shfl_sync(FULL, cu.z, j + 1);
-                if ((uint32_t)lane < cnt1) next = load_col_read<TR, CP>(sectors, off1, cnt1, (uint32_t)lane, p1);
-            }
-            int med2[3][2] = {{-1, -1}, {-1, -1}, {-1, -1}};
-            uint64_t s2[3] = {0, 0, 0};
-            if (kind != VFK_KIND_SNV || cnt > 64u) {  // not for this kernel: the read-major kernels take it
-                if (lane == 0) {
-                    // located units (host entry point) are routed here, the others by locate_list_kernel
-                    const uint32_t n_cand = res ? __ldg(&res[u].hi) - __ldg(&res[u].lo) : 0u;
-                    if (n_cand > (uint32_t)WARP_PATH_MAX_CAND) block_list[atomicAdd(n_block, 1u)] = (uint32_t)u;
-                    else warp_list[atomicAdd(n_warp, 1u)] = (uint32_t)u;
-                    store_counts(out + u, 0, 0, 0, 0, med2, s2, kind | VFK_ST_DEFERRED, cnt, 0u);
-                }
-                continue;
-            }
-            if (cnt == 0u) {
-                if (lane == 0) store_counts(out + u, 0, 0, 0, 0, med2, s2, kind, 0u, 0u);
-                continue;
-            }
-            if ((uint32_t)lane >= cnt) c0.e = c0.h0 = c0.h1 = 0u;
-            ColRead c1;
-            c1.e = c1.h0 = c1.h1 = 0u;
-            if (cnt > 32u && (uint32_t)lane + 32u < cnt) c1 = load_col_read<TR, CP>(sectors, off, cnt, 32u + (uint32_t)lane, p);
-            // overlap partners: sector k + offset of the same run, i.e. an entry another lane holds
-            const int off0 = (int)(int8_t)((c0.h0 >> 20) & 0xFFu), off1 = (int)(int8_t)((c1.h0 >> 20) & 0xFFu);
-            const int k0p = lane + off0, k1p = 32 + lane + off1;
-            const uint32_t a0 = __shfl_sync(FULL, c0.e, k0p & 31), b0 = __shfl_sync(FULL, c1.e, k0p & 31);
-            uint32_t partner0 = off0 ? (k0p < 32 ? a0 : b0) : 0u, partner1 = 0u;
-            if (cnt > 32u) {
-                const uint32_t a1 = __shfl_sync(FULL, c0.e, k1p & 31), b1 = __shfl_sync(FULL, c1.e, k1p & 31);
-                partner1 = off1 ? (k1p < 32 ? a1 : b1) : 0u;
-            }
-            // a passing read inside a deletion, or an unusable sector: the read-major path decides
-            const bool in0 = ((c0.e >> 12) & 3u) != 0u && ((c0.h0 >> 28) & 1u), in1 = ((c1.e >> 12) & 3u) != 0u && ((c1.h0 >> 28) & 1u);
-            const bool hard = (in0 && (((c0.e >> 12) & 3u) == 2u || (c0.h0 >> 31))) || (in1 && (((c1.e >> 12) & 3u) == 2u || (c1.h0 >> 31)));
-            Eval e0, e1;
-            e0.alt = e1.alt = 0u;
-            col_evaluate(c0, partner0, p, P, ref_code, alt_code, e0.pk, e0.fl);
-            col_evaluate(c1, partner1, p, P, ref_code, alt_code, e1.pk, e1.fl);
-            const bool k0 = e0.pk != 0u, k1 = e1.pk != 0u;
-            const uint32_t m0 = __ballot_sync(FULL, k0), m1 = __ballot_sync(FULL, k1);
-            uint32_t pk = e0.pk;
-            if (m1) {  // move the second chunk's contributions into lanes the first one left free
-                const int n1 = __popc(m1);
-                if (k1) stage[__popc(m1 & lt_mask)] = e1.pk;
-                __syncwarp();
-                if (!k0) {
-                    const int f = __popc(~m0 & lt_mask);
-                    if (f < n1) pk = stage[f];
-                }
-                __syncwarp();
-            }
-            SlotShape sh;
-            sh.is_ref = pk & PK_REF;
-            sh.is_alt = pk & PK_ALT;
-            sh.R = __ballot_sync(FULL, sh.is_ref);
-            sh.A = __ballot_sync(FULL, sh.is_alt);
-            if (__any_sync(FULL, hard) || __popc(m0) + __popc(m1) > 32 || (sh.R & sh.A)) {
-                if (lane == 0) {
-                    warp_list[atomicAdd(n_warp, 1u)] = (uint32_t)u;
-                    store_counts(out + u, 0, 0, 0, 0, med2, s2, kind | VFK_ST_DEFERRED, cnt, 0u);
-                }
-                continue;
-            }
-            const uint32_t tally = __reduce_add_sync(FULL, e0.fl + e1.fl);
-            const int n_cover = (int)(tally & 0xFFu), n_col = (int)((tally >> 8) & 0xFFu), n_amb = (int)(tally >> 24);
-            int dp = (int)((tally >> 16) & 0xFFu);
-            const int ac_ref = __popc(sh.R), ac_alt = __popc(sh.A);
-            if (sh.R | sh.A) {
-                uint32_t lt, eq, w;
-                const uint32_t mq = pk & 0xFFu, bq = (pk >> 8) & 0xFFu, qp = (pk >> 16) & 0xFFFu;
-                sh.R_low = sh.R & lt_mask; sh.A_low = sh.A & lt_mask;
-                sh.r1 = (ac_ref - 1) >> 1; sh.a1 = (ac_alt - 1) >> 1;
-                sh.dr = (uint32_t)(ac_ref >> 1) - (uint32_t)sh.r1; sh.da = (uint32_t)(ac_alt >> 1) - (uint32_t)sh.a1;
-                sh.sh_r = 1u - sh.dr; sh.sh_a = 17u - sh.da;
-                if constexpr (MQS) select_compare(mq, sh.R | sh.A, 1u << lane, lt, eq);
-                else radix_compare<8>(mq, sh.R | sh.A, lt, eq);
-                uint32_t term = radix_finish(mq, lt, eq, sh, w);
-                med2[0][0] = ac_ref ? (int)(w & 0xFFFFu) : -1; med2[0][1] = ac_alt ? (int)(w >> 16) : -1;
-                radix_compare<8>(bq, sh.R | sh.A, lt, eq);
-                term |= radix_finish(bq, lt, eq, sh, w) << 10;
-                med2[1][0] = ac_ref ? (int)(w & 0xFFFFu) : -1; med2[1][1] = ac_alt ? (int)(w >> 16) : -1;
-                radix_compare<L::POS_BITS>(qp, sh.R | sh.A, lt, eq);
-                term |= radix_finish(qp, lt, eq, sh, w) << 20;
-                med2[2][0] = ac_ref ? (int)(w & 0xFFFFu) : -1; med2[2][1] = ac_alt ? (int)(w >> 16) : -1;
-                if (ac_ref && ac_alt) {
-                    const uint32_t sums = __reduce_add_sync(FULL, term);
-                    const uint64_t base2 = (uint64_t)(ac_alt * ac_alt + ac_alt);
-                    s2[0] = base2 + (sums & 0x3FFu);
-                    s2[1] = base2 + ((sums >> 10) & 0x3FFu);
-                    s2[2] = base2 + (sums >> 20);
-                }
-            }
-            if (!P.include_ambiguous) dp -= n_amb;  // pileups.py:224-227
-            if (lane == 0) store_counts(out + u, dp, n_amb, ac_ref, ac_alt, med2, s2, kind, cnt, (uint32_t)n_cover, (uint32_t)n_col);
         }
     }
 }
@@ -886,26 +694,15 @@ template <int POSB>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 pileup_deep_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, const uint8_t *__restrict__ ins_seq, vfk_params P,
                    vfk_counts *__restrict__ out, const uint32_t *__restrict__ warp_list, const uint32_t *__restrict__ n_warp,
-                   uint32_t *__restrict__ deep_work) {
+                   uint32_t *__restrict__ deep_work, const uint32_t *__restrict__ batch_status) {
     using L = Layout<POSB>;
     constexpr int WORDS = L::BINS / 2;  // u16 bins
     extern __shared__ __align__(16) uint32_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *ref_slot = smem + (size_t)warp * 2 * WORDS;
     uint32_t *alt_slot = ref_slot + WORDS;
-    __shared__ __align__(128) uint4 s_hot[WARPS_PER_CTA][2][32];
-    __shared__ __align__(8) uint64_t s_bar[WARPS_PER_CTA][2];
-    StageRing ring;
-    ring.hot = &s_hot[warp][0][0];
-    ring.bar = &s_bar[warp][0];
-    ring.parity = 0u;
-    if (lane == 0) {
-        mbar_init(ring.bar + 0, 1);
-        mbar_init(ring.bar + 1, 1);
-        mbar_fence_init();
-    }
-    __syncwarp();
     const uint32_t n = *n_warp;
+    const uint32_t bad = *batch_status;
     // listed unit k goes to warp k first (no atomics when the list is short or empty), the rest through a counter
     const uint32_t n_warps = gridDim.x * WARPS_PER_CTA;
     uint32_t k = blockIdx.x * WARPS_PER_CTA + warp;
@@ -915,7 +712,7 @@ pileup_deep_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, const uint8
         if (u != LIST_VOID) {
             Unit U;
             unit_from(res[u], ins_seq, U);
-            unit_by_histogram<POSB, true>(R, P, U, ref_slot, alt_slot, lane, out + u, &ring);
+            unit_by_histogram<POSB>(R, P, U, ref_slot, alt_slot, lane, out + u, bad);
         }
         if (lane == 0) k = n_warps + atomicAdd(deep_work, 1u);
         k = __shfl_sync(FULL, k, 0);
@@ -1002,144 +799,113 @@ pileup_block_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, const uint
 // ------------------------------------------------------------------------------------------
 // host-side launchers (called from vfk_api.cu)
 // ------------------------------------------------------------------------------------------
-cudaError_t launch_locate(const ReadsDev &R, const UnitsDev &V, void *resolved, unsigned long long *cand_sum, cudaStream_t stream,
-                          int *launches) {
-    if (V.n <= 0) return cudaSuccess;
-    uint4 *cunits = R.col_off ? reinterpret_cast<uint4 *>((char *)resolved + (size_t)V.n * sizeof(ResolvedUnit)) : nullptr;
-    locate_kernel<<<(unsigned)((V.n + 255) / 256), 256, 0, stream>>>(R, V, (ResolvedUnit *)resolved, cunits, cand_sum);
-    ++*launches;
-    return cudaGetLastError();
-}
+cudaError_t launch_link(const ReadsDev &R, const vfk_params &P, const void *resolved, const uint32_t *list, const uint32_t *n_list,
+                        int64_t n_all, uint32_t *heads, uint32_t n_buckets, uint32_t *next, int32_t *column, uint32_t *claimed,
+                        uint32_t *mate, int sm_count, cudaStream_t stream, int *launches);
 
-// set by the host entry point (vfk_api.cu) around a launch whose column runs it has gathered unit by unit
-thread_local bool column_runs_gathered = false;
+// Per-call device scratch (owned by the handle / a staging slot).
+//   counters (64 bytes): @0 u64 unit work counter, @8 u32 block-list length, @12 u32 warp-list length, @16 u32 deep-kernel
+//   work counter, @20 u32 batch status (VFK_ST_BADBATCH or 0).   lists: 2 * n_units u32.
+struct PileupScratch {
+    void *resolved;   // n_units * 32 B
+    void *counters;   // 64 B
+    uint32_t *lists;  // 2 * n_units
+    // link scratch
+    uint32_t *heads;
+    uint32_t n_buckets;
+    uint32_t *next;
+    int32_t *column;
+    uint32_t *claimed;
+    uint32_t *mate;
+};
 
-// the staged variants are chosen per call (tools/ab_staged.py switches them inside one process)
-static bool env_flag(const char *name) {
-    const char *v = getenv(name);
-    return v && v[0] == '1';
-}
-
-// scratch words (32 bytes, device): @0 u64 unit work counter, @8 u32 block-list length, @12 u32 warp-list
-// length, @16 u32 deep-kernel work counter, @24 u64 candidate sum (locate pass).  lists: 2 * n_units u32.
 template <int POSB>
-static cudaError_t launch_posb(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, vfk_counts *out, ResolvedUnit *res,
-                               void *counters, uint32_t *lists, int sm_count, cudaStream_t stream, int *launches, bool located) {
+static cudaError_t launch_posb(ReadsDev R, const UnitsDev &V, const vfk_params &P, vfk_counts *out, const PileupScratch &S,
+                               int sm_count, cudaStream_t stream, int *launches, bool link_all) {
     using L = Layout<POSB>;
     const size_t smem_deep = (size_t)WARPS_PER_CTA * 2 * (L::BINS / 2) * sizeof(uint32_t);
     const size_t smem_block = (size_t)2 * L::BINS * sizeof(uint32_t);
-    unsigned long long *work = (unsigned long long *)counters;
-    uint32_t *n_block = (uint32_t *)((char *)counters + 8), *n_warp = (uint32_t *)((char *)counters + 12);
-    uint32_t *deep_work = (uint32_t *)((char *)counters + 16);
-    uint32_t *block_list = lists, *warp_list = lists + V.n;
+    ResolvedUnit *res = (ResolvedUnit *)S.resolved;
+    unsigned long long *work = (unsigned long long *)S.counters;
+    uint32_t *n_block = (uint32_t *)((char *)S.counters + 8), *n_warp = (uint32_t *)((char *)S.counters + 12);
+    uint32_t *deep_work = (uint32_t *)((char *)S.counters + 16);
+    const uint32_t *batch_status = (const uint32_t *)((char *)S.counters + 20);
+    uint32_t *block_list = S.lists, *warp_list = S.lists + V.n;
     cudaError_t e;
-    {
-        // static (staging ring) + dynamic (histograms) shared memory beyond 48 KB needs an opt-in
-        cudaFuncAttributes fa;
-        e = cudaFuncGetAttributes(&fa, pileup_deep_kernel<POSB>);
+    if (smem_deep > 48 * 1024) {
+        e = cudaFuncSetAttribute(pileup_deep_kernel<POSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_deep);
         if (e != cudaSuccess) return e;
-        if (smem_deep + fa.sharedSizeBytes > 48 * 1024) {
-            e = cudaFuncSetAttribute(pileup_deep_kernel<POSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_deep);
-            if (e != cudaSuccess) return e;
-        }
     }
+    R.mate = S.mate;
+    locate_kernel<<<(unsigned)((V.n + 255) / 256), 256, 0, stream>>>(R, V, res);
+    ++*launches;
     int ctas_per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pileup_warp_kernel<POSB, false>, WARPS_PER_CTA * 32, 0);
+    e = link_all ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pileup_warp_kernel<POSB, false>, WARPS_PER_CTA * 32, 0)
+                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pileup_warp_kernel<POSB, true>, WARPS_PER_CTA * 32, 0);
     if (e != cudaSuccess) return e;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     // persistent grid: a whole number of waves, never more CTAs than there is work
     int64_t want = (V.n + (int64_t)GRAB * WARPS_PER_CTA - 1) / ((int64_t)GRAB * WARPS_PER_CTA);
     int64_t grid = (int64_t)sm_count * ctas_per_sm;
     if (want < grid) grid = want < 1 ? 1 : want;
-    // EXPERIMENTAL (VFK_LIST_SHALLOW=1): the column kernel's list goes through the shallow warp kernel first; its work
-    // counter is the u64 at byte 24 of the scratch words (the locate pass's candidate sum has been consumed by then)
-    const bool list_shallow = env_flag("VFK_LIST_SHALLOW");
-    e = cudaMemsetAsync(counters, 0, list_shallow ? 32 : 24, stream);
-    if (e != cudaSuccess) return e;
-    if (R.col_off) {  // column store: SNV units from contiguous sector runs, the rest through the lists
-        // layout of the store the caller built: sector form unless both sides were told otherwise (see load_col_read)
-        const bool transposed = env_flag("VFK_COL_TRANSPOSED");
-        int col_ctas = 0;
-        const bool mq_select = env_flag("VFK_MQ_SELECT");
-        auto column_kernel = pileup_column_kernel<POSB, false, false, false>;
-        if (column_runs_gathered && mq_select) column_kernel = pileup_column_kernel<POSB, false, true, true>;
-        else if (column_runs_gathered) column_kernel = pileup_column_kernel<POSB, false, false, true>;
-        else if (transposed && mq_select) column_kernel = pileup_column_kernel<POSB, true, true, false>;
-        else if (transposed) column_kernel = pileup_column_kernel<POSB, true, false, false>;
-        else if (mq_select) column_kernel = pileup_column_kernel<POSB, false, true, false>;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&col_ctas, column_kernel, WARPS_PER_CTA * 32, 0);
+    if (link_all) {
+        e = launch_link(R, P, res, nullptr, nullptr, V.n, S.heads, S.n_buckets, S.next, S.column, S.claimed, S.mate, sm_count, stream, launches);
         if (e != cudaSuccess) return e;
-        int64_t col_grid = (int64_t)sm_count * std::max(col_ctas, 1);
-        if (want < col_grid) col_grid = want < 1 ? 1 : want;
-        uint4 *cunits = reinterpret_cast<uint4 *>((char *)res + (size_t)V.n * sizeof(ResolvedUnit));
-        if (!located) {  // lazy locate: every unit gets its window now, only the listed ones are searched afterwards
-            column_units_kernel<<<(unsigned)((V.n + 255) / 256), 256, 0, stream>>>(R, V, cunits);
-            ++*launches;
-        }
-        column_kernel<<<(unsigned)col_grid, WARPS_PER_CTA * 32, 0, stream>>>(R, cunits, located ? res : nullptr, V.n, P, out, work, block_list,
-                                                                             n_block, warp_list, n_warp);
-        if (!located) {
-            ++*launches;
-            locate_list_kernel<<<(unsigned)((V.n + 255) / 256), 256, 0, stream>>>(R, V, res, warp_list, n_warp, block_list, n_block);
-        }
-        if (list_shallow) {
-            ++*launches;
-            pileup_warp_kernel<POSB, true><<<(unsigned)grid, WARPS_PER_CTA * 32, 0, stream>>>(
-                R, res, V.n, V.ins_seq, P, out, (unsigned long long *)((char *)counters + 24), block_list, n_block, warp_list, n_warp);
-        }
+        pileup_warp_kernel<POSB, false><<<(unsigned)grid, WARPS_PER_CTA * 32, 0, stream>>>(R, res, V.n, V.ins_seq, P, out, work, block_list,
+                                                                                           n_block, warp_list, n_warp, batch_status);
     } else {
-        pileup_warp_kernel<POSB, false><<<(unsigned)grid, WARPS_PER_CTA * 32, 0, stream>>>(R, res, V.n, V.ins_seq, P, out, work,
-                                                                                           block_list, n_block, warp_list, n_warp);
+        pileup_warp_kernel<POSB, true><<<(unsigned)grid, WARPS_PER_CTA * 32, 0, stream>>>(R, res, V.n, V.ins_seq, P, out, work, block_list,
+                                                                                          n_block, warp_list, n_warp, batch_status);
     }
     ++*launches;
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    if (!link_all) {  // overlap partners of the reads inside the windows of the listed units (both lists)
+        e = launch_link(R, P, res, warp_list, n_warp, V.n, S.heads, S.n_buckets, S.next, S.column, S.claimed, S.mate, sm_count, stream, launches);
+        if (e != cudaSuccess) return e;
+        if (R.n_reads > WARP_PATH_MAX_CAND) {
+            e = launch_link(R, P, res, block_list, n_block, V.n, S.heads, S.n_buckets, S.next, S.column, S.claimed, S.mate, sm_count, stream,
+                            launches);
+            if (e != cudaSuccess) return e;
+        }
+    }
     int deep_ctas = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&deep_ctas, pileup_deep_kernel<POSB>, WARPS_PER_CTA * 32, smem_deep);
     if (e != cudaSuccess) return e;
     if (deep_ctas < 1) deep_ctas = 1;
     int64_t deep_grid = std::min<int64_t>((int64_t)sm_count * deep_ctas, (V.n + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
-    pileup_deep_kernel<POSB><<<(unsigned)deep_grid, WARPS_PER_CTA * 32, smem_deep, stream>>>(R, res, V.ins_seq, P, out, warp_list,
-                                                                                             n_warp, deep_work);
+    pileup_deep_kernel<POSB><<<(unsigned)deep_grid, WARPS_PER_CTA * 32, smem_deep, stream>>>(R, res, V.ins_seq, P, out, warp_list, n_warp,
+                                                                                             deep_work, batch_status);
     ++*launches;
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (R.n_reads > WARP_PATH_MAX_CAND) {  // only then can a column be too deep for the warp kernels
-        pileup_block_kernel<POSB><<<(unsigned)sm_count, WARPS_PER_CTA * 32, smem_block, stream>>>(R, res, V.ins_seq, P, out,
-                                                                                                  block_list, n_block);
+        pileup_block_kernel<POSB><<<(unsigned)sm_count, WARPS_PER_CTA * 32, smem_block, stream>>>(R, res, V.ins_seq, P, out, block_list,
+                                                                                                  n_block);
         ++*launches;
         e = cudaGetLastError();
     }
     return e;
 }
 
-static cudaError_t launch_pileup_sized(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, int max_l_qseq, vfk_counts *out,
-                                       void *resolved, void *counters, uint32_t *lists, int sm_count, cudaStream_t stream,
-                                       int *launches, bool located) {
-    ResolvedUnit *res = (ResolvedUnit *)resolved;
-    // read positions run 0 .. l_qseq (a read hanging in a trailing deletion reports l_qseq)
-    if (max_l_qseq < 256) return launch_posb<256>(R, V, P, out, res, counters, lists, sm_count, stream, launches, located);
-    if (max_l_qseq < 512) return launch_posb<512>(R, V, P, out, res, counters, lists, sm_count, stream, launches, located);
-    if (max_l_qseq < 1024) return launch_posb<1024>(R, V, P, out, res, counters, lists, sm_count, stream, launches, located);
-    return launch_posb<4096>(R, V, P, out, res, counters, lists, sm_count, stream, launches, located);
-}
-
-// the pileup kernels on units that launch_locate (or the host) has resolved
-cudaError_t launch_pileup_resolved(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, int max_l_qseq, vfk_counts *out,
-                                   void *resolved, void *counters, uint32_t *lists, int sm_count, cudaStream_t stream,
-                                   int *launches) {
-    return launch_pileup_sized(R, V, P, max_l_qseq, out, resolved, counters, lists, sm_count, stream, launches, true);
-}
-
+// locate + pileup kernels on a batch prep_kernel has prepared (R.end / R.ev / R.blk_incl valid, counters zeroed except the
+// batch status word)
 cudaError_t launch_pileup(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, int max_l_qseq, vfk_counts *out,
-                          void *resolved_scratch, void *counters, uint32_t *lists, int sm_count, cudaStream_t stream,
-                          int *launches) {
+                          const PileupScratch &S, int sm_count, cudaStream_t stream, int *launches, bool link_all) {
     if (V.n <= 0) return cudaSuccess;
-    if (R.col_off && !getenv("VFK_EAGER_LOCATE"))  // column store: the position index is searched for the listed units only
-        return launch_pileup_sized(R, V, P, max_l_qseq, out, resolved_scratch, counters, lists, sm_count, stream, launches, false);
-    cudaError_t e = launch_locate(R, V, resolved_scratch, nullptr, stream, launches);
-    if (e != cudaSuccess) return e;
-    return launch_pileup_resolved(R, V, P, max_l_qseq, out, resolved_scratch, counters, lists, sm_count, stream, launches);
+    // read positions run 0 .. l_qseq (a read hanging in a trailing deletion reports l_qseq)
+    if (max_l_qseq < 256) return launch_posb<256>(R, V, P, out, S, sm_count, stream, launches, link_all);
+    if (max_l_qseq < 512) return launch_posb<512>(R, V, P, out, S, sm_count, stream, launches, link_all);
+    if (max_l_qseq < 1024) return launch_posb<1024>(R, V, P, out, S, sm_count, stream, launches, link_all);
+    return launch_posb<4096>(R, V, P, out, S, sm_count, stream, launches, link_all);
+}
+
+// the located record of every unit, for the list-shaped auxiliary (vfk_values.cu)
+cudaError_t launch_locate_only(const ReadsDev &R, const UnitsDev &V, void *resolved, cudaStream_t stream, int *launches) {
+    if (V.n <= 0) return cudaSuccess;
+    locate_kernel<<<(unsigned)((V.n + 255) / 256), 256, 0, stream>>>(R, V, (ResolvedUnit *)resolved);
+    ++*launches;
+    return cudaGetLastError();
 }
 
 }  // namespace vfk

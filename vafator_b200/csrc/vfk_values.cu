@@ -12,26 +12,14 @@ namespace vfk {
 
 // packed value: mq | bq << 8 | qpos << 16 | ref << 28 | alt << 29  (same as the pileup kernel)
 __global__ void __launch_bounds__(256)
-values_kernel(ReadsDev R, UnitsDev V, vfk_params P, int32_t max_per_unit, uint32_t *__restrict__ values,
-              int32_t *__restrict__ n_values) {
+values_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_units, const uint8_t *__restrict__ ins_seq, vfk_params P,
+              int32_t max_per_unit, uint32_t *__restrict__ values, int32_t *__restrict__ n_values) {
     const int lane = threadIdx.x & 31;
     const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (u >= V.n) return;
-    // locate (one warp, lane 0 searches: this path is not performance critical)
-    const int32_t tid = __ldg(V.tid + u), col = __ldg(V.pos + u);
-    const bool known = tid >= 0 && tid < R.n_contigs;
-    const int64_t c0 = known ? __ldg(R.contig_off + tid) : 0, c1 = known ? __ldg(R.contig_off + tid + 1) : 0;
-    int64_t a = c0, b = c1;
-    while (a < b) {
-        const int64_t m = (a + b) >> 1;
-        if (__ldg(&R.sb[m].x) > col) b = m; else a = m + 1;
-    }
-    ResolvedUnit ru;
-    ru.col = col; ru.meta = __ldg(V.meta + u); ru.len = __ldg(V.length + u); ru.ins_off = __ldg(V.seq_off + u);
-    ru.hi = (uint32_t)a; ru.lo = a > c0 ? (uint32_t)__ldg(&R.sb[a - 1].y) : (uint32_t)a;
-    ru.stop = V.stop ? __ldg(V.stop + u) : 0x7FFFFFFF; ru.c1 = (uint32_t)c1;
+    if (u >= n_units) return;
+    // the units have been located and the reads of their windows linked (locate_kernel, link kernels) by this call
     Unit U;
-    unit_from(ru, V.ins_seq, U);
+    unit_from(res[u], ins_seq, U);
     uint32_t *out = values + (size_t)u * max_per_unit;
     int n = 0;
     for (int64_t base = U.lo; base < U.hi; base += 32) {
@@ -87,11 +75,12 @@ ranksum_kernel(int64_t n_pairs, const uint32_t *__restrict__ alt, const int64_t 
     }
 }
 
-cudaError_t launch_values(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, int32_t max_per_unit, uint32_t *values,
-                          int32_t *n_values, cudaStream_t stream, int *launches) {
-    if (V.n <= 0) return cudaSuccess;
-    const int64_t threads = V.n * 32;
-    values_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(R, V, P, max_per_unit, values, n_values);
+cudaError_t launch_values(const ReadsDev &R, const void *resolved, int64_t n_units, const uint8_t *ins_seq, const vfk_params &P,
+                          int32_t max_per_unit, uint32_t *values, int32_t *n_values, cudaStream_t stream, int *launches) {
+    if (n_units <= 0) return cudaSuccess;
+    const int64_t threads = n_units * 32;
+    values_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(R, (const ResolvedUnit *)resolved, n_units, ins_seq, P, max_per_unit,
+                                                                         values, n_values);
     ++*launches;
     return cudaGetLastError();
 }

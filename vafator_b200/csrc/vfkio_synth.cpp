@@ -321,8 +321,13 @@ int check_cfg(const vfkio_synth_cfg *c) {
     if (c->tile_stride < 1024) return vfkio_fail(VFK_EINVAL, "synth: tile_stride must be >= 1024");
     if ((int64_t)c->tile_offset + (int64_t)c->tile_stride * c->tiles_per_contig > (int64_t)INT32_MAX - 8192)
         return vfkio_fail(VFK_EINVAL, "synth: contig exceeds int32 coordinates");
+    if (c->g_first < 0 || c->g_count < 0 || c->g_first + c->g_count > (int64_t)c->n_contigs * c->tiles_per_contig)
+        return vfkio_fail(VFK_EINVAL, "synth: generated tile range outside the genome");
     return VFK_OK;
 }
+// the tiles this call generates: [first, first + count) of the genome's global tile index
+inline int64_t gen_first(const vfkio_synth_cfg *c) { return c->g_count > 0 ? c->g_first : 0; }
+inline int64_t gen_count(const vfkio_synth_cfg *c) { return c->g_count > 0 ? c->g_count : (int64_t)c->n_contigs * c->tiles_per_contig; }
 
 }  // namespace
 
@@ -330,7 +335,7 @@ extern "C" int vfkio_synth_plan_reads(const vfkio_synth_cfg *c, vfkio_synth_plan
     int rc = check_cfg(c);
     if (rc) return rc;
     if (!plan) return vfkio_fail(VFK_EINVAL, "synth: NULL plan");
-    const int64_t tiles = (int64_t)c->n_contigs * c->tiles_per_contig;
+    const int64_t tiles = gen_count(c), g0 = gen_first(c);
     int64_t nr = 0, nc = 0, ns = 0, nq = 0;
 #pragma omp parallel
     {
@@ -338,7 +343,7 @@ extern "C" int vfkio_synth_plan_reads(const vfkio_synth_cfg *c, vfkio_synth_plan
         TileCtx ctx;
 #pragma omp for schedule(dynamic, 64) reduction(+ : nr, nc, ns, nq)
         for (int64_t g = 0; g < tiles; ++g) {
-            gen_tile(c, (int32_t)(g / c->tiles_per_contig), g % c->tiles_per_contig, buf, ctx);
+            gen_tile(c, (int32_t)((g0 + g) / c->tiles_per_contig), (g0 + g) % c->tiles_per_contig, buf, ctx);
             int64_t tcg = 0, tsq = 0, tql = 0;
             for (const ReadOut &o : buf) {
                 tcg += (int64_t)o.cigar.size();
@@ -361,7 +366,7 @@ extern "C" int vfkio_synth_fill_reads(const vfkio_synth_cfg *c, const vfkio_synt
     int rc = check_cfg(c);
     if (rc) return rc;
     if (!plan || !out || !tile_sizes) return vfkio_fail(VFK_EINVAL, "synth: NULL argument");
-    const int64_t tiles = (int64_t)c->n_contigs * c->tiles_per_contig;
+    const int64_t tiles = gen_count(c), g0 = gen_first(c);
     // per-tile sizes (from the plan pass) -> offsets
     std::vector<int64_t> tr(tiles + 1, 0), tc(tiles + 1, 0), ts(tiles + 1, 0), tq(tiles + 1, 0);
     for (int64_t g = 0; g < tiles; ++g) {
@@ -383,8 +388,8 @@ extern "C" int vfkio_synth_fill_reads(const vfkio_synth_cfg *c, const vfkio_synt
         TileCtx ctx;
 #pragma omp for schedule(dynamic, 64)
         for (int64_t g = 0; g < tiles; ++g) {
-            const int32_t t = (int32_t)(g / c->tiles_per_contig);
-            gen_tile(c, t, g % c->tiles_per_contig, buf, ctx);
+            const int32_t t = (int32_t)((g0 + g) / c->tiles_per_contig);
+            gen_tile(c, t, (g0 + g) % c->tiles_per_contig, buf, ctx);
             if ((int64_t)buf.size() != tile_sizes[4 * g]) continue;  // inconsistent plan: caught by the caller's checks
             int64_t i = tr[g], ic = tc[g], is = ts[g], iq = tq[g];
             for (const ReadOut &o : buf) {

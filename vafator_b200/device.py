@@ -23,28 +23,23 @@ COUNTS_DTYPE = np.dtype([("dp", "<i4"), ("n_amb", "<i4"), ("ac_ref", "<i4"), ("a
                          ("n_cover", "<u4"), ("n_col", "<u4")])
 STATS_DTYPE = np.dtype([("z", "<f8", (3,)), ("p", "<f8", (3,)), ("pu", "<f8"), ("pw", "<f8"), ("k", "<i4"),
                         ("pad", "<i4")])
-HOT_DTYPE = np.dtype([("pos", "<i4"), ("span", "<u4"), ("fmk", "<u4"), ("pay", "<u4")])
-COLD_DTYPE = np.dtype([("cigar_off", "<u4"), ("n_cigar", "<u4"), ("l_qseq", "<u4"), ("event", "<u4")])
 assert COUNTS_DTYPE.itemsize == 80 and STATS_DTYPE.itemsize == 72
 
-ST_KIND_MASK, ST_DEFERRED, ST_READLEN = 0x3, 0x10, 0x20
+ST_KIND_MASK, ST_DEFERRED, ST_READLEN, ST_BADBATCH = 0x3, 0x10, 0x20, 0x40
 
 
 class VfkError(RuntimeError):
     pass
 
 
+_READ_ARRAYS = ("pos", "flag", "mapq", "l_qseq", "n_cigar", "cigar_off", "seq_off", "qual_off", "cigar", "seq", "qual",
+                "mtid", "mpos", "isize", "qname_id", "qname_hash")
+
+
 class _ReadBatchC(C.Structure):
-    _fields_ = [("n_reads", C.c_int64), ("n_contigs", C.c_int32), ("max_l_qseq", C.c_int32),
-                ("contig_off", C.c_void_p), ("hot", C.c_void_p), ("cold", C.c_void_p), ("mate", C.c_void_p),
-                ("sb", C.c_void_p), ("cigar", C.c_void_p), ("payload", C.c_void_p),
-                ("n_cigar_words", C.c_int64), ("n_sectors", C.c_int64),
-                ("col_wbase", C.c_void_p), ("col_off", C.c_void_p), ("col_sectors", C.c_void_p),
-                ("n_col_windows", C.c_int64), ("n_col_sectors", C.c_int64)]
-
-
-class _ColPlanC(C.Structure):
-    _fields_ = [("n_windows", C.c_int64), ("n_sectors", C.c_int64)]
+    _fields_ = ([("n_reads", C.c_int64), ("n_contigs", C.c_int32), ("max_l_qseq", C.c_int32), ("contig_off", C.c_void_p)] +
+                [(k, C.c_void_p) for k in _READ_ARRAYS] +
+                [("n_cigar_words", C.c_int64), ("n_seq_bytes", C.c_int64), ("n_qual_bytes", C.c_int64)])
 
 
 class _VariantBatchC(C.Structure):
@@ -69,11 +64,6 @@ class _IoReadsC(C.Structure):
     _fields_ = [("n", C.c_int64), ("n_contigs", C.c_int32), ("pad", C.c_int32)] + [(k, C.c_void_p) for k in (
         "tid", "pos", "flag", "mapq", "l_qseq", "n_cigar", "cigar_off", "seq_off", "qual_off", "cigar", "seq", "qual",
         "mtid", "mpos", "isize", "qname_id", "qname_hash")]
-
-
-class _PlanC(C.Structure):
-    _fields_ = [("n_placed", C.c_int64), ("n_cigar_words", C.c_int64), ("n_sectors", C.c_int64),
-                ("max_l_qseq", C.c_int32), ("pad", C.c_int32)]
 
 
 _IO_DT = dict(tid=np.int32, pos=np.int32, flag=np.uint16, mapq=np.uint8, l_qseq=np.int32, n_cigar=np.int32,
@@ -119,10 +109,6 @@ def libvfk():
         lib.vfk_annotate_host_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                                 C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.vfk_wait.argtypes = [C.c_void_p, C.c_int]
-        lib.vfk_zero_copy_batches.restype = C.c_int64
-        lib.vfk_zero_copy_batches.argtypes = [C.c_void_p]
-        lib.vfk_column_batches.restype = C.c_int64
-        lib.vfk_column_batches.argtypes = [C.c_void_p]
         lib.vfk_transfer_stats.restype = C.c_int
         lib.vfk_transfer_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         lib.vfk_annotate_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
@@ -165,60 +151,57 @@ def _empty(n, dtype, pinned: bool):
     return np.empty(n, dtype)
 
 
-@dataclass
-class PackedReads:
-    """Host copy of the HBM layout (include/vfk.h vfk_read_batch)."""
-    contigs: list
-    contig_off: np.ndarray
-    hot: np.ndarray
-    cold: np.ndarray
-    mate: np.ndarray
-    sb: np.ndarray        # [n, 2] int32 {start, back}
-    cigar: np.ndarray
-    payload: np.ndarray
-    max_l_qseq: int
-    # column store (include/vfk.h), optional
-    col_wbase: Optional[np.ndarray] = None
-    col_off: Optional[np.ndarray] = None
-    col_sectors: Optional[np.ndarray] = None
+class HostReads:
+    """The canonical columnar batch (include/vfk.h vfk_read_batch) in host memory: the placed reads of a ReadBatch, array
+    by array as the decoder wrote them, plus the batch metadata (contig table, longest read).  Nothing is derived from the
+    reads here -- spans, position index, CIGAR shapes, mate pairing are the kernels' work.  `pinned`: the arrays are
+    copied once into page-locked memory (the decoder / generator can also write there directly: bamio, synth)."""
 
-    @property
-    def has_columns(self) -> bool:
-        return self.col_off is not None
+    def __init__(self, batch: ReadBatch, pinned: bool = False):
+        n = batch.n_placed
+        self.batch = batch
+        self.contigs = list(batch.contigs)
+        self.n_reads = n
+        self.contig_off = batch.contig_off
+        self.max_l_qseq = batch.max_l_qseq
+        self.arrays = {}
+        for k in _READ_ARRAYS:
+            a = getattr(batch, k)
+            if k not in ("cigar", "seq", "qual"):
+                a = a[:n]
+            a = np.ascontiguousarray(a, dtype=_IO_DT[k])
+            if pinned and not getattr(batch, "pinned", False):
+                p = _empty(a.shape[0], a.dtype, True)
+                p[:] = a
+                a = p
+            self.arrays[k] = a
 
     @property
     def starts(self):
-        return self.sb[:, 0]
-
-    @property
-    def n_reads(self):
-        return int(self.hot.shape[0])
+        return self.arrays["pos"]
 
     def array_names(self):
-        base = ("contig_off", "hot", "cold", "mate", "sb", "cigar", "payload")
-        return base + (("col_wbase", "col_off", "col_sectors") if self.has_columns else ())
+        return ("contig_off",) + _READ_ARRAYS
 
     def nbytes(self) -> int:
-        return int(sum(getattr(self, k).nbytes for k in self.array_names()))
+        return int(self.contig_off.nbytes + sum(a.nbytes for a in self.arrays.values()))
 
-    def c_struct(self, arrays: Optional[Dict[str, int]] = None) -> _ReadBatchC:
-        p = arrays or {k: getattr(self, k).ctypes.data for k in self.array_names()}
+    def c_struct(self, ptrs: Optional[Dict[str, int]] = None) -> _ReadBatchC:
         s = _ReadBatchC()
         s.n_reads, s.n_contigs, s.max_l_qseq = self.n_reads, len(self.contigs), self.max_l_qseq
-        s.n_cigar_words, s.n_sectors = int(self.cigar.shape[0]), int(self.payload.shape[0] // 32)
-        if self.has_columns:
-            s.n_col_windows, s.n_col_sectors = int(self.col_off.shape[0] - 1), int(self.col_sectors.shape[0] // 32)
-        for k, v in p.items():
+        s.n_cigar_words = int(self.arrays["cigar"].shape[0])
+        s.n_seq_bytes = int(self.arrays["seq"].shape[0])
+        s.n_qual_bytes = int(self.arrays["qual"].shape[0])
+        if ptrs is None:
+            ptrs = {k: a.ctypes.data for k, a in self.arrays.items()}
+            ptrs["contig_off"] = self.contig_off.ctypes.data
+        for k, v in ptrs.items():
             setattr(s, k, v)
         return s
 
 
-def link_mates(batch: ReadBatch, params: ParamsC) -> np.ndarray:
-    s, keep = _io_reads(batch)
-    n_placed = int(np.count_nonzero(batch.tid >= 0))
-    mate = np.empty(n_placed, np.uint32)
-    _io_check(libio().vfkio_link_mates(C.byref(s), C.byref(params), C.c_void_p(mate.ctypes.data)))
-    return mate
+def host_reads(batch: ReadBatch, pinned: bool = False) -> HostReads:
+    return HostReads(batch, pinned=pinned)
 
 
 def read_passes(batch: ReadBatch, params: ParamsC) -> np.ndarray:
@@ -229,67 +212,6 @@ def read_passes(batch: ReadBatch, params: ParamsC) -> np.ndarray:
     if params.ignore_orphans:
         ok &= ~(((f & 1) != 0) & ((f & 2) == 0))
     return ok & (batch.tid >= 0)
-
-
-def pack_reads(batch: ReadBatch, params: ParamsC, pinned: bool = False, mate: np.ndarray = None,
-               columns: bool = False) -> PackedReads:
-    """Canonical batch -> HBM layout (+ mate links under `params`, unless given: a slice of a larger batch
-    must carry the links computed on the whole batch).  columns=True also builds the reference-anchored column
-    store (include/vfk.h) the SNV kernel reads; it bakes in the read filter of `params`."""
-    s, keep = _io_reads(batch)
-    plan = _PlanC()
-    _io_check(libio().vfkio_pack_plan(C.byref(s), C.byref(plan)))
-    n = plan.n_placed
-    contig_off = np.empty(len(batch.contigs) + 1, np.int64)
-    hot = _empty(n, HOT_DTYPE, pinned)
-    cold = _empty(n, COLD_DTYPE, pinned)
-    sb = _empty(2 * n, np.int32, pinned)
-    cigar = _empty(max(plan.n_cigar_words, 1), np.uint32, pinned)[:plan.n_cigar_words]
-    payload = _empty(plan.n_sectors * 32, np.uint8, pinned)
-    _io_check(libio().vfkio_pack(C.byref(s), C.byref(plan), C.c_void_p(contig_off.ctypes.data),
-                                 C.c_void_p(hot.ctypes.data), C.c_void_p(cold.ctypes.data),
-                                 C.c_void_p(sb.ctypes.data),
-                                 C.c_void_p(cigar.ctypes.data), C.c_void_p(payload.ctypes.data)))
-    mate_out = _empty(n, np.uint32, pinned)
-    if mate is None:
-        _io_check(libio().vfkio_link_mates(C.byref(s), C.byref(params), C.c_void_p(mate_out.ctypes.data)))
-    else:
-        mate_out[:] = np.asarray(mate, np.uint32)[:n]
-    mate = mate_out
-    packed = PackedReads(list(batch.contigs), contig_off, hot, cold, mate, sb.reshape(-1, 2), cigar, payload,
-                         int(plan.max_l_qseq))
-    if columns:
-        wbase = np.empty(len(batch.contigs) + 1, np.int64)
-        cp = _ColPlanC()
-        rc = libio().vfkio_columns_plan(C.byref(s), C.c_void_p(wbase.ctypes.data), C.byref(cp))
-        if rc == -4:  # VFK_EUNSUPPORTED: more than 2^32 sectors -- the batch keeps its read-major layout only
-            import warnings
-            warnings.warn("column store not built (%s): SNV units take the read-major kernels" %
-                          libio().vfkio_last_error().decode())
-            return packed
-        _io_check(rc)
-        # Reads dominated by reference skips (RNA-seq: a spliced read leaves a sector in every window of every intron
-        # it spans) would make the store many times the size of the reads themselves; a fully aligned read leaves
-        # ~1.7 column sectors per payload sector.  Such a batch keeps its read-major layout only.
-        if cp.n_sectors > 16 * plan.n_sectors + 4 * n:
-            import warnings
-            warnings.warn("column store not built (%d sectors for %d reads: reference skips dominate): SNV units take "
-                          "the read-major kernels" % (cp.n_sectors, n))
-            return packed
-        woff = _empty(cp.n_windows + 1, np.uint32, pinned)
-        sectors = _empty(cp.n_sectors * 32, np.uint8, pinned)
-        _io_check(libio().vfkio_columns_fill(C.byref(s), C.byref(params), C.c_void_p(mate.ctypes.data),
-                                             C.c_void_p(wbase.ctypes.data), C.byref(cp), C.c_void_p(woff.ctypes.data),
-                                             C.c_void_p(sectors.ctypes.data)))
-        if os.environ.get("VFK_COL_TRANSPOSED", "")[:1] == "1":
-            # EXPERIMENTAL, not yet verified on a GPU: the window-transposed form (a column reads 10 of 32 bytes per
-            # read); libvfk.so picks the matching kernel instantiation from the same variable (vfk_pileup.cu)
-            transposed = _empty(cp.n_sectors * 32, np.uint8, pinned)
-            _io_check(libio().vfkio_columns_transpose(C.c_void_p(woff.ctypes.data), C.c_int64(cp.n_windows),
-                                                      C.c_void_p(sectors.ctypes.data), C.c_void_p(transposed.ctypes.data)))
-            sectors = transposed
-        packed.col_wbase, packed.col_off, packed.col_sectors = wbase, woff, sectors
-    return packed
 
 
 def units_c_struct(u: VariantUnits, stop: Optional[np.ndarray], ptrs: Optional[Dict[str, int]] = None) -> _VariantBatchC:
@@ -306,20 +228,21 @@ def units_c_struct(u: VariantUnits, stop: Optional[np.ndarray], ptrs: Optional[D
 
 
 class DeviceReads:
-    """A read batch resident in HBM (torch tensors own the memory)."""
+    """A canonical read batch resident in HBM (torch tensors own the memory): the host arrays, copied verbatim."""
 
-    def __init__(self, packed: PackedReads, device, non_blocking: bool = True):
+    def __init__(self, host: HostReads, device, non_blocking: bool = True):
         import torch
-        self.packed = packed
+        self.host = host
         self.t = {}
-        for k in packed.array_names():
-            a = getattr(packed, k)
+        src = dict(host.arrays)
+        src["contig_off"] = host.contig_off
+        for k, a in src.items():
             h = torch.from_numpy(a.view(np.uint8).reshape(-1)) if a.size else torch.zeros(16, dtype=torch.uint8)
             self.t[k] = h.to(device, non_blocking=non_blocking) if a.size else h.to(device)
-        self.c = packed.c_struct({k: v.data_ptr() for k, v in self.t.items()})
+        self.c = host.c_struct({k: v.data_ptr() for k, v in self.t.items()})
 
     def nbytes(self):
-        return self.packed.nbytes()
+        return self.host.nbytes()
 
 
 class DeviceUnits:
@@ -372,8 +295,11 @@ class Device:
     def _stream(self):
         return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
 
-    def upload_reads(self, packed: PackedReads) -> DeviceReads:
-        return DeviceReads(packed, self.device)
+    def upload_reads(self, reads) -> DeviceReads:
+        """reads: a HostReads, or a ReadBatch (wrapped first)."""
+        if isinstance(reads, ReadBatch):
+            reads = HostReads(reads)
+        return DeviceReads(reads, self.device)
 
     def upload_units(self, units: VariantUnits, stop: Optional[np.ndarray] = None) -> DeviceUnits:
         return DeviceUnits(units, stop, self.device)
@@ -435,7 +361,7 @@ class Device:
                                            C.c_void_p(out.data_ptr()), self._stream()))
         return out.cpu().numpy().view(np.uint64).reshape(n, 3)
 
-    def annotate_host(self, packed: PackedReads, units: VariantUnits, stop, params: ParamsC, eaf: np.ndarray,
+    def annotate_host(self, packed: HostReads, units: VariantUnits, stop, params: ParamsC, eaf: np.ndarray,
                       fpr: float, error_rate: float, counts_out=None, stats_out=None):
         """HOST buffers in, HOST results out (copies inside): the end-to-end entry point."""
         n = units.n_units
@@ -450,7 +376,7 @@ class Device:
                                           C.c_void_p(counts.ctypes.data), C.c_void_p(stats.ctypes.data)))
         return counts, stats
 
-    def annotate_host_async(self, packed: PackedReads, units: VariantUnits, stop, params: ParamsC, eaf: np.ndarray,
+    def annotate_host_async(self, packed: HostReads, units: VariantUnits, stop, params: ParamsC, eaf: np.ndarray,
                             fpr: float, error_rate: float, counts_out: np.ndarray, stats_out: np.ndarray):
         """Enqueue one batch on one of the two staging slots; returns a ticket for `wait`.  All host
         arrays (inputs and outputs) must stay alive and untouched until `wait(ticket)` returns."""
@@ -470,18 +396,11 @@ class Device:
         _check(self.lib.vfk_wait(self.h, C.c_int(ticket)))
         self.__dict__.get("_inflight", {}).pop(ticket, None)
 
-    def zero_copy_batches(self) -> int:
-        return int(self.lib.vfk_zero_copy_batches(self.h))
-
-    def column_batches(self) -> int:
-        return int(self.lib.vfk_column_batches(self.h))
-
     def transfer_stats(self) -> Dict[str, int]:
         """Host entry point accounting since the handle was created (vfk_transfer_stats)."""
         out = (C.c_int64 * 4)()
         _check(self.lib.vfk_transfer_stats(self.h, out))
-        return dict(staged_bytes=int(out[0]), zero_copy_batches=int(out[1]), zero_copy_hot_batches=int(out[2]),
-                    host_located_batches=int(out[3]))
+        return dict(staged_bytes=int(out[0]), zero_copy_batches=int(out[1]), staged_batches=int(out[2]), d2h_bytes=int(out[3]))
 
     def to_host(self, buf, dtype, n):
         return buf.cpu().numpy().view(dtype)[:n].copy()

@@ -1,7 +1,9 @@
 """Host-side composition of the annotation around the two device stages.
 
-    reads (ReadBatch) --pack--> HBM layout --vfk_pileup--> integer counts per unit
-    counts + expected VAF --vfk_epilogue--> FP64 z / p / pu / pw / k per reported row
+    reads (ReadBatch: the canonical columnar batch, as decoded) + units + expected VAF
+        --vfk_annotate_host_async--> integer counts and FP64 z / p / pu / pw / k per unit
+    (one call per BAM: read preparation, locate, pileup and epilogue kernels, one copy in, one copy out;
+     two batches in flight)
 
 What stays on the host is what the reference also does in Python after its arithmetic
 (vafator/annotator.py:260-432): merging replicate BAMs, choosing which values a Counter / dict
@@ -365,11 +367,9 @@ class Engine:
     format_parallel_from = 200_000                                               # ... of record sets at least this large
 
     def __init__(self, device_index: int = 0, min_mapq: int = 0, min_baseq: int = 29, include_ambiguous: bool = True,
-                 fpr: float = 5e-7, error_rate: float = 1e-3, devices: Optional[Sequence[int]] = None, columns: bool = True):
+                 fpr: float = 5e-7, error_rate: float = 1e-3, devices: Optional[Sequence[int]] = None):
         """`devices`: CUDA device indexes to shard the pileup over (interval x BAM shards, one host
-        thread per device, no collective); default: just `device_index`.  `columns`: also build the
-        reference-anchored column store of every batch (include/vfk.h) -- SNV units are then evaluated from it."""
-        self.columns = columns
+        thread per device, no collective); default: just `device_index`."""
         self.dev = _dev.Device(device_index)
         self.extra_devs = [_dev.Device(d) for d in (devices or [])[1:]] if devices and len(devices) > 1 else []
         self.params = _dev.make_params(min_mapq=min_mapq, min_baseq=min_baseq, include_ambiguous=include_ambiguous)
@@ -381,74 +381,94 @@ class Engine:
             d.close()
 
     # ---- device stages on host arrays -------------------------------------------------------
-    def prepack(self, batch: ReadBatch) -> None:
-        """Pack `batch` into the HBM layout on the host now (native code, no CUDA call: safe on a helper thread
-        while the device works on another batch); `_device_reads` then only uploads it."""
-        packed = _dev.pack_reads(batch, self.params, columns=self.columns)
-        with self._cache_lock():
-            self.__dict__.setdefault("_packed", {})[id(batch)] = (batch, packed)
-
     def _cache_lock(self):
         import threading
         return self.__dict__.setdefault("_lock", threading.Lock())
 
+    def _host_reads(self, batch: ReadBatch) -> "_dev.HostReads":
+        """The batch as the C ABI takes it (no copy: the arrays of the ReadBatch themselves; page-locked when the decoder
+        wrote them that way)."""
+        with self._cache_lock():
+            cache = self.__dict__.setdefault("_hreads", {})
+            hit = cache.get(id(batch))
+            if hit is None:
+                hit = cache[id(batch)] = (batch, _dev.HostReads(batch))
+        return hit[1]
+
     def _device_reads(self, batch: ReadBatch):
+        """Device-resident copy (only the list-shaped auxiliary of the replicate merge needs one)."""
         with self._cache_lock():
             cache = self.__dict__.setdefault("_dreads", {})
             hit = cache.get(id(batch))
-            pre = self.__dict__.get("_packed", {}).pop(id(batch), None)
         if hit is None:
-            packed = pre[1] if pre is not None else _dev.pack_reads(batch, self.params, columns=self.columns)
-            hit = (batch, self.dev.upload_reads(packed))
+            hit = (batch, self.dev.upload_reads(self._host_reads(batch)))
             with self._cache_lock():
                 cache[id(batch)] = hit
         return hit[1]
 
     def release_reads(self, batches: Optional[Sequence[ReadBatch]] = None):
-        """Drop the device (and prepacked host) copies of `batches`, or of every batch."""
+        """Drop the cached host wrappers / device copies of `batches`, or of every batch."""
         with self._cache_lock():
-            if batches is None:
-                self.__dict__.pop("_dreads", None)
-                self.__dict__.pop("_packed", None)
-            else:
-                for b in batches:
-                    self.__dict__.get("_dreads", {}).pop(id(b), None)
-                    self.__dict__.get("_packed", {}).pop(id(b), None)
+            for name in ("_dreads", "_hreads"):
+                if batches is None:
+                    self.__dict__.pop(name, None)
+                else:
+                    for b in batches:
+                        self.__dict__.get(name, {}).pop(id(b), None)
 
-    def _pileup_sharded(self, batch: ReadBatch, units: VariantUnits, stop: np.ndarray) -> np.ndarray:
-        """Interval shards of one BAM over several devices (vafator_b200/sharding.py)."""
+    def submit(self, batch: ReadBatch, units: VariantUnits, stop: np.ndarray, eaf_units: np.ndarray):
+        """Enqueue one (BAM, units) batch on the device through the host entry point (vfk_annotate_host_async: one copy in,
+        kernels, one copy out; the library keeps two batches in flight).  Returns a job for `finish`."""
+        n = units.n_units
+        counts = np.empty(n, _dev.COUNTS_DTYPE)
+        stats = np.empty(n, _dev.STATS_DTYPE)
+        if n == 0:
+            return (None, counts, stats)
+        if self.extra_devs and n >= 2 * (1 + len(self.extra_devs)):
+            in_order = np.all((units.tid[1:] > units.tid[:-1]) | ((units.tid[1:] == units.tid[:-1]) & (units.pos[1:] >= units.pos[:-1])))
+            if in_order:
+                c, s = self._annotate_sharded(batch, units, stop, eaf_units)
+                return (None, c, s)
+        ticket = self.dev.annotate_host_async(self._host_reads(batch), units, stop, self.params, eaf_units, self.fpr, self.error_rate,
+                                              counts, stats)
+        return (ticket, counts, stats)
+
+    def finish(self, job):
+        ticket, counts, stats = job
+        if ticket is not None:
+            self.dev.wait(ticket)
+        return counts, stats
+
+    def _annotate_sharded(self, batch: ReadBatch, units: VariantUnits, stop: np.ndarray, eaf_units: np.ndarray):
+        """Interval shards of one BAM over several devices (vafator_b200/sharding.py): one host thread per device, each
+        shard a self-contained slice of the canonical batch; no collective, the per-unit records are concatenated."""
         from concurrent.futures import ThreadPoolExecutor
         from . import sharding
         devs = [self.dev] + self.extra_devs
-        mate = _dev.link_mates(batch, self.params)
         passes = _dev.read_passes(batch, self.params)
         shards = sharding.plan_shards(batch, units, len(devs), passes, stop)
 
         def work(k):
             sh, dev = shards[k], devs[k % len(devs)]
-            sub, sub_mate = sharding.slice_reads(batch, mate, sh.read_lo, sh.read_hi)
+            sub = sharding.slice_reads(batch, sh.read_lo, sh.read_hi)
             su = sharding.slice_units(units, sh.unit_lo, sh.unit_hi)
-            dreads = dev.upload_reads(_dev.pack_reads(sub, self.params, mate=sub_mate, columns=self.columns))
-            buf = dev.pileup(dreads, dev.upload_units(su, stop[sh.unit_lo:sh.unit_hi]), self.params)
-            return dev.to_host(buf, _dev.COUNTS_DTYPE, su.n_units)
+            return dev.annotate_host(_dev.HostReads(sub), su, stop[sh.unit_lo:sh.unit_hi], self.params, eaf_units[sh.unit_lo:sh.unit_hi],
+                                     self.fpr, self.error_rate)
 
         with ThreadPoolExecutor(len(devs)) as pool:
             parts = list(pool.map(work, range(len(shards))))
-        return np.concatenate(parts)
+        return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+
+    def pileup_stats(self, batch: ReadBatch, units: VariantUnits, stop: np.ndarray, eaf_units) -> Tuple[np.ndarray, np.ndarray]:
+        """(counts, stats) per unit of one BAM: the fused device call."""
+        eaf_units = np.broadcast_to(np.asarray(eaf_units, np.float64), (units.n_units,)).copy()
+        return self.finish(self.submit(batch, units, stop, eaf_units))
 
     def pileup(self, batch: ReadBatch, units: VariantUnits, stop: np.ndarray) -> np.ndarray:
-        if units.n_units == 0:
-            return np.zeros(0, _dev.COUNTS_DTYPE)
-        if self.extra_devs and units.n_units >= 2 * (1 + len(self.extra_devs)):
-            in_order = np.all((units.tid[1:] > units.tid[:-1]) | ((units.tid[1:] == units.tid[:-1]) & (units.pos[1:] >= units.pos[:-1])))
-            if in_order:
-                return self._pileup_sharded(batch, units, stop)
-        dreads = self._device_reads(batch)
-        dunits = self.dev.upload_units(units, stop)
-        buf = self.dev.pileup(dreads, dunits, self.params)
-        return self.dev.to_host(buf, _dev.COUNTS_DTYPE, units.n_units)
+        return self.pileup_stats(batch, units, stop, 0.5)[0]
 
     def epilogue(self, counts: np.ndarray, eaf: np.ndarray) -> np.ndarray:
+        """FP64 statistics of explicit count records (merged replicates, rows without a unit of their own)."""
         n = len(counts)
         if n == 0:
             return np.zeros(0, _dev.STATS_DTYPE)
@@ -457,6 +477,31 @@ class Engine:
         e = torch.from_numpy(np.ascontiguousarray(eaf, np.float64)).to(self.dev.device)
         buf = self.dev.epilogue(n, c, e, self.fpr, self.error_rate)
         return self.dev.to_host(buf, _dev.STATS_DTYPE, n)
+
+    def _row_stats(self, res: "BamResult", counts_u: np.ndarray, stats_u: np.ndarray, eaf_row: np.ndarray) -> np.ndarray:
+        """Statistics on the row table.  A row backed by a unit whose counts the host did not touch takes the unit's
+        statistics as the fused call computed them; the others (no unit of their own: second ALT of an indel, MNV, record
+        outside its group's span; or a count the reference's key lookup zeroes) are evaluated from the row's counts."""
+        rc = res.row_counts
+        nrow = len(rc)
+        st = np.zeros(nrow, _dev.STATS_DTYPE)
+        if nrow == 0:
+            return st
+        ru = res.row_unit
+        have = ru >= 0
+        same = have.copy()
+        if len(counts_u):
+            cu = counts_u[np.where(have, ru, 0)]
+            for f in ("dp", "ac_alt", "ac_ref"):
+                same &= rc[f] == cu[f]
+            same &= np.all(rc["s2"] == cu["s2"], axis=1)
+            st[same] = stats_u[ru[same]]
+        else:
+            same[:] = False
+        fix = ~same
+        if fix.any():
+            st[fix] = self.epilogue(rc[fix], eaf_row[fix])
+        return st
 
     def values(self, batch: ReadBatch, units: VariantUnits, stop: np.ndarray):
         """Packed per-read values of the units' REF / ALT lists: list of uint32 arrays."""
@@ -504,22 +549,40 @@ class Engine:
         fmt = SampleFormatter(rows)
         per_sample = OrderedDict()
         units_of_header = {}
+        # every (sample, BAM) is one fused device call; they are submitted ahead of being collected so that the copies of one
+        # batch overlap the kernels of the previous one (two staging slots per device)
+        tasks = []
         for sample, batches in bams.items():
-            eaf_row = np.asarray(eaf[sample], np.float64)[rows.rec] if rows.n_rows else np.zeros(0)
-            results, stats = [], []
             for batch in batches:
                 contigs_key = tuple(batch.contigs)
                 if contigs_key not in units_of_header:  # BAMs of one run nearly always share their reference
                     recs_in = records if in_range.all() else [r if ok else (r[0], r[1], "", []) for r, ok in zip(records, in_range)]
                     units_of_header[contigs_key] = build_units(recs_in, batch.contigs)
-                units = units_of_header[contigs_key]
-                counts = self.pileup(batch, units, stop_rec[units.rec] if units.n_units else np.zeros(0, np.int32))
+                tasks.append((sample, batch, units_of_header[contigs_key]))
+        jobs, done = [], {}
+        for t, (sample, batch, units) in enumerate(tasks):
+            if t >= 2:
+                done[t - 2] = self.finish(jobs[t - 2])
+            stop_u = stop_rec[units.rec] if units.n_units else np.zeros(0, np.int32)
+            eaf_u = np.asarray(eaf[sample], np.float64)[units.rec] if units.n_units else np.zeros(0)
+            jobs.append(self.submit(batch, units, stop_u, eaf_u))
+        for t in range(len(tasks)):
+            if t not in done:
+                done[t] = self.finish(jobs[t])
+        t = 0
+        for sample, batches in bams.items():
+            eaf_row = np.asarray(eaf[sample], np.float64)[rows.rec] if rows.n_rows else np.zeros(0)
+            results, stats = [], []
+            for batch in batches:
+                units = tasks[t][2]
+                counts, stats_u = done[t]
+                t += 1
                 bad = counts["status"] & _dev.ST_READLEN if len(counts) else np.zeros(0, np.uint32)
                 if len(counts) and bad.any():
                     raise _dev.VfkError("a read position exceeded the histogram range (reads longer than supported)")
                 res = BamResult(rows, units, counts, in_range)
                 results.append(res)
-                stats.append(RoundedStats(self.epilogue(res.row_counts, eaf_row)))
+                stats.append(RoundedStats(self._row_stats(res, counts, stats_u, eaf_row)))
             merged_stats = None
             if len(batches) > 1:
                 mc = np.zeros(rows.n_rows, _dev.COUNTS_DTYPE)

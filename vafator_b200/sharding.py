@@ -14,7 +14,6 @@ import numpy as np
 
 from .batch import ReadBatch, VariantUnits
 
-NO_MATE = 0xFFFFFFFF
 
 
 @dataclass
@@ -77,10 +76,9 @@ def _ref_span(batch: ReadBatch) -> np.ndarray:
     return csum[batch.cigar_off + batch.n_cigar] - csum[batch.cigar_off]
 
 
-def slice_reads(batch: ReadBatch, mate: np.ndarray, lo: int, hi: int) -> Tuple[ReadBatch, np.ndarray]:
-    """Reads [lo, hi) as a self-contained batch; mate links (computed on the WHOLE batch, the pairing is
-    order dependent) are re-based, links leaving the slice are cut -- such a partner cannot overlap any
-    column of the shard."""
+def slice_reads(batch: ReadBatch, lo: int, hi: int) -> ReadBatch:
+    """Reads [lo, hi) as a self-contained canonical batch (pool offsets re-based).  The kernels pair overlapping mates
+    among the reads they are given: a partner left outside the slice cannot overlap any column of the shard."""
     sl = slice(lo, hi)
     c0 = int(batch.cigar_off[lo]) if hi > lo else 0
     c1 = int(batch.cigar_off[hi - 1] + batch.n_cigar[hi - 1]) if hi > lo else 0
@@ -88,18 +86,12 @@ def slice_reads(batch: ReadBatch, mate: np.ndarray, lo: int, hi: int) -> Tuple[R
     s1 = int(batch.seq_off[hi - 1] + (batch.l_qseq[hi - 1] + 1) // 2) if hi > lo else 0
     q0 = int(batch.qual_off[lo]) if hi > lo else 0
     q1 = int(batch.qual_off[hi - 1] + batch.l_qseq[hi - 1]) if hi > lo else 0
-    sub = ReadBatch(contigs=batch.contigs, tid=batch.tid[sl], pos=batch.pos[sl], flag=batch.flag[sl], mapq=batch.mapq[sl],
-                    l_qseq=batch.l_qseq[sl], n_cigar=batch.n_cigar[sl], cigar_off=batch.cigar_off[sl] - c0,
-                    cigar=batch.cigar[c0:c1], seq_off=batch.seq_off[sl] - s0, seq=batch.seq[s0:s1],
-                    qual_off=batch.qual_off[sl] - q0, qual=batch.qual[q0:q1], mtid=batch.mtid[sl], mpos=batch.mpos[sl],
-                    isize=batch.isize[sl], qname_id=batch.qname_id[sl], qname_hash=batch.qname_hash[sl],
-                    contig_lengths=batch.contig_lengths)
-    m = mate[lo:hi].astype(np.int64)
-    linked = m != NO_MATE
-    partner = (m & 0x7FFFFFFF) - lo
-    inside = linked & (partner >= 0) & (partner < hi - lo)
-    out = np.where(inside, (partner & 0x7FFFFFFF) | (m & 0x80000000), NO_MATE).astype(np.uint32)
-    return sub, out
+    return ReadBatch(contigs=batch.contigs, tid=batch.tid[sl], pos=batch.pos[sl], flag=batch.flag[sl], mapq=batch.mapq[sl],
+                     l_qseq=batch.l_qseq[sl], n_cigar=batch.n_cigar[sl], cigar_off=batch.cigar_off[sl] - c0,
+                     cigar=batch.cigar[c0:c1], seq_off=batch.seq_off[sl] - s0, seq=batch.seq[s0:s1],
+                     qual_off=batch.qual_off[sl] - q0, qual=batch.qual[q0:q1], mtid=batch.mtid[sl], mpos=batch.mpos[sl],
+                     isize=batch.isize[sl], qname_id=batch.qname_id[sl], qname_hash=batch.qname_hash[sl],
+                     contig_lengths=batch.contig_lengths)
 
 
 def slice_units(units: VariantUnits, a: int, b: int) -> VariantUnits:
@@ -107,20 +99,20 @@ def slice_units(units: VariantUnits, a: int, b: int) -> VariantUnits:
                    seq_off=units.seq_off[a:b], rec=units.rec[a:b], alt_index=units.alt_index[a:b], unit_of={})
 
 
-def run_sharded(batch: ReadBatch, units: VariantUnits, stop: np.ndarray, mate: np.ndarray, passes: np.ndarray,
+def run_sharded(batch: ReadBatch, units: VariantUnits, stop: np.ndarray, passes: np.ndarray,
                 n_shards: int, rank: int, world: int,
-                compute: Callable[[ReadBatch, np.ndarray, VariantUnits, np.ndarray], np.ndarray],
+                compute: Callable[[ReadBatch, VariantUnits, np.ndarray], np.ndarray],
                 gather: Callable[[list], list]) -> Optional[np.ndarray]:
     """Shard, compute this rank's shards (shard k -> rank k % world), gather on rank 0 in unit order.
-    `compute(sub_batch, sub_mate, sub_units, sub_stop)` returns the per-unit records of one shard;
+    `compute(sub_batch, sub_units, sub_stop)` returns the per-unit records of one shard;
     `gather(obj)` returns the list of every rank's object on rank 0 (None elsewhere)."""
     shards = plan_shards(batch, units, n_shards, passes, stop)
     mine = []
     for k, sh in enumerate(shards):
         if k % world != rank:
             continue
-        sub, sub_mate = slice_reads(batch, mate, sh.read_lo, sh.read_hi)
-        res = compute(sub, sub_mate, slice_units(units, sh.unit_lo, sh.unit_hi), stop[sh.unit_lo:sh.unit_hi])
+        sub = slice_reads(batch, sh.read_lo, sh.read_hi)
+        res = compute(sub, slice_units(units, sh.unit_lo, sh.unit_hi), stop[sh.unit_lo:sh.unit_hi])
         mine.append((k, res))
     everything = gather(mine)
     if everything is None:

@@ -24,7 +24,8 @@ class SynthCfgC(C.Structure):
                 ("frag_mean", C.c_float), ("frag_sd", C.c_float),
                 ("p_softclip", C.c_float), ("p_del", C.c_float), ("p_ins", C.c_float), ("p_skip", C.c_float),
                 ("p_dup", C.c_float), ("p_supp", C.c_float), ("p_secondary", C.c_float), ("p_qcfail", C.c_float),
-                ("p_orphan", C.c_float), ("p_mapq60", C.c_float), ("base_error", C.c_float), ("p_n", C.c_float)]
+                ("p_orphan", C.c_float), ("p_mapq60", C.c_float), ("base_error", C.c_float), ("p_n", C.c_float),
+                ("g_first", C.c_int64), ("g_count", C.c_int64)]
 
 
 class _PlanC(C.Structure):
@@ -62,6 +63,10 @@ class SynthConfig:
     p_mapq60: float = 0.85
     base_error: float = 0.002
     p_n: float = 0.001
+    # generate only the tiles [g_first, g_first + g_count) of the genome (global tile index = contig * tiles_per_contig +
+    # tile; g_count 0 = everything): an interval shard of the SAME input, read for read
+    g_first: int = 0
+    g_count: int = 0
 
     def c(self) -> SynthCfgC:
         return SynthCfgC(*[getattr(self, f[0]) for f in SynthCfgC._fields_])
@@ -69,6 +74,10 @@ class SynthConfig:
     @property
     def contigs(self) -> List[str]:
         return ["chr%d" % (i + 1) for i in range(self.n_contigs)]
+
+    @property
+    def n_tiles_generated(self) -> int:
+        return self.g_count if self.g_count > 0 else self.n_contigs * self.tiles_per_contig
 
 
 def wes(n_tiles=200_000, seed=BASE_SEED + 2, normal=False, **kw) -> SynthConfig:
@@ -111,22 +120,23 @@ def _lib():
     return lib
 
 
-def reads(cfg: SynthConfig, read_seed: int = None) -> ReadBatch:
-    """Generate the canonical columnar batch.  `read_seed` changes the reads but not the genome /
-    sites when two samples must share their variant sites -- see `sample_cfg`."""
+def reads(cfg: SynthConfig, pinned: bool = False) -> ReadBatch:
+    """Generate the canonical columnar batch (what a BAM decoder would hand over: nothing is derived from the reads).
+    `pinned`: the arrays are allocated page-locked, so the host entry point can read them in place."""
     lib = _lib()
     c = cfg.c()
     plan = _PlanC()
-    tiles = cfg.n_contigs * cfg.tiles_per_contig
+    tiles = cfg.n_tiles_generated
     tile_sizes = np.zeros(4 * tiles, np.int64)
     _dev._io_check(lib.vfkio_synth_plan_reads(C.byref(c), C.byref(plan), C.c_void_p(tile_sizes.ctypes.data)))
     n = plan.n_reads
-    arr = dict(tid=np.empty(n, np.int32), pos=np.empty(n, np.int32), flag=np.empty(n, np.uint16),
-               mapq=np.empty(n, np.uint8), l_qseq=np.empty(n, np.int32), n_cigar=np.empty(n, np.int32),
-               cigar_off=np.empty(n, np.int64), seq_off=np.empty(n, np.int64), qual_off=np.empty(n, np.int64),
-               cigar=np.empty(max(plan.n_cigar, 1), np.uint32), seq=np.empty(max(plan.n_seq_bytes, 1), np.uint8),
-               qual=np.empty(max(plan.n_qual_bytes, 1), np.uint8), mtid=np.empty(n, np.int32), mpos=np.empty(n, np.int32),
-               isize=np.empty(n, np.int32), qname_id=np.empty(n, np.uint64), qname_hash=np.empty(n, np.uint32))
+    E = lambda k, dt: _dev._empty(k, dt, pinned)
+    arr = dict(tid=np.empty(n, np.int32), pos=E(n, np.int32), flag=E(n, np.uint16),
+               mapq=E(n, np.uint8), l_qseq=E(n, np.int32), n_cigar=E(n, np.int32),
+               cigar_off=E(n, np.int64), seq_off=E(n, np.int64), qual_off=E(n, np.int64),
+               cigar=E(max(plan.n_cigar, 1), np.uint32), seq=E(max(plan.n_seq_bytes, 1), np.uint8),
+               qual=E(max(plan.n_qual_bytes, 1), np.uint8), mtid=E(n, np.int32), mpos=E(n, np.int32),
+               isize=E(n, np.int32), qname_id=E(n, np.uint64), qname_hash=E(n, np.uint32))
     s = _dev._IoReadsC()
     s.n, s.n_contigs = n, cfg.n_contigs
     for k, a in arr.items():
@@ -135,7 +145,7 @@ def reads(cfg: SynthConfig, read_seed: int = None) -> ReadBatch:
     arr["cigar"] = arr["cigar"][:plan.n_cigar]
     arr["seq"] = arr["seq"][:plan.n_seq_bytes]
     arr["qual"] = arr["qual"][:plan.n_qual_bytes]
-    return ReadBatch(contigs=cfg.contigs, **arr)
+    return ReadBatch(contigs=cfg.contigs, pinned=pinned, **arr)
 
 
 def sites(cfg: SynthConfig):
