@@ -1,23 +1,32 @@
 #!/usr/bin/env python
 """bench.py -- variants x BAMs annotated per second on B200, kernel-only and end to end.
 
-Workload at N=1 (BASELINE.json configs[1], "C2"): synthetic 30x WES tumour/normal pair --
-200 000 targets of 250 bp (50 Mbp), 2 x 14.4 M reads, ~100 k SNVs, CLI default filters
-(MQ>=1, BQ>=30) => ~200 k (variant, BAM) units per step.  One *step* = one pass of the hot path
-(pileup kernel + FP64 epilogue kernel) over both BAMs.  For N>1 every rank owns an equally
-sized, independent shard (different genomic intervals: different seed) -- weak scaling, no
-collective on the data path; torch.distributed is used for the barrier and the
-max-over-ranks only.
+Both arms start from the SAME boundary: the canonical columnar read batch (include/vfk.h: start, flag, MAPQ, CIGAR, 4-bit
+sequence, qualities, mate fields, name id -- what a BAM decoder hands over) plus the variant records.  Everything derived
+from the reads -- reference spans, position index, CIGAR shapes, read filter, mate pairing -- is inside the timed regions,
+on the device for the GPU arm, in the C restatement for the CPU arm.
 
-  value     units/s with the read batches resident in HBM (CUDA events around the K steps)
-  e2e       units/s through vfk_annotate_host(): pinned HOST buffers in, HOST results out,
-            H2D + kernels + D2H inside the timed region
-  roofline  pileup kernel: SURVEY.md 8(d) algorithmic bytes / CUDA-event time of that kernel,
-            against the measured HBM copy peak (MEASURED_PEAKS.json)
+Workloads (BASELINE.json configs; --config):
+  C3 (default)  ONE synthetic 30x WGS tumour BAM: 24 contigs x 10 Mbp (240 Mbp: chr1-22 scaled down 12x, stated), 48 M reads,
+                1 variant per ~720 bp (90 % SNV, 5 % INS, 5 % DEL) => ~334 k units.  --gpus N cuts this one input into N
+                interval shards of equal unit count (vafator_b200/sharding.py unit cuts), one per rank: STRONG scaling, no
+                collective on the data path; each rank materialises only the reads of its own shard.
+  C2            30x WES tumour/normal pair, 200 000 x 250 bp targets, 2 x 14.4 M reads, ~100 k SNVs => ~200 k units.
+  C4            8 samples x 60x over a shared target set (--tiles, default 40 000 = 10 Mbp: 1/5 of the 50 Mbp of SURVEY.md 8d,
+                stated), per-sample purity + 1 000-segment copy-number BED, 2 % multiallelic sites.
+  C5            1000x amplicon panel: 5 000 amplicons, ~9 M reads, ~50 k variants (the histogram path).
+One *step* = one pass of the hot path over every batch of the rank (a rank's shard is processed as a few interval
+sub-batches so that the copies of one overlap the kernels of the previous one).
+
+  value     units/s with the canonical batches resident in HBM: read preparation + locate + pileup + epilogue kernels
+            (CUDA events around the K steps, max over ranks)
+  e2e       units/s through vfk_annotate_host_async(): page-locked HOST arrays in, HOST results out, every copy inside
+  roofline  pileup_warp_kernel: SURVEY.md 8(d) algorithmic bytes / its own CUDA-event time (vfk_last_timing), against the
+            measured HBM copy peak (MEASURED_PEAKS.json)
   cpu_baseline / --impl reference
-            the oracle port (C restatement of the pysam/htslib pileup, OpenMP on all host cores
-            + the reference's scalar scipy epilogue on a process pool) on a bounded sample of the
-            same workload.  pysam itself is not installable on either box.
+            the oracle port (C restatement of the pysam/htslib pileup incl. mate linking, OpenMP on all host cores + the
+            reference's scalar scipy epilogue on a process pool) on a bounded sample of the same workload.  pysam itself is
+            not installable on either box.
 """
 from __future__ import annotations
 
@@ -29,8 +38,8 @@ import sys
 import threading
 import time
 
-# torchrun pins OMP_NUM_THREADS=1 for its children; the host-side batch builder (OpenMP) should use
-# this rank's share of the host cores instead.  Must happen before any OpenMP runtime is loaded.
+# torchrun pins OMP_NUM_THREADS=1 for its children; the synthetic generator (OpenMP) should use this rank's share of the
+# host cores instead.  Must happen before any OpenMP runtime is loaded.
 if int(os.environ.get("WORLD_SIZE", "1")) > 1:
     os.environ["OMP_NUM_THREADS"] = str(max(2, (os.cpu_count() or 2) // int(os.environ["WORLD_SIZE"])))
 
@@ -48,7 +57,6 @@ sys.path.insert(0, ROOT)
 
 MIN_MAPQ, MIN_BASEQ = 1, 30          # CLI defaults, vafator/command_line.py:63,71
 FPR, ERROR_RATE = 5e-7, 1e-3         # vafator/power.py:10-11
-PURITY, PLOIDY = {"tumor": 0.8, "normal": 1.0}, {"tumor": 2.0, "normal": 2.0}
 
 
 def log(*a):
@@ -57,8 +65,7 @@ def log(*a):
 
 def pin_to_gpu_numa_node(local_rank: int):
     """Multi-GPU runs: keep this rank's host threads -- and with them its pinned buffers (first touch) -- on the
-    NUMA node its GPU hangs off, so that eight ranks do not all pull their batches through one memory
-    controller / PCIe root.  Best effort: returns the node, or None when the topology cannot be read."""
+    NUMA node its GPU hangs off.  Best effort: returns the node, or None when the topology cannot be read."""
     try:
         vis = os.environ.get("CUDA_VISIBLE_DEVICES")
         idx = local_rank
@@ -96,80 +103,118 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def eaf_of(sample):
-    pur = PURITY[sample]
-    return pur / (pur * max(1, PLOIDY[sample]) + (1 - pur) * 2)
-
-
 # --------------------------------------------------------------------------------------------
-# workload
+# workloads
 # --------------------------------------------------------------------------------------------
-def build_workload(n_tiles: int, rank: int, pinned: bool, no_columns: bool = False):
-    """Tumour + normal batch over the same targets / sites; returns packed host batches + units."""
-    from vafator_b200 import device, synth
-    from vafator_b200.batch import build_units
-    params = device.make_params(min_mapq=MIN_MAPQ, min_baseq=MIN_BASEQ, include_ambiguous=True)
-    seed = synth.BASE_SEED + 2 + 1000 * rank
-    t0 = time.time()
-    if not no_columns:
-        # both layouts of the two BAMs are ~23 GB of (page-locked) host memory per rank, plus ~12 GB while a batch is
-        # being built: on a host that cannot give every rank that much the run keeps to the read-major layout
-        try:
-            import psutil
-            avail = psutil.virtual_memory().available / max(int(os.environ.get("WORLD_SIZE", "1")), 1)
-            need = 40e9 * n_tiles / 200_000
-            if avail < need:
-                log("[bench] rank %d: %.0f GB of host memory per rank < %.0f GB: no column store" % (rank, avail / 1e9, need / 1e9))
-                no_columns = True
-        except ImportError:
-            pass
-    cfg_t = synth.wes(n_tiles=n_tiles, seed=seed, normal=False)
-    recs = synth.variant_records(cfg_t)
-    units = build_units(recs, cfg_t.contigs)
-    last = {}
-    for c, p, r, a in recs:
-        last[c] = p
-    stop = np.asarray([last[recs[i][0]] for i in units.rec], np.int32)
-    packed = {}
-    n_reads = 0
-    for sample, normal in (("tumor", False), ("normal", True)):
-        # same seed => same genome and sites; the normal sample differs in VAF spectrum, which also
-        # re-draws which reads carry an allele
-        cfg = synth.wes(n_tiles=n_tiles, seed=seed, normal=normal)
-        batch = synth.reads(cfg)
-        n_reads += batch.n_reads
-        packed[sample] = device.pack_reads(batch, params, pinned=pinned, columns=not no_columns)
-        del batch
-    log("[bench] rank %d workload: %d tiles, %d reads, %d records, %d units/BAM, %.1f s" %
-        (rank, n_tiles, n_reads, len(recs), units.n_units, time.time() - t0))
-    return dict(params=params, recs=recs, units=units, stop=stop, packed=packed, n_reads=n_reads, columns=not no_columns)
+class Workload:
+    """A config of BASELINE.json: the samples (one synthetic BAM each, same genome and planted sites), their expected-VAF
+    model and how many interval sub-batches a rank cuts each of its BAM shards into."""
+
+    def __init__(self, name, args):
+        from vafator_b200 import synth
+        self.name = name
+        S = synth.BASE_SEED
+        if name == "C2":
+            tiles = args.tiles or 200_000
+            self.samples = [("tumor", synth.wes(n_tiles=tiles, seed=S + 2, normal=False)), ("normal", synth.wes(n_tiles=tiles, seed=S + 2, normal=True))]
+            self.purity = {"tumor": 0.8, "normal": 1.0}
+            self.sub = args.sub_batches or 2
+            self.text = "C2: synthetic 30x WES tumor/normal, %d x 250bp targets, 2x150 reads, ~%dk SNVs, MQ>=1 BQ>=30" % (tiles, tiles // 2000)
+            self.cpu_units = 20_000
+        elif name == "C3":
+            n_contigs, clen = args.contigs or 24, args.contig_len or 10_000_000
+            self.samples = [("tumor", synth.wgs(n_contigs=n_contigs, contig_len=clen, seed=S + 3))]
+            self.purity = {"tumor": 0.8}
+            self.sub = args.sub_batches or 4
+            self.text = ("C3: ONE synthetic 30x WGS tumor BAM, %d contigs x %.0f Mbp (chr1-22 scaled down to %.0f Mbp), 2x150 reads, 1 variant / ~720 bp "
+                         "(90%% SNV, 5%% INS, 5%% DEL), MQ>=1 BQ>=30; cut into one interval shard per GPU") % (
+                             n_contigs, clen / 1e6, n_contigs * clen / 1e6)
+            self.cpu_units = 40_000
+        elif name == "C4":
+            tiles = args.tiles or 40_000
+            self.samples = [("s%d" % k, synth.multisample(k, n_tiles=tiles, seed=S + 4)) for k in range(8)]
+            self.purity = {"s%d" % k: round(0.2 + 0.75 * k / 7.0, 3) for k in range(8)}
+            self.sub = args.sub_batches or 1
+            self.text = ("C4: 8 synthetic 60x samples over %d shared 250bp targets (%.0f Mbp; 50 Mbp in SURVEY.md 8d), per-sample purity + "
+                         "1000-segment copy-number BED, 2%% multiallelic SNV sites, indels, MQ>=1 BQ>=30") % (tiles, tiles * 250 / 1e6)
+            self.cpu_units = 16_000
+        elif name == "C5":
+            tiles = args.tiles or 5_000
+            self.samples = [("panel", synth.amplicon(n_tiles=tiles, depth_pairs=900, seed=S + 5))]
+            self.purity = {"panel": 0.6}
+            self.sub = args.sub_batches or 2
+            self.text = "C5: synthetic 1000x amplicon panel, %d amplicons, ~%dk variants (1 per ~25 bp), MQ>=1 BQ>=30" % (tiles, tiles * 10 // 1000)
+            self.cpu_units = 1_500
+        else:
+            raise SystemExit("unknown config " + name)
+        self.cfg0 = self.samples[0][1]
+        self.recs = synth.variant_records(self.cfg0)
+        self.contigs = self.cfg0.contigs
+        last = {}
+        for c, p, r, a in self.recs:
+            last[c] = p
+        self.last = last
+        from vafator_b200.batch import build_units
+        self.units_all = build_units(self.recs, self.contigs)
+        self.stop_all = np.asarray([last[self.recs[i][0]] for i in self.units_all.rec], np.int32)
+
+    def eaf(self, sample, recs):
+        """Expected VAF per record (vafator/power.py:52-82); C4: per-sample copy-number BED of 1 000 segments."""
+        pur = self.purity[sample]
+        if self.name != "C4":
+            ploidy = np.full(len(recs), 2.0)
+        else:
+            # 1 000 equal segments over the concatenated target space, CN in [0.5, 6] (the lookup itself is host work of
+            # the reference too: vafator/ploidies.py:36-50; here a vectorised searchsorted)
+            k = int(self.samples[[s for s, _ in self.samples].index(sample)][1].read_salt) % 97
+            cn = 0.5 + 5.5 * ((np.arange(1000) * 37 + k * 11) % 101) / 100.0
+            tid_of = {c: i for i, c in enumerate(self.contigs)}
+            key = np.asarray([tid_of[r[0]] * (1 << 31) + r[1] for r in recs], np.int64)
+            span = len(self.contigs) * (1 << 31)
+            ploidy = cn[np.minimum((key * 1000) // span, 999)]
+        return pur / (pur * np.maximum(1, ploidy) + (1 - pur) * 2)
 
 
-def cpu_sample(n_tiles: int, rank: int):
-    """Canonical (un-packed) batches of a bounded sample of the same workload, for the CPU arm."""
+def unit_cuts(n: int, k: int):
+    from vafator_b200 import sharding
+    return sharding.unit_cuts(n, k)
+
+
+def build_batches(w: Workload, rank: int, world: int, pinned: bool, cap_units: int = None):
+    """This rank's share of the ONE input: units [cut[rank], cut[rank+1]) of every BAM, as `w.sub` interval sub-batches per BAM;
+    each sub-batch holds the canonical reads of the tiles its columns can reach.  cap_units: only the first units (CPU sample)."""
     from vafator_b200 import synth
-    from vafator_b200.batch import build_units
-    seed = synth.BASE_SEED + 2 + 1000 * rank
-    cfg = synth.wes(n_tiles=n_tiles, seed=seed)
-    recs = synth.variant_records(cfg)
-    units = build_units(recs, cfg.contigs)
-    tid_of = {c: i for i, c in enumerate(cfg.contigs)}
-    last = {}
-    for c, p, r, a in recs:
-        last[c] = p
-    ounits = [(tid_of[recs[i][0]], recs[i][1], recs[i][2], recs[i][3][j], recs[i][3][0], last[recs[i][0]])
-              for i, j in zip(units.rec, units.alt_index)]
-    batches = {s: synth.reads(synth.wes(n_tiles=n_tiles, seed=seed, normal=(s == "normal"))) for s in ("tumor", "normal")}
-    return batches, ounits
+    from dataclasses import replace
+    from vafator_b200 import sharding
+    units_all, stop_all = w.units_all, w.stop_all
+    n = units_all.n_units if cap_units is None else min(cap_units, units_all.n_units)
+    cuts = unit_cuts(n, world)
+    lo, hi = cuts[rank], cuts[rank + 1]
+    sub_cuts = [lo + c for c in unit_cuts(hi - lo, w.sub)]
+    batches = []
+    t0 = time.time()
+    for sample, cfg in w.samples:
+        eaf_all = w.eaf(sample, w.recs)
+        for a, b in zip(sub_cuts[:-1], sub_cuts[1:]):
+            if b <= a:
+                continue
+            units = sharding.slice_units(units_all, a, b)  # `rec` keeps indexing the records of the whole input
+            g0, gc = synth.tile_range(cfg, int(units.tid[0]), int(units.pos[0]), int(units.tid[-1]), int(units.pos[-1]))
+            batch = synth.reads(replace(cfg, g_first=g0, g_count=gc), pinned=pinned)
+            batches.append(dict(sample=sample, batch=batch, units=units, stop=np.ascontiguousarray(stop_all[a:b]),
+                                eaf=np.ascontiguousarray(eaf_all[units.rec], np.float64), recs=w.recs))
+    log("[bench] rank %d: %s units [%d, %d) of %d, %d batches, %d reads, %.1f s" % (
+        rank, w.name, lo, hi, n, len(batches), sum(b["batch"].n_reads for b in batches), time.time() - t0))
+    return batches, n
 
 
 def _epilogue_chunk(args):
     """The reference's per-unit scalar epilogue (vafator/annotator.py:382-420) on one chunk."""
     from oracle import vafator_ref as vr
-    rows, eaf = args
+    rows, eafs = args
     power = vr.Power(fpr=FPR, error_rate=ERROR_RATE)
     out = 0
-    for dp, ac_alt, ac_ref, s2 in rows:
+    for (dp, ac_alt, ac_ref, s2), eaf in zip(rows, eafs):
         power.pu(dp, ac_alt, eaf)
         power.pw(dp, eaf)
         for m in range(3):
@@ -181,34 +226,42 @@ def _epilogue_chunk(args):
     return out
 
 
-def run_cpu_arm(n_tiles: int, rank: int, repeats: int = 1):
-    """Oracle port timed on the host cores: C pileup (OpenMP) + scalar scipy epilogue (process pool)."""
+def run_cpu_arm(w: Workload, repeats: int = 1):
+    """Oracle port timed on the host cores: C mate linking + pileup (OpenMP) + scalar scipy epilogue (process pool), from the
+    canonical arrays -- the boundary the GPU arm starts at."""
     import multiprocessing as mp
     from oracle import c_oracle
     cores = os.cpu_count() or 1
-    batches, ounits = cpu_sample(n_tiles, rank)
+    batches, n_units_sample = build_batches(w, 0, 1, pinned=False, cap_units=w.cpu_units)
+    tid_of = {c: i for i, c in enumerate(w.contigs)}
     prm = c_oracle.params(min_mapq=MIN_MAPQ, min_baseq=MIN_BASEQ)
     c_oracle.lib()
+    jobs = []
+    for b in batches:
+        u, recs = b["units"], b["recs"]
+        ounits = [(tid_of[recs[i][0]], recs[i][1], recs[i][2], recs[i][3][j], recs[i][3][0], w.last[recs[i][0]]) for i, j in zip(u.rec, u.alt_index)]
+        jobs.append((b["batch"].as_dict(), ounits, b["eaf"].tolist()))
     times = []
     n_units = 0
     with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_epilogue_chunk, [([(10, 3, 5, [0, 0, 0])], [0.5])] * (2 * cores))  # workers import scipy before the clock starts
         for _ in range(repeats):
             t0 = time.perf_counter()
             n_units = 0
-            for sample, batch in batches.items():
-                d = batch.as_dict()
+            for d, ounits, eafs in jobs:
                 mate = c_oracle.link_mates(d, prm)
                 out = c_oracle.pileup(d, ounits, prm, mate)
                 rows = list(zip(out["dp"].tolist(), out["ac_alt"].tolist(), out["ac_ref"].tolist(), out["s2"].tolist()))
                 step = max(1, len(rows) // (cores * 4))
-                chunks = [(rows[i:i + step], eaf_of(sample)) for i in range(0, len(rows), step)]
+                chunks = [(rows[i:i + step], eafs[i:i + step]) for i in range(0, len(rows), step)]
                 n_units += sum(pool.map(_epilogue_chunk, chunks))
             times.append(time.perf_counter() - t0)
-    return n_units, times, cores
+    n_reads = sum(len(d["pos"]) for d, _, _ in jobs)
+    return n_units, times, cores, n_reads
 
 
 # --------------------------------------------------------------------------------------------
-# clocks
+# clocks, PCIe
 # --------------------------------------------------------------------------------------------
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -244,6 +297,46 @@ class ClockSampler:
                     reasons=reasons, samples=len(sm))
 
 
+class PcieRxSampler:
+    """Bytes the GPU receives over PCIe, from NVML's RX throughput counter (a 20 ms window per query), sampled while the
+    end-to-end loop runs: covers the bulk copies AND what the kernels read in place from page-locked host memory."""
+
+    def __init__(self, index):
+        self.samples, self.ok, self._stop = [], False, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                ids = [x.strip() for x in vis.split(",") if x.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    index = int(ids[index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            pynvml.nvmlDeviceGetPcieThroughput(self.h, pynvml.NVML_PCIE_UTIL_RX_BYTES)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def start(self):
+        if self.ok:
+            self.th = threading.Thread(target=self._run, daemon=True)
+            self.th.start()
+
+    def _run(self):
+        while not self._stop:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetPcieThroughput(self.h, self.nv.NVML_PCIE_UTIL_RX_BYTES))  # KB/s
+            except Exception:
+                break
+
+    def stop(self):
+        self._stop = True
+        if self.ok:
+            self.th.join(timeout=1.0)
+        return float(np.mean(self.samples)) * 1024.0 if self.samples else None  # bytes/s
+
+
 # --------------------------------------------------------------------------------------------
 # the two arms
 # --------------------------------------------------------------------------------------------
@@ -253,34 +346,35 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--tiles", type=int, default=200_000, help="WES targets per BAM (200000 = the 50 Mbp C2 config)")
-    ap.add_argument("--cpu-tiles", type=int, default=20_000, help="targets in the bounded CPU-baseline sample")
+    ap.add_argument("--config", default="C3", choices=["C2", "C3", "C4", "C5"])
+    ap.add_argument("--tiles", type=int, default=0, help="C2 / C4 / C5: targets (amplicons) per BAM; 0 = the config's default")
+    ap.add_argument("--contigs", type=int, default=0, help="C3: contigs (default 24)")
+    ap.add_argument("--contig-len", type=int, default=0, help="C3: bases per contig (default 10 Mbp)")
+    ap.add_argument("--sub-batches", type=int, default=0, help="interval sub-batches a rank cuts each BAM shard into")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-columns", action="store_true", help="read-major kernels only (no column store in the batches)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    workload = "C2: synthetic 30x WES tumor/normal, %d x 250bp targets, 2x150 reads, ~%dk SNVs, MQ>=1 BQ>=30" % (
-        args.tiles, args.tiles // 2000)
 
     if args.impl == "reference":
         if rank != 0:
             return
-        n_units, times, cores = run_cpu_arm(args.cpu_tiles, 0, repeats=args.warmup + args.steps)
+        w = Workload(args.config, args)
+        n_units, times, cores, n_reads = run_cpu_arm(w, repeats=args.warmup + args.steps)
         timed = times[args.warmup:]
         dt = sum(timed)
         val = n_units * len(timed) / dt
-        sample = ("%d of %d targets of the same workload (%d units/step): C pileup restatement (OpenMP) + "
-                  "reference-style scalar scipy epilogue (process pool); pysam not installable") % (
-                      args.cpu_tiles, args.tiles, n_units)
+        sample = ("the first %d units (%d reads) of the same workload: C mate linking + pileup restatement (OpenMP) + "
+                  "reference-style scalar scipy epilogue (process pool), from the canonical read arrays; pysam not installable") % (
+                      n_units, n_reads)
         print(json.dumps({
             "impl": "reference", "metric": "variants x BAMs annotated per second", "value": val, "unit": "units/s",
             "n_gpus": args.gpus, "steps": len(timed), "warmup": args.warmup, "ms_per_step": 1e3 * dt / len(timed),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/f64", "data": "synthetic",
-            "config": {"workload": workload, "sample": sample},
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32/f64", "data": "synthetic",
+            "config": {"workload": w.text, "sample": sample},
             "cpu_baseline": {"value": val, "unit": "units/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "units/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}), file=_RESULT_OUT, flush=True)
@@ -303,34 +397,27 @@ def main():
         torch.cuda.synchronize()
 
     dev = device.Device(local_rank)
-    w = build_workload(args.tiles, rank, pinned=not args.no_e2e, no_columns=args.no_columns)
-    units, stop, params = w["units"], w["stop"], w["params"]
-    nu = units.n_units
-    samples = ("tumor", "normal")
-    dunits = dev.upload_units(units, stop)
-    dreads = {s: dev.upload_reads(w["packed"][s]) for s in samples}
-    eaf_host = {s: np.full(nu, eaf_of(s)) for s in samples}
-    eaf_dev = {s: torch.from_numpy(eaf_host[s]).to(dev.device) for s in samples}
-    counts = {s: dev.alloc_counts(nu) for s in samples}
-    stats = {s: dev.alloc_stats(nu) for s in samples}
+    params = device.make_params(min_mapq=MIN_MAPQ, min_baseq=MIN_BASEQ, include_ambiguous=True)
+    w = Workload(args.config, args)
+    batches, units_total = build_batches(w, rank, world, pinned=not args.no_e2e)
+    for b in batches:
+        b["host"] = device.HostReads(b["batch"])           # the canonical arrays, as generated (page-locked)
+        b["dreads"] = dev.upload_reads(b["host"])          # ... and the same arrays resident in HBM, verbatim
+        b["dunits"] = dev.upload_units(b["units"], b["stop"])
+        b["deaf"] = torch.from_numpy(b["eaf"]).to(dev.device)
+        b["counts"] = dev.alloc_counts(b["units"].n_units)
+        b["stats"] = dev.alloc_stats(b["units"].n_units)
     torch.cuda.synchronize()
-    units_per_step = nu * len(samples)
+    units_per_step = sum(b["units"].n_units for b in batches)
+    reads_rank = sum(b["batch"].n_reads for b in batches)
 
-    k_ev = []  # (start, end) CUDA events around every pileup launch of the timed region
-
-    def step(record):
-        for s in samples:
-            if record:
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-            dev.pileup(dreads[s], dunits, params, out=counts[s])
-            if record:
-                b.record()
-                k_ev.append((a, b))
-            dev.epilogue(nu, counts[s], eaf_dev[s], FPR, ERROR_RATE, out=stats[s])
+    def step():
+        for b in batches:
+            dev.pileup(b["dreads"], b["dunits"], params, out=b["counts"])
+            dev.epilogue(b["units"].n_units, b["counts"], b["deaf"], FPR, ERROR_RATE, out=b["stats"])
 
     for _ in range(warmup):
-        step(False)
+        step()
     barrier()
     clocks = ClockSampler(local_rank)
     clocks.start()
@@ -338,7 +425,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        step(True)
+        step()
     e1.record()
     barrier()
     launches = dev.launch_count() - l0
@@ -346,120 +433,141 @@ def main():
     # keep the GPU busy a little longer so that the clock sampler sees it under load
     t_end = time.time() + 1.0
     while time.time() < t_end:
-        step(False)
+        step()
     torch.cuda.synchronize()
     clk = clocks.stop()
-    k_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
 
-    # parity guard on the benchmarked data itself: depth statistics must be sane and reproducible
-    c_host = dev.to_host(counts["tumor"], device.COUNTS_DTYPE, nu)
-    assert int(c_host["status"].max()) & (device.ST_DEFERRED | device.ST_READLEN) == 0
-    d_raw = float(c_host["n_cover"].mean())
-    n_cand = float(c_host["n_cand"].mean())
+    # ---- per-phase device times of the same calls (CUDA events recorded by the library on the launching stream)
+    dev.set_timing(True)
+    phase = dict(prep=0.0, locate=0.0, pileup=0.0, lists=0.0)
+    n_timed = 0
+    for _ in range(max(3, min(args.steps, 10))):
+        for b in batches:
+            dev.pileup(b["dreads"], b["dunits"], params, out=b["counts"])
+            t = dev.last_timing()
+            for k in phase:
+                phase[k] += t[k]
+            n_timed += 1
+    dev.set_timing(False)
+    phase = {k: v / n_timed for k, v in phase.items()}  # ms per launch (one batch)
 
-    # ---- end to end: pinned host buffers -> results on the host, through vfk_annotate_host ----
+    # sanity on the benchmarked data itself
+    c_host = [dev.to_host(b["counts"], device.COUNTS_DTYPE, b["units"].n_units) for b in batches]
+    for c in c_host:
+        assert int(c["status"].max()) & (device.ST_DEFERRED | device.ST_READLEN | device.ST_BADBATCH) == 0
+    d_raw = float(np.concatenate([c["n_cover"] for c in c_host]).mean())
+    n_cand = float(np.concatenate([c["n_cand"] for c in c_host]).mean())
+
+    # ---- end to end: page-locked canonical host arrays -> results on the host, through vfk_annotate_host_async ----
     e2e = None
     if not args.no_e2e:
-        c_out = {s: np.empty(nu, device.COUNTS_DTYPE) for s in samples}
-        s_out = {s: np.empty(nu, device.STATS_DTYPE) for s in samples}
+        c_out = [np.empty(b["units"].n_units, device.COUNTS_DTYPE) for b in batches]
+        s_out = [np.empty(b["units"].n_units, device.STATS_DTYPE) for b in batches]
 
         def e2e_step():
-            # both BAMs are submitted before either is waited for: the library double-buffers, so the
-            # copies of the second batch overlap the kernels of the first
-            tickets = [dev.annotate_host_async(w["packed"][s], units, stop, params, eaf_host[s], FPR, ERROR_RATE,
-                                               c_out[s], s_out[s]) for s in samples]
-            for t in tickets:
+            # two batches in flight: the library double-buffers, the copies of one batch overlap the kernels of the previous
+            tickets = []
+            for k, b in enumerate(batches):
+                if k >= 2:
+                    dev.wait(tickets[k - 2])
+                tickets.append(dev.annotate_host_async(b["host"], b["units"], b["stop"], params, b["eaf"], FPR, ERROR_RATE, c_out[k], s_out[k]))
+            for t in tickets[-2:]:
                 dev.wait(t)
         for _ in range(2):
             e2e_step()
         barrier()
         ts0 = dev.transfer_stats()
-        cb0 = dev.column_batches()
+        rx = PcieRxSampler(local_rank)
+        rx.start()
         t0 = time.perf_counter()
         n_e2e = max(3, min(args.steps, 5))
         for _ in range(n_e2e):
             e2e_step()
         torch.cuda.synchronize()
         dt_e2e = (time.perf_counter() - t0) / n_e2e
+        rx_rate = rx.stop()
         ts1 = dev.transfer_stats()
-        assert np.array_equal(c_out["tumor"]["dp"], c_host["dp"]) and np.array_equal(c_out["tumor"]["ac_alt"], c_host["ac_alt"])
-        n_batches = n_e2e * len(samples)
-        zc = (ts1["zero_copy_batches"] - ts0["zero_copy_batches"]) / n_batches
-        zc_hot = (ts1["zero_copy_hot_batches"] - ts0["zero_copy_hot_batches"]) / n_batches
-        host_loc = (ts1["host_located_batches"] - ts0["host_located_batches"]) / n_batches
-        col = (dev.column_batches() - cb0) / n_batches
-        # bytes the library copied in bulk (counted by the library) + what the kernels gathered from pinned host
-        # memory: per candidate read one 32-byte payload sector plus the overlap partner's / cold record's share
-        # (~64 B), and its 20-byte header when the hot / mate arrays are gathered too
-        h2d = (ts1["staged_bytes"] - ts0["staged_bytes"]) / n_e2e
-        if col > 0.5:
-            # column store: one contiguous run of 32-byte sectors per unit (n_cand = sectors of the column's window);
-            # the few units left to the read-major kernels (~2 %) gather ~84 B per candidate read as before
-            # (staged VFK_COL_TRANSPOSED=1 layout: one 8-byte header pair and one 2-byte entry per sector of the run)
-            per_sector = 10.0 if os.environ.get("VFK_COL_TRANSPOSED", "")[:1] == "1" else 32.0
-            if os.environ.get("VFK_HOST_GATHER", "")[:1] == "1":
-                per_sector = 0.0  # staged: the runs are gathered on the host and bulk-copied (counted by the library)
-            h2d += len(samples) * nu * n_cand * (per_sector + 0.02 * 84.0)
+        for k in range(len(batches)):
+            for f in ("dp", "ac_alt", "ac_ref", "med2"):
+                assert np.array_equal(c_out[k][f], c_host[k][f]), f
+        staged = (ts1["staged_bytes"] - ts0["staged_bytes"]) / n_e2e
+        zero_copy = (ts1["zero_copy_batches"] - ts0["zero_copy_batches"]) / (n_e2e * len(batches))
+        d2h = (ts1["d2h_bytes"] - ts0["d2h_bytes"]) / n_e2e
+        if rx_rate is not None:
+            h2d, h2d_how = rx_rate * dt_e2e, "NVML PCIe RX counter sampled over the timed region x step time"
         else:
-            h2d += len(samples) * nu * n_cand * (64.0 * zc + 20.0 * zc_hot)
-        transfer = ("column store: SNV units read one contiguous sector run each from pinned host memory; " if col > 0.5 else "") + (
-            "units located %s; headers %s; payload + cold + CIGAR %s; two batches in flight (double buffered)" % (
-            "on the host (32 B per unit copied, no index transfer)" if host_loc > 0.5 else "by the locate kernel (index staged)",
-            "gathered by the kernel from pinned host memory" if zc_hot > 0.5 else "staged by async copies",
-            "gathered by the kernel from pinned host memory (zero copy)" if zc > 0.5 else "staged by async copies"))
-        d2h = len(samples) * nu * (device.COUNTS_DTYPE.itemsize + device.STATS_DTYPE.itemsize)
-        e2e = (dt_e2e, h2d, d2h, transfer)
+            # fallback when NVML has no counter: the library's own count of copied bytes + per candidate read the in-place reads
+            # (header fields 27 B, quality + base sectors 64 B)
+            h2d, h2d_how = staged + zero_copy * units_per_step * n_cand * 91.0, "library-counted copies + 91 B per candidate read (no NVML counter)"
+        transfer = ("page-locked canonical arrays: starts / CIGARs / read lengths copied (%.0f MB per step, counted by the library), every other "
+                    "array read in place over PCIe for the reads that overlap a column; two batches in flight" % (staged / 1e6)) if zero_copy > 0.5 else \
+                   "every array staged by async copies (%.0f MB per step); two batches in flight" % (staged / 1e6)
+        e2e = dict(dt=dt_e2e, h2d=h2d, d2h=d2h, transfer=transfer, staged=staged, h2d_how=h2d_how, rx_gbs=None if rx_rate is None else rx_rate / 1e9)
 
     # ---- max over ranks ----
     if dist is not None:
-        t = torch.tensor([ms_total, e2e[0] if e2e else 0.0, k_ms], device=dev.device, dtype=torch.float64)
+        t = torch.tensor([ms_total, e2e["dt"] if e2e else 0.0, phase["pileup"], phase["prep"], phase["locate"], phase["lists"]],
+                         device=dev.device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_dt, k_ms = [float(x) for x in t.tolist()]
+        ms_total, e2e_dt = float(t[0]), float(t[1])
+        phase = dict(pileup=float(t[2]), prep=float(t[3]), locate=float(t[4]), lists=float(t[5]))
         if e2e:
-            e2e = (e2e_dt, e2e[1], e2e[2], e2e[3])
-        tot = torch.tensor([units_per_step], device=dev.device, dtype=torch.float64)
+            e2e["dt"] = e2e_dt
+        tot = torch.tensor([units_per_step, reads_rank, e2e["h2d"] if e2e else 0.0, e2e["d2h"] if e2e else 0.0], device=dev.device, dtype=torch.float64)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        units_total_per_step = float(tot.item())
+        units_step_all, reads_all = float(tot[0]), float(tot[1])
+        if e2e:
+            e2e["h2d"], e2e["d2h"] = float(tot[2]), float(tot[3])
     else:
-        units_total_per_step = float(units_per_step)
+        units_step_all, reads_all = float(units_per_step), float(reads_rank)
 
     if rank == 0:
         peak, peak_src = measured_peak()
         # B_unit = 16 (variant) + 8 (index bounds) + 32 * D_raw + 160 (outputs), biallelic
         b_unit = 16 + 8 + 32.0 * d_raw + 160
-        achieved = nu * b_unit / (k_ms * 1e-3) / 1e9
-        top_kernel = "pileup_column_kernel" if w["columns"] else "pileup_warp_kernel"
+        units_per_launch = units_per_step / len(batches)
+        achieved = units_per_launch * b_unit / (phase["pileup"] * 1e-3) / 1e9
+        reads_per_launch = reads_rank / len(batches)
+        cig = float(np.mean([len(b["batch"].cigar) / max(b["batch"].n_reads, 1) for b in batches]))
+        prep_bytes = reads_per_launch * (4 + 4 + 8 + 4 + 4 * cig + 8)  # starts, CIGAR counts / offsets / words, read lengths in; end + shape out
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             with open(tp) as fh:
-                traffic = json.load(fh).get("%s_dram_bytes_per_launch" % top_kernel)
+                traffic = json.load(fh).get("r02_%s_pileup_warp_kernel_dram_bytes_per_launch" % w.name)
         cpu = None
         if not args.no_cpu_baseline:
-            n_cpu, times, cores = run_cpu_arm(args.cpu_tiles, 0, repeats=1)
+            n_cpu, times, cores, n_reads_cpu = run_cpu_arm(w, repeats=1)
             cpu = {"value": n_cpu / times[0], "unit": "units/s", "cores": cores, "kind": "port",
-                   "sample": "%d of %d targets (%d units, %.1f s): C pileup restatement (OpenMP) + reference-style scalar "
-                             "scipy epilogue (process pool); pysam itself is not installable here" % (
-                                 args.cpu_tiles, args.tiles, n_cpu, times[0])}
+                   "sample": "the first %d units (%d reads, %.1f s) of the same workload: C mate linking + pileup restatement (OpenMP) + "
+                             "reference-style scalar scipy epilogue (process pool), from the canonical read arrays; pysam itself is not "
+                             "installable here" % (n_cpu, n_reads_cpu, times[0])}
         line = {
-            "metric": "variants x BAMs annotated per second", "value": units_total_per_step * args.steps / (ms_total * 1e-3),
+            "metric": "variants x BAMs annotated per second", "value": units_step_all * args.steps / (ms_total * 1e-3),
             "unit": "units/s", "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/f64", "data": "synthetic",
-            "config": {"workload": workload, "units_per_step_per_gpu": units_per_step, "reads_per_gpu": w["n_reads"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32/f64", "data": "synthetic",
+            "config": {"workload": w.text, "units_total": int(units_step_all), "reads_total": int(reads_all),
+                       "units_per_step_rank0": units_per_step, "batches_per_step_rank0": len(batches),
+                       "boundary": "canonical columnar read batch (decoded BAM fields, untouched) + variant units in; counts + statistics out. "
+                                   "Read preparation (spans, position index, CIGAR shapes, filter, mate pairing) runs on the device inside every step",
                        "mean_depth_raw": round(d_raw, 2), "mean_candidates": round(n_cand, 2),
-                       "l2": "inputs (%.1f GB of read batches per GPU) exceed L2; tumour and normal batches alternate" % (
-                           sum(w["packed"][s].nbytes() for s in samples) / 1e9),
-                       "layout": "read-major + column store" if w["columns"] else "read-major",
-                       "sharding": "one independent interval shard per GPU, no collective",
+                       "l2": "inputs (%.1f GB of canonical read arrays on rank 0) exceed L2; the batches of a step alternate" % (
+                           sum(b["host"].nbytes() for b in batches) / 1e9),
+                       "sharding": "ONE input; units cut into %d equal interval shards (sharding.unit_cuts), shard k -> rank k, each rank holds the "
+                                   "reads its columns can reach; no collective on the data path" % world,
                        "numa_node_rank0": numa},
-            "roofline": {"bound": "hbm", "kernel": top_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "pileup_warp_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_unit": b_unit, "units_per_launch": nu, "kernel_ms": k_ms},
+                         "algorithmic_bytes_per_unit": b_unit, "units_per_launch": units_per_launch, "kernel_ms": phase["pileup"],
+                         "phases_ms_per_launch": {k: round(v, 5) for k, v in phase.items()},
+                         "prep_kernels": {"bytes_per_launch": prep_bytes, "achieved": prep_bytes / (phase["prep"] * 1e-3) / 1e9 if phase["prep"] > 0 else None,
+                                          "unit": "GB/s", "frac": prep_bytes / (phase["prep"] * 1e-3) / 1e9 / peak if phase["prep"] > 0 else None}},
             "cpu_baseline": cpu,
-            "e2e": None if e2e is None else {"value": units_total_per_step / e2e[0], "unit": "units/s",
-                                            "h2d_bytes_per_step": int(e2e[1]), "d2h_bytes_per_step": int(e2e[2]),
-                                            "ms_per_step": 1e3 * e2e[0],
-                                            "transfer": e2e[3]},
+            "e2e": None if e2e is None else {"value": units_step_all / e2e["dt"], "unit": "units/s",
+                                            "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),
+                                            "ms_per_step": 1e3 * e2e["dt"], "h2d_measured_by": e2e["h2d_how"],
+                                            "h2d_copied_bytes_per_step_rank0": int(e2e["staged"]), "pcie_rx_gbs_rank0": e2e["rx_gbs"],
+                                            "transfer": e2e["transfer"]},
             "gpu_launches": int(launches), "clocks": clk,
         }
         print(json.dumps(line), file=_RESULT_OUT, flush=True)

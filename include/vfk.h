@@ -194,6 +194,13 @@ int vfk_pileup_values(vfk_handle *h, const vfk_read_batch *reads, const vfk_vari
 int vfk_ranksum_values(vfk_handle *h, int64_t n_pairs, const uint32_t *alt, const int64_t *alt_off, const uint32_t *ref,
                        const int64_t *ref_off, uint64_t *s2, void *stream);
 
+/* Per-phase device times of the handle's calls, measured with CUDA events on the launching stream (what bench.py's roofline
+ * is computed from).  vfk_set_timing(h, 1), then after a call (and, for the host entry point, its vfk_wait):
+ * vfk_last_timing -> ms[0] read preparation (prep + scan kernels), ms[1] locate kernel, ms[2] the register pileup kernel
+ * (pileup_warp_kernel), ms[3] list path (link + histogram kernels), ms[4] epilogue kernel (host entry point only, else 0). */
+int vfk_set_timing(vfk_handle *h, int on);
+int vfk_last_timing(vfk_handle *h, double ms[5]);
+
 /* Number of kernel launches issued through this handle since it was created. */
 int64_t vfk_launch_count(vfk_handle *h);
 

@@ -83,6 +83,8 @@ typedef struct {
     float p_softclip, p_del, p_ins, p_skip;            /* private CIGAR noise per read */
     float p_dup, p_supp, p_secondary, p_qcfail, p_orphan;
     float p_mapq60, base_error, p_n;
+    uint64_t read_salt;         /* mixed into the seed of every read pair, not into the genome / planted sites: samples that
+                                   share their variant sites but not their reads (0 = the plain seed) */
     int64_t g_first, g_count;   /* generate only the tiles [g_first, g_first + g_count) of the genome, global tile index =
                                    contig * tiles_per_contig + tile (g_count 0 = all): an interval shard of the same input */
 } vfkio_synth_cfg;

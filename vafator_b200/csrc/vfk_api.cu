@@ -18,6 +18,7 @@ struct PileupScratch {
     int32_t *column;
     uint32_t *claimed;
     uint32_t *mate;
+    cudaEvent_t *ev;
 };
 cudaError_t launch_prep(const ReadsDev &R, const int32_t *pos_src, int32_t *pos_copy, int32_t *end_out, uint32_t *ev_out, int64_t *blk_max,
                         int64_t *blk_incl, uint32_t *batch_status, cudaStream_t stream, int *launches);
@@ -99,6 +100,8 @@ struct Work {
     DevBuf end, ev, blk_max, blk_incl, resolved, lists, next, column, claimed, mate, heads;
     uint32_t n_buckets = 0;
     void *counters = nullptr;  // 64 B, layout in vfk_pileup.cu (PileupScratch)
+    cudaEvent_t tev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // phase boundaries when timing is on
+    bool ev_epilogue = false;
     int reserve(int64_t n_reads, int64_t n_units, cudaStream_t st) {
         const size_t nr = (size_t)(n_reads > 0 ? n_reads : 1), nu = (size_t)(n_units > 0 ? n_units : 1);
         const size_t nb = (nr + vfk::PREP_BLOCK - 1) / vfk::PREP_BLOCK;
@@ -126,6 +129,7 @@ struct Work {
         s.resolved = resolved.p; s.counters = counters; s.lists = (uint32_t *)lists.p;
         s.heads = (uint32_t *)heads.p; s.n_buckets = n_buckets; s.next = (uint32_t *)next.p; s.column = (int32_t *)column.p;
         s.claimed = (uint32_t *)claimed.p; s.mate = (uint32_t *)mate.p;
+        s.ev = nullptr;
         return s;
     }
     void release() {
@@ -134,6 +138,10 @@ struct Work {
         n_buckets = 0;
         if (counters) cudaFree(counters);
         counters = nullptr;
+        for (cudaEvent_t &e : tev) {
+            if (e) cudaEventDestroy(e);
+            e = nullptr;
+        }
     }
 };
 
@@ -166,6 +174,8 @@ struct vfk_handle {
     Slot slot[2];
     int next_slot = 0;
     int64_t staged_bytes = 0, d2h_bytes = 0, zero_copy_batches = 0, staged_batches = 0;
+    bool timing = false;     // vfk_set_timing
+    Work *timed = nullptr;   // the working set of the last timed call
     bool link_all = false;   // debug hook (VFK_DEBUG_LINK_ALL=1 when the handle is created): partners from the link kernels everywhere
     bool stage_all = false;  // VFK_HOST_STAGE_ALL=1 when the handle is created: the host entry point copies every array
     // Carter k / d per depth for the last (fpr, error_rate) seen, depths [0, CARTER_DEPTHS)
@@ -295,11 +305,25 @@ static void to_dev(const vfk_read_batch *r, const vfk_variant_batch *v, const Wo
 // read preparation on `st`: counters zeroed, spans / shapes / position index derived (R's canonical pointers are device
 // visible; `pos_src` is where prep_kernel reads the starts, `pos_copy` an optional device copy it writes)
 static int enqueue_prep(vfk_handle *h, Work &w, const vfk::ReadsDev &R, cudaStream_t st, int *launches) {
+    if (h->timing) {
+        for (cudaEvent_t &e : w.tev)
+            if (!e) CU(cudaEventCreate(&e));
+        w.ev_epilogue = false;
+        h->timed = &w;
+        CU(cudaEventRecord(w.tev[0], st));
+    }
     CU(cudaMemsetAsync(w.counters, 0, 64, st));
     cudaError_t e = vfk::launch_prep(R, R.pos, nullptr, (int32_t *)w.end.p, (uint32_t *)w.ev.p, (int64_t *)w.blk_max.p, (int64_t *)w.blk_incl.p,
                                      (uint32_t *)((char *)w.counters + 20), st, launches);
     if (e != cudaSuccess) return fail(VFK_ECUDA, "prep launch: %s", cudaGetErrorString(e));
+    if (h->timing) CU(cudaEventRecord(w.tev[1], st));
     return VFK_OK;
+}
+
+static vfk::PileupScratch scratch_of(vfk_handle *h, Work &w) {
+    vfk::PileupScratch s = w.scratch();
+    if (h->timing) s.ev = w.tev;
+    return s;
 }
 
 extern "C" int vfk_pileup(vfk_handle *h, const vfk_read_batch *reads, const vfk_variant_batch *units,
@@ -319,7 +343,7 @@ extern "C" int vfk_pileup(vfk_handle *h, const vfk_read_batch *reads, const vfk_
     int launches = 0;
     rc = enqueue_prep(h, h->work, R, st, &launches);
     if (rc) return rc;
-    cudaError_t e = vfk::launch_pileup(R, V, *params, reads->max_l_qseq, out, h->work.scratch(), h->sm_count, st, &launches, h->link_all);
+    cudaError_t e = vfk::launch_pileup(R, V, *params, reads->max_l_qseq, out, scratch_of(h, h->work), h->sm_count, st, &launches, h->link_all);
     h->launches += launches;
     if (e != cudaSuccess) return fail(VFK_ECUDA, "pileup launch: %s", cudaGetErrorString(e));
     return VFK_OK;
@@ -496,7 +520,7 @@ extern "C" int vfk_annotate_host_async(vfk_handle *h, const vfk_read_batch *read
         to_dev(&dr, &dv, S.work, R, V);
         rc = enqueue_prep(h, S.work, R, st, &launches);
         if (rc) goto failed;
-        e = vfk::launch_pileup(R, V, *params, reads->max_l_qseq, (vfk_counts *)S.counts.p, S.work.scratch(), h->sm_count, st, &launches,
+        e = vfk::launch_pileup(R, V, *params, reads->max_l_qseq, (vfk_counts *)S.counts.p, scratch_of(h, S.work), h->sm_count, st, &launches,
                                h->link_all);
         if (e != cudaSuccess) { rc = fail(VFK_ECUDA, "pileup launch: %s", cudaGetErrorString(e)); goto failed; }
         rc = ensure_carter(h, fpr, error_rate, st);
@@ -504,6 +528,10 @@ extern "C" int vfk_annotate_host_async(vfk_handle *h, const vfk_read_batch *read
         e = vfk::launch_epilogue(nu, (const vfk_counts *)S.counts.p, d_eaf, fpr, error_rate, h->carter.p, CARTER_DEPTHS, (vfk_stats *)S.stats.p,
                                  st, &launches);
         if (e != cudaSuccess) { rc = fail(VFK_ECUDA, "epilogue launch: %s", cudaGetErrorString(e)); goto failed; }
+        if (h->timing) {
+            cudaEventRecord(S.work.tev[5], st);
+            S.work.ev_epilogue = true;
+        }
     }
     h->launches += launches;
     if (cudaMemcpyAsync(counts_out, S.counts.p, (size_t)nu * sizeof(vfk_counts), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
@@ -533,6 +561,29 @@ extern "C" int vfk_annotate_host(vfk_handle *h, const vfk_read_batch *reads, con
     int rc = vfk_annotate_host_async(h, reads, units, params, eaf, fpr, error_rate, counts_out, stats_out, &ticket);
     if (rc) return rc;
     return vfk_wait(h, ticket);
+}
+
+extern "C" int vfk_set_timing(vfk_handle *h, int on) {
+    if (!h) return fail(VFK_EINVAL, "vfk_set_timing: NULL handle");
+    h->timing = on != 0;
+    if (!h->timing) h->timed = nullptr;
+    return VFK_OK;
+}
+
+extern "C" int vfk_last_timing(vfk_handle *h, double ms[5]) {
+    if (!h || !ms) return fail(VFK_EINVAL, "vfk_last_timing: NULL argument");
+    if (!h->timed) return fail(VFK_EINVAL, "vfk_last_timing: no timed call (vfk_set_timing first)");
+    Work &w = *h->timed;
+    CU(cudaSetDevice(h->device));
+    CU(cudaEventSynchronize(w.tev[w.ev_epilogue ? 5 : 4]));
+    for (int k = 0; k < 5; ++k) {
+        float t = 0.f;
+        ms[k] = 0.0;
+        if (k == 4 && !w.ev_epilogue) break;
+        CU(cudaEventElapsedTime(&t, w.tev[k], w.tev[k + 1]));
+        ms[k] = (double)t;
+    }
+    return VFK_OK;
 }
 
 extern "C" int vfk_transfer_stats(vfk_handle *h, int64_t out[4]) {

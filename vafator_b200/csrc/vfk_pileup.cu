@@ -817,6 +817,7 @@ struct PileupScratch {
     int32_t *column;
     uint32_t *claimed;
     uint32_t *mate;
+    cudaEvent_t *ev;  // timing (vfk_set_timing): [2] after locate, [3] after the register kernel, [4] after the list path; or NULL
 };
 
 template <int POSB>
@@ -839,6 +840,7 @@ static cudaError_t launch_posb(ReadsDev R, const UnitsDev &V, const vfk_params &
     R.mate = S.mate;
     locate_kernel<<<(unsigned)((V.n + 255) / 256), 256, 0, stream>>>(R, V, res);
     ++*launches;
+    if (S.ev) cudaEventRecord(S.ev[2], stream);
     int ctas_per_sm = 0;
     e = link_all ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pileup_warp_kernel<POSB, false>, WARPS_PER_CTA * 32, 0)
                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pileup_warp_kernel<POSB, true>, WARPS_PER_CTA * 32, 0);
@@ -860,6 +862,7 @@ static cudaError_t launch_posb(ReadsDev R, const UnitsDev &V, const vfk_params &
     ++*launches;
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    if (S.ev) cudaEventRecord(S.ev[3], stream);
     if (!link_all) {  // overlap partners of the reads inside the windows of the listed units (both lists)
         e = launch_link(R, P, res, warp_list, n_warp, V.n, S.heads, S.n_buckets, S.next, S.column, S.claimed, S.mate, sm_count, stream, launches);
         if (e != cudaSuccess) return e;
@@ -885,6 +888,7 @@ static cudaError_t launch_posb(ReadsDev R, const UnitsDev &V, const vfk_params &
         ++*launches;
         e = cudaGetLastError();
     }
+    if (S.ev) cudaEventRecord(S.ev[4], stream);
     return e;
 }
 

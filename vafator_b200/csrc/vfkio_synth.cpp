@@ -245,7 +245,7 @@ void gen_pairs(const vfkio_synth_cfg *c, int32_t tid, int64_t k, int32_t own_lo,
     ctx.build(c, tid, T, T + c->tile_len + 700 + c->read_len + 64);
     for (int j = 0; j < c->pairs_per_tile; ++j) {
         const uint64_t pair_id = ((uint64_t)tid * (uint64_t)c->tiles_per_contig + (uint64_t)k) * (uint64_t)c->pairs_per_tile + (uint64_t)j + 1;
-        Rng rng(hash3(c->seed, pair_id, 0x9A12ull));
+        Rng rng(hash3(c->seed ^ c->read_salt, pair_id, 0x9A12ull));
         int frag = (int)std::lround(c->frag_mean + c->frag_sd * rng.gauss());
         frag = std::max(frag, c->read_len);
         frag = std::min(frag, c->read_len + 700);
@@ -265,7 +265,7 @@ void gen_pairs(const vfkio_synth_cfg *c, int32_t tid, int64_t k, int32_t own_lo,
         }
         const uint8_t mq1 = rng.uni() < c->p_mapq60 ? 60 : LOWMQ[rng.below(6)];
         const uint8_t mq2 = rng.uni() < c->p_mapq60 ? 60 : LOWMQ[rng.below(6)];
-        Rng r1(hash3(c->seed, pair_id, 1)), r2(hash3(c->seed, pair_id, 2));
+        Rng r1(hash3(c->seed ^ c->read_salt, pair_id, 1)), r2(hash3(c->seed ^ c->read_salt, pair_id, 2));
         if (s1 >= own_lo && s1 < own_hi) {
             out.emplace_back();
             ReadOut &o = out.back();

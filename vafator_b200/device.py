@@ -109,6 +109,8 @@ def libvfk():
         lib.vfk_annotate_host_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                                 C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.vfk_wait.argtypes = [C.c_void_p, C.c_int]
+        lib.vfk_set_timing.argtypes = [C.c_void_p, C.c_int]
+        lib.vfk_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         lib.vfk_transfer_stats.restype = C.c_int
         lib.vfk_transfer_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         lib.vfk_annotate_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
@@ -401,6 +403,15 @@ class Device:
         out = (C.c_int64 * 4)()
         _check(self.lib.vfk_transfer_stats(self.h, out))
         return dict(staged_bytes=int(out[0]), zero_copy_batches=int(out[1]), staged_batches=int(out[2]), d2h_bytes=int(out[3]))
+
+    def set_timing(self, on: bool):
+        _check(self.lib.vfk_set_timing(self.h, C.c_int(1 if on else 0)))
+
+    def last_timing(self) -> Dict[str, float]:
+        """Device milliseconds per phase of the last call made while timing was on (vfk_last_timing)."""
+        out = (C.c_double * 5)()
+        _check(self.lib.vfk_last_timing(self.h, out))
+        return dict(prep=out[0], locate=out[1], pileup=out[2], lists=out[3], epilogue=out[4])
 
     def to_host(self, buf, dtype, n):
         return buf.cpu().numpy().view(dtype)[:n].copy()

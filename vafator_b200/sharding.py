@@ -24,6 +24,12 @@ class Shard:
     read_hi: int
 
 
+def unit_cuts(n_units: int, n_shards: int) -> List[int]:
+    """Boundaries of <= n_shards contiguous runs of units (genome order) of equal size: shard k = [cuts[k], cuts[k+1])."""
+    n_shards = max(1, min(n_shards, max(n_units, 1)))
+    return [int(round(k * n_units / n_shards)) for k in range(n_shards + 1)]
+
+
 def plan_shards(batch: ReadBatch, units: VariantUnits, n_shards: int, passes: Optional[np.ndarray] = None,
                 stop: Optional[np.ndarray] = None) -> List[Shard]:
     """Cut `units` (in genome order) into <= n_shards contiguous runs and find, for each, the read index
@@ -38,8 +44,8 @@ def plan_shards(batch: ReadBatch, units: VariantUnits, n_shards: int, passes: Op
     order_ok = np.all((units.tid[1:] > units.tid[:-1]) | ((units.tid[1:] == units.tid[:-1]) & (units.pos[1:] >= units.pos[:-1])))
     if not order_ok:
         raise ValueError("units must be in genome order to be sharded by interval")
-    n_shards = max(1, min(n_shards, n))
-    cuts = [int(round(k * n / n_shards)) for k in range(n_shards + 1)]
+    cuts = unit_cuts(n, n_shards)
+    n_shards = len(cuts) - 1
     placed = batch.tid >= 0
     tid = batch.tid[placed].astype(np.int64)
     pos = batch.pos[placed].astype(np.int64)

@@ -25,7 +25,7 @@ class SynthCfgC(C.Structure):
                 ("p_softclip", C.c_float), ("p_del", C.c_float), ("p_ins", C.c_float), ("p_skip", C.c_float),
                 ("p_dup", C.c_float), ("p_supp", C.c_float), ("p_secondary", C.c_float), ("p_qcfail", C.c_float),
                 ("p_orphan", C.c_float), ("p_mapq60", C.c_float), ("base_error", C.c_float), ("p_n", C.c_float),
-                ("g_first", C.c_int64), ("g_count", C.c_int64)]
+                ("read_salt", C.c_uint64), ("g_first", C.c_int64), ("g_count", C.c_int64)]
 
 
 class _PlanC(C.Structure):
@@ -63,6 +63,7 @@ class SynthConfig:
     p_mapq60: float = 0.85
     base_error: float = 0.002
     p_n: float = 0.001
+    read_salt: int = 0  # changes the reads, not the genome / planted sites: several samples over one variant set
     # generate only the tiles [g_first, g_first + g_count) of the genome (global tile index = contig * tiles_per_contig +
     # tile; g_count 0 = everything): an interval shard of the SAME input, read for read
     g_first: int = 0
@@ -102,8 +103,8 @@ def wgs(n_contigs=1, contig_len=10_000_000, seed=BASE_SEED + 3, **kw) -> SynthCo
 def multisample(sample: int, n_tiles=40_000, seed=BASE_SEED + 4, **kw) -> SynthConfig:
     """C4: 60x samples over a shared target set (same sites for every sample: site hashes do not
     depend on the read seed), 2 % multiallelic SNV sites."""
-    c = wes(n_tiles=n_tiles, seed=seed, pairs_per_tile=72, multiallelic_pct=2, indel_period=5000, **kw)
-    return c
+    return wes(n_tiles=n_tiles, seed=seed, pairs_per_tile=72, multiallelic_pct=2, indel_period=5000,
+               read_salt=0x5A17 * (sample + 1), **kw)
 
 
 def amplicon(n_tiles=5_000, depth_pairs=900, seed=BASE_SEED + 5, **kw) -> SynthConfig:
@@ -148,10 +149,21 @@ def reads(cfg: SynthConfig, pinned: bool = False) -> ReadBatch:
     return ReadBatch(contigs=cfg.contigs, pinned=pinned, **arr)
 
 
+def tile_range(cfg: SynthConfig, tid_a: int, pos_a: int, tid_b: int, pos_b: int, margin: int = 2):
+    """(g_first, g_count): the tiles whose reads can reach the columns from (tid_a, pos_a) to (tid_b, pos_b), `margin`
+    tiles added on both sides (a read starts at most one stride + its reference span before a column it covers)."""
+    def g(tid, pos, d):
+        k = (pos - cfg.tile_offset) // cfg.tile_stride + d
+        return tid * cfg.tiles_per_contig + min(max(k, 0), cfg.tiles_per_contig - 1)
+    a, b = g(tid_a, pos_a, -margin), g(tid_b, pos_b, margin)
+    return a, b - a + 1
+
+
 def sites(cfg: SynthConfig):
-    """Planted sites as structured arrays (tid, pos1, kind, length, bases[24])."""
+    """Planted sites as structured arrays (tid, pos1, kind, length, bases[24]) -- of the whole genome, whatever tile range
+    the config generates reads for."""
     lib = _lib()
-    c = cfg.c()
+    c = replace(cfg, g_first=0, g_count=0).c()
     cap = 1 << 16
     while True:
         tid = np.empty(cap, np.int32)
