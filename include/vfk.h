@@ -194,6 +194,12 @@ int vfk_pileup_values(vfk_handle *h, const vfk_read_batch *reads, const vfk_vari
 int vfk_ranksum_values(vfk_handle *h, int64_t n_pairs, const uint32_t *alt, const int64_t *alt_off, const uint32_t *ref,
                        const int64_t *ref_off, uint64_t *s2, void *stream);
 
+/* The words the read-preparation kernel derives per read, for tests and tools (DEVICE pointers): end[i] = pos + reference bases
+ * consumed (htslib bam_endpos); shape[i] = 0 when the CIGAR is one M/=/X op covering the read, 0xFFFFFFFF for a general CIGAR,
+ * else leading soft clip | first block length << 12 | event (1 I, 2 D, 3 N) << 24 | event length << 26 for
+ * [H*][S] M [ (I|D|N) M ] [S][H*]; *status = VFK_ST_BADBATCH or 0. */
+int vfk_prep_words(vfk_handle *h, const vfk_read_batch *reads, int32_t *end_out, uint32_t *shape_out, uint32_t *status_out, void *stream);
+
 /* Per-phase device times of the handle's calls, measured with CUDA events on the launching stream (what bench.py's roofline
  * is computed from).  vfk_set_timing(h, 1), then after a call (and, for the host entry point, its vfk_wait):
  * vfk_last_timing -> ms[0] read preparation (prep + scan kernels), ms[1] locate kernel, ms[2] the register pileup kernel

@@ -126,27 +126,42 @@ def test_power_and_rank_sum_api_known_answers():
     assert get_rank_sum_tests({"A": [20, 25, 30]}, v) == ([], [])
 
 
-def test_collect_metrics_for_chrom_call_site(tmp_path):
-    """The reference's first call site, same signature, on a BAM file."""
+@pytest.mark.parametrize("name,run_index", [("pileup_random_11.json", 0), ("pileup_random_14.json", 2), ("pileup_handmade.json", 1)])
+def test_collect_metrics_for_chrom_call_site(tmp_path, name, run_index):
+    """The reference's first call site, same signature and same return type, on a BAM file: every field of every
+    CoverageMetrics -- allele counts of every observed base, depth, medians, and the full per-read lists in read order --
+    equals what the unmodified reference function returned (goldens).  (The reference also keeps a "" entry for reads
+    inside a deletion, which nothing downstream reads: not reproduced.)  The same objects drive the unmodified reference
+    annotator in tests/test_reference_callsite.py."""
     from vafator_b200.pileups import collect_metrics_for_chrom
-    sc = H.load_scenario(os.path.join(H.GOLDEN, "pileup_random_11.json"))
-    run = sc["runs"][0]
+    sc = H.load_scenario(os.path.join(H.GOLDEN, name))
+    run = sc["runs"][run_index]
     p = tmp_path / "a.bam"
     bamio.write_bam(str(p), sc["bams"][0], sc["contigs"])
     bam = bamio.BamFile(str(p))
-    variants = [VariantRecord(v["chrom"], v["pos"], v["ref"], v["alts"]) for v in sc["variants"]]
-    res = collect_metrics_for_chrom("chr1", variants, bam, run["params"]["min_bq"], run["params"]["min_mq"], True)
     gold = run["metrics"][0]
-    assert {"chr1:%d:%s:%s" % k for k in res} == set(gold)
-    for (pos, ref, alt0), m in res.items():
-        g = gold["chr1:%d:%s:%s" % (pos, ref, alt0)]
-        assert m.dp == g["dp"]
-        for allele, n in g["ac"].items():
-            if allele in (ref, alt0.upper() if len(ref) != len(alt0) else alt0):
-                assert m.ac[allele] == n
-        for allele in m.mqs:
-            want = g["mqs"].get(allele)
-            assert (math.isnan(m.mqs[allele]) and want is None) or m.mqs[allele] == want
+    seen = set()
+    for chrom in sc["contigs"]:
+        variants = [VariantRecord(v["chrom"], v["pos"], v["ref"], v["alts"]) for v in sc["variants"] if v["chrom"] == chrom]
+        if not variants:
+            continue
+        res = collect_metrics_for_chrom(chrom, variants, bam, run["params"]["min_bq"], run["params"]["min_mq"],
+                                        run["params"]["include_ambiguous"])
+        for (pos, ref, alt0), m in res.items():
+            key = "%s:%d:%s:%s" % (chrom, pos, ref, alt0)
+            seen.add(key)
+            g = gold[key]
+            strip = lambda d: {k: v for k, v in d.items() if k != ""}
+            assert m.dp == g["dp"], key
+            assert {k: v for k, v in m.ac.items() if v} == {k: v for k, v in strip(g["ac"]).items() if v}, key
+            for ours, theirs in ((m.all_mqs, g["all_mqs"]), (m.all_bqs, g["all_bqs"]), (m.all_positions, g["all_positions"])):
+                assert {k: list(v) for k, v in dict(ours).items()} == strip(theirs), key
+            for ours, theirs in ((m.mqs, g["mqs"]), (m.bqs, g["bqs"]), (m.positions, g["positions"])):
+                t = strip(theirs)
+                assert set(dict(ours)) == set(t), key
+                for k, v in t.items():
+                    assert (v is None and math.isnan(ours[k])) or ours[k] == v, (key, k)
+    assert seen == set(gold)
 
 
 def test_nist_variant_set_on_the_device_equals_the_oracle_double(tmp_path_factory, monkeypatch):

@@ -332,3 +332,54 @@ def test_three_alignments_of_one_name_take_the_general_protocol(dev):
     for mq, bq in ((0, 0), (1, 30), (0, 41)):
         want = c_oracle.pileup(batch.as_dict(), ou, c_oracle.params(min_mapq=mq, min_baseq=bq))
         _compare(_gpu(dev, batch, units, stop, mq, bq), want)
+
+
+def _one_event_word(ops, l_qseq):
+    """include/vfk.h vfk_prep_words: [H*][S] M [ I|D|N M ] [S][H*] -> lead | m1 << 12 | event << 24 | len << 26, else None."""
+    import re
+    m = re.fullmatch(r"(?:\d+H)*(?:(\d+)S)?(\d+)[M=X](?:(\d+)([IDN])(\d+)[M=X])?(?:\d+S)?(?:\d+H)*", "".join("%d%s" % (n, o) for n, o in ops))
+    if not m:
+        return None
+    lead, m1 = int(m.group(1) or 0), int(m.group(2))
+    ev, ln = ("IDN".index(m.group(4)) + 1, int(m.group(3))) if m.group(4) else (0, 0)
+    if m1 == 0 or m1 >= 4096 or lead >= 4096 or ln >= 64 or l_qseq > 4095 or (m.group(4) and (ln == 0 or int(m.group(5)) == 0)):
+        return None
+    return lead | (m1 << 12) | (ev << 24) | (ln << 26)
+
+
+def test_read_preparation_words(dev):
+    """prep_kernel against an independent reading of every CIGAR: reference end (htslib bam_endpos) and the shape word, on
+    synthetic reads with heavy CIGAR noise and on handmade shapes (hard clips, pads, consecutive events, zero lengths)."""
+    import random
+    from vafator_b200.batch import ReadBatch, CIGAR_CHARS
+    cfg = synth.wes(n_tiles=1500, p_softclip=0.3, p_del=0.2, p_ins=0.2, p_skip=0.1)
+    batch = synth.reads(cfg)
+    rng = random.Random(5)
+    recs = []
+    shapes = ["20M", "5S15M", "3H5S12M3S2H", "10M2D10M", "10M2I8M", "4S6M100N10M", "20S", "10M2D", "5M0D15M", "5M1P1I14M", "5M2I2I11M",
+              "2H18M2H", "5M3D5M2D10M", "10M70D10M", "10M63I10M", "18M2S", "2S3S15M", "5H5H20M", "10M2D0M", "1M", "20="]
+    for k in range(400):
+        if k < len(shapes):
+            cg = shapes[k]
+        else:
+            parts = []
+            for _ in range(rng.randint(1, 6)):
+                parts.append("%d%s" % (rng.choice([0, 1, 2, 5, 17, 63, 64, 120]), rng.choice("MIDNSHP=X")))
+            cg = "".join(parts)
+        import re
+        ops = [(int(n), o) for n, o in re.findall(r"(\d+)([MIDNSHP=X])", cg)]
+        lq = sum(n for n, o in ops if o in "MIS=X")
+        recs.append(dict(qname="r%d" % k, flag=0, tid=0, pos=1000 + k, mapq=60, cigar=cg, seq="A" * lq, qual=[30] * lq))
+    hand = ReadBatch.from_records(recs, ["c"])
+    for b in (batch, hand):
+        end, shape, status = dev.prep_words(dev.upload_reads(b))
+        assert status == 0
+        n = b.n_placed
+        for i in range(n):
+            ops = [(int(w) >> 4, CIGAR_CHARS[int(w) & 15]) for w in b.cigar[int(b.cigar_off[i]):int(b.cigar_off[i]) + int(b.n_cigar[i])]]
+            span = sum(l for l, o in ops if o in "MDN=X")
+            assert end[i] == b.pos[i] + span, (i, ops)
+            lq = int(b.l_qseq[i])
+            simple = len(ops) == 1 and ops[0][1] in "M=X" and ops[0][0] == lq
+            word = 0 if simple else _one_event_word(ops, lq)
+            assert shape[i] == (0xFFFFFFFF if word is None else word), (i, ops, hex(int(shape[i])), word)

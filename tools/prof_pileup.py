@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Minimal driver for profiling: one synthetic WES BAM (C2 geometry), N launches of the pileup path.
+"""Minimal driver for profiling: one synthetic BAM (canonical batch resident in HBM), N launches of the pileup path (read preparation, locate, pileup kernels).
     python tools/prof_pileup.py [--tiles 200000] [--launches 6] [--workload wes|wgs|amplicon]"""
 import argparse
 import os
@@ -17,10 +17,9 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--tiles", type=int, default=200_000)
 ap.add_argument("--launches", type=int, default=6)
 ap.add_argument("--workload", default="wes")
-ap.add_argument("--columns", action="store_true", help="evaluate SNV units from the column store")
 ap.add_argument("--snv-period", type=int, default=500, help="wes: one SNV per this many target bases (small = L2-resident reads, many units)")
 a = ap.parse_args()
-cfg = {"wes": lambda: synth.wes(n_tiles=a.tiles, snv_period=a.snv_period), "wgs": lambda: synth.wgs(contig_len=a.tiles * 4096 // 10),
+cfg = {"wes": lambda: synth.wes(n_tiles=a.tiles, snv_period=a.snv_period), "wgs": lambda: synth.wgs(contig_len=a.tiles * 4096 // 10, n_contigs=2),
        "amplicon": lambda: synth.amplicon(n_tiles=max(a.tiles // 100, 10))}[a.workload]()
 t0 = time.time()
 batch = synth.reads(cfg)
@@ -28,7 +27,7 @@ recs = synth.variant_records(cfg)
 units = build_units(recs, cfg.contigs)
 params = device.make_params(min_mapq=1, min_baseq=30)
 dev = device.Device(0)
-dreads = dev.upload_reads(device.pack_reads(batch, params, columns=a.columns))
+dreads = dev.upload_reads(batch)
 dunits = dev.upload_units(units, None)
 out = dev.alloc_counts(units.n_units)
 print("setup %.1f s: %d reads, %d units" % (time.time() - t0, batch.n_reads, units.n_units), flush=True)
@@ -56,3 +55,8 @@ ms = [x.elapsed_time(y) for x, y in evs]
 c = dev.to_host(out, device.COUNTS_DTYPE, units.n_units)
 print("pileup ms per launch:", " ".join("%.3f" % m for m in ms), "| mean n_cover %.2f n_cand %.2f dp %.2f" % (
     c["n_cover"].mean(), c["n_cand"].mean(), c["dp"].mean()))
+st = (c["status"] >> 4)
+print("units by status bits:", {int(k): int(v) for k, v in zip(*np.unique(st, return_counts=True))})
+dev.set_timing(True)
+dev.pileup(dreads, dunits, params, out=out)
+print("phases ms:", dev.last_timing())

@@ -20,8 +20,8 @@ struct PileupScratch {
     uint32_t *mate;
     cudaEvent_t *ev;
 };
-cudaError_t launch_prep(const ReadsDev &R, const int32_t *pos_src, int32_t *pos_copy, int32_t *end_out, uint32_t *ev_out, int64_t *blk_max,
-                        int64_t *blk_incl, uint32_t *batch_status, cudaStream_t stream, int *launches);
+cudaError_t launch_prep(const ReadsDev &R, const int32_t *pos_src, int32_t *pos_copy, int32_t *end_out, uint32_t *ev_out, int64_t *chunk_max,
+                        int64_t *blk_max, int64_t *blk_incl, uint32_t *batch_status, cudaStream_t stream, int *launches);
 cudaError_t launch_pileup(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, int max_l_qseq, vfk_counts *out,
                           const PileupScratch &S, int sm_count, cudaStream_t stream, int *launches, bool link_all);
 cudaError_t launch_locate_only(const ReadsDev &R, const UnitsDev &V, void *resolved, cudaStream_t stream, int *launches);
@@ -97,7 +97,7 @@ struct PinBuf {  // page-locked host scratch
 // lists and the link scratch.  The bucket heads and the claim bitmap are kept clean by the link kernels themselves
 // (set once when (re)allocated).
 struct Work {
-    DevBuf end, ev, blk_max, blk_incl, resolved, lists, next, column, claimed, mate, heads;
+    DevBuf end, ev, chunk_max, blk_max, blk_incl, resolved, lists, next, column, claimed, mate, heads;
     uint32_t n_buckets = 0;
     void *counters = nullptr;  // 64 B, layout in vfk_pileup.cu (PileupScratch)
     cudaEvent_t tev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // phase boundaries when timing is on
@@ -106,7 +106,7 @@ struct Work {
         const size_t nr = (size_t)(n_reads > 0 ? n_reads : 1), nu = (size_t)(n_units > 0 ? n_units : 1);
         const size_t nb = (nr + vfk::PREP_BLOCK - 1) / vfk::PREP_BLOCK;
         int rc;
-        if ((rc = end.reserve(nr * 4)) || (rc = ev.reserve(nr * 4)) || (rc = blk_max.reserve(nb * 8)) || (rc = blk_incl.reserve((nb + 1) * 8)) ||
+        if ((rc = end.reserve(nr * 4)) || (rc = ev.reserve(nr * 4)) || (rc = chunk_max.reserve((nr / 32 + 1) * 8)) || (rc = blk_max.reserve(nb * 8)) || (rc = blk_incl.reserve((nb + 1) * 8)) ||
             (rc = resolved.reserve(nu * sizeof(vfk::ResolvedUnit))) || (rc = lists.reserve(nu * 2 * sizeof(uint32_t))) ||
             (rc = next.reserve(nr * 4)) || (rc = column.reserve(nr * 4)) || (rc = mate.reserve(nr * 4)))
             return rc;
@@ -133,7 +133,7 @@ struct Work {
         return s;
     }
     void release() {
-        DevBuf *bufs[] = {&end, &ev, &blk_max, &blk_incl, &resolved, &lists, &next, &column, &claimed, &mate, &heads};
+        DevBuf *bufs[] = {&end, &ev, &chunk_max, &blk_max, &blk_incl, &resolved, &lists, &next, &column, &claimed, &mate, &heads};
         for (DevBuf *b : bufs) b->release();
         n_buckets = 0;
         if (counters) cudaFree(counters);
@@ -296,6 +296,7 @@ static void to_dev(const vfk_read_batch *r, const vfk_variant_batch *v, const Wo
     R.n_contigs = r->n_contigs;
     R.end = (const int32_t *)w.end.p;
     R.ev = (const uint32_t *)w.ev.p;
+    R.chunk_max = (const int64_t *)w.chunk_max.p;
     R.blk_incl = (const int64_t *)w.blk_incl.p;
     R.mate = (const uint32_t *)w.mate.p;
     V.n = v->n_units;
@@ -313,7 +314,7 @@ static int enqueue_prep(vfk_handle *h, Work &w, const vfk::ReadsDev &R, cudaStre
         CU(cudaEventRecord(w.tev[0], st));
     }
     CU(cudaMemsetAsync(w.counters, 0, 64, st));
-    cudaError_t e = vfk::launch_prep(R, R.pos, nullptr, (int32_t *)w.end.p, (uint32_t *)w.ev.p, (int64_t *)w.blk_max.p, (int64_t *)w.blk_incl.p,
+    cudaError_t e = vfk::launch_prep(R, R.pos, nullptr, (int32_t *)w.end.p, (uint32_t *)w.ev.p, (int64_t *)w.chunk_max.p, (int64_t *)w.blk_max.p, (int64_t *)w.blk_incl.p,
                                      (uint32_t *)((char *)w.counters + 20), st, launches);
     if (e != cudaSuccess) return fail(VFK_ECUDA, "prep launch: %s", cudaGetErrorString(e));
     if (h->timing) CU(cudaEventRecord(w.tev[1], st));
@@ -393,6 +394,34 @@ extern "C" int vfk_pileup_values(vfk_handle *h, const vfk_read_batch *reads, con
     if (e == cudaSuccess) e = vfk::launch_values(R, S.resolved, V.n, V.ins_seq, *params, max_per_unit, values, n_values, st, &launches);
     h->launches += launches;
     if (e != cudaSuccess) return fail(VFK_ECUDA, "values launch: %s", cudaGetErrorString(e));
+    return VFK_OK;
+}
+
+extern "C" int vfk_prep_words(vfk_handle *h, const vfk_read_batch *reads, int32_t *end_out, uint32_t *shape_out, uint32_t *status_out,
+                              void *stream) {
+    if (!h) return fail(VFK_EINVAL, "vfk_prep_words: NULL handle");
+    vfk_variant_batch none;
+    memset(&none, 0, sizeof(none));
+    vfk_params prm;
+    memset(&prm, 0, sizeof(prm));
+    int rc = check_batches(reads, &none, &prm);
+    if (rc) return rc;
+    if (reads->n_reads == 0) return VFK_OK;
+    if (!end_out || !shape_out || !status_out) return fail(VFK_EINVAL, "vfk_prep_words: NULL output");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = h->work.reserve(reads->n_reads, 1, st);
+    if (rc) return rc;
+    vfk::ReadsDev R;
+    vfk::UnitsDev V;
+    to_dev(reads, &none, h->work, R, V);
+    int launches = 0;
+    rc = enqueue_prep(h, h->work, R, st, &launches);
+    h->launches += launches;
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(end_out, h->work.end.p, (size_t)reads->n_reads * 4, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(shape_out, h->work.ev.p, (size_t)reads->n_reads * 4, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(status_out, (char *)h->work.counters + 20, 4, cudaMemcpyDeviceToDevice, st));
     return VFK_OK;
 }
 

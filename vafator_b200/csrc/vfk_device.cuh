@@ -32,7 +32,8 @@ enum : unsigned { F_PAIRED = 1, F_PROPER = 2, F_UNMAP = 4, F_MUNMAP = 8 };
 constexpr uint32_t SHAPE_SIMPLE = 0u, SHAPE_GENERAL = 1u, SHAPE_ONE_EVENT = 2u;
 constexpr uint32_t EV_SIMPLE = 0u, EV_GENERAL = 0xFFFFFFFFu;
 constexpr int EVK_NONE = 0, EVK_INS = 1, EVK_DEL = 2, EVK_SKIP = 3;
-constexpr int PREP_BLOCK = 128;  // reads per entry of the block-level position index
+constexpr int PREP_BLOCK = 1024;  // reads per entry of the block-level position index (a chunk = 32 reads: the level below)
+constexpr int PREP_THREADS = 256;
 
 struct ReadsDev {
     // canonical arrays (device memory, or page-locked host memory read in place)
@@ -59,7 +60,8 @@ struct ReadsDev {
     // derived per call by prep_kernel / scan_kernel (device memory)
     const int32_t *__restrict__ end;       // pos + reference bases consumed
     const uint32_t *__restrict__ ev;       // CIGAR shape word
-    const int64_t *__restrict__ blk_incl;  // [n_blocks + 1]: entry b + 1 = max over the reads of blocks 0..b of tid << 32 | end
+    const int64_t *__restrict__ chunk_max; // [n_reads / 32]: max over the 32 reads of a chunk of tid << 32 | end
+    const int64_t *__restrict__ blk_incl;  // [n_blocks + 1]: entry b + 1 = max over the reads of blocks 0..b of the same key
     // overlap partners of the reads inside the windows of listed units (link kernels): partner | tie_break << 31
     const uint32_t *__restrict__ mate;
 };

@@ -83,28 +83,31 @@ __device__ __forceinline__ ResolvedUnit locate_unit(const ReadsDev &R, const Uni
     }
     // lo = first read of the contig whose end exceeds the column (no earlier read can overlap it).  blk_incl[b] is the
     // maximum of tid << 32 | end over the reads of blocks 0 .. b-1: a binary search names the first block that holds
-    // such a read, one pass over that block finds it.  The block of read a-1 may also hold reads starting beyond the
-    // column (their ends exceed it trivially), so it is scanned directly instead of being judged by its maximum.
+    // such a read, the chunk maxima of that block name the chunk (32 reads), one pass over the chunk finds the read.  The
+    // chunk of read a-1 may also hold reads starting beyond the column (their ends exceed it trivially), so it is scanned
+    // directly instead of being judged by a maximum.
     int64_t lo = a;
     if (a > c0) {
         const long long key = ((long long)tid << 32) | (long long)(uint32_t)col;
         const int64_t b_first = c0 / PREP_BLOCK, b_last = (a - 1) / PREP_BLOCK;
-        int64_t from, to;
+        int64_t ch = b_last * (PREP_BLOCK / 32);  // first chunk to look at
         if (b_last > b_first && __ldg(R.blk_incl + b_last) > key) {
             int64_t ba = b_first, bb = b_last - 1;  // smallest block with an inclusive maximum beyond the key
             while (ba < bb) {
                 const int64_t m = (ba + bb) >> 1;
                 if (__ldg(R.blk_incl + m + 1) > key) bb = m; else ba = m + 1;
             }
-            from = max(c0, ba * PREP_BLOCK);
-            to = (ba + 1) * PREP_BLOCK;  // the read is in [from, to)
-        } else {
-            from = max(c0, b_last * PREP_BLOCK);
-            to = a;
+            ch = ba * (PREP_BLOCK / 32);
         }
-        int64_t i = from;
+        ch = max(ch, c0 >> 5);
+        const int64_t ch_last = (a - 1) >> 5;
+        // a chunk before the last one qualifies by its maximum (all its reads precede `a`; reads of an earlier contig carry a
+        // smaller key); the last one is scanned whatever its maximum says
+        while (ch < ch_last && __ldg(R.chunk_max + ch) <= key) ++ch;
+        int64_t i = max(c0, ch << 5);
+        const int64_t to = min(a, (ch + 1) << 5);
         while (i < to && __ldg(R.end + i) <= col) ++i;
-        lo = min(i, a);
+        lo = i < to ? i : a;
     }
     ResolvedUnit r;
     r.col = col;

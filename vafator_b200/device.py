@@ -109,6 +109,7 @@ def libvfk():
         lib.vfk_annotate_host_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                                 C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.vfk_wait.argtypes = [C.c_void_p, C.c_int]
+        lib.vfk_prep_words.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.vfk_set_timing.argtypes = [C.c_void_p, C.c_int]
         lib.vfk_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         lib.vfk_transfer_stats.restype = C.c_int
@@ -403,6 +404,17 @@ class Device:
         out = (C.c_int64 * 4)()
         _check(self.lib.vfk_transfer_stats(self.h, out))
         return dict(staged_bytes=int(out[0]), zero_copy_batches=int(out[1]), staged_batches=int(out[2]), d2h_bytes=int(out[3]))
+
+    def prep_words(self, reads: "DeviceReads"):
+        """(end, shape word, status) the read-preparation kernel derives per read (vfk_prep_words) -- for tests."""
+        t = self.torch
+        n = reads.host.n_reads
+        end = t.empty(max(n, 1), dtype=t.int32, device=self.device)
+        shape = t.empty(max(n, 1), dtype=t.int32, device=self.device)
+        status = t.zeros(1, dtype=t.int32, device=self.device)
+        _check(self.lib.vfk_prep_words(self.h, C.byref(reads.c), C.c_void_p(end.data_ptr()), C.c_void_p(shape.data_ptr()),
+                                       C.c_void_p(status.data_ptr()), self._stream()))
+        return end.cpu().numpy()[:n], shape.cpu().numpy().view(np.uint32)[:n], int(status.cpu().numpy().view(np.uint32)[0])
 
     def set_timing(self, on: bool):
         _check(self.lib.vfk_set_timing(self.h, C.c_int(1 if on else 0)))

@@ -1,9 +1,14 @@
-"""Carrier types of the pileup path (mirror of vafator/pileup_utils.py:9-119)."""
+"""Carrier types of the pileup path (mirror of vafator/pileup_utils.py:9-119): same names, same fields, same types, so
+that the reference's own Annotator._add_stats / _annotate_sample / _annotate_replicate (vafator/annotator.py:260-420) run
+unchanged on what vafator_b200.pileups.collect_metrics_for_chrom returns."""
 from __future__ import annotations
 
 from collections import Counter
-from dataclasses import dataclass, field
-from typing import Dict, List, Optional
+from dataclasses import dataclass
+from math import nan
+from typing import Dict, List
+
+import numpy as np
 
 
 @dataclass
@@ -16,29 +21,38 @@ class VariantRecord:
 
 
 @dataclass
-class RankSum:
-    """Rank-sum result for one metric and one ALT allele (raw, unrounded FP64 from the device)."""
-    z: float
-    p: float
-
-
-@dataclass
 class CoverageMetrics:
-    """Pileup metrics of one variant in one BAM (pileup_utils.py:27-49).  Where the reference carries
-    the full per-read lists (all_bqs / all_mqs / all_positions) only to feed scipy.stats.ranksums,
-    this carries what the device already reduced them to: `ranksums[metric][alt] = RankSum`, and
-    `keys[metric]` = the alleles that have a (possibly empty) list in the reference's dictionaries."""
-    ac: Counter
+    """Pileup metrics of one variant in one BAM (vafator/pileup_utils.py:27-49), field for field:
+    ac            allele counts per observed base (Counter), including the reference and every IUPAC letter seen
+    dp            depth
+    bqs / mqs / positions          median per allele (Counter: a missing allele reads 0, an empty list nan)
+    all_bqs / all_mqs / all_positions   the per-read values per allele, in read order -- read back from the device
+                                        (vfk_pileup_values) by collect_metrics_for_chrom"""
+    ac: dict
     dp: int
-    bqs: Counter = field(default_factory=Counter)
-    mqs: Counter = field(default_factory=Counter)
-    positions: Counter = field(default_factory=Counter)
-    ranksums: Dict[str, Dict[str, RankSum]] = field(default_factory=lambda: {"mq": {}, "bq": {}, "pos": {}})
-    keys: Dict[str, set] = field(default_factory=lambda: {"mq": set(), "bq": set(), "pos": set()})
-    counts: Dict[str, int] = field(default_factory=dict)  # allele -> number of values in its lists
+    bqs: dict = None
+    mqs: dict = None
+    positions: dict = None
+    all_bqs: dict = None
+    all_mqs: dict = None
+    all_positions: dict = None
 
 
-EMPTY_METRICS = CoverageMetrics(ac=Counter(), dp=0)
+EMPTY_METRICS = CoverageMetrics(ac=Counter(), dp=0, bqs=Counter(), mqs=Counter(), positions=Counter(), all_bqs={}, all_mqs={},
+                                all_positions={})
+
+
+def aggregate_list_per_base(bases: List[str], values: list) -> Dict[str, list]:
+    """vafator/pileup_utils.py:64-79."""
+    out: Dict[str, list] = {}
+    for b, v in zip(bases, values):
+        out.setdefault(b, []).append(v)
+    return out
+
+
+def safe_median(values: list) -> float:
+    """vafator/pileup_utils.py:82-92: the median, nan for an empty list."""
+    return float(np.median(values)) if len(values) else nan
 
 
 def is_snp(variant) -> bool:

@@ -1,15 +1,20 @@
 """collect_metrics_for_chrom -- the first of the three call sites the reference's Annotator makes
 (vafator/pileups.py:106-159, called at annotator.py:225-232), backed by the device.  `bam` is a
-vafator_b200.bamio.BamFile (or anything with .read_batch()) instead of a pysam.AlignmentFile."""
+vafator_b200.bamio.BamFile (or anything with .read_batch()) instead of a pysam.AlignmentFile.
+
+Same signature, same return type: {(POS, REF, ALT[0]): CoverageMetrics} with the reference's fields -- allele counts for every
+observed base, medians, and the full per-read lists -- so the reference's own annotator code runs on it unchanged
+(tests/test_reference_callsite.py).  It is the compatibility surface: the product's Annotator goes through
+vafator_b200.engine.Engine, which keeps everything as arrays and never materialises per-read lists."""
 from __future__ import annotations
 
 from collections import Counter
-from typing import Dict, List, Tuple
+from typing import Dict, List, Sequence, Tuple
 
 import numpy as np
 
-from .batch import KIND_SNV, build_units, variant_kind
-from .pileup_utils import CoverageMetrics, RankSum
+from .batch import KIND_SNV, SEQ_CHARS, VariantUnits, build_units, variant_kind
+from .pileup_utils import CoverageMetrics, safe_median
 
 _engines = {}
 
@@ -37,6 +42,70 @@ def stream_variants_by_chrom(vcf):
         yield chrom, group
 
 
+def callsite_records(chrom: str, variants: Sequence) -> List[Tuple[str, int, str, List[str]]]:
+    """The records the compatibility call evaluates on the device.  The reference counts EVERY base it observes in an SNV
+    column (vafator/pileups.py:214-222): such a record asks for one unit per letter of the BAM alphabet other than REF, so
+    that every observed base gets its count, its medians and its lists.  Indels keep ALT[0] (pileups.py:253-261); records
+    outside [first.POS, last.POS] get no column (pileups.py:137-138)."""
+    first, last = variants[0].POS, variants[-1].POS
+    out = []
+    for v in variants:
+        if not (first <= v.POS <= last) or not v.ALT:
+            out.append((chrom, v.POS, "", []))
+        elif variant_kind(v.REF, v.ALT[0]) == KIND_SNV:
+            out.append((chrom, v.POS, v.REF, [c for c in SEQ_CHARS if c != v.REF]))
+        else:
+            out.append((chrom, v.POS, v.REF, [v.ALT[0]]))
+    return out
+
+
+def metrics_from_device(variants: Sequence, units: VariantUnits, counts: np.ndarray, values: Sequence[np.ndarray]) -> Dict[Tuple, CoverageMetrics]:
+    """Device records -> the reference's CoverageMetrics.  counts[u]: vfk_counts of unit u; values[u]: its packed per-read
+    words (vfk_pileup_values: mq | bq << 8 | read position << 16 | in_REF_list << 28 | in_ALT_list << 29), in read order.
+    `units` were built from callsite_records(...)."""
+    out: Dict[Tuple, CoverageMetrics] = {}
+    split = lambda w: ((w & 0xFF).tolist(), ((w >> 8) & 0xFF).tolist(), ((w >> 16) & 0xFFF).tolist())
+    for i, v in enumerate(variants):
+        u0 = units.unit_of.get((i, 0))
+        if u0 is None or counts["n_col"][u0] == 0:
+            continue  # no pileup column: the reference has no entry either (-> EMPTY_METRICS at annotator.py:248-250)
+        kind = variant_kind(v.REF, v.ALT[0])
+        dp = int(counts["dp"][u0])
+        if kind == KIND_SNV:
+            all_mqs, all_bqs, all_pos = {}, {}, {}
+            w0 = np.asarray(values[u0], np.uint32)
+            ref_words = w0[(w0 >> 28) & 1 == 1]
+            if len(ref_words):
+                all_mqs[v.REF], all_bqs[v.REF], all_pos[v.REF] = split(ref_words)
+            alleles = [c for c in SEQ_CHARS if c != v.REF]
+            for j, a in enumerate(alleles):
+                w = np.asarray(values[units.unit_of[(i, j)]], np.uint32)
+                w = w[(w >> 29) & 1 == 1]
+                if len(w):
+                    all_mqs[a], all_bqs[a], all_pos[a] = split(w)
+            m = CoverageMetrics(ac=Counter({b: len(l) for b, l in all_mqs.items()}), dp=dp,
+                                bqs=Counter({b: safe_median(l) for b, l in all_bqs.items()}),
+                                mqs=Counter({b: safe_median(l) for b, l in all_mqs.items()}),
+                                positions=Counter({b: safe_median(l) for b, l in all_pos.items()}),
+                                all_bqs=all_bqs, all_mqs=all_mqs, all_positions=all_pos)
+        else:
+            up = v.ALT[0].upper()
+            w0 = np.asarray(values[u0], np.uint32)
+            ref_mq, _, ref_pos = split(w0[(w0 >> 28) & 1 == 1])
+            alt_mq, _, alt_pos = split(w0[(w0 >> 29) & 1 == 1])
+            mq = {a.upper(): [] for a in v.ALT}
+            pos = {a.upper(): [] for a in v.ALT}
+            mq[v.REF], pos[v.REF] = ref_mq, ref_pos
+            mq[up], pos[up] = alt_mq, alt_pos
+            ac = {a.upper(): 0 for a in v.ALT}
+            ac[up] = int(counts["ac_alt"][u0])
+            m = CoverageMetrics(ac=Counter(ac), dp=dp, mqs=Counter({k: safe_median(l) for k, l in mq.items()}),
+                                positions=Counter({k: safe_median(l) for k, l in pos.items()}), bqs=Counter(),
+                                all_mqs=mq, all_positions=pos, all_bqs=Counter())
+        out[(v.POS, v.REF, v.ALT[0])] = m
+    return out
+
+
 def collect_metrics_for_chrom(chrom: str, variants: List, bam, min_base_quality: int, min_mapping_quality: int,
                               include_ambiguous_bases: bool = False) -> Dict[Tuple, CoverageMetrics]:
     """{(POS, REF, ALT[0]): CoverageMetrics} for the variants with a pileup column; position-sorted input,
@@ -49,56 +118,8 @@ def collect_metrics_for_chrom(chrom: str, variants: List, bam, min_base_quality:
     from .fetch import fetch_group
     # the reads the columns depend on, out of the span the reference fetches (windows around the variants: fetch.py)
     batch = fetch_group(bam, chrom, first, last, [v.POS for v in variants], eng.params) if isinstance(bam, BamFile) else bam.read_batch()
-    records = [(chrom, v.POS, v.REF, list(v.ALT)) if first <= v.POS <= last else (chrom, v.POS, "", []) for v in variants]
-    units = build_units(records, batch.contigs)
-    counts = eng.pileup(batch, units, np.full(units.n_units, last, np.int32))
-    stats = eng.epilogue(counts, np.full(units.n_units, 0.5))
-    out: Dict[Tuple, CoverageMetrics] = {}
-    for i, v in enumerate(variants):
-        u0 = units.unit_of.get((i, 0))
-        if u0 is None or counts["n_col"][u0] == 0:
-            continue
-        kind = variant_kind(v.REF, v.ALT[0])
-        c0 = counts[u0]
-        m = CoverageMetrics(ac=Counter(), dp=int(c0["dp"]))
-        med = lambda x: float(x) / 2.0 if x >= 0 else float("nan")
-        names = ("mq", "bq", "pos")
-        stores = {"mq": m.mqs, "bq": m.bqs, "pos": m.positions}
-        if kind == KIND_SNV:
-            if c0["ac_ref"] > 0:
-                m.ac[v.REF] = int(c0["ac_ref"])
-                m.counts[v.REF] = int(c0["ac_ref"])
-                for k, name in enumerate(names):
-                    stores[name][v.REF] = med(c0["med2"][k][0])
-                    m.keys[name].add(v.REF)
-            for j, alt in enumerate(v.ALT):
-                u = units.unit_of[(i, j)]
-                c = counts[u]
-                if c["ac_alt"] > 0:
-                    m.ac[alt] = int(c["ac_alt"])
-                    m.counts[alt] = int(c["ac_alt"])
-                    for k, name in enumerate(names):
-                        stores[name][alt] = med(c["med2"][k][1])
-                        m.keys[name].add(alt)
-                        if c["ac_ref"] > 0:
-                            m.ranksums[name][alt] = RankSum(float(stats[u]["z"][k]), float(stats[u]["p"][k]))
-            # ambiguous bases are part of `ac` in the reference (Counter over every observed base)
-            if c0["n_amb"] > 0:
-                m.ac["N*"] = int(c0["n_amb"])  # aggregate of all IUPAC codes; see CoverageMetrics docstring
-        else:
-            up = v.ALT[0].upper()
-            m.ac[up] = int(c0["ac_alt"])
-            m.counts[v.REF], m.counts[up] = int(c0["ac_ref"]), int(c0["ac_alt"])
-            for k, name in ((0, "mq"), (2, "pos")):
-                stores[name][v.REF] = med(c0["med2"][k][0])
-                stores[name][up] = med(c0["med2"][k][1])
-                m.keys[name].update((v.REF, up))
-                if c0["ac_ref"] > 0 and c0["ac_alt"] > 0:
-                    m.ranksums[name][up] = RankSum(float(stats[u0]["z"][k]), float(stats[u0]["p"][k]))
-            for alt in v.ALT[1:]:
-                m.ac.setdefault(alt.upper(), 0)
-                for name in ("mq", "pos"):
-                    stores[name].setdefault(alt.upper(), float("nan"))
-                    m.keys[name].add(alt.upper())
-        out[(v.POS, v.REF, v.ALT[0])] = m
-    return out
+    units = build_units(callsite_records(chrom, variants), batch.contigs)
+    stop = np.full(units.n_units, last, np.int32)
+    counts = eng.pileup(batch, units, stop)
+    values = eng.values(batch, units, stop)
+    return metrics_from_device(variants, units, counts, values)
