@@ -50,11 +50,16 @@ class OracleEngine(engine.Engine):
         for u in range(units.n_units):
             chrom, pos1 = batch.contigs[units.tid[u]], int(units.pos[u]) + 1
             kind = int(units.meta[u]) & 3
-            assert kind == 0
             ref_code, alt_code = (int(units.meta[u]) >> 8) & 0xFF, (int(units.meta[u]) >> 16) & 0xFF
             words = []
             for col in f.pileup(chrom, pos1 - 1, pos1, min_base_quality=self._prm[1], min_mapping_quality=self._prm[0],
                                 max_depth=10 ** 6):
+                if kind != 0:  # indel unit: REF list = reads without an indel here, ALT list = supporting reads (no BQ)
+                    _, _, ref, alts = recs[units.rec[u]]
+                    m = vr.column_metrics(pos1, ref, alts, col)
+                    for allele, bit in ((ref, 28), (alts[0].upper(), 29)):
+                        words += [mq | (qp << 16) | (1 << bit) for mq, qp in zip(m.dist["mq"][allele], m.dist["pos"][allele])]
+                    continue
                 for pr in col.pileups:
                     if pr.is_del or pr.is_refskip:
                         continue
@@ -296,7 +301,7 @@ def test_collect_metrics_for_chrom_call_site_on_cpu(tmp_path, monkeypatch, index
             continue
         variants = [VariantRecord(v["chrom"], v["pos"], v["ref"], v["alts"]) for v in mine]
         eng = OracleEngine(prm["min_mq"], prm["min_bq"], True, 5e-7, 1e-3)
-        eng._records = [(chrom, v.POS, v.REF, list(v.ALT)) for v in variants]
+        eng._records = pileups.callsite_records(chrom, variants)  # one unit per letter other than REF for an SNV record
         monkeypatch.setattr(pileups, "_engine", lambda *a, **k: eng)
         res = pileups.collect_metrics_for_chrom(chrom, variants, bam, prm["min_bq"], prm["min_mq"], True)
         assert {"%s:%d:%s:%s" % ((chrom,) + k) for k in res} == {k for k in gold if k.startswith(chrom + ":")}
