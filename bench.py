@@ -526,7 +526,9 @@ def main():
         # B_unit = 16 (variant) + 8 (index bounds) + 32 * D_raw + 160 (outputs), biallelic
         b_unit = 16 + 8 + 32.0 * d_raw + 160
         units_per_launch = units_per_step / len(batches)
-        achieved = units_per_launch * b_unit / (phase["pileup"] * 1e-3) / 1e9
+        # the dominant kernel of the call: the register kernel (30x / 60x columns) or the list path (deep columns: tail_kernel)
+        dominant, dom_ms = ("pileup_warp_kernel", phase["pileup"]) if phase["pileup"] >= phase["lists"] else ("tail_kernel", phase["lists"])
+        achieved = units_per_launch * b_unit / (dom_ms * 1e-3) / 1e9
         reads_per_launch = reads_rank / len(batches)
         cig = float(np.mean([len(b["batch"].cigar) / max(b["batch"].n_reads, 1) for b in batches]))
         prep_bytes = reads_per_launch * (4 + 4 + 8 + 4 + 4 * cig + 8)  # starts, CIGAR counts / offsets / words, read lengths in; end + shape out
@@ -534,7 +536,7 @@ def main():
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             with open(tp) as fh:
-                traffic = json.load(fh).get("r02_%s_pileup_warp_kernel_dram_bytes_per_launch" % w.name)
+                traffic = json.load(fh).get("r02_%s_%s_dram_bytes_per_launch" % (w.name, dominant))
         cpu = None
         if not args.no_cpu_baseline:
             n_cpu, times, cores, n_reads_cpu = run_cpu_arm(w, repeats=1)
@@ -556,9 +558,9 @@ def main():
                        "sharding": "ONE input; units cut into %d equal interval shards (sharding.unit_cuts), shard k -> rank k, each rank holds the "
                                    "reads its columns can reach; no collective on the data path" % world,
                        "numa_node_rank0": numa},
-            "roofline": {"bound": "hbm", "kernel": "pileup_warp_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_unit": b_unit, "units_per_launch": units_per_launch, "kernel_ms": phase["pileup"],
+                         "algorithmic_bytes_per_unit": b_unit, "units_per_launch": units_per_launch, "kernel_ms": dom_ms,
                          "phases_ms_per_launch": {k: round(v, 5) for k, v in phase.items()},
                          "prep_kernels": {"bytes_per_launch": prep_bytes, "achieved": prep_bytes / (phase["prep"] * 1e-3) / 1e9 if phase["prep"] > 0 else None,
                                           "unit": "GB/s", "frac": prep_bytes / (phase["prep"] * 1e-3) / 1e9 / peak if phase["prep"] > 0 else None}},

@@ -267,8 +267,19 @@ def test_decoder_rejects_damaged_files(tmp_path):
     damaged = bytearray(raw)
     damaged[len(raw) // 2] ^= 0xFF
     damaged[len(raw) // 2 + 1] ^= 0xFF
-    for o in attempt("flip.bam", bytes(damaged), bai):  # either zlib notices or the records stop parsing; never more reads
+    outcomes = attempt("flip.bam", bytes(damaged), bai)
+    assert isinstance(outcomes[0], str), outcomes  # whole file: inflate fails or the member's CRC32 does not match
+    for o in outcomes:  # region fetch: an error, or the damaged member lies outside the region
         assert isinstance(o, str) or o <= n_good
+    # stored (level 0) members: DEFLATE itself cannot notice a flipped quality byte, the BGZF CRC32 must (htslib fails such a block)
+    b = bamio.BamFile(str(good), use_index=False).read_batch()
+    stored = tmp_path / "stored.bam"
+    bamio.write_bam_batch(str(stored), b, level=0)
+    assert bamio.BamFile(str(stored), use_index=False).read_batch().n_reads == n_good
+    raw0 = bytearray(open(stored, "rb").read())
+    raw0[len(raw0) // 2] ^= 0x01
+    out = attempt("stored_flip.bam", bytes(raw0))
+    assert isinstance(out[0], str), out
     assert all(isinstance(o, str) for o in attempt("noindex.bam", raw, b"BAI\1" + b"\0" * 3)[1:])
 
 

@@ -57,10 +57,10 @@ def main():
     # ---- SASS counters x source lines
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "vafator_b200", "libvfk.so")], cwd=tmp, capture_output=True)
-    cubin = [f for f in os.listdir(tmp) if f.startswith("vfk_pileup") and f.endswith(".cubin")]
+    cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")]
     if not cubin:
         return
-    dis = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, cubin[0])], capture_output=True, text=True).stdout
+    dis = "\n".join(subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, c)], capture_output=True, text=True).stdout for c in cubin)
     funcs, fn, cur = {}, None, None
     for ln in dis.split("\n"):
         m = re.match(r"\s*\.text\.(\S+):", ln)

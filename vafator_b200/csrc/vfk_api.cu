@@ -20,8 +20,8 @@ struct PileupScratch {
     uint32_t *mate;
     cudaEvent_t *ev;
 };
-cudaError_t launch_prep(const ReadsDev &R, const int32_t *pos_src, int32_t *pos_copy, int32_t *end_out, uint32_t *ev_out, int64_t *chunk_max,
-                        int64_t *blk_max, int64_t *blk_incl, uint32_t *batch_status, cudaStream_t stream, int *launches);
+cudaError_t launch_prep(const ReadsDev &R, uint2 *ee_out, int64_t *chunk_max, int64_t *blk_max, int64_t *blk_incl, uint32_t *batch_status,
+                        cudaStream_t stream, int *launches);
 cudaError_t launch_pileup(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, int max_l_qseq, vfk_counts *out,
                           const PileupScratch &S, int sm_count, cudaStream_t stream, int *launches, bool link_all);
 cudaError_t launch_locate_only(const ReadsDev &R, const UnitsDev &V, void *resolved, cudaStream_t stream, int *launches);
@@ -97,7 +97,7 @@ struct PinBuf {  // page-locked host scratch
 // lists and the link scratch.  The bucket heads and the claim bitmap are kept clean by the link kernels themselves
 // (set once when (re)allocated).
 struct Work {
-    DevBuf end, ev, chunk_max, blk_max, blk_incl, resolved, lists, next, column, claimed, mate, heads;
+    DevBuf ee, chunk_max, blk_max, blk_incl, resolved, lists, next, column, claimed, mate, heads;
     uint32_t n_buckets = 0;
     void *counters = nullptr;  // 64 B, layout in vfk_pileup.cu (PileupScratch)
     cudaEvent_t tev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // phase boundaries when timing is on
@@ -106,7 +106,7 @@ struct Work {
         const size_t nr = (size_t)(n_reads > 0 ? n_reads : 1), nu = (size_t)(n_units > 0 ? n_units : 1);
         const size_t nb = (nr + vfk::PREP_BLOCK - 1) / vfk::PREP_BLOCK;
         int rc;
-        if ((rc = end.reserve(nr * 4)) || (rc = ev.reserve(nr * 4)) || (rc = chunk_max.reserve((nr / 32 + 1) * 8)) || (rc = blk_max.reserve(nb * 8)) || (rc = blk_incl.reserve((nb + 1) * 8)) ||
+        if ((rc = ee.reserve(nr * 8)) || (rc = chunk_max.reserve((nr / 32 + 1) * 8)) || (rc = blk_max.reserve(nb * 8)) || (rc = blk_incl.reserve((nb + 1) * 8)) ||
             (rc = resolved.reserve(nu * sizeof(vfk::ResolvedUnit))) || (rc = lists.reserve(nu * 2 * sizeof(uint32_t))) ||
             (rc = next.reserve(nr * 4)) || (rc = column.reserve(nr * 4)) || (rc = mate.reserve(nr * 4)))
             return rc;
@@ -133,7 +133,7 @@ struct Work {
         return s;
     }
     void release() {
-        DevBuf *bufs[] = {&end, &ev, &chunk_max, &blk_max, &blk_incl, &resolved, &lists, &next, &column, &claimed, &mate, &heads};
+        DevBuf *bufs[] = {&ee, &chunk_max, &blk_max, &blk_incl, &resolved, &lists, &next, &column, &claimed, &mate, &heads};
         for (DevBuf *b : bufs) b->release();
         n_buckets = 0;
         if (counters) cudaFree(counters);
@@ -294,8 +294,7 @@ static void to_dev(const vfk_read_batch *r, const vfk_variant_batch *v, const Wo
     R.n_reads = r->n_reads;
     R.n_cigar_words = r->n_cigar_words; R.n_seq_bytes = r->n_seq_bytes; R.n_qual_bytes = r->n_qual_bytes;
     R.n_contigs = r->n_contigs;
-    R.end = (const int32_t *)w.end.p;
-    R.ev = (const uint32_t *)w.ev.p;
+    R.ee = (const uint2 *)w.ee.p;
     R.chunk_max = (const int64_t *)w.chunk_max.p;
     R.blk_incl = (const int64_t *)w.blk_incl.p;
     R.mate = (const uint32_t *)w.mate.p;
@@ -303,8 +302,7 @@ static void to_dev(const vfk_read_batch *r, const vfk_variant_batch *v, const Wo
     V.tid = v->tid; V.pos = v->pos; V.meta = v->meta; V.length = v->length; V.seq_off = v->seq_off; V.ins_seq = v->ins_seq; V.stop = v->stop;
 }
 
-// read preparation on `st`: counters zeroed, spans / shapes / position index derived (R's canonical pointers are device
-// visible; `pos_src` is where prep_kernel reads the starts, `pos_copy` an optional device copy it writes)
+// read preparation on `st`: counters zeroed, spans / shapes / position index derived (R's canonical pointers are device visible)
 static int enqueue_prep(vfk_handle *h, Work &w, const vfk::ReadsDev &R, cudaStream_t st, int *launches) {
     if (h->timing) {
         for (cudaEvent_t &e : w.tev)
@@ -314,7 +312,7 @@ static int enqueue_prep(vfk_handle *h, Work &w, const vfk::ReadsDev &R, cudaStre
         CU(cudaEventRecord(w.tev[0], st));
     }
     CU(cudaMemsetAsync(w.counters, 0, 64, st));
-    cudaError_t e = vfk::launch_prep(R, R.pos, nullptr, (int32_t *)w.end.p, (uint32_t *)w.ev.p, (int64_t *)w.chunk_max.p, (int64_t *)w.blk_max.p, (int64_t *)w.blk_incl.p,
+    cudaError_t e = vfk::launch_prep(R, (uint2 *)w.ee.p, (int64_t *)w.chunk_max.p, (int64_t *)w.blk_max.p, (int64_t *)w.blk_incl.p,
                                      (uint32_t *)((char *)w.counters + 20), st, launches);
     if (e != cudaSuccess) return fail(VFK_ECUDA, "prep launch: %s", cudaGetErrorString(e));
     if (h->timing) CU(cudaEventRecord(w.tev[1], st));
@@ -419,8 +417,9 @@ extern "C" int vfk_prep_words(vfk_handle *h, const vfk_read_batch *reads, int32_
     rc = enqueue_prep(h, h->work, R, st, &launches);
     h->launches += launches;
     if (rc) return rc;
-    CU(cudaMemcpyAsync(end_out, h->work.end.p, (size_t)reads->n_reads * 4, cudaMemcpyDeviceToDevice, st));
-    CU(cudaMemcpyAsync(shape_out, h->work.ev.p, (size_t)reads->n_reads * 4, cudaMemcpyDeviceToDevice, st));
+    // the kernels keep {end, shape} as one 8-byte pair per read: two strided copies split it
+    CU(cudaMemcpy2DAsync(end_out, 4, h->work.ee.p, 8, 4, (size_t)reads->n_reads, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpy2DAsync(shape_out, 4, (const char *)h->work.ee.p + 4, 8, 4, (size_t)reads->n_reads, cudaMemcpyDeviceToDevice, st));
     CU(cudaMemcpyAsync(status_out, (char *)h->work.counters + 20, 4, cudaMemcpyDeviceToDevice, st));
     return VFK_OK;
 }
@@ -459,6 +458,33 @@ extern "C" int vfk_wait(vfk_handle *h, int ticket) {
     if (*s.h_status & VFK_ST_BADBATCH)
         return fail(VFK_EINVAL, "malformed read batch (not coordinate sorted, negative start, CIGAR outside its pool or read too long)");
     return VFK_OK;
+}
+
+// Reads starting inside (col - max_l_qseq, col], averaged over 64 evenly spaced units: the depth of the variant columns
+// as far as two binary searches per sampled unit can tell (HOST arrays).
+static double sampled_depth(const vfk_read_batch *r, const vfk_variant_batch *v) {
+    const int64_t nu = v->n_units;
+    const int32_t w = r->max_l_qseq > 0 ? r->max_l_qseq : 1;
+    double sum = 0.0;
+    int n = 0;
+    for (int s = 0; s < 64 && s < nu; ++s) {
+        const int64_t u = nu <= 64 ? s : (int64_t)((2 * s + 1) * (double)nu / 128.0);
+        const int32_t tid = v->tid[u], col = v->pos[u];
+        if (tid < 0 || tid >= r->n_contigs) continue;
+        const int32_t *b = r->pos + r->contig_off[tid], *e = r->pos + r->contig_off[tid + 1];
+        const int32_t *hi = b, *lo = b;
+        for (int64_t len = e - b; len > 0;) {  // first start beyond col
+            const int64_t half = len >> 1;
+            if (hi[half] <= col) { hi += half + 1; len -= half + 1; } else len = half;
+        }
+        for (int64_t len = e - b; len > 0;) {  // first start beyond col - w
+            const int64_t half = len >> 1;
+            if ((int64_t)lo[half] <= (int64_t)col - w) { lo += half + 1; len -= half + 1; } else len = half;
+        }
+        sum += (double)(hi - lo);
+        ++n;
+    }
+    return n ? sum / n : 0.0;
 }
 
 // copy `bytes` of a host array into the slot's staging buffer; *dst = the device copy
@@ -503,6 +529,14 @@ extern "C" int vfk_annotate_host_async(vfk_handle *h, const vfk_read_batch *read
                          pinned_alias(reads->isize), pinned_alias(reads->qname_id), pinned_alias(reads->qname_hash)};
     bool zero_copy = !h->stage_all && nr > 0;
     for (const void *p : z) zero_copy = zero_copy && p != nullptr;
+    if (zero_copy) {
+        // In place pays per (unit, candidate read) pair -- about 256 bytes cross the bus for each (a dozen arrays, 64-byte requests) --
+        // a bulk copy pays per read.  Sparse variant sets against 30x / 60x reads touch a fifth of the batch: in place.  A deep
+        // panel touches every read many times over: staged.  The depth is estimated from a sample of the units.
+        const double touches = (double)nu * sampled_depth(reads, units);
+        const double per_read = 43.0 + (double)(reads->n_seq_bytes + reads->n_qual_bytes) / (double)nr;
+        zero_copy = touches * 256.0 < (double)nr * per_read;
+    }
     rc = S.work.reserve(nr, nu, st);
     if (rc) goto failed;
     STAGE(S.contig, reads->contig_off, (size_t)(reads->n_contigs + 1) * sizeof(int64_t), dr.contig_off);

@@ -1,9 +1,9 @@
 // vfk_device.cuh -- device-side building blocks shared by the kernels (sm_100a).
 //
 // The kernels read the CANONICAL columnar read batch (include/vfk.h: the fields of the decoded BAM records,
-// array by array) plus three words per read that prep_kernel (vfk_prep.cu) derives from it on the device in
-// every call: the reference end, the CIGAR shape word and -- per block of reads -- the running maximum of the
-// ends, which is the position index.  Nothing is prepared on the host.
+// array by array) plus what prep_kernel (vfk_prep.cu) derives from it on the device in every call: the reference end
+// and the CIGAR shape word of every read (one 8-byte pair) and -- per chunk / block of reads -- the running maximum of
+// the ends, which is the position index.  Nothing is prepared on the host.
 //
 // What is evaluated per (variant column, read) pair follows pysam 0.21.0 / htslib 1.17 as
 // vafator drives them (vafator/pileups.py:71-80, :184-362):
@@ -58,8 +58,7 @@ struct ReadsDev {
     int64_t n_cigar_words, n_seq_bytes, n_qual_bytes;
     int32_t n_contigs;
     // derived per call by prep_kernel / scan_kernel (device memory)
-    const int32_t *__restrict__ end;       // pos + reference bases consumed
-    const uint32_t *__restrict__ ev;       // CIGAR shape word
+    const uint2 *__restrict__ ee;          // {end = pos + reference bases consumed, CIGAR shape word}
     const int64_t *__restrict__ chunk_max; // [n_reads / 32]: max over the 32 reads of a chunk of tid << 32 | end
     const int64_t *__restrict__ blk_incl;  // [n_blocks + 1]: entry b + 1 = max over the reads of blocks 0..b of the same key
     // overlap partners of the reads inside the windows of listed units (link kernels): partner | tie_break << 31
@@ -85,7 +84,7 @@ struct __align__(16) ResolvedUnit {
     uint32_t ins_off;  // offset of ALT0[1:] in ins_seq
     uint32_t lo, hi;   // candidate reads [lo, hi): hi = first read starting beyond col, lo = back[hi-1]
     int32_t stop;      // reads starting at or beyond it were never fetched by the reference
-    uint32_t c1;       // end of the contig's read range
+    int32_t tid;       // contig of the column (its read range ends at contig_off[tid + 1]); the candidate range is empty for an unknown contig
 };
 
 struct Unit {
@@ -95,7 +94,7 @@ struct Unit {
     uint32_t ref_code, alt_code;
     int32_t len;
     const uint8_t *ins;
-    int64_t c1;
+    int32_t tid;
     int64_t lo, hi;
 };
 
@@ -155,13 +154,16 @@ __device__ __forceinline__ int word_base(uint32_t w) { return (int)(w >> 8); }
 // ---- per-read records assembled from the arrays.  hot = {pos, span, flag | mapq << 16 | shape << 24, read index},
 // cold = {cigar_off, n_cigar, l_qseq, one-event word}: the shapes the evaluation code below is written against.
 __device__ __forceinline__ uint32_t shape_of_ev(uint32_t ev) { return ev == EV_SIMPLE ? SHAPE_SIMPLE : ev == EV_GENERAL ? SHAPE_GENERAL : SHAPE_ONE_EVENT; }
+__device__ __forceinline__ int32_t ld_end(const ReadsDev &R, int64_t i) { return (int32_t)__ldg(&R.ee[i].x); }
+__device__ __forceinline__ uint32_t ld_ev(const ReadsDev &R, int64_t i) { return __ldg(&R.ee[i].y); }
 __device__ __forceinline__ uint4 load_hot(const ReadsDev &R, int64_t i) {
     const int32_t p = __ldg(R.pos + i);
     const uint32_t fm = (uint32_t)__ldg(R.flag + i) | ((uint32_t)__ldg(R.mapq + i) << 16);
-    return make_uint4((uint32_t)p, (uint32_t)(__ldg(R.end + i) - p), fm | (shape_of_ev(__ldg(R.ev + i)) << 24), (uint32_t)i);
+    const uint2 e = __ldg(R.ee + i);
+    return make_uint4((uint32_t)p, (uint32_t)((int32_t)e.x - p), fm | (shape_of_ev(e.y) << 24), (uint32_t)i);
 }
 __device__ __forceinline__ uint4 load_cold(const ReadsDev &R, int64_t i) {
-    const uint32_t ev = __ldg(R.ev + i);
+    const uint32_t ev = ld_ev(R, i);
     return make_uint4((uint32_t)__ldg(R.cigar_off + i), (uint32_t)__ldg(R.n_cigar + i), (uint32_t)__ldg(R.l_qseq + i),
                       ev == EV_GENERAL ? 0u : ev);
 }
@@ -291,6 +293,9 @@ __device__ __forceinline__ int32_t refpos_of_query(const ReadsDev &R, int32_t rp
     return -1;
 }
 
+// end of the read range of contig `tid` (only for units with candidate reads: their contig is known)
+__device__ __forceinline__ int64_t contig_end(const ReadsDev &R, int32_t tid) { return __ldg(R.contig_off + tid + 1); }
+
 // first read at or after `from` (same contig, start < stop) that the reference would have pushed
 __device__ __forceinline__ int64_t next_pushed(const ReadsDev &R, const vfk_params &P, int64_t from, int64_t c1, int32_t stop) {
     for (int64_t j = from; j < c1; ++j) {
@@ -318,7 +323,7 @@ __device__ __forceinline__ int32_t push_column(const ReadsDev &R, const vfk_para
 __device__ __forceinline__ bool reaches_hash(const ReadsDev &R, const vfk_params &P, int64_t i, int32_t tid, int32_t column) {
     const uint32_t fm = fm_of(R, i);
     if (!read_passes(fm, P)) return false;
-    const int32_t end = __ldg(R.end + i);
+    const int32_t end = ld_end(R, i);
     if (end <= column) return false;  // never appended to the buffer
     if ((fm & F_MUNMAP) || !(fm & F_PROPER)) return false;
     const int32_t mt = __ldg(R.mtid + i);
@@ -352,7 +357,7 @@ __device__ __forceinline__ int tweaked_quality(const ReadsDev &R, const vfk_para
         m = (int64_t)(mw & 0x7FFFFFFFu);
         const uint4 mh = load_hot(R, m);
         if (m > i && (int32_t)mh.x > U.col)  // the mate starts beyond the column: it can only matter to a base further on
-            paired = !q_is_column_base && next_pushed(R, P, U.hi, U.c1, U.stop) == m;
+            paired = !q_is_column_base && next_pushed(R, P, U.hi, contig_end(R, U.tid), U.stop) == m;
         int32_t rp = -1;
         if (paired) rp = q_is_column_base ? U.col : (general ? refpos_of_query(R, (int32_t)hot.x, cold_if_general, q)
                                                              : (int32_t)hot.x + q);
@@ -513,12 +518,103 @@ __device__ __forceinline__ Eval evaluate_packed(const ReadsDev &R, const vfk_par
     return o;
 }
 
+// the rare, long pieces of the register kernel's per-read code, out of line: its hot loop should fit the instruction cache
+static __device__ __noinline__ uint32_t indel_hits(const ReadsDev &R, int64_t i, uint32_t kind, int32_t col, int32_t len, const uint8_t *ins) {
+    Unit U;
+    U.col = col; U.len = len; U.ins = ins; U.kind = kind; U.stop = 0; U.ref_code = U.alt_code = 0u; U.tid = 0; U.lo = U.hi = 0;
+    const uint4 hot = load_hot(R, i), cold = load_cold(R, i);
+    return kind == VFK_KIND_INS ? insertion_hits(R, hot, cold, U) : deletion_hits(R, hot, cold, U);
+}
+static __device__ __noinline__ Resolved resolve_general_call(const ReadsDev &R, int64_t i, int32_t rpos, int32_t col) {
+    return resolve_general(R, rpos, load_cold(R, i), col);
+}
+
+// ---- the same evaluation in three steps, for the register kernel: all candidate reads of a column sit in the lanes of one
+// warp, so a read's overlap partner is another lane and its base / quality at the column arrive by a shuffle instead of a
+// second gather (resolve_column -> payload loads in flight -> exchange -> finish_column).
+struct ColRead {
+    uint32_t fl;   // FL_COVERS | FL_IN_COL
+    bool aligned;  // in the column at an aligned base inside the read: its base / quality at the column exist
+    bool hard;     // in the column inside a deletion / skip, with a next base: the base-quality filter looks at that base (general protocol)
+    bool is_del, is_refskip;
+    bool pay;      // a base / quality lookup is due (aligned or hard)
+    int qpos, indel;
+};
+// `passes`: the read is valid and passes the read filter (read_passes)
+__device__ __forceinline__ ColRead resolve_column(const ReadsDev &R, int32_t col, int64_t i, const uint4 &hot, bool valid, bool passes) {
+    ColRead c;
+    c.fl = 0u; c.aligned = false; c.hard = false; c.is_del = false; c.is_refskip = false; c.pay = false; c.qpos = 0; c.indel = 0;
+    const int32_t rpos = (int32_t)hot.x;
+    if (!valid || (uint32_t)(col - rpos) >= hot.y) return c;  // col < pos wraps to a huge unsigned
+    c.fl = FL_COVERS;
+    if (!passes) return c;
+    const uint32_t shape = hot.z >> 24;
+    int l_qseq = (int)hot.y;
+    if (shape == SHAPE_SIMPLE) {
+        c.qpos = col - rpos;
+    } else {
+        const Resolved r = shape == SHAPE_ONE_EVENT ? resolve_one_event(rpos, load_cold(R, i), col) : resolve_general_call(R, i, rpos, col);
+        if (!r.covered) return c;
+        c.is_del = r.is_del; c.is_refskip = r.is_refskip; c.qpos = r.qpos; c.indel = r.indel;
+        l_qseq = r.l_qseq;
+    }
+    c.fl |= FL_IN_COL;
+    c.pay = c.qpos < l_qseq;
+    c.aligned = !c.is_del && c.pay;
+    c.hard = c.is_del && c.pay;
+    return c;
+}
+// htslib tweak_overlap_quality for a read and its partner that both show an aligned base at the column.
+// partner: quality | base << 8 | 1 << 31 when the partner has such a base, else 0; sel = the name-hash tie-break bit.
+__device__ __forceinline__ int overlap_quality(uint32_t my_word, uint32_t partner, bool i_first, uint32_t sel) {
+    const int qi = word_qual(my_word);
+    if (!(partner >> 31)) return qi;
+    const int qm = (int)(partner & 0xFFu);
+    const uint32_t mymul = i_first ? sel : (1u - sel);
+    if (((my_word ^ partner) & 0xF00u) == 0u) {
+        int s = qi + qm;
+        if (s > 200) s = 200;
+        return mymul ? s : 0;
+    }
+    if (qi > qm) return (qi * 4) / 5;
+    if (qi < qm) return 0;
+    return mymul ? (qi * 4) / 5 : 0;
+}
+// quality `q` (after the overlap adjustment) and payload word known: filter + allele classification
+__device__ __forceinline__ Eval finish_column(const ReadsDev &R, const vfk_params &P, const Unit &U, int64_t i, const uint4 &hot, const ColRead &c,
+                                              int q, uint32_t my_word) {
+    Eval o;
+    o.pk = 0u; o.fl = c.fl; o.alt = 0u; o.hard = 0u;
+    if (!(c.fl & FL_IN_COL)) return o;
+    if (q < P.min_baseq) return o;  // pysam pileup_base_qual_skip
+    const uint32_t mq_pos = ((hot.z >> 16) & 0xFFu) | ((uint32_t)c.qpos << 16);
+    if (U.kind == VFK_KIND_SNV) {
+        if (c.is_refskip) return o;
+        o.fl |= FL_IN_DP;
+        if (c.is_del) return o;  // counted in DP as the "" allele, belongs to no reported list
+        const uint32_t code = (uint32_t)word_base(my_word);
+        if (code_is_ambiguous((int)code)) o.fl |= FL_AMBIGUOUS;
+        const uint32_t lists = (code == U.ref_code ? PK_REF : 0u) | (code == U.alt_code ? PK_ALT : 0u);
+        if (lists) o.pk = mq_pos | ((uint32_t)q << 8) | lists;
+        o.alt = code == U.alt_code ? 1u : 0u;
+    } else {
+        o.fl |= FL_IN_DP;
+        if (c.indel == 0) {
+            o.pk = mq_pos | PK_REF;  // "considers all reads without indels to be the reference" (pileups.py:291-294)
+        } else if ((hot.z >> 24) != SHAPE_SIMPLE) {
+            if ((U.kind == VFK_KIND_INS && c.indel > 0) || (U.kind == VFK_KIND_DEL && c.indel < 0)) o.alt = indel_hits(R, i, U.kind, U.col, U.len, U.ins);
+            if (o.alt) o.pk = mq_pos | PK_ALT;
+        }
+    }
+    return o;
+}
+
 __device__ __forceinline__ Contribution evaluate(const ReadsDev &R, const vfk_params &P, const Unit &U, int64_t i, const uint4 &hot,
                                                  uint32_t mw) {
     return decode(evaluate_packed(R, P, U, i, hot, mw));
 }
 __device__ __forceinline__ Contribution evaluate(const ReadsDev &R, const vfk_params &P, const Unit &U, int64_t i) {
-    return evaluate(R, P, U, i, load_hot(R, i), __ldg(R.mate + i));
+    return evaluate(R, P, U, i, load_hot(R, i), __ldcg(R.mate + i));  // written by the link passes, possibly earlier in the same launch: not the read-only path
 }
 
 // ---- bulk asynchronous copies (TMA, cp.async.bulk) completed on an mbarrier ----
@@ -559,7 +655,7 @@ __device__ __forceinline__ void unit_from(const ResolvedUnit &r, const uint8_t *
     U.alt_code = (r.meta >> 16) & 0xFFu;
     U.len = r.len;
     U.ins = ins_seq + r.ins_off;
-    U.c1 = (int64_t)r.c1;
+    U.tid = r.tid;
     U.lo = (int64_t)r.lo;
     U.hi = (int64_t)r.hi;
 }

@@ -20,7 +20,10 @@
 // pileup_block_kernel : one CTA per listed unit, u32 counters, for columns with > 32767 candidates.
 #include <algorithm>
 #include <cstdlib>
-#include "vfk_device.cuh"
+#include <cooperative_groups.h>
+#include "vfk_link.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace vfk {
 
@@ -106,7 +109,7 @@ __device__ __forceinline__ ResolvedUnit locate_unit(const ReadsDev &R, const Uni
         while (ch < ch_last && __ldg(R.chunk_max + ch) <= key) ++ch;
         int64_t i = max(c0, ch << 5);
         const int64_t to = min(a, (ch + 1) << 5);
-        while (i < to && __ldg(R.end + i) <= col) ++i;
+        while (i < to && ld_end(R, i) <= col) ++i;
         lo = i < to ? i : a;
     }
     ResolvedUnit r;
@@ -117,7 +120,7 @@ __device__ __forceinline__ ResolvedUnit locate_unit(const ReadsDev &R, const Uni
     r.hi = (uint32_t)a;
     r.lo = (uint32_t)lo;
     r.stop = V.stop ? __ldg(V.stop + u) : 0x7FFFFFFF;
-    r.c1 = (uint32_t)c1;
+    r.tid = tid;
     return r;
 }
 __device__ __forceinline__ void store_resolved(ResolvedUnit *dst, const ResolvedUnit &r) {
@@ -383,16 +386,14 @@ constexpr uint32_t ST_STORES = 1u;
 // MATCH.ANY inside a chunk and by a short loop across the chunks.  Returns false when the column needs the general
 // protocol (three records of one name, a zero-span record): the unit then goes to the list path, whose link kernels
 // replay the hash in full.
+// passA / passB: the slot holds a read that passes the read filter.
 __device__ __forceinline__ bool pair_in_registers(const ReadsDev &R, const vfk_params &P, int32_t tid, int lane, uint32_t lt_mask,
-                                                  bool validA, bool validB, int64_t iA, int64_t iB, Cand &A, Cand &B) {
+                                                  bool passA, bool passB, int64_t iA, int64_t iB, Cand &A, Cand &B) {
     A.mw = VFK_NO_MATE;
     B.mw = VFK_NO_MATE;
     A.st = B.st = 0u;
     if (!P.ignore_overlaps) return true;
-    auto pre = [&](bool valid, const uint4 &h) {
-        return valid && read_passes(h.z, P) && (h.z & F_PROPER) && !(h.z & F_MUNMAP);
-    };
-    const bool preA = pre(validA, A.hot), preB = pre(validB, B.hot);
+    const bool preA = passA && (A.hot.z & (F_PROPER | F_MUNMAP)) == F_PROPER, preB = passB && (B.hot.z & (F_PROPER | F_MUNMAP)) == F_PROPER;
     unsigned long long idA = 0ull, idB = 0ull;
     int32_t mposA = 0, mposB = 0;
     bool eligA = false, eligB = false, zero = false;
@@ -467,16 +468,70 @@ __device__ __forceinline__ bool pair_in_registers(const ReadsDev &R, const vfk_p
     return true;
 }
 
+// A unit whose contributions do not fit the one-value-per-lane ranking (more than 32 contributing reads -- every 60x column --,
+// an insertion one read supports more than once, REF == ALT): the per-read results are already in registers, only the
+// reduction changes -- per-warp shared-memory histograms, no second evaluation, no second kernel.
+template <int POSB>
+__device__ __noinline__ void reduce_by_histogram(Eval e0, Eval e1, uint32_t kind, int include_ambiguous, uint32_t *ref_slot, uint32_t *alt_slot, int lane,
+                                              vfk_counts *out, uint32_t n_cand) {
+    using L = Layout<POSB>;
+    constexpr int WORDS = L::BINS / 2;
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(ref_slot);
+        for (int w = lane; w < (2 * WORDS) / 4; w += 32) z[w] = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+    uint32_t status = kind;
+    const bool with_bq = kind == VFK_KIND_SNV;
+    const Contribution c0 = decode(e0), c1 = decode(e1);
+    accumulate<uint16_t, POSB>(ref_slot, alt_slot, c0, with_bq, status);
+    accumulate<uint16_t, POSB>(ref_slot, alt_slot, c1, with_bq, status);
+    __syncwarp();
+    const uint32_t tally = __reduce_add_sync(FULL, e0.fl + e1.fl);  // four counters (each <= 64) in the byte lanes of one word
+    const int n_cover = (int)(tally & 0xFFu), n_col = (int)((tally >> 8) & 0xFFu), n_amb = (int)(tally >> 24);
+    int dp = (int)((tally >> 16) & 0xFFu);
+    const int ac_ref = __reduce_add_sync(FULL, (c0.ref ? 1 : 0) + (c1.ref ? 1 : 0));
+    const int ac_alt = __reduce_add_sync(FULL, (int)(c0.alt + c1.alt));
+    status = __reduce_or_sync(FULL, status);
+    int med2[3][2] = {{-1, -1}, {-1, -1}, {-1, -1}};
+    uint64_t s2[3] = {0, 0, 0};
+    if (ac_ref | ac_alt) {
+        reduce_metric<uint16_t, 256>(ref_slot, alt_slot, L::MQ_OFF, lane, med2[0][0], med2[0][1], s2[0]);
+        if (with_bq) reduce_metric<uint16_t, 256>(ref_slot, alt_slot, L::BQ_OFF, lane, med2[1][0], med2[1][1], s2[1]);
+        reduce_metric<uint16_t, POSB>(ref_slot, alt_slot, L::POS_OFF, lane, med2[2][0], med2[2][1], s2[2]);
+    }
+    if (kind == VFK_KIND_SNV && !include_ambiguous) dp -= n_amb;  // pileups.py:224-227
+    if (lane == 0) store_counts(out, dp, n_amb, ac_ref, ac_alt, med2, s2, status, n_cand, (uint32_t)n_cover, (uint32_t)n_col);
+    __syncwarp();
+}
+
+// The base-quality filter of a read that sits in a deletion / reference skip at the column looks at its NEXT base; whether that
+// base has been overlap-adjusted depends on the push timing of the mate.  Rare (a few units in a hundred have such
+// a read): kept out of line so that it costs the common path no registers.
+static __device__ __noinline__ int hard_quality(const ReadsDev &R, const vfk_params &P, int32_t col, int32_t stop, int32_t tid, int64_t hi, int64_t i,
+                                         uint32_t mw, int qpos, uint32_t own_q, uint32_t own_s) {
+    Unit U;
+    U.col = col; U.stop = stop; U.tid = tid; U.hi = hi; U.lo = 0; U.kind = 0u; U.ref_code = U.alt_code = 0u; U.len = 0; U.ins = nullptr;
+    PayLoad own;
+    own.q = own_q; own.s = own_s; own.odd = (uint32_t)qpos & 1u;
+    const uint4 hot = load_hot(R, i), cold = load_cold(R, i);
+    uint32_t my_word;
+    return tweaked_quality(R, P, U, i, hot, mw, cold, true, qpos, (int)cold.z, false, own, my_word);
+}
+
 // INWARP = true: overlap partners are found in registers (pair_in_registers); false (debug hook, VFK_DEBUG_LINK_ALL=1 at
 // vfk_create): the link kernels have run over every unit and the partners come from R.mate, as on the list path.
 template <int POSB, bool INWARP>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, VFK_MIN_CTAS)
-pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_units, const uint8_t *__restrict__ ins_seq,
-                   vfk_params P, vfk_counts *__restrict__ out, unsigned long long *__restrict__ work_counter,
+pileup_warp_kernel(const __grid_constant__ ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_units, const uint8_t *__restrict__ ins_seq,
+                   const __grid_constant__ vfk_params P, vfk_counts *__restrict__ out, unsigned long long *__restrict__ work_counter,
                    uint32_t *__restrict__ block_list, uint32_t *__restrict__ n_block, uint32_t *__restrict__ warp_list,
                    uint32_t *__restrict__ n_warp, const uint32_t *__restrict__ batch_status) {
     using L = Layout<POSB>;
+    constexpr bool HIST_HERE = POSB <= 512;  // per-warp histograms fit the static shared memory
+    constexpr int HIST_WORDS = HIST_HERE ? L::BINS : 1;  // two slots of BINS / 2 words
     __shared__ uint32_t stage_all[WARPS_PER_CTA][32];
+    __shared__ __align__(16) uint32_t hist_all[WARPS_PER_CTA][HIST_WORDS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t *stage = stage_all[warp];
@@ -513,7 +568,7 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
             ru.col = (int32_t)__shfl_sync(FULL, ra.x, j); ru.meta = __shfl_sync(FULL, ra.y, j);
             ru.len = (int32_t)__shfl_sync(FULL, ra.z, j); ru.ins_off = __shfl_sync(FULL, ra.w, j);
             ru.lo = __shfl_sync(FULL, rb.x, j); ru.hi = __shfl_sync(FULL, rb.y, j);
-            ru.stop = (int32_t)__shfl_sync(FULL, rb.z, j); ru.c1 = __shfl_sync(FULL, rb.w, j);
+            ru.stop = (int32_t)__shfl_sync(FULL, rb.z, j); ru.tid = (int32_t)__shfl_sync(FULL, rb.w, j);
             Unit U;
             unit_from(ru, ins_seq, U);
             Cand A;
@@ -539,96 +594,102 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
                 }
                 continue;
             }
-            // ---- shallow ----
+            // ---- shallow: lane k holds candidate k (slot A) and, when more than 32 reads are candidates, candidate 32 + k (slot B)
+            const bool two = n_cand > 32;
             const bool validA = lane < n_cand, validB = lane + 32 < n_cand;
-            int64_t i_a = U.lo + lane;
-            const int64_t i_b = U.lo + 32 + lane;
+            const int64_t i_a = U.lo + lane, i_b = U.lo + 32 + lane;
             Cand B;
             B.hot = make_uint4(0, 0, 0, 0);
             B.mw = VFK_NO_MATE;
             B.st = 0u;
             if (validB) B.hot = load_hot(R, i_b);
-            bool hard = false;
-            int32_t tid = 0;
+            // column resolution and the reads' own base / quality lookups, all in flight before the pairing consumes anything
+            const bool passA = validA && read_passes(A.hot.z, P), passB = validB && read_passes(B.hot.z, P);
+            const ColRead cA = resolve_column(R, U.col, i_a, A.hot, validA, passA);
+            PayLoad ownA, ownB;
+            ownA.q = ownA.s = ownA.odd = 0u;
+            ownB = ownA;
+            if (cA.pay) ownA = pay_issue(R, A.hot.w, (uint32_t)cA.qpos);
+            ColRead cB = resolve_column(R, U.col, i_b, B.hot, false, false);
+            if (two) {
+                cB = resolve_column(R, U.col, i_b, B.hot, validB, passB);
+                if (cB.pay) ownB = pay_issue(R, B.hot.w, (uint32_t)cB.qpos);
+            }
+            bool general_protocol = false;
             if constexpr (INWARP) {
-                if (lane == 0) {  // contig of the column: the one whose read range ends at c1
-                    int32_t a = 0, b = R.n_contigs;
-                    while (b - a > 1) {
-                        const int32_t m = (a + b) >> 1;
-                        if (__ldg(R.contig_off + m) < (int64_t)U.c1) a = m; else b = m;
-                    }
-                    tid = a;
-                }
-                tid = __shfl_sync(FULL, tid, 0);
-                hard = !pair_in_registers(R, P, tid, lane, lt_mask, validA, validB, i_a, i_b, A, B);
+                general_protocol = !pair_in_registers(R, P, U.tid, lane, lt_mask, passA, passB, i_a, i_b, A, B);
             } else {
                 if (validA) A.mw = __ldg(R.mate + i_a);
                 if (validB) B.mw = __ldg(R.mate + i_b);
             }
-            // the reads that span the column are packed into the lanes (first chunk in place, second chunk into the
-            // lanes the first one leaves free) and evaluated in one pass; a second pass only runs for the overflow
-            // when more than 32 reads span the column
-            bool act = validA && (uint32_t)(U.col - (int32_t)A.hot.x) < A.hot.y;
-            Eval e0, e1;
-            e0.pk = e0.fl = e0.alt = e0.hard = 0u;
-            e1 = e0;
-            if (n_cand > 32 && !hard) {
-                const bool cov1 = validB && (uint32_t)(U.col - (int32_t)B.hot.x) < B.hot.y;
-                const uint32_t c0m = __ballot_sync(FULL, act), c1m = __ballot_sync(FULL, cov1);
-                const int n_free = 32 - __popc(c0m), idx1 = __popc(c1m & lt_mask);
-                const int n_move = min(n_free, __popc(c1m));
-                if (cov1 && idx1 < n_move) stage[idx1] = (uint32_t)lane;
-                __syncwarp();
-                const int slot = __popc(~c0m & lt_mask);  // this lane's rank among the free lanes
-                const bool adopt = !act && slot < n_move;
-                const int src = adopt ? (int)stage[slot] : lane;
-                __syncwarp();
-                const uint32_t hx = __shfl_sync(FULL, B.hot.x, src), hy = __shfl_sync(FULL, B.hot.y, src);
-                const uint32_t hz = __shfl_sync(FULL, B.hot.z, src), hw = __shfl_sync(FULL, B.hot.w, src);
-                const uint32_t hm = __shfl_sync(FULL, B.mw, src), hs = __shfl_sync(FULL, B.st, src);
-                if (adopt) {
-                    A.hot = make_uint4(hx, hy, hz, hw);
-                    A.mw = hm;
-                    A.st = hs;
-                    i_a = U.lo + 32 + src;
-                    act = true;
+            if (general_protocol) {  // three records of one name, a zero-span record: the link kernels replay the hash in full
+                if (lane == 0) {
+                    warp_list[atomicAdd(n_warp, 1u)] = (uint32_t)u;
+                    store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind | VFK_ST_DEFERRED, (uint32_t)n_cand, 0u);
                 }
-                const bool over = cov1 && idx1 >= n_move;
-                if (__any_sync(FULL, over)) {
-                    if (over) e1 = evaluate_packed(R, P, U, i_b, B.hot, B.mw);
-                }
+                continue;
             }
-            if (act && !hard) e0 = evaluate_packed(R, P, U, i_a, A.hot, A.mw);
             if constexpr (INWARP) {
                 // A read inside a deletion / skip at the column is filtered on its NEXT base, and the overlap adjustment of that
                 // base exists once the mate has been pushed -- which also holds for the first record pushed after the column
                 // (bam_plp_auto reads one ahead).  That record lies outside the candidate range: when such a read stored itself
-                // and found no partner among the candidates, the record after the column is tried, and the read re-evaluated.
-                const bool t0 = e0.hard && A.mw == VFK_NO_MATE && (A.st & ST_STORES), t1 = e1.hard && B.mw == VFK_NO_MATE && (B.st & ST_STORES);
+                // and found no partner among the candidates, the record after the column is tried.
+                const bool t0 = cA.hard && A.mw == VFK_NO_MATE && (A.st & ST_STORES), t1 = cB.hard && B.mw == VFK_NO_MATE && (B.st & ST_STORES);
                 if (__any_sync(FULL, t0 || t1)) {
                     long long nx = -1;
-                    if (lane == 0) nx = next_pushed(R, P, U.hi, U.c1, U.stop);
+                    if (lane == 0) nx = next_pushed(R, P, U.hi, contig_end(R, U.tid), U.stop);
                     nx = __shfl_sync(FULL, nx, 0);
-                    if (nx >= 0 && __ldg(R.end + nx) > __ldg(R.pos + nx) && reaches_hash(R, P, nx, tid, INT32_MIN)) {
+                    if (nx >= 0 && ld_end(R, nx) > __ldg(R.pos + nx) && reaches_hash(R, P, nx, U.tid, INT32_MIN)) {
                         const unsigned long long idn = __ldg(R.qname_id + nx);
                         const uint32_t hn = __ldg(R.qname_hash + nx);
-                        if (t0 && __ldg(R.qname_id + i_a) == idn && __ldg(R.qname_hash + i_a) == hn) {
-                            A.mw = (uint32_t)nx | ((wang_hash(hn) & 1u) << 31);
-                            e0 = evaluate_packed(R, P, U, i_a, A.hot, A.mw);
-                        }
-                        if (t1 && __ldg(R.qname_id + i_b) == idn && __ldg(R.qname_hash + i_b) == hn) {
-                            B.mw = (uint32_t)nx | ((wang_hash(hn) & 1u) << 31);
-                            e1 = evaluate_packed(R, P, U, i_b, B.hot, B.mw);
-                        }
+                        if (t0 && __ldg(R.qname_id + i_a) == idn && __ldg(R.qname_hash + i_a) == hn) A.mw = (uint32_t)nx | ((wang_hash(hn) & 1u) << 31);
+                        if (t1 && __ldg(R.qname_id + i_b) == idn && __ldg(R.qname_hash + i_b) == hn) B.mw = (uint32_t)nx | ((wang_hash(hn) & 1u) << 31);
                     }
                 }
             }
+            // the reads' payload words; a read's overlap partner is another candidate of the column: its word comes by a shuffle
+            const uint32_t wA = pay_word(ownA), wB = pay_word(ownB);
+            const uint32_t xA = cA.aligned ? (wA | 0x80000000u) : 0u, xB = cB.aligned ? (wB | 0x80000000u) : 0u;
+            const int64_t kA = (int64_t)(A.mw & 0x7FFFFFFFu) - U.lo, kB = (int64_t)(B.mw & 0x7FFFFFFFu) - U.lo;  // partner as a candidate index
+            uint32_t pA = __shfl_sync(FULL, xA, (int)(kA & 31)), pB = 0u;
+            if (two) {
+                const uint32_t pAb = __shfl_sync(FULL, xB, (int)(kA & 31));
+                const uint32_t pBa = __shfl_sync(FULL, xA, (int)(kB & 31)), pBb = __shfl_sync(FULL, xB, (int)(kB & 31));
+                if (kA >= 32) pA = pAb;
+                pB = kB >= 32 ? pBb : pBa;
+                if (B.mw == VFK_NO_MATE || kB < 0 || kB >= n_cand) pB = 0u;
+            }
+            if (A.mw == VFK_NO_MATE || kA < 0 || kA >= n_cand) pA = 0u;
+            int qA = 0, qB = 0;
+            uint32_t mwA = 0u, mwB = 0u;  // the payload word the classification sees
+            if (cA.aligned) { mwA = wA; qA = overlap_quality(wA, pA, i_a < (int64_t)(A.mw & 0x7FFFFFFFu), A.mw >> 31); }
+            if (cB.aligned) { mwB = wB; qB = overlap_quality(wB, pB, i_b < (int64_t)(B.mw & 0x7FFFFFFFu), B.mw >> 31); }
+            if (__any_sync(FULL, cA.hard || cB.hard)) {
+                if (cA.hard) { mwA = wA; qA = hard_quality(R, P, U.col, U.stop, U.tid, U.hi, i_a, A.mw, cA.qpos, ownA.q, ownA.s); }
+                if (cB.hard) { mwB = wB; qB = hard_quality(R, P, U.col, U.stop, U.tid, U.hi, i_b, B.mw, cB.qpos, ownB.q, ownB.s); }
+            }
+            const Eval e0 = finish_column(R, P, U, i_a, A.hot, cA, qA, mwA);
+            Eval e1;
+            e1.pk = e1.fl = e1.alt = e1.hard = 0u;
+            if (two) e1 = finish_column(R, P, U, i_b, B.hot, cB, qB, mwB);
             const bool k0 = e0.pk != 0u, k1 = e1.pk != 0u;
             const uint32_t m0 = __ballot_sync(FULL, k0), m1 = __ballot_sync(FULL, k1);
-            // a read can support an insertion more than once (pileups.py:267-290): such units take the deep path
-            const bool heavy = hard || (U.kind == VFK_KIND_INS && __any_sync(FULL, e0.alt > 1u || e1.alt > 1u));
+            const uint32_t both_lists = (e0.pk & (e0.pk << 1) & PK_ALT) | (e1.pk & (e1.pk << 1) & PK_ALT);  // REF == ALT: a read in both lists
+            // more contributions than lanes, an insertion a read supports more than once (pileups.py:267-290), REF == ALT
+            const bool by_histogram = __popc(m0) + __popc(m1) > 32 || __any_sync(FULL, e0.alt > 1u || e1.alt > 1u || both_lists != 0u);
+            if (by_histogram) {
+                if constexpr (HIST_HERE) {
+                    reduce_by_histogram<POSB>(e0, e1, U.kind, P.include_ambiguous, hist_all[warp], hist_all[warp] + L::BINS / 2, lane, out + u, (uint32_t)n_cand);
+                } else {
+                    if (lane == 0) {
+                        warp_list[atomicAdd(n_warp, 1u)] = (uint32_t)u;
+                        store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind | VFK_ST_DEFERRED, (uint32_t)n_cand, 0u);
+                    }
+                }
+                continue;
+            }
             uint32_t pk = e0.pk;
-            if (m1) {  // move the overflow pass's contributions into lanes the first pass left free
+            if (m1) {  // move slot B's contributions into lanes slot A left free
                 const int n1 = __popc(m1);
                 if (k1) stage[__popc(m1 & lt_mask)] = e1.pk;
                 __syncwarp();
@@ -643,15 +704,6 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
             sh.is_alt = pk & PK_ALT;
             sh.R = __ballot_sync(FULL, sh.is_ref);
             sh.A = __ballot_sync(FULL, sh.is_alt);
-            // rare: more contributions than lanes, a multiply supported insertion, REF == ALT (a read in both lists), or a
-            // column whose pairing / base-quality filter needs the general protocol -- re-done through the histograms
-            if (heavy || __popc(m0) + __popc(m1) > 32 || (sh.R & sh.A)) {
-                if (lane == 0) {
-                    warp_list[atomicAdd(n_warp, 1u)] = (uint32_t)u;
-                    store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind | VFK_ST_DEFERRED, (uint32_t)n_cand, 0u);
-                }
-                continue;
-            }
             // four counters (each <= 64) in the byte lanes of one word, one reduction
             const uint32_t tally = __reduce_add_sync(FULL, e0.fl + e1.fl);
             const int n_cover = (int)(tally & 0xFFu), n_col = (int)((tally >> 8) & 0xFFu), n_amb = (int)(tally >> 24);
@@ -691,22 +743,20 @@ pileup_warp_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_u
 }
 
 // ------------------------------------------------------------------------------------------
-// warp per listed unit, shared-memory histograms
+// the list path, ONE cooperative launch: mate linking of the listed units' windows (three passes, grid barriers in between),
+// then a warp per listed unit with shared-memory histograms, then a CTA per unit for columns deeper than the u16 bins allow.
+// With empty lists (nearly every 30x / 60x call) every CTA leaves at the first line.
 // ------------------------------------------------------------------------------------------
 template <int POSB>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-pileup_deep_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, const uint8_t *__restrict__ ins_seq, vfk_params P,
-                   vfk_counts *__restrict__ out, const uint32_t *__restrict__ warp_list, const uint32_t *__restrict__ n_warp,
-                   uint32_t *__restrict__ deep_work, const uint32_t *__restrict__ batch_status) {
+__device__ __forceinline__ void deep_units(const ReadsDev &R, const ResolvedUnit *__restrict__ res, const uint8_t *__restrict__ ins_seq, const vfk_params &P,
+                                           vfk_counts *__restrict__ out, const uint32_t *__restrict__ warp_list, uint32_t n, uint32_t *__restrict__ deep_work,
+                                           uint32_t bad, uint32_t *smem) {
     using L = Layout<POSB>;
     constexpr int WORDS = L::BINS / 2;  // u16 bins
-    extern __shared__ __align__(16) uint32_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *ref_slot = smem + (size_t)warp * 2 * WORDS;
     uint32_t *alt_slot = ref_slot + WORDS;
-    const uint32_t n = *n_warp;
-    const uint32_t bad = *batch_status;
-    // listed unit k goes to warp k first (no atomics when the list is short or empty), the rest through a counter
+    // listed unit k goes to warp k first (no atomics when the list is short), the rest through a counter
     const uint32_t n_warps = gridDim.x * WARPS_PER_CTA;
     uint32_t k = blockIdx.x * WARPS_PER_CTA + warp;
     for (;;) {
@@ -722,28 +772,23 @@ pileup_deep_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, const uint8
     }
 }
 
-// ------------------------------------------------------------------------------------------
 // CTA per unit, u32 counters: columns deeper than the warp path's u16 bins allow
-// ------------------------------------------------------------------------------------------
 template <int POSB>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-pileup_block_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, const uint8_t *__restrict__ ins_seq, vfk_params P,
-                    vfk_counts *__restrict__ out, const uint32_t *__restrict__ deferred,
-                    const uint32_t *__restrict__ n_deferred) {
+__device__ __forceinline__ void block_units(const ReadsDev &R, const ResolvedUnit *__restrict__ res, const uint8_t *__restrict__ ins_seq, const vfk_params &P,
+                                            vfk_counts *__restrict__ out, const uint32_t *__restrict__ deferred, uint32_t nd, uint32_t *smem) {
     using L = Layout<POSB>;
     constexpr int WORDS = L::BINS;  // u32 bins
-    extern __shared__ __align__(16) uint32_t smem[];
     __shared__ int red[6];
     __shared__ uint32_t red_status;
     __shared__ int s_med2[3][2];
     __shared__ unsigned long long s_s2[3];
     uint32_t *ref_slot = smem, *alt_slot = smem + WORDS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t nd = *n_deferred;
     for (uint32_t d = blockIdx.x; d < nd; d += gridDim.x) {
         const int64_t u = deferred[d];
         Unit U;
         unit_from(res[u], ins_seq, U);
+        __syncthreads();
         for (int w = threadIdx.x; w < 2 * WORDS; w += blockDim.x) smem[w] = 0u;
         if (threadIdx.x < 6) red[threadIdx.x] = 0;
         if (threadIdx.x == 0) red_status = U.kind;
@@ -795,8 +840,32 @@ pileup_block_kernel(ReadsDev R, const ResolvedUnit *__restrict__ res, const uint
             store_counts(out + u, d_p, red[1], red[2], red[3], med2, s2, red_status & ~VFK_ST_DEFERRED, (uint32_t)(U.hi - U.lo),
                          (uint32_t)red[4], (uint32_t)red[5]);
         }
-        __syncthreads();
     }
+}
+
+// LINK: false when the link kernels have already run over every unit (debug hook)
+template <int POSB, bool LINK>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+tail_kernel(const __grid_constant__ ReadsDev R, const ResolvedUnit *__restrict__ res, const uint8_t *__restrict__ ins_seq,
+            const __grid_constant__ vfk_params P, vfk_counts *__restrict__ out, const uint32_t *__restrict__ block_list,
+            const uint32_t *__restrict__ n_block, const uint32_t *__restrict__ warp_list, const uint32_t *__restrict__ n_warp,
+            uint32_t *__restrict__ deep_work, const uint32_t *__restrict__ batch_status, const __grid_constant__ LinkScratch Lk) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const uint32_t nw = *n_warp, nb = *n_block;  // written by the register kernel (an earlier launch)
+    if (nw == 0u && nb == 0u) return;            // the whole grid takes the same way out: no barrier is left waiting
+    if constexpr (LINK) {
+        cg::grid_group grid = cg::this_grid();
+        link_pass<0>(R, P, res, warp_list, (int64_t)nw, Lk);
+        link_pass<0>(R, P, res, block_list, (int64_t)nb, Lk);
+        grid.sync();
+        link_pass<1>(R, P, res, warp_list, (int64_t)nw, Lk);
+        link_pass<1>(R, P, res, block_list, (int64_t)nb, Lk);
+        grid.sync();
+        link_pass<2>(R, P, res, warp_list, (int64_t)nw, Lk);
+        link_pass<2>(R, P, res, block_list, (int64_t)nb, Lk);
+    }
+    deep_units<POSB>(R, res, ins_seq, P, out, warp_list, nw, deep_work, *batch_status, smem);
+    if (nb) block_units<POSB>(R, res, ins_seq, P, out, block_list, nb, smem);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -823,23 +892,54 @@ struct PileupScratch {
     cudaEvent_t *ev;  // timing (vfk_set_timing): [2] after locate, [3] after the register kernel, [4] after the list path; or NULL
 };
 
+template <int POSB, bool LINK>
+static cudaError_t launch_tail(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, vfk_counts *out, const PileupScratch &S, int sm_count,
+                               cudaStream_t stream, int *launches) {
+    using L = Layout<POSB>;
+    const size_t smem = std::max((size_t)WARPS_PER_CTA * 2 * (L::BINS / 2) * sizeof(uint32_t),  // a pair of u16 histograms per warp
+                                 (size_t)2 * L::BINS * sizeof(uint32_t));                        // a pair of u32 histograms per CTA
+    cudaError_t e;
+    if (smem > 40 * 1024) {  // with the kernel's static shared memory on top, 48 KB is the limit without the opt-in
+        e = cudaFuncSetAttribute(tail_kernel<POSB, LINK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    // the occupancy query assumes the largest shared-memory carve-out: ask for it, so that the launch sees the same limit
+    (void)cudaFuncSetAttribute(tail_kernel<POSB, LINK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    int ctas = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, tail_kernel<POSB, LINK>, WARPS_PER_CTA * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (ctas < 1) ctas = 1;
+    // every CTA must be resident (grid barriers); more warps than units would only idle
+    int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)sm_count * ctas, (V.n + WARPS_PER_CTA - 1) / WARPS_PER_CTA));
+    const ResolvedUnit *res = (const ResolvedUnit *)S.resolved;
+    const uint8_t *ins_seq = V.ins_seq;
+    const uint32_t *n_block = (const uint32_t *)((char *)S.counters + 8), *n_warp = (const uint32_t *)((char *)S.counters + 12);
+    uint32_t *deep_work = (uint32_t *)((char *)S.counters + 16);
+    const uint32_t *batch_status = (const uint32_t *)((char *)S.counters + 20);
+    const uint32_t *block_list = S.lists, *warp_list = S.lists + V.n;
+    LinkScratch Lk;
+    Lk.heads = S.heads; Lk.n_buckets = S.n_buckets; Lk.next = S.next; Lk.column = S.column; Lk.claimed = S.claimed; Lk.mate = S.mate;
+    void *args[] = {(void *)&R, (void *)&res, (void *)&ins_seq, (void *)&P, (void *)&out, (void *)&block_list, (void *)&n_block,
+                    (void *)&warp_list, (void *)&n_warp, (void *)&deep_work, (void *)&batch_status, (void *)&Lk};
+    e = cudaLaunchCooperativeKernel((const void *)tail_kernel<POSB, LINK>, dim3((unsigned)grid), dim3(WARPS_PER_CTA * 32), args, smem, stream);
+    if (e == cudaErrorCooperativeLaunchTooLarge && grid > sm_count) {  // the driver counts fewer resident CTAs than the query: one per SM always fits
+        (void)cudaGetLastError();
+        grid = sm_count;
+        e = cudaLaunchCooperativeKernel((const void *)tail_kernel<POSB, LINK>, dim3((unsigned)grid), dim3(WARPS_PER_CTA * 32), args, smem, stream);
+    }
+    ++*launches;
+    return e;
+}
+
 template <int POSB>
 static cudaError_t launch_posb(ReadsDev R, const UnitsDev &V, const vfk_params &P, vfk_counts *out, const PileupScratch &S,
                                int sm_count, cudaStream_t stream, int *launches, bool link_all) {
-    using L = Layout<POSB>;
-    const size_t smem_deep = (size_t)WARPS_PER_CTA * 2 * (L::BINS / 2) * sizeof(uint32_t);
-    const size_t smem_block = (size_t)2 * L::BINS * sizeof(uint32_t);
     ResolvedUnit *res = (ResolvedUnit *)S.resolved;
     unsigned long long *work = (unsigned long long *)S.counters;
     uint32_t *n_block = (uint32_t *)((char *)S.counters + 8), *n_warp = (uint32_t *)((char *)S.counters + 12);
-    uint32_t *deep_work = (uint32_t *)((char *)S.counters + 16);
     const uint32_t *batch_status = (const uint32_t *)((char *)S.counters + 20);
     uint32_t *block_list = S.lists, *warp_list = S.lists + V.n;
     cudaError_t e;
-    if (smem_deep > 48 * 1024) {
-        e = cudaFuncSetAttribute(pileup_deep_kernel<POSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_deep);
-        if (e != cudaSuccess) return e;
-    }
     R.mate = S.mate;
     locate_kernel<<<(unsigned)((V.n + 255) / 256), 256, 0, stream>>>(R, V, res);
     ++*launches;
@@ -866,36 +966,13 @@ static cudaError_t launch_posb(ReadsDev R, const UnitsDev &V, const vfk_params &
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (S.ev) cudaEventRecord(S.ev[3], stream);
-    if (!link_all) {  // overlap partners of the reads inside the windows of the listed units (both lists)
-        e = launch_link(R, P, res, warp_list, n_warp, V.n, S.heads, S.n_buckets, S.next, S.column, S.claimed, S.mate, sm_count, stream, launches);
-        if (e != cudaSuccess) return e;
-        if (R.n_reads > WARP_PATH_MAX_CAND) {
-            e = launch_link(R, P, res, block_list, n_block, V.n, S.heads, S.n_buckets, S.next, S.column, S.claimed, S.mate, sm_count, stream,
-                            launches);
-            if (e != cudaSuccess) return e;
-        }
-    }
-    int deep_ctas = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&deep_ctas, pileup_deep_kernel<POSB>, WARPS_PER_CTA * 32, smem_deep);
-    if (e != cudaSuccess) return e;
-    if (deep_ctas < 1) deep_ctas = 1;
-    int64_t deep_grid = std::min<int64_t>((int64_t)sm_count * deep_ctas, (V.n + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
-    pileup_deep_kernel<POSB><<<(unsigned)deep_grid, WARPS_PER_CTA * 32, smem_deep, stream>>>(R, res, V.ins_seq, P, out, warp_list, n_warp,
-                                                                                             deep_work, batch_status);
-    ++*launches;
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    if (R.n_reads > WARP_PATH_MAX_CAND) {  // only then can a column be too deep for the warp kernels
-        pileup_block_kernel<POSB><<<(unsigned)sm_count, WARPS_PER_CTA * 32, smem_block, stream>>>(R, res, V.ins_seq, P, out, block_list,
-                                                                                                  n_block);
-        ++*launches;
-        e = cudaGetLastError();
-    }
+    // the listed units: their windows linked, then the histogram paths -- one launch
+    e = link_all ? launch_tail<POSB, false>(R, V, P, out, S, sm_count, stream, launches) : launch_tail<POSB, true>(R, V, P, out, S, sm_count, stream, launches);
     if (S.ev) cudaEventRecord(S.ev[4], stream);
     return e;
 }
 
-// locate + pileup kernels on a batch prep_kernel has prepared (R.end / R.ev / R.blk_incl valid, counters zeroed except the
+// locate + pileup kernels on a batch prep_kernel has prepared (R.ee / R.chunk_max / R.blk_incl valid, counters zeroed except the
 // batch status word)
 cudaError_t launch_pileup(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, int max_l_qseq, vfk_counts *out,
                           const PileupScratch &S, int sm_count, cudaStream_t stream, int *launches, bool link_all) {

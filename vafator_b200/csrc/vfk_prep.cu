@@ -17,7 +17,7 @@
 //                bucket (atomicExch on a bucket head), then every record replays the protocol over the records
 //                that share its name, in file order: found -> pair and delete; not found -> stored if the mate is
 //                still to come; an entry whose record has left the pileup buffer is dropped.
-#include "vfk_device.cuh"
+#include "vfk_link.cuh"
 
 namespace vfk {
 
@@ -43,29 +43,47 @@ __device__ __forceinline__ CigarInfo cigar_single(uint32_t w, int32_t l_qseq) { 
     else o.ev = (len == 0u || len >= 4096u || l_qseq > VFK_MAX_READ_LEN) ? EV_GENERAL : (len << 12);
     return o;
 }
+// The state machine as tables: no branch in the loop body (a walk runs with whatever lanes hold a multi-op CIGAR).
+//   op class: H 0, S 1, M/=/X 2, I/D/N 3, anything else 4 (three bits per BAM op code)
+//   NEXT[class]: three bits per state
+constexpr uint64_t cigar_class_lut() {
+    uint64_t t = 0;
+    for (int op = 0; op < 16; ++op) {
+        const uint64_t c = op == OP_H ? 0 : op == OP_S ? 1 : (op == OP_M || op == OP_EQ || op == OP_X) ? 2 : (op == OP_I || op == OP_D || op == OP_N) ? 3 : 4;
+        t |= c << (3 * op);
+    }
+    return t;
+}
+constexpr uint32_t pack_states(int s0, int s1, int s2, int s3, int s4, int s5, int s6, int s7) {
+    return (uint32_t)s0 | (uint32_t)s1 << 3 | (uint32_t)s2 << 6 | (uint32_t)s3 << 9 | (uint32_t)s4 << 12 | (uint32_t)s5 << 15 | (uint32_t)s6 << 18 | (uint32_t)s7 << 21;
+}
+constexpr uint64_t CIGAR_CLASS = cigar_class_lut();
+constexpr uint32_t NEXT_H = pack_states(0, 7, 6, 7, 6, 6, 6, 7), NEXT_S = pack_states(1, 7, 5, 7, 5, 7, 7, 7);
+constexpr uint32_t NEXT_M = pack_states(2, 2, 7, 4, 7, 7, 7, 7), NEXT_E = pack_states(7, 7, 3, 7, 7, 7, 7, 7);
 __device__ __forceinline__ CigarInfo cigar_walk(const uint32_t *__restrict__ c, int n, int32_t l_qseq) {
     CigarInfo o;
     uint32_t span = 0, lead = 0, m1 = 0, ev = EVK_NONE, elen = 0;
-    int state = 0;
+    uint32_t state = 0;
+    // the first four ops are requested together (one round trip; nearly every multi-op CIGAR has two to four ops)
+    const uint32_t w0 = n > 0 ? __ldg(c) : 0u, w1 = n > 1 ? __ldg(c + 1) : 0u, w2 = n > 2 ? __ldg(c + 2) : 0u, w3 = n > 3 ? __ldg(c + 3) : 0u;
+#pragma unroll 1
     for (int k = 0; k < n; ++k) {
-        const uint32_t w = __ldg(c + k);
+        const uint32_t w = k == 0 ? w0 : k == 1 ? w1 : k == 2 ? w2 : k == 3 ? w3 : __ldg(c + k);
         const uint32_t op = w & 15u, len = w >> 4;
-        if (op_consumes_ref(op)) span += len;
-        int next = 7;  // 7 = not of this shape
-        if (op == OP_H) next = (state == 0) ? 0 : (state == 2 || state >= 4) ? 6 : 7;
-        else if (op == OP_S) {
-            if (state == 0) { next = 1; lead = len; }
-            else if (state == 2 || state == 4) next = 5;
-        } else if (op_is_match(op)) {
-            if (state <= 1) { next = (len == 0u) ? 7 : 2; m1 = len; }
-            else if (state == 3) next = (len == 0u) ? 7 : 4;
-        } else if (op == OP_I || op == OP_D || op == OP_N) {
-            if (state == 2 && len != 0u) { next = 3; ev = op == OP_I ? EVK_INS : op == OP_D ? EVK_DEL : EVK_SKIP; elen = len; }
-        }
-        state = (state == 7) ? 7 : next;
+        span += ((0x18Du >> op) & 1u) ? len : 0u;  // M D N = X consume the reference
+        const uint32_t cls = (uint32_t)(CIGAR_CLASS >> (3u * op)) & 7u;
+        const uint32_t table = cls == 0u ? NEXT_H : cls == 1u ? NEXT_S : cls == 2u ? NEXT_M : cls == 3u ? NEXT_E : 0xFFFFFFu;
+        uint32_t next = (table >> (3u * state)) & 7u;
+        if (cls >= 2u && len == 0u) next = 7u;            // an empty block / event is not of this shape
+        lead = (cls == 1u && state == 0u) ? len : lead;
+        m1 = (cls == 2u && state <= 1u) ? len : m1;
+        const bool event = next == 3u;                    // I / D / N right after the first block
+        ev = event ? (op == OP_I ? EVK_INS : op == OP_D ? EVK_DEL : EVK_SKIP) : ev;
+        elen = event ? len : elen;
+        state = next;
     }
     o.span = span;
-    const bool shaped = (state == 2 || state >= 4) && state != 7 && m1 != 0u && m1 < 4096u && lead < 4096u && elen < 64u && l_qseq <= VFK_MAX_READ_LEN;
+    const bool shaped = (state == 2u || (state >= 4u && state != 7u)) && m1 != 0u && m1 < 4096u && lead < 4096u && elen < 64u && l_qseq <= VFK_MAX_READ_LEN;
     o.ev = shaped ? (lead | (m1 << 12) | (ev << 24) | (elen << 26)) : EV_GENERAL;
     return o;
 }
@@ -82,256 +100,278 @@ __device__ __forceinline__ int32_t contig_of(const int64_t *__restrict__ contig_
     return a;
 }
 
-// One CTA = PREP_BLOCK (1024) reads, PREP_THREADS (256) threads: a warp takes four CHUNKS of 32 consecutive reads, every
-// thread one read of each -- all of a thread's loads (four reads x starts, CIGAR counts / offsets, read lengths) are issued
-// before the first is consumed, and the contig of the block is searched by one thread meanwhile.  Writes end / shape word per
-// read, the maximum end key (tid << 32 | end) per chunk and per block: the two levels of the position index.
-__global__ void __launch_bounds__(PREP_THREADS)
-prep_kernel(ReadsDev R, const int32_t *__restrict__ pos_src, int32_t *__restrict__ pos_copy, int32_t *__restrict__ end_out,
-            uint32_t *__restrict__ ev_out, int64_t *__restrict__ chunk_max, int64_t *__restrict__ blk_max,
-            uint32_t *__restrict__ batch_status) {
-    constexpr int PER = PREP_BLOCK / PREP_THREADS;  // reads per thread
-    __shared__ long long s_max[PREP_THREADS / 32];
-    __shared__ int32_t s_tid[2];
-    const int64_t b0 = (int64_t)blockIdx.x * PREP_BLOCK, b1 = min(b0 + PREP_BLOCK, R.n_reads) - 1;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int32_t p[PER], n[PER], lq[PER], prev[PER];
-    int64_t off[PER], idx[PER];
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-        // chunk (warp * PER + j) of the block: consecutive reads per warp instruction, consecutive chunks per warp
-        idx[j] = b0 + (int64_t)(warp * PER + j) * 32 + lane;
-        const bool in = idx[j] < R.n_reads;
-        p[j] = in ? __ldg(pos_src + idx[j]) : 0;
-        n[j] = in ? __ldg(R.n_cigar + idx[j]) : 0;
-        off[j] = in ? __ldg(R.cigar_off + idx[j]) : 0;
-        lq[j] = in ? __ldg(R.l_qseq + idx[j]) : 0;
+// One CTA = PREP_BLOCK (1024) reads = 8 warps of 128 reads; a warp works alone (no CTA barrier after the first line): four
+// CHUNKS of 32 consecutive reads, two at a time -- both chunks' loads (start, CIGAR count / offset, read length) are in flight
+// before either is consumed.  Nine reads in ten have a one-op CIGAR and are finished on the spot; the others are put on the
+// warp's shared-memory list and walked afterwards, ~10 lanes at once instead of two or three per chunk, their first four ops
+// requested together.  Writes {end, shape word} per read, the maximum end key (tid << 32 | end) per chunk and per block:
+// the two levels of the position index.  The last warp of a CTA to finish folds the eight warp keys into the block key.
+struct PrepRead {
+    int32_t p, n, lq;
+    int64_t off;
+};
+__device__ __forceinline__ PrepRead prep_load(const ReadsDev &R, int64_t i, bool in) {
+    PrepRead r;
+    r.p = in ? __ldg(R.pos + i) : 0;
+    r.n = in ? __ldg(R.n_cigar + i) : 0;
+    r.off = in ? __ldg(R.cigar_off + i) : 0;
+    r.lq = in ? __ldg(R.l_qseq + i) : 0;
+    return r;
+}
+// negative start / count / offset, CIGAR outside its pool, read longer than the position histograms cover
+__device__ __forceinline__ bool prep_malformed(const ReadsDev &R, const PrepRead &r) {
+    return (r.p | r.n) < 0 || (uint64_t)r.off + (uint64_t)(uint32_t)r.n > (uint64_t)R.n_cigar_words || (uint32_t)r.lq > (uint32_t)VFK_MAX_READ_LEN;
+}
+// a warp whose reads straddle a contig boundary (one in tens of thousands): every read looks its own contig up and walks its own CIGAR
+__device__ __noinline__ long long straddling_read(const ReadsDev &R, int64_t i, bool in, uint2 *__restrict__ ee_out, uint32_t *__restrict__ batch_status) {
+    long long key = LLONG_MIN;
+    if (in) {
+        const PrepRead r = prep_load(R, i, true);
+        const int32_t tid = contig_of(R.contig_off, R.n_contigs, i);
+        bool bad = prep_malformed(R, r) || (i > __ldg(R.contig_off + tid) && __ldg(R.pos + i - 1) > r.p);
+        CigarInfo ci;
+        ci.span = 0u;
+        ci.ev = EV_GENERAL;
+        if (!bad && r.n > 0) ci = cigar_info(R.cigar + r.off, r.n, r.lq);
+        if ((uint64_t)(uint32_t)r.p + ci.span > 0x7FFFFFFFull) { bad = true; ci.span = 0u; }
+        const int32_t end = r.p + (int32_t)ci.span;
+        ee_out[i] = make_uint2((uint32_t)end, ci.ev);
+        if (bad) atomicOr(batch_status, VFK_ST_BADBATCH);
+        key = ((long long)tid << 32) | (long long)(uint32_t)end;
     }
 #pragma unroll
-    for (int j = 0; j < PER; ++j) {  // the start before this one (sortedness): the lane below has it, lane 0 reads it
-        prev[j] = __shfl_up_sync(FULL, p[j], 1);
-        if (lane == 0) prev[j] = (idx[j] > 0 && idx[j] < R.n_reads) ? __ldg(pos_src + idx[j] - 1) : 0;
-    }
-    if (threadIdx.x < 2) s_tid[threadIdx.x] = contig_of(R.contig_off, R.n_contigs, threadIdx.x ? b1 : b0);
-    __syncthreads();
-    const bool one_contig = s_tid[0] == s_tid[1];
-    const int64_t first_of_contig = one_contig ? __ldg(R.contig_off + s_tid[0]) : 0;
-    bool bad = false;
-    uint32_t span[PER], ev[PER];
-    uint32_t pending = 0u;  // reads of this thread whose CIGAR has more than one op
-    // pass 1: checks + the one-op CIGARs, every lane busy
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-        span[j] = 0u;
-        ev[j] = EV_GENERAL;
-        if (idx[j] < R.n_reads) {
-            const bool b = p[j] < 0 || n[j] < 0 || off[j] < 0 || off[j] + n[j] > R.n_cigar_words || lq[j] < 0 || lq[j] > VFK_MAX_READ_LEN;
-            bad = bad || b;
-            if (!b && n[j] == 1) {
-                const CigarInfo ci = cigar_single(__ldg(R.cigar + off[j]), lq[j]);
-                span[j] = ci.span;
-                ev[j] = ci.ev;
-            } else if (!b && n[j] > 1) {
-                pending |= 1u << j;
-            }
-        }
-    }
-    // pass 2: the other CIGARs, one per thread and round -- the few complex reads of a warp's four chunks share the rounds
-    while (__any_sync(FULL, pending != 0u)) {
-        if (pending) {
-            const int j = __ffs(pending) - 1;
-            pending &= pending - 1u;
-            const int64_t o = j == 0 ? off[0] : j == 1 ? off[1] : j == 2 ? off[2] : off[3];
-            const int nn = j == 0 ? n[0] : j == 1 ? n[1] : j == 2 ? n[2] : n[3];
-            const int32_t l = j == 0 ? lq[0] : j == 1 ? lq[1] : j == 2 ? lq[2] : lq[3];
-            const CigarInfo ci = cigar_walk(R.cigar + o, nn, l);
-#pragma unroll
-            for (int t = 0; t < PER; ++t)
-                if (t == j) { span[t] = ci.span; ev[t] = ci.ev; }
-        }
-    }
-    long long blk_key = LLONG_MIN;
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-        const int64_t i = idx[j];
-        const bool in = i < R.n_reads;
-        int32_t tid = s_tid[0];
-        if (in) {
-            bool b = false;
-            if (!one_contig) tid = contig_of(R.contig_off, R.n_contigs, i);
-            // coordinate sorted inside the contig
-            if (i > (one_contig ? first_of_contig : __ldg(R.contig_off + tid)) && prev[j] > p[j]) b = true;
-            if ((uint64_t)(uint32_t)p[j] + span[j] > 0x7FFFFFFFull) { b = true; span[j] = 0u; }
-            if (pos_copy) pos_copy[i] = p[j];
-            end_out[i] = p[j] + (int32_t)span[j];
-            ev_out[i] = ev[j];
-            bad = bad || b;
-        }
-        long long key;
-        if (one_contig) {  // one REDUX instead of a 64-bit butterfly
-            const int32_t e = __reduce_max_sync(FULL, in ? p[j] + (int32_t)span[j] : -1);
-            key = e < 0 ? LLONG_MIN : (((long long)tid << 32) | (long long)(uint32_t)e);
-        } else {
-            key = in ? (((long long)tid << 32) | (long long)(uint32_t)(p[j] + (int32_t)span[j])) : LLONG_MIN;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(FULL, key, o));
-        }
-        const int64_t chunk = (b0 >> 5) + warp * PER + j;
-        if (lane == 0 && chunk * 32 < R.n_reads) chunk_max[chunk] = key;
-        blk_key = max(blk_key, key);
-    }
-    if (__any_sync(FULL, bad) && lane == 0) atomicOr(batch_status, VFK_ST_BADBATCH);
-    if (lane == 0) s_max[warp] = blk_key;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        long long m = s_max[0];
-#pragma unroll
-        for (int w = 1; w < PREP_THREADS / 32; ++w) m = max(m, s_max[w]);
-        blk_max[blockIdx.x] = m;
-    }
+    for (int o = 16; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(FULL, key, o));
+    return key;
 }
 
-// blk_incl[0] = LLONG_MIN, blk_incl[b + 1] = max(blk_max[0..b]) -- one CTA walks the array (n_reads / 1024 entries) in tiles
-// of 1024: coalesced load, warp scans + a scan of the warp totals, the running maximum carried from tile to tile
+constexpr int PREP_WARPS = PREP_THREADS / 32;           // 8
+constexpr int PREP_WARP_READS = PREP_BLOCK / PREP_WARPS;  // 128: four chunks
+// ---- the two ways a warp gets through its 128 reads.  Both leave: {end, shape} of every one-op read written, the reads with
+// more ops on the warp's list (s_list / cnt), the maximum end of the finished reads of each chunk in s_cend.
+//
+// scalar: lane = read, four chunks two at a time; any alignment, any tail.
+__device__ __forceinline__ void prep_chunks_scalar(const ReadsDev &R, int64_t w0, int lane, uint32_t lt_mask, int64_t first_of_contig,
+                                                   uint2 *__restrict__ ee_out, uint8_t *s_list, int32_t *s_cend, uint32_t &cnt, bool &bad) {
+    PrepRead r[2];
+#pragma unroll 1
+    for (int round = 0; round < 2; ++round) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) r[j] = prep_load(R, w0 + (2 * round + j) * 32 + lane, w0 + (2 * round + j) * 32 + lane < R.n_reads);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int c = 2 * round + j;
+            const int64_t i = w0 + c * 32 + lane;
+            const bool in = i < R.n_reads;
+            // the start before this one (coordinate sorted inside the contig): the lane below has it, lane 0 reads it
+            int32_t prev = __shfl_up_sync(FULL, r[j].p, 1);
+            if (lane == 0) prev = (in && i > first_of_contig) ? __ldg(R.pos + i - 1) : INT32_MIN;
+            int32_t end = -1;  // a read whose CIGAR is still to be walked does not vote
+            bool multi = false;
+            if (in) {
+                bool b = prep_malformed(R, r[j]) || (prev > r[j].p && i > first_of_contig);
+                multi = !b && r[j].n > 1;
+                if (!multi) {
+                    CigarInfo ci;
+                    ci.span = 0u;
+                    ci.ev = EV_GENERAL;
+                    if (!b && r[j].n == 1) ci = cigar_single(__ldg(R.cigar + r[j].off), r[j].lq);
+                    if ((uint64_t)(uint32_t)r[j].p + ci.span > 0x7FFFFFFFull) { b = true; ci.span = 0u; }
+                    end = r[j].p + (int32_t)ci.span;
+                    ee_out[i] = make_uint2((uint32_t)end, ci.ev);
+                }
+                bad = bad || b;
+            }
+            const uint32_t mm = __ballot_sync(FULL, multi);
+            if (multi) s_list[cnt + __popc(mm & lt_mask)] = (uint8_t)(c * 32 + lane);
+            cnt += __popc(mm);
+            const int32_t e = __reduce_max_sync(FULL, end);
+            if (lane == 0) s_cend[c] = e;
+        }
+    }
+}
+// vector: lane = four consecutive reads -- one 128-bit load per array (two for the 64-bit CIGAR offsets) serves the warp's 128
+// reads, two 128-bit stores write their {end, shape} pairs.  Needs all 128 reads in range and 16-byte aligned arrays.
+__device__ __forceinline__ void prep_chunks_vector(const ReadsDev &R, int64_t w0, int lane, uint32_t lt_mask, int64_t first_of_contig,
+                                                   uint2 *__restrict__ ee_out, uint8_t *s_list, int32_t *s_cend, uint32_t &cnt, bool &bad) {
+    const int64_t base = w0 + 4 * lane;
+    const int4 p4 = __ldg(reinterpret_cast<const int4 *>(R.pos + base));
+    const int4 n4 = __ldg(reinterpret_cast<const int4 *>(R.n_cigar + base));
+    const int4 l4 = __ldg(reinterpret_cast<const int4 *>(R.l_qseq + base));
+    const longlong2 o01 = __ldg(reinterpret_cast<const longlong2 *>(R.cigar_off + base));
+    const longlong2 o23 = __ldg(reinterpret_cast<const longlong2 *>(R.cigar_off + base + 2));
+    PrepRead r[4];
+    r[0].p = p4.x; r[1].p = p4.y; r[2].p = p4.z; r[3].p = p4.w;
+    r[0].n = n4.x; r[1].n = n4.y; r[2].n = n4.z; r[3].n = n4.w;
+    r[0].lq = l4.x; r[1].lq = l4.y; r[2].lq = l4.z; r[3].lq = l4.w;
+    r[0].off = o01.x; r[1].off = o01.y; r[2].off = o23.x; r[3].off = o23.y;
+    // the start before the lane's first read: the lane below has it, lane 0 reads it
+    int32_t prev = __shfl_up_sync(FULL, p4.w, 1);
+    if (lane == 0) prev = w0 > first_of_contig ? __ldg(R.pos + w0 - 1) : INT32_MIN;
+    bool b[4], multi[4];
+    uint32_t word[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        b[j] = prep_malformed(R, r[j]) || ((j ? r[j - 1].p : prev) > r[j].p && base + j > first_of_contig);
+        multi[j] = !b[j] && r[j].n > 1;
+        word[j] = (!b[j] && r[j].n == 1) ? __ldg(R.cigar + r[j].off) : 0xFFFFFFFFu;  // the four CIGAR words in flight together
+    }
+    uint32_t out[8];
+    int32_t e = -1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        CigarInfo ci;
+        ci.span = 0u;
+        ci.ev = EV_GENERAL;
+        if (!b[j] && r[j].n == 1) ci = cigar_single(word[j], r[j].lq);
+        if ((uint64_t)(uint32_t)r[j].p + ci.span > 0x7FFFFFFFull) { b[j] = true; ci.span = 0u; }
+        const int32_t end = r[j].p + (int32_t)ci.span;
+        out[2 * j] = (uint32_t)end;  // a multi-op read gets a placeholder here; its walker overwrites it after the warp barrier
+        out[2 * j + 1] = ci.ev;
+        e = multi[j] ? e : max(e, end);
+        bad = bad || b[j];
+        const uint32_t mm = __ballot_sync(FULL, multi[j]);
+        if (multi[j]) s_list[cnt + __popc(mm & lt_mask)] = (uint8_t)(4 * lane + j);
+        cnt += __popc(mm);
+    }
+    uint4 *o = reinterpret_cast<uint4 *>(ee_out + base);
+    o[0] = make_uint4(out[0], out[1], out[2], out[3]);
+    o[1] = make_uint4(out[4], out[5], out[6], out[7]);
+    // a chunk = 32 reads = 8 lanes: maximum over each group of eight lanes
+#pragma unroll
+    for (int k = 1; k < 8; k <<= 1) e = max(e, __shfl_xor_sync(FULL, e, k));
+    if ((lane & 7) == 0) s_cend[lane >> 3] = e;
+}
+
+#ifndef VFK_PREP_MIN_CTAS
+#define VFK_PREP_MIN_CTAS 5  // 48 registers, 40 warps per SM
+#endif
+// VEC: the four per-read arrays the kernel streams are 16-byte aligned (checked by the launcher)
+template <bool VEC>
+__global__ void __launch_bounds__(PREP_THREADS, VFK_PREP_MIN_CTAS)
+prep_kernel(const __grid_constant__ ReadsDev R, uint2 *__restrict__ ee_out, int64_t *__restrict__ chunk_max, int64_t *__restrict__ blk_max,
+            uint32_t *__restrict__ batch_status) {
+    __shared__ uint8_t s_list[PREP_WARPS][PREP_WARP_READS];  // per warp: its reads with more than one CIGAR op
+    __shared__ int32_t s_cend[PREP_WARPS][4];                // per warp: maximum end of each of its chunks
+    __shared__ long long s_wkey[PREP_WARPS];                 // per warp: its maximum end key
+    __shared__ uint32_t s_arrived;
+    if (threadIdx.x == 0) s_arrived = 0u;
+    __syncthreads();  // the only CTA-wide barrier, before anything is in flight
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const int64_t w0 = (int64_t)blockIdx.x * PREP_BLOCK + (int64_t)warp * PREP_WARP_READS;  // this warp's reads [w0, w0 + 128)
+    const int64_t w1 = min(w0 + PREP_WARP_READS, R.n_reads) - 1;
+    long long wkey = LLONG_MIN;
+    if (w0 < R.n_reads) {
+        int32_t t = 0;  // contig of the warp's first / last read
+        if (lane < 2) t = contig_of(R.contig_off, R.n_contigs, lane ? w1 : w0);
+        const int32_t tid0 = __shfl_sync(FULL, t, 0);
+        if (tid0 != __shfl_sync(FULL, t, 1)) {
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                const int64_t i = w0 + c * 32 + lane;
+                const long long key = straddling_read(R, i, i < R.n_reads, ee_out, batch_status);
+                if (lane == 0 && (w0 + c * 32) < R.n_reads) chunk_max[(w0 >> 5) + c] = key;
+                wkey = max(wkey, key);
+            }
+        } else {
+            const int64_t first_of_contig = __ldg(R.contig_off + tid0);
+            uint32_t cnt = 0u;
+            bool bad = false;
+            if (VEC && w0 + PREP_WARP_READS <= R.n_reads) prep_chunks_vector(R, w0, lane, lt_mask, first_of_contig, ee_out, s_list[warp], s_cend[warp], cnt, bad);
+            else prep_chunks_scalar(R, w0, lane, lt_mask, first_of_contig, ee_out, s_list[warp], s_cend[warp], cnt, bad);
+            __syncwarp();
+            // the multi-op CIGARs of the warp's 128 reads, one per lane
+            for (uint32_t k = lane; k < cnt; k += 32) {
+                const uint32_t idx = s_list[warp][k];
+                const int64_t i = w0 + idx;
+                const int32_t p = __ldg(R.pos + i);
+                CigarInfo ci = cigar_walk(R.cigar + __ldg(R.cigar_off + i), __ldg(R.n_cigar + i), __ldg(R.l_qseq + i));
+                if ((uint64_t)(uint32_t)p + ci.span > 0x7FFFFFFFull) { bad = true; ci.span = 0u; }
+                const int32_t end = p + (int32_t)ci.span;
+                ee_out[i] = make_uint2((uint32_t)end, ci.ev);
+                atomicMax(&s_cend[warp][idx >> 5], end);
+            }
+            if (__any_sync(FULL, bad) && lane == 0) atomicOr(batch_status, VFK_ST_BADBATCH);
+            __syncwarp();
+            const int32_t e = lane < 4 ? s_cend[warp][lane] : -1;
+            const long long key = e < 0 ? LLONG_MIN : (((long long)tid0 << 32) | (long long)(uint32_t)e);
+            if (lane < 4 && (w0 + lane * 32) < R.n_reads) chunk_max[(w0 >> 5) + lane] = key;
+            const int32_t m = __reduce_max_sync(FULL, e);
+            wkey = m < 0 ? LLONG_MIN : (((long long)tid0 << 32) | (long long)(uint32_t)m);
+        }
+    }
+    // block key: the last warp to arrive folds the eight warp keys
+    if (lane == 0) {
+        s_wkey[warp] = wkey;
+        __threadfence_block();
+        if (atomicAdd(&s_arrived, 1u) == PREP_WARPS - 1) {
+            __threadfence_block();
+            long long m = LLONG_MIN;
+#pragma unroll
+            for (int w = 0; w < PREP_WARPS; ++w) m = max(m, ((volatile long long *)s_wkey)[w]);
+            blk_max[blockIdx.x] = m;
+        }
+    }
+}
+static_assert(PREP_WARP_READS == 128, "a warp owns four chunks");
+
+// blk_incl[0] = LLONG_MIN, blk_incl[b + 1] = max(blk_max[0..b]) -- ONE CTA, one pass: every thread owns a run of consecutive
+// entries (n_reads / 1024 entries in all), the run maxima are scanned across the CTA, the runs are then written out
 constexpr int SCAN_THREADS = 1024;
 __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const int64_t *__restrict__ blk_max, int64_t n_blocks, int64_t *__restrict__ blk_incl) {
     __shared__ long long s_warp[32];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    long long carry = LLONG_MIN;
-    if (t == 0) blk_incl[0] = LLONG_MIN;
-    for (int64_t base = 0; base < n_blocks; base += SCAN_THREADS) {
-        const int64_t k = base + t;
-        long long v = k < n_blocks ? (long long)blk_max[k] : LLONG_MIN;
+    const int64_t per = (n_blocks + SCAN_THREADS - 1) / SCAN_THREADS;
+    const int64_t k0 = (int64_t)t * per, k1 = min(k0 + per, n_blocks);
+    long long v = LLONG_MIN;
+    for (int64_t k = k0; k < k1; ++k) v = max(v, (long long)__ldg(blk_max + k));
+    long long incl = v;  // inclusive scan of the run maxima: warp, then the warp totals
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long u = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl = max(incl, u);
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        long long w = s_warp[lane];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const long long u = __shfl_up_sync(FULL, v, o);
-            if (lane >= o) v = max(v, u);
+            const long long u = __shfl_up_sync(FULL, w, o);
+            if (lane >= o) w = max(w, u);
         }
-        if (lane == 31) s_warp[warp] = v;
-        __syncthreads();
-        if (warp == 0) {
-            long long w = s_warp[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const long long u = __shfl_up_sync(FULL, w, o);
-                if (lane >= o) w = max(w, u);
-            }
-            s_warp[lane] = w;
-        }
-        __syncthreads();
-        const long long before = warp > 0 ? s_warp[warp - 1] : LLONG_MIN;
-        v = max(max(v, before), carry);
-        if (k < n_blocks) blk_incl[k + 1] = v;
-        carry = max(carry, s_warp[31]);
-        __syncthreads();
+        s_warp[lane] = w;
+    }
+    __syncthreads();
+    long long run = __shfl_up_sync(FULL, incl, 1);  // exclusive prefix of this thread's run
+    if (lane == 0) run = LLONG_MIN;
+    if (warp > 0) run = max(run, s_warp[warp - 1]);
+    if (t == 0) blk_incl[0] = LLONG_MIN;
+    for (int64_t k = k0; k < k1; ++k) {
+        run = max(run, (long long)__ldg(blk_max + k));
+        blk_incl[k + 1] = run;
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// mate linking for the windows of listed units
+// mate linking as three launches (the list-shaped auxiliary vfk_pileup_values, and the debug hook that links every unit);
+// the pileup call itself runs the passes fused inside tail_kernel (vfk_pileup.cu)
 // ------------------------------------------------------------------------------------------
-constexpr uint32_t LINK_EMPTY = 0xFFFFFFFFu;
-__device__ __forceinline__ uint64_t mix64(uint64_t z) {
-    z += 0x9E3779B97F4A7C15ull;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
-}
-struct LinkScratch {
-    uint32_t *heads;     // [n_buckets] bucket -> last inserted record, LINK_EMPTY when empty (restored after every call)
-    uint32_t n_buckets;  // power of two
-    uint32_t *next;      // [n_reads] chain
-    int32_t *column;     // [n_reads] push_column of the chained records
-    uint32_t *claimed;   // [n_reads / 32 + 1] bitmap: record handled by this call
-    uint32_t *mate;      // [n_reads] result
-};
-__device__ __forceinline__ uint32_t bucket_of(const ReadsDev &R, const LinkScratch &L, int64_t i, int32_t tid) {
-    return (uint32_t)mix64(__ldg(R.qname_id + i) ^ ((uint64_t)(uint32_t)tid << 40) ^ __ldg(R.qname_hash + i)) & (L.n_buckets - 1u);
-}
-
-// the window of a located unit as the linker sees it: its candidate reads plus the first record pushed after the column
-// (bam_plp_auto reads one record ahead: that record's arrival can still pair with a read of the column)
-__device__ __forceinline__ int64_t window_end(const ReadsDev &R, const vfk_params &P, const ResolvedUnit &r) {
-    const int64_t nx = next_pushed(R, P, (int64_t)r.hi, (int64_t)r.c1, r.stop);
-    return nx >= 0 ? nx + 1 : (int64_t)r.hi;
-}
-
-// phase: 0 = claim + chain, 1 = replay the protocol and write mate[], 2 = restore the bucket heads and the bitmap
 template <int PHASE>
 __global__ void __launch_bounds__(256)
 link_kernel(ReadsDev R, vfk_params P, const ResolvedUnit *__restrict__ res, const uint32_t *__restrict__ list, const uint32_t *__restrict__ n_list,
             int64_t n_all, LinkScratch L) {
-    const int lane = threadIdx.x & 31;
-    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t n = list ? (int64_t)*n_list : n_all;
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t k = w; k < n; k += n_warps) {
-        const uint32_t u = list ? list[k] : (uint32_t)k;
-        if (u == 0xFFFFFFFFu) continue;
-        const ResolvedUnit r = res[u];
-        const int64_t c1 = (int64_t)r.c1;
-        if (r.hi <= r.lo) continue;
-        int64_t last = 0;
-        if (lane == 0) last = window_end(R, P, r);
-        last = __shfl_sync(FULL, last, 0);
-        const int32_t tid = contig_of(R.contig_off, R.n_contigs, (int64_t)r.lo);
-        const int64_t c0 = __ldg(R.contig_off + tid);
-        for (int64_t i = (int64_t)r.lo + lane; i < last; i += 32) {
-            if (i >= (int64_t)r.hi && i != last - 1) continue;  // between the column and the next pushed record: filtered reads
-            const uint32_t bit = 1u << (i & 31);
-            if (PHASE == 0) {
-                if (atomicOr(L.claimed + (i >> 5), bit) & bit) continue;  // another unit's warp has it
-                L.mate[i] = VFK_NO_MATE;
-                L.next[i] = LINK_EMPTY - 1u;  // not chained
-                const int32_t column = push_column(R, P, i, c0);
-                if (!P.ignore_overlaps || !reaches_hash(R, P, i, tid, column)) continue;
-                L.column[i] = column;
-                L.next[i] = atomicExch(L.heads + bucket_of(R, L, i, tid), (uint32_t)i);
-            } else if (PHASE == 1) {
-                if (L.next[i] == LINK_EMPTY - 1u) continue;
-                if (L.mate[i] != VFK_NO_MATE) continue;  // written by its partner's thread (same value)
-                // replay over the records sharing this name, in file order; stop once record i is settled
-                const uint64_t id = __ldg(R.qname_id + i);
-                const uint32_t qh = __ldg(R.qname_hash + i);
-                const uint32_t head = L.heads[bucket_of(R, L, i, tid)];
-                int64_t waiting = -1, cur = -1;
-                uint32_t result = VFK_NO_MATE;
-                for (;;) {
-                    int64_t m = -1;  // smallest member beyond cur
-                    for (uint32_t j = head; j != LINK_EMPTY; j = L.next[j]) {
-                        if ((int64_t)j > cur && (m < 0 || (int64_t)j < m) && (int64_t)j >= c0 && (int64_t)j < c1 && __ldg(R.qname_id + j) == id &&
-                            __ldg(R.qname_hash + j) == qh)
-                            m = (int64_t)j;
-                    }
-                    if (m < 0) break;
-                    if (waiting >= 0 && __ldg(R.end + waiting) < L.column[m]) waiting = -1;  // its record already left the buffer
-                    if (waiting < 0) {
-                        if (stores_itself(R, m)) waiting = m;
-                    } else {
-                        if (waiting == i || m == i) {
-                            const uint32_t sel = wang_hash(__ldg(R.qname_hash + waiting)) & 1u;
-                            result = (uint32_t)(waiting == i ? m : waiting) | (sel << 31);
-                            break;
-                        }
-                        waiting = -1;
-                    }
-                    cur = m;
-                    if (m >= i && waiting != i) break;  // record i has been through without a partner
-                }
-                L.mate[i] = result;
-            } else {
-                if (L.next[i] != LINK_EMPTY - 1u) L.heads[bucket_of(R, L, i, tid)] = LINK_EMPTY;
-                L.claimed[i >> 5] = 0u;  // benign race: every writer stores zero
-            }
-        }
-    }
+    link_pass<PHASE>(R, P, res, list, list ? (int64_t)*n_list : n_all, L);
 }
 
-cudaError_t launch_prep(const ReadsDev &R, const int32_t *pos_src, int32_t *pos_copy, int32_t *end_out, uint32_t *ev_out, int64_t *chunk_max,
-                        int64_t *blk_max, int64_t *blk_incl, uint32_t *batch_status, cudaStream_t stream, int *launches) {
+cudaError_t launch_prep(const ReadsDev &R, uint2 *ee_out, int64_t *chunk_max, int64_t *blk_max, int64_t *blk_incl, uint32_t *batch_status,
+                        cudaStream_t stream, int *launches) {
     if (R.n_reads <= 0) return cudaSuccess;
     const int64_t nb = (R.n_reads + PREP_BLOCK - 1) / PREP_BLOCK;
-    prep_kernel<<<(unsigned)nb, PREP_THREADS, 0, stream>>>(R, pos_src, pos_copy, end_out, ev_out, chunk_max, blk_max, batch_status);
+    // the vector path reads four reads per lane with 128-bit loads: the streamed arrays must be 16-byte aligned (device allocations are)
+    const bool aligned = (((uintptr_t)R.pos | (uintptr_t)R.n_cigar | (uintptr_t)R.l_qseq | (uintptr_t)R.cigar_off | (uintptr_t)ee_out) & 15u) == 0u;
+    if (aligned) prep_kernel<true><<<(unsigned)nb, PREP_THREADS, 0, stream>>>(R, ee_out, chunk_max, blk_max, batch_status);
+    else prep_kernel<false><<<(unsigned)nb, PREP_THREADS, 0, stream>>>(R, ee_out, chunk_max, blk_max, batch_status);
     scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(blk_max, nb, blk_incl);
     *launches += 2;
     return cudaGetLastError();

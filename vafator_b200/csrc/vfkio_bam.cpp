@@ -47,7 +47,12 @@ struct Inflater {
     z_stream zs;
     bool ready = false;
     ~Inflater() { if (ready) inflateEnd(&zs); }
+    // inflate one BGZF payload to exactly `cap` bytes and verify the member's CRC32 (the four bytes after the payload), as htslib does
     int block(const uint8_t *src, size_t n, uint8_t *dst, size_t cap) {
+        if (inflate_only(src, n, dst, cap)) return -1;
+        return (uint32_t)crc32(crc32(0L, Z_NULL, 0), dst, (uInt)cap) == le32(src + n) ? 0 : -1;
+    }
+    int inflate_only(const uint8_t *src, size_t n, uint8_t *dst, size_t cap) {
         static const bool zlib_only = getenv("VFKIO_ZLIB") != nullptr;
         if (!zlib_only && vfkio_inflate_raw(src, n, dst, cap) == 0) return 0;  // vfkio_inflate.cpp; zlib decides the rest
         if (!ready) {  // the zlib state (32 KB window and all) is only set up by a thread that needs it
@@ -90,7 +95,7 @@ struct Mapped {
     uint8_t operator[](size_t i) const { return p[i]; }
 };
 
-// fixed fields + name + CIGAR + sequence + qualities must lie inside the record (nothing verifies the BGZF CRC)
+// fixed fields + name + CIGAR + sequence + qualities must lie inside the record
 inline bool record_fits(const uint8_t *r, uint32_t block_size) {
     const uint64_t l_name = r[8], n_cig = le16(r + 12), l_seq = le32(r + 16);
     return 32 + l_name + 4 * n_cig + (l_seq + 1) / 2 + l_seq <= block_size;
@@ -110,7 +115,7 @@ int bgzf_member(const Mapped &raw, size_t p, Blk &blk, size_t &blen) {
     int bsize = -1;
     while (x + 4 <= xe) {
         const uint16_t slen = le16(raw.data() + x + 2);
-        if (raw[x] == 'B' && raw[x + 1] == 'C' && slen == 2) bsize = le16(raw.data() + x + 4);
+        if (raw[x] == 'B' && raw[x + 1] == 'C' && slen == 2 && x + 6 <= xe) bsize = le16(raw.data() + x + 4);
         x += 4 + slen;
     }
     if (bsize < 0) return -1;

@@ -89,7 +89,7 @@ def libvfk():
     """libvfk.so (CUDA).  Raises if it cannot be loaded -- there is no fallback path."""
     global _libvfk
     if _libvfk is None:
-        path = _build.LIBVFK
+        path = os.environ.get("VFK_LIBVFK") or _build.LIBVFK  # VFK_LIBVFK: an alternative build of the same library (tools/build_variants.py, A/B runs)
         if not os.path.exists(path):
             path = _build.build_cuda()
         try:
