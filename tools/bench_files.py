@@ -21,10 +21,10 @@ def write_inputs(args):
     length = int(args.mbp * 1e6)
     paths = {}
     for sample, normal in (("tumor", False), ("normal", True)):
-        cfg = synth.wgs(n_contigs=args.contigs, contig_len=length, normal_vaf=int(normal))
+        cfg = synth.wgs(n_contigs=args.contigs, contig_len=length, normal_vaf=int(normal), read_salt=7 if normal else 0)
         p = os.path.join(args.dir, "%s_%dx%gMbp.bam" % (sample, args.contigs, args.mbp))
         if not os.path.exists(p + ".bai"):
-            batch = synth.reads(cfg, read_seed=cfg.seed + (7 if normal else 0))
+            batch = synth.reads(cfg)
             bamio.write_bam_batch(p, batch, [length + 1000] * args.contigs, level=args.level)
         paths[sample] = p
     cfg = synth.wgs(n_contigs=args.contigs, contig_len=length)

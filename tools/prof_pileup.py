@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Minimal driver for profiling: one synthetic BAM (canonical batch resident in HBM), N launches of the pileup path (read preparation, locate, pileup kernels).
-    python tools/prof_pileup.py [--tiles 200000] [--launches 6] [--workload wes|wgs|amplicon]"""
+    python tools/prof_pileup.py [--tiles 200000] [--launches 6] [--workload wes|wgs|amplicon|multisample]"""
 import argparse
 import os
 import sys
@@ -20,7 +20,8 @@ ap.add_argument("--workload", default="wes")
 ap.add_argument("--snv-period", type=int, default=500, help="wes: one SNV per this many target bases (small = L2-resident reads, many units)")
 a = ap.parse_args()
 cfg = {"wes": lambda: synth.wes(n_tiles=a.tiles, snv_period=a.snv_period), "wgs": lambda: synth.wgs(contig_len=a.tiles * 4096 // 10, n_contigs=2),
-       "amplicon": lambda: synth.amplicon(n_tiles=max(a.tiles // 100, 10))}[a.workload]()
+       "amplicon": lambda: synth.amplicon(n_tiles=max(a.tiles // 100, 10)),
+       "multisample": lambda: synth.multisample(0, n_tiles=a.tiles)}[a.workload]()  # one 60x sample of C4
 t0 = time.time()
 batch = synth.reads(cfg)
 recs = synth.variant_records(cfg)

@@ -50,6 +50,8 @@ static int fail(int code, const char *fmt, const char *detail = "") {
         if (e_ != cudaSuccess) return fail(VFK_ECUDA, #call ": %s", cudaGetErrorString(e_)); \
     } while (0)
 
+static const size_t COUNTER_BYTES = 64 + 256 * 4;  // per-call counters + one work counter per SM segment (vfk_pileup.cu)
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -99,7 +101,7 @@ struct PinBuf {  // page-locked host scratch
 struct Work {
     DevBuf ee, chunk_max, blk_max, blk_incl, resolved, lists, next, column, claimed, mate, heads;
     uint32_t n_buckets = 0;
-    void *counters = nullptr;  // 64 B, layout in vfk_pileup.cu (PileupScratch)
+    void *counters = nullptr;  // COUNTER_BYTES, layout in vfk_pileup.cu (PileupScratch)
     cudaEvent_t tev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // phase boundaries when timing is on
     bool ev_epilogue = false;
     int reserve(int64_t n_reads, int64_t n_units, cudaStream_t st) {
@@ -238,11 +240,11 @@ extern "C" int vfk_create(int device, vfk_handle **out) {
     for (Slot &s : h->slot) {
         CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
-        CU(cudaMalloc(&s.work.counters, 64));
+        CU(cudaMalloc(&s.work.counters, COUNTER_BYTES));
         CU(cudaMallocHost((void **)&s.h_status, sizeof(uint32_t)));
         *s.h_status = 0u;
     }
-    CU(cudaMalloc(&h->work.counters, 64));
+    CU(cudaMalloc(&h->work.counters, COUNTER_BYTES));
     *out = h;
     return VFK_OK;
 }
@@ -311,7 +313,7 @@ static int enqueue_prep(vfk_handle *h, Work &w, const vfk::ReadsDev &R, cudaStre
         h->timed = &w;
         CU(cudaEventRecord(w.tev[0], st));
     }
-    CU(cudaMemsetAsync(w.counters, 0, 64, st));
+    CU(cudaMemsetAsync(w.counters, 0, COUNTER_BYTES, st));
     cudaError_t e = vfk::launch_prep(R, (uint2 *)w.ee.p, (int64_t *)w.chunk_max.p, (int64_t *)w.blk_max.p, (int64_t *)w.blk_incl.p,
                                      (uint32_t *)((char *)w.counters + 20), st, launches);
     if (e != cudaSuccess) return fail(VFK_ECUDA, "prep launch: %s", cudaGetErrorString(e));

@@ -35,12 +35,16 @@ __device__ __forceinline__ int64_t window_end(const ReadsDev &R, const vfk_param
     return nx >= 0 ? nx + 1 : (int64_t)r.hi;
 }
 
-// One pass of the linker over the units of a list (list == nullptr: units 0 .. n-1), warps striding over the units.
-// phase: 0 = claim + chain, 1 = replay the protocol and write mate[], 2 = restore the bucket heads and the bitmap.
+// The linker in two kinds of passes.
+//   link_mark   a warp per listed unit (list == nullptr: units 0 .. n-1): the reads of its window -- its candidate reads plus
+//               the first record pushed after the column -- are marked in the `claimed` bitmap, a word (32 reads) per
+//               atomic.  Windows of neighbouring units overlap many times over in a deep panel; a bit is set once.
+//   link_reads  a thread per marked read, warps striding over the bitmap words.  PHASE 0 = chain the records that reach
+//               overlap_push per name bucket, 1 = replay the protocol and write mate[], 2 = restore the bucket heads and
+//               clear the bitmap.
 // The scratch arrays are written and read inside one launch when the passes run fused (tail_kernel, grid barriers in
 // between): every access to them is a plain (coherent) load or store, never the read-only path.
-template <int PHASE>
-__device__ __forceinline__ void link_pass(const ReadsDev &R, const vfk_params &P, const ResolvedUnit *__restrict__ res, const uint32_t *list, int64_t n,
+__device__ __forceinline__ void link_mark(const ReadsDev &R, const vfk_params &P, const ResolvedUnit *__restrict__ res, const uint32_t *list, int64_t n,
                                           const LinkScratch &L) {
     const int lane = threadIdx.x & 31;
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -50,62 +54,95 @@ __device__ __forceinline__ void link_pass(const ReadsDev &R, const vfk_params &P
         if (u == 0xFFFFFFFFu) continue;
         const ResolvedUnit r = res[u];
         if (r.hi <= r.lo) continue;
-        const int64_t c1 = contig_end(R, r.tid);
-        int64_t last = 0;
-        if (lane == 0) last = window_end(R, P, r);
-        last = __shfl_sync(FULL, last, 0);
-        const int32_t tid = r.tid;
-        const int64_t c0 = __ldg(R.contig_off + tid);
-        for (int64_t i = (int64_t)r.lo + lane; i < last; i += 32) {
-            if (i >= (int64_t)r.hi && i != last - 1) continue;  // between the column and the next pushed record: filtered reads
-            const uint32_t bit = 1u << (i & 31);
-            if (PHASE == 0) {
-                if (atomicOr(L.claimed + (i >> 5), bit) & bit) continue;  // another unit's warp has it
-                L.mate[i] = VFK_NO_MATE;
-                L.next[i] = LINK_EMPTY - 1u;  // not chained
-                const int32_t column = push_column(R, P, i, c0);
-                if (!P.ignore_overlaps || !reaches_hash(R, P, i, tid, column)) continue;
-                L.column[i] = column;
-                L.next[i] = atomicExch(L.heads + bucket_of(R, L, i, tid), (uint32_t)i);
-            } else if (PHASE == 1) {
-                if (L.next[i] == LINK_EMPTY - 1u) continue;
-                if (L.mate[i] != VFK_NO_MATE) continue;  // written by its partner's thread (same value)
-                // replay over the records sharing this name, in file order; stop once record i is settled
-                const uint64_t id = __ldg(R.qname_id + i);
-                const uint32_t qh = __ldg(R.qname_hash + i);
-                const uint32_t head = L.heads[bucket_of(R, L, i, tid)];
-                int64_t waiting = -1, cur = -1;
-                uint32_t result = VFK_NO_MATE;
-                for (;;) {
-                    int64_t m = -1;  // smallest member beyond cur
-                    for (uint32_t j = head; j != LINK_EMPTY; j = L.next[j]) {
-                        if ((int64_t)j > cur && (m < 0 || (int64_t)j < m) && (int64_t)j >= c0 && (int64_t)j < c1 && __ldg(R.qname_id + j) == id &&
-                            __ldg(R.qname_hash + j) == qh)
-                            m = (int64_t)j;
-                    }
-                    if (m < 0) break;
-                    if (waiting >= 0 && ld_end(R, waiting) < L.column[m]) waiting = -1;  // its record already left the buffer
-                    if (waiting < 0) {
-                        if (stores_itself(R, m)) waiting = m;
-                    } else {
-                        if (waiting == i || m == i) {
-                            const uint32_t sel = wang_hash(__ldg(R.qname_hash + waiting)) & 1u;
-                            result = (uint32_t)(waiting == i ? m : waiting) | (sel << 31);
-                            break;
-                        }
-                        waiting = -1;
-                    }
-                    cur = m;
-                    if (m >= i && waiting != i) break;  // record i has been through without a partner
-                }
-                L.mate[i] = result;
-            } else {
-                if (L.next[i] != LINK_EMPTY - 1u) L.heads[bucket_of(R, L, i, tid)] = LINK_EMPTY;
-                L.claimed[i >> 5] = 0u;  // benign race: every writer stores zero
-            }
+        const int64_t lo = (int64_t)r.lo, hi = (int64_t)r.hi;
+        for (int64_t word = (lo >> 5) + lane; word <= ((hi - 1) >> 5); word += 32) {
+            uint32_t m = 0xFFFFFFFFu;
+            if (word == (lo >> 5)) m &= 0xFFFFFFFFu << (lo & 31);
+            if (word == ((hi - 1) >> 5)) m &= 0xFFFFFFFFu >> (31 - ((hi - 1) & 31));
+            if ((L.claimed[word] & m) != m) atomicOr(L.claimed + word, m);
+        }
+        if (lane == 0) {
+            const int64_t last = window_end(R, P, r);  // the first record pushed after the column, or hi
+            if (last > hi) atomicOr(L.claimed + ((last - 1) >> 5), 1u << ((last - 1) & 31));
         }
     }
 }
 
+template <int PHASE>
+__device__ __forceinline__ void link_one_read(const ReadsDev &R, const vfk_params &P, const LinkScratch &L, int64_t i, int32_t tid) {
+    const int64_t c0 = __ldg(R.contig_off + tid), c1 = __ldg(R.contig_off + tid + 1);
+    if (PHASE == 0) {
+        L.mate[i] = VFK_NO_MATE;
+        L.next[i] = LINK_EMPTY - 1u;  // not chained
+        const int32_t column = push_column(R, P, i, c0);
+        if (!P.ignore_overlaps || !reaches_hash(R, P, i, tid, column)) return;
+        L.column[i] = column;
+        L.next[i] = atomicExch(L.heads + bucket_of(R, L, i, tid), (uint32_t)i);
+    } else if (PHASE == 1) {
+        if (L.next[i] == LINK_EMPTY - 1u) return;
+        if (L.mate[i] != VFK_NO_MATE) return;  // written by its partner's thread (same value)
+        // replay over the records sharing this name, in file order; stop once record i is settled
+        const uint64_t id = __ldg(R.qname_id + i);
+        const uint32_t qh = __ldg(R.qname_hash + i);
+        const uint32_t head = L.heads[bucket_of(R, L, i, tid)];
+        int64_t waiting = -1, cur = -1;
+        uint32_t result = VFK_NO_MATE;
+        for (;;) {
+            int64_t m = -1;  // smallest member beyond cur
+            for (uint32_t j = head; j != LINK_EMPTY; j = L.next[j]) {
+                if ((int64_t)j > cur && (m < 0 || (int64_t)j < m) && (int64_t)j >= c0 && (int64_t)j < c1 && __ldg(R.qname_id + j) == id &&
+                    __ldg(R.qname_hash + j) == qh)
+                    m = (int64_t)j;
+            }
+            if (m < 0) break;
+            if (waiting >= 0 && ld_end(R, waiting) < L.column[m]) waiting = -1;  // its record already left the buffer
+            if (waiting < 0) {
+                if (stores_itself(R, m)) waiting = m;
+            } else {
+                if (waiting == i || m == i) {
+                    const uint32_t sel = wang_hash(__ldg(R.qname_hash + waiting)) & 1u;
+                    result = (uint32_t)(waiting == i ? m : waiting) | (sel << 31);
+                    break;
+                }
+                waiting = -1;
+            }
+            cur = m;
+            if (m >= i && waiting != i) break;  // record i has been through without a partner
+        }
+        L.mate[i] = result;
+    } else {
+        if (L.next[i] != LINK_EMPTY - 1u) L.heads[bucket_of(R, L, i, tid)] = LINK_EMPTY;
+    }
+}
+
+template <int PHASE>
+__device__ __forceinline__ void link_reads(const ReadsDev &R, const vfk_params &P, const LinkScratch &L) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n_words = (R.n_reads >> 5) + 1;
+    // Warp w owns the words w, w + n_warps, w + 2 n_warps, ...: marked reads come in runs (the windows of neighbouring units),
+    // and a run of consecutive words spreads over as many warps.  A warp fetches 32 of its words at a time (one per lane)
+    // and then visits those that have a bit set.
+    for (int64_t k0 = 0; w + k0 * n_warps < n_words; k0 += 32) {
+        const int64_t my_word = w + (k0 + lane) * n_warps;
+        const uint32_t mine = my_word < n_words ? L.claimed[my_word] : 0u;
+        uint32_t nz = __ballot_sync(FULL, mine != 0u);
+        if (PHASE == 2 && mine != 0u) L.claimed[my_word] = 0u;  // every pass has seen the word by now (grid barrier before this pass)
+        while (nz) {
+            const int j = __ffs(nz) - 1;
+            nz &= nz - 1u;
+            const uint32_t bits = __shfl_sync(FULL, mine, j);
+            const int64_t i = ((w + (k0 + j) * n_warps) << 5) + lane;
+            if (!((bits >> lane) & 1u) || i >= R.n_reads) continue;
+            int32_t a = 0, b = R.n_contigs;  // contig of read i: last t with contig_off[t] <= i
+            while (b - a > 1) {
+                const int32_t m = (a + b) >> 1;
+                if (__ldg(R.contig_off + m) <= i) a = m; else b = m;
+            }
+            link_one_read<PHASE>(R, P, L, i, a);
+        }
+    }
+}
 
 }  // namespace vfk

@@ -747,28 +747,65 @@ pileup_warp_kernel(const __grid_constant__ ReadsDev R, const ResolvedUnit *__res
 // then a warp per listed unit with shared-memory histograms, then a CTA per unit for columns deeper than the u16 bins allow.
 // With empty lists (nearly every 30x / 60x call) every CTA leaves at the first line.
 // ------------------------------------------------------------------------------------------
+// The listed units that fit the u16 histograms, found again by their status word (VFK_ST_DEFERRED, written by the register
+// kernel) in UNIT order: a CTA takes eight consecutive units at a time and its eight warps work on neighbouring columns at the
+// same moment -- their windows overlap (a deep panel: many times over), so a read's bytes are fetched from DRAM once and
+// found in L1 / L2 by the warps next door.  Taken in list order (scrambled by the register kernel's self-scheduling) the
+// same units re-fetch every read once per unit.
+// Work distribution: the unit range is cut into one contiguous segment per SM; a CTA reads the id of the SM it runs on and
+// takes the next eight units of THAT segment (one per warp), so that everything resident on an SM -- four CTAs, 32 warps --
+// works on the same stretch of columns and shares its L1, and the whole grid touches ~148 stretches at a time, which L2 holds.
+// An SM that runs out of its segment takes from the next one that still has units.
+constexpr int MAX_SEGMENTS = 256;
+__device__ __forceinline__ uint32_t sm_id() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+    return r;
+}
 template <int POSB>
-__device__ __forceinline__ void deep_units(const ReadsDev &R, const ResolvedUnit *__restrict__ res, const uint8_t *__restrict__ ins_seq, const vfk_params &P,
-                                           vfk_counts *__restrict__ out, const uint32_t *__restrict__ warp_list, uint32_t n, uint32_t *__restrict__ deep_work,
-                                           uint32_t bad, uint32_t *smem) {
+__device__ __forceinline__ void deep_units(const ReadsDev &R, const ResolvedUnit *__restrict__ res, int64_t n_units, const uint8_t *__restrict__ ins_seq,
+                                           const vfk_params &P, vfk_counts *__restrict__ out, uint32_t bad, uint32_t *smem, uint32_t *seg_ctr, int n_seg) {
     using L = Layout<POSB>;
     constexpr int WORDS = L::BINS / 2;  // u16 bins
+    __shared__ long long s_base;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *ref_slot = smem + (size_t)warp * 2 * WORDS;
     uint32_t *alt_slot = ref_slot + WORDS;
-    // listed unit k goes to warp k first (no atomics when the list is short), the rest through a counter
-    const uint32_t n_warps = gridDim.x * WARPS_PER_CTA;
-    uint32_t k = blockIdx.x * WARPS_PER_CTA + warp;
+    const int64_t seg_len = ((n_units + n_seg - 1) / n_seg + WARPS_PER_CTA - 1) / WARPS_PER_CTA * WARPS_PER_CTA;  // a multiple of 8
+    const int home = (int)(sm_id() % (uint32_t)n_seg);
     for (;;) {
-        if (k >= n) break;
-        const uint32_t u = warp_list[k];
-        if (u != LIST_VOID) {
-            Unit U;
-            unit_from(res[u], ins_seq, U);
-            unit_by_histogram<POSB>(R, P, U, ref_slot, alt_slot, lane, out + u, bad);
+        __syncthreads();  // the previous base has been read by every warp
+        if (warp == 0) {
+            long long base = -1;
+            for (int first = 0; first < n_seg && base < 0; first += 32) {  // segments home, home + 1, ... 32 at a time
+                const int k = first + lane;
+                const int cand = (home + k) % n_seg;
+                const int64_t have = min(seg_len, n_units - (int64_t)cand * seg_len);  // units of the segment (<= 0: none)
+                bool open = k < n_seg && (int64_t)*((volatile uint32_t *)seg_ctr + cand) < have;
+                uint32_t m = __ballot_sync(FULL, open);
+                while (m && base < 0) {
+                    const int l = __ffs(m) - 1;
+                    m &= m - 1u;
+                    const int c = __shfl_sync(FULL, cand, l);
+                    const int64_t c_have = __shfl_sync(FULL, have, l);
+                    uint32_t start = 0u;
+                    if (lane == 0) start = atomicAdd(seg_ctr + c, (uint32_t)WARPS_PER_CTA);
+                    start = __shfl_sync(FULL, start, 0);
+                    if ((int64_t)start < c_have) base = (int64_t)c * seg_len + start;
+                }
+            }
+            if (lane == 0) s_base = base;
         }
-        if (lane == 0) k = n_warps + atomicAdd(deep_work, 1u);
-        k = __shfl_sync(FULL, k, 0);
+        __syncthreads();
+        const long long base = s_base;
+        if (base < 0) break;
+        const int64_t u = base + warp;
+        if (u >= n_units) continue;
+        const uint4 w = reinterpret_cast<const uint4 *>(out + u)[2];  // {med2[2][0], med2[2][1], status, n_cand}
+        if (!(w.z & VFK_ST_DEFERRED) || w.w > (uint32_t)WARP_PATH_MAX_CAND) continue;
+        Unit U;
+        unit_from(res[u], ins_seq, U);
+        unit_by_histogram<POSB>(R, P, U, ref_slot, alt_slot, lane, out + u, bad);
     }
 }
 
@@ -845,27 +882,27 @@ __device__ __forceinline__ void block_units(const ReadsDev &R, const ResolvedUni
 
 // LINK: false when the link kernels have already run over every unit (debug hook)
 template <int POSB, bool LINK>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-tail_kernel(const __grid_constant__ ReadsDev R, const ResolvedUnit *__restrict__ res, const uint8_t *__restrict__ ins_seq,
-            const __grid_constant__ vfk_params P, vfk_counts *__restrict__ out, const uint32_t *__restrict__ block_list,
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
+tail_kernel(const __grid_constant__ ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_units, const uint8_t *__restrict__ ins_seq,
+            const __grid_constant__ vfk_params P, vfk_counts *out, const uint32_t *__restrict__ block_list,
             const uint32_t *__restrict__ n_block, const uint32_t *__restrict__ warp_list, const uint32_t *__restrict__ n_warp,
-            uint32_t *__restrict__ deep_work, const uint32_t *__restrict__ batch_status, const __grid_constant__ LinkScratch Lk) {
+            const uint32_t *__restrict__ batch_status, uint32_t *seg_ctr, int n_seg, const __grid_constant__ LinkScratch Lk) {
     extern __shared__ __align__(16) uint32_t smem[];
     const uint32_t nw = *n_warp, nb = *n_block;  // written by the register kernel (an earlier launch)
     if (nw == 0u && nb == 0u) return;            // the whole grid takes the same way out: no barrier is left waiting
     if constexpr (LINK) {
         cg::grid_group grid = cg::this_grid();
-        link_pass<0>(R, P, res, warp_list, (int64_t)nw, Lk);
-        link_pass<0>(R, P, res, block_list, (int64_t)nb, Lk);
+        link_mark(R, P, res, warp_list, (int64_t)nw, Lk);
+        link_mark(R, P, res, block_list, (int64_t)nb, Lk);
         grid.sync();
-        link_pass<1>(R, P, res, warp_list, (int64_t)nw, Lk);
-        link_pass<1>(R, P, res, block_list, (int64_t)nb, Lk);
+        link_reads<0>(R, P, Lk);
         grid.sync();
-        link_pass<2>(R, P, res, warp_list, (int64_t)nw, Lk);
-        link_pass<2>(R, P, res, block_list, (int64_t)nb, Lk);
+        link_reads<1>(R, P, Lk);
+        grid.sync();
     }
-    deep_units<POSB>(R, res, ins_seq, P, out, warp_list, nw, deep_work, *batch_status, smem);
+    if (nw) deep_units<POSB>(R, res, n_units, ins_seq, P, out, *batch_status, smem, seg_ctr, n_seg);
     if (nb) block_units<POSB>(R, res, ins_seq, P, out, block_list, nb, smem);
+    if constexpr (LINK) link_reads<2>(R, P, Lk);  // bucket heads and bitmap left clean for the next call
 }
 
 // ------------------------------------------------------------------------------------------
@@ -876,8 +913,8 @@ cudaError_t launch_link(const ReadsDev &R, const vfk_params &P, const void *reso
                         uint32_t *mate, int sm_count, cudaStream_t stream, int *launches);
 
 // Per-call device scratch (owned by the handle / a staging slot).
-//   counters (64 bytes): @0 u64 unit work counter, @8 u32 block-list length, @12 u32 warp-list length, @16 u32 deep-kernel
-//   work counter, @20 u32 batch status (VFK_ST_BADBATCH or 0).   lists: 2 * n_units u32.
+//   counters: @0 u64 unit work counter, @8 u32 block-list length, @12 u32 warp-list length, @20 u32 batch status
+//   (VFK_ST_BADBATCH or 0), @64 256 x u32 per-SM segment counters of the list path.   lists: 2 * n_units u32.
 struct PileupScratch {
     void *resolved;   // n_units * 32 B
     void *counters;   // 64 B
@@ -914,13 +951,15 @@ static cudaError_t launch_tail(const ReadsDev &R, const UnitsDev &V, const vfk_p
     const ResolvedUnit *res = (const ResolvedUnit *)S.resolved;
     const uint8_t *ins_seq = V.ins_seq;
     const uint32_t *n_block = (const uint32_t *)((char *)S.counters + 8), *n_warp = (const uint32_t *)((char *)S.counters + 12);
-    uint32_t *deep_work = (uint32_t *)((char *)S.counters + 16);
     const uint32_t *batch_status = (const uint32_t *)((char *)S.counters + 20);
     const uint32_t *block_list = S.lists, *warp_list = S.lists + V.n;
+    int64_t n_units = V.n;
+    uint32_t *seg_ctr = (uint32_t *)((char *)S.counters + 64);  // one work counter per SM segment (zeroed with the counters)
+    int n_seg = std::min(sm_count, MAX_SEGMENTS);
     LinkScratch Lk;
     Lk.heads = S.heads; Lk.n_buckets = S.n_buckets; Lk.next = S.next; Lk.column = S.column; Lk.claimed = S.claimed; Lk.mate = S.mate;
-    void *args[] = {(void *)&R, (void *)&res, (void *)&ins_seq, (void *)&P, (void *)&out, (void *)&block_list, (void *)&n_block,
-                    (void *)&warp_list, (void *)&n_warp, (void *)&deep_work, (void *)&batch_status, (void *)&Lk};
+    void *args[] = {(void *)&R, (void *)&res, (void *)&n_units, (void *)&ins_seq, (void *)&P, (void *)&out, (void *)&block_list, (void *)&n_block,
+                    (void *)&warp_list, (void *)&n_warp, (void *)&batch_status, (void *)&seg_ctr, (void *)&n_seg, (void *)&Lk};
     e = cudaLaunchCooperativeKernel((const void *)tail_kernel<POSB, LINK>, dim3((unsigned)grid), dim3(WARPS_PER_CTA * 32), args, smem, stream);
     if (e == cudaErrorCooperativeLaunchTooLarge && grid > sm_count) {  // the driver counts fewer resident CTAs than the query: one per SM always fits
         (void)cudaGetLastError();

@@ -357,11 +357,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const int64_t *__res
 // mate linking as three launches (the list-shaped auxiliary vfk_pileup_values, and the debug hook that links every unit);
 // the pileup call itself runs the passes fused inside tail_kernel (vfk_pileup.cu)
 // ------------------------------------------------------------------------------------------
-template <int PHASE>
 __global__ void __launch_bounds__(256)
-link_kernel(ReadsDev R, vfk_params P, const ResolvedUnit *__restrict__ res, const uint32_t *__restrict__ list, const uint32_t *__restrict__ n_list,
-            int64_t n_all, LinkScratch L) {
-    link_pass<PHASE>(R, P, res, list, list ? (int64_t)*n_list : n_all, L);
+link_mark_kernel(ReadsDev R, vfk_params P, const ResolvedUnit *__restrict__ res, const uint32_t *__restrict__ list, const uint32_t *__restrict__ n_list,
+                 int64_t n_all, LinkScratch L) {
+    link_mark(R, P, res, list, list ? (int64_t)*n_list : n_all, L);
+}
+template <int PHASE>
+__global__ void __launch_bounds__(256) link_reads_kernel(ReadsDev R, vfk_params P, LinkScratch L) {
+    link_reads<PHASE>(R, P, L);
 }
 
 cudaError_t launch_prep(const ReadsDev &R, uint2 *ee_out, int64_t *chunk_max, int64_t *blk_max, int64_t *blk_incl, uint32_t *batch_status,
@@ -386,9 +389,12 @@ cudaError_t launch_link(const ReadsDev &R, const vfk_params &P, const void *reso
     const int64_t warps = list ? (int64_t)sm_count * 64 : n_all;
     const unsigned grid = (unsigned)std::min<int64_t>((warps + 7) / 8, (int64_t)sm_count * 8);
     const ResolvedUnit *res = (const ResolvedUnit *)resolved;
-    link_kernel<0><<<grid, 256, 0, stream>>>(R, P, res, list, n_list, n_all, L);
-    link_kernel<1><<<grid, 256, 0, stream>>>(R, P, res, list, n_list, n_all, L);
-    link_kernel<2><<<grid, 256, 0, stream>>>(R, P, res, list, n_list, n_all, L);
+    link_mark_kernel<<<grid, 256, 0, stream>>>(R, P, res, list, n_list, n_all, L);
+    const unsigned rgrid = (unsigned)sm_count * 8;
+    link_reads_kernel<0><<<rgrid, 256, 0, stream>>>(R, P, L);
+    link_reads_kernel<1><<<rgrid, 256, 0, stream>>>(R, P, L);
+    link_reads_kernel<2><<<rgrid, 256, 0, stream>>>(R, P, L);
+    ++*launches;
     *launches += 3;
     return cudaGetLastError();
 }
