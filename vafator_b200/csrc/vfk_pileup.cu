@@ -753,7 +753,7 @@ pileup_warp_kernel(const __grid_constant__ ReadsDev R, const ResolvedUnit *__res
 // found in L1 / L2 by the warps next door.  Taken in list order (scrambled by the register kernel's self-scheduling) the
 // same units re-fetch every read once per unit.
 // Work distribution: the unit range is cut into one contiguous segment per SM; a CTA reads the id of the SM it runs on and
-// takes the next eight units of THAT segment (one per warp), so that everything resident on an SM -- four CTAs, 32 warps --
+// takes the next units of THAT segment (one per warp and visit), so that everything resident on an SM -- four CTAs, 32 warps --
 // works on the same stretch of columns and shares its L1, and the whole grid touches ~148 stretches at a time, which L2 holds.
 // An SM that runs out of its segment takes from the next one that still has units.
 constexpr int MAX_SEGMENTS = 256;
@@ -767,40 +767,31 @@ __device__ __forceinline__ void deep_units(const ReadsDev &R, const ResolvedUnit
                                            const vfk_params &P, vfk_counts *__restrict__ out, uint32_t bad, uint32_t *smem, uint32_t *seg_ctr, int n_seg) {
     using L = Layout<POSB>;
     constexpr int WORDS = L::BINS / 2;  // u16 bins
-    __shared__ long long s_base;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *ref_slot = smem + (size_t)warp * 2 * WORDS;
     uint32_t *alt_slot = ref_slot + WORDS;
-    const int64_t seg_len = ((n_units + n_seg - 1) / n_seg + WARPS_PER_CTA - 1) / WARPS_PER_CTA * WARPS_PER_CTA;  // a multiple of 8
+    const int64_t seg_len = (n_units + n_seg - 1) / n_seg;
     const int home = (int)(sm_id() % (uint32_t)n_seg);
-    for (;;) {
-        __syncthreads();  // the previous base has been read by every warp
-        if (warp == 0) {
-            long long base = -1;
-            for (int first = 0; first < n_seg && base < 0; first += 32) {  // segments home, home + 1, ... 32 at a time
-                const int k = first + lane;
-                const int cand = (home + k) % n_seg;
-                const int64_t have = min(seg_len, n_units - (int64_t)cand * seg_len);  // units of the segment (<= 0: none)
-                bool open = k < n_seg && (int64_t)*((volatile uint32_t *)seg_ctr + cand) < have;
-                uint32_t m = __ballot_sync(FULL, open);
-                while (m && base < 0) {
-                    const int l = __ffs(m) - 1;
-                    m &= m - 1u;
-                    const int c = __shfl_sync(FULL, cand, l);
-                    const int64_t c_have = __shfl_sync(FULL, have, l);
-                    uint32_t start = 0u;
-                    if (lane == 0) start = atomicAdd(seg_ctr + c, (uint32_t)WARPS_PER_CTA);
-                    start = __shfl_sync(FULL, start, 0);
-                    if ((int64_t)start < c_have) base = (int64_t)c * seg_len + start;
-                }
+    for (;;) {  // every warp takes its next unit by itself: no CTA barrier on this path
+        long long u = -1;
+        for (int first = 0; first < n_seg && u < 0; first += 32) {  // segments home, home + 1, ... 32 at a time
+            const int k = first + lane;
+            const int cand = (home + k) % n_seg;
+            const int64_t have = min(seg_len, n_units - (int64_t)cand * seg_len);  // units of the segment (<= 0: none)
+            const bool open = k < n_seg && (int64_t)*((volatile uint32_t *)seg_ctr + cand) < have;
+            uint32_t m = __ballot_sync(FULL, open);
+            while (m && u < 0) {
+                const int l = __ffs(m) - 1;
+                m &= m - 1u;
+                const int c = __shfl_sync(FULL, cand, l);
+                const int64_t c_have = __shfl_sync(FULL, have, l);
+                uint32_t start = 0u;
+                if (lane == 0) start = atomicAdd(seg_ctr + c, 1u);
+                start = __shfl_sync(FULL, start, 0);
+                if ((int64_t)start < c_have) u = (int64_t)c * seg_len + start;
             }
-            if (lane == 0) s_base = base;
         }
-        __syncthreads();
-        const long long base = s_base;
-        if (base < 0) break;
-        const int64_t u = base + warp;
-        if (u >= n_units) continue;
+        if (u < 0) break;
         const uint4 w = reinterpret_cast<const uint4 *>(out + u)[2];  // {med2[2][0], med2[2][1], status, n_cand}
         if (!(w.z & VFK_ST_DEFERRED) || w.w > (uint32_t)WARP_PATH_MAX_CAND) continue;
         Unit U;
