@@ -39,8 +39,8 @@ def main():
     want = sys.argv[3] if len(sys.argv) > 3 and not sys.argv[3].startswith("--") else "pileup_warp_kernel"
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "vafator_b200", "libvfk.so")], cwd=tmp, capture_output=True)
-    cubin = [f for f in os.listdir(tmp) if f.startswith("vfk_pileup") and f.endswith(".cubin")][0]
-    dis = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+    cubins = [f for f in os.listdir(tmp) if f.endswith(".cubin")]
+    dis = "\n".join(subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, c)], capture_output=True, text=True).stdout for c in cubins)
     funcs, fn, cur = {}, None, None
     for ln in dis.split("\n"):
         m = re.match(r"\s*\.text\.(\S+):", ln)

@@ -109,7 +109,7 @@ struct Work {
         const size_t nb = (nr + vfk::PREP_BLOCK - 1) / vfk::PREP_BLOCK;
         int rc;
         if ((rc = ee.reserve(nr * 8)) || (rc = chunk_max.reserve((nr / 32 + 1) * 8)) || (rc = blk_max.reserve(nb * 8)) || (rc = blk_incl.reserve((nb + 1) * 8)) ||
-            (rc = resolved.reserve(nu * sizeof(vfk::ResolvedUnit))) || (rc = lists.reserve(nu * 2 * sizeof(uint32_t))) ||
+            (rc = resolved.reserve(nu * sizeof(vfk::ResolvedUnit))) || (rc = lists.reserve(nu * 3 * sizeof(uint32_t))) ||
             (rc = next.reserve(nr * 4)) || (rc = column.reserve(nr * 4)) || (rc = mate.reserve(nr * 4)))
             return rc;
         const size_t claim_bytes = (nr / 32 + 1) * 4;

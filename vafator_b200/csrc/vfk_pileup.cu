@@ -107,10 +107,18 @@ __device__ __forceinline__ ResolvedUnit locate_unit(const ReadsDev &R, const Uni
         // a chunk before the last one qualifies by its maximum (all its reads precede `a`; reads of an earlier contig carry a
         // smaller key); the last one is scanned whatever its maximum says
         while (ch < ch_last && __ldg(R.chunk_max + ch) <= key) ++ch;
-        int64_t i = max(c0, ch << 5);
-        const int64_t to = min(a, (ch + 1) << 5);
-        while (i < to && ld_end(R, i) <= col) ++i;
-        lo = i < to ? i : a;
+        // first read of [from, to) whose end exceeds the column: the chunk's {end, shape} pairs are fetched eight reads at a time
+        // (four independent 128-bit loads; a chunk starts on a 256-byte boundary of `ee`) instead of one dependent load per read
+        const int64_t from = max(c0, ch << 5), to = min(a, (ch + 1) << 5);
+        lo = a;
+        for (int64_t g = (ch << 5); g < to && lo == a; g += 8) {
+            const uint4 *q = reinterpret_cast<const uint4 *>(R.ee + g);
+            const uint4 v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2), v3 = __ldg(q + 3);
+            const int32_t e[8] = {(int32_t)v0.x, (int32_t)v0.z, (int32_t)v1.x, (int32_t)v1.z, (int32_t)v2.x, (int32_t)v2.z, (int32_t)v3.x, (int32_t)v3.z};
+#pragma unroll
+            for (int j = 7; j >= 0; --j)
+                if (g + j >= from && g + j < to && e[j] > col) lo = g + j;
+        }
     }
     ResolvedUnit r;
     r.col = col;
@@ -519,6 +527,233 @@ static __device__ __noinline__ int hard_quality(const ReadsDev &R, const vfk_par
     return tweaked_quality(R, P, U, i, hot, mw, cold, true, qpos, (int)cold.z, false, own, my_word);
 }
 
+// ------------------------------------------------------------------------------------------
+// medium columns: 65 .. MED_CAP candidate reads (every fourth 60x column).  Same protocol as the two register slots, for as
+// many slots of 32 as the column has, with the per-read state parked in shared memory between the passes:
+//   pass 1  read filter, column resolution, the read's own base / quality, overlap_push eligibility -> key / cp / xw
+//   pairing the eligible reads meet in a small hash table keyed by the X31 name hash (names confirmed by their 64-bit ids): the
+//           first record of a name claims a slot, the second finds it and the two name each other, a third makes the column
+//           one for the general protocol (list), exactly as in pair_in_registers
+//   pass 2  overlap adjustment from the partner's parked word, base-quality filter, classification, histograms
+// ------------------------------------------------------------------------------------------
+constexpr int MED_CAP = 192, MED_TAB = 512;
+constexpr uint32_t MED_NONE = 0xFFFFu;
+struct MedSmem {
+    uint32_t key[MED_CAP];   // X31 name hash of an eligible read
+    uint32_t cp[MED_CAP];    // packed per-read state (bits below)
+    uint16_t xw[MED_CAP];    // quality | base << 8 of the read at the column (or at its next base), bit 15: aligned at the column
+    uint16_t prt[MED_CAP];   // partner (candidate index) or MED_NONE
+    uint16_t tab[MED_TAB];   // name hash table: candidate index or MED_NONE
+    uint32_t general;        // the column needs the general protocol
+    uint32_t pad[3];
+};
+static_assert(sizeof(MedSmem) % 16 == 0, "per-warp blocks stay 16-byte aligned");
+constexpr uint32_t CP_QPOS = 0xFFFu, CP_COVERS = 1u << 20, CP_IN_COL = 1u << 21, CP_DEL = 1u << 22, CP_SKIP = 1u << 23, CP_ALIGNED = 1u << 24,
+                   CP_HARD = 1u << 25, CP_INS = 1u << 26, CP_DELN = 1u << 27, CP_NONSIMPLE = 1u << 28, CP_ELIG = 1u << 29, CP_STORES = 1u << 30;
+
+// compare-and-swap on a 16-bit cell of shared memory, through its 32-bit word
+__device__ __forceinline__ uint32_t cas16(uint16_t *cell, uint32_t expect, uint32_t val) {
+    uint32_t *word = reinterpret_cast<uint32_t *>(reinterpret_cast<uintptr_t>(cell) & ~(uintptr_t)3);
+    const uint32_t sh = (reinterpret_cast<uintptr_t>(cell) & 2) ? 16u : 0u;
+    uint32_t seen = *reinterpret_cast<volatile uint32_t *>(word);
+    for (;;) {
+        const uint32_t cur = (seen >> sh) & 0xFFFFu;
+        if (cur != expect) return cur;
+        const uint32_t old = atomicCAS(word, seen, (seen & ~(0xFFFFu << sh)) | (val << sh));
+        if (old == seen) return cur;
+        seen = old;
+    }
+}
+
+template <int POSB>
+static __device__ __forceinline__ bool medium_unit(const ReadsDev &R, const vfk_params &P, int32_t col, uint32_t meta, int32_t len, const uint8_t *ins,
+                                                uint32_t lo, uint32_t hi, int32_t stop, int32_t tid, MedSmem *M, uint32_t *ref_slot, uint32_t *alt_slot,
+                                                vfk_counts *out) {
+    using L = Layout<POSB>;
+    constexpr int WORDS = L::BINS / 2;
+    const int lane = threadIdx.x & 31;
+    const int n = (int)(hi - lo);
+    Unit U;
+    U.col = col; U.stop = stop; U.kind = meta & 3u; U.ref_code = (meta >> 8) & 0xFFu; U.alt_code = (meta >> 16) & 0xFFu; U.len = len; U.ins = ins;
+    U.tid = tid; U.lo = lo; U.hi = hi;
+    for (int k = lane; k < MED_TAB / 2; k += 32) reinterpret_cast<uint32_t *>(M->tab)[k] = 0xFFFFFFFFu;
+    if (lane == 0) M->general = 0u;
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(ref_slot);
+        for (int w = lane; w < (2 * WORDS) / 4; w += 32) z[w] = make_uint4(0, 0, 0, 0);
+    }
+    // ---- pass 1
+    bool zero = false;
+    for (int k = lane; k < n; k += 32) {
+        const int64_t i = (int64_t)lo + k;
+        const uint4 hot = load_hot(R, i);
+        const bool pass = read_passes(hot.z, P);
+        const ColRead c = resolve_column(R, col, i, hot, true, pass);
+        PayLoad own;
+        own.q = own.s = own.odd = 0u;
+        if (c.pay) own = pay_issue(R, hot.w, (uint32_t)c.qpos);
+        bool elig = P.ignore_overlaps && pass && (hot.z & (F_PROPER | F_MUNMAP)) == F_PROPER, stores = false;
+        uint32_t key = 0u;
+        if (elig) {  // htslib overlap_push past its early exits (cf. pair_in_registers)
+            const int32_t mp = __ldg(R.mpos + i), mt = __ldg(R.mtid + i);
+            key = __ldg(R.qname_hash + i);
+            if (mt >= 0 && mt != tid) elig = false;
+            const int32_t end = (int32_t)hot.x + (int32_t)hot.y;
+            if (elig && mp >= end) {
+                const long long isz = (long long)__ldg(R.isize + i);
+                const int lq = (hot.z >> 24) == SHAPE_SIMPLE ? (int)hot.y : __ldg(R.l_qseq + i);
+                if ((isz < 0 ? -isz : isz) >= 2LL * lq) elig = false;
+            }
+            zero = zero || (elig && hot.y == 0u);
+            stores = elig && (mp >= (int32_t)hot.x || ((hot.z & F_PAIRED) && mp == -1));
+        }
+        const uint32_t word = pay_word(own);
+        M->key[k] = key;
+        M->prt[k] = (uint16_t)MED_NONE;
+        M->xw[k] = (uint16_t)((c.pay ? (word & 0xFFFu) : 0u) | (c.aligned ? 0x8000u : 0u));
+        M->cp[k] = ((uint32_t)c.qpos & CP_QPOS) | (((hot.z >> 16) & 0xFFu) << 12) | ((c.fl & FL_COVERS) ? CP_COVERS : 0u) | ((c.fl & FL_IN_COL) ? CP_IN_COL : 0u) |
+                   (c.is_del ? CP_DEL : 0u) | (c.is_refskip ? CP_SKIP : 0u) | (c.aligned ? CP_ALIGNED : 0u) | (c.hard ? CP_HARD : 0u) |
+                   (c.indel > 0 ? CP_INS : 0u) | (c.indel < 0 ? CP_DELN : 0u) | ((hot.z >> 24) != SHAPE_SIMPLE ? CP_NONSIMPLE : 0u) |
+                   (elig ? CP_ELIG : 0u) | (stores ? CP_STORES : 0u);
+    }
+    if (__any_sync(FULL, zero)) return false;  // bam_plp_push may not append a zero-span record: push order decides
+    __syncwarp();
+    // ---- pairing
+    for (int base = 0; base < n; base += 32) {
+        const int k = base + lane;
+        const bool elig = k < n && (M->cp[k < n ? k : 0] & CP_ELIG);
+        const uint32_t key = M->key[k < n ? k : 0];
+        uint32_t slot = (key * 2654435761u) >> 23;  // 9 bits
+        bool open = elig;
+        for (int probe = 0; probe < MED_TAB && __any_sync(FULL, open); ++probe) {
+            if (open) {
+                const uint32_t old = cas16(&M->tab[slot], MED_NONE, (uint32_t)k);
+                if (old == MED_NONE) {
+                    open = false;  // first record of its name
+                } else if (M->key[old] == key && __ldg(R.qname_id + lo + old) == __ldg(R.qname_id + lo + k)) {
+                    if (cas16(&M->prt[old], MED_NONE, (uint32_t)k) != MED_NONE) M->general = 1u;  // a third record of the name
+                    else M->prt[k] = (uint16_t)old;
+                    open = false;
+                } else {
+                    slot = (slot + 1u) & (MED_TAB - 1);
+                }
+            }
+        }
+    }
+    __syncwarp();
+    const bool general = __any_sync(FULL, M->general != 0u);  // a third record of some name: the column goes to the list
+    // ---- pass 2
+    int dp = 0, n_amb = 0, ac_ref = 0, ac_alt = 0, n_cover = 0, n_col = 0;
+    uint32_t status = U.kind;
+    const bool with_bq = U.kind == VFK_KIND_SNV;
+    long long nx = -2;  // the first record pushed after the column, looked up once if a read needs it
+    for (int base = 0; base < n; base += 32) {
+        const int k = base + lane;
+        const bool valid = k < n;
+        const int64_t i = (int64_t)lo + k;
+        const uint32_t cp = valid ? M->cp[k] : 0u;
+        const uint32_t pj = valid ? (uint32_t)M->prt[k] : MED_NONE;
+        // two records of one name pair up iff the earlier one stored itself
+        const bool paired = pj != MED_NONE && (M->cp[min((uint32_t)k, pj)] & CP_STORES);  // (pj != MED_NONE implies a valid k)
+        const uint32_t xw = valid ? (uint32_t)M->xw[k] : 0u;
+        const uint32_t word = xw & 0xFFFu;
+        const uint32_t sel = wang_hash(valid ? M->key[k] : 0u) & 1u;
+        uint32_t mw = paired ? (((uint32_t)lo + pj) | (sel << 31)) : VFK_NO_MATE;
+        int q = 0;
+        uint32_t my_word = 0u;
+        if (cp & CP_ALIGNED) {
+            const uint32_t px = paired ? (uint32_t)M->xw[pj] : 0u;
+            my_word = word;
+            q = overlap_quality(word, (px & 0x8000u) ? ((px & 0xFFFu) | 0x80000000u) : 0u, (uint32_t)k < pj, sel);
+        }
+        const bool hard = cp & CP_HARD;
+        if (__any_sync(FULL, hard)) {
+            // a stored read without a partner among the candidates: the record after the column may be its mate (bam_plp_auto reads one ahead)
+            const bool t = hard && !paired && (cp & CP_STORES);
+            if (__any_sync(FULL, t)) {
+                if (nx == -2) {
+                    long long v = -1;
+                    if (lane == 0) {
+                        v = next_pushed(R, P, U.hi, contig_end(R, U.tid), U.stop);
+                        if (v >= 0 && !(ld_end(R, v) > __ldg(R.pos + v) && reaches_hash(R, P, v, U.tid, INT32_MIN))) v = -1;
+                    }
+                    nx = __shfl_sync(FULL, v, 0);
+                }
+                if (t && nx >= 0 && __ldg(R.qname_id + i) == __ldg(R.qname_id + nx) && __ldg(R.qname_hash + i) == __ldg(R.qname_hash + nx))
+                    mw = (uint32_t)nx | ((wang_hash(__ldg(R.qname_hash + nx)) & 1u) << 31);
+            }
+            if (hard) {
+                my_word = word;
+                q = hard_quality(R, P, U.col, U.stop, U.tid, U.hi, i, mw, (int)(cp & CP_QPOS), word & 0xFFu, (word >> 8) * 0x11u);  // the base in both nibbles
+            }
+        }
+        ColRead c;
+        c.fl = ((cp & CP_COVERS) ? FL_COVERS : 0u) | ((cp & CP_IN_COL) ? FL_IN_COL : 0u);
+        c.aligned = cp & CP_ALIGNED; c.hard = hard; c.is_del = cp & CP_DEL; c.is_refskip = cp & CP_SKIP; c.pay = false;
+        c.qpos = (int)(cp & CP_QPOS); c.indel = (cp & CP_INS) ? 1 : (cp & CP_DELN) ? -1 : 0;
+        uint4 hot = make_uint4(0u, 0u, ((cp >> 12) & 0xFFu) << 16 | ((cp & CP_NONSIMPLE) ? (SHAPE_GENERAL << 24) : 0u), 0u);  // what finish_column reads of it
+        const Eval e = finish_column(R, P, U, i, hot, c, q, my_word);
+        const Contribution cb = decode(e);
+        n_cover += cb.covers ? 1 : 0;
+        n_col += cb.in_col ? 1 : 0;
+        dp += cb.in_dp ? 1 : 0;
+        n_amb += cb.ambiguous ? 1 : 0;
+        ac_ref += cb.ref ? 1 : 0;
+        ac_alt += (int)cb.alt;
+        accumulate<uint16_t, POSB>(ref_slot, alt_slot, cb, with_bq, status);
+    }
+    __syncwarp();
+    dp = __reduce_add_sync(FULL, dp);
+    n_amb = __reduce_add_sync(FULL, n_amb);
+    ac_ref = __reduce_add_sync(FULL, ac_ref);
+    ac_alt = __reduce_add_sync(FULL, ac_alt);
+    n_cover = __reduce_add_sync(FULL, n_cover);
+    n_col = __reduce_add_sync(FULL, n_col);
+    status = __reduce_or_sync(FULL, status);
+    int med2[3][2] = {{-1, -1}, {-1, -1}, {-1, -1}};
+    uint64_t s2[3] = {0, 0, 0};
+    if (ac_ref | ac_alt) {
+        reduce_metric<uint16_t, 256>(ref_slot, alt_slot, L::MQ_OFF, lane, med2[0][0], med2[0][1], s2[0]);
+        if (with_bq) reduce_metric<uint16_t, 256>(ref_slot, alt_slot, L::BQ_OFF, lane, med2[1][0], med2[1][1], s2[1]);
+        reduce_metric<uint16_t, POSB>(ref_slot, alt_slot, L::POS_OFF, lane, med2[2][0], med2[2][1], s2[2]);
+    }
+    if (U.kind == VFK_KIND_SNV && !P.include_ambiguous) dp -= n_amb;  // pileups.py:224-227
+    if (lane == 0 && !general) store_counts(out, dp, n_amb, ac_ref, ac_alt, med2, s2, status, (uint32_t)n, (uint32_t)n_cover, (uint32_t)n_col);
+    __syncwarp();
+    return !general;
+}
+
+// one warp per listed medium unit; a unit that turns out to need the general protocol moves on to the tail kernel's list
+template <int POSB>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+medium_kernel(const __grid_constant__ ReadsDev R, const ResolvedUnit *__restrict__ res, const uint8_t *__restrict__ ins_seq,
+              const __grid_constant__ vfk_params P, vfk_counts *__restrict__ out, const uint32_t *__restrict__ medium_list,
+              const uint32_t *__restrict__ n_medium, uint32_t *__restrict__ warp_list, uint32_t *__restrict__ n_warp) {
+    using L = Layout<POSB>;
+    extern __shared__ __align__(16) uint32_t dyn_smem[];  // per warp: a pair of u16 histograms, then MedSmem
+    constexpr int PER_WARP = L::BINS + (int)(sizeof(MedSmem) / 4);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *hist = dyn_smem + (size_t)warp * PER_WARP;
+    MedSmem *med = reinterpret_cast<MedSmem *>(hist + L::BINS);
+    const uint32_t n = *n_medium;  // written by the register kernel (an earlier launch)
+    for (uint32_t k = blockIdx.x * WARPS_PER_CTA + warp; k < n; k += gridDim.x * WARPS_PER_CTA) {
+        const uint32_t u = medium_list[k];
+        const ResolvedUnit ru = res[u];
+        const bool ok = medium_unit<POSB>(R, P, ru.col, ru.meta, ru.len, ins_seq + ru.ins_off, ru.lo, ru.hi, ru.stop, ru.tid, med, hist, hist + L::BINS / 2, out + u);
+        if (!ok && lane == 0) warp_list[atomicAdd(n_warp, 1u)] = u;  // its record keeps VFK_ST_DEFERRED
+        __syncwarp();
+    }
+}
+
+// dynamic shared memory of the register kernel, per warp
+template <int POSB>
+struct WarpSmem {
+    static constexpr bool HIST_HERE = POSB <= 512;  // per-warp histograms (and with them the medium path) fit next to four CTAs per SM
+    static constexpr int HIST_WORDS = HIST_HERE ? Layout<POSB>::BINS : 0;  // two slots of BINS / 2 words
+    static constexpr int WORDS_PER_WARP = HIST_WORDS;
+    static constexpr size_t BYTES = (size_t)WARPS_PER_CTA * WORDS_PER_WARP * 4;
+};
+
 // INWARP = true: overlap partners are found in registers (pair_in_registers); false (debug hook, VFK_DEBUG_LINK_ALL=1 at
 // vfk_create): the link kernels have run over every unit and the partners come from R.mate, as on the list path.
 template <int POSB, bool INWARP>
@@ -526,15 +761,16 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, VFK_MIN_CTAS)
 pileup_warp_kernel(const __grid_constant__ ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_units, const uint8_t *__restrict__ ins_seq,
                    const __grid_constant__ vfk_params P, vfk_counts *__restrict__ out, unsigned long long *__restrict__ work_counter,
                    uint32_t *__restrict__ block_list, uint32_t *__restrict__ n_block, uint32_t *__restrict__ warp_list,
-                   uint32_t *__restrict__ n_warp, const uint32_t *__restrict__ batch_status) {
+                   uint32_t *__restrict__ n_warp, uint32_t *__restrict__ medium_list, uint32_t *__restrict__ n_medium,
+                   const uint32_t *__restrict__ batch_status) {
     using L = Layout<POSB>;
-    constexpr bool HIST_HERE = POSB <= 512;  // per-warp histograms fit the static shared memory
-    constexpr int HIST_WORDS = HIST_HERE ? L::BINS : 1;  // two slots of BINS / 2 words
+    constexpr bool HIST_HERE = WarpSmem<POSB>::HIST_HERE;
     __shared__ uint32_t stage_all[WARPS_PER_CTA][32];
-    __shared__ __align__(16) uint32_t hist_all[WARPS_PER_CTA][HIST_WORDS];
+    extern __shared__ __align__(16) uint32_t dyn_smem[];  // per warp: a pair of u16 histograms (WarpSmem)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t *stage = stage_all[warp];
+    uint32_t *hist = dyn_smem + (size_t)warp * WarpSmem<POSB>::WORDS_PER_WARP;
     const int64_t n_warps = (int64_t)gridDim.x * WARPS_PER_CTA;
     int64_t last_base = 0;
     const uint32_t bad = *batch_status;  // prep_kernel has finished: VFK_ST_BADBATCH or 0
@@ -585,6 +821,15 @@ pileup_warp_kernel(const __grid_constant__ ReadsDev R, const ResolvedUnit *__res
             if (n_cand == 0 || bad) {
                 if (lane == 0) store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind | bad, 0u, 0u);
                 continue;
+            }
+            if constexpr (WarpSmem<POSB>::HIST_HERE && INWARP) {
+                if (n_cand > 64 && n_cand <= MED_CAP) {  // medium: its own kernel (slots of 32, per-read state parked in shared memory)
+                    if (lane == 0) {
+                        medium_list[atomicAdd(n_medium, 1u)] = (uint32_t)u;
+                        store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind | VFK_ST_DEFERRED, (uint32_t)n_cand, 0u);
+                    }
+                    continue;
+                }
             }
             if (n_cand > 64) {  // deep: handed to the histogram kernels through a device-side list
                 if (lane == 0) {
@@ -679,7 +924,7 @@ pileup_warp_kernel(const __grid_constant__ ReadsDev R, const ResolvedUnit *__res
             const bool by_histogram = __popc(m0) + __popc(m1) > 32 || __any_sync(FULL, e0.alt > 1u || e1.alt > 1u || both_lists != 0u);
             if (by_histogram) {
                 if constexpr (HIST_HERE) {
-                    reduce_by_histogram<POSB>(e0, e1, U.kind, P.include_ambiguous, hist_all[warp], hist_all[warp] + L::BINS / 2, lane, out + u, (uint32_t)n_cand);
+                    reduce_by_histogram<POSB>(e0, e1, U.kind, P.include_ambiguous, hist, hist + L::BINS / 2, lane, out + u, (uint32_t)n_cand);
                 } else {
                     if (lane == 0) {
                         warp_list[atomicAdd(n_warp, 1u)] = (uint32_t)u;
@@ -905,7 +1150,7 @@ cudaError_t launch_link(const ReadsDev &R, const vfk_params &P, const void *reso
 
 // Per-call device scratch (owned by the handle / a staging slot).
 //   counters: @0 u64 unit work counter, @8 u32 block-list length, @12 u32 warp-list length, @20 u32 batch status
-//   (VFK_ST_BADBATCH or 0), @64 256 x u32 per-SM segment counters of the list path.   lists: 2 * n_units u32.
+//   (VFK_ST_BADBATCH or 0), @24 u32 medium-list length, @64 256 x u32 per-SM segment counters of the list path.   lists: 3 * n_units u32.
 struct PileupScratch {
     void *resolved;   // n_units * 32 B
     void *counters;   // 64 B
@@ -968,15 +1213,22 @@ static cudaError_t launch_posb(ReadsDev R, const UnitsDev &V, const vfk_params &
     unsigned long long *work = (unsigned long long *)S.counters;
     uint32_t *n_block = (uint32_t *)((char *)S.counters + 8), *n_warp = (uint32_t *)((char *)S.counters + 12);
     const uint32_t *batch_status = (const uint32_t *)((char *)S.counters + 20);
-    uint32_t *block_list = S.lists, *warp_list = S.lists + V.n;
+    uint32_t *block_list = S.lists, *warp_list = S.lists + V.n, *medium_list = S.lists + 2 * V.n;
+    uint32_t *n_medium = (uint32_t *)((char *)S.counters + 24);
     cudaError_t e;
     R.mate = S.mate;
     locate_kernel<<<(unsigned)((V.n + 255) / 256), 256, 0, stream>>>(R, V, res);
     ++*launches;
     if (S.ev) cudaEventRecord(S.ev[2], stream);
     int ctas_per_sm = 0;
-    e = link_all ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pileup_warp_kernel<POSB, false>, WARPS_PER_CTA * 32, 0)
-                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pileup_warp_kernel<POSB, true>, WARPS_PER_CTA * 32, 0);
+    const size_t warp_smem = WarpSmem<POSB>::BYTES;
+    if (warp_smem > 40 * 1024) {
+        e = link_all ? cudaFuncSetAttribute(pileup_warp_kernel<POSB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem)
+                     : cudaFuncSetAttribute(pileup_warp_kernel<POSB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem);
+        if (e != cudaSuccess) return e;
+    }
+    e = link_all ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pileup_warp_kernel<POSB, false>, WARPS_PER_CTA * 32, warp_smem)
+                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pileup_warp_kernel<POSB, true>, WARPS_PER_CTA * 32, warp_smem);
     if (e != cudaSuccess) return e;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     // persistent grid: a whole number of waves, never more CTAs than there is work
@@ -986,16 +1238,29 @@ static cudaError_t launch_posb(ReadsDev R, const UnitsDev &V, const vfk_params &
     if (link_all) {
         e = launch_link(R, P, res, nullptr, nullptr, V.n, S.heads, S.n_buckets, S.next, S.column, S.claimed, S.mate, sm_count, stream, launches);
         if (e != cudaSuccess) return e;
-        pileup_warp_kernel<POSB, false><<<(unsigned)grid, WARPS_PER_CTA * 32, 0, stream>>>(R, res, V.n, V.ins_seq, P, out, work, block_list,
-                                                                                           n_block, warp_list, n_warp, batch_status);
+        pileup_warp_kernel<POSB, false><<<(unsigned)grid, WARPS_PER_CTA * 32, warp_smem, stream>>>(R, res, V.n, V.ins_seq, P, out, work, block_list,
+                                                                                           n_block, warp_list, n_warp, medium_list, n_medium, batch_status);
     } else {
-        pileup_warp_kernel<POSB, true><<<(unsigned)grid, WARPS_PER_CTA * 32, 0, stream>>>(R, res, V.n, V.ins_seq, P, out, work, block_list,
-                                                                                          n_block, warp_list, n_warp, batch_status);
+        pileup_warp_kernel<POSB, true><<<(unsigned)grid, WARPS_PER_CTA * 32, warp_smem, stream>>>(R, res, V.n, V.ins_seq, P, out, work, block_list,
+                                                                                          n_block, warp_list, n_warp, medium_list, n_medium, batch_status);
     }
     ++*launches;
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (S.ev) cudaEventRecord(S.ev[3], stream);
+    if constexpr (WarpSmem<POSB>::HIST_HERE) {
+        if (!link_all) {  // columns with 65 .. MED_CAP candidate reads (the list is empty for a 30x batch: the CTAs leave at once)
+            using L = Layout<POSB>;
+            const size_t med_smem = (size_t)WARPS_PER_CTA * (L::BINS * 4 + sizeof(MedSmem));
+            e = cudaFuncSetAttribute(medium_kernel<POSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)med_smem);
+            if (e != cudaSuccess) return e;
+            const int64_t med_grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)sm_count * 3, (V.n + WARPS_PER_CTA - 1) / WARPS_PER_CTA));
+            medium_kernel<POSB><<<(unsigned)med_grid, WARPS_PER_CTA * 32, med_smem, stream>>>(R, res, V.ins_seq, P, out, medium_list, n_medium, warp_list, n_warp);
+            ++*launches;
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+        }
+    }
     // the listed units: their windows linked, then the histogram paths -- one launch
     e = link_all ? launch_tail<POSB, false>(R, V, P, out, S, sm_count, stream, launches) : launch_tail<POSB, true>(R, V, P, out, S, sm_count, stream, launches);
     if (S.ev) cudaEventRecord(S.ev[4], stream);

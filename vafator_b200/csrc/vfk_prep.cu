@@ -43,48 +43,53 @@ __device__ __forceinline__ CigarInfo cigar_single(uint32_t w, int32_t l_qseq) { 
     else o.ev = (len == 0u || len >= 4096u || l_qseq > VFK_MAX_READ_LEN) ? EV_GENERAL : (len << 12);
     return o;
 }
-// The state machine as tables: no branch in the loop body (a walk runs with whatever lanes hold a multi-op CIGAR).
-//   op class: H 0, S 1, M/=/X 2, I/D/N 3, anything else 4 (three bits per BAM op code)
-//   NEXT[class]: three bits per state
-constexpr uint64_t cigar_class_lut() {
-    uint64_t t = 0;
-    for (int op = 0; op < 16; ++op) {
-        const uint64_t c = op == OP_H ? 0 : op == OP_S ? 1 : (op == OP_M || op == OP_EQ || op == OP_X) ? 2 : (op == OP_I || op == OP_D || op == OP_N) ? 3 : 4;
-        t |= c << (3 * op);
-    }
-    return t;
-}
+// The state machine as a table in constant memory: no branch in a step (a walk runs with whatever lanes hold a multi-op CIGAR).
+//   CIGAR_STEP[op]: bits 0-23 the next state for each of the eight states (three bits each), bit 24 the op consumes the
+//   reference, bit 25 it is a soft clip, bit 26 an aligned block (M = X), bit 27 an event (I D N)
 constexpr uint32_t pack_states(int s0, int s1, int s2, int s3, int s4, int s5, int s6, int s7) {
     return (uint32_t)s0 | (uint32_t)s1 << 3 | (uint32_t)s2 << 6 | (uint32_t)s3 << 9 | (uint32_t)s4 << 12 | (uint32_t)s5 << 15 | (uint32_t)s6 << 18 | (uint32_t)s7 << 21;
 }
-constexpr uint64_t CIGAR_CLASS = cigar_class_lut();
-constexpr uint32_t NEXT_H = pack_states(0, 7, 6, 7, 6, 6, 6, 7), NEXT_S = pack_states(1, 7, 5, 7, 5, 7, 7, 7);
-constexpr uint32_t NEXT_M = pack_states(2, 2, 7, 4, 7, 7, 7, 7), NEXT_E = pack_states(7, 7, 3, 7, 7, 7, 7, 7);
+constexpr uint32_t STEP_REF = 1u << 24, STEP_CLIP = 1u << 25, STEP_BLOCK = 1u << 26, STEP_EVENT = 1u << 27;
+constexpr uint32_t NEXT_H = pack_states(0, 7, 6, 7, 6, 6, 6, 7), NEXT_S = pack_states(1, 7, 5, 7, 5, 7, 7, 7) | STEP_CLIP;
+constexpr uint32_t NEXT_M = pack_states(2, 2, 7, 4, 7, 7, 7, 7) | STEP_BLOCK | STEP_REF, NEXT_E = pack_states(7, 7, 3, 7, 7, 7, 7, 7) | STEP_EVENT;
+constexpr uint32_t NEXT_NONE = pack_states(7, 7, 7, 7, 7, 7, 7, 7);
+__constant__ uint32_t CIGAR_STEP[16] = {
+    /* M */ NEXT_M, /* I */ NEXT_E, /* D */ NEXT_E | STEP_REF, /* N */ NEXT_E | STEP_REF, /* S */ NEXT_S, /* H */ NEXT_H, /* P */ NEXT_NONE,
+    /* = */ NEXT_M, /* X */ NEXT_M, NEXT_NONE, NEXT_NONE, NEXT_NONE, NEXT_NONE, NEXT_NONE, NEXT_NONE, NEXT_NONE};
+struct WalkState {
+    uint32_t span, lead, m1, ev, elen, state;
+};
+__device__ __forceinline__ void cigar_step(WalkState &s, uint32_t w) {
+    const uint32_t op = w & 15u, len = w >> 4;
+    const uint32_t t = CIGAR_STEP[op];
+    s.span += (t & STEP_REF) ? len : 0u;
+    uint32_t next = (t >> (3u * s.state)) & 7u;
+    if ((t & (STEP_BLOCK | STEP_EVENT)) && len == 0u) next = 7u;  // an empty block / event is not of this shape
+    s.lead = ((t & STEP_CLIP) && s.state == 0u) ? len : s.lead;
+    s.m1 = ((t & STEP_BLOCK) && s.state <= 1u) ? len : s.m1;
+    const bool event = next == 3u;  // I / D / N right after the first block
+    s.ev = event ? (op == OP_I ? (uint32_t)EVK_INS : op == OP_D ? (uint32_t)EVK_DEL : (uint32_t)EVK_SKIP) : s.ev;
+    s.elen = event ? len : s.elen;
+    s.state = next;
+}
+// n >= 2 ops.  The first four are requested together and stepped through without a loop (nearly every multi-op CIGAR has two
+// to four ops; a lane with fewer just sits out the steps it does not need), the rest in a loop.
 __device__ __forceinline__ CigarInfo cigar_walk(const uint32_t *__restrict__ c, int n, int32_t l_qseq) {
-    CigarInfo o;
-    uint32_t span = 0, lead = 0, m1 = 0, ev = EVK_NONE, elen = 0;
-    uint32_t state = 0;
-    // the first four ops are requested together (one round trip; nearly every multi-op CIGAR has two to four ops)
     const uint32_t w0 = n > 0 ? __ldg(c) : 0u, w1 = n > 1 ? __ldg(c + 1) : 0u, w2 = n > 2 ? __ldg(c + 2) : 0u, w3 = n > 3 ? __ldg(c + 3) : 0u;
+    WalkState s;
+    s.span = s.lead = s.m1 = s.elen = s.state = 0u;
+    s.ev = EVK_NONE;
+    if (n > 0) cigar_step(s, w0);
+    if (n > 1) cigar_step(s, w1);
+    if (n > 2) cigar_step(s, w2);
+    if (n > 3) cigar_step(s, w3);
 #pragma unroll 1
-    for (int k = 0; k < n; ++k) {
-        const uint32_t w = k == 0 ? w0 : k == 1 ? w1 : k == 2 ? w2 : k == 3 ? w3 : __ldg(c + k);
-        const uint32_t op = w & 15u, len = w >> 4;
-        span += ((0x18Du >> op) & 1u) ? len : 0u;  // M D N = X consume the reference
-        const uint32_t cls = (uint32_t)(CIGAR_CLASS >> (3u * op)) & 7u;
-        const uint32_t table = cls == 0u ? NEXT_H : cls == 1u ? NEXT_S : cls == 2u ? NEXT_M : cls == 3u ? NEXT_E : 0xFFFFFFu;
-        uint32_t next = (table >> (3u * state)) & 7u;
-        if (cls >= 2u && len == 0u) next = 7u;            // an empty block / event is not of this shape
-        lead = (cls == 1u && state == 0u) ? len : lead;
-        m1 = (cls == 2u && state <= 1u) ? len : m1;
-        const bool event = next == 3u;                    // I / D / N right after the first block
-        ev = event ? (op == OP_I ? EVK_INS : op == OP_D ? EVK_DEL : EVK_SKIP) : ev;
-        elen = event ? len : elen;
-        state = next;
-    }
-    o.span = span;
-    const bool shaped = (state == 2u || (state >= 4u && state != 7u)) && m1 != 0u && m1 < 4096u && lead < 4096u && elen < 64u && l_qseq <= VFK_MAX_READ_LEN;
-    o.ev = shaped ? (lead | (m1 << 12) | (ev << 24) | (elen << 26)) : EV_GENERAL;
+    for (int k = 4; k < n; ++k) cigar_step(s, __ldg(c + k));
+    CigarInfo o;
+    o.span = s.span;
+    const bool shaped = (s.state == 2u || (s.state >= 4u && s.state != 7u)) && s.m1 != 0u && s.m1 < 4096u && s.lead < 4096u && s.elen < 64u &&
+                        l_qseq <= VFK_MAX_READ_LEN;
+    o.ev = shaped ? (s.lead | (s.m1 << 12) | (s.ev << 24) | (s.elen << 26)) : EV_GENERAL;
     return o;
 }
 __device__ __forceinline__ CigarInfo cigar_info(const uint32_t *__restrict__ c, int n, int32_t l_qseq) {
@@ -324,7 +329,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const int64_t *__res
     const int64_t per = (n_blocks + SCAN_THREADS - 1) / SCAN_THREADS;
     const int64_t k0 = (int64_t)t * per, k1 = min(k0 + per, n_blocks);
     long long v = LLONG_MIN;
-    for (int64_t k = k0; k < k1; ++k) v = max(v, (long long)__ldg(blk_max + k));
+    {
+        int64_t k = k0;
+        for (; k + 4 <= k1; k += 4) {  // four independent loads in flight
+            const long long a = __ldg(blk_max + k), b = __ldg(blk_max + k + 1), c = __ldg(blk_max + k + 2), d = __ldg(blk_max + k + 3);
+            v = max(max(v, max(a, b)), max(c, d));
+        }
+        for (; k < k1; ++k) v = max(v, (long long)__ldg(blk_max + k));
+    }
     long long incl = v;  // inclusive scan of the run maxima: warp, then the warp totals
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
