@@ -15,8 +15,9 @@ Workloads (BASELINE.json configs; --config):
   C4            8 samples x 60x over a shared target set (--tiles, default 40 000 = 10 Mbp: 1/5 of the 50 Mbp of SURVEY.md 8d,
                 stated), per-sample purity + 1 000-segment copy-number BED, 2 % multiallelic sites.
   C5            1000x amplicon panel: 5 000 amplicons, ~9 M reads, ~50 k variants (the histogram path).
-One *step* = one pass of the hot path over every batch of the rank (a rank's shard is processed as a few interval
-sub-batches so that the copies of one overlap the kernels of the previous one).
+One *step* = one pass of the hot path over the rank's shard of every BAM.  Resident in HBM that is ONE call per BAM shard; end
+to end the same shard is fed as a few interval sub-batches (slices of the same host arrays, sharding.plan_shards) so that the
+copies of one overlap the kernels of the previous one.
 
   value     units/s with the canonical batches resident in HBM: read preparation + locate + pileup + epilogue kernels
             (CUDA events around the K steps, max over ranks)
@@ -182,32 +183,51 @@ def unit_cuts(n: int, k: int):
     return sharding.unit_cuts(n, k)
 
 
-def build_batches(w: Workload, rank: int, world: int, pinned: bool, cap_units: int = None):
-    """This rank's share of the ONE input: units [cut[rank], cut[rank+1]) of every BAM, as `w.sub` interval sub-batches per BAM;
-    each sub-batch holds the canonical reads of the tiles its columns can reach.  cap_units: only the first units (CPU sample)."""
-    from vafator_b200 import synth
+def build_batches(w: Workload, rank: int, world: int, pinned: bool, cap_units: int = None, sub: int = 1, params=None):
+    """This rank's share of the ONE input: units [cut[rank], cut[rank+1]) of every BAM with the canonical reads of the tiles their
+    columns can reach -- one batch per BAM.  sub > 1: also the same shard cut into `sub` interval sub-batches (slices of the same
+    host arrays; only the re-based pool offsets are new arrays), for the end-to-end loop.  cap_units: only the first units
+    (CPU sample).  Returns (batches, sub_batches, n_units)."""
+    from vafator_b200 import synth, device
     from dataclasses import replace
     from vafator_b200 import sharding
     units_all, stop_all = w.units_all, w.stop_all
     n = units_all.n_units if cap_units is None else min(cap_units, units_all.n_units)
     cuts = unit_cuts(n, world)
     lo, hi = cuts[rank], cuts[rank + 1]
-    sub_cuts = [lo + c for c in unit_cuts(hi - lo, w.sub)]
-    batches = []
+    batches, subs = [], []
     t0 = time.time()
     for sample, cfg in w.samples:
         eaf_all = w.eaf(sample, w.recs)
-        for a, b in zip(sub_cuts[:-1], sub_cuts[1:]):
-            if b <= a:
-                continue
-            units = sharding.slice_units(units_all, a, b)  # `rec` keeps indexing the records of the whole input
-            g0, gc = synth.tile_range(cfg, int(units.tid[0]), int(units.pos[0]), int(units.tid[-1]), int(units.pos[-1]))
-            batch = synth.reads(replace(cfg, g_first=g0, g_count=gc), pinned=pinned)
-            batches.append(dict(sample=sample, batch=batch, units=units, stop=np.ascontiguousarray(stop_all[a:b]),
-                                eaf=np.ascontiguousarray(eaf_all[units.rec], np.float64), recs=w.recs))
-    log("[bench] rank %d: %s units [%d, %d) of %d, %d batches, %d reads, %.1f s" % (
-        rank, w.name, lo, hi, n, len(batches), sum(b["batch"].n_reads for b in batches), time.time() - t0))
-    return batches, n
+        if hi <= lo:
+            continue
+        units = sharding.slice_units(units_all, lo, hi)  # `rec` keeps indexing the records of the whole input
+        g0, gc = synth.tile_range(cfg, int(units.tid[0]), int(units.pos[0]), int(units.tid[-1]), int(units.pos[-1]))
+        batch = synth.reads(replace(cfg, g_first=g0, g_count=gc), pinned=pinned)
+        stop = np.ascontiguousarray(stop_all[lo:hi])
+        eaf = np.ascontiguousarray(eaf_all[units.rec], np.float64)
+        batches.append(dict(sample=sample, batch=batch, units=units, stop=stop, eaf=eaf, recs=w.recs))
+        if sub > 1:
+            for sh in sharding.plan_shards(batch, units, sub, device.read_passes(batch, params), stop):
+                subs.append(dict(sample=sample, batch=sharding.slice_reads(batch, sh.read_lo, sh.read_hi),
+                                 units=sharding.slice_units(units, sh.unit_lo, sh.unit_hi), stop=np.ascontiguousarray(stop[sh.unit_lo:sh.unit_hi]),
+                                 eaf=np.ascontiguousarray(eaf[sh.unit_lo:sh.unit_hi]), recs=w.recs))
+    log("[bench] rank %d: %s units [%d, %d) of %d, %d batches (%d sub-batches), %d reads, %.1f s" % (
+        rank, w.name, lo, hi, n, len(batches), len(subs), sum(b["batch"].n_reads for b in batches), time.time() - t0))
+    return batches, (subs if sub > 1 else batches), n
+
+
+def host_view(b, pinned: bool):
+    """HostReads of a sub-batch whose per-read arrays are slices of a page-locked parent batch: only the re-based pool offsets
+    (new arrays) are copied into page-locked memory."""
+    from vafator_b200 import device
+    h = device.HostReads(b["batch"], pinned=False)
+    if pinned and not h.implicit_offsets:  # (implicit offsets: the arrays stay on the host, nothing reads them)
+        for k in ("cigar_off", "seq_off", "qual_off"):
+            p = device._empty(h.arrays[k].shape[0], h.arrays[k].dtype, True)
+            p[:] = h.arrays[k]
+            h.arrays[k] = p
+    return h
 
 
 def _epilogue_chunk(args):
@@ -234,7 +254,7 @@ def run_cpu_arm(w: Workload, repeats: int = 1):
     import multiprocessing as mp
     from oracle import c_oracle
     cores = os.cpu_count() or 1
-    batches, n_units_sample = build_batches(w, 0, 1, pinned=False, cap_units=w.cpu_units)
+    batches, _, n_units_sample = build_batches(w, 0, 1, pinned=False, cap_units=w.cpu_units)
     tid_of = {c: i for i, c in enumerate(w.contigs)}
     prm = c_oracle.params(min_mapq=MIN_MAPQ, min_baseq=MIN_BASEQ)
     c_oracle.lib()
@@ -401,7 +421,7 @@ def main():
     dev = device.Device(local_rank)
     params = device.make_params(min_mapq=MIN_MAPQ, min_baseq=MIN_BASEQ, include_ambiguous=True)
     w = Workload(args.config, args)
-    batches, units_total = build_batches(w, rank, world, pinned=not args.no_e2e)
+    batches, subs, units_total = build_batches(w, rank, world, pinned=not args.no_e2e, sub=1 if args.no_e2e else w.sub, params=params)
     for b in batches:
         b["host"] = device.HostReads(b["batch"])           # the canonical arrays, as generated (page-locked)
         b["dreads"] = dev.upload_reads(b["host"])          # ... and the same arrays resident in HBM, verbatim
@@ -409,6 +429,9 @@ def main():
         b["deaf"] = torch.from_numpy(b["eaf"]).to(dev.device)
         b["counts"] = dev.alloc_counts(b["units"].n_units)
         b["stats"] = dev.alloc_stats(b["units"].n_units)
+    for b in subs:
+        if "host" not in b:
+            b["host"] = host_view(b, pinned=True)
     torch.cuda.synchronize()
     units_per_step = sum(b["units"].n_units for b in batches)
     reads_rank = sum(b["batch"].n_reads for b in batches)
@@ -463,13 +486,13 @@ def main():
     # ---- end to end: page-locked canonical host arrays -> results on the host, through vfk_annotate_host_async ----
     e2e = None
     if not args.no_e2e:
-        c_out = [np.empty(b["units"].n_units, device.COUNTS_DTYPE) for b in batches]
-        s_out = [np.empty(b["units"].n_units, device.STATS_DTYPE) for b in batches]
+        c_out = [np.empty(b["units"].n_units, device.COUNTS_DTYPE) for b in subs]
+        s_out = [np.empty(b["units"].n_units, device.STATS_DTYPE) for b in subs]
 
         def e2e_step():
             # two batches in flight: the library double-buffers, the copies of one batch overlap the kernels of the previous
             tickets = []
-            for k, b in enumerate(batches):
+            for k, b in enumerate(subs):
                 if k >= 2:
                     dev.wait(tickets[k - 2])
                 tickets.append(dev.annotate_host_async(b["host"], b["units"], b["stop"], params, b["eaf"], FPR, ERROR_RATE, c_out[k], s_out[k]))
@@ -489,11 +512,18 @@ def main():
         dt_e2e = (time.perf_counter() - t0) / n_e2e
         rx_rate = rx.stop()
         ts1 = dev.transfer_stats()
-        for k in range(len(batches)):
-            for f in ("dp", "ac_alt", "ac_ref", "med2"):
-                assert np.array_equal(c_out[k][f], c_host[k][f]), f
+        # the sub-batches of a BAM shard, put back in unit order, must equal the resident call on the whole shard
+        at = 0
+        for c in c_host:
+            n_here = 0
+            while n_here < len(c):
+                for f in ("dp", "ac_alt", "ac_ref", "med2"):
+                    assert np.array_equal(c_out[at][f], c[f][n_here:n_here + len(c_out[at])]), f
+                n_here += len(c_out[at])
+                at += 1
+        assert at == len(subs)
         staged = (ts1["staged_bytes"] - ts0["staged_bytes"]) / n_e2e
-        zero_copy = (ts1["zero_copy_batches"] - ts0["zero_copy_batches"]) / (n_e2e * len(batches))
+        zero_copy = (ts1["zero_copy_batches"] - ts0["zero_copy_batches"]) / (n_e2e * len(subs))
         d2h = (ts1["d2h_bytes"] - ts0["d2h_bytes"]) / n_e2e
         if rx_rate is not None:
             h2d, h2d_how = rx_rate * dt_e2e, "NVML PCIe RX counter sampled over the timed region x step time"
@@ -551,11 +581,11 @@ def main():
             "unit": "units/s", "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32/f64", "data": "synthetic",
             "config": {"workload": w.text, "units_total": int(units_step_all), "reads_total": int(reads_all),
-                       "units_per_step_rank0": units_per_step, "batches_per_step_rank0": len(batches),
+                       "units_per_step_rank0": units_per_step, "batches_per_step_rank0": len(batches), "e2e_sub_batches_rank0": len(subs),
                        "boundary": "canonical columnar read batch (decoded BAM fields, untouched) + variant units in; counts + statistics out. "
                                    "Read preparation (spans, position index, CIGAR shapes, filter, mate pairing) runs on the device inside every step",
                        "mean_depth_raw": round(d_raw, 2), "mean_candidates": round(n_cand, 2),
-                       "l2": "inputs (%.1f GB of canonical read arrays on rank 0) exceed L2; the batches of a step alternate" % (
+                       "l2": "inputs (%.1f GB of canonical read arrays on rank 0) exceed L2 many times over" % (
                            sum(b["host"].nbytes() for b in batches) / 1e9),
                        "sharding": "ONE input; units cut into %d equal interval shards (sharding.unit_cuts), shard k -> rank k, each rank holds the "
                                    "reads its columns can reach; no collective on the data path" % world,

@@ -62,6 +62,10 @@ enum {
  *              base q of read i = nibble q of seq[seq_off[i] ...]
  *   qual       one byte per base at qual[qual_off[i] + q]
  *   mtid/mpos/isize   mate contig, mate start, template length (RNEXT / PNEXT / TLEN)
+ *   cigar_off / seq_off / qual_off   where read i's CIGAR ops / packed bases / qualities start in their pools.  All three may be
+ *              NULL: the pools are then contiguous in read order (what a decoder that appends record by record produces) and
+ *              the offsets -- prefix sums of n_cigar, (l_qseq + 1) / 2 and l_qseq -- are derived on the device (the host entry
+ *              point then moves 8 bytes per read less and reads no offset array over the bus).
  *   qname_id   any 64-bit id that is equal iff the read names are equal
  *   qname_hash khash X31 of the read name (htslib's overlap tie-break hashes it)
  * vfk_pileup: every pointer is a DEVICE pointer.  vfk_annotate_host: HOST pointers.                    */

@@ -383,3 +383,27 @@ def test_read_preparation_words(dev):
             simple = len(ops) == 1 and ops[0][1] in "M=X" and ops[0][0] == lq
             word = 0 if simple else _one_event_word(ops, lq)
             assert shape[i] == (0xFFFFFFFF if word is None else word), (i, ops, hex(int(shape[i])), word)
+
+
+def test_implicit_pool_offsets(dev):
+    """A batch with contiguous pools may leave cigar_off / seq_off / qual_off NULL (include/vfk.h): the device derives them.  Same
+    records out as with the explicit arrays, through the host entry (pageable and page-locked) and the device-pointer entry."""
+    cfg = synth.wgs(contig_len=700_000, n_contigs=2, multiallelic_pct=5)
+    batch, recs, units, stop, ounits = _setup(cfg)
+    params = device.make_params(min_mapq=1, min_baseq=30)
+    eaf = np.full(units.n_units, 0.4)
+    ref = dev.annotate_host(device.host_reads(batch, implicit_offsets=False), units, stop, params, eaf, 5e-7, 1e-3)
+    for pinned in (False, True):
+        got = dev.annotate_host(device.host_reads(batch, pinned=pinned, implicit_offsets=True), units, stop, params, eaf, 5e-7, 1e-3)
+        assert np.array_equal(got[0].view(np.uint8), ref[0].view(np.uint8))
+        assert np.array_equal(got[1].view(np.uint8), ref[1].view(np.uint8), equal_nan=False) or np.array_equal(got[1]["k"], ref[1]["k"])
+    # device-pointer entry: explicit offsets resident vs NULL
+    dreads = dev.upload_reads(device.host_reads(batch, implicit_offsets=False))
+    want = dev.to_host(dev.pileup(dreads, dev.upload_units(units, stop), params), device.COUNTS_DTYPE, units.n_units)
+    dreads.c.cigar_off = dreads.c.seq_off = dreads.c.qual_off = None
+    got = dev.to_host(dev.pileup(dreads, dev.upload_units(units, stop), params), device.COUNTS_DTYPE, units.n_units)
+    assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
+    # one of the three missing: refused
+    dreads.c.cigar_off = dreads.t["cigar_off"].data_ptr()
+    with pytest.raises(ValueError):
+        dev.pileup(dreads, dev.upload_units(units, stop), params)

@@ -102,3 +102,27 @@ def test_cabi_library_exports_every_declared_symbol():
     assert np.dtype(device.COUNTS_DTYPE).itemsize == 80
     sass = subprocess.run(["cuobjdump", "-lelf", libvfk], capture_output=True, text=True).stdout
     assert "sm_100a" in sass
+
+
+def test_decoders_write_contiguous_pools(tmp_path):
+    """ReadBatch.contiguous (set by the synthetic generator and the BAM decoder) promises that the three pool offset arrays are the
+    prefix sums of the lengths -- the condition under which the host entry point hands them over as NULL (include/vfk.h) and
+    slices keep the property."""
+    from vafator_b200 import bamio, sharding, synth
+    cfg = synth.wgs(contig_len=200_000, n_contigs=2)
+    b = synth.reads(cfg)
+    p = tmp_path / "c.bam"
+    bamio.write_bam_batch(str(p), b)
+    decoded = bamio.BamFile(str(p), use_index=False).read_batch()
+    for batch in (b, decoded, sharding.slice_reads(b, 1000, 5000)):
+        assert batch.contiguous
+        n = batch.n_reads
+        lq = batch.l_qseq.astype(np.int64)
+        assert np.array_equal(batch.cigar_off, np.cumsum(batch.n_cigar.astype(np.int64)) - batch.n_cigar)
+        assert np.array_equal(batch.seq_off, np.cumsum((lq + 1) // 2) - (lq + 1) // 2)
+        assert np.array_equal(batch.qual_off, np.cumsum(lq) - lq)
+        assert len(batch.cigar) == int(batch.n_cigar.sum()) and len(batch.qual) == int(lq.sum()) and n > 0
+    hr = device.host_reads(b)
+    c = hr.c_struct()
+    assert hr.implicit_offsets and not c.cigar_off and not c.seq_off and not c.qual_off  # NULL on the host entry ...
+    assert device.host_reads(b, implicit_offsets=False).c_struct().cigar_off           # ... unless asked otherwise

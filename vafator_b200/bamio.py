@@ -85,7 +85,7 @@ class BamFile:
             setattr(s, k, a.ctypes.data)
         _dev._io_check(self._lib.vfkio_bam_fill(h, C.byref(s)))
         arr["cigar"], arr["seq"], arr["qual"] = arr["cigar"][:plan.n_cigar], arr["seq"][:plan.n_seq_bytes], arr["qual"][:plan.n_qual_bytes]
-        return ReadBatch(contigs=list(self.contigs), contig_lengths=self.lengths, **arr)
+        return ReadBatch(contigs=list(self.contigs), contig_lengths=self.lengths, contiguous=True, **arr)  # vfkio_bam_fill: prefix-sum offsets
 
     def read_batch(self, regions: Optional[Sequence[tuple]] = None) -> ReadBatch:
         """regions: [(contig, start, stop)] 0-based half open, any order; overlapping ones are merged.  A read

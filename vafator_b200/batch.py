@@ -76,6 +76,8 @@ class ReadBatch:
     qname_hash: np.ndarray
     contig_lengths: Optional[np.ndarray] = None
     pinned: bool = False  # the arrays already live in page-locked memory (bamio / synth with pinned=True)
+    contiguous: bool = False  # the CIGAR / sequence / quality pools are contiguous in read order (a decoder that appends record by
+    #                           record produces that): the three offset arrays are prefix sums of the lengths and need not travel
 
     @property
     def n_reads(self) -> int:

@@ -22,6 +22,8 @@ struct PileupScratch {
 };
 cudaError_t launch_prep(const ReadsDev &R, uint2 *ee_out, int64_t *chunk_max, int64_t *blk_max, int64_t *blk_incl, uint32_t *batch_status,
                         cudaStream_t stream, int *launches);
+cudaError_t launch_offsets(const ReadsDev &R, long long *blk_sums, int64_t *cigar_off, int64_t *seq_off, int64_t *qual_off, cudaStream_t stream,
+                           int *launches);
 cudaError_t launch_pileup(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, int max_l_qseq, vfk_counts *out,
                           const PileupScratch &S, int sm_count, cudaStream_t stream, int *launches, bool link_all);
 cudaError_t launch_locate_only(const ReadsDev &R, const UnitsDev &V, void *resolved, cudaStream_t stream, int *launches);
@@ -99,6 +101,7 @@ struct PinBuf {  // page-locked host scratch
 // lists and the link scratch.  The bucket heads and the claim bitmap are kept clean by the link kernels themselves
 // (set once when (re)allocated).
 struct Work {
+    DevBuf off_c, off_s, off_q, off_sums;  // derived pool offsets of a batch that leaves them NULL
     DevBuf ee, chunk_max, blk_max, blk_incl, resolved, lists, next, column, claimed, mate, heads;
     uint32_t n_buckets = 0;
     void *counters = nullptr;  // COUNTER_BYTES, layout in vfk_pileup.cu (PileupScratch)
@@ -135,7 +138,7 @@ struct Work {
         return s;
     }
     void release() {
-        DevBuf *bufs[] = {&ee, &chunk_max, &blk_max, &blk_incl, &resolved, &lists, &next, &column, &claimed, &mate, &heads};
+        DevBuf *bufs[] = {&off_c, &off_s, &off_q, &off_sums, &ee, &chunk_max, &blk_max, &blk_incl, &resolved, &lists, &next, &column, &claimed, &mate, &heads};
         for (DevBuf *b : bufs) b->release();
         n_buckets = 0;
         if (counters) cudaFree(counters);
@@ -279,9 +282,12 @@ static int check_batches(const vfk_read_batch *r, const vfk_variant_batch *v, co
     if (r->n_cigar_words >= ((int64_t)1 << 32)) return fail(VFK_EUNSUPPORTED, "CIGAR pool exceeds 2^32 words: split the batch");
     if (r->max_l_qseq > VFK_MAX_READ_LEN) return fail(VFK_EUNSUPPORTED, "read longer than VFK_MAX_READ_LEN");
     if (!r->contig_off) return fail(VFK_EINVAL, "contig_off is NULL");
-    if (r->n_reads > 0 && (!r->pos || !r->flag || !r->mapq || !r->l_qseq || !r->n_cigar || !r->cigar_off || !r->seq_off || !r->qual_off ||
-                           !r->cigar || !r->seq || !r->qual || !r->mtid || !r->mpos || !r->isize || !r->qname_id || !r->qname_hash))
+    if (r->n_reads > 0 && (!r->pos || !r->flag || !r->mapq || !r->l_qseq || !r->n_cigar || !r->cigar || !r->seq || !r->qual || !r->mtid ||
+                           !r->mpos || !r->isize || !r->qname_id || !r->qname_hash))
         return fail(VFK_EINVAL, "read batch has a NULL array");
+    // the three pool offset arrays: all given, or all NULL (pools contiguous in read order: the offsets are derived on the device)
+    if (r->n_reads > 0 && ((!r->cigar_off) != (!r->seq_off) || (!r->cigar_off) != (!r->qual_off)))
+        return fail(VFK_EINVAL, "cigar_off / seq_off / qual_off must be all given or all NULL");
     if (v->n_units > 0 && (!v->tid || !v->pos || !v->meta || !v->length || !v->seq_off || !v->ins_seq))
         return fail(VFK_EINVAL, "variant batch has a NULL array");
     return VFK_OK;
@@ -305,7 +311,17 @@ static void to_dev(const vfk_read_batch *r, const vfk_variant_batch *v, const Wo
 }
 
 // read preparation on `st`: counters zeroed, spans / shapes / position index derived (R's canonical pointers are device visible)
-static int enqueue_prep(vfk_handle *h, Work &w, const vfk::ReadsDev &R, cudaStream_t st, int *launches) {
+static int enqueue_prep(vfk_handle *h, Work &w, vfk::ReadsDev &R, cudaStream_t st, int *launches) {
+    if (!R.cigar_off && R.n_reads > 0) {  // implicit pool offsets (check_batches: then all three are NULL)
+        const size_t nr = (size_t)R.n_reads;
+        int rc;
+        if ((rc = w.off_c.reserve(nr * 8)) || (rc = w.off_s.reserve(nr * 8)) || (rc = w.off_q.reserve(nr * 8)) ||
+            (rc = w.off_sums.reserve((nr / 1024 + 1) * 24)))
+            return rc;
+        cudaError_t e = vfk::launch_offsets(R, (long long *)w.off_sums.p, (int64_t *)w.off_c.p, (int64_t *)w.off_s.p, (int64_t *)w.off_q.p, st, launches);
+        if (e != cudaSuccess) return fail(VFK_ECUDA, "offsets launch: %s", cudaGetErrorString(e));
+        R.cigar_off = (const int64_t *)w.off_c.p; R.seq_off = (const int64_t *)w.off_s.p; R.qual_off = (const int64_t *)w.off_q.p;
+    }
     if (h->timing) {
         for (cudaEvent_t &e : w.tev)
             if (!e) CU(cudaEventCreate(&e));
@@ -526,11 +542,12 @@ extern "C" int vfk_annotate_host_async(vfk_handle *h, const vfk_read_batch *read
     // ---- how the read arrays reach the kernels.  Page-locked arrays: only what the position index is built from (starts,
     // CIGARs, read lengths: ~25 bytes per read) is copied; flags, qualities, bases, mate fields and name ids are read in place
     // over PCIe, and only for the reads that overlap a variant column.  Pageable arrays: everything is staged.
+    const bool implicit = !reads->cigar_off;  // pool offsets derived on the device: nothing of them crosses the bus
     const void *z[11] = {pinned_alias(reads->flag), pinned_alias(reads->mapq), pinned_alias(reads->seq_off), pinned_alias(reads->qual_off),
                          pinned_alias(reads->seq), pinned_alias(reads->qual), pinned_alias(reads->mtid), pinned_alias(reads->mpos),
                          pinned_alias(reads->isize), pinned_alias(reads->qname_id), pinned_alias(reads->qname_hash)};
     bool zero_copy = !h->stage_all && nr > 0;
-    for (const void *p : z) zero_copy = zero_copy && p != nullptr;
+    for (int k = 0; k < 11; ++k) zero_copy = zero_copy && (z[k] != nullptr || (implicit && (k == 2 || k == 3)));
     if (zero_copy) {
         // In place pays per (unit, candidate read) pair -- about 256 bytes cross the bus for each (a dozen arrays, 64-byte requests) --
         // a bulk copy pays per read.  Sparse variant sets against 30x / 60x reads touch a fifth of the batch: in place.  A deep
@@ -544,7 +561,7 @@ extern "C" int vfk_annotate_host_async(vfk_handle *h, const vfk_read_batch *read
     STAGE(S.contig, reads->contig_off, (size_t)(reads->n_contigs + 1) * sizeof(int64_t), dr.contig_off);
     STAGE(S.pos, reads->pos, (size_t)nr * 4, dr.pos);
     STAGE(S.n_cigar, reads->n_cigar, (size_t)nr * 4, dr.n_cigar);
-    STAGE(S.cigar_off, reads->cigar_off, (size_t)nr * 8, dr.cigar_off);
+    if (!implicit) STAGE(S.cigar_off, reads->cigar_off, (size_t)nr * 8, dr.cigar_off);
     STAGE(S.l_qseq, reads->l_qseq, (size_t)nr * 4, dr.l_qseq);
     STAGE(S.cigar, reads->cigar, (size_t)reads->n_cigar_words * 4, dr.cigar);
     if (zero_copy) {
@@ -555,8 +572,10 @@ extern "C" int vfk_annotate_host_async(vfk_handle *h, const vfk_read_batch *read
     } else {
         STAGE(S.flag, reads->flag, (size_t)nr * 2, dr.flag);
         STAGE(S.mapq, reads->mapq, (size_t)nr, dr.mapq);
-        STAGE(S.seq_off, reads->seq_off, (size_t)nr * 8, dr.seq_off);
-        STAGE(S.qual_off, reads->qual_off, (size_t)nr * 8, dr.qual_off);
+        if (!implicit) {
+            STAGE(S.seq_off, reads->seq_off, (size_t)nr * 8, dr.seq_off);
+            STAGE(S.qual_off, reads->qual_off, (size_t)nr * 8, dr.qual_off);
+        }
         STAGE(S.seq, reads->seq, (size_t)reads->n_seq_bytes, dr.seq);
         STAGE(S.qual, reads->qual, (size_t)reads->n_qual_bytes, dr.qual);
         STAGE(S.mtid, reads->mtid, (size_t)nr * 4, dr.mtid);

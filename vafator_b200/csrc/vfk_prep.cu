@@ -379,6 +379,112 @@ __global__ void __launch_bounds__(256) link_reads_kernel(ReadsDev R, vfk_params 
     link_reads<PHASE>(R, P, L);
 }
 
+// ------------------------------------------------------------------------------------------
+// implicit pool offsets: a batch whose CIGAR / sequence / quality pools are contiguous in read order (what a decoder that
+// appends record by record produces) may leave cigar_off / seq_off / qual_off NULL; they are then the exclusive prefix sums of
+// n_cigar, (l_qseq + 1) / 2 and l_qseq, derived here.  The host entry point saves 8 bytes per read of bulk copy and the in-place
+// reads of two offset arrays that way.  Three launches: per-block sums, a scan over the blocks, per-block apply.
+// ------------------------------------------------------------------------------------------
+constexpr int OFF_THREADS = 256, OFF_PER = 4;  // a block of 1024 reads, four consecutive reads per thread
+struct Off3 {
+    long long c, s, q;
+};
+__device__ __forceinline__ Off3 off3_add(const Off3 &a, const Off3 &b) { return Off3{a.c + b.c, a.s + b.s, a.q + b.q}; }
+__device__ __forceinline__ Off3 off3_shfl_up(const Off3 &v, int d) {
+    return Off3{__shfl_up_sync(FULL, v.c, d), __shfl_up_sync(FULL, v.s, d), __shfl_up_sync(FULL, v.q, d)};
+}
+__device__ __forceinline__ Off3 off3_of(const ReadsDev &R, int64_t i) {
+    Off3 v{0, 0, 0};
+    if (i < R.n_reads) {
+        const long long n = max(__ldg(R.n_cigar + i), 0), l = max(__ldg(R.l_qseq + i), 0);  // negative lengths: prep_kernel refuses the batch
+        v.c = n; v.s = (l + 1) >> 1; v.q = l;
+    }
+    return v;
+}
+// inclusive scan of one value per thread over the CTA; returns the inclusive prefix, *total = the CTA sum
+__device__ __forceinline__ Off3 off3_cta_scan(Off3 v, Off3 *s_warp, Off3 *total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const Off3 u = off3_shfl_up(v, d);
+        if (lane >= d) v = off3_add(v, u);
+    }
+    if (lane == 31) s_warp[warp] = v;
+    __syncthreads();
+    Off3 before{0, 0, 0}, all{0, 0, 0};
+    for (int w = 0; w < OFF_THREADS / 32; ++w) {
+        if (w < warp) before = off3_add(before, s_warp[w]);
+        all = off3_add(all, s_warp[w]);
+    }
+    *total = all;
+    return off3_add(v, before);
+}
+__global__ void __launch_bounds__(OFF_THREADS) offsets_sums_kernel(ReadsDev R, long long *__restrict__ blk_sums) {
+    __shared__ Off3 s_warp[OFF_THREADS / 32];
+    const int64_t i0 = ((int64_t)blockIdx.x * OFF_THREADS + threadIdx.x) * OFF_PER;
+    Off3 v{0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < OFF_PER; ++j) v = off3_add(v, off3_of(R, i0 + j));
+    Off3 total;
+    (void)off3_cta_scan(v, s_warp, &total);
+    if (threadIdx.x == 0) {
+        blk_sums[3 * (int64_t)blockIdx.x] = total.c;
+        blk_sums[3 * (int64_t)blockIdx.x + 1] = total.s;
+        blk_sums[3 * (int64_t)blockIdx.x + 2] = total.q;
+    }
+}
+// exclusive scan of the block sums in place, ONE CTA: every thread owns a run of consecutive blocks
+__global__ void __launch_bounds__(OFF_THREADS) offsets_scan_kernel(long long *__restrict__ blk_sums, int64_t n_blocks) {
+    __shared__ Off3 s_warp[OFF_THREADS / 32];
+    const int64_t per = (n_blocks + OFF_THREADS - 1) / OFF_THREADS;
+    const int64_t k0 = (int64_t)threadIdx.x * per, k1 = min(k0 + per, n_blocks);
+    Off3 v{0, 0, 0};
+    for (int64_t k = k0; k < k1; ++k) v = off3_add(v, Off3{blk_sums[3 * k], blk_sums[3 * k + 1], blk_sums[3 * k + 2]});
+    Off3 total;
+    const Off3 incl = off3_cta_scan(v, s_warp, &total);
+    Off3 run{incl.c - v.c, incl.s - v.s, incl.q - v.q};  // exclusive prefix of this thread's run
+    for (int64_t k = k0; k < k1; ++k) {
+        const Off3 x{blk_sums[3 * k], blk_sums[3 * k + 1], blk_sums[3 * k + 2]};
+        blk_sums[3 * k] = run.c; blk_sums[3 * k + 1] = run.s; blk_sums[3 * k + 2] = run.q;
+        run = off3_add(run, x);
+    }
+}
+__global__ void __launch_bounds__(OFF_THREADS)
+offsets_apply_kernel(ReadsDev R, const long long *__restrict__ blk_excl, int64_t *__restrict__ cigar_off, int64_t *__restrict__ seq_off,
+                     int64_t *__restrict__ qual_off) {
+    __shared__ Off3 s_warp[OFF_THREADS / 32];
+    const int64_t i0 = ((int64_t)blockIdx.x * OFF_THREADS + threadIdx.x) * OFF_PER;
+    Off3 x[OFF_PER], v{0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < OFF_PER; ++j) {
+        x[j] = off3_of(R, i0 + j);
+        v = off3_add(v, x[j]);
+    }
+    Off3 total;
+    const Off3 incl = off3_cta_scan(v, s_warp, &total);
+    Off3 run{blk_excl[3 * (int64_t)blockIdx.x] + incl.c - v.c, blk_excl[3 * (int64_t)blockIdx.x + 1] + incl.s - v.s,
+             blk_excl[3 * (int64_t)blockIdx.x + 2] + incl.q - v.q};
+#pragma unroll
+    for (int j = 0; j < OFF_PER; ++j) {
+        if (i0 + j < R.n_reads) {
+            cigar_off[i0 + j] = run.c;
+            seq_off[i0 + j] = run.s;
+            qual_off[i0 + j] = run.q;
+        }
+        run = off3_add(run, x[j]);
+    }
+}
+cudaError_t launch_offsets(const ReadsDev &R, long long *blk_sums, int64_t *cigar_off, int64_t *seq_off, int64_t *qual_off, cudaStream_t stream,
+                           int *launches) {
+    if (R.n_reads <= 0) return cudaSuccess;
+    const int64_t nb = (R.n_reads + OFF_THREADS * OFF_PER - 1) / (OFF_THREADS * OFF_PER);
+    offsets_sums_kernel<<<(unsigned)nb, OFF_THREADS, 0, stream>>>(R, blk_sums);
+    offsets_scan_kernel<<<1, OFF_THREADS, 0, stream>>>(blk_sums, nb);
+    offsets_apply_kernel<<<(unsigned)nb, OFF_THREADS, 0, stream>>>(R, blk_sums, cigar_off, seq_off, qual_off);
+    *launches += 3;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_prep(const ReadsDev &R, uint2 *ee_out, int64_t *chunk_max, int64_t *blk_max, int64_t *blk_incl, uint32_t *batch_status,
                         cudaStream_t stream, int *launches) {
     if (R.n_reads <= 0) return cudaSuccess;

@@ -160,9 +160,11 @@ class HostReads:
     reads here -- spans, position index, CIGAR shapes, mate pairing are the kernels' work.  `pinned`: the arrays are
     copied once into page-locked memory (the decoder / generator can also write there directly: bamio, synth)."""
 
-    def __init__(self, batch: ReadBatch, pinned: bool = False):
+    def __init__(self, batch: ReadBatch, pinned: bool = False, implicit_offsets: Optional[bool] = None):
         n = batch.n_placed
         self.batch = batch
+        # pools contiguous in read order: the offset arrays are handed over as NULL and derived on the device (include/vfk.h)
+        self.implicit_offsets = bool(batch.contiguous) if implicit_offsets is None else bool(implicit_offsets)
         self.contigs = list(batch.contigs)
         self.n_reads = n
         self.contig_off = batch.contig_off
@@ -190,6 +192,7 @@ class HostReads:
         return int(self.contig_off.nbytes + sum(a.nbytes for a in self.arrays.values()))
 
     def c_struct(self, ptrs: Optional[Dict[str, int]] = None) -> _ReadBatchC:
+        ptrs_given = ptrs  # device pointers of a resident copy (DeviceReads): those keep their explicit offsets
         s = _ReadBatchC()
         s.n_reads, s.n_contigs, s.max_l_qseq = self.n_reads, len(self.contigs), self.max_l_qseq
         s.n_cigar_words = int(self.arrays["cigar"].shape[0])
@@ -200,11 +203,13 @@ class HostReads:
             ptrs["contig_off"] = self.contig_off.ctypes.data
         for k, v in ptrs.items():
             setattr(s, k, v)
+        if self.implicit_offsets and ptrs_given is None:  # host entry: derived on the device, nothing of them crosses the bus
+            s.cigar_off = s.seq_off = s.qual_off = None
         return s
 
 
-def host_reads(batch: ReadBatch, pinned: bool = False) -> HostReads:
-    return HostReads(batch, pinned=pinned)
+def host_reads(batch: ReadBatch, pinned: bool = False, implicit_offsets: Optional[bool] = None) -> HostReads:
+    return HostReads(batch, pinned=pinned, implicit_offsets=implicit_offsets)
 
 
 def read_passes(batch: ReadBatch, params: ParamsC) -> np.ndarray:

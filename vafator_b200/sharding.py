@@ -97,7 +97,7 @@ def slice_reads(batch: ReadBatch, lo: int, hi: int) -> ReadBatch:
                      cigar=batch.cigar[c0:c1], seq_off=batch.seq_off[sl] - s0, seq=batch.seq[s0:s1],
                      qual_off=batch.qual_off[sl] - q0, qual=batch.qual[q0:q1], mtid=batch.mtid[sl], mpos=batch.mpos[sl],
                      isize=batch.isize[sl], qname_id=batch.qname_id[sl], qname_hash=batch.qname_hash[sl],
-                     contig_lengths=batch.contig_lengths)
+                     contig_lengths=batch.contig_lengths, contiguous=batch.contiguous)
 
 
 def slice_units(units: VariantUnits, a: int, b: int) -> VariantUnits:

@@ -146,7 +146,7 @@ def reads(cfg: SynthConfig, pinned: bool = False) -> ReadBatch:
     arr["cigar"] = arr["cigar"][:plan.n_cigar]
     arr["seq"] = arr["seq"][:plan.n_seq_bytes]
     arr["qual"] = arr["qual"][:plan.n_qual_bytes]
-    return ReadBatch(contigs=cfg.contigs, pinned=pinned, **arr)
+    return ReadBatch(contigs=cfg.contigs, pinned=pinned, contiguous=True, **arr)  # vfkio_synth_fill_reads: prefix-sum offsets
 
 
 def tile_range(cfg: SynthConfig, tid_a: int, pos_a: int, tid_b: int, pos_b: int, margin: int = 2):
