@@ -44,14 +44,16 @@ __device__ __forceinline__ int64_t window_end(const ReadsDev &R, const vfk_param
 //               clear the bitmap.
 // The scratch arrays are written and read inside one launch when the passes run fused (tail_kernel, grid barriers in
 // between): every access to them is a plain (coherent) load or store, never the read-only path.
+// `out` (may be nullptr): a listed unit whose record no longer carries VFK_ST_DEFERRED has been finished by the tile kernel
 __device__ __forceinline__ void link_mark(const ReadsDev &R, const vfk_params &P, const ResolvedUnit *__restrict__ res, const uint32_t *list, int64_t n,
-                                          const LinkScratch &L) {
+                                          const LinkScratch &L, const vfk_counts *out = nullptr) {
     const int lane = threadIdx.x & 31;
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t k = w; k < n; k += n_warps) {
         const uint32_t u = list ? list[k] : (uint32_t)k;
         if (u == 0xFFFFFFFFu) continue;
+        if (out && !(out[u].status & VFK_ST_DEFERRED)) continue;
         const ResolvedUnit r = res[u];
         if (r.hi <= r.lo) continue;
         const int64_t lo = (int64_t)r.lo, hi = (int64_t)r.hi;

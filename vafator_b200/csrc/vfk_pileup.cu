@@ -745,6 +745,263 @@ medium_kernel(const __grid_constant__ ReadsDev R, const ResolvedUnit *__restrict
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// deep panels: neighbouring deep columns share their reads (1000x amplicon: a read covers ~6 variant columns, the ten columns of
+// an amplicon see the same ~1 800 reads).  A CTA takes a TILE -- up to TILE_UNITS consecutive deep units whose windows fit
+// TILE_READS reads together -- and evaluates read-major: a read's header and pairing fields are fetched ONCE for all the
+// columns it covers, its base / quality bytes come from the same one or two cache lines, the reads are paired ONCE per tile in
+// a shared-memory name hash, and every column of the tile has its pair of histograms in shared memory.
+//   A  per read: header -> smem, read filter, overlap_push eligibility, name hash
+//   B  pairing: htslib's name hash replayed over the tile's reads in shared memory (the general protocol: a deep column nearly
+//      always holds a supplementary record, i.e. three records of one name)
+//   C  per (read, column): column resolution, the read's own base / quality -> xw[column][read]
+//   D  per (read, column): overlap adjustment from the partner's xw, base-quality filter, classification, histograms
+//   E  per column: medians / rank sums from the histograms, the unit's record
+// ------------------------------------------------------------------------------------------
+constexpr int TILE_READS = 2048, TILE_UNITS = 16, TILE_TAB = 4096, TILE_THREADS = 1024;  // one CTA per SM (shared memory): 32 warps of it
+constexpr uint32_t RS_PASS = 1u, RS_ELIG = 2u, RS_STORES = 4u;
+template <int POSB>
+struct TileSmem {
+    uint4 hot[TILE_READS];
+    uint32_t key[TILE_READS];
+    uint16_t prt[TILE_READS];
+    uint16_t nxt[TILE_READS];   // chain of the records that share a name-hash bucket
+    int32_t pcol[TILE_READS];   // push column of a chained record (bam_plp_push: the start of the record pushed just before it)
+    uint16_t tab[TILE_TAB];     // bucket -> last chained record
+    uint8_t rs[TILE_READS];
+    uint16_t xw[TILE_UNITS][TILE_READS];
+    uint32_t hist[TILE_UNITS][Layout<POSB>::BINS];  // per column: REF slot then ALT slot of BINS / 2 words (u16 bins)
+    int cnt[TILE_UNITS][8];                          // n_cover, n_col, dp, n_amb, ac_ref, ac_alt, status
+    ResolvedUnit ru[TILE_UNITS];
+    uint32_t unit[TILE_UNITS];                       // unit index of column j of the tile
+    uint32_t deep[TILE_UNITS];                       // group scan: unit k of the group is a deep, deferred unit
+    uint32_t general, n_cols, t_lo, t_hi, next_k, pad[3];
+};
+
+template <int POSB>
+__global__ void __launch_bounds__(TILE_THREADS, 1)
+tile_kernel(const __grid_constant__ ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_units, const uint8_t *__restrict__ ins_seq,
+            const __grid_constant__ vfk_params P, vfk_counts *out, const uint32_t *__restrict__ n_deep, uint32_t *__restrict__ n_tiled) {
+    using L = Layout<POSB>;
+    constexpr int WORDS = L::BINS / 2;
+    if (*n_deep == 0u) return;  // written by the register kernel (an earlier launch): a 30x / 60x call leaves here
+    extern __shared__ __align__(16) uint8_t tile_raw[];
+    TileSmem<POSB> &S = *reinterpret_cast<TileSmem<POSB> *>(tile_raw);
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int64_t n_groups = (n_units + TILE_UNITS - 1) / TILE_UNITS;
+    for (int64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const int64_t u0 = g * TILE_UNITS;
+        __syncthreads();
+        if (t < TILE_UNITS) {
+            const int64_t u = u0 + t;
+            bool deep = false;
+            if (u < n_units) {
+                const uint4 w = reinterpret_cast<const uint4 *>(out + u)[2];  // {med2[2][0], med2[2][1], status, n_cand}
+                deep = (w.z & VFK_ST_DEFERRED) && w.w > 64u && w.w <= (uint32_t)TILE_READS;
+                if (deep) S.ru[t] = res[u];
+            }
+            S.deep[t] = deep ? 1u : 0u;
+        }
+        if (t == 0) S.next_k = 0u;
+        __syncthreads();
+        for (;;) {  // the group's deep units, one tile after the other
+            if (t == 0) {  // next tile: consecutive deep units of one contig while their windows fit TILE_READS reads together
+                uint32_t k = S.next_k, n_cols = 0u, lo = 0u, hi = 0u;
+                int32_t tid = 0;
+                while (k < (uint32_t)TILE_UNITS && !S.deep[k]) ++k;
+                for (; k < (uint32_t)TILE_UNITS; ++k) {
+                    if (!S.deep[k]) continue;
+                    const ResolvedUnit &r = S.ru[k];
+                    if (n_cols == 0u) { lo = r.lo; hi = r.hi; tid = r.tid; }
+                    else if (r.tid != tid || max(hi, r.hi) - min(lo, r.lo) > (uint32_t)TILE_READS) break;
+                    lo = min(lo, r.lo); hi = max(hi, r.hi);
+                    S.unit[n_cols++] = k;
+                }
+                S.next_k = k; S.n_cols = n_cols; S.t_lo = lo; S.t_hi = hi; S.general = 0u;
+            }
+            __syncthreads();
+            const int J = (int)S.n_cols;
+            if (J == 0) break;
+            const uint32_t t_lo = S.t_lo, T = S.t_hi - S.t_lo;
+            const int32_t tid = S.ru[S.unit[0]].tid;
+            const int64_t c0 = __ldg(R.contig_off + tid);
+            for (int k = t; k < TILE_TAB / 2; k += TILE_THREADS) reinterpret_cast<uint32_t *>(S.tab)[k] = 0xFFFFFFFFu;
+            for (int k = t; k < J * L::BINS; k += TILE_THREADS) (&S.hist[0][0])[k] = 0u;
+            if (t < J * 8) (&S.cnt[0][0])[t] = (t & 7) == 6 ? (int)(S.ru[S.unit[t >> 3]].meta & 3u) : 0;
+            // ---- A
+            for (uint32_t r = t; r < T; r += TILE_THREADS) {
+                const int64_t i = (int64_t)t_lo + r;
+                const uint4 hot = load_hot(R, i);
+                const bool pass = read_passes(hot.z, P);
+                bool elig = P.ignore_overlaps && pass && (hot.z & (F_PROPER | F_MUNMAP)) == F_PROPER, stores = false;
+                uint32_t key = 0u;
+                if (elig) {  // htslib overlap_push past its early exits (cf. pair_in_registers)
+                    const int32_t mp = __ldg(R.mpos + i), mt = __ldg(R.mtid + i);
+                    key = __ldg(R.qname_hash + i);
+                    if (mt >= 0 && mt != tid) elig = false;
+                    const int32_t end = (int32_t)hot.x + (int32_t)hot.y;
+                    if (elig && mp >= end) {
+                        const long long isz = (long long)__ldg(R.isize + i);
+                        const int lq = (hot.z >> 24) == SHAPE_SIMPLE ? (int)hot.y : __ldg(R.l_qseq + i);
+                        if ((isz < 0 ? -isz : isz) >= 2LL * lq) elig = false;
+                    }
+                    int32_t column = 0;
+                    if (elig) {
+                        column = push_column(R, P, i, c0);
+                        if ((int32_t)hot.x + (int32_t)hot.y <= column) elig = false;  // never appended to the pileup buffer (a zero-span record)
+                    }
+                    S.pcol[r] = column;
+                    stores = elig && (mp >= (int32_t)hot.x || ((hot.z & F_PAIRED) && mp == -1));
+                }
+                S.hot[r] = hot;
+                S.key[r] = key;
+                S.prt[r] = (uint16_t)MED_NONE;
+                S.nxt[r] = (uint16_t)MED_NONE;
+                S.rs[r] = (uint8_t)((pass ? RS_PASS : 0u) | (elig ? RS_ELIG : 0u) | (stores ? RS_STORES : 0u));
+            }
+            __syncthreads();
+            // ---- B: htslib's name hash replayed for the tile (cf. link_one_read): the records that reach overlap_push are chained per
+            // bucket, then every record walks the records of its name in file order -- found: pair and delete; not found: stored
+            // if the mate is still to come; an entry whose record has left the pileup buffer is dropped
+            for (uint32_t r = t; r < T; r += TILE_THREADS) {
+                if (!(S.rs[r] & RS_ELIG)) continue;
+                const uint32_t slot = (S.key[r] * 2654435761u) >> 20;  // 12 bits
+                uint32_t head = S.tab[slot];
+                for (;;) {  // push onto the bucket's chain
+                    S.nxt[r] = (uint16_t)head;
+                    const uint32_t seen = cas16(&S.tab[slot], head, r);
+                    if (seen == head) break;
+                    head = seen;
+                }
+            }
+            __syncthreads();
+            for (uint32_t r = t; r < T; r += TILE_THREADS) {
+                if (!(S.rs[r] & RS_ELIG)) continue;
+                const uint32_t key = S.key[r];
+                const unsigned long long id = __ldg(R.qname_id + t_lo + r);
+                const uint32_t head = S.tab[(key * 2654435761u) >> 20];
+                int waiting = -1, cur = -1;
+                uint32_t result = MED_NONE;
+                for (;;) {
+                    int m = -1;  // smallest member of the name beyond cur
+                    for (uint32_t j = head; j != MED_NONE; j = S.nxt[j])
+                        if ((int)j > cur && (m < 0 || (int)j < m) && S.key[j] == key && __ldg(R.qname_id + t_lo + j) == id) m = (int)j;
+                    if (m < 0) break;
+                    if (waiting >= 0 && (int32_t)S.hot[waiting].x + (int32_t)S.hot[waiting].y < S.pcol[m]) waiting = -1;  // its record already left the buffer
+                    if (waiting < 0) {
+                        if (S.rs[m] & RS_STORES) waiting = m;
+                    } else {
+                        if (waiting == (int)r || m == (int)r) {
+                            result = (uint32_t)(waiting == (int)r ? m : waiting);
+                            break;
+                        }
+                        waiting = -1;
+                    }
+                    cur = m;
+                    if (m >= (int)r && waiting != (int)r) break;  // record r has been through without a partner
+                }
+                S.prt[r] = (uint16_t)result;
+            }
+            __syncthreads();
+            // ---- C
+            for (uint32_t r = t; r < T; r += TILE_THREADS) {
+                const int64_t i = (int64_t)t_lo + r;
+                const uint4 hot = S.hot[r];
+                const bool pass = S.rs[r] & RS_PASS;
+                int64_t qo = 0, so = 0;
+                if (pass) { qo = __ldg(R.qual_off + i); so = __ldg(R.seq_off + i); }
+                for (int j = 0; j < J; ++j) {
+                    const ResolvedUnit &ru = S.ru[S.unit[j]];
+                    uint32_t x = 0u;
+                    if (i >= (int64_t)ru.lo && i < (int64_t)ru.hi) {
+                        const ColRead c = resolve_column(R, ru.col, i, hot, true, pass);
+                        if (c.pay) {
+                            const uint32_t q = (uint32_t)__ldg(R.qual + qo + c.qpos), b = (uint32_t)__ldg(R.seq + so + (c.qpos >> 1));
+                            x = q | (((c.qpos & 1) ? (b & 15u) : (b >> 4)) << 8) | (c.aligned ? 0x8000u : 0u);
+                        }
+                    }
+                    S.xw[j][r] = (uint16_t)x;
+                }
+            }
+            __syncthreads();
+            // ---- D: a warp works on one column at a time (its counters are reduced across the warp), warps start at different columns
+            for (uint32_t r0 = warp * 32; r0 < T; r0 += TILE_THREADS) {
+                const uint32_t r = r0 + lane;
+                const bool in = r < T;
+                const int64_t i = (int64_t)t_lo + r;
+                const uint4 hot = in ? S.hot[r] : make_uint4(0, 0, 0, 0);
+                const uint32_t rs = in ? (uint32_t)S.rs[r] : 0u;
+                const uint32_t pj = in ? (uint32_t)S.prt[r] : MED_NONE;
+                const bool paired = pj != MED_NONE;  // (the replay has applied the protocol: stored / found / deleted)
+                const uint32_t sel = wang_hash(in ? S.key[r] : 0u) & 1u;
+                for (int jj = 0; jj < J; ++jj) {
+                    int j = jj + (warp & (TILE_UNITS - 1));  // warps start at different columns
+                    j = j >= J ? j - J : j;
+                    j = j >= J ? j % J : j;
+                    const ResolvedUnit &ru = S.ru[S.unit[j]];
+                    Unit U;
+                    unit_from(ru, ins_seq, U);
+                    const bool cand = in && i >= (int64_t)ru.lo && i < (int64_t)ru.hi;
+                    const ColRead c = resolve_column(R, ru.col, i, hot, cand, cand && (rs & RS_PASS));
+                    const uint32_t xw = cand ? (uint32_t)S.xw[j][r] : 0u;
+                    const uint32_t word = xw & 0xFFFu;
+                    int q = 0;
+                    uint32_t my_word = 0u;
+                    if (c.aligned) {
+                        const uint32_t px = paired ? (uint32_t)S.xw[j][pj] : 0u;
+                        my_word = word;
+                        q = overlap_quality(word, (px & 0x8000u) ? ((px & 0xFFFu) | 0x80000000u) : 0u, r < pj, sel);
+                    } else if (c.hard) {
+                        uint32_t mw = paired ? ((t_lo + pj) | (sel << 31)) : VFK_NO_MATE;
+                        if (!paired && (rs & RS_STORES)) {  // the record after the column may be its mate (bam_plp_auto reads one ahead)
+                            const int64_t nx = next_pushed(R, P, U.hi, contig_end(R, U.tid), U.stop);
+                            if (nx >= 0 && ld_end(R, nx) > __ldg(R.pos + nx) && reaches_hash(R, P, nx, U.tid, INT32_MIN) &&
+                                __ldg(R.qname_id + i) == __ldg(R.qname_id + nx) && __ldg(R.qname_hash + i) == __ldg(R.qname_hash + nx))
+                                mw = (uint32_t)nx | ((wang_hash(__ldg(R.qname_hash + nx)) & 1u) << 31);
+                        }
+                        my_word = word;
+                        q = hard_quality(R, P, U.col, U.stop, U.tid, U.hi, i, mw, c.qpos, word & 0xFFu, (word >> 8) * 0x11u);
+                    }
+                    const Eval e = finish_column(R, P, U, i, hot, c, q, my_word);
+                    const Contribution cb = decode(e);
+                    uint32_t status = 0u;
+                    accumulate<uint16_t, POSB>(S.hist[j], S.hist[j] + WORDS, cb, U.kind == VFK_KIND_SNV, status);
+                    const int n_cover = __reduce_add_sync(FULL, cb.covers ? 1 : 0), n_col = __reduce_add_sync(FULL, cb.in_col ? 1 : 0);
+                    const int dp = __reduce_add_sync(FULL, cb.in_dp ? 1 : 0), n_amb = __reduce_add_sync(FULL, cb.ambiguous ? 1 : 0);
+                    const int ac_ref = __reduce_add_sync(FULL, cb.ref ? 1 : 0), ac_alt = __reduce_add_sync(FULL, (int)cb.alt);
+                    status = __reduce_or_sync(FULL, status);
+                    if (lane == 0 && n_cover) {
+                        atomicAdd(&S.cnt[j][0], n_cover); atomicAdd(&S.cnt[j][1], n_col); atomicAdd(&S.cnt[j][2], dp);
+                        atomicAdd(&S.cnt[j][3], n_amb); atomicAdd(&S.cnt[j][4], ac_ref); atomicAdd(&S.cnt[j][5], ac_alt);
+                        if (status) atomicOr(&S.cnt[j][6], (int)status);
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- E
+            for (int j = warp; j < J; j += TILE_THREADS / 32) {
+                const ResolvedUnit &ru = S.ru[S.unit[j]];
+                const uint32_t kind = ru.meta & 3u;
+                const int *cn = S.cnt[j];
+                int med2[3][2] = {{-1, -1}, {-1, -1}, {-1, -1}};
+                uint64_t s2[3] = {0, 0, 0};
+                const uint32_t *ref_slot = S.hist[j], *alt_slot = S.hist[j] + WORDS;
+                if (cn[4] | cn[5]) {
+                    reduce_metric<uint16_t, 256>(ref_slot, alt_slot, L::MQ_OFF, lane, med2[0][0], med2[0][1], s2[0]);
+                    if (kind == VFK_KIND_SNV) reduce_metric<uint16_t, 256>(ref_slot, alt_slot, L::BQ_OFF, lane, med2[1][0], med2[1][1], s2[1]);
+                    reduce_metric<uint16_t, POSB>(ref_slot, alt_slot, L::POS_OFF, lane, med2[2][0], med2[2][1], s2[2]);
+                }
+                int dp = cn[2];
+                if (kind == VFK_KIND_SNV && !P.include_ambiguous) dp -= cn[3];  // pileups.py:224-227
+                if (lane == 0)
+                    store_counts(out + u0 + S.unit[j], dp, cn[3], cn[4], cn[5], med2, s2, (uint32_t)cn[6], ru.hi - ru.lo, (uint32_t)cn[0], (uint32_t)cn[1]);
+            }
+            if (t == 0) atomicAdd(n_tiled, (uint32_t)J);
+            __syncthreads();
+        }
+    }
+}
+
 // dynamic shared memory of the register kernel, per warp
 template <int POSB>
 struct WarpSmem {
@@ -835,6 +1092,7 @@ pileup_warp_kernel(const __grid_constant__ ReadsDev R, const ResolvedUnit *__res
                 if (lane == 0) {
                     if (n_cand > WARP_PATH_MAX_CAND) block_list[atomicAdd(n_block, 1u)] = (uint32_t)u;
                     else warp_list[atomicAdd(n_warp, 1u)] = (uint32_t)u;
+                    atomicAdd(n_medium + 1, 1u);  // counters @28: deep units (the tile kernel looks for them only if there are any)
                     store_counts(out + u, 0, 0, 0, 0, med2, s2, U.kind | VFK_ST_DEFERRED, (uint32_t)n_cand, 0u);
                 }
                 continue;
@@ -1122,14 +1380,16 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
 tail_kernel(const __grid_constant__ ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_units, const uint8_t *__restrict__ ins_seq,
             const __grid_constant__ vfk_params P, vfk_counts *out, const uint32_t *__restrict__ block_list,
             const uint32_t *__restrict__ n_block, const uint32_t *__restrict__ warp_list, const uint32_t *__restrict__ n_warp,
-            const uint32_t *__restrict__ batch_status, uint32_t *seg_ctr, int n_seg, const __grid_constant__ LinkScratch Lk) {
+            const uint32_t *__restrict__ batch_status, const uint32_t *__restrict__ n_tiled, uint32_t *seg_ctr, int n_seg,
+            const __grid_constant__ LinkScratch Lk) {
     extern __shared__ __align__(16) uint32_t smem[];
-    const uint32_t nw = *n_warp, nb = *n_block;  // written by the register kernel (an earlier launch)
-    if (nw == 0u && nb == 0u) return;            // the whole grid takes the same way out: no barrier is left waiting
+    const uint32_t nw = *n_warp, nb = *n_block;  // written by the register / medium kernels (earlier launches)
+    if (nw <= *n_tiled && nb == 0u) return;      // nothing listed, or the tile kernel has finished all of it: the whole grid leaves here
+                                                 // (every CTA takes the same way out: no barrier is left waiting)
     if constexpr (LINK) {
         cg::grid_group grid = cg::this_grid();
-        link_mark(R, P, res, warp_list, (int64_t)nw, Lk);
-        link_mark(R, P, res, block_list, (int64_t)nb, Lk);
+        link_mark(R, P, res, warp_list, (int64_t)nw, Lk, out);
+        link_mark(R, P, res, block_list, (int64_t)nb, Lk, out);
         grid.sync();
         link_reads<0>(R, P, Lk);
         grid.sync();
@@ -1150,7 +1410,7 @@ cudaError_t launch_link(const ReadsDev &R, const vfk_params &P, const void *reso
 
 // Per-call device scratch (owned by the handle / a staging slot).
 //   counters: @0 u64 unit work counter, @8 u32 block-list length, @12 u32 warp-list length, @20 u32 batch status
-//   (VFK_ST_BADBATCH or 0), @24 u32 medium-list length, @64 256 x u32 per-SM segment counters of the list path.   lists: 3 * n_units u32.
+//   (VFK_ST_BADBATCH or 0), @24 u32 medium-list length, @28 u32 deep units listed, @32 u32 units finished by the tile kernel, @64 256 x u32 per-SM segment counters of the list path.   lists: 3 * n_units u32.
 struct PileupScratch {
     void *resolved;   // n_units * 32 B
     void *counters;   // 64 B
@@ -1190,12 +1450,13 @@ static cudaError_t launch_tail(const ReadsDev &R, const UnitsDev &V, const vfk_p
     const uint32_t *batch_status = (const uint32_t *)((char *)S.counters + 20);
     const uint32_t *block_list = S.lists, *warp_list = S.lists + V.n;
     int64_t n_units = V.n;
+    const uint32_t *n_tiled = (const uint32_t *)((char *)S.counters + 32);
     uint32_t *seg_ctr = (uint32_t *)((char *)S.counters + 64);  // one work counter per SM segment (zeroed with the counters)
     int n_seg = std::min(sm_count, MAX_SEGMENTS);
     LinkScratch Lk;
     Lk.heads = S.heads; Lk.n_buckets = S.n_buckets; Lk.next = S.next; Lk.column = S.column; Lk.claimed = S.claimed; Lk.mate = S.mate;
     void *args[] = {(void *)&R, (void *)&res, (void *)&n_units, (void *)&ins_seq, (void *)&P, (void *)&out, (void *)&block_list, (void *)&n_block,
-                    (void *)&warp_list, (void *)&n_warp, (void *)&batch_status, (void *)&seg_ctr, (void *)&n_seg, (void *)&Lk};
+                    (void *)&warp_list, (void *)&n_warp, (void *)&batch_status, (void *)&n_tiled, (void *)&seg_ctr, (void *)&n_seg, (void *)&Lk};
     e = cudaLaunchCooperativeKernel((const void *)tail_kernel<POSB, LINK>, dim3((unsigned)grid), dim3(WARPS_PER_CTA * 32), args, smem, stream);
     if (e == cudaErrorCooperativeLaunchTooLarge && grid > sm_count) {  // the driver counts fewer resident CTAs than the query: one per SM always fits
         (void)cudaGetLastError();
@@ -1256,6 +1517,18 @@ static cudaError_t launch_posb(ReadsDev R, const UnitsDev &V, const vfk_params &
             if (e != cudaSuccess) return e;
             const int64_t med_grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)sm_count * 3, (V.n + WARPS_PER_CTA - 1) / WARPS_PER_CTA));
             medium_kernel<POSB><<<(unsigned)med_grid, WARPS_PER_CTA * 32, med_smem, stream>>>(R, res, V.ins_seq, P, out, medium_list, n_medium, warp_list, n_warp);
+            ++*launches;
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+        }
+    }
+    if constexpr (WarpSmem<POSB>::HIST_HERE) {
+        if (!link_all) {  // deep panels: tiles of neighbouring deep units, read-major (no deep unit listed: the CTAs leave at once)
+            const size_t tile_smem = sizeof(TileSmem<POSB>);
+            e = cudaFuncSetAttribute(tile_kernel<POSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem);
+            if (e != cudaSuccess) return e;
+            const int64_t tile_grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)sm_count, (V.n + TILE_UNITS - 1) / TILE_UNITS));
+            tile_kernel<POSB><<<(unsigned)tile_grid, TILE_THREADS, tile_smem, stream>>>(R, res, V.n, V.ins_seq, P, out, n_medium + 1, n_medium + 2);
             ++*launches;
             e = cudaGetLastError();
             if (e != cudaSuccess) return e;

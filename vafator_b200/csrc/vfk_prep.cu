@@ -320,49 +320,38 @@ prep_kernel(const __grid_constant__ ReadsDev R, uint2 *__restrict__ ee_out, int6
 }
 static_assert(PREP_WARP_READS == 128, "a warp owns four chunks");
 
-// blk_incl[0] = LLONG_MIN, blk_incl[b + 1] = max(blk_max[0..b]) -- ONE CTA, one pass: every thread owns a run of consecutive
-// entries (n_reads / 1024 entries in all), the run maxima are scanned across the CTA, the runs are then written out
+// blk_incl[0] = LLONG_MIN, blk_incl[b + 1] = max(blk_max[0..b]).  CTA c owns entries [1024 c, 1024 c + 1024): it first folds
+// every entry before its own (a coalesced sweep -- a maximum needs no order, and the whole array is a few hundred KB of L2),
+// then scans its 1 024 entries with that carry.  One launch, no chain between the CTAs.
 constexpr int SCAN_THREADS = 1024;
 __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const int64_t *__restrict__ blk_max, int64_t n_blocks, int64_t *__restrict__ blk_incl) {
     __shared__ long long s_warp[32];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int64_t per = (n_blocks + SCAN_THREADS - 1) / SCAN_THREADS;
-    const int64_t k0 = (int64_t)t * per, k1 = min(k0 + per, n_blocks);
-    long long v = LLONG_MIN;
-    {
-        int64_t k = k0;
-        for (; k + 4 <= k1; k += 4) {  // four independent loads in flight
-            const long long a = __ldg(blk_max + k), b = __ldg(blk_max + k + 1), c = __ldg(blk_max + k + 2), d = __ldg(blk_max + k + 3);
-            v = max(max(v, max(a, b)), max(c, d));
-        }
-        for (; k < k1; ++k) v = max(v, (long long)__ldg(blk_max + k));
-    }
-    long long incl = v;  // inclusive scan of the run maxima: warp, then the warp totals
+    const int64_t first = (int64_t)blockIdx.x * SCAN_THREADS;
+    long long carry = LLONG_MIN;
+    for (int64_t k = t; k < first; k += SCAN_THREADS) carry = max(carry, (long long)__ldg(blk_max + k));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) carry = max(carry, __shfl_xor_sync(FULL, carry, o));
+    if (lane == 0) s_warp[warp] = carry;
+    __syncthreads();
+    carry = s_warp[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) carry = max(carry, __shfl_xor_sync(FULL, carry, o));  // every thread: maximum of all entries before the CTA's
+    __syncthreads();
+    const int64_t k = first + t;
+    long long v = k < n_blocks ? (long long)__ldg(blk_max + k) : LLONG_MIN;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const long long u = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl = max(incl, u);
+        const long long u = __shfl_up_sync(FULL, v, o);
+        if (lane >= o) v = max(v, u);
     }
-    if (lane == 31) s_warp[warp] = incl;
+    if (lane == 31) s_warp[warp] = v;
     __syncthreads();
-    if (warp == 0) {
-        long long w = s_warp[lane];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const long long u = __shfl_up_sync(FULL, w, o);
-            if (lane >= o) w = max(w, u);
-        }
-        s_warp[lane] = w;
-    }
-    __syncthreads();
-    long long run = __shfl_up_sync(FULL, incl, 1);  // exclusive prefix of this thread's run
-    if (lane == 0) run = LLONG_MIN;
-    if (warp > 0) run = max(run, s_warp[warp - 1]);
-    if (t == 0) blk_incl[0] = LLONG_MIN;
-    for (int64_t k = k0; k < k1; ++k) {
-        run = max(run, (long long)__ldg(blk_max + k));
-        blk_incl[k + 1] = run;
-    }
+    long long before = carry;
+    for (int w = 0; w < warp; ++w) before = max(before, s_warp[w]);
+    v = max(v, before);
+    if (k < n_blocks) blk_incl[k + 1] = v;
+    if (k == 0) blk_incl[0] = LLONG_MIN;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -493,7 +482,7 @@ cudaError_t launch_prep(const ReadsDev &R, uint2 *ee_out, int64_t *chunk_max, in
     const bool aligned = (((uintptr_t)R.pos | (uintptr_t)R.n_cigar | (uintptr_t)R.l_qseq | (uintptr_t)R.cigar_off | (uintptr_t)ee_out) & 15u) == 0u;
     if (aligned) prep_kernel<true><<<(unsigned)nb, PREP_THREADS, 0, stream>>>(R, ee_out, chunk_max, blk_max, batch_status);
     else prep_kernel<false><<<(unsigned)nb, PREP_THREADS, 0, stream>>>(R, ee_out, chunk_max, blk_max, batch_status);
-    scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(blk_max, nb, blk_incl);
+    scan_kernel<<<(unsigned)((nb + SCAN_THREADS - 1) / SCAN_THREADS), SCAN_THREADS, 0, stream>>>(blk_max, nb, blk_incl);
     *launches += 2;
     return cudaGetLastError();
 }
