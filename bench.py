@@ -558,8 +558,9 @@ def main():
         # B_unit = 16 (variant) + 8 (index bounds) + 32 * D_raw + 160 (outputs), biallelic
         b_unit = 16 + 8 + 32.0 * d_raw + 160
         units_per_launch = units_per_step / len(batches)
-        # the dominant kernel of the call: the register kernel (30x / 60x columns) or the list path (deep columns: tail_kernel)
-        dominant, dom_ms = ("pileup_warp_kernel", phase["pileup"]) if phase["pileup"] >= phase["lists"] else ("tail_kernel", phase["lists"])
+        # the dominant kernel of the call: the register kernel (30x / 60x columns) or the list path (deep columns: tile_kernel, with the
+        # medium / tail kernels' share of that phase)
+        dominant, dom_ms = ("pileup_warp_kernel", phase["pileup"]) if phase["pileup"] >= phase["lists"] else ("tile_kernel", phase["lists"])
         achieved = units_per_launch * b_unit / (dom_ms * 1e-3) / 1e9
         reads_per_launch = reads_rank / len(batches)
         cig = float(np.mean([len(b["batch"].cigar) / max(b["batch"].n_reads, 1) for b in batches]))

@@ -772,6 +772,8 @@ struct TileSmem {
     uint16_t xw[TILE_UNITS][TILE_READS];
     uint32_t hist[TILE_UNITS][Layout<POSB>::BINS];  // per column: REF slot then ALT slot of BINS / 2 words (u16 bins)
     int cnt[TILE_UNITS][8];                          // n_cover, n_col, dp, n_amb, ac_ref, ac_alt, status
+    int med2[TILE_UNITS][3][2];
+    unsigned long long s2[TILE_UNITS][3];
     ResolvedUnit ru[TILE_UNITS];
     uint32_t unit[TILE_UNITS];                       // unit index of column j of the tile
     uint32_t deep[TILE_UNITS];                       // group scan: unit k of the group is a deep, deferred unit
@@ -978,23 +980,33 @@ tile_kernel(const __grid_constant__ ReadsDev R, const ResolvedUnit *__restrict__
                 }
             }
             __syncthreads();
-            // ---- E
-            for (int j = warp; j < J; j += TILE_THREADS / 32) {
+            // ---- E: one warp per (column, metric); then the records
+            for (int task = warp; task < 3 * J; task += TILE_THREADS / 32) {
+                const int j = task / 3, m = task - 3 * j;
+                const ResolvedUnit &ru = S.ru[S.unit[j]];
+                const int *cn = S.cnt[j];
+                int m_ref = -1, m_alt = -1;
+                uint64_t s2 = 0;
+                const uint32_t *ref_slot = S.hist[j], *alt_slot = S.hist[j] + WORDS;
+                if ((cn[4] | cn[5]) && (m != 1 || (ru.meta & 3u) == VFK_KIND_SNV)) {
+                    if (m == 0) reduce_metric<uint16_t, 256>(ref_slot, alt_slot, L::MQ_OFF, lane, m_ref, m_alt, s2);
+                    else if (m == 1) reduce_metric<uint16_t, 256>(ref_slot, alt_slot, L::BQ_OFF, lane, m_ref, m_alt, s2);
+                    else reduce_metric<uint16_t, POSB>(ref_slot, alt_slot, L::POS_OFF, lane, m_ref, m_alt, s2);
+                }
+                if (lane == 0) { S.med2[j][m][0] = m_ref; S.med2[j][m][1] = m_alt; S.s2[j][m] = s2; }
+            }
+            __syncthreads();
+            if (t < J) {
+                const int j = t;
                 const ResolvedUnit &ru = S.ru[S.unit[j]];
                 const uint32_t kind = ru.meta & 3u;
                 const int *cn = S.cnt[j];
-                int med2[3][2] = {{-1, -1}, {-1, -1}, {-1, -1}};
-                uint64_t s2[3] = {0, 0, 0};
-                const uint32_t *ref_slot = S.hist[j], *alt_slot = S.hist[j] + WORDS;
-                if (cn[4] | cn[5]) {
-                    reduce_metric<uint16_t, 256>(ref_slot, alt_slot, L::MQ_OFF, lane, med2[0][0], med2[0][1], s2[0]);
-                    if (kind == VFK_KIND_SNV) reduce_metric<uint16_t, 256>(ref_slot, alt_slot, L::BQ_OFF, lane, med2[1][0], med2[1][1], s2[1]);
-                    reduce_metric<uint16_t, POSB>(ref_slot, alt_slot, L::POS_OFF, lane, med2[2][0], med2[2][1], s2[2]);
-                }
+                int med2[3][2];
+                uint64_t s2[3];
+                for (int m = 0; m < 3; ++m) { med2[m][0] = S.med2[j][m][0]; med2[m][1] = S.med2[j][m][1]; s2[m] = S.s2[j][m]; }
                 int dp = cn[2];
                 if (kind == VFK_KIND_SNV && !P.include_ambiguous) dp -= cn[3];  // pileups.py:224-227
-                if (lane == 0)
-                    store_counts(out + u0 + S.unit[j], dp, cn[3], cn[4], cn[5], med2, s2, (uint32_t)cn[6], ru.hi - ru.lo, (uint32_t)cn[0], (uint32_t)cn[1]);
+                store_counts(out + u0 + S.unit[j], dp, cn[3], cn[4], cn[5], med2, s2, (uint32_t)cn[6], ru.hi - ru.lo, (uint32_t)cn[0], (uint32_t)cn[1]);
             }
             if (t == 0) atomicAdd(n_tiled, (uint32_t)J);
             __syncthreads();
