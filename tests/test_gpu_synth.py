@@ -58,7 +58,9 @@ def _compare(got, want, amb=True):
 CASES = {
     "wes": (lambda: synth.wes(n_tiles=3000), [(1, 30), (0, 0), (20, 13)]),
     "wgs_indels": (lambda: synth.wgs(contig_len=1_500_000, n_contigs=2, multiallelic_pct=5), [(1, 30), (0, 0)]),
-    "amplicon_1000x": (lambda: synth.amplicon(n_tiles=24, depth_pairs=900), [(1, 30), (0, 20)]),
+    "amplicon_1000x": (lambda: synth.amplicon(n_tiles=24, depth_pairs=900), [(1, 30), (0, 20)]),       # tile_kernel (<= 2048 reads per tile)
+    "amplicon_5000x": (lambda: synth.amplicon(n_tiles=14, depth_pairs=2500), [(1, 30)]),               # too deep for a tile: tail_kernel
+    "multisample_60x": (lambda: synth.multisample(1, n_tiles=1500), [(1, 30), (0, 0)]),               # 65..192 candidates: medium_kernel
     "noisy_cigars": (lambda: synth.wes(n_tiles=1500, indel_period=40, snv_period=30, multiallelic_pct=20, p_softclip=0.2,
                                        p_del=0.15, p_ins=0.15, p_skip=0.05, p_supp=0.05, p_orphan=0.05, p_n=0.02,
                                        frag_mean=200.0, frag_sd=40.0), [(1, 30), (0, 0), (0, 41)]),
@@ -74,8 +76,17 @@ def test_gpu_matches_c_oracle(dev, name):
         want = c_oracle.pileup(batch.as_dict(), ounits, c_oracle.params(min_mapq=mq, min_baseq=bq))
         _compare(_gpu(dev, batch, units, stop, mq, bq), want)
     want = c_oracle.pileup(batch.as_dict(), ounits, c_oracle.params(min_mapq=1, min_baseq=30))
-    _compare(_gpu(dev, batch, units, stop, 1, 30, amb=False), want, amb=False)
+    got = _gpu(dev, batch, units, stop, 1, 30, amb=False)
+    _compare(got, want, amb=False)
     assert want["ac_alt"].sum() > 0 and want["n_amb"].sum() >= 0
+    # the case really takes the path it is named for (n_cand = candidate reads of the position index)
+    n_cand = got["n_cand"]
+    if name == "multisample_60x":
+        assert np.mean((n_cand > 64) & (n_cand <= 192)) > 0.1
+    elif name == "amplicon_1000x":
+        assert np.mean((n_cand > 192) & (n_cand <= 2048)) > 0.5
+    elif name == "amplicon_5000x":
+        assert np.mean(n_cand > 2048) > 0.5
 
 
 def test_deep_column_block_path(dev):

@@ -8,6 +8,10 @@
 #include "vfk_device.cuh"
 
 namespace vfk {
+struct LaunchCache {
+    bool ready;
+    int warp_ctas, tail_ctas;
+};
 struct PileupScratch {
     void *resolved;
     void *counters;
@@ -19,6 +23,7 @@ struct PileupScratch {
     uint32_t *claimed;
     uint32_t *mate;
     cudaEvent_t *ev;
+    LaunchCache *cache;
 };
 cudaError_t launch_prep(const ReadsDev &R, uint2 *ee_out, int64_t *chunk_max, int64_t *blk_max, int64_t *blk_incl, uint32_t *batch_status,
                         cudaStream_t stream, int *launches);
@@ -135,6 +140,7 @@ struct Work {
         s.heads = (uint32_t *)heads.p; s.n_buckets = n_buckets; s.next = (uint32_t *)next.p; s.column = (int32_t *)column.p;
         s.claimed = (uint32_t *)claimed.p; s.mate = (uint32_t *)mate.p;
         s.ev = nullptr;
+        s.cache = nullptr;
         return s;
     }
     void release() {
@@ -181,6 +187,7 @@ struct vfk_handle {
     int64_t staged_bytes = 0, d2h_bytes = 0, zero_copy_batches = 0, staged_batches = 0;
     bool timing = false;     // vfk_set_timing
     Work *timed = nullptr;   // the working set of the last timed call
+    vfk::LaunchCache launch_cache[4] = {};  // per position-range instantiation of the pileup kernels (vfk_pileup.cu)
     bool link_all = false;   // debug hook (VFK_DEBUG_LINK_ALL=1 when the handle is created): partners from the link kernels everywhere
     bool stage_all = false;  // VFK_HOST_STAGE_ALL=1 when the handle is created: the host entry point copies every array
     // Carter k / d per depth for the last (fpr, error_rate) seen, depths [0, CARTER_DEPTHS)
@@ -340,6 +347,7 @@ static int enqueue_prep(vfk_handle *h, Work &w, vfk::ReadsDev &R, cudaStream_t s
 static vfk::PileupScratch scratch_of(vfk_handle *h, Work &w) {
     vfk::PileupScratch s = w.scratch();
     if (h->timing) s.ev = w.tev;
+    s.cache = h->launch_cache;
     return s;
 }
 

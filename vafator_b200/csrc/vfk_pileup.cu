@@ -1420,6 +1420,13 @@ cudaError_t launch_link(const ReadsDev &R, const vfk_params &P, const void *reso
                         int64_t n_all, uint32_t *heads, uint32_t n_buckets, uint32_t *next, int32_t *column, uint32_t *claimed,
                         uint32_t *mate, int sm_count, cudaStream_t stream, int *launches);
 
+// What a launch needs to know about its kernels and need not ask the runtime on every call (a call is a fraction of a
+// millisecond; each attribute set / occupancy query costs the host several microseconds).
+struct LaunchCache {
+    bool ready;
+    int warp_ctas, tail_ctas;
+};
+
 // Per-call device scratch (owned by the handle / a staging slot).
 //   counters: @0 u64 unit work counter, @8 u32 block-list length, @12 u32 warp-list length, @20 u32 batch status
 //   (VFK_ST_BADBATCH or 0), @24 u32 medium-list length, @28 u32 deep units listed, @32 u32 units finished by the tile kernel, @64 256 x u32 per-SM segment counters of the list path.   lists: 3 * n_units u32.
@@ -1435,7 +1442,10 @@ struct PileupScratch {
     uint32_t *claimed;
     uint32_t *mate;
     cudaEvent_t *ev;  // timing (vfk_set_timing): [2] after locate, [3] after the register kernel, [4] after the list path; or NULL
+    LaunchCache *cache;  // [4], one per position-range instantiation: function attributes set / occupancies queried once per handle
 };
+
+constexpr int posb_index(int posb) { return posb == 256 ? 0 : posb == 512 ? 1 : posb == 1024 ? 2 : 3; }
 
 template <int POSB, bool LINK>
 static cudaError_t launch_tail(const ReadsDev &R, const UnitsDev &V, const vfk_params &P, vfk_counts *out, const PileupScratch &S, int sm_count,
@@ -1444,16 +1454,20 @@ static cudaError_t launch_tail(const ReadsDev &R, const UnitsDev &V, const vfk_p
     const size_t smem = std::max((size_t)WARPS_PER_CTA * 2 * (L::BINS / 2) * sizeof(uint32_t),  // a pair of u16 histograms per warp
                                  (size_t)2 * L::BINS * sizeof(uint32_t));                        // a pair of u32 histograms per CTA
     cudaError_t e;
-    if (smem > 40 * 1024) {  // with the kernel's static shared memory on top, 48 KB is the limit without the opt-in
-        e = cudaFuncSetAttribute(tail_kernel<POSB, LINK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    LaunchCache &C = S.cache[posb_index(POSB)];
+    if (!C.tail_ctas) {
+        if (smem > 40 * 1024) {  // with the kernel's static shared memory on top, 48 KB is the limit without the opt-in
+            e = cudaFuncSetAttribute(tail_kernel<POSB, LINK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        // the occupancy query assumes the largest shared-memory carve-out: ask for it, so that the launch sees the same limit
+        (void)cudaFuncSetAttribute(tail_kernel<POSB, LINK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        int ctas = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, tail_kernel<POSB, LINK>, WARPS_PER_CTA * 32, smem);
         if (e != cudaSuccess) return e;
+        C.tail_ctas = ctas < 1 ? 1 : ctas;
     }
-    // the occupancy query assumes the largest shared-memory carve-out: ask for it, so that the launch sees the same limit
-    (void)cudaFuncSetAttribute(tail_kernel<POSB, LINK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    int ctas = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, tail_kernel<POSB, LINK>, WARPS_PER_CTA * 32, smem);
-    if (e != cudaSuccess) return e;
-    if (ctas < 1) ctas = 1;
+    const int ctas = C.tail_ctas;
     // every CTA must be resident (grid barriers); more warps than units would only idle
     int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)sm_count * ctas, (V.n + WARPS_PER_CTA - 1) / WARPS_PER_CTA));
     const ResolvedUnit *res = (const ResolvedUnit *)S.resolved;
@@ -1495,15 +1509,27 @@ static cudaError_t launch_posb(ReadsDev R, const UnitsDev &V, const vfk_params &
     if (S.ev) cudaEventRecord(S.ev[2], stream);
     int ctas_per_sm = 0;
     const size_t warp_smem = WarpSmem<POSB>::BYTES;
-    if (warp_smem > 40 * 1024) {
-        e = link_all ? cudaFuncSetAttribute(pileup_warp_kernel<POSB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem)
-                     : cudaFuncSetAttribute(pileup_warp_kernel<POSB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem);
+    LaunchCache &C = S.cache[posb_index(POSB)];
+    if (!C.ready) {  // once per handle: function attributes and the register kernel's occupancy
+        if (warp_smem > 40 * 1024) {
+            e = link_all ? cudaFuncSetAttribute(pileup_warp_kernel<POSB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem)
+                         : cudaFuncSetAttribute(pileup_warp_kernel<POSB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem);
+            if (e != cudaSuccess) return e;
+        }
+        e = link_all ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pileup_warp_kernel<POSB, false>, WARPS_PER_CTA * 32, warp_smem)
+                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pileup_warp_kernel<POSB, true>, WARPS_PER_CTA * 32, warp_smem);
         if (e != cudaSuccess) return e;
+        C.warp_ctas = ctas_per_sm < 1 ? 1 : ctas_per_sm;
+        if constexpr (WarpSmem<POSB>::HIST_HERE) {
+            using L = Layout<POSB>;
+            e = cudaFuncSetAttribute(medium_kernel<POSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)WARPS_PER_CTA * (L::BINS * 4 + sizeof(MedSmem))));
+            if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(tile_kernel<POSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem<POSB>));
+            if (e != cudaSuccess) return e;
+        }
+        C.ready = true;
     }
-    e = link_all ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pileup_warp_kernel<POSB, false>, WARPS_PER_CTA * 32, warp_smem)
-                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pileup_warp_kernel<POSB, true>, WARPS_PER_CTA * 32, warp_smem);
-    if (e != cudaSuccess) return e;
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    ctas_per_sm = C.warp_ctas;
     // persistent grid: a whole number of waves, never more CTAs than there is work
     int64_t want = (V.n + (int64_t)GRAB * WARPS_PER_CTA - 1) / ((int64_t)GRAB * WARPS_PER_CTA);
     int64_t grid = (int64_t)sm_count * ctas_per_sm;
@@ -1525,8 +1551,6 @@ static cudaError_t launch_posb(ReadsDev R, const UnitsDev &V, const vfk_params &
         if (!link_all) {  // columns with 65 .. MED_CAP candidate reads (the list is empty for a 30x batch: the CTAs leave at once)
             using L = Layout<POSB>;
             const size_t med_smem = (size_t)WARPS_PER_CTA * (L::BINS * 4 + sizeof(MedSmem));
-            e = cudaFuncSetAttribute(medium_kernel<POSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)med_smem);
-            if (e != cudaSuccess) return e;
             const int64_t med_grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)sm_count * 3, (V.n + WARPS_PER_CTA - 1) / WARPS_PER_CTA));
             medium_kernel<POSB><<<(unsigned)med_grid, WARPS_PER_CTA * 32, med_smem, stream>>>(R, res, V.ins_seq, P, out, medium_list, n_medium, warp_list, n_warp);
             ++*launches;
@@ -1537,8 +1561,6 @@ static cudaError_t launch_posb(ReadsDev R, const UnitsDev &V, const vfk_params &
     if constexpr (WarpSmem<POSB>::HIST_HERE) {
         if (!link_all) {  // deep panels: tiles of neighbouring deep units, read-major (no deep unit listed: the CTAs leave at once)
             const size_t tile_smem = sizeof(TileSmem<POSB>);
-            e = cudaFuncSetAttribute(tile_kernel<POSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem);
-            if (e != cudaSuccess) return e;
             const int64_t tile_grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)sm_count, (V.n + TILE_UNITS - 1) / TILE_UNITS));
             tile_kernel<POSB><<<(unsigned)tile_grid, TILE_THREADS, tile_smem, stream>>>(R, res, V.n, V.ins_seq, P, out, n_medium + 1, n_medium + 2);
             ++*launches;
