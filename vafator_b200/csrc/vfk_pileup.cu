@@ -8,16 +8,20 @@
 // from them in the same call (vfk_prep.cu); nothing has been prepared on the host.
 //
 // locate_kernel       : one thread per unit: 8-ary search of the sorted starts for the end of the candidate range,
-//                       binary search of the block-level running maximum of the read ends + one block pass for its start.
-// pileup_warp_kernel  : one warp per unit, lanes = reads spanning the column.  Persistent grid, units handed
-//                       out in contiguous grabs from a global counter (shrinking towards the end).  Handles
-//                       the shallow columns (<= 64 candidates, <= 32 of them contributing -- nearly every
-//                       30x / 60x column): values stay in registers, ranks come from a bit-sliced (radix)
-//                       comparison built on warp ballots.  No shared-memory histograms, no atomics, no
-//                       calls, no stack.  Anything else is appended to one of two device-side lists:
-// pileup_deep_kernel  : one warp per listed unit, histograms in shared memory (u16 counters, two per
-//                       word) + warp scans;
-// pileup_block_kernel : one CTA per listed unit, u32 counters, for columns with > 32767 candidates.
+//                       binary search of the block-level running maximum of the read ends + one chunk pass for its start.
+// pileup_warp_kernel  : one warp per unit, lanes = candidate reads (two slots of 32).  Persistent grid, units handed out in
+//                       contiguous grabs from a global counter (shrinking towards the end).  Every column with <= 64
+//                       candidates -- all of 30x, three quarters of 60x: mate pairing in registers, a read's overlap
+//                       partner answers by shuffle, <= 32 contributing reads are ranked by a bit-sliced (radix) comparison
+//                       built on warp ballots, more go through per-warp shared-memory histograms in the same kernel.
+// medium_kernel       : one warp per listed unit with 65 .. 192 candidates: slots of 32, per-read state and a name-hash table
+//                       in shared memory.
+// tile_kernel         : deep panels: a CTA per group of neighbouring deep units, read-major, htslib's name hash replayed in
+//                       shared memory, a pair of histograms per column in shared memory.
+// tail_kernel         : what is left on the lists (deeper than a tile): global mate linking of the listed windows, one warp
+//                       per unit with u16 histograms, one CTA per unit with u32 counters beyond 32767 candidates; one
+//                       cooperative launch.
+// The three list-path kernels leave at their first line when nothing was listed for them (every 30x call).
 #include <algorithm>
 #include <cstdlib>
 #include <cooperative_groups.h>
@@ -143,7 +147,6 @@ __global__ void __launch_bounds__(256) locate_kernel(ReadsDev R, UnitsDev V, Res
     if (u >= V.n) return;
     store_resolved(res + u, locate_unit(R, V, u));
 }
-constexpr uint32_t LIST_VOID = 0xFFFFFFFFu;
 
 // ------------------------------------------------------------------------------------------
 // histogram access.  CT = uint16_t: two bins per 32-bit word; CT = uint32_t: one bin per word.
@@ -777,7 +780,7 @@ struct TileSmem {
     ResolvedUnit ru[TILE_UNITS];
     uint32_t unit[TILE_UNITS];                       // unit index of column j of the tile
     uint32_t deep[TILE_UNITS];                       // group scan: unit k of the group is a deep, deferred unit
-    uint32_t general, n_cols, t_lo, t_hi, next_k, pad[3];
+    uint32_t n_cols, t_lo, t_hi, next_k;
 };
 
 template <int POSB>
@@ -819,7 +822,7 @@ tile_kernel(const __grid_constant__ ReadsDev R, const ResolvedUnit *__restrict__
                     lo = min(lo, r.lo); hi = max(hi, r.hi);
                     S.unit[n_cols++] = k;
                 }
-                S.next_k = k; S.n_cols = n_cols; S.t_lo = lo; S.t_hi = hi; S.general = 0u;
+                S.next_k = k; S.n_cols = n_cols; S.t_lo = lo; S.t_hi = hi;
             }
             __syncthreads();
             const int J = (int)S.n_cols;

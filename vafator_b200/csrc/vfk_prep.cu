@@ -2,21 +2,16 @@
 // is derived here, on the device, inside every call (the reference starts at bam.pileup(), vafator/pileups.py:71-80,
 // with nothing but the decoded records either).
 //
-//  prep_kernel   one thread per read: walks the CIGAR once -> reference end (htslib bam_endpos), the shape word
-//                (vfk_device.cuh) and the maximum of the end keys per chunk of 32 reads and per block of PREP_BLOCK reads;
+//  offsets_*     (only for a batch that leaves its pool offsets NULL) exclusive prefix sums of n_cigar, (l_qseq + 1) / 2, l_qseq.
+//  prep_kernel   a warp per 128 reads, four consecutive reads per lane: reference end (htslib bam_endpos) and CIGAR shape word
+//                per read (vfk_device.cuh), the maximum of the end keys per chunk of 32 reads and per block of PREP_BLOCK reads;
 //                checks the batch (sorted, starts >= 0, CIGAR inside its pool, lengths in range) and raises
 //                VFK_ST_BADBATCH otherwise.
 //  scan_kernel   inclusive running maximum over the block maxima: the top level of the position index.  A column's
 //                first overlapping read is the first read whose end exceeds it -- found by a binary search over the
 //                blocks, a walk over the chunk maxima of one block and one pass over a chunk (locate_kernel, vfk_pileup.cu).
-//  link kernels  htslib's mate-overlap pairing (sam.c overlap_push / overlap_remove) for the reads
-//                inside the windows of the units on a device-side list -- the histogram paths (deep columns, and
-//                the few shallow ones the register kernel hands on) take a read's partner from `mate[]`; the
-//                register kernel pairs the reads of its column in registers instead.
-//                Emulation of the sequential name hash: the records that reach overlap_push are chained per name
-//                bucket (atomicExch on a bucket head), then every record replays the protocol over the records
-//                that share its name, in file order: found -> pair and delete; not found -> stored if the mate is
-//                still to come; an entry whose record has left the pileup buffer is dropped.
+//  link kernels  the mate-linking passes of vfk_link.cuh as separate launches, for the list-shaped auxiliary
+//                (vfk_pileup_values) and the debug hook that links every unit; the pileup call runs them fused in tail_kernel.
 #include "vfk_link.cuh"
 
 namespace vfk {
