@@ -190,6 +190,21 @@ def test_longer_reads_use_wider_position_range(dev, read_len):
     assert int(want["med2"][:, 2, :].max()) > 2 * 255  # medians of read positions beyond one byte
 
 
+@pytest.mark.parametrize("pairs", [60, 300, 1400])
+def test_longer_reads_through_the_medium_tile_and_tail_paths(dev, pairs):
+    """300-bp reads (the 512-bin instantiations) at depths that take the medium kernel (65..192 candidates), the tile kernel
+    (<= 2048 reads per tile) and the tail kernel (deeper than a tile)."""
+    cfg = synth.wes(n_tiles=40 if pairs > 1000 else 160, read_len=300, frag_mean=660.0, frag_sd=60.0, tile_len=600, var_lo=300, var_hi=900,
+                    snv_period=60, indel_period=400, pairs_per_tile=pairs)
+    batch, recs, units, stop, ounits = _setup(cfg)
+    assert batch.l_qseq.max() == 300 and units.n_units > 100
+    want = c_oracle.pileup(batch.as_dict(), ounits, c_oracle.params(min_mapq=1, min_baseq=30))
+    got = _gpu(dev, batch, units, stop, 1, 30)
+    _compare(got, want)
+    lo, hi = {60: (64, 192), 300: (192, 2048), 1400: (2048, 1 << 30)}[pairs]
+    assert np.mean((got["n_cand"] > lo) & (got["n_cand"] <= hi)) > 0.3, np.percentile(got["n_cand"], [5, 50, 95])
+
+
 def test_degenerate_inputs(dev):
     """Empty read batch, contig without reads, column 0, every read filtered out."""
     from vafator_b200.batch import ReadBatch
