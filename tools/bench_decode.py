@@ -1,5 +1,6 @@
-"""Host-side timing of the file path around the kernels (no GPU): BGZF/BAM decode, packing into the HBM
-layout, mate linking, column-store build -- on a synthetic coordinate-sorted BAM written here.
+"""Host-side timing of the file path around the kernels (no GPU): BGZF/BAM decode into the canonical columnar batch -- whole
+file, one region, a tenth of a contig -- on a synthetic coordinate-sorted BAM written here.  (Everything derived from the
+records is the kernels' work now: there is no host packing or mate linking left to time.)
 
     python tools/bench_decode.py [--mbp 3] [--threads N]
 """
@@ -11,7 +12,7 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from vafator_b200 import bamio, device, synth  # noqa: E402
+from vafator_b200 import bamio, synth  # noqa: E402
 
 
 def main():
@@ -43,13 +44,6 @@ def main():
     print("decode (.bai, whole contig as one region)  %.3f s  %.2f M reads/s" % (t, reg.n_reads / t / 1e6))
     t, reg = best(lambda: bamio.BamFile(args.out).read_batch([(batch.contigs[0], L // 2, L // 2 + L // 10)]))
     print("decode (.bai, a tenth of the contig)       %.3f s  %.2f M reads/s (%d reads)" % (t, reg.n_reads / t / 1e6, reg.n_reads))
-    params = device.make_params(min_mapq=1, min_baseq=30)
-    t, mate = best(lambda: device.link_mates(got, params))
-    print("link_mates      %.3f s  %.2f M reads/s" % (t, got.n_reads / t / 1e6))
-    t, _ = best(lambda: device.pack_reads(got, params, mate=mate, columns=False))
-    print("pack            %.3f s  %.2f M reads/s" % (t, got.n_reads / t / 1e6))
-    t, _ = best(lambda: device.pack_reads(got, params, mate=mate, columns=True))
-    print("pack + columns  %.3f s  %.2f M reads/s" % (t, got.n_reads / t / 1e6))
 
 
 if __name__ == "__main__":

@@ -1,6 +1,6 @@
 #!/bin/bash
-# The CPU test suite against an AddressSanitizer + UndefinedBehaviorSanitizer build of libvfkio.so (decoder, inflate,
-# packing, column store, synthesis).  The release library is put back afterwards.   usage: tools/sanitize_host.sh
+# The CPU test suite against an AddressSanitizer + UndefinedBehaviorSanitizer build of libvfkio.so (BGZF / BAM decoder, inflate,
+# synthesis).  The release library is put back afterwards.   usage: tools/sanitize_host.sh
 set -u
 cd "$(dirname "$0")/.."
 lib=vafator_b200/libvfkio.so
