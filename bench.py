@@ -418,6 +418,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    if world > 1 and "VFK_HOST_THREADS" not in os.environ:  # the host threads of the fetch-list gather: the box's cores shared out
+        os.environ["VFK_HOST_THREADS"] = str(max(2, min(16, len(os.sched_getaffinity(0)) // world)))
     dev = device.Device(local_rank)
     params = device.make_params(min_mapq=MIN_MAPQ, min_baseq=MIN_BASEQ, include_ambiguous=True)
     w = Workload(args.config, args)
@@ -486,8 +488,9 @@ def main():
     # ---- end to end: page-locked canonical host arrays -> results on the host, through vfk_annotate_host_async ----
     e2e = None
     if not args.no_e2e:
-        c_out = [np.empty(b["units"].n_units, device.COUNTS_DTYPE) for b in subs]
-        s_out = [np.empty(b["units"].n_units, device.STATS_DTYPE) for b in subs]
+        # results land in page-locked arrays (pageable ones work too: the library then bounces them, one more host copy in vfk_wait)
+        c_out = [device.pinned_empty(b["units"].n_units, device.COUNTS_DTYPE) for b in subs]
+        s_out = [device.pinned_empty(b["units"].n_units, device.STATS_DTYPE) for b in subs]
 
         def e2e_step():
             # two batches in flight: the library double-buffers, the copies of one batch overlap the kernels of the previous
@@ -524,17 +527,25 @@ def main():
         assert at == len(subs)
         staged = (ts1["staged_bytes"] - ts0["staged_bytes"]) / n_e2e
         zero_copy = (ts1["zero_copy_batches"] - ts0["zero_copy_batches"]) / (n_e2e * len(subs))
-        d2h = (ts1["d2h_bytes"] - ts0["d2h_bytes"]) / n_e2e
+        pairs = (ts1["fetch_pairs"] - ts0["fetch_pairs"]) / n_e2e
+        gather_ms = (ts1["fetch_ns"] - ts0["fetch_ns"]) / n_e2e / 1e6
+        d2h = (ts1["d2h_bytes"] - ts0["d2h_bytes"]) / n_e2e + 16.0 * pairs  # results + the fetch list's requests (written by the kernel)
         if rx_rate is not None:
             h2d, h2d_how = rx_rate * dt_e2e, "NVML PCIe RX counter sampled over the timed region x step time"
         else:
             # fallback when NVML has no counter: the library's own count of copied bytes + per candidate read the in-place reads
             # (header fields 27 B, quality + base sectors 64 B)
             h2d, h2d_how = staged + zero_copy * units_per_step * n_cand * 91.0, "library-counted copies + 91 B per candidate read (no NVML counter)"
-        transfer = ("page-locked canonical arrays: starts / CIGARs / read lengths copied (%.0f MB per step, counted by the library), every other "
+        transfer = ("page-locked canonical arrays: starts / CIGARs / read lengths copied; the quality and sequence byte of every (column, read) pair "
+                    "named by the device on a fetch list (%.1f M pairs per step, 16 B each written to the host), gathered by %d host threads between "
+                    "two kernels of the call and copied back (bulk copies: %.0f MB per step, counted by the library); flags / MAPQ / mate fields / name "
+                    "ids read in place over PCIe for the reads that overlap a column; two batches in flight"
+                    % (pairs / 1e6, ts1["fetch_threads"], staged / 1e6)) if zero_copy > 0.5 and pairs > 0 else \
+                   ("page-locked canonical arrays: starts / CIGARs / read lengths copied (%.0f MB per step, counted by the library), every other "
                     "array read in place over PCIe for the reads that overlap a column; two batches in flight" % (staged / 1e6)) if zero_copy > 0.5 else \
                    "every array staged by async copies (%.0f MB per step); two batches in flight" % (staged / 1e6)
-        e2e = dict(dt=dt_e2e, h2d=h2d, d2h=d2h, transfer=transfer, staged=staged, h2d_how=h2d_how, rx_gbs=None if rx_rate is None else rx_rate / 1e9)
+        e2e = dict(dt=dt_e2e, h2d=h2d, d2h=d2h, transfer=transfer, staged=staged, h2d_how=h2d_how, rx_gbs=None if rx_rate is None else rx_rate / 1e9,
+                   pairs=pairs, gather_ms=gather_ms, threads=ts1["fetch_threads"])
 
     # ---- max over ranks ----
     if dist is not None:
@@ -602,6 +613,8 @@ def main():
                                             "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),
                                             "ms_per_step": 1e3 * e2e["dt"], "h2d_measured_by": e2e["h2d_how"],
                                             "h2d_copied_bytes_per_step_rank0": int(e2e["staged"]), "pcie_rx_gbs_rank0": e2e["rx_gbs"],
+                                            "fetch_pairs_per_step_rank0": int(e2e["pairs"]), "host_gather_ms_per_step_rank0": round(e2e["gather_ms"], 3),
+                                            "host_gather_threads": e2e["threads"],
                                             "transfer": e2e["transfer"]},
             "gpu_launches": int(launches), "clocks": clk,
         }

@@ -183,6 +183,12 @@ int vfk_wait(vfk_handle *h, int ticket);
  * bulk copies, out[1] batches whose arrays were read in place (zero copy), out[2] batches staged in full,
  * out[3] bytes copied device -> host                                                               */
 int vfk_transfer_stats(vfk_handle *h, int64_t out[4]);
+/* fetch lists of the host entry point since vfk_create (batches read in place: the one quality byte and the one sequence
+ * byte a column needs of each read are named by the device, gathered by host threads between two kernels of the call and
+ * copied in bulk, instead of being read over the bus one request each): out[0] (unit, read) pairs gathered, out[1] batches
+ * that carried a list, out[2] nanoseconds the host spent gathering, out[3] host threads of a gather.  Environment, read by vfk_create: VFK_HOST_FETCH=0 switches the lists off, VFK_HOST_THREADS=n sets
+ * the host threads of the gather (default: the OpenMP maximum, at most 16).                                            */
+int vfk_fetch_stats(vfk_handle *h, int64_t out[4]);
 
 /* ---- list-shaped auxiliaries (DEVICE pointers) ------------------------------------------------
  * vfk_pileup_values: per unit, the per-read values the reference keeps in all_mqs / all_bqs /

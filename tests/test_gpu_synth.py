@@ -190,7 +190,7 @@ def test_longer_reads_use_wider_position_range(dev, read_len):
     assert int(want["med2"][:, 2, :].max()) > 2 * 255  # medians of read positions beyond one byte
 
 
-@pytest.mark.parametrize("pairs", [60, 300, 1400])
+@pytest.mark.parametrize("pairs", [160, 500, 4000])
 def test_longer_reads_through_the_medium_tile_and_tail_paths(dev, pairs):
     """300-bp reads (the 512-bin instantiations) at depths that take the medium kernel (65..192 candidates), the tile kernel
     (<= 2048 reads per tile) and the tail kernel (deeper than a tile)."""
@@ -201,7 +201,7 @@ def test_longer_reads_through_the_medium_tile_and_tail_paths(dev, pairs):
     want = c_oracle.pileup(batch.as_dict(), ounits, c_oracle.params(min_mapq=1, min_baseq=30))
     got = _gpu(dev, batch, units, stop, 1, 30)
     _compare(got, want)
-    lo, hi = {60: (64, 192), 300: (192, 2048), 1400: (2048, 1 << 30)}[pairs]
+    lo, hi = {160: (64, 192), 500: (192, 2048), 4000: (2048, 1 << 30)}[pairs]
     assert np.mean((got["n_cand"] > lo) & (got["n_cand"] <= hi)) > 0.3, np.percentile(got["n_cand"], [5, 50, 95])
 
 
@@ -226,14 +226,22 @@ def test_degenerate_inputs(dev):
     assert got["dp"].tolist() == [1, 1, 0, 0] and got["n_cover"].tolist() == [3, 3, 0, 0] and got["ac_ref"].tolist() == [1, 1, 0, 0]
 
 
-@pytest.mark.parametrize("mode", ["pageable", "pinned", "pinned_stage_all"])
+@pytest.mark.parametrize("mode", ["pageable", "pinned", "pinned_stage_all", "pinned_no_fetch", "pinned_short_list", "pinned_explicit_offsets"])
 def test_host_entry_point_transfer_strategies(mode, monkeypatch):
     """vfk_annotate_host moves a batch in one of two ways -- page-locked arrays: the position-index inputs are copied, the
-    rest is read in place over PCIe; pageable arrays (or VFK_HOST_STAGE_ALL=1 when the handle is created): everything is
-    staged -- and returns exactly what the device-pointer entry points return, for VCF-ordered and for shuffled units."""
+    rest is read in place over PCIe, except the base / quality bytes at the columns, which the device asks for on a fetch
+    list and host threads gather (VFK_HOST_FETCH=0: read in place too; a list too short for the call: the units that do not
+    fit read in place; a batch that hands over its pool offsets: requests by read index); pageable arrays (or
+    VFK_HOST_STAGE_ALL=1 when the handle is created): everything is staged -- and returns exactly what the device-pointer
+    entry points return, for VCF-ordered and for shuffled units."""
     from dataclasses import replace
     if mode == "pinned_stage_all":
         monkeypatch.setenv("VFK_HOST_STAGE_ALL", "1")
+    if mode == "pinned_no_fetch":
+        monkeypatch.setenv("VFK_HOST_FETCH", "0")
+    if mode == "pinned_short_list":
+        monkeypatch.setenv("VFK_HOST_FETCH_SLACK", "0.4")
+    in_place = mode in ("pinned", "pinned_no_fetch", "pinned_short_list", "pinned_explicit_offsets")
     dev = device.Device(0)
     cfg = synth.wes(n_tiles=3000, indel_period=700, multiallelic_pct=5)
     batch, recs, units, stop, _ = _setup(cfg)
@@ -242,7 +250,7 @@ def test_host_entry_point_transfer_strategies(mode, monkeypatch):
     shuffled = replace(units, tid=units.tid[perm], pos=units.pos[perm], meta=units.meta[perm], length=units.length[perm],
                        seq_off=units.seq_off[perm], rec=units.rec[perm], alt_index=units.alt_index[perm])
     params = device.make_params(min_mapq=1, min_baseq=30)
-    host = device.host_reads(batch, pinned=mode != "pageable")
+    host = device.host_reads(batch, pinned=mode != "pageable", implicit_offsets=False if mode == "pinned_explicit_offsets" else None)
     dreads = dev.upload_reads(host)
     eaf = np.full(units.n_units, 0.4)
     for u, s in ((units, stop), (shuffled, stop[perm])):
@@ -256,11 +264,20 @@ def test_host_entry_point_transfer_strategies(mode, monkeypatch):
         after = dev.transfer_stats()
         assert got_c.tobytes() == want_c.tobytes()
         assert got_s.tobytes() == want_s.tobytes()
-        assert (after["zero_copy_batches"] - before["zero_copy_batches"]) == (1 if mode == "pinned" else 0)
-        assert (after["staged_batches"] - before["staged_batches"]) == (0 if mode == "pinned" else 1)
+        assert (after["zero_copy_batches"] - before["zero_copy_batches"]) == (1 if in_place else 0)
+        assert (after["staged_batches"] - before["staged_batches"]) == (0 if in_place else 1)
+        pairs = after["fetch_pairs"] - before["fetch_pairs"]
+        if in_place and mode != "pinned_no_fetch":
+            n_cand = int(want_c["n_cand"].astype(np.int64)[want_c["n_cand"] <= 64].sum())
+            assert after["fetch_batches"] - before["fetch_batches"] == 1
+            # every candidate of every register-kernel unit is on the list -- or, with a list cut short, as many as it holds
+            assert pairs == n_cand if mode != "pinned_short_list" else 0 < pairs < n_cand
+        else:
+            assert pairs == 0
         # two batches in flight through the double-buffered entry
         c2 = [np.empty(u.n_units, device.COUNTS_DTYPE) for _ in range(3)]
         s2 = [np.empty(u.n_units, device.STATS_DTYPE) for _ in range(3)]
+        c2[1], s2[2] = device.pinned_empty(u.n_units, device.COUNTS_DTYPE), device.pinned_empty(u.n_units, device.STATS_DTYPE)  # written directly
         tickets = []
         for k in range(3):
             if k >= 2:

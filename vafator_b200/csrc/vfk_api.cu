@@ -4,6 +4,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <new>
+#include <omp.h>
 #include "vfk.h"
 #include "vfk_device.cuh"
 
@@ -24,6 +25,13 @@ struct PileupScratch {
     uint32_t *mate;
     cudaEvent_t *ev;
     LaunchCache *cache;
+    uint32_t fetch_cap;
+    int fetch_by_index;
+    uint32_t *fetch_base;
+    void *fetch_req;
+    const uint16_t *fetched;
+    cudaError_t (*fetch_between)(void *ctx, const uint32_t *pair_counter, cudaStream_t stream);
+    void *fetch_ctx;
 };
 cudaError_t launch_prep(const ReadsDev &R, uint2 *ee_out, int64_t *chunk_max, int64_t *blk_max, int64_t *blk_incl, uint32_t *batch_status,
                         cudaStream_t stream, int *launches);
@@ -141,6 +149,7 @@ struct Work {
         s.claimed = (uint32_t *)claimed.p; s.mate = (uint32_t *)mate.p;
         s.ev = nullptr;
         s.cache = nullptr;
+        s.fetch_cap = 0u; s.fetch_by_index = 0; s.fetch_base = nullptr; s.fetch_req = nullptr; s.fetched = nullptr; s.fetch_between = nullptr; s.fetch_ctx = nullptr;
         return s;
     }
     void release() {
@@ -156,20 +165,82 @@ struct Work {
     }
 };
 
+// The host's part of a fetch list (vfk_pileup.cu request_kernel): between the two kernels of a call, in stream order, the bytes
+// the device asked for are gathered from the caller's arrays into a page-locked buffer that one bulk copy takes to the device.
+struct FetchJob {
+    const ulonglong2 *req = nullptr;  // written by request_kernel
+    uint16_t *out = nullptr;          // quality | sequence byte << 8 per pair
+    const uint32_t *h_total = nullptr;
+    uint32_t cap = 0;
+    const uint8_t *qual = nullptr, *seq = nullptr;
+    const int64_t *qual_off = nullptr, *seq_off = nullptr;  // the caller's offset arrays when requests go by read index, else NULL
+    int64_t n_reads = 0, n_qual = 0, n_seq = 0;
+    int threads = 1;
+    int64_t *pairs = nullptr, *nanos = nullptr;  // handle statistics: pairs gathered, wall time of the gathers
+};
+
+static void CUDART_CB fetch_cb(void *p) {
+    const FetchJob &j = *(const FetchJob *)p;
+    const double t0 = omp_get_wtime();
+    const int64_t n = (int64_t)(*j.h_total < j.cap ? *j.h_total : j.cap);
+    const int64_t n_blk = (n + 63) / 64;
+    const unsigned long long none = ~0ull;
+#pragma omp parallel for schedule(static) num_threads(j.threads)
+    for (int64_t b = 0; b < n_blk; ++b) {
+        const int64_t p0 = b * 64, p1 = p0 + 64 < n ? p0 + 64 : n;
+        uint64_t qa[64], sa[64];
+        for (int64_t q = p0; q < p1; ++q) {  // addresses first, every line asked for before the first one is used
+            const ulonglong2 r = j.req[q];
+            uint64_t a = none, c = 0;
+            if (r.x != none) {
+                if (j.qual_off) {
+                    if ((int64_t)r.x < j.n_reads) { a = (uint64_t)j.qual_off[r.x] + r.y; c = (uint64_t)j.seq_off[r.x] + (r.y >> 1); }
+                } else {
+                    a = r.x; c = r.y;
+                }
+                if (a >= (uint64_t)j.n_qual || c >= (uint64_t)j.n_seq) a = none;  // a malformed batch must not take the host down
+            }
+            qa[q - p0] = a; sa[q - p0] = c;
+            if (a != none) {
+                __builtin_prefetch(j.qual + a);
+                __builtin_prefetch(j.seq + c);
+            }
+        }
+        for (int64_t q = p0; q < p1; ++q) {
+            const uint64_t a = qa[q - p0];
+            j.out[q] = a == none ? (uint16_t)0 : (uint16_t)(j.qual[a] | ((uint16_t)j.seq[sa[q - p0]] << 8));
+        }
+    }
+    if (j.pairs) __atomic_fetch_add(j.pairs, n, __ATOMIC_RELAXED);
+    if (j.nanos) __atomic_fetch_add(j.nanos, (int64_t)((omp_get_wtime() - t0) * 1e9), __ATOMIC_RELAXED);
+}
+
 // One of the two staging slots of the host entry point: its own stream, working memory and device staging
 // buffers, so that the copies of one batch overlap the kernels of the previous one (double buffering).
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
     bool busy = false;
-    uint32_t *h_status = nullptr;  // pinned: the batch status word of the slot's last batch
+    uint32_t *h_status = nullptr;  // pinned: [0] the batch status word of the slot's last batch, [1] pairs on its fetch list
     Work work;
+    // Pageable unit arrays / result buffers would make their "asynchronous" copies synchronous (the call would return only once
+    // the whole batch is through, and the two slots would never overlap): they go through page-locked bounce buffers, the
+    // results reaching the caller's arrays in vfk_wait.
+    PinBuf h_in, h_counts, h_stats;
+    vfk_counts *user_counts = nullptr;
+    vfk_stats *user_stats = nullptr;
+    int64_t user_n = 0;
+    PinBuf fetch_req, fetch_out;   // fetch list: requests (written by the device), gathered bytes
+    DevBuf fetch_base, fetched;
+    FetchJob job;
     DevBuf contig, pos, flag, mapq, l_qseq, n_cigar, cigar_off, seq_off, qual_off, cigar, seq, qual, mtid, mpos, isize, qname_id, qname_hash;
     DevBuf tid, upos, meta, len, soff, ins, stop, eaf, counts, stats;
     void release() {
         DevBuf *bufs[] = {&contig, &pos, &flag, &mapq, &l_qseq, &n_cigar, &cigar_off, &seq_off, &qual_off, &cigar, &seq, &qual, &mtid, &mpos,
                           &isize, &qname_id, &qname_hash, &tid, &upos, &meta, &len, &soff, &ins, &stop, &eaf, &counts, &stats};
         for (DevBuf *b : bufs) b->release();
+        fetch_base.release(); fetched.release(); fetch_req.release(); fetch_out.release();
+        h_in.release(); h_counts.release(); h_stats.release();
         work.release();
         if (h_status) cudaFreeHost(h_status);
         if (done) cudaEventDestroy(done);
@@ -190,6 +261,10 @@ struct vfk_handle {
     vfk::LaunchCache launch_cache[4] = {};  // per position-range instantiation of the pileup kernels (vfk_pileup.cu)
     bool link_all = false;   // debug hook (VFK_DEBUG_LINK_ALL=1 when the handle is created): partners from the link kernels everywhere
     bool stage_all = false;  // VFK_HOST_STAGE_ALL=1 when the handle is created: the host entry point copies every array
+    bool fetch = true;       // in-place batches get their base / quality bytes through a fetch list (VFK_HOST_FETCH=0 when the handle is created: off)
+    double fetch_slack = 1.15;  // list capacity = units x (sampled depth x slack + 6); VFK_HOST_FETCH_SLACK at creation (tests: a short list)
+    int fetch_threads = 1;   // host threads of the gather (VFK_HOST_THREADS at creation, else up to 16 of the cores)
+    int64_t fetch_pairs = 0, fetch_batches = 0, fetch_nanos = 0;
     // Carter k / d per depth for the last (fpr, error_rate) seen, depths [0, CARTER_DEPTHS)
     DevBuf carter;
     double carter_fpr = -1.0, carter_err = -1.0;
@@ -242,6 +317,15 @@ extern "C" int vfk_create(int device, vfk_handle **out) {
     h->link_all = env_on("VFK_DEBUG_LINK_ALL");
     h->stage_all = env_on("VFK_HOST_STAGE_ALL");
     {
+        const char *v = getenv("VFK_HOST_FETCH");
+        h->fetch = !(v && v[0] == '0');
+        if ((v = getenv("VFK_HOST_FETCH_SLACK")) && atof(v) > 0.0) h->fetch_slack = atof(v);
+        int t = omp_get_max_threads();
+        if ((v = getenv("VFK_HOST_THREADS")) && atoi(v) > 0) t = atoi(v);
+        else if (t > 16) t = 16;
+        h->fetch_threads = t < 1 ? 1 : t;
+    }
+    {
         // The path gathers single 32-byte sectors (one quality byte, one sequence byte per (read, column) pair):
         // ask L2 not to promote misses to 64/128-byte DRAM fetches.  A hint; failure is harmless.
         (void)cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
@@ -251,8 +335,8 @@ extern "C" int vfk_create(int device, vfk_handle **out) {
         CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
         CU(cudaMalloc(&s.work.counters, COUNTER_BYTES));
-        CU(cudaMallocHost((void **)&s.h_status, sizeof(uint32_t)));
-        *s.h_status = 0u;
+        CU(cudaMallocHost((void **)&s.h_status, 2 * sizeof(uint32_t)));
+        s.h_status[0] = s.h_status[1] = 0u;
     }
     CU(cudaMalloc(&h->work.counters, COUNTER_BYTES));
     *out = h;
@@ -481,6 +565,10 @@ extern "C" int vfk_wait(vfk_handle *h, int ticket) {
     CU(cudaSetDevice(h->device));
     CU(cudaEventSynchronize(s.done));
     s.busy = false;
+    if (s.user_counts) memcpy(s.user_counts, s.h_counts.p, (size_t)s.user_n * sizeof(vfk_counts));
+    if (s.user_stats) memcpy(s.user_stats, s.h_stats.p, (size_t)s.user_n * sizeof(vfk_stats));
+    s.user_counts = nullptr;
+    s.user_stats = nullptr;
     if (*s.h_status & VFK_ST_BADBATCH)
         return fail(VFK_EINVAL, "malformed read batch (not coordinate sorted, negative start, CIGAR outside its pool or read too long)");
     return VFK_OK;
@@ -513,6 +601,16 @@ static double sampled_depth(const vfk_read_batch *r, const vfk_variant_batch *v)
     return n ? sum / n : 0.0;
 }
 
+// fetch list, between request_kernel and the register kernel (stream order): how many pairs, the host's gather, the bytes back
+static cudaError_t fetch_between(void *ctx, const uint32_t *pair_counter, cudaStream_t st) {
+    Slot &S = *(Slot *)ctx;
+    cudaError_t e = cudaMemcpyAsync(S.h_status + 1, pair_counter, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return e;
+    e = cudaLaunchHostFunc(st, fetch_cb, &S.job);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(S.fetched.p, S.fetch_out.p, (size_t)S.job.cap * sizeof(uint16_t), cudaMemcpyHostToDevice, st);
+}
+
 // copy `bytes` of a host array into the slot's staging buffer; *dst = the device copy
 #define STAGE(buf, src, bytes, dst)                                                              \
     do {                                                                                         \
@@ -525,6 +623,20 @@ static double sampled_depth(const vfk_read_batch *r, const vfk_variant_batch *v)
         }                                                                                        \
         h->staged_bytes += (int64_t)b_;                                                          \
         (dst) = (decltype(dst))(buf).p;                                                          \
+    } while (0)
+
+// the same for a small host array that may be pageable: through the slot's page-locked bounce arena (at *used), so that the copy
+// is asynchronous whatever memory the caller handed over
+#define STAGE_SMALL(buf, src, bytes, dst)                                                        \
+    do {                                                                                         \
+        size_t n_ = (size_t)(bytes);                                                             \
+        const void *from_ = (src);                                                               \
+        if (n_ && !pinned_alias(from_)) {                                                        \
+            memcpy((char *)S.h_in.p + arena_used, from_, n_);                                    \
+            from_ = (char *)S.h_in.p + arena_used;                                               \
+            arena_used += (n_ + 63) & ~(size_t)63;                                               \
+        }                                                                                        \
+        STAGE(buf, from_, n_, dst);                                                              \
     } while (0)
 
 extern "C" int vfk_annotate_host_async(vfk_handle *h, const vfk_read_batch *reads, const vfk_variant_batch *units,
@@ -546,6 +658,7 @@ extern "C" int vfk_annotate_host_async(vfk_handle *h, const vfk_read_batch *read
     vfk_read_batch dr = *reads;
     vfk_variant_batch dv = *units;
     int launches = 0;
+    size_t arena_used = 0;
     cudaError_t e = cudaSuccess;
     // ---- how the read arrays reach the kernels.  Page-locked arrays: only what the position index is built from (starts,
     // CIGARs, read lengths: ~25 bytes per read) is copied; flags, qualities, bases, mate fields and name ids are read in place
@@ -555,18 +668,21 @@ extern "C" int vfk_annotate_host_async(vfk_handle *h, const vfk_read_batch *read
                          pinned_alias(reads->seq), pinned_alias(reads->qual), pinned_alias(reads->mtid), pinned_alias(reads->mpos),
                          pinned_alias(reads->isize), pinned_alias(reads->qname_id), pinned_alias(reads->qname_hash)};
     bool zero_copy = !h->stage_all && nr > 0;
+    double depth = 0.0;
+    vfk::PileupScratch scratch;
     for (int k = 0; k < 11; ++k) zero_copy = zero_copy && (z[k] != nullptr || (implicit && (k == 2 || k == 3)));
     if (zero_copy) {
         // In place pays per (unit, candidate read) pair -- about 256 bytes cross the bus for each (a dozen arrays, 64-byte requests) --
         // a bulk copy pays per read.  Sparse variant sets against 30x / 60x reads touch a fifth of the batch: in place.  A deep
         // panel touches every read many times over: staged.  The depth is estimated from a sample of the units.
-        const double touches = (double)nu * sampled_depth(reads, units);
+        depth = sampled_depth(reads, units);
+        const double touches = (double)nu * depth;
         const double per_read = 43.0 + (double)(reads->n_seq_bytes + reads->n_qual_bytes) / (double)nr;
         zero_copy = touches * 256.0 < (double)nr * per_read;
     }
     rc = S.work.reserve(nr, nu, st);
     if (rc) goto failed;
-    STAGE(S.contig, reads->contig_off, (size_t)(reads->n_contigs + 1) * sizeof(int64_t), dr.contig_off);
+    STAGE(S.contig, reads->contig_off, (size_t)(reads->n_contigs + 1) * sizeof(int64_t), dr.contig_off);  // (a few hundred bytes: synchronous at worst on an idle stream)
     STAGE(S.pos, reads->pos, (size_t)nr * 4, dr.pos);
     STAGE(S.n_cigar, reads->n_cigar, (size_t)nr * 4, dr.n_cigar);
     if (!implicit) STAGE(S.cigar_off, reads->cigar_off, (size_t)nr * 8, dr.cigar_off);
@@ -593,16 +709,18 @@ extern "C" int vfk_annotate_host_async(vfk_handle *h, const vfk_read_batch *read
         STAGE(S.qname_hash, reads->qname_hash, (size_t)nr * 4, dr.qname_hash);
         ++h->staged_batches;
     }
-    STAGE(S.tid, units->tid, (size_t)nu * 4, dv.tid);
-    STAGE(S.upos, units->pos, (size_t)nu * 4, dv.pos);
-    STAGE(S.meta, units->meta, (size_t)nu * 4, dv.meta);
-    STAGE(S.len, units->length, (size_t)nu * 4, dv.length);
-    STAGE(S.soff, units->seq_off, (size_t)nu * 4, dv.seq_off);
-    STAGE(S.ins, units->ins_seq, (size_t)(units->n_ins_seq > 0 ? units->n_ins_seq : 1), dv.ins_seq);
-    if (units->stop) STAGE(S.stop, units->stop, (size_t)nu * 4, dv.stop);
+    rc = S.h_in.reserve((size_t)nu * (6 * 4 + 8) + (size_t)(units->n_ins_seq > 0 ? units->n_ins_seq : 1) + (size_t)(reads->n_contigs + 1) * 8 + 16 * 64);
+    if (rc) goto failed;
+    STAGE_SMALL(S.tid, units->tid, (size_t)nu * 4, dv.tid);
+    STAGE_SMALL(S.upos, units->pos, (size_t)nu * 4, dv.pos);
+    STAGE_SMALL(S.meta, units->meta, (size_t)nu * 4, dv.meta);
+    STAGE_SMALL(S.len, units->length, (size_t)nu * 4, dv.length);
+    STAGE_SMALL(S.soff, units->seq_off, (size_t)nu * 4, dv.seq_off);
+    STAGE_SMALL(S.ins, units->ins_seq, (size_t)(units->n_ins_seq > 0 ? units->n_ins_seq : 1), dv.ins_seq);
+    if (units->stop) STAGE_SMALL(S.stop, units->stop, (size_t)nu * 4, dv.stop);
     {
         const double *d_eaf = nullptr;
-        STAGE(S.eaf, eaf, (size_t)nu * sizeof(double), d_eaf);
+        STAGE_SMALL(S.eaf, eaf, (size_t)nu * sizeof(double), d_eaf);
         rc = S.counts.reserve((size_t)nu * sizeof(vfk_counts));
         if (rc) goto failed;
         rc = S.stats.reserve((size_t)nu * sizeof(vfk_stats));
@@ -612,7 +730,28 @@ extern "C" int vfk_annotate_host_async(vfk_handle *h, const vfk_read_batch *read
         to_dev(&dr, &dv, S.work, R, V);
         rc = enqueue_prep(h, S.work, R, st, &launches);
         if (rc) goto failed;
-        e = vfk::launch_pileup(R, V, *params, reads->max_l_qseq, (vfk_counts *)S.counts.p, scratch_of(h, S.work), h->sm_count, st, &launches,
+        scratch = scratch_of(h, S.work);
+        if (zero_copy && h->fetch && !h->link_all && nu < ((int64_t)1 << 25)) {
+            // the reads' base / quality bytes at the columns: asked for by the device, gathered by the host, copied in bulk
+            double want = (double)nu * (depth * h->fetch_slack + 6.0) + 1024.0;
+            if (want > (double)nu * 64.0) want = (double)nu * 64.0;
+            const uint32_t cap = (uint32_t)want;
+            if ((rc = S.fetch_req.reserve((size_t)cap * 16)) || (rc = S.fetch_out.reserve((size_t)cap * 2)) || (rc = S.fetched.reserve((size_t)cap * 2)) ||
+                (rc = S.fetch_base.reserve((size_t)nu * 4)))
+                goto failed;
+            FetchJob &J = S.job;
+            J.req = (const ulonglong2 *)S.fetch_req.p; J.out = (uint16_t *)S.fetch_out.p; J.h_total = S.h_status + 1; J.cap = cap;
+            J.qual = reads->qual; J.seq = reads->seq;
+            J.qual_off = implicit ? nullptr : reads->qual_off; J.seq_off = implicit ? nullptr : reads->seq_off;
+            J.n_reads = nr; J.n_qual = reads->n_qual_bytes; J.n_seq = reads->n_seq_bytes;
+            J.threads = h->fetch_threads; J.pairs = &h->fetch_pairs; J.nanos = &h->fetch_nanos;
+            scratch.fetch_cap = cap; scratch.fetch_by_index = implicit ? 0 : 1;
+            scratch.fetch_base = (uint32_t *)S.fetch_base.p; scratch.fetch_req = (void *)pinned_alias(S.fetch_req.p);
+            scratch.fetched = (const uint16_t *)S.fetched.p; scratch.fetch_between = fetch_between; scratch.fetch_ctx = &S;
+            if (!scratch.fetch_req) scratch.fetch_cap = 0u;
+            else { ++h->fetch_batches; h->staged_bytes += (int64_t)cap * 2; }
+        }
+        e = vfk::launch_pileup(R, V, *params, reads->max_l_qseq, (vfk_counts *)S.counts.p, scratch, h->sm_count, st, &launches,
                                h->link_all);
         if (e != cudaSuccess) { rc = fail(VFK_ECUDA, "pileup launch: %s", cudaGetErrorString(e)); goto failed; }
         rc = ensure_carter(h, fpr, error_rate, st);
@@ -626,11 +765,27 @@ extern "C" int vfk_annotate_host_async(vfk_handle *h, const vfk_read_batch *read
         }
     }
     h->launches += launches;
-    if (cudaMemcpyAsync(counts_out, S.counts.p, (size_t)nu * sizeof(vfk_counts), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-        cudaMemcpyAsync(stats_out, S.stats.p, (size_t)nu * sizeof(vfk_stats), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-        cudaMemcpyAsync(S.h_status, (char *)S.work.counters + 20, sizeof(uint32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess) {
-        rc = fail(VFK_ECUDA, "cudaMemcpyAsync(results) failed");
-        goto failed;
+    {
+        void *c_to = counts_out, *s_to = stats_out;
+        if (!pinned_alias(counts_out)) {
+            rc = S.h_counts.reserve((size_t)nu * sizeof(vfk_counts));
+            if (rc) goto failed;
+            c_to = S.h_counts.p;
+        }
+        if (!pinned_alias(stats_out)) {
+            rc = S.h_stats.reserve((size_t)nu * sizeof(vfk_stats));
+            if (rc) goto failed;
+            s_to = S.h_stats.p;
+        }
+        if (cudaMemcpyAsync(c_to, S.counts.p, (size_t)nu * sizeof(vfk_counts), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemcpyAsync(s_to, S.stats.p, (size_t)nu * sizeof(vfk_stats), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemcpyAsync(S.h_status, (char *)S.work.counters + 20, sizeof(uint32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess) {
+            rc = fail(VFK_ECUDA, "cudaMemcpyAsync(results) failed");
+            goto failed;
+        }
+        S.user_counts = c_to == (void *)counts_out ? nullptr : counts_out;
+        S.user_stats = s_to == (void *)stats_out ? nullptr : stats_out;
+        S.user_n = nu;
     }
     h->d2h_bytes += (int64_t)nu * (int64_t)(sizeof(vfk_counts) + sizeof(vfk_stats)) + 4;
     CU(cudaEventRecord(S.done, st));
@@ -675,6 +830,15 @@ extern "C" int vfk_last_timing(vfk_handle *h, double ms[5]) {
         CU(cudaEventElapsedTime(&t, w.tev[k], w.tev[k + 1]));
         ms[k] = (double)t;
     }
+    return VFK_OK;
+}
+
+extern "C" int vfk_fetch_stats(vfk_handle *h, int64_t out[4]) {
+    if (!h || !out) return fail(VFK_EINVAL, "vfk_fetch_stats: NULL argument");
+    out[0] = __atomic_load_n(&h->fetch_pairs, __ATOMIC_RELAXED);
+    out[1] = h->fetch_batches;
+    out[2] = __atomic_load_n(&h->fetch_nanos, __ATOMIC_RELAXED);
+    out[3] = h->fetch_threads;
     return VFK_OK;
 }
 

@@ -146,6 +146,15 @@ __device__ __forceinline__ PayLoad pay_issue(const ReadsDev &R, uint32_t i, uint
     l.odd = q & 1u;
     return l;
 }
+// the same pair of bytes as the host gathered them for a fetch list (vfk_pileup.cu request_kernel): quality | sequence byte << 8
+__device__ __forceinline__ PayLoad pay_fetched(const uint16_t *__restrict__ fetched, uint32_t pair, uint32_t q) {
+    const uint32_t g = (uint32_t)__ldg(fetched + pair);
+    PayLoad l;
+    l.q = g & 0xFFu;
+    l.s = g >> 8;
+    l.odd = q & 1u;
+    return l;
+}
 __device__ __forceinline__ uint32_t pay_word(const PayLoad &l) { return l.q | ((l.odd ? (l.s & 15u) : (l.s >> 4)) << 8); }
 __device__ __forceinline__ uint32_t pay_lookup(const ReadsDev &R, uint32_t i, uint32_t q) { return pay_word(pay_issue(R, i, q)); }
 __device__ __forceinline__ int word_qual(uint32_t w) { return (int)(w & 0xFFu); }

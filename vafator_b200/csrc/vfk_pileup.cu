@@ -149,6 +149,59 @@ __global__ void __launch_bounds__(256) locate_kernel(ReadsDev R, UnitsDev V, Res
 }
 
 // ------------------------------------------------------------------------------------------
+// fetch lists (host entry point, read arrays left in place in page-locked host memory).  A column needs ONE quality byte and
+// ONE sequence byte of each read that shows a base at it; read in place each costs the link a request (~3.4 ns, as much as
+// 190 bytes of bulk copy) and the two make up three quarters of a call's requests.  Everything that decides WHICH bytes --
+// starts, CIGARs, the position index -- is on the device already, so the call asks for them instead:
+//   request_kernel (a warp per unit with <= 64 candidates, lane = candidate): the column is resolved exactly as the register
+//   kernel will resolve it, and the pool offsets of the read's quality / sequence byte at the column are written -- 16 bytes per
+//   (unit, candidate) pair, coalesced, straight into page-locked host memory -- at pair index base[u] + k, base[u] handed out
+//   by an atomic counter (a unit that no longer fits the list keeps reading in place: base[u] = NO_FETCH);
+//   the host (cudaLaunchHostFunc between the two kernels, vfk_api.cu) gathers the bytes named, two per pair;
+//   one bulk copy brings them back and pileup_warp_kernel<.., FETCHED> takes a lane's own base / quality from pair base[u] + k.
+// The read filter is not consulted here (flags and MAPQ stay on the host): a request is made for every covering read, a superset.
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t NO_FETCH = 0xFFFFFFFFu;
+constexpr unsigned long long NO_REQUEST = ~0ull;
+__global__ void __launch_bounds__(256) request_kernel(const __grid_constant__ ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_units,
+                                                      uint32_t *__restrict__ pair_base, ulonglong2 *__restrict__ req, uint32_t *__restrict__ pair_counter,
+                                                      uint32_t cap, int by_index, const uint32_t *__restrict__ batch_status) {
+    const int lane = threadIdx.x & 31;
+    const int64_t u = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (u >= n_units) return;
+    const uint4 rb = __ldg(reinterpret_cast<const uint4 *>(res + u) + 1);  // lo, hi, stop, tid
+    const int32_t col = __ldg(&res[u].col);
+    const uint32_t n_cand = rb.y - rb.x;
+    if (*batch_status || n_cand == 0u || n_cand > 64u) {
+        if (lane == 0) pair_base[u] = NO_FETCH;
+        return;
+    }
+    uint32_t b = 0u;
+    if (lane == 0) b = atomicAdd(pair_counter, n_cand);
+    b = __shfl_sync(0xFFFFFFFFu, b, 0);
+    const bool fits = (uint64_t)b + n_cand <= (uint64_t)cap;
+    if (lane == 0) pair_base[u] = fits ? b : NO_FETCH;
+    for (uint32_t k = (uint32_t)lane; k < n_cand; k += 32u) {
+        const uint64_t p = (uint64_t)b + k;
+        if (p >= (uint64_t)cap) break;  // the host walks [0, min(total, cap)): every entry below the cap is written, request or not
+        ulonglong2 rq = make_ulonglong2(NO_REQUEST, 0ull);
+        if (fits) {
+            const int64_t i = (int64_t)rb.x + k;
+            const int32_t rp = __ldg(R.pos + i);
+            const uint2 e = __ldg(R.ee + i);
+            const uint4 hot = make_uint4((uint32_t)rp, (uint32_t)((int32_t)e.x - rp), shape_of_ev(e.y) << 24, (uint32_t)i);
+            const ColRead c = resolve_column(R, col, i, hot, true, true);
+            // by_index: the pool offsets are the caller's own arrays on the host -- the host looks them up (read index, read position);
+            // else they were derived on the device (a batch with implicit offsets): the request names the two bytes outright
+            if (c.pay)
+                rq = by_index ? make_ulonglong2((unsigned long long)i, (unsigned long long)c.qpos)
+                              : make_ulonglong2((unsigned long long)(__ldg(R.qual_off + i) + c.qpos), (unsigned long long)(__ldg(R.seq_off + i) + (c.qpos >> 1)));
+        }
+        req[p] = rq;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // histogram access.  CT = uint16_t: two bins per 32-bit word; CT = uint32_t: one bin per word.
 // ------------------------------------------------------------------------------------------
 template <typename CT>
@@ -1028,13 +1081,15 @@ struct WarpSmem {
 
 // INWARP = true: overlap partners are found in registers (pair_in_registers); false (debug hook, VFK_DEBUG_LINK_ALL=1 at
 // vfk_create): the link kernels have run over every unit and the partners come from R.mate, as on the list path.
-template <int POSB, bool INWARP>
+// FETCHED = true (host entry point with the read arrays in place): a lane's own base / quality come from the bytes the host
+// gathered for the call's fetch list (request_kernel), at pair fetch_base[u] + candidate index.
+template <int POSB, bool INWARP, bool FETCHED>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, VFK_MIN_CTAS)
 pileup_warp_kernel(const __grid_constant__ ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_units, const uint8_t *__restrict__ ins_seq,
                    const __grid_constant__ vfk_params P, vfk_counts *__restrict__ out, unsigned long long *__restrict__ work_counter,
                    uint32_t *__restrict__ block_list, uint32_t *__restrict__ n_block, uint32_t *__restrict__ warp_list,
                    uint32_t *__restrict__ n_warp, uint32_t *__restrict__ medium_list, uint32_t *__restrict__ n_medium,
-                   const uint32_t *__restrict__ batch_status) {
+                   const uint32_t *__restrict__ batch_status, const uint32_t *__restrict__ fetch_base, const uint16_t *__restrict__ fetched) {
     using L = Layout<POSB>;
     constexpr bool HIST_HERE = WarpSmem<POSB>::HIST_HERE;
     __shared__ uint32_t stage_all[WARPS_PER_CTA][32];
@@ -1063,6 +1118,10 @@ pileup_warp_kernel(const __grid_constant__ ReadsDev R, const ResolvedUnit *__res
             ra = q[0];  // written by locate_kernel (an earlier launch of this call)
             rb = q[1];
         }
+        uint32_t fbv = NO_FETCH;
+        if constexpr (FETCHED) {
+            if (lane < n_here) fbv = __ldg(fetch_base + base + lane);
+        }
         // software pipeline: the header words of the NEXT unit's first 32 candidates are requested before the current
         // unit is processed
         uint4 hot_n = make_uint4(0, 0, 0, 0);
@@ -1079,6 +1138,8 @@ pileup_warp_kernel(const __grid_constant__ ReadsDev R, const ResolvedUnit *__res
             ru.stop = (int32_t)__shfl_sync(FULL, rb.z, j); ru.tid = (int32_t)__shfl_sync(FULL, rb.w, j);
             Unit U;
             unit_from(ru, ins_seq, U);
+            uint32_t fb = NO_FETCH;
+            if constexpr (FETCHED) fb = __shfl_sync(FULL, fbv, j);
             Cand A;
             A.hot = hot_n;
             A.mw = VFK_NO_MATE;
@@ -1127,11 +1188,11 @@ pileup_warp_kernel(const __grid_constant__ ReadsDev R, const ResolvedUnit *__res
             PayLoad ownA, ownB;
             ownA.q = ownA.s = ownA.odd = 0u;
             ownB = ownA;
-            if (cA.pay) ownA = pay_issue(R, A.hot.w, (uint32_t)cA.qpos);
+            if (cA.pay) ownA = (FETCHED && fb != NO_FETCH) ? pay_fetched(fetched, fb + (uint32_t)lane, (uint32_t)cA.qpos) : pay_issue(R, A.hot.w, (uint32_t)cA.qpos);
             ColRead cB = resolve_column(R, U.col, i_b, B.hot, false, false);
             if (two) {
                 cB = resolve_column(R, U.col, i_b, B.hot, validB, passB);
-                if (cB.pay) ownB = pay_issue(R, B.hot.w, (uint32_t)cB.qpos);
+                if (cB.pay) ownB = (FETCHED && fb != NO_FETCH) ? pay_fetched(fetched, fb + 32u + (uint32_t)lane, (uint32_t)cB.qpos) : pay_issue(R, B.hot.w, (uint32_t)cB.qpos);
             }
             bool general_protocol = false;
             if constexpr (INWARP) {
@@ -1432,7 +1493,8 @@ struct LaunchCache {
 
 // Per-call device scratch (owned by the handle / a staging slot).
 //   counters: @0 u64 unit work counter, @8 u32 block-list length, @12 u32 warp-list length, @20 u32 batch status
-//   (VFK_ST_BADBATCH or 0), @24 u32 medium-list length, @28 u32 deep units listed, @32 u32 units finished by the tile kernel, @64 256 x u32 per-SM segment counters of the list path.   lists: 3 * n_units u32.
+//   (VFK_ST_BADBATCH or 0), @24 u32 medium-list length, @28 u32 deep units listed, @32 u32 units finished by the tile kernel, @40 u32 pairs
+//   handed out by request_kernel, @64 256 x u32 per-SM segment counters of the list path.   lists: 3 * n_units u32.
 struct PileupScratch {
     void *resolved;   // n_units * 32 B
     void *counters;   // 64 B
@@ -1446,6 +1508,14 @@ struct PileupScratch {
     uint32_t *mate;
     cudaEvent_t *ev;  // timing (vfk_set_timing): [2] after locate, [3] after the register kernel, [4] after the list path; or NULL
     LaunchCache *cache;  // [4], one per position-range instantiation: function attributes set / occupancies queried once per handle
+    // fetch list of the host entry point (request_kernel above); fetch_cap = 0: none
+    uint32_t fetch_cap;         // pairs the list holds
+    int fetch_by_index;         // requests name (read, read position) instead of pool offsets
+    uint32_t *fetch_base;       // [n_units] device: first pair of a unit, or NO_FETCH
+    void *fetch_req;            // [fetch_cap] x 16 B, page-locked host memory as the device sees it
+    const uint16_t *fetched;    // [fetch_cap] device: the gathered bytes (copied in by fetch_between)
+    cudaError_t (*fetch_between)(void *ctx, const uint32_t *pair_counter, cudaStream_t stream);  // host gather + copy, enqueued between the two kernels
+    void *fetch_ctx;
 };
 
 constexpr int posb_index(int posb) { return posb == 256 ? 0 : posb == 512 ? 1 : posb == 1024 ? 2 : 3; }
@@ -1510,17 +1580,29 @@ static cudaError_t launch_posb(ReadsDev R, const UnitsDev &V, const vfk_params &
     locate_kernel<<<(unsigned)((V.n + 255) / 256), 256, 0, stream>>>(R, V, res);
     ++*launches;
     if (S.ev) cudaEventRecord(S.ev[2], stream);
+    const bool fetch = S.fetch_cap > 0u && !link_all;
+    if (fetch) {
+        uint32_t *pair_counter = (uint32_t *)((char *)S.counters + 40);
+        request_kernel<<<(unsigned)((V.n + 7) / 8), 256, 0, stream>>>(R, res, V.n, S.fetch_base, (ulonglong2 *)S.fetch_req, pair_counter, S.fetch_cap, S.fetch_by_index, batch_status);
+        ++*launches;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        e = S.fetch_between(S.fetch_ctx, pair_counter, stream);
+        if (e != cudaSuccess) return e;
+    }
     int ctas_per_sm = 0;
     const size_t warp_smem = WarpSmem<POSB>::BYTES;
     LaunchCache &C = S.cache[posb_index(POSB)];
     if (!C.ready) {  // once per handle: function attributes and the register kernel's occupancy
         if (warp_smem > 40 * 1024) {
-            e = link_all ? cudaFuncSetAttribute(pileup_warp_kernel<POSB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem)
-                         : cudaFuncSetAttribute(pileup_warp_kernel<POSB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem);
+            e = link_all ? cudaFuncSetAttribute(pileup_warp_kernel<POSB, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem)
+                         : cudaFuncSetAttribute(pileup_warp_kernel<POSB, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem);
+            if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(pileup_warp_kernel<POSB, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem);
             if (e != cudaSuccess) return e;
         }
-        e = link_all ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pileup_warp_kernel<POSB, false>, WARPS_PER_CTA * 32, warp_smem)
-                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pileup_warp_kernel<POSB, true>, WARPS_PER_CTA * 32, warp_smem);
+        e = link_all ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pileup_warp_kernel<POSB, false, false>, WARPS_PER_CTA * 32, warp_smem)
+                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pileup_warp_kernel<POSB, true, false>, WARPS_PER_CTA * 32, warp_smem);
         if (e != cudaSuccess) return e;
         C.warp_ctas = ctas_per_sm < 1 ? 1 : ctas_per_sm;
         if constexpr (WarpSmem<POSB>::HIST_HERE) {
@@ -1540,11 +1622,14 @@ static cudaError_t launch_posb(ReadsDev R, const UnitsDev &V, const vfk_params &
     if (link_all) {
         e = launch_link(R, P, res, nullptr, nullptr, V.n, S.heads, S.n_buckets, S.next, S.column, S.claimed, S.mate, sm_count, stream, launches);
         if (e != cudaSuccess) return e;
-        pileup_warp_kernel<POSB, false><<<(unsigned)grid, WARPS_PER_CTA * 32, warp_smem, stream>>>(R, res, V.n, V.ins_seq, P, out, work, block_list,
-                                                                                           n_block, warp_list, n_warp, medium_list, n_medium, batch_status);
+        pileup_warp_kernel<POSB, false, false><<<(unsigned)grid, WARPS_PER_CTA * 32, warp_smem, stream>>>(
+            R, res, V.n, V.ins_seq, P, out, work, block_list, n_block, warp_list, n_warp, medium_list, n_medium, batch_status, nullptr, nullptr);
+    } else if (fetch) {
+        pileup_warp_kernel<POSB, true, true><<<(unsigned)grid, WARPS_PER_CTA * 32, warp_smem, stream>>>(
+            R, res, V.n, V.ins_seq, P, out, work, block_list, n_block, warp_list, n_warp, medium_list, n_medium, batch_status, S.fetch_base, S.fetched);
     } else {
-        pileup_warp_kernel<POSB, true><<<(unsigned)grid, WARPS_PER_CTA * 32, warp_smem, stream>>>(R, res, V.n, V.ins_seq, P, out, work, block_list,
-                                                                                          n_block, warp_list, n_warp, medium_list, n_medium, batch_status);
+        pileup_warp_kernel<POSB, true, false><<<(unsigned)grid, WARPS_PER_CTA * 32, warp_smem, stream>>>(
+            R, res, V.n, V.ins_seq, P, out, work, block_list, n_block, warp_list, n_warp, medium_list, n_medium, batch_status, nullptr, nullptr);
     }
     ++*launches;
     e = cudaGetLastError();

@@ -114,6 +114,8 @@ def libvfk():
         lib.vfk_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         lib.vfk_transfer_stats.restype = C.c_int
         lib.vfk_transfer_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        lib.vfk_fetch_stats.restype = C.c_int
+        lib.vfk_fetch_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         lib.vfk_annotate_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                           C.c_double, C.c_void_p, C.c_void_p]
         _libvfk = lib
@@ -152,6 +154,12 @@ def _empty(n, dtype, pinned: bool):
             a = t.numpy().view(dtype)[:n]
             return a
     return np.empty(n, dtype)
+
+
+def pinned_empty(n, dtype):
+    """Page-locked host array (inputs read in place / results written directly by the host entry point; pageable arrays work
+    too and go through the library's bounce buffers)."""
+    return _empty(n, dtype, True)
 
 
 class HostReads:
@@ -408,7 +416,10 @@ class Device:
         """Host entry point accounting since the handle was created (vfk_transfer_stats)."""
         out = (C.c_int64 * 4)()
         _check(self.lib.vfk_transfer_stats(self.h, out))
-        return dict(staged_bytes=int(out[0]), zero_copy_batches=int(out[1]), staged_batches=int(out[2]), d2h_bytes=int(out[3]))
+        f = (C.c_int64 * 4)()
+        _check(self.lib.vfk_fetch_stats(self.h, f))
+        return dict(staged_bytes=int(out[0]), zero_copy_batches=int(out[1]), staged_batches=int(out[2]), d2h_bytes=int(out[3]),
+                    fetch_pairs=int(f[0]), fetch_batches=int(f[1]), fetch_ns=int(f[2]), fetch_threads=int(f[3]))
 
     def prep_words(self, reads: "DeviceReads"):
         """(end, shape word, status) the read-preparation kernel derives per read (vfk_prep_words) -- for tests."""
