@@ -128,7 +128,7 @@ class Workload:
             self.purity = {"tumor": 0.8}
             # a rank's shard goes through the device as a few interval sub-batches (the copies of one overlap the kernels of the
             # previous one); with more ranks a shard is smaller and fewer, larger launches serve it better
-            self.sub = args.sub_batches or max(2, 4 // max(1, int(os.environ.get("WORLD_SIZE", "1"))))
+            self.sub = args.sub_batches or max(2, 8 // max(1, int(os.environ.get("WORLD_SIZE", "1"))))
             self.text = ("C3: ONE synthetic 30x WGS tumor BAM, %d contigs x %.0f Mbp (chr1-22 scaled down to %.0f Mbp), 2x150 reads, 1 variant / ~720 bp "
                          "(90%% SNV, 5%% INS, 5%% DEL), MQ>=1 BQ>=30; cut into one interval shard per GPU") % (
                              n_contigs, clen / 1e6, n_contigs * clen / 1e6)
