@@ -189,6 +189,14 @@ int vfk_transfer_stats(vfk_handle *h, int64_t out[4]);
  * that carried a list, out[2] nanoseconds the host spent gathering, out[3] host threads of a gather.  Environment, read by vfk_create: VFK_HOST_FETCH=0 switches the lists off, VFK_HOST_THREADS=n sets
  * the host threads of the gather (default: the OpenMP maximum, at most 16).                                            */
 int vfk_fetch_stats(vfk_handle *h, int64_t out[4]);
+/* The host's half of a fetch list on its own (no device involved; what the stream callback of vfk_annotate_host_async runs):
+ * req holds two 64-bit words per pair as request_kernel writes them -- word 0 = ~0: nothing wanted (out = 0); with
+ * qual_off / seq_off given: word 0 = read index, word 1 = read position; with both NULL: word 0 = offset of the quality byte
+ * in `qual`, word 1 = offset of the sequence byte in `seq`.  out[p] = quality | sequence byte << 8; an entry that points
+ * outside the arrays yields 0.                                                                                         */
+int vfk_fetch_gather(const uint64_t *req, int64_t n_pairs, const uint8_t *qual, int64_t n_qual_bytes, const uint8_t *seq,
+                     int64_t n_seq_bytes, const int64_t *qual_off, const int64_t *seq_off, int64_t n_reads, int threads,
+                     uint16_t *out);
 
 /* ---- list-shaped auxiliaries (DEVICE pointers) ------------------------------------------------
  * vfk_pileup_values: per unit, the per-read values the reference keeps in all_mqs / all_bqs /

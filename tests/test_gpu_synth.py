@@ -268,7 +268,7 @@ def test_host_entry_point_transfer_strategies(mode, monkeypatch):
         assert (after["staged_batches"] - before["staged_batches"]) == (0 if in_place else 1)
         pairs = after["fetch_pairs"] - before["fetch_pairs"]
         if in_place and mode != "pinned_no_fetch":
-            n_cand = int(want_c["n_cand"].astype(np.int64)[want_c["n_cand"] <= 64].sum())
+            n_cand = int(want_c["n_cand"].astype(np.int64)[want_c["n_cand"] <= 192].sum())  # (register and medium kernel units)
             assert after["fetch_batches"] - before["fetch_batches"] == 1
             # every candidate of every register-kernel unit is on the list -- or, with a list cut short, as many as it holds
             assert pairs == n_cand if mode != "pinned_short_list" else 0 < pairs < n_cand
@@ -287,6 +287,30 @@ def test_host_entry_point_transfer_strategies(mode, monkeypatch):
             dev.wait(t)
         for k in range(3):
             assert c2[k].tobytes() == want_c.tobytes() and s2[k].tobytes() == want_s.tobytes()
+    dev.close()
+
+
+def test_fetch_lists_cover_medium_columns():
+    """60x-like columns (65..192 candidate reads: medium kernel) through the host entry point with the arrays in place: their
+    base / quality bytes come from the fetch list too, and the results equal the resident call byte for byte."""
+    dev = device.Device(0)
+    cfg = synth.wes(n_tiles=600, indel_period=700, multiallelic_pct=5, pairs_per_tile=130)
+    batch, recs, units, stop, _ = _setup(cfg)
+    params = device.make_params(min_mapq=1, min_baseq=30)
+    host = device.host_reads(batch, pinned=True)
+    eaf = np.full(units.n_units, 0.5)
+    counts_dev = dev.pileup(dev.upload_reads(host), dev.upload_units(units, stop), params)
+    stats_dev = dev.epilogue(units.n_units, counts_dev, dev.torch.as_tensor(eaf, device=dev.device), 5e-7, 1e-3)
+    dev.sync()
+    want_c = dev.to_host(counts_dev, device.COUNTS_DTYPE, units.n_units)
+    want_s = dev.to_host(stats_dev, device.STATS_DTYPE, units.n_units)
+    assert np.mean((want_c["n_cand"] > 64) & (want_c["n_cand"] <= 192)) > 0.3, np.percentile(want_c["n_cand"], [5, 50, 95])
+    before = dev.transfer_stats()
+    got_c, got_s = dev.annotate_host(host, units, stop, params, eaf, 5e-7, 1e-3)
+    after = dev.transfer_stats()
+    assert after["zero_copy_batches"] - before["zero_copy_batches"] == 1 and after["fetch_batches"] - before["fetch_batches"] == 1
+    assert after["fetch_pairs"] - before["fetch_pairs"] == int(want_c["n_cand"].astype(np.int64)[want_c["n_cand"] <= 192].sum())
+    assert got_c.tobytes() == want_c.tobytes() and got_s.tobytes() == want_s.tobytes()
     dev.close()
 
 

@@ -104,6 +104,40 @@ def test_cabi_library_exports_every_declared_symbol():
     assert "sm_100a" in sass
 
 
+@pytest.mark.parametrize("by_index", [False, True])
+@pytest.mark.parametrize("threads", [1, 5])
+def test_fetch_list_host_gather(by_index, threads):
+    """The host half of a fetch list (vfk_fetch_gather: what the stream callback of the host entry point runs between two
+    kernels) against numpy: both request formats, entries that want nothing, entries that point outside the arrays; lists that
+    end inside a block of 64 and lists shorter than the thread count."""
+    lib = device.libvfk()
+    rng = np.random.default_rng(7)
+    n_reads = 5000
+    l = rng.integers(30, 200, n_reads)
+    qual_off = np.concatenate([[0], np.cumsum(l)[:-1]]).astype(np.int64)
+    seq_off = np.concatenate([[0], np.cumsum((l + 1) // 2)[:-1]]).astype(np.int64)
+    qual = rng.integers(0, 94, int(l.sum())).astype(np.uint8)
+    seq = rng.integers(0, 256, int(((l + 1) // 2).sum())).astype(np.uint8)
+    for n in (0, 3, 64, 1000, 12345):
+        i = rng.integers(0, n_reads, n)
+        q = (rng.random(n) * l[i]).astype(np.int64)
+        want = qual[qual_off[i] + q].astype(np.uint16) | (seq[seq_off[i] + q // 2].astype(np.uint16) << 8)
+        req = np.empty((n, 2), np.uint64)
+        req[:, 0], req[:, 1] = (i, q) if by_index else (qual_off[i] + q, seq_off[i] + q // 2)
+        nothing = rng.random(n) < 0.2
+        req[nothing, 0] = np.uint64(0xFFFFFFFFFFFFFFFF)
+        outside = (rng.random(n) < 0.05) & ~nothing
+        req[outside, 0 if by_index else 1] = np.uint64(1 << 40)
+        want[nothing | outside] = 0
+        out = np.full(n, 0xABCD, np.uint16)
+        rc = lib.vfk_fetch_gather(C.c_void_p(req.ctypes.data), C.c_int64(n), C.c_void_p(qual.ctypes.data), C.c_int64(len(qual)),
+                                  C.c_void_p(seq.ctypes.data), C.c_int64(len(seq)),
+                                  C.c_void_p(qual_off.ctypes.data if by_index else None), C.c_void_p(seq_off.ctypes.data if by_index else None),
+                                  C.c_int64(n_reads), C.c_int(threads), C.c_void_p(out.ctypes.data))
+        assert rc == 0
+        assert np.array_equal(out, want)
+
+
 def test_decoders_write_contiguous_pools(tmp_path):
     """ReadBatch.contiguous (set by the synthetic generator and the BAM decoder) promises that the three pool offset arrays are the
     prefix sums of the lengths -- the condition under which the host entry point hands them over as NULL (include/vfk.h) and

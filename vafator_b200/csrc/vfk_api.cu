@@ -185,30 +185,44 @@ static void CUDART_CB fetch_cb(void *p) {
     const int64_t n = (int64_t)(*j.h_total < j.cap ? *j.h_total : j.cap);
     const int64_t n_blk = (n + 63) / 64;
     const unsigned long long none = ~0ull;
-#pragma omp parallel for schedule(static) num_threads(j.threads)
-    for (int64_t b = 0; b < n_blk; ++b) {
-        const int64_t p0 = b * 64, p1 = p0 + 64 < n ? p0 + 64 : n;
-        uint64_t qa[64], sa[64];
-        for (int64_t q = p0; q < p1; ++q) {  // addresses first, every line asked for before the first one is used
-            const ulonglong2 r = j.req[q];
-            uint64_t a = none, c = 0;
-            if (r.x != none) {
-                if (j.qual_off) {
-                    if ((int64_t)r.x < j.n_reads) { a = (uint64_t)j.qual_off[r.x] + r.y; c = (uint64_t)j.seq_off[r.x] + (r.y >> 1); }
-                } else {
-                    a = r.x; c = r.y;
+    // a thread owns a contiguous run of 64-pair blocks and works one block ahead: the addresses of block b + 1 are computed and
+    // every line they name is requested before the bytes of block b are picked up (two random cache lines per pair; nothing
+    // but the number of lines in flight per core bounds this loop)
+#pragma omp parallel num_threads(j.threads)
+    {
+        const int64_t t = omp_get_thread_num(), nt = omp_get_num_threads();
+        const int64_t b0 = n_blk * t / nt, b1 = n_blk * (t + 1) / nt;
+        uint64_t qa[2][64], sa[2][64];
+        auto ask = [&](int64_t b) {
+            const int64_t p0 = b * 64, p1 = p0 + 64 < n ? p0 + 64 : n;
+            uint64_t *qq = qa[b & 1], *ss = sa[b & 1];
+            for (int64_t q = p0; q < p1; ++q) {
+                const ulonglong2 r = j.req[q];
+                uint64_t a = none, c = 0;
+                if (r.x != none) {
+                    if (j.qual_off) {
+                        if ((int64_t)r.x < j.n_reads) { a = (uint64_t)j.qual_off[r.x] + r.y; c = (uint64_t)j.seq_off[r.x] + (r.y >> 1); }
+                    } else {
+                        a = r.x; c = r.y;
+                    }
+                    if (a >= (uint64_t)j.n_qual || c >= (uint64_t)j.n_seq) a = none;  // a malformed batch must not take the host down
                 }
-                if (a >= (uint64_t)j.n_qual || c >= (uint64_t)j.n_seq) a = none;  // a malformed batch must not take the host down
+                qq[q - p0] = a; ss[q - p0] = c;
+                if (a != none) {
+                    __builtin_prefetch(j.qual + a);
+                    __builtin_prefetch(j.seq + c);
+                }
             }
-            qa[q - p0] = a; sa[q - p0] = c;
-            if (a != none) {
-                __builtin_prefetch(j.qual + a);
-                __builtin_prefetch(j.seq + c);
+        };
+        if (b0 < b1) ask(b0);
+        for (int64_t b = b0; b < b1; ++b) {
+            if (b + 1 < b1) ask(b + 1);
+            const int64_t p0 = b * 64, p1 = p0 + 64 < n ? p0 + 64 : n;
+            const uint64_t *qq = qa[b & 1], *ss = sa[b & 1];
+            for (int64_t q = p0; q < p1; ++q) {
+                const uint64_t a = qq[q - p0];
+                j.out[q] = a == none ? (uint16_t)0 : (uint16_t)(j.qual[a] | ((uint16_t)j.seq[ss[q - p0]] << 8));
             }
-        }
-        for (int64_t q = p0; q < p1; ++q) {
-            const uint64_t a = qa[q - p0];
-            j.out[q] = a == none ? (uint16_t)0 : (uint16_t)(j.qual[a] | ((uint16_t)j.seq[sa[q - p0]] << 8));
         }
     }
     if (j.pairs) __atomic_fetch_add(j.pairs, n, __ATOMIC_RELAXED);
@@ -731,10 +745,11 @@ extern "C" int vfk_annotate_host_async(vfk_handle *h, const vfk_read_batch *read
         rc = enqueue_prep(h, S.work, R, st, &launches);
         if (rc) goto failed;
         scratch = scratch_of(h, S.work);
-        if (zero_copy && h->fetch && !h->link_all && nu < ((int64_t)1 << 25)) {
+        if (zero_copy && h->fetch && !h->link_all && nu < ((int64_t)1 << 24)) {
             // the reads' base / quality bytes at the columns: asked for by the device, gathered by the host, copied in bulk
             double want = (double)nu * (depth * h->fetch_slack + 6.0) + 1024.0;
-            if (want > (double)nu * 64.0) want = (double)nu * 64.0;
+            if (want > (double)nu * 192.0) want = (double)nu * 192.0;  // (the deepest column that asks: the medium kernel's)
+            if (want > 4.0e9) want = 4.0e9;
             const uint32_t cap = (uint32_t)want;
             if ((rc = S.fetch_req.reserve((size_t)cap * 16)) || (rc = S.fetch_out.reserve((size_t)cap * 2)) || (rc = S.fetched.reserve((size_t)cap * 2)) ||
                 (rc = S.fetch_base.reserve((size_t)nu * 4)))
@@ -830,6 +845,21 @@ extern "C" int vfk_last_timing(vfk_handle *h, double ms[5]) {
         CU(cudaEventElapsedTime(&t, w.tev[k], w.tev[k + 1]));
         ms[k] = (double)t;
     }
+    return VFK_OK;
+}
+
+extern "C" int vfk_fetch_gather(const uint64_t *req, int64_t n_pairs, const uint8_t *qual, int64_t n_qual_bytes, const uint8_t *seq,
+                                int64_t n_seq_bytes, const int64_t *qual_off, const int64_t *seq_off, int64_t n_reads, int threads, uint16_t *out) {
+    if (n_pairs < 0 || n_pairs > 0xFFFFFFFFll) return fail(VFK_EINVAL, "vfk_fetch_gather: bad pair count");
+    if (n_pairs == 0) return VFK_OK;
+    if (!req || !qual || !seq || !out || (!qual_off) != (!seq_off)) return fail(VFK_EINVAL, "vfk_fetch_gather: NULL array");
+    const uint32_t total = (uint32_t)n_pairs;
+    FetchJob j;
+    j.req = (const ulonglong2 *)req; j.out = out; j.h_total = &total; j.cap = total;
+    j.qual = qual; j.seq = seq; j.qual_off = qual_off; j.seq_off = seq_off;
+    j.n_reads = n_reads; j.n_qual = n_qual_bytes; j.n_seq = n_seq_bytes;
+    j.threads = threads > 0 ? threads : 1;
+    fetch_cb(&j);
     return VFK_OK;
 }
 

@@ -153,26 +153,27 @@ __global__ void __launch_bounds__(256) locate_kernel(ReadsDev R, UnitsDev V, Res
 // ONE sequence byte of each read that shows a base at it; read in place each costs the link a request (~3.4 ns, as much as
 // 190 bytes of bulk copy) and the two make up three quarters of a call's requests.  Everything that decides WHICH bytes --
 // starts, CIGARs, the position index -- is on the device already, so the call asks for them instead:
-//   request_kernel (a warp per unit with <= 64 candidates, lane = candidate): the column is resolved exactly as the register
-//   kernel will resolve it, and the pool offsets of the read's quality / sequence byte at the column are written -- 16 bytes per
+//   request_kernel (a warp per unit with <= 64 candidates -- <= 192 where the medium kernel exists --, lane = candidate): the
+//   column is resolved exactly as the register / medium kernel will resolve it, and the pool offsets of the read's quality / sequence byte at the column are written -- 16 bytes per
 //   (unit, candidate) pair, coalesced, straight into page-locked host memory -- at pair index base[u] + k, base[u] handed out
 //   by an atomic counter (a unit that no longer fits the list keeps reading in place: base[u] = NO_FETCH);
 //   the host (cudaLaunchHostFunc between the two kernels, vfk_api.cu) gathers the bytes named, two per pair;
-//   one bulk copy brings them back and pileup_warp_kernel<.., FETCHED> takes a lane's own base / quality from pair base[u] + k.
+//   one bulk copy brings them back and pileup_warp_kernel<.., FETCHED> / medium_kernel take a read's own base / quality from pair
+//   base[u] + k.
 // The read filter is not consulted here (flags and MAPQ stay on the host): a request is made for every covering read, a superset.
 // ------------------------------------------------------------------------------------------
 constexpr uint32_t NO_FETCH = 0xFFFFFFFFu;
 constexpr unsigned long long NO_REQUEST = ~0ull;
 __global__ void __launch_bounds__(256) request_kernel(const __grid_constant__ ReadsDev R, const ResolvedUnit *__restrict__ res, int64_t n_units,
                                                       uint32_t *__restrict__ pair_base, ulonglong2 *__restrict__ req, uint32_t *__restrict__ pair_counter,
-                                                      uint32_t cap, int by_index, const uint32_t *__restrict__ batch_status) {
+                                                      uint32_t cap, uint32_t max_cand, int by_index, const uint32_t *__restrict__ batch_status) {
     const int lane = threadIdx.x & 31;
     const int64_t u = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (u >= n_units) return;
     const uint4 rb = __ldg(reinterpret_cast<const uint4 *>(res + u) + 1);  // lo, hi, stop, tid
     const int32_t col = __ldg(&res[u].col);
     const uint32_t n_cand = rb.y - rb.x;
-    if (*batch_status || n_cand == 0u || n_cand > 64u) {
+    if (*batch_status || n_cand == 0u || n_cand > max_cand) {
         if (lane == 0) pair_base[u] = NO_FETCH;
         return;
     }
@@ -624,7 +625,7 @@ __device__ __forceinline__ uint32_t cas16(uint16_t *cell, uint32_t expect, uint3
 template <int POSB>
 static __device__ __forceinline__ bool medium_unit(const ReadsDev &R, const vfk_params &P, int32_t col, uint32_t meta, int32_t len, const uint8_t *ins,
                                                 uint32_t lo, uint32_t hi, int32_t stop, int32_t tid, MedSmem *M, uint32_t *ref_slot, uint32_t *alt_slot,
-                                                vfk_counts *out) {
+                                                vfk_counts *out, uint32_t fb, const uint16_t *__restrict__ fetched) {
     using L = Layout<POSB>;
     constexpr int WORDS = L::BINS / 2;
     const int lane = threadIdx.x & 31;
@@ -647,7 +648,7 @@ static __device__ __forceinline__ bool medium_unit(const ReadsDev &R, const vfk_
         const ColRead c = resolve_column(R, col, i, hot, true, pass);
         PayLoad own;
         own.q = own.s = own.odd = 0u;
-        if (c.pay) own = pay_issue(R, hot.w, (uint32_t)c.qpos);
+        if (c.pay) own = fb != NO_FETCH ? pay_fetched(fetched, fb + (uint32_t)k, (uint32_t)c.qpos) : pay_issue(R, hot.w, (uint32_t)c.qpos);  // (fetch list of the host entry point)
         bool elig = P.ignore_overlaps && pass && (hot.z & (F_PROPER | F_MUNMAP)) == F_PROPER, stores = false;
         uint32_t key = 0u;
         if (elig) {  // htslib overlap_push past its early exits (cf. pair_in_registers)
@@ -784,7 +785,8 @@ template <int POSB>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 medium_kernel(const __grid_constant__ ReadsDev R, const ResolvedUnit *__restrict__ res, const uint8_t *__restrict__ ins_seq,
               const __grid_constant__ vfk_params P, vfk_counts *__restrict__ out, const uint32_t *__restrict__ medium_list,
-              const uint32_t *__restrict__ n_medium, uint32_t *__restrict__ warp_list, uint32_t *__restrict__ n_warp) {
+              const uint32_t *__restrict__ n_medium, uint32_t *__restrict__ warp_list, uint32_t *__restrict__ n_warp,
+              const uint32_t *__restrict__ fetch_base, const uint16_t *__restrict__ fetched) {
     using L = Layout<POSB>;
     extern __shared__ __align__(16) uint32_t dyn_smem[];  // per warp: a pair of u16 histograms, then MedSmem
     constexpr int PER_WARP = L::BINS + (int)(sizeof(MedSmem) / 4);
@@ -795,7 +797,9 @@ medium_kernel(const __grid_constant__ ReadsDev R, const ResolvedUnit *__restrict
     for (uint32_t k = blockIdx.x * WARPS_PER_CTA + warp; k < n; k += gridDim.x * WARPS_PER_CTA) {
         const uint32_t u = medium_list[k];
         const ResolvedUnit ru = res[u];
-        const bool ok = medium_unit<POSB>(R, P, ru.col, ru.meta, ru.len, ins_seq + ru.ins_off, ru.lo, ru.hi, ru.stop, ru.tid, med, hist, hist + L::BINS / 2, out + u);
+        const uint32_t fb = fetch_base ? __ldg(fetch_base + u) : NO_FETCH;
+        const bool ok = medium_unit<POSB>(R, P, ru.col, ru.meta, ru.len, ins_seq + ru.ins_off, ru.lo, ru.hi, ru.stop, ru.tid, med, hist, hist + L::BINS / 2, out + u,
+                                          fb, fetched);
         if (!ok && lane == 0) warp_list[atomicAdd(n_warp, 1u)] = u;  // its record keeps VFK_ST_DEFERRED
         __syncwarp();
     }
@@ -1583,7 +1587,8 @@ static cudaError_t launch_posb(ReadsDev R, const UnitsDev &V, const vfk_params &
     const bool fetch = S.fetch_cap > 0u && !link_all;
     if (fetch) {
         uint32_t *pair_counter = (uint32_t *)((char *)S.counters + 40);
-        request_kernel<<<(unsigned)((V.n + 7) / 8), 256, 0, stream>>>(R, res, V.n, S.fetch_base, (ulonglong2 *)S.fetch_req, pair_counter, S.fetch_cap, S.fetch_by_index, batch_status);
+        request_kernel<<<(unsigned)((V.n + 7) / 8), 256, 0, stream>>>(R, res, V.n, S.fetch_base, (ulonglong2 *)S.fetch_req, pair_counter, S.fetch_cap,
+                                                                     WarpSmem<POSB>::HIST_HERE ? (uint32_t)MED_CAP : 64u, S.fetch_by_index, batch_status);
         ++*launches;
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -1640,7 +1645,8 @@ static cudaError_t launch_posb(ReadsDev R, const UnitsDev &V, const vfk_params &
             using L = Layout<POSB>;
             const size_t med_smem = (size_t)WARPS_PER_CTA * (L::BINS * 4 + sizeof(MedSmem));
             const int64_t med_grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)sm_count * 3, (V.n + WARPS_PER_CTA - 1) / WARPS_PER_CTA));
-            medium_kernel<POSB><<<(unsigned)med_grid, WARPS_PER_CTA * 32, med_smem, stream>>>(R, res, V.ins_seq, P, out, medium_list, n_medium, warp_list, n_warp);
+            medium_kernel<POSB><<<(unsigned)med_grid, WARPS_PER_CTA * 32, med_smem, stream>>>(R, res, V.ins_seq, P, out, medium_list, n_medium, warp_list, n_warp,
+                                                                                              fetch ? S.fetch_base : nullptr, fetch ? S.fetched : nullptr);
             ++*launches;
             e = cudaGetLastError();
             if (e != cudaSuccess) return e;
