@@ -186,8 +186,9 @@ int vfk_transfer_stats(vfk_handle *h, int64_t out[4]);
 /* fetch lists of the host entry point since vfk_create (batches read in place: the one quality byte and the one sequence
  * byte a column needs of each read are named by the device, gathered by host threads between two kernels of the call and
  * copied in bulk, instead of being read over the bus one request each): out[0] (unit, read) pairs gathered, out[1] batches
- * that carried a list, out[2] nanoseconds the host spent gathering, out[3] host threads of a gather.  Environment, read by vfk_create: VFK_HOST_FETCH=0 switches the lists off, VFK_HOST_THREADS=n sets
- * the host threads of the gather (default: the OpenMP maximum, at most 16).                                            */
+ * that carried a list, out[2] nanoseconds the host spent gathering, out[3] host threads of a gather.  Environment, read by vfk_create: VFK_HOST_THREADS=n sets the host threads
+ * of the gather (default: the OpenMP maximum, at most 16); the lists are used when there are at least six of them (several
+ * GPUs sharing few host cores: reading in place is faster), VFK_HOST_FETCH=1 / 0 decides outright.                                            */
 int vfk_fetch_stats(vfk_handle *h, int64_t out[4]);
 /* The host's half of a fetch list on its own (no device involved; what the stream callback of vfk_annotate_host_async runs):
  * req holds two 64-bit words per pair as request_kernel writes them -- word 0 = ~0: nothing wanted (out = 0); with

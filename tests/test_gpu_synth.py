@@ -241,6 +241,8 @@ def test_host_entry_point_transfer_strategies(mode, monkeypatch):
         monkeypatch.setenv("VFK_HOST_FETCH", "0")
     if mode == "pinned_short_list":
         monkeypatch.setenv("VFK_HOST_FETCH_SLACK", "0.4")
+    if mode in ("pinned", "pinned_short_list", "pinned_explicit_offsets"):
+        monkeypatch.setenv("VFK_HOST_FETCH", "1")  # (the default asks for six host threads)
     in_place = mode in ("pinned", "pinned_no_fetch", "pinned_short_list", "pinned_explicit_offsets")
     dev = device.Device(0)
     cfg = synth.wes(n_tiles=3000, indel_period=700, multiallelic_pct=5)
@@ -290,9 +292,10 @@ def test_host_entry_point_transfer_strategies(mode, monkeypatch):
     dev.close()
 
 
-def test_fetch_lists_cover_medium_columns():
+def test_fetch_lists_cover_medium_columns(monkeypatch):
     """60x-like columns (65..192 candidate reads: medium kernel) through the host entry point with the arrays in place: their
     base / quality bytes come from the fetch list too, and the results equal the resident call byte for byte."""
+    monkeypatch.setenv("VFK_HOST_FETCH", "1")
     dev = device.Device(0)
     cfg = synth.wes(n_tiles=600, indel_period=700, multiallelic_pct=5, pairs_per_tile=130)
     batch, recs, units, stop, _ = _setup(cfg)

@@ -331,13 +331,17 @@ extern "C" int vfk_create(int device, vfk_handle **out) {
     h->link_all = env_on("VFK_DEBUG_LINK_ALL");
     h->stage_all = env_on("VFK_HOST_STAGE_ALL");
     {
-        const char *v = getenv("VFK_HOST_FETCH");
-        h->fetch = !(v && v[0] == '0');
+        const char *v;
         if ((v = getenv("VFK_HOST_FETCH_SLACK")) && atof(v) > 0.0) h->fetch_slack = atof(v);
         int t = omp_get_max_threads();
         if ((v = getenv("VFK_HOST_THREADS")) && atoi(v) > 0) t = atoi(v);
         else if (t > 16) t = 16;
         h->fetch_threads = t < 1 ? 1 : t;
+        // A pair costs a gathering thread ~32 ns and saves the link two requests (~7 ns): with fewer than six threads for this
+        // GPU the gather is longer than the link time it saves (measured: eight ranks on a 32-core host, four threads each: 19.0 ms
+        // per C3 step with the lists, 14.1 ms in place; 16 threads, one GPU: 34.8 against 52.0 ms).  VFK_HOST_FETCH=1 / 0 decides outright.
+        v = getenv("VFK_HOST_FETCH");
+        h->fetch = v && v[0] == '1' ? true : v && v[0] == '0' ? false : h->fetch_threads >= 6;
     }
     {
         // The path gathers single 32-byte sectors (one quality byte, one sequence byte per (read, column) pair):
