@@ -492,14 +492,16 @@ def main():
         c_out = [device.pinned_empty(b["units"].n_units, device.COUNTS_DTYPE) for b in subs]
         s_out = [device.pinned_empty(b["units"].n_units, device.STATS_DTYPE) for b in subs]
 
+        n_slots = dev.slots
+
         def e2e_step():
-            # two batches in flight: the library double-buffers, the copies of one batch overlap the kernels of the previous
+            # a few batches in flight (the library's staging slots): the copies of one batch overlap the host gather and the kernels of others
             tickets = []
             for k, b in enumerate(subs):
-                if k >= 2:
-                    dev.wait(tickets[k - 2])
+                if k >= n_slots:
+                    dev.wait(tickets[k - n_slots])
                 tickets.append(dev.annotate_host_async(b["host"], b["units"], b["stop"], params, b["eaf"], FPR, ERROR_RATE, c_out[k], s_out[k]))
-            for t in tickets[-2:]:
+            for t in tickets[-n_slots:]:
                 dev.wait(t)
         for _ in range(2):
             e2e_step()
@@ -539,11 +541,11 @@ def main():
         transfer = ("page-locked canonical arrays: starts / CIGARs / read lengths copied; the quality and sequence byte of every (column, read) pair "
                     "named by the device on a fetch list (%.1f M pairs per step, 16 B each written to the host), gathered by %d host threads between "
                     "two kernels of the call and copied back (bulk copies: %.0f MB per step, counted by the library); flags / MAPQ / mate fields / name "
-                    "ids read in place over PCIe for the reads that overlap a column; two batches in flight"
-                    % (pairs / 1e6, ts1["fetch_threads"], staged / 1e6)) if zero_copy > 0.5 and pairs > 0 else \
+                    "ids read in place over PCIe for the reads that overlap a column; %d batches in flight"
+                    % (pairs / 1e6, ts1["fetch_threads"], staged / 1e6, n_slots)) if zero_copy > 0.5 and pairs > 0 else \
                    ("page-locked canonical arrays: starts / CIGARs / read lengths copied (%.0f MB per step, counted by the library), every other "
-                    "array read in place over PCIe for the reads that overlap a column; two batches in flight" % (staged / 1e6)) if zero_copy > 0.5 else \
-                   "every array staged by async copies (%.0f MB per step); two batches in flight" % (staged / 1e6)
+                    "array read in place over PCIe for the reads that overlap a column; %d batches in flight" % (staged / 1e6, n_slots)) if zero_copy > 0.5 else \
+                   "every array staged by async copies (%.0f MB per step); %d batches in flight" % (staged / 1e6, n_slots)
         e2e = dict(dt=dt_e2e, h2d=h2d, d2h=d2h, transfer=transfer, staged=staged, h2d_how=h2d_how, rx_gbs=None if rx_rate is None else rx_rate / 1e9,
                    pairs=pairs, gather_ms=gather_ms, threads=ts1["fetch_threads"])
 

@@ -171,14 +171,17 @@ int vfk_annotate_host(vfk_handle *h, const vfk_read_batch *reads, const vfk_vari
                       const vfk_params *params, const double *eaf, double fpr, double error_rate,
                       vfk_counts *counts_out, vfk_stats *stats_out);
 
-/* Double-buffered variant: returns once the batch is enqueued on one of the handle's two staging
- * slots; *ticket (0 or 1) names the slot.  Submitting a third batch waits for the slot it reuses.
+/* Pipelined variant: returns once the batch is enqueued on one of the handle's VFK_SLOTS staging slots (each with its own
+ * stream and staging memory: the copies of one batch, the host gather of another and the kernels of a third overlap);
+ * *ticket (0 .. VFK_SLOTS-1) names the slot.  Submitting one batch more waits for the slot it reuses.
  * The host buffers (inputs and outputs) must stay valid until vfk_wait(h, ticket) returns; vfk_wait
  * returns VFK_EINVAL when the batch turned out to be malformed (VFK_ST_BADBATCH).                    */
 int vfk_annotate_host_async(vfk_handle *h, const vfk_read_batch *reads, const vfk_variant_batch *units,
                             const vfk_params *params, const double *eaf, double fpr, double error_rate,
                             vfk_counts *counts_out, vfk_stats *stats_out, int *ticket);
 int vfk_wait(vfk_handle *h, int ticket);
+#define VFK_SLOTS 2
+int vfk_slot_count(void); /* VFK_SLOTS of the library at hand */
 /* transfer accounting of the host entry point since vfk_create: out[0] bytes copied host -> device by
  * bulk copies, out[1] batches whose arrays were read in place (zero copy), out[2] batches staged in full,
  * out[3] bytes copied device -> host                                                               */

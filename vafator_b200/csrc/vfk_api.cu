@@ -267,7 +267,7 @@ struct vfk_handle {
     int sm_count = 0;
     Work work;  // the device-pointer API (vfk_pileup, vfk_pileup_values)
     int64_t launches = 0;
-    Slot slot[2];
+    Slot slot[VFK_SLOTS];
     int next_slot = 0;
     int64_t staged_bytes = 0, d2h_bytes = 0, zero_copy_batches = 0, staged_batches = 0;
     bool timing = false;     // vfk_set_timing
@@ -308,6 +308,7 @@ static int ensure_carter(vfk_handle *h, double fpr, double error_rate, cudaStrea
 }
 
 extern "C" int vfk_version(void) { return VFK_VERSION; }
+extern "C" int vfk_slot_count(void) { return VFK_SLOTS; }
 extern "C" const char *vfk_last_error(void) { return g_err; }
 
 static bool env_on(const char *name) {
@@ -577,7 +578,7 @@ static const void *pinned_alias(const void *host) {
 }
 
 extern "C" int vfk_wait(vfk_handle *h, int ticket) {
-    if (!h || ticket < 0 || ticket > 1) return fail(VFK_EINVAL, "vfk_wait: bad handle or ticket");
+    if (!h || ticket < 0 || ticket >= VFK_SLOTS) return fail(VFK_EINVAL, "vfk_wait: bad handle or ticket");
     Slot &s = h->slot[ticket];
     if (!s.busy) return VFK_OK;
     CU(cudaSetDevice(h->device));
@@ -809,7 +810,7 @@ extern "C" int vfk_annotate_host_async(vfk_handle *h, const vfk_read_batch *read
     h->d2h_bytes += (int64_t)nu * (int64_t)(sizeof(vfk_counts) + sizeof(vfk_stats)) + 4;
     CU(cudaEventRecord(S.done, st));
     S.busy = true;
-    h->next_slot ^= 1;
+    h->next_slot = (h->next_slot + 1) % VFK_SLOTS;
     return VFK_OK;
 failed:
     // copies and kernels already enqueued may still read the caller's buffers: they must have finished before the

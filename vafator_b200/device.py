@@ -394,7 +394,7 @@ class Device:
 
     def annotate_host_async(self, packed: HostReads, units: VariantUnits, stop, params: ParamsC, eaf: np.ndarray,
                             fpr: float, error_rate: float, counts_out: np.ndarray, stats_out: np.ndarray):
-        """Enqueue one batch on one of the two staging slots; returns a ticket for `wait`.  All host
+        """Enqueue one batch on one of the staging slots (`slots` of them); returns a ticket for `wait`.  All host
         arrays (inputs and outputs) must stay alive and untouched until `wait(ticket)` returns."""
         eaf = np.ascontiguousarray(eaf, np.float64)
         stop = None if stop is None else np.ascontiguousarray(stop, np.int32)
@@ -407,6 +407,11 @@ class Device:
                                                 C.byref(ticket)))
         self.__dict__.setdefault("_inflight", {})[ticket.value] = (packed, units, stop, eaf, counts_out, stats_out)
         return ticket.value
+
+    @property
+    def slots(self) -> int:
+        """Batches the host entry point keeps in flight (vfk_slot_count)."""
+        return int(self.lib.vfk_slot_count())
 
     def wait(self, ticket: int):
         _check(self.lib.vfk_wait(self.h, C.c_int(ticket)))

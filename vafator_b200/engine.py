@@ -550,7 +550,7 @@ class Engine:
         per_sample = OrderedDict()
         units_of_header = {}
         # every (sample, BAM) is one fused device call; they are submitted ahead of being collected so that the copies of one
-        # batch overlap the kernels of the previous one (two staging slots per device)
+        # batch overlap the host gather and the kernels of the previous ones (the device's staging slots)
         tasks = []
         for sample, batches in bams.items():
             for batch in batches:
@@ -560,9 +560,10 @@ class Engine:
                     units_of_header[contigs_key] = build_units(recs_in, batch.contigs)
                 tasks.append((sample, batch, units_of_header[contigs_key]))
         jobs, done = [], {}
+        n_slots = getattr(getattr(self, "dev", None), "slots", 2)  # batches the host entry point keeps in flight
         for t, (sample, batch, units) in enumerate(tasks):
-            if t >= 2:
-                done[t - 2] = self.finish(jobs[t - 2])
+            if t >= n_slots:
+                done[t - n_slots] = self.finish(jobs[t - n_slots])
             stop_u = stop_rec[units.rec] if units.n_units else np.zeros(0, np.int32)
             eaf_u = np.asarray(eaf[sample], np.float64)[units.rec] if units.n_units else np.zeros(0)
             jobs.append(self.submit(batch, units, stop_u, eaf_u))
