@@ -163,10 +163,12 @@ int vfk_epilogue(vfk_handle *h, int64_t n_units, const vfk_counts *counts, const
 
 /* Same path with HOST buffers, results in host memory before it returns.
  * Page-locked read arrays (cudaHostAlloc / cudaHostRegister, as vafator_b200.bamio and .synth allocate them):
- * only what the position index is built from -- pos, n_cigar, cigar_off, l_qseq, the CIGAR pool: ~25 bytes per
- * read -- is copied to the device; every other array (flags, qualities, bases, mate fields, name ids) is read
- * IN PLACE by the kernels over PCIe, and only for the reads that overlap a variant column.
- * Pageable arrays: everything is staged by asynchronous copies first.  Results are identical.          */
+ * what the position index is built from -- pos, n_cigar, cigar_off (unless NULL), l_qseq, the CIGAR pool: 17 to 25 bytes
+ * per read -- is copied to the device; the one quality byte and the one sequence byte a column needs of a read reach it
+ * through a fetch list (vfk_fetch_stats below); flags, MAPQ, mate fields and name ids are read IN PLACE by the kernels
+ * over PCIe, and only for the reads that overlap a variant column.  A deep or dense variant set (sampled on the host), or
+ * pageable arrays: everything is staged by asynchronous copies first.  Unit arrays and result buffers may be pageable
+ * either way (page-locked bounce buffers inside).  Results are identical.                                            */
 int vfk_annotate_host(vfk_handle *h, const vfk_read_batch *reads, const vfk_variant_batch *units,
                       const vfk_params *params, const double *eaf, double fpr, double error_rate,
                       vfk_counts *counts_out, vfk_stats *stats_out);
@@ -189,9 +191,10 @@ int vfk_transfer_stats(vfk_handle *h, int64_t out[4]);
 /* fetch lists of the host entry point since vfk_create (batches read in place: the one quality byte and the one sequence
  * byte a column needs of each read are named by the device, gathered by host threads between two kernels of the call and
  * copied in bulk, instead of being read over the bus one request each): out[0] (unit, read) pairs gathered, out[1] batches
- * that carried a list, out[2] nanoseconds the host spent gathering, out[3] host threads of a gather.  Environment, read by vfk_create: VFK_HOST_THREADS=n sets the host threads
- * of the gather (default: the OpenMP maximum, at most 16); the lists are used when there are at least six of them (several
- * GPUs sharing few host cores: reading in place is faster), VFK_HOST_FETCH=1 / 0 decides outright.                                            */
+ * that carried a list, out[2] nanoseconds the host spent gathering, out[3] host threads of a gather.
+ * Environment, read by vfk_create: VFK_HOST_THREADS=n sets the host threads of the gather (default: the OpenMP maximum, at
+ * most 16); the lists are used when there are at least six of them (several GPUs sharing few host cores: reading in place
+ * is faster), VFK_HOST_FETCH=1 / 0 decides outright.                                                                  */
 int vfk_fetch_stats(vfk_handle *h, int64_t out[4]);
 /* The host's half of a fetch list on its own (no device involved; what the stream callback of vfk_annotate_host_async runs):
  * req holds two 64-bit words per pair as request_kernel writes them -- word 0 = ~0: nothing wanted (out = 0); with
