@@ -103,6 +103,33 @@ int64_t vfkio_synth_sites(const vfkio_synth_cfg *cfg, int64_t cap, int32_t *tid,
 /* reference bases (ASCII) of [start, start+len) */
 int vfkio_synth_ref(const vfkio_synth_cfg *cfg, int32_t tid, int32_t start, int32_t len, char *out);
 
+/* ---- INFO text of one single-BAM sample (vfkio_format.cpp) --------------------------------------------------
+ * The strings vafator/annotator.py:304-420 builds per record ("{sample}_af=..;{sample}_ac=..;...;{sample}_pos=..", then the
+ * rank-sum pairs that exist), from the arrays vafator_b200/engine.py holds: per record i (rows first[i] .. first[i+1], one per
+ * ALT): kind (0 SNV, 1 INS, 2 DEL, -1 none), has (a pileup column exists), dp, n, ac_ref, med2_ref[i][mq,bq,pos] (twice the
+ * median), eaf; per row: alt_idx, present (ALT text is upper case), ac, med2_alt, pu / pw / z[3] / p[3] (already rounded), k.
+ * Floats are printed as Python's repr(float) prints them, af = round(ac / dp, 5) as Python rounds.  *text_out (malloc'ed:
+ * vfkio_free) holds the records back to back, record i = [offsets_out[i], offsets_out[i+1]) (n_rec + 1 entries). */
+typedef struct {
+    const char *sample;
+    int64_t n_rec;
+    const int64_t *first;
+    const int64_t *kind_rec;
+    const uint8_t *has_rec;
+    const int64_t *dp, *n, *ac_ref, *med2_ref;
+    const double *eaf;
+    const int64_t *alt_idx;
+    const uint8_t *present_row;
+    const int64_t *ac, *med2_alt;
+    const double *pu, *pw;
+    const int64_t *k;
+    const double *z, *p;
+} vfkio_format_in;
+int vfkio_format_info(const vfkio_format_in *in, char **text_out, int64_t *offsets_out);
+void vfkio_free(void *p);
+/* repr(float) as CPython prints it, into out32 (>= 32 bytes, not NUL terminated); returns the length */
+int vfkio_py_repr(double x, char *out32);
+
 #ifdef __cplusplus
 }
 #endif

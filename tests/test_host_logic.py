@@ -313,3 +313,61 @@ def test_collect_metrics_for_chrom_call_site_on_cpu(tmp_path, monkeypatch, index
                 assert (math.isnan(m.mqs[allele]) and want is None) or m.mqs[allele] == want
             n_keys += 1
     assert n_keys > 150
+
+
+def test_native_float_text_is_pythons():
+    """vfkio_py_repr (the float printing of the native INFO formatter) against repr(float): random doubles of every magnitude,
+    values rounded to 3 / 5 decimals as the statistics are, halves, integers, the switch-overs to exponent notation, specials."""
+    import ctypes as C
+    lib = device.libio()
+    lib.vfkio_py_repr.argtypes = [C.c_double, C.c_char_p]
+    rng = np.random.default_rng(3)
+    xs = [0.0, -0.0, 1.0, -1.0, 0.5, 1e-4, 9.999e-5, 1e-5, 1.5e-5, 1e16, 9999999999999998.0, 1e15, 123456789012345678.0, 5e-324, 1.7976931348623157e308,
+          float("nan"), float("inf"), float("-inf"), 0.1, 0.30000000000000004, 2.0 / 3.0, 100.0, 1e22, 1e23]
+    xs += (rng.random(2000) * 10.0 ** rng.integers(-12, 20, 2000) * rng.choice([-1, 1], 2000)).tolist()
+    xs += np.round(rng.random(2000), 5).tolist() + np.round(rng.normal(0, 8, 2000), 3).tolist() + (rng.integers(0, 600, 500) / 2.0).tolist()
+    xs += np.frombuffer(rng.bytes(8 * 2000), np.float64).tolist()
+    buf = C.create_string_buffer(40)
+    for x in xs:
+        n = lib.vfkio_py_repr(C.c_double(x), buf)
+        assert buf.raw[:n].decode() == repr(float(x)), (x, buf.raw[:n])
+
+
+def test_native_info_text_equals_python_formatter():
+    """vfkio_format_info (libvfkio: what Annotator.run prints with) against format_single_bam with the text templates, string for
+    string, on random per-record / per-row arrays: SNVs, indels, records without a unit or a column, multiallelic and ALT-less
+    records, lower-case ALTs, empty lists, NaN statistics, depths of zero, allele-frequency rounding ties."""
+    rng = np.random.default_rng(5)
+    for trial in range(6):
+        n_rec = [1, 7, 300, 5000, 5000, 40000][trial]
+        n_alt = rng.choice([0, 1, 1, 1, 1, 2, 3], n_rec)
+        first = np.concatenate([[0], np.cumsum(n_alt)]).astype(np.int64)
+        n_row = int(first[-1])
+        rec_of = np.repeat(np.arange(n_rec), n_alt)
+        kind = rng.choice([-1, 0, 0, 0, 1, 2], n_rec).astype(np.int64)
+        has = rng.random(n_rec) < 0.9
+        dp = np.where(rng.random(n_rec) < 0.05, 0, rng.integers(1, 3000, n_rec)).astype(np.int64)
+        n_amb = rng.integers(0, 3, n_rec).astype(np.int64)
+        ac_ref = np.where(rng.random(n_rec) < 0.2, 0, rng.integers(1, 200, n_rec)).astype(np.int64)
+        med2_ref = rng.integers(0, 600, (n_rec, 3)).astype(np.int64)
+        eaf = np.where(rng.random(n_rec) < 0.5, 0.5, rng.random(n_rec))
+        alt_idx = (np.arange(n_row) - first[rec_of]).astype(np.int64)
+        present = rng.random(n_row) < 0.9
+        ac = np.where(rng.random(n_row) < 0.3, 0, rng.integers(1, 3000, n_row)).astype(np.int64)
+        if trial == 4:  # ties of round(ac / dp, 5): k / 200000, k odd
+            dp[:] = 200000
+            ac[:] = rng.integers(0, 100000, n_row) * 2 + 1
+        med2_alt = rng.integers(0, 600, (n_row, 3)).astype(np.int64)
+        pu, pw = np.round(rng.random(n_row), 5), np.round(rng.random(n_row) ** 8, 5)
+        k = rng.integers(1, 60, n_row).astype(np.int64)
+        z = np.round(rng.normal(0, 6, (n_row, 3)), 3)
+        p = np.round(rng.random((n_row, 3)) ** 6, 5)
+        z[rng.random((n_row, 3)) < 0.05] = np.nan
+        p[np.isnan(z)] = np.nan
+        args = (first, kind, alt_idx, present, has, dp, n_amb, ac, ac_ref, med2_ref, med2_alt, pu, pw, k, z, p, eaf)
+        for sample in ("tumor", "s%1"):
+            want, _ = engine.format_single_bam(*args, templates=engine.text_templates(sample))
+            got = engine.format_single_bam_native(sample, *args)
+            assert len(got) == len(want) == n_rec
+            for i, (g, w) in enumerate(zip(got, want)):
+                assert g == w, (trial, i, g, w)

@@ -280,6 +280,53 @@ def format_single_bam(first, kind_rec, alt_idx, present_row, has_rec, dp, n_amb,
     return values, masks
 
 
+import ctypes as _C
+
+
+class _FormatIn(_C.Structure):  # include/vfk_io.h vfkio_format_in
+    _fields_ = [("sample", _C.c_char_p), ("n_rec", _C.c_int64)] + [(_k, _C.c_void_p) for _k in (
+        "first", "kind_rec", "has_rec", "dp", "n", "ac_ref", "med2_ref", "eaf", "alt_idx", "present_row", "ac", "med2_alt", "pu", "pw", "k", "z", "p")]
+
+
+def format_single_bam_native(sample, first, kind_rec, alt_idx, present_row, has_rec, dp, n_amb, ac, ac_ref, med2_ref, med2_alt,
+                             pu, pw, k, z, p, eaf) -> List[str]:
+    """The finished INFO text of one single-BAM sample per record -- format_single_bam(..., templates=text_templates(sample))[0],
+    printed by libvfkio (vfkio_format_info: all cores, Python's own float formatting restated in C++; tests compare the two
+    string for string)."""
+    import ctypes as C
+    lib = _dev.libio()
+    n_rec = len(first) - 1
+    if n_rec <= 0:
+        return []
+    keep = dict(first=np.ascontiguousarray(first, np.int64), kind_rec=np.ascontiguousarray(kind_rec, np.int64),
+                has_rec=np.ascontiguousarray(has_rec, np.uint8), dp=np.ascontiguousarray(dp, np.int64), n=np.ascontiguousarray(n_amb, np.int64),
+                ac_ref=np.ascontiguousarray(ac_ref, np.int64), med2_ref=np.ascontiguousarray(med2_ref, np.int64).reshape(-1),
+                eaf=np.ascontiguousarray(eaf, np.float64), alt_idx=np.ascontiguousarray(alt_idx, np.int64),
+                present_row=np.ascontiguousarray(present_row, np.uint8), ac=np.ascontiguousarray(ac, np.int64),
+                med2_alt=np.ascontiguousarray(med2_alt, np.int64).reshape(-1), pu=np.ascontiguousarray(pu, np.float64),
+                pw=np.ascontiguousarray(pw, np.float64), k=np.ascontiguousarray(k, np.int64), z=np.ascontiguousarray(z, np.float64).reshape(-1),
+                p=np.ascontiguousarray(p, np.float64).reshape(-1))
+    arg = _FormatIn()
+    arg.sample, arg.n_rec = sample.encode(), n_rec
+    for name, a in keep.items():
+        setattr(arg, name, a.ctypes.data)
+    text = C.c_void_p()
+    off = np.empty(n_rec + 1, np.int64)
+    lib.vfkio_format_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.vfkio_free.argtypes = [C.c_void_p]
+    _dev._io_check(lib.vfkio_format_info(C.byref(arg), C.byref(text), C.c_void_p(off.ctypes.data)))
+    try:
+        buf = C.string_at(text, int(off[-1])).decode("utf-8")
+    finally:
+        lib.vfkio_free(text)
+    if len(buf) != int(off[-1]):  # a sample name outside ASCII: byte offsets are not character offsets
+        raw = buf.encode("utf-8")
+        o = off.tolist()
+        return [raw[a:b].decode("utf-8") for a, b in zip(o[:-1], o[1:])]
+    o = off.tolist()
+    return [buf[a:b] for a, b in zip(o[:-1], o[1:])]
+
+
 def sample_keys(sample: str):
     """Per mask (which rank-sum pairs are present) the INFO keys of a single-BAM sample, in emission order."""
     base = tuple("{}_{}".format(sample, k) for k in _SINGLE_KEYS)
@@ -327,6 +374,8 @@ class SingleBamColumns:
     mask bit m set when the rank-sum pair of _RS_TAGS[m] is present.  `processes` > 1: the records are cut into
     chunks formatted by worker processes (worth it from some 10^5 records on)."""
 
+    native_text = True  # as_text: printed by libvfkio (vfkio_format_info); False: by format_single_bam here
+
     def __init__(self, sample: str, rows: RowTable, res: BamResult, st: RoundedStats, eaf: np.ndarray, processes: int = 1,
                  as_text: bool = False):
         """as_text: `values[i]` is the sample's finished INFO text ("key=value;...") instead of the value tuple."""
@@ -345,6 +394,10 @@ class SingleBamColumns:
                     text_templates(sample) if as_text else None)
 
         values = masks = None
+        if as_text and self.native_text:
+            self.values = format_single_bam_native(sample, *args(0, n_rec)[:17])
+            self.masks, self.keys = None, sample_keys(sample)
+            return
         if processes > 1 and n_rec >= 2 * processes:
             try:
                 cuts = [n_rec * c // (4 * processes) for c in range(4 * processes + 1)]
