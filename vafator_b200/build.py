@@ -1,7 +1,7 @@
 """In-tree build of the native libraries (no JIT cache: the .so files travel with the repo).
 
     libvfk.so    CUDA kernels + C ABI (include/vfk.h), nvcc, sm_100a only
-    libvfkio.so  host companion (include/vfk_io.h): packing, mate linking, BAM decode, synthesis
+    libvfkio.so  host companion (include/vfk_io.h): BGZF / BAM decode, INFO text, synthetic data
 """
 from __future__ import annotations
 
