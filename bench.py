@@ -614,6 +614,9 @@ def main():
             "e2e": None if e2e is None else {"value": units_step_all / e2e["dt"], "unit": "units/s",
                                             "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),
                                             "ms_per_step": 1e3 * e2e["dt"], "h2d_measured_by": e2e["h2d_how"],
+                                            # read preparation (spans, shapes, position index: prep + scan kernels) runs on the device inside
+                                            # every timed call; its device time per step, from the resident calls' phase events
+                                            "prep_ms": round(phase["prep"] * len(batches), 4),
                                             "h2d_copied_bytes_per_step_rank0": int(e2e["staged"]), "pcie_rx_gbs_rank0": e2e["rx_gbs"],
                                             "fetch_pairs_per_step_rank0": int(e2e["pairs"]), "host_gather_ms_per_step_rank0": round(e2e["gather_ms"], 3),
                                             "host_gather_threads": e2e["threads"],
