@@ -127,10 +127,10 @@ class FileOracleEngine(OracleEngine):
         OracleEngine.__init__(self, min_mapq, min_baseq, include_ambiguous, fpr, error_rate)
         self.released = 0
 
-    def annotate(self, records, bams, eaf, as_text=False):
+    def annotate(self, records, bams, eaf, as_text=False, span=None):
         self._records = records
         FileOracleEngine.calls.append((records[0][0], len(records), [b.n_reads for bs in bams.values() for b in bs]))
-        return OracleEngine.annotate(self, records, bams, eaf, as_text=as_text)
+        return OracleEngine.annotate(self, records, bams, eaf, as_text=as_text, span=span)
 
     def release_reads(self, batches=None):
         self.released += 1
@@ -155,14 +155,18 @@ def _write_inputs(tmp_path, sc, indexed):
     return str(vcf), bams
 
 
+@pytest.mark.parametrize("chunk", [None, 3, 1], ids=["whole_groups", "chunks_of_3", "chunks_of_1"])
 @pytest.mark.parametrize("indexed", [False, True], ids=["whole_file", "bai_regions"])
 @pytest.mark.parametrize("name", ["pileup_random_13.json", "pileup_handmade.json", "pileup_testx_real.json"])
-def test_annotator_streams_chromosome_groups(tmp_path, monkeypatch, name, indexed):
+def test_annotator_streams_chromosome_groups(tmp_path, monkeypatch, name, indexed, chunk):
     """Annotator.run on files (VCF reader, BAM decoder, region fetch, chromosome-group streaming, INFO append, VCF
     writer) with the device stages doubled by the oracle: every INFO key=value of the unmodified reference, one
-    engine call per chromosome group, region batches released between groups."""
+    engine call per chromosome group, region batches released between groups.  A group annotated in chunks (each with
+    the reads its own windows fetch, inside the span and under the read bound of the whole group) prints the same."""
     from vafator_b200 import annotator as ann
     from vafator_b200.ploidies import PloidyManager
+    if chunk:
+        monkeypatch.setattr(ann, "GROUP_CHUNK", chunk)
     sc = H.load_scenario(os.path.join(H.GOLDEN, name))
     run = sc["runs"][3] if len(sc["runs"]) > 3 else sc["runs"][-1]
     prm = run["params"]
@@ -192,11 +196,15 @@ def test_annotator_streams_chromosome_groups(tmp_path, monkeypatch, name, indexe
             assert info[:2] == ["OLD=1", "DP=7"]
             info = info[2:]
         assert info == ["%s=%s" % (key, val) for key, val in want], (k, sc["variants"][k])
-    # one engine call per run of consecutive records of one chromosome
+    # one engine call per run of consecutive records of one chromosome (per chunk of it)
     chroms = [v["chrom"] for v in sc["variants"]]
     groups = [c for i, c in enumerate(chroms) if i == 0 or chroms[i - 1] != c]
-    assert [c[0] for c in FileOracleEngine.calls] == groups
     assert sum(c[1] for c in FileOracleEngine.calls) == len(chroms)
+    if chunk:
+        sizes = [len(list(g)) for _, g in __import__("itertools").groupby(chroms)]
+        assert len(FileOracleEngine.calls) == sum(-(-n // chunk) for n in sizes) and max(c[1] for c in FileOracleEngine.calls) <= chunk
+        return
+    assert [c[0] for c in FileOracleEngine.calls] == groups
     assert a.engine.released == (len(groups) + 1 if indexed else 1)
     assert not a.engine.__dict__.get("_hreads") or not indexed  # the wrappers of a group's batches are gone with the group
     if indexed and len(groups) > 1:  # a group's batches hold that chromosome's region only

@@ -20,6 +20,9 @@ from .power import DEFAULT_ERROR_RATE, DEFAULT_FPR, PowerCalculator
 from .vcf import VcfReader, VcfWriter
 
 
+GROUP_CHUNK = 20000  # records of a chromosome group per engine call: bounds the reads held at once and lets decoding overlap annotation
+
+
 class Annotator(object):
 
     def __init__(self, input_vcf: str, output_vcf: str, input_bams: dict, purities: dict = None,
@@ -77,23 +80,27 @@ class Annotator(object):
         """Annotate every record of the input VCF and write the output VCF.
 
         The VCF is streamed one chromosome group at a time -- consecutive records of one CHROM, the unit the
-        reference piles up (stream_variants_by_chrom, vafator/pileups.py:83-103) -- so the host never holds more
-        than the reads of two chromosome groups: with an indexed BAM only the reads the group's columns depend on are decoded
-        (windows around the variants inside [first.POS-1, last.POS), the span the reference fetches; fetch.py) and
-        the batch is dropped, on the host and on the device, when the group is written; the next group is decoded in
-        the background meanwhile.  A BAM without an index is decoded once and stays resident."""
+        reference piles up (stream_variants_by_chrom, vafator/pileups.py:83-103) -- and a group in chunks of GROUP_CHUNK
+        records, so the host never holds more than the reads of two chunks: with an indexed BAM only the reads the chunk's
+        columns depend on are decoded (windows around the variants inside [first.POS-1, last.POS), the span the reference
+        fetches for the group; fetch.py) and the batch is dropped, on the host and on the device, when the chunk is
+        written; the next chunk is decoded in the background meanwhile (a single-chromosome VCF overlaps decoding and
+        annotation too).  A BAM without an index is decoded once and stays resident."""
         import time
         from concurrent.futures import ThreadPoolExecutor
         t_run = time.perf_counter()
-        with ThreadPoolExecutor(1) as pool:  # decodes group k+1 (native code, GIL released) while group k is annotated
+        with ThreadPoolExecutor(1) as pool:  # decodes chunk k+1 (native code, GIL released) while chunk k is annotated
             pending = None
             for group in self._chromosome_groups():
-                fetched = pool.submit(self._fetch_group, group)
-                if pending is not None:
-                    self._annotate_group(pending[0], pending[1].result())
-                pending = (group, fetched)
+                span = (group[0].POS, group[-1].POS)  # the span the reference piles up for the whole group
+                for at in range(0, len(group), GROUP_CHUNK):
+                    chunk = group[at:at + GROUP_CHUNK]
+                    fetched = pool.submit(self._fetch_group, chunk, span)
+                    if pending is not None:
+                        self._annotate_group(pending[0], pending[1].result(), pending[2])
+                    pending = (chunk, fetched, span)
             if pending is not None:
-                self._annotate_group(pending[0], pending[1].result())
+                self._annotate_group(pending[0], pending[1].result(), pending[2])
         self.vcf_writer.close()
         self.vcf.close()
         self.engine.release_reads()
@@ -114,29 +121,29 @@ class Annotator(object):
         if group:
             yield group
 
-    def _fetch_group(self, variants: list) -> "OrderedDict":
-        """The read batches of one chromosome group: windows around the variants inside the span the reference
-        fetches, [first.POS-1, last.POS) (vafator/pileups.py:137-138); a dense group gets the whole span
-        (vafator_b200/fetch.py)."""
+    def _fetch_group(self, variants: list, span) -> "OrderedDict":
+        """The read batches of one chunk of a chromosome group: windows around its variants inside the span the
+        reference fetches for the group, [first.POS-1, last.POS) (vafator/pileups.py:137-138); a dense chunk gets the
+        stretch from its first to its last window (vafator_b200/fetch.py)."""
         import time
         t0 = time.perf_counter()
         chrom = variants[0].CHROM
         positions = [v.POS for v in variants]
-        bams = OrderedDict((s, [fetch_group(r, chrom, positions[0], positions[-1], positions, self.engine.params) for r in readers])
+        bams = OrderedDict((s, [fetch_group(r, chrom, span[0], span[1], positions, self.engine.params) for r in readers])
                            for s, readers in self.bam_readers.items())
         self.timings["fetch"] += time.perf_counter() - t0
         self.timings["reads"] += sum(b.n_reads for batches in bams.values() for b in batches)
         return bams
 
-    def _annotate_group(self, variants: list, bams: "OrderedDict") -> None:
-        """One chromosome group: annotate, write, release its reads."""
+    def _annotate_group(self, variants: list, bams: "OrderedDict", span) -> None:
+        """One chunk of a chromosome group: annotate, write, release its reads."""
         records = [(v.CHROM, v.POS, v.REF, v.ALT) for v in variants]
         chrom = records[0][0]
         positions = [r[1] for r in records]
         import time
         t0 = time.perf_counter()
         eaf = {s: self.power.expected_vafs(s, [chrom] * len(records), positions) for s in bams}
-        infos = self.engine.annotate(records, bams, eaf, as_text=True)
+        infos = self.engine.annotate(records, bams, eaf, as_text=True, span=span)
         t1 = time.perf_counter()
         batch = []
         for v, info in zip(variants, infos):

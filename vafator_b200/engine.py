@@ -47,6 +47,14 @@ def chrom_groups(records: Sequence[Record]):
     return in_range, stop
 
 
+def span_range(records: Sequence[Record], span: Tuple[int, int]):
+    """The same for records that are PART of a chromosome group whose first / last record lie at span = (first.POS, last.POS):
+    what `chrom_groups` would say about them inside the whole group (a group too large for one call is annotated in chunks)."""
+    first, last = int(span[0]), int(span[1])
+    pos = np.asarray([r[1] for r in records], np.int64)
+    return (pos >= first) & (pos <= last), np.full(len(records), last, np.int32)
+
+
 class RowTable:
     """One row per (record, ALT allele) -- the granularity of the A-numbered INFO fields."""
 
@@ -594,11 +602,13 @@ class Engine:
 
     # ---- the annotation -----------------------------------------------------------------------
     def annotate(self, records: Sequence[Record], bams: "OrderedDict[str, List[ReadBatch]]",
-                 eaf: Dict[str, np.ndarray], as_text: bool = False) -> List["OrderedDict"]:
+                 eaf: Dict[str, np.ndarray], as_text: bool = False, span: Optional[Tuple[int, int]] = None) -> List["OrderedDict"]:
         """INFO fields (ordered) for every record.  `eaf[sample][i]` = expected VAF of record i.
-        as_text: the same fields as one "key=value;key=value" string per record (what a VCF writer appends)."""
+        as_text: the same fields as one "key=value;key=value" string per record (what a VCF writer appends).
+        span: the records are a chunk of ONE chromosome group whose first / last record lie at (first.POS, last.POS) -- the span
+        the reference piles up (vafator/pileups.py:137-138) and the bound on the reads it ever fetches."""
         rows = RowTable(records)
-        in_range, stop_rec = chrom_groups(records)
+        in_range, stop_rec = chrom_groups(records) if span is None else span_range(records, span)
         fmt = SampleFormatter(rows)
         per_sample = OrderedDict()
         units_of_header = {}

@@ -13,8 +13,8 @@ is the whole genome's worth of reads for a few thousand columns.  A column's met
 
 So the group is fetched as windows [col - pad, col + 1 + pad) merged when they are close, clipped to the span
 the reference fetches, and `missing_reads` then proves, column by column, that the first pushed read after the
-column is among the fetched ones -- or names the window to extend.  Dense variant sets merge into the
-reference's own span.  Not reproduced: three or more alignments sharing one read name (supplementary
+column is among the fetched ones -- or names the window to extend.  Dense variant sets merge into one stretch
+from their first to their last window (for a whole group: nearly the reference's own span).  Not reproduced: three or more alignments sharing one read name (supplementary
 alignments) whose extra record lies outside every window while both mates of the pair lie inside -- the same
 class of effect DESIGN.md section 7 lists for the fetch-region edge.
 """
@@ -29,7 +29,7 @@ from .sharding import _ref_span
 
 PAD = 1000         # bases fetched on either side of a column
 MERGE_GAP = 8192   # windows closer than this are one region: decoding the gap is cheaper than another seek
-DENSE = 0.5        # windows covering more than this share of the span: fetch the span, as the reference does
+DENSE = 0.5        # windows covering more than this share of the stretch they span: fetch the stretch as one window
 MAX_ROUNDS = 4
 
 
@@ -54,17 +54,17 @@ def missing_reads(batch: ReadBatch, passes: np.ndarray, cols: Sequence[int], win
     of the column's window, or the window ends where the reference stops reading.  Otherwise it only matters if
     it could be the mate of a read overlapping the column, i.e. if such a read names a mate position at or beyond
     the window end: returns [(window index, end needed)] for those."""
-    sel = batch.tid == tid
-    pos = batch.pos[sel].astype(np.int64)
+    # (a region fetch of one contig holds reads of that contig only: plain views then, no masked copies)
+    all_here = bool(len(batch.tid)) and int(batch.tid[0]) == tid and int(batch.tid[-1]) == tid
+    sel = slice(None) if all_here else batch.tid == tid
+    pos = batch.pos[sel]
     n = len(pos)
     if n == 0 or not len(cols):
         return []
     ok = passes[sel]
-    end = pos + _ref_span(batch)[sel]
-    pmax = np.maximum.accumulate(end)
     # position of the first passing read at or after index j (sentinel: beyond everything)
     big = np.int64(1) << 40
-    nxt_pos = np.where(ok, pos, big)
+    nxt_pos = np.where(ok, pos.astype(np.int64), big)
     nxt_pos = np.minimum.accumulate(nxt_pos[::-1])[::-1]
     nxt_pos = np.concatenate([nxt_pos, [big]])
     cols = np.asarray(sorted(set(int(c) for c in cols)), np.int64)
@@ -73,11 +73,17 @@ def missing_reads(batch: ReadBatch, passes: np.ndarray, cols: Sequence[int], win
     w_of = np.searchsorted(w_lo, cols, side="right") - 1
     hi = np.searchsorted(pos, cols, side="right")
     known = (nxt_pos[hi] < w_hi[w_of]) | (w_hi[w_of] >= span_hi)
+    unknown = np.nonzero(~known)[0].tolist()
+    if not unknown:
+        return []
+    # the rest only for the few columns at a window's end that are left: reference spans, mate fields
+    end = pos.astype(np.int64) + _ref_span(batch)[sel]
+    pmax = np.maximum.accumulate(end)
     need = {}
     flag = batch.flag[sel]
     mtid = batch.mtid[sel]
     mpos = batch.mpos[sel].astype(np.int64)
-    for k in np.nonzero(~known)[0].tolist():
+    for k in unknown:
         c, w = int(cols[k]), int(w_of[k])
         lo = int(np.searchsorted(pmax, c, side="right"))
         j = slice(lo, int(hi[k]))
@@ -90,9 +96,9 @@ def missing_reads(batch: ReadBatch, passes: np.ndarray, cols: Sequence[int], win
 
 def fetch_group(bam, chrom: str, first_pos: int, last_pos: int, positions: Sequence[int], params,
                 pad: int = PAD, merge_gap: int = MERGE_GAP) -> ReadBatch:
-    """The read batch of one chromosome group (1-based POS values; first / last = the group's first and last
-    record, whose span the reference fetches: vafator/pileups.py:137-138).  Without an index the file's whole
-    batch is returned (bamio.BamFile caches it)."""
+    """The read batch for `positions` -- a chromosome group or a chunk of one -- (1-based POS values; first / last = the
+    GROUP's first and last record, whose span the reference fetches: vafator/pileups.py:137-138).  Without an index the
+    file's whole batch is returned (bamio.BamFile caches it)."""
     from . import device as _dev
     if not getattr(bam, "index_path", None):
         return bam.read_batch(None)
@@ -104,8 +110,10 @@ def fetch_group(bam, chrom: str, first_pos: int, last_pos: int, positions: Seque
         return bam.read_batch(span)
     tid = bam.contigs.index(chrom)
     for _ in range(MAX_ROUNDS):
-        if sum(b - a for a, b in windows) > DENSE * (span_hi - span_lo):
-            break
+        if len(windows) > 1 and sum(b - a for a, b in windows) > DENSE * (windows[-1][1] - windows[0][0]):
+            # dense: one stretch from the first to the last window (for a whole group nearly the reference's own span; for a chunk
+            # of a group just its share of it), checked and extended like any other window
+            windows = [[windows[0][0], windows[-1][1]]]
         batch = bam.read_batch([(chrom, a, b) for a, b in windows])
         ext = missing_reads(batch, _dev.read_passes(batch, params), cols, windows, span_hi, tid)
         if not ext:
