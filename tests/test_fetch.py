@@ -83,6 +83,40 @@ def test_windows_on_low_coverage_reads_with_long_skips(tmp_path, seed):
     assert extended > 0
 
 
+@pytest.mark.parametrize("seed", [7, 8])
+def test_chunks_of_a_group_fetch_what_their_columns_need(tmp_path, seed):
+    """A chromosome group annotated in chunks (annotator.GROUP_CHUNK): each chunk fetches the windows of its own columns inside
+    the GROUP's span and keeps the group's read bound.  Every unit of every chunk, from the chunk's batch, equals the unit computed
+    from the whole span -- on low-coverage reads with long skips, sparse chunks, dense chunks, chunks of one record."""
+    cfg = synth.wgs(n_contigs=1, contig_len=400_000, seed=synth.BASE_SEED + 60 + seed, pairs_per_tile=12, p_skip=0.25, p_del=0.15,
+                    p_ins=0.05, p_softclip=0.05, frag_mean=260.0, frag_sd=80.0, snv_period=300, indel_period=900)
+    batch = synth.reads(cfg)
+    p = tmp_path / "s.bam"
+    bamio.write_bam_batch(str(p), batch, [401_000])
+    bam = bamio.BamFile(str(p))
+    chrom = bam.contigs[0]
+    recs = [r for r in synth.variant_records(cfg) if r[0] == chrom]
+    rng = np.random.default_rng(seed)
+    group = [recs[k] for k in sorted(rng.choice(len(recs), size=min(len(recs), 400), replace=False).tolist())]
+    first, last = group[0][1], group[-1][1]
+    params = device.make_params(min_mapq=1, min_baseq=20)
+    full = bam.read_batch([(chrom, first - 1, last)])
+    want = _oracle(full, bam.contigs, group, last, 1, 20)
+    n_units = [len(r[3]) for r in group]
+    unit0 = np.concatenate([[0], np.cumsum(n_units)])
+    fewer = 0
+    for size, pad, gap in ((1, 0, 1), (7, 40, 100), (50, fetch.PAD, fetch.MERGE_GAP), (150, 0, 1)):
+        for at in range(0, len(group), size):
+            chunk = group[at:at + size]
+            part = fetch.fetch_group(bam, chrom, first, last, [r[1] for r in chunk], params, pad=pad, merge_gap=gap)
+            got = _oracle(part, bam.contigs, chunk, last, 1, 20)
+            u0, u1 = int(unit0[at]), int(unit0[min(at + size, len(group))])
+            for f in FIELDS:
+                assert np.array_equal(got[f], want[f][u0:u1]), (size, at, f)
+            fewer += part.n_reads < full.n_reads
+    assert fewer > 0
+
+
 def test_plan_windows():
     assert fetch.plan_windows([100, 105, 5000, 20000], 50, 19000, pad=10, merge_gap=20) == [[90, 116], [4990, 5011]]
     assert fetch.plan_windows([100, 130], 0, 1000, pad=10, merge_gap=20) == [[90, 141]]
