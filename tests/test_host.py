@@ -91,7 +91,7 @@ def test_cabi_library_exports_every_declared_symbol():
     """The shared libraries build (nvcc cross-compiles without a GPU), load, and export exactly what
     include/*.h declares.  No compute call is made here."""
     libvfk, libio = build.build_all()
-    for header, path in (("vfk.h", libvfk), ("vfk_io.h", libio)):
+    for header, path in (("vfk.h", libvfk), ("vfk_io.h", libio), ("vfk_synth.h", build.LIBVFKSYNTH)):
         text = open(os.path.join(ROOT, "include", header)).read()
         declared = set(re.findall(r"\b(vfk(?:io)?_[a-z_]+)\s*\(", text))
         lib = C.CDLL(path)

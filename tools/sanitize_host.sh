@@ -1,6 +1,6 @@
 #!/bin/bash
 # The CPU test suite against an AddressSanitizer + UndefinedBehaviorSanitizer build of libvfkio.so (BGZF / BAM decoder, inflate,
-# synthesis).  The release library is put back afterwards.   usage: tools/sanitize_host.sh
+# INFO text).  The release library is put back afterwards.   usage: tools/sanitize_host.sh
 set -u
 cd "$(dirname "$0")/.."
 lib=vafator_b200/libvfkio.so
@@ -8,7 +8,7 @@ keep=$(mktemp)
 cp "$lib" "$keep"
 trap 'cp "$keep" "$lib"; touch "$lib"; rm -f "$keep"' EXIT
 g++ -O1 -g -std=c++17 -fPIC -shared -fopenmp -fsanitize=address,undefined -fno-omit-frame-pointer -I include \
-    -o "$lib" vafator_b200/csrc/vfkio_*.cpp -lz -lpthread || exit 1
+    -o "$lib" $(ls vafator_b200/csrc/vfkio_*.cpp | grep -v vfkio_synth.cpp) -lz -lpthread || exit 1
 touch "$lib"
 log=$(mktemp)
 LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:halt_on_error=1 UBSAN_OPTIONS=print_stacktrace=1 \

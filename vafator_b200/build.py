@@ -1,7 +1,8 @@
 """In-tree build of the native libraries (no JIT cache: the .so files travel with the repo).
 
     libvfk.so    CUDA kernels + C ABI (include/vfk.h), nvcc, sm_100a only
-    libvfkio.so  host companion (include/vfk_io.h): BGZF / BAM decode, INFO text, synthetic data
+    libvfkio.so  host companion (include/vfk_io.h): BGZF / BAM decode, INFO text
+    libvfksynth.so  synthetic benchmark / test data (include/vfk_synth.h): not product code
 """
 from __future__ import annotations
 
@@ -17,6 +18,7 @@ CSRC = os.path.join(PKG, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 LIBVFK = os.path.join(PKG, "libvfk.so")
 LIBVFKIO = os.path.join(PKG, "libvfkio.so")
+LIBVFKSYNTH = os.path.join(PKG, "libvfksynth.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-shared", "-I", INCLUDE]
@@ -47,16 +49,29 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     return LIBVFK
 
 
+_SYNTH_SRCS = ("vfkio_synth.cpp", "vfkio_util.cpp")
+
+
 def build_host(force: bool = False) -> str:
-    srcs = sorted(glob.glob(os.path.join(CSRC, "vfkio_*.cpp")))
+    srcs = sorted(s for s in glob.glob(os.path.join(CSRC, "vfkio_*.cpp")) if os.path.basename(s) != "vfkio_synth.cpp")
     deps = srcs + glob.glob(os.path.join(INCLUDE, "*.h"))
     if force or _stale(LIBVFKIO, deps):
         subprocess.check_call(["g++"] + CXX_FLAGS + ["-o", LIBVFKIO] + srcs + ["-lz", "-lpthread"])
     return LIBVFKIO
 
 
+def build_synth(force: bool = False) -> str:
+    srcs = [os.path.join(CSRC, s) for s in _SYNTH_SRCS]
+    deps = srcs + glob.glob(os.path.join(INCLUDE, "*.h"))
+    if force or _stale(LIBVFKSYNTH, deps):
+        subprocess.check_call(["g++"] + CXX_FLAGS + ["-o", LIBVFKSYNTH] + srcs + ["-lpthread"])
+    return LIBVFKSYNTH
+
+
 def build_all(force: bool = False, verbose: bool = False):
-    return build_cuda(force, verbose), build_host(force)
+    libs = build_cuda(force, verbose), build_host(force)
+    build_synth(force)
+    return libs
 
 
 if __name__ == "__main__":

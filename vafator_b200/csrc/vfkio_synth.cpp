@@ -9,7 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <vector>
-#include "vfk_io.h"
+#include "vfk_synth.h"
 
 int vfkio_fail(int code, const char *msg);
 

@@ -85,6 +85,20 @@ def libio():
     return _libio
 
 
+_libsynth = None
+
+
+def libsynth():
+    """libvfksynth.so (synthetic benchmark / test data; not product code).  Built in-tree on first use."""
+    global _libsynth
+    if _libsynth is None:
+        path = _build.LIBVFKSYNTH if os.path.exists(_build.LIBVFKSYNTH) and not os.environ.get("VFK_REBUILD") else _build.build_synth()
+        lib = C.CDLL(path)
+        lib.vfkio_last_error.restype = C.c_char_p
+        _libsynth = lib
+    return _libsynth
+
+
 def libvfk():
     """libvfk.so (CUDA).  Raises if it cannot be loaded -- there is no fallback path."""
     global _libvfk

@@ -116,9 +116,14 @@ def amplicon(n_tiles=5_000, depth_pairs=900, seed=BASE_SEED + 5, **kw) -> SynthC
 
 
 def _lib():
-    lib = _dev.libio()
+    lib = _dev.libsynth()
     lib.vfkio_synth_sites.restype = C.c_int64
     return lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise ValueError("vfkio: %s" % _lib().vfkio_last_error().decode())
 
 
 def reads(cfg: SynthConfig, pinned: bool = False) -> ReadBatch:
@@ -129,7 +134,7 @@ def reads(cfg: SynthConfig, pinned: bool = False) -> ReadBatch:
     plan = _PlanC()
     tiles = cfg.n_tiles_generated
     tile_sizes = np.zeros(4 * tiles, np.int64)
-    _dev._io_check(lib.vfkio_synth_plan_reads(C.byref(c), C.byref(plan), C.c_void_p(tile_sizes.ctypes.data)))
+    _check(lib.vfkio_synth_plan_reads(C.byref(c), C.byref(plan), C.c_void_p(tile_sizes.ctypes.data)))
     n = plan.n_reads
     E = lambda k, dt: _dev._empty(k, dt, pinned)
     arr = dict(tid=np.empty(n, np.int32), pos=E(n, np.int32), flag=E(n, np.uint16),
@@ -142,7 +147,7 @@ def reads(cfg: SynthConfig, pinned: bool = False) -> ReadBatch:
     s.n, s.n_contigs = n, cfg.n_contigs
     for k, a in arr.items():
         setattr(s, k, a.ctypes.data)
-    _dev._io_check(lib.vfkio_synth_fill_reads(C.byref(c), C.byref(plan), C.c_void_p(tile_sizes.ctypes.data), C.byref(s)))
+    _check(lib.vfkio_synth_fill_reads(C.byref(c), C.byref(plan), C.c_void_p(tile_sizes.ctypes.data), C.byref(s)))
     arr["cigar"] = arr["cigar"][:plan.n_cigar]
     arr["seq"] = arr["seq"][:plan.n_seq_bytes]
     arr["qual"] = arr["qual"][:plan.n_qual_bytes]
@@ -174,7 +179,7 @@ def sites(cfg: SynthConfig):
         n = lib.vfkio_synth_sites(C.byref(c), C.c_int64(cap), C.c_void_p(tid.ctypes.data), C.c_void_p(pos1.ctypes.data),
                                   C.c_void_p(kind.ctypes.data), C.c_void_p(length.ctypes.data), C.c_void_p(bases.ctypes.data))
         if n < 0:
-            _dev._io_check(int(n))
+            _check(int(n))
         if n <= cap:
             return tid[:n], pos1[:n], kind[:n], length[:n], bases[:n * 24].reshape(n, 24)
         cap = int(n)
@@ -182,7 +187,7 @@ def sites(cfg: SynthConfig):
 
 def ref_bases(cfg: SynthConfig, tid: int, start: int, length: int) -> str:
     buf = C.create_string_buffer(length + 1)
-    _dev._io_check(_lib().vfkio_synth_ref(C.byref(cfg.c()), tid, start, length, buf))
+    _check(_lib().vfkio_synth_ref(C.byref(cfg.c()), tid, start, length, buf))
     return buf.raw[:length].decode()
 
 
